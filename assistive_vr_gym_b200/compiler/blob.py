@@ -1,0 +1,139 @@
+"""ModelBlob writer/reader: numpy mirrors of the structs in `include/avg_model.h`."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import xform as X
+from .mbody import JOINT_FREE, SHAPE_HULL
+from .scene import CompiledScene, _world_aabb
+
+AVG_MAGIC = 0x4D475641
+AVG_VERSION = 3
+ENV_STRIDE = 192
+
+BODY_DT = np.dtype([
+    ("parent", "<i4"), ("jtype", "<i4"), ("dof", "<i4"), ("qidx", "<i4"),
+    ("ta_pos", "<f4", 3), ("ta_quat", "<f4", 4), ("axis", "<f4", 3), ("tb_pos", "<f4", 3), ("tb_quat", "<f4", 4),
+    ("mass", "<f4"), ("inertia", "<f4", 3), ("gravity", "<f4", 3), ("anc_mask", "<u4"),
+    ("ref_body", "<i4"), ("ref_joint", "<i4"), ("pad", "<i4"),
+])
+DOF_DT = np.dtype([
+    ("body", "<i4"), ("flags", "<u4"), ("lower", "<f4"), ("upper", "<f4"), ("rep_lower", "<f4"), ("rep_upper", "<f4"),
+    ("kp", "<f4"), ("kd", "<f4"), ("max_force", "<f4"), ("action", "<i4"), ("human_slot", "<i4"), ("init_target", "<f4"),
+    ("pad", "<i4", 4),
+])
+SHAPE_DT = np.dtype([
+    ("type", "<i4"), ("body", "<i4"), ("ref_body", "<i4"), ("ref_link", "<i4"),
+    ("pos", "<f4", 3), ("quat", "<f4", 4), ("radius", "<f4"), ("half", "<f4", 3), ("margin", "<f4"),
+    ("vert_off", "<i4"), ("vert_cnt", "<i4"), ("plane_off", "<i4"), ("plane_cnt", "<i4"),
+    ("friction", "<f4"), ("thr", "<f4"), ("aabb_c", "<f4", 3), ("aabb_h", "<f4", 3), ("pad", "<i4", 4),
+])
+FRAME_DT = np.dtype([("body", "<i4"), ("pos", "<f4", 3), ("quat", "<f4", 4)])
+HEADER_DT = np.dtype([
+    ("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("task", "<i4"),
+    ("n_body", "<i4"), ("n_ebody", "<i4"), ("n_dof", "<i4"), ("n_jdof", "<i4"), ("n_free", "<i4"),
+    ("n_shape", "<i4"), ("n_mshape", "<i4"), ("n_vert", "<i4"), ("n_plane", "<i4"), ("n_pair", "<i4"), ("n_frame", "<i4"),
+    ("substeps", "<i4"), ("solver_iters", "<i4"),
+    ("n_action_robot", "<i4"), ("n_action_human", "<i4"), ("n_obs_robot", "<i4"), ("n_obs_human", "<i4"),
+    ("human_control", "<i4"),
+    ("dt", "<f4"), ("erp", "<f4"), ("lin_damp", "<f4"), ("ang_damp", "<f4"), ("residual_thr", "<f4"), ("max_vel", "<f4"),
+    ("action_scale", "<f4"), ("weld_max_force", "<f4"), ("weld_body_a", "<i4"), ("weld_body_b", "<i4"),
+    ("task_f", "<f4", 32),
+    ("off_body", "<u4"), ("off_dof", "<u4"), ("off_shape", "<u4"), ("off_vert", "<u4"), ("off_plane", "<u4"),
+    ("off_pair", "<u4"), ("off_frame", "<u4"), ("pad", "<u4", 8),
+])
+assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
+
+
+def _align(n: int, a: int = 16) -> int:
+    return (n + a - 1) // a * a
+
+
+def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
+    nb = len(scene.bodies)
+    bodies = np.zeros(nb, dtype=BODY_DT)
+    for i, b in enumerate(scene.bodies):
+        r = bodies[i]
+        r["parent"] = b.parent; r["jtype"] = b.jtype; r["dof"] = b.dof; r["qidx"] = b.qidx
+        r["ta_pos"] = b.ta_pos; r["ta_quat"] = b.ta_quat; r["axis"] = b.axis
+        r["tb_pos"] = b.tb_pos; r["tb_quat"] = b.tb_quat
+        r["mass"] = b.mass; r["inertia"] = b.inertia; r["gravity"] = b.gravity
+        mask = 1 << i
+        p = b.parent
+        while p >= 0:
+            mask |= 1 << p
+            p = scene.bodies[p].parent
+        r["anc_mask"] = mask
+        r["ref_body"] = scene.multibodies[b.art].ref_body; r["ref_joint"] = b.ref_joint
+    dofs = np.zeros(len(scene.dofs), dtype=DOF_DT)
+    for i, d in enumerate(scene.dofs):
+        for k in ("body", "flags", "lower", "upper", "rep_lower", "rep_upper", "kp", "kd", "max_force", "action",
+                  "human_slot", "init_target"):
+            dofs[i][k] = d[k]
+    verts = []
+    planes = []
+    shapes = np.zeros(len(scene.shapes), dtype=SHAPE_DT)
+    hull_index = {}
+    for i, s in enumerate(scene.shapes):
+        r = shapes[i]
+        d = s.desc
+        r["type"] = d.kind; r["body"] = s.body; r["ref_body"] = s.ref_body; r["ref_link"] = s.ref_link
+        r["pos"] = s.pos; r["quat"] = s.quat; r["radius"] = d.radius; r["half"] = d.half; r["margin"] = s.margin
+        if d.kind == SHAPE_HULL:
+            key = id(d.verts)
+            if key not in hull_index:
+                hull_index[key] = (sum(len(v) for v in verts), len(d.verts), sum(len(p) for p in planes), len(d.planes))
+                verts.append(np.asarray(d.verts, dtype=np.float32))
+                planes.append(np.asarray(d.planes, dtype=np.float32))
+            r["vert_off"], r["vert_cnt"], r["plane_off"], r["plane_cnt"] = hull_index[key]
+        r["friction"] = d.friction; r["thr"] = s.thr
+        if s.body >= 0:
+            lo, hi = d.local_aabb()
+            r["aabb_c"] = 0.5 * (lo + hi); r["aabb_h"] = 0.5 * (hi - lo)
+        else:
+            c, h = _world_aabb(d, s.pos, s.quat)
+            r["aabb_c"] = c; r["aabb_h"] = h
+    verts = np.concatenate(verts, axis=0).astype("<f4") if verts else np.zeros((0, 3), "<f4")
+    planes = np.concatenate(planes, axis=0).astype("<f4") if planes else np.zeros((0, 4), "<f4")
+    pairs = (scene.pairs[:, 0].astype("<u4") | (scene.pairs[:, 1].astype("<u4") << 16)).astype("<u4")
+    frames = np.zeros(len(scene.frames), dtype=FRAME_DT)
+    for i, (b, p, q) in enumerate(scene.frames):
+        frames[i]["body"] = b; frames[i]["pos"] = p; frames[i]["quat"] = q
+
+    hdr = np.zeros(1, dtype=HEADER_DT)
+    h = hdr[0]
+    h["magic"] = AVG_MAGIC; h["version"] = AVG_VERSION
+    vals = dict(scene.header)
+    if overrides:
+        vals.update(overrides)
+    for k, v in vals.items():
+        h[k] = v
+    h["n_shape"] = len(shapes); h["n_mshape"] = scene.n_mshape; h["n_vert"] = len(verts); h["n_plane"] = len(planes)
+    h["n_pair"] = len(pairs); h["n_frame"] = len(frames)
+    off = _align(HEADER_DT.itemsize)
+    sections = []
+    for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
+                      ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames)):
+        h[name] = off
+        sections.append((off, arr.tobytes()))
+        off = _align(off + arr.nbytes)
+    h["total_bytes"] = off
+    buf = bytearray(off)
+    buf[:HEADER_DT.itemsize] = hdr.tobytes()
+    for o, b in sections:
+        buf[o:o + len(b)] = b
+    return bytes(buf)
+
+
+def read_blob(blob: bytes) -> dict:
+    h = np.frombuffer(blob, dtype=HEADER_DT, count=1)[0]
+    assert h["magic"] == AVG_MAGIC and h["version"] == AVG_VERSION, "bad model blob"
+    out = {"header": h}
+    out["bodies"] = np.frombuffer(blob, dtype=BODY_DT, count=int(h["n_body"]), offset=int(h["off_body"]))
+    out["dofs"] = np.frombuffer(blob, dtype=DOF_DT, count=int(h["n_dof"]), offset=int(h["off_dof"]))
+    out["shapes"] = np.frombuffer(blob, dtype=SHAPE_DT, count=int(h["n_shape"]), offset=int(h["off_shape"]))
+    out["verts"] = np.frombuffer(blob, dtype="<f4", count=3 * int(h["n_vert"]), offset=int(h["off_vert"])).reshape(-1, 3)
+    out["planes"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_plane"]), offset=int(h["off_plane"])).reshape(-1, 4)
+    out["pairs"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_pair"]), offset=int(h["off_pair"]))
+    out["frames"] = np.frombuffer(blob, dtype=FRAME_DT, count=int(h["n_frame"]), offset=int(h["off_frame"]))
+    return out

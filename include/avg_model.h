@@ -1,0 +1,175 @@
+/* avg_model.h — binary layout of the compiled model ("ModelBlob") and of the per-environment state record.
+ *
+ * This is a DATA FORMAT definition shared by the model compiler (Python, assistive_vr_gym_b200/compiler/blob.py),
+ * the CUDA product (assistive_vr_gym_b200/csrc) and the CPU oracle (oracle/avg_oracle.c, test infrastructure only).
+ * It replaces what the reference keeps inside the PyBullet server after `loadURDF` / `createMultiBody` /
+ * `createConstraint` / `setCollisionFilterPair` (reference world_creation.py:27-93,274-365, human_creation.py:275-294).
+ *
+ * Everything is little-endian, 4-byte fields, sections 16-byte aligned.  Quaternions are xyzw (PyBullet).
+ */
+#ifndef AVG_MODEL_H
+#define AVG_MODEL_H
+#include <stdint.h>
+
+#define AVG_MAGIC   0x4D475641u  /* "AVGM" */
+#define AVG_VERSION 3u
+
+#define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
+#define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
+#define AVG_MAX_EBODY   8   /* env-static bodies (pose given per environment)             */
+#define AVG_MAX_CONTACT 16  /* contact points kept per sub-step                           */
+#define AVG_MAX_ROWS   64   /* constraint rows per sub-step (2 per lane)                  */
+#define AVG_MAX_HULL_VERTS 48
+
+enum { AVG_JOINT_REVOLUTE = 0, AVG_JOINT_PRISMATIC = 1, AVG_JOINT_FREE = 2 };
+enum { AVG_SHAPE_SPHERE = 0, AVG_SHAPE_CAPSULE = 1, AVG_SHAPE_BOX = 2, AVG_SHAPE_CYLINDER = 3,
+       AVG_SHAPE_HULL = 4, AVG_SHAPE_PLANE = 5 };
+enum { AVG_TASK_SCRATCH_ITCH = 0, AVG_TASK_BED_BATHING = 1, AVG_TASK_FEEDING = 2, AVG_TASK_DRINKING = 3 };
+/* contact-report body ids (what the reference compares getContactPoints bodies against) */
+enum { AVG_REF_ROBOT = 0, AVG_REF_HUMAN = 1, AVG_REF_TOOL = 2, AVG_REF_FURNITURE = 3, AVG_REF_PLANE = 4 };
+
+/* dof flags */
+#define AVG_DOF_LIMIT        1u   /* Bullet joint-limit constraint exists (revolute/prismatic with lower<=upper) */
+#define AVG_DOF_MOTOR        2u   /* position motor active                                                       */
+#define AVG_DOF_HUMAN        4u   /* limits scale with limit_scale, motor force with human strength, kp=human_kp */
+#define AVG_DOF_HARD_LIMIT   8u   /* teleported back inside limits after every sub-step (env.py:389-410)         */
+
+typedef struct AvgBody {          /* 32 x 4 bytes */
+    int32_t  parent;              /* dynamic body index, -1 = static world                                  */
+    int32_t  jtype;
+    int32_t  dof;                 /* first velocity dof                                                     */
+    int32_t  qidx;                /* first position coordinate in AvgEnv q[]                                */
+    float    ta_pos[3];           /* parent body frame (or world) -> joint frame at q = 0                   */
+    float    ta_quat[4];
+    float    axis[3];             /* joint axis, joint frame                                                */
+    float    tb_pos[3];           /* joint frame -> body frame (composite COM, principal axes)              */
+    float    tb_quat[4];
+    float    mass;
+    float    inertia[3];
+    float    gravity[3];          /* per-body gravity (reference setGravity(..., body=))                    */
+    uint32_t anc_mask;            /* bit k: body k is this body or one of its ancestors                     */
+    int32_t  ref_body;
+    int32_t  ref_joint;
+    int32_t  pad;
+} AvgBody;
+
+typedef struct AvgDof {           /* 16 x 4 bytes, one per velocity dof */
+    int32_t  body;
+    uint32_t flags;
+    float    lower, upper;        /* enforced limits (before limit_scale)                                   */
+    float    rep_lower, rep_upper;/* limits as reported by getJointInfo, used by the action mask            */
+    float    kp, kd, max_force;   /* position motor (kd = PyBullet default 1.0)                             */
+    int32_t  action;              /* index into the action vector, -1 = none                                */
+    int32_t  human_slot;          /* index 0..9 into the reference's controllable-joint list, -1 = none     */
+    float    init_target;
+    int32_t  pad[4];
+} AvgDof;
+
+typedef struct AvgShape {         /* 32 x 4 bytes */
+    int32_t  type;
+    int32_t  body;                /* dyn body, n_body+e for env-static body e, -1 = static (pose in world)   */
+    int32_t  ref_body, ref_link;
+    float    pos[3];              /* shape frame in the body frame (world if static)                        */
+    float    quat[4];
+    float    radius;              /* sphere / capsule / cylinder                                            */
+    float    half[3];             /* box half extents; capsule / cylinder: half[2] = half length            */
+    float    margin;              /* rounding radius added around the GJK core                              */
+    int32_t  vert_off, vert_cnt;  /* hull vertices (shape frame)                                            */
+    int32_t  plane_off, plane_cnt;/* hull face planes (n, d), n.x <= d inside                               */
+    float    friction;
+    float    thr;                 /* contact-breaking threshold of the owning link's compound               */
+    float    aabb_c[3];           /* AABB centre / half extents: shape frame for moving shapes, world for static */
+    float    aabb_h[3];
+    int32_t  pad[4];
+} AvgShape;
+
+typedef struct AvgFrame {         /* 8 x 4 bytes: a frame rigidly attached to a body */
+    int32_t  body;                /* dyn body, n_body+e, or -1 (world)                                       */
+    float    pos[3];
+    float    quat[4];
+} AvgFrame;
+
+/* frames of interest, indices into the frame table */
+enum {
+    AVG_F_TOOL_TIP = 0,   /* ScratchItch: tool link 1 COM (scratch_itch.py:54,106); other tasks: tool reference frame */
+    AVG_F_TOOL_BASE,      /* tool base COM frame = weld child frame                                           */
+    AVG_F_WELD_PARENT,    /* weld frame on the robot end-effector link (world_creation.py:356)               */
+    AVG_F_TORSO,          /* robot link 0 (15 for PR2) COM, scratch_itch.py:105                              */
+    AVG_F_CHEST,          /* human link 3, scratch_itch.py:113                                               */
+    AVG_F_SHOULDER,       /* human link 9  COM frame (upper arm), scratch_itch.py:118                        */
+    AVG_F_ELBOW,          /* human link 11 COM frame (forearm)                                               */
+    AVG_F_WRIST,          /* human link 13 COM frame (hand)                                                  */
+    AVG_F_COUNT
+};
+
+typedef struct AvgModelHeader {
+    uint32_t magic, version;
+    uint32_t total_bytes;
+    int32_t  task;
+    int32_t  n_body, n_ebody, n_dof, n_jdof, n_free;
+    int32_t  n_shape, n_mshape;   /* shapes [0, n_mshape) move (dyn or env-static); the rest are static       */
+    int32_t  n_vert, n_plane, n_pair, n_frame;
+    int32_t  substeps;            /* frame_skip, env.py:16                                                   */
+    int32_t  solver_iters;        /* numSolverIterations, scratch_itch.py:258                                */
+    int32_t  n_action_robot, n_action_human, n_obs_robot, n_obs_human;
+    int32_t  human_control;
+    float    dt;                  /* time_step 0.02                                                          */
+    float    erp;                 /* joint / contact ERP (0.2)                                               */
+    float    lin_damp, ang_damp;  /* btMultiBody linear / angular damping (0.04)                             */
+    float    residual_thr;        /* leastSquaresResidualThreshold (1e-7); 0 disables the early exit         */
+    float    max_vel;             /* btMultiBody max coordinate velocity (100)                               */
+    float    action_scale;        /* 0.05, env.py:280                                                        */
+    float    weld_max_force;      /* 500, world_creation.py:364                                              */
+    int32_t  weld_body_a, weld_body_b;   /* dyn body indices (robot EE composite, tool)                      */
+    float    task_f[32];          /* task constants, see AVG_TF_*                                             */
+    uint32_t off_body, off_dof, off_shape, off_vert, off_plane, off_pair, off_frame;
+    uint32_t pad[8];
+} AvgModelHeader;
+
+/* task_f indices (config.ini + task files) */
+enum {
+    AVG_TF_DISTANCE_W = 0, AVG_TF_ACTION_W, AVG_TF_TOOL_FORCE_W, AVG_TF_SCRATCH_W, AVG_TF_SUCCESS_THR,
+    AVG_TF_C_V, AVG_TF_C_F, AVG_TF_C_HF, AVG_TF_C_FD, AVG_TF_C_FDV,
+    AVG_TF_TARGET_RADIUS,        /* 0.025, scratch_itch.py:97 */
+    AVG_TF_SCRATCH_MOVE,         /* 0.01,  scratch_itch.py:66 */
+    AVG_TF_FORCE_CAP,            /* 10,    scratch_itch.py:66 */
+    AVG_TF_HUMAN_KP_ACTIVE,      /* human_gains passed to take_step (0.05), scratch_itch.py:45 */
+    AVG_TF_HUMAN_FORCE           /* human_forces (1.0) */
+};
+
+/* ---- per-environment record: AVG_ENV_STRIDE floats (int fields stored as int32 in the same slots) ---- */
+#define AVG_ENV_STRIDE 192
+enum {
+    AVG_E_Q        = 0,     /* [32] joint positions; free body k: pos(3) + quat(4) at body.qidx                */
+    AVG_E_QD       = 32,    /* [32] generalized velocities (free body: v(3) world, w(3) world)                 */
+    AVG_E_MTARGET  = 64,    /* [32] motor targets per dof                                                      */
+    /* episode parameters */
+    AVG_E_STRENGTH = 96, AVG_E_LIMIT_SCALE = 97, AVG_E_HUMAN_KP = 98, AVG_E_TREMOR_ON = 99,
+    AVG_E_TREMOR   = 100,   /* [10] world_creation.human_tremors                                               */
+    AVG_E_TARGET_H = 110,   /* [10] target_human_joint_positions (mutated by the tremor path, env.py:332)      */
+    AVG_E_TARGET_ON_ARM = 120, /* [3] scratch_itch.py:281 */
+    AVG_E_LIMB_FRAME = 123, /* int: AVG_F_SHOULDER or AVG_F_ELBOW                                              */
+    AVG_E_EBODY    = 124,   /* [4][7] env-static body poses (pos, quat)  (first 4 env-static bodies)           */
+    /* task state */
+    AVG_E_ITERATION = 152,  /* int */
+    AVG_E_TASK_SUCCESS = 153,
+    AVG_E_PREV_CONTACT = 154, /* [3] prev_target_contact_pos */
+    AVG_E_VALID_POSE = 157, /* [4] right_arm_previous_valid_pose */
+    AVG_E_HAS_VALID = 161,  /* int */
+    AVG_E_TARGET_POS = 162, /* [3] derived each sub-step, kept for inspection */
+    AVG_E_EPISODE_RETURN = 165,
+    AVG_E_OVERFLOW = 166,   /* int: bit0 contact overflow, bit1 row overflow (never silently dropped)          */
+    AVG_E_LAST = 167
+};
+
+/* one reported contact point (parity / debug), 16 floats */
+typedef struct AvgContact {
+    int32_t shape_a, shape_b;     /* shape indices, A is the moving shape listed first in the pair table        */
+    float   pos_a[3], pos_b[3];   /* world */
+    float   normal[3];            /* from B to A */
+    float   dist;
+    float   force;                /* normal impulse / dt, as getContactPoints()[9] */
+    int32_t pad[3];
+} AvgContact;
+
+#endif /* AVG_MODEL_H */

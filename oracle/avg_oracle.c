@@ -1,0 +1,1072 @@
+/* avg_oracle.c — float64 CPU restatement of the reference hot path (TEST INFRASTRUCTURE, NOT PRODUCT).
+ *
+ * PARITY UNPINNED: the reference's arithmetic for this path lives in the third-party `pybullet` C extension
+ * (reference setup.py:18, unpinned; in practice a custom bullet3 fork — SURVEY.md §0 F2), which is absent from
+ * /root/reference and not installable here, and the reference ships no tests, golden vectors or fixtures
+ * (SURVEY.md §4, §8c).  What is restated below therefore has two kinds of source:
+ *   (1) code that IS in the reference tree and is followed line by line (cited per function):
+ *       AssistiveEnv.take_step            env.py:274-351
+ *       enforce_hard_human_joint_limits   env.py:389-410
+ *       human_preferences                 env.py:412-448
+ *       ScratchItchEnv.step/reward        scratch_itch.py:30-82
+ *       ScratchItchEnv.get_total_force    scratch_itch.py:84-102
+ *       ScratchItchEnv._get_obs           scratch_itch.py:104-128
+ *       ScratchItchEnv.update_targets     scratch_itch.py:289-293
+ *   (2) p.stepSimulation / setJointMotorControlArray / createConstraint / getContactPoints, restated from the
+ *       published algorithms Bullet implements (Featherstone articulated-body algorithm; GJK closest points;
+ *       projected Gauss-Seidel sequential impulses) with the Bullet semantics listed in SURVEY.md App. D.  Every
+ *       such choice is tagged [UPSTREAM-BULLET] and remains unverified until a PyBullet capture exists.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * It deliberately shares no code with the CUDA product: forward dynamics here is the recursive O(n) ABA and the
+ * solver iterates in velocity space like Bullet, whereas the kernels use a mass-matrix / Delassus formulation.
+ *
+ * Build: make -C oracle   (gcc -O2 -shared -fPIC)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/avg_model.h"
+
+#define MAXB AVG_MAX_BODY
+#define MAXD AVG_MAX_DOF
+#define MAXC AVG_MAX_CONTACT
+#define MAXR AVG_MAX_ROWS
+
+typedef struct { double x, y, z; } v3;
+typedef struct { double m[3][3]; } m3;
+typedef struct { double x, y, z, w; } quat;
+
+static v3 V(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 vscale(v3 a, double s) { return V(a.x * s, a.y * s, a.z * s); }
+static double vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static double vnorm(v3 a) { return sqrt(vdot(a, a)); }
+static v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static v3 f3(const float* f) { return V(f[0], f[1], f[2]); }
+static quat qf(const float* f) { quat q = {f[0], f[1], f[2], f[3]}; return q; }
+static quat qmul(quat a, quat b) {
+    quat r = {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+              a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+    return r;
+}
+static quat qnormalize(quat q) {
+    double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    quat r = {q.x / n, q.y / n, q.z / n, q.w / n};
+    return r;
+}
+static quat qconj(quat q) { quat r = {-q.x, -q.y, -q.z, q.w}; return r; }
+static m3 qmat(quat q) {
+    m3 r; double x = q.x, y = q.y, z = q.z, w = q.w;
+    r.m[0][0] = 1 - 2 * (y * y + z * z); r.m[0][1] = 2 * (x * y - z * w); r.m[0][2] = 2 * (x * z + y * w);
+    r.m[1][0] = 2 * (x * y + z * w); r.m[1][1] = 1 - 2 * (x * x + z * z); r.m[1][2] = 2 * (y * z - x * w);
+    r.m[2][0] = 2 * (x * z - y * w); r.m[2][1] = 2 * (y * z + x * w); r.m[2][2] = 1 - 2 * (x * x + y * y);
+    return r;
+}
+static v3 mmulv(const m3* a, v3 v) {
+    return V(a->m[0][0] * v.x + a->m[0][1] * v.y + a->m[0][2] * v.z, a->m[1][0] * v.x + a->m[1][1] * v.y + a->m[1][2] * v.z,
+             a->m[2][0] * v.x + a->m[2][1] * v.y + a->m[2][2] * v.z);
+}
+static v3 mtmulv(const m3* a, v3 v) {
+    return V(a->m[0][0] * v.x + a->m[1][0] * v.y + a->m[2][0] * v.z, a->m[0][1] * v.x + a->m[1][1] * v.y + a->m[2][1] * v.z,
+             a->m[0][2] * v.x + a->m[1][2] * v.y + a->m[2][2] * v.z);
+}
+static v3 qrot(quat q, v3 v) { m3 r = qmat(q); return mmulv(&r, v); }
+static quat qaxis(v3 axis, double ang) {
+    double s = sin(ang * 0.5); quat r = {axis.x * s, axis.y * s, axis.z * s, cos(ang * 0.5)}; return r;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const AvgModelHeader* h;
+    const AvgBody* body;
+    const AvgDof* dof;
+    const AvgShape* shape;
+    const float* vert;
+    const float* plane;
+    const uint32_t* pair;
+    const AvgFrame* frame;
+} Model;
+
+static int model_open(const void* blob, Model* m) {
+    const AvgModelHeader* h = (const AvgModelHeader*)blob;
+    if (h->magic != AVG_MAGIC || h->version != AVG_VERSION) return -1;
+    if (h->n_body > MAXB || h->n_dof > MAXD) return -2;
+    const char* b = (const char*)blob;
+    m->h = h;
+    m->body = (const AvgBody*)(b + h->off_body);
+    m->dof = (const AvgDof*)(b + h->off_dof);
+    m->shape = (const AvgShape*)(b + h->off_shape);
+    m->vert = (const float*)(b + h->off_vert);
+    m->plane = (const float*)(b + h->off_plane);
+    m->pair = (const uint32_t*)(b + h->off_pair);
+    m->frame = (const AvgFrame*)(b + h->off_frame);
+    return 0;
+}
+
+/* per-sub-step kinematic state */
+typedef struct {
+    v3 p[MAXB];      /* body frame origin (composite COM), world */
+    quat q[MAXB];
+    m3 R[MAXB];
+    v3 axis[MAXB];   /* joint axis, world */
+    v3 org[MAXB];    /* joint origin, world */
+} Kin;
+
+static void body_pose(const Kin* k, int body, v3* p, quat* q) {
+    if (body < 0) { *p = V(0, 0, 0); quat id = {0, 0, 0, 1}; *q = id; }
+    else { *p = k->p[body]; *q = k->q[body]; }
+}
+
+/* forward kinematics: C_body = C_parent ∘ Ta ∘ joint(q) ∘ Tb  (include/avg_model.h AvgBody) */
+static void fk(const Model* m, const double* env, Kin* k) {
+    for (int b = 0; b < m->h->n_body; ++b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) {
+            const double* q = env + AVG_E_Q + B->qidx;
+            k->p[b] = V(q[0], q[1], q[2]);
+            quat r = {q[3], q[4], q[5], q[6]};
+            k->q[b] = qnormalize(r);
+            k->R[b] = qmat(k->q[b]);
+            k->axis[b] = V(0, 0, 0); k->org[b] = k->p[b];
+            continue;
+        }
+        v3 pp; quat pq;
+        body_pose(k, B->parent, &pp, &pq);
+        v3 jp = vadd(pp, qrot(pq, f3(B->ta_pos)));
+        quat jq = qmul(pq, qf(B->ta_quat));
+        v3 ax = f3(B->axis);
+        double qv = env[AVG_E_Q + B->qidx];
+        k->axis[b] = qrot(jq, ax);
+        k->org[b] = jp;
+        if (B->jtype == AVG_JOINT_REVOLUTE) jq = qmul(jq, qaxis(ax, qv));
+        else jp = vadd(jp, vscale(k->axis[b], qv));
+        k->p[b] = vadd(jp, qrot(jq, f3(B->tb_pos)));
+        k->q[b] = qnormalize(qmul(jq, qf(B->tb_quat)));
+        k->R[b] = qmat(k->q[b]);
+    }
+}
+
+static void frame_pose(const Model* m, const Kin* k, int f, v3* p, quat* q) {
+    const AvgFrame* F = &m->frame[f];
+    v3 bp; quat bq;
+    body_pose(k, F->body, &bp, &bq);
+    *p = vadd(bp, qrot(bq, f3(F->pos)));
+    *q = qnormalize(qmul(bq, qf(F->quat)));
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Collision: support-function shapes, GJK closest points on the cores, rounding margins added afterwards.
+ * [UPSTREAM-BULLET] Bullet runs GJK on margin-shrunk cores and reports distance minus both margins; one new point
+ * per shape pair per step; a point is kept when distance < the manifold's contact-breaking threshold
+ * (min over the two collision objects of 0.02 x angular-motion-disc).  Persistent 4-point manifolds and
+ * warm starting are NOT restated (documented deviation).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const AvgShape* s;
+    v3 p; m3 R;
+    const float* verts;
+    const float* planes;
+} WShape;
+
+static void shape_world(const Model* m, const Kin* k, int si, WShape* w) {
+    const AvgShape* s = &m->shape[si];
+    w->s = s; w->verts = m->vert + 3 * s->vert_off; w->planes = m->plane + 4 * s->plane_off;
+    if (s->body < 0) { w->p = f3(s->pos); w->R = qmat(qf(s->quat)); }
+    else {
+        w->p = vadd(k->p[s->body], qrot(k->q[s->body], f3(s->pos)));
+        w->R = qmat(qnormalize(qmul(k->q[s->body], qf(s->quat))));
+    }
+}
+
+static void shape_aabb(const WShape* w, v3* c, v3* h) {
+    const AvgShape* s = w->s;
+    if (s->body < 0) { *c = f3(s->aabb_c); *h = f3(s->aabb_h); return; }
+    v3 lc = f3(s->aabb_c), lh = f3(s->aabb_h);
+    *c = vadd(w->p, mmulv(&w->R, lc));
+    h->x = fabs(w->R.m[0][0]) * lh.x + fabs(w->R.m[0][1]) * lh.y + fabs(w->R.m[0][2]) * lh.z;
+    h->y = fabs(w->R.m[1][0]) * lh.x + fabs(w->R.m[1][1]) * lh.y + fabs(w->R.m[1][2]) * lh.z;
+    h->z = fabs(w->R.m[2][0]) * lh.x + fabs(w->R.m[2][1]) * lh.y + fabs(w->R.m[2][2]) * lh.z;
+}
+
+/* support point of the CORE of shape w in world direction d */
+static v3 support(const WShape* w, v3 d) {
+    const AvgShape* s = w->s;
+    v3 l = mtmulv(&w->R, d), r;
+    switch (s->type) {
+    case AVG_SHAPE_SPHERE: r = V(0, 0, 0); break;
+    case AVG_SHAPE_CAPSULE: r = V(0, 0, l.z >= 0 ? s->half[2] : -s->half[2]); break;
+    case AVG_SHAPE_BOX: {
+        double hx = s->half[0] - s->margin, hy = s->half[1] - s->margin, hz = s->half[2] - s->margin;
+        r = V(l.x >= 0 ? hx : -hx, l.y >= 0 ? hy : -hy, l.z >= 0 ? hz : -hz); break;
+    }
+    case AVG_SHAPE_CYLINDER: {
+        double rc = s->radius - s->margin, hc = s->half[2] - s->margin;
+        double n = sqrt(l.x * l.x + l.y * l.y);
+        if (n > 1e-12) r = V(rc * l.x / n, rc * l.y / n, l.z >= 0 ? hc : -hc);
+        else r = V(rc, 0, l.z >= 0 ? hc : -hc);
+        break;
+    }
+    case AVG_SHAPE_HULL: {
+        int best = 0; double bd = -1e300;
+        for (int i = 0; i < s->vert_cnt; ++i) {
+            double dd = l.x * w->verts[3 * i] + l.y * w->verts[3 * i + 1] + l.z * w->verts[3 * i + 2];
+            if (dd > bd) { bd = dd; best = i; }
+        }
+        r = V(w->verts[3 * best], w->verts[3 * best + 1], w->verts[3 * best + 2]); break;
+    }
+    default: r = V(0, 0, 0);
+    }
+    return vadd(w->p, mmulv(&w->R, r));
+}
+
+typedef struct { v3 w[4], a[4], b[4]; double lam[4]; int n; } Simplex;
+
+/* closest point to the origin on the simplex; reduces the simplex to the supporting feature, fills lam.
+ * returns 1 if the origin is enclosed (tetrahedron case). */
+static void closest_seg(Simplex* s, int i0, int i1, double* lam0, double* lam1, int* keep_mask) {
+    v3 a = s->w[i0], b = s->w[i1];
+    v3 ab = vsub(b, a);
+    double t = -vdot(a, ab), den = vdot(ab, ab);
+    if (t <= 0 || den <= 0) { *lam0 = 1; *lam1 = 0; *keep_mask = 1; }
+    else if (t >= den) { *lam0 = 0; *lam1 = 1; *keep_mask = 2; }
+    else { *lam1 = t / den; *lam0 = 1 - *lam1; *keep_mask = 3; }
+}
+
+/* closest point on triangle (i0,i1,i2) to origin (Ericson, Real-Time Collision Detection 5.1.5) */
+static void closest_tri(const Simplex* s, int i0, int i1, int i2, double lam[3], int* keep_mask) {
+    v3 a = s->w[i0], b = s->w[i1], c = s->w[i2];
+    v3 ab = vsub(b, a), ac = vsub(c, a), ap = vneg(a);
+    double d1 = vdot(ab, ap), d2 = vdot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) { lam[0] = 1; lam[1] = 0; lam[2] = 0; *keep_mask = 1; return; }
+    v3 bp = vneg(b);
+    double d3 = vdot(ab, bp), d4 = vdot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) { lam[0] = 0; lam[1] = 1; lam[2] = 0; *keep_mask = 2; return; }
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { double v = d1 / (d1 - d3); lam[0] = 1 - v; lam[1] = v; lam[2] = 0; *keep_mask = 3; return; }
+    v3 cp = vneg(c);
+    double d5 = vdot(ab, cp), d6 = vdot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) { lam[0] = 0; lam[1] = 0; lam[2] = 1; *keep_mask = 4; return; }
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { double w = d2 / (d2 - d6); lam[0] = 1 - w; lam[1] = 0; lam[2] = w; *keep_mask = 5; return; }
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); lam[0] = 0; lam[1] = 1 - w; lam[2] = w; *keep_mask = 6; return;
+    }
+    double den = 1.0 / (va + vb + vc);
+    lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2]; *keep_mask = 7;
+}
+
+static int simplex_closest(Simplex* s, v3* v) {
+    double lam[4] = {0, 0, 0, 0};
+    int mask = 0;
+    if (s->n == 1) { lam[0] = 1; mask = 1; }
+    else if (s->n == 2) { closest_seg(s, 0, 1, &lam[0], &lam[1], &mask); }
+    else if (s->n == 3) { closest_tri(s, 0, 1, 2, lam, &mask); }
+    else {
+        /* tetrahedron: test the four faces whose outside half-space contains the origin */
+        static const int F[4][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 3, 1}, {1, 2, 3, 0}};
+        double best = 1e300; int any = 0;
+        for (int f = 0; f < 4; ++f) {
+            v3 a = s->w[F[f][0]], b = s->w[F[f][1]], c = s->w[F[f][2]], d = s->w[F[f][3]];
+            v3 n = vcross(vsub(b, a), vsub(c, a));
+            double so = -vdot(a, n), sd = vdot(vsub(d, a), n);
+            if (sd == 0 || so * sd <= 0) {      /* origin not strictly on the inner side of this face */
+                double l3[3]; int km;
+                closest_tri(s, F[f][0], F[f][1], F[f][2], l3, &km);
+                v3 p = vadd(vadd(vscale(a, l3[0]), vscale(b, l3[1])), vscale(c, l3[2]));
+                double dd = vdot(p, p);
+                if (dd < best) {
+                    best = dd; any = 1;
+                    lam[0] = lam[1] = lam[2] = lam[3] = 0;
+                    lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
+                    mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
+                }
+            }
+        }
+        if (!any) return 1;   /* origin inside */
+    }
+    /* compact */
+    Simplex r; r.n = 0;
+    v3 p = V(0, 0, 0);
+    for (int i = 0; i < s->n; ++i) if (mask & (1 << i)) {
+        r.w[r.n] = s->w[i]; r.a[r.n] = s->a[i]; r.b[r.n] = s->b[i]; r.lam[r.n] = lam[i];
+        p = vadd(p, vscale(s->w[i], lam[i]));
+        r.n++;
+    }
+    *s = r; *v = p;
+    return 0;
+}
+
+/* returns 0 = separated cores (dist, pa, pb valid), 1 = cores overlap */
+static int gjk(const WShape* A, const WShape* B, double* dist, v3* pa, v3* pb) {
+    Simplex s; s.n = 0;
+    v3 v = vsub(A->p, B->p);
+    if (vdot(v, v) < 1e-12) v = V(1, 0, 0);
+    for (int it = 0; it < 48; ++it) {
+        v3 sa = support(A, vneg(v)), sb = support(B, v);
+        v3 w = vsub(sa, sb);
+        double vv = vdot(v, v), vw = vdot(v, w);
+        if (s.n > 0 && (vv - vw) <= 1e-10 * vv + 1e-18) break;      /* no progress possible: v is the closest point */
+        int dup = 0;
+        for (int i = 0; i < s.n; ++i) { v3 d = vsub(s.w[i], w); if (vdot(d, d) < 1e-24) dup = 1; }
+        if (dup) break;
+        s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
+        if (simplex_closest(&s, &v)) return 1;
+        if (vdot(v, v) < 1e-20) return 1;
+    }
+    v3 a = V(0, 0, 0), b = V(0, 0, 0);
+    for (int i = 0; i < s.n; ++i) { a = vadd(a, vscale(s.a[i], s.lam[i])); b = vadd(b, vscale(s.b[i], s.lam[i])); }
+    *pa = a; *pb = b; *dist = vnorm(v);
+    return 0;
+}
+
+/* deep-penetration fallback: smallest overlap among face-normal / centre axes evaluated with support functions */
+static void sat_axis(const WShape* A, const WShape* B, v3 n, double* best, v3* bn, v3* bpa) {
+    double ln = vnorm(n);
+    if (ln < 1e-12) return;
+    n = vscale(n, 1.0 / ln);
+    v3 sa = support(A, vneg(n)), sb = support(B, n);
+    double depth = vdot(sb, n) - vdot(sa, n);
+    if (depth < *best) { *best = depth; *bn = n; *bpa = sa; }
+}
+static void shape_axes(const WShape* S, const WShape* O, double sign, const WShape* A, const WShape* B, double* best, v3* bn, v3* bpa) {
+    const AvgShape* s = S->s;
+    /* `sign` = +1 when S is B (its outward normals point from B to A), -1 when S is A */
+    if (s->type == AVG_SHAPE_BOX || s->type == AVG_SHAPE_CYLINDER) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (s->type == AVG_SHAPE_CYLINDER && ax < 2) continue;
+            v3 n = V(S->R.m[0][ax], S->R.m[1][ax], S->R.m[2][ax]);
+            sat_axis(A, B, vscale(n, sign), best, bn, bpa);
+            sat_axis(A, B, vscale(n, -sign), best, bn, bpa);
+        }
+        if (s->type == AVG_SHAPE_CYLINDER) {
+            v3 az = V(S->R.m[0][2], S->R.m[1][2], S->R.m[2][2]);
+            v3 d = vsub(O->p, S->p);
+            v3 rad = vsub(d, vscale(az, vdot(d, az)));
+            sat_axis(A, B, vscale(rad, sign), best, bn, bpa);
+        }
+    } else if (s->type == AVG_SHAPE_HULL) {
+        for (int i = 0; i < s->plane_cnt; ++i) {
+            v3 n = mmulv(&S->R, V(S->planes[4 * i], S->planes[4 * i + 1], S->planes[4 * i + 2]));
+            sat_axis(A, B, vscale(n, sign), best, bn, bpa);
+        }
+    }
+}
+static void deep_contact(const WShape* A, const WShape* B, double* depth, v3* n, v3* pa_core) {
+    double best = 1e300; v3 bn = V(0, 0, 1), bpa = A->p;
+    shape_axes(A, B, -1.0, A, B, &best, &bn, &bpa);
+    shape_axes(B, A, +1.0, A, B, &best, &bn, &bpa);
+    v3 cc = vsub(A->p, B->p);
+    sat_axis(A, B, cc, &best, &bn, &bpa);
+    if (best > 1e299) { best = 0; }
+    *depth = best; *n = bn; *pa_core = bpa;
+}
+
+typedef struct {
+    int sa, sb;
+    v3 pa, pb, n;     /* world; n from B to A */
+    double dist;
+    double lambda_n;  /* normal impulse after the solve */
+} Contact;
+
+static int narrowphase(const WShape* A, const WShape* B, double thr, Contact* c) {
+    double ma = A->s->margin, mb = B->s->margin;
+    if (B->s->type == AVG_SHAPE_PLANE) {            /* static ground: half-space z <= 0 */
+        v3 s = support(A, V(0, 0, -1));
+        double d = s.z - ma;
+        if (d >= thr) return 0;
+        c->n = V(0, 0, 1); c->pa = V(s.x, s.y, s.z - ma); c->pb = V(s.x, s.y, 0); c->dist = d;
+        return 1;
+    }
+    double dist; v3 pa, pb;
+    if (!gjk(A, B, &dist, &pa, &pb)) {
+        double d = dist - ma - mb;
+        if (d >= thr) return 0;
+        v3 n = vscale(vsub(pa, pb), 1.0 / dist);
+        c->n = n; c->pa = vsub(pa, vscale(n, ma)); c->pb = vadd(pb, vscale(n, mb)); c->dist = d;
+        return 1;
+    }
+    double depth; v3 n, pac;
+    deep_contact(A, B, &depth, &n, &pac);
+    c->n = n; c->dist = -depth - ma - mb;
+    c->pa = vsub(pac, vscale(n, ma));
+    c->pb = vadd(vadd(pac, vscale(n, depth)), vscale(n, mb));
+    return 1;
+}
+
+static int collide(const Model* m, const Kin* k, Contact* out, int* overflow) {
+    int ns = m->h->n_shape, nc = 0;
+    WShape* ws = (WShape*)malloc(sizeof(WShape) * ns);
+    v3* ac = (v3*)malloc(sizeof(v3) * ns); v3* ah = (v3*)malloc(sizeof(v3) * ns);
+    for (int i = 0; i < ns; ++i) { shape_world(m, k, i, &ws[i]); shape_aabb(&ws[i], &ac[i], &ah[i]); }
+    for (int pi = 0; pi < m->h->n_pair; ++pi) {
+        int a = m->pair[pi] & 0xffff, b = m->pair[pi] >> 16;
+        double thr = fmin(ws[a].s->thr, ws[b].s->thr);
+        if (ws[b].s->type != AVG_SHAPE_PLANE) {
+            if (fabs(ac[a].x - ac[b].x) > ah[a].x + ah[b].x + thr) continue;
+            if (fabs(ac[a].y - ac[b].y) > ah[a].y + ah[b].y + thr) continue;
+            if (fabs(ac[a].z - ac[b].z) > ah[a].z + ah[b].z + thr) continue;
+        } else if (ac[a].z - ah[a].z > thr) continue;
+        Contact c;
+        if (narrowphase(&ws[a], &ws[b], thr, &c)) {
+            if (nc >= MAXC) { *overflow |= 1; break; }
+            c.sa = a; c.sb = b; c.lambda_n = 0;
+            out[nc++] = c;
+        }
+    }
+    free(ws); free(ac); free(ah);
+    return nc;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dynamics: articulated-body algorithm with all spatial quantities expressed in world coordinates about the world
+ * origin (motion [w; v_O], force [n_O; f]).  [UPSTREAM-BULLET] btMultiBody::computeAccelerationsArticulatedBody
+ * AlgorithmMultiDof, including its velocity damping: every link gets the extra bias force
+ * m v (k + k |v|) and I w (k + k |w|) with k = linear/angular damping 0.04, and the gyroscopic term.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct { double v[6]; } sv;            /* spatial vector */
+typedef struct { double m[6][6]; } sm;         /* spatial matrix */
+
+static sv sv_make(v3 a, v3 l) { sv r = {{a.x, a.y, a.z, l.x, l.y, l.z}}; return r; }
+static v3 sv_ang(const sv* s) { return V(s->v[0], s->v[1], s->v[2]); }
+static v3 sv_lin(const sv* s) { return V(s->v[3], s->v[4], s->v[5]); }
+static double sv_dot(const sv* a, const sv* b) { double r = 0; for (int i = 0; i < 6; ++i) r += a->v[i] * b->v[i]; return r; }
+static sv sm_mul(const sm* A, const sv* x) {
+    sv r; for (int i = 0; i < 6; ++i) { double s = 0; for (int j = 0; j < 6; ++j) s += A->m[i][j] * x->v[j]; r.v[i] = s; } return r;
+}
+/* motion cross motion: [w;v] x [w2;v2] = [w x w2 ; w x v2 + v x w2] */
+static sv crm(const sv* a, const sv* b) {
+    v3 w = sv_ang(a), v = sv_lin(a), w2 = sv_ang(b), v2 = sv_lin(b);
+    return sv_make(vcross(w, w2), vadd(vcross(w, v2), vcross(v, w2)));
+}
+/* motion cross force: [w;v] x* [n;f] = [w x n + v x f ; w x f] */
+static sv crf(const sv* a, const sv* f) {
+    v3 w = sv_ang(a), v = sv_lin(a), n = sv_ang(f), ff = sv_lin(f);
+    return sv_make(vadd(vcross(w, n), vcross(v, ff)), vcross(w, ff));
+}
+static void skew(v3 c, double S[3][3]) {
+    S[0][0] = 0; S[0][1] = -c.z; S[0][2] = c.y; S[1][0] = c.z; S[1][1] = 0; S[1][2] = -c.x; S[2][0] = -c.y; S[2][1] = c.x; S[2][2] = 0;
+}
+/* spatial inertia about the world origin of a body with mass m, COM c, rotational inertia Ic (world axes) */
+static void spatial_inertia(double mass, v3 c, const double Ic[3][3], sm* I) {
+    double C[3][3]; skew(c, C);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double cct = 0; for (int k = 0; k < 3; ++k) cct += C[i][k] * C[j][k];      /* C C^T */
+        I->m[i][j] = Ic[i][j] + mass * cct;
+        I->m[i][j + 3] = mass * C[i][j];
+        I->m[i + 3][j] = mass * C[j][i];
+        I->m[i + 3][j + 3] = (i == j) ? mass : 0.0;
+    }
+}
+
+typedef struct {
+    sv S[MAXB];        /* joint motion subspace (world) */
+    sv vel[MAXB];      /* body spatial velocity */
+    sv cb[MAXB];       /* velocity-product acceleration */
+    sm IA[MAXB];       /* articulated inertia */
+    sv U[MAXB];
+    double D[MAXB], invD[MAXB];
+    double Iw[MAXB][3][3];   /* rotational inertia about COM, world axes */
+    double IwInv[MAXB][3][3];
+} Dyn;
+
+static void world_inertia(const Model* m, const Kin* k, Dyn* d) {
+    for (int b = 0; b < m->h->n_body; ++b) {
+        const AvgBody* B = &m->body[b];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            double s = 0, si = 0;
+            for (int a = 0; a < 3; ++a) {
+                s += k->R[b].m[i][a] * B->inertia[a] * k->R[b].m[j][a];
+                si += (B->inertia[a] > 0) ? k->R[b].m[i][a] / B->inertia[a] * k->R[b].m[j][a] : 0.0;
+            }
+            d->Iw[b][i][j] = s; d->IwInv[b][i][j] = si;
+        }
+    }
+}
+
+/* unconstrained accelerations; also caches IA, U, D for the impulse-response solves */
+static void aba(const Model* m, const Kin* k, const double* env, Dyn* d, double* qdd) {
+    const AvgModelHeader* h = m->h;
+    int nb = h->n_body;
+    sv pA[MAXB];
+    world_inertia(m, k, d);
+    /* pass 1 */
+    for (int b = 0; b < nb; ++b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) continue;
+        double qd = env[AVG_E_QD + B->dof];
+        if (B->jtype == AVG_JOINT_REVOLUTE) d->S[b] = sv_make(k->axis[b], vcross(k->org[b], k->axis[b]));
+        else d->S[b] = sv_make(V(0, 0, 0), k->axis[b]);
+        sv vj = d->S[b]; for (int i = 0; i < 6; ++i) vj.v[i] *= qd;
+        if (B->parent >= 0) { for (int i = 0; i < 6; ++i) d->vel[b].v[i] = d->vel[B->parent].v[i] + vj.v[i]; }
+        else d->vel[b] = vj;
+        d->cb[b] = crm(&d->vel[b], &vj);
+        spatial_inertia(B->mass, k->p[b], d->Iw[b], &d->IA[b]);
+        sv Iv = sm_mul(&d->IA[b], &d->vel[b]);
+        pA[b] = crf(&d->vel[b], &Iv);
+        /* external force at the COM: gravity and Bullet's velocity damping */
+        v3 w = sv_ang(&d->vel[b]);
+        v3 vc = vadd(sv_lin(&d->vel[b]), vcross(w, k->p[b]));
+        v3 f = vscale(f3(B->gravity), B->mass);
+        f = vsub(f, vscale(vc, B->mass * (h->lin_damp + h->lin_damp * vnorm(vc))));
+        v3 Iw_w = V(d->Iw[b][0][0] * w.x + d->Iw[b][0][1] * w.y + d->Iw[b][0][2] * w.z,
+                    d->Iw[b][1][0] * w.x + d->Iw[b][1][1] * w.y + d->Iw[b][1][2] * w.z,
+                    d->Iw[b][2][0] * w.x + d->Iw[b][2][1] * w.y + d->Iw[b][2][2] * w.z);
+        v3 n = vneg(vscale(Iw_w, h->ang_damp + h->ang_damp * vnorm(w)));
+        v3 nO = vadd(n, vcross(k->p[b], f));
+        pA[b].v[0] -= nO.x; pA[b].v[1] -= nO.y; pA[b].v[2] -= nO.z;
+        pA[b].v[3] -= f.x; pA[b].v[4] -= f.y; pA[b].v[5] -= f.z;
+    }
+    /* pass 2 */
+    double u[MAXB];
+    for (int b = nb - 1; b >= 0; --b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) continue;
+        d->U[b] = sm_mul(&d->IA[b], &d->S[b]);
+        d->D[b] = sv_dot(&d->S[b], &d->U[b]);
+        d->invD[b] = (d->D[b] >= 2.2e-16) ? 1.0 / d->D[b] : 0.0;       /* [UPSTREAM-BULLET] D < eps => joint frozen */
+        u[b] = 0.0 - sv_dot(&d->S[b], &pA[b]);
+        if (B->parent >= 0) {
+            sm Ia = d->IA[b];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Ia.m[i][j] -= d->U[b].v[i] * d->invD[b] * d->U[b].v[j];
+            sv Iac = sm_mul(&Ia, &d->cb[b]);
+            for (int i = 0; i < 6; ++i) {
+                pA[B->parent].v[i] += pA[b].v[i] + Iac.v[i] + d->U[b].v[i] * d->invD[b] * u[b];
+                for (int j = 0; j < 6; ++j) d->IA[B->parent].m[i][j] += Ia.m[i][j];
+            }
+        }
+    }
+    /* pass 3 */
+    sv acc[MAXB];
+    for (int b = 0; b < nb; ++b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) {
+            /* free rigid body (floating-base btMultiBody without links): Newton-Euler with the same damping */
+            const double* qd = env + AVG_E_QD + B->dof;
+            v3 v = V(qd[0], qd[1], qd[2]), w = V(qd[3], qd[4], qd[5]);
+            v3 g = f3(B->gravity);
+            v3 a = vsub(g, vscale(v, h->lin_damp + h->lin_damp * vnorm(v)));
+            v3 Iw_w = V(d->Iw[b][0][0] * w.x + d->Iw[b][0][1] * w.y + d->Iw[b][0][2] * w.z,
+                        d->Iw[b][1][0] * w.x + d->Iw[b][1][1] * w.y + d->Iw[b][1][2] * w.z,
+                        d->Iw[b][2][0] * w.x + d->Iw[b][2][1] * w.y + d->Iw[b][2][2] * w.z);
+            v3 tau = vsub(vneg(vscale(Iw_w, h->ang_damp + h->ang_damp * vnorm(w))), vcross(w, Iw_w));
+            v3 al = V(d->IwInv[b][0][0] * tau.x + d->IwInv[b][0][1] * tau.y + d->IwInv[b][0][2] * tau.z,
+                      d->IwInv[b][1][0] * tau.x + d->IwInv[b][1][1] * tau.y + d->IwInv[b][1][2] * tau.z,
+                      d->IwInv[b][2][0] * tau.x + d->IwInv[b][2][1] * tau.y + d->IwInv[b][2][2] * tau.z);
+            if (B->mass <= 0) { a = V(0, 0, 0); }
+            qdd[B->dof + 0] = a.x; qdd[B->dof + 1] = a.y; qdd[B->dof + 2] = a.z;
+            qdd[B->dof + 3] = al.x; qdd[B->dof + 4] = al.y; qdd[B->dof + 5] = al.z;
+            continue;
+        }
+        sv ap;
+        if (B->parent >= 0) { for (int i = 0; i < 6; ++i) ap.v[i] = acc[B->parent].v[i] + d->cb[b].v[i]; }
+        else ap = d->cb[b];
+        double a = d->invD[b] * (u[b] - sv_dot(&d->U[b], &ap));
+        qdd[B->dof] = a;
+        for (int i = 0; i < 6; ++i) acc[b].v[i] = ap.v[i] + d->S[b].v[i] * a;
+    }
+}
+
+/* response M^-1 tau for a generalized impulse tau (Bullet: calcAccelerationDeltasMultiDof) */
+static void aba_delta(const Model* m, const Dyn* d, const double* tau, double* out) {
+    int nb = m->h->n_body;
+    sv p[MAXB]; double u[MAXB];
+    memset(p, 0, sizeof(p));
+    for (int b = nb - 1; b >= 0; --b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) continue;
+        u[b] = tau[B->dof] - sv_dot(&d->S[b], &p[b]);
+        if (B->parent >= 0) for (int i = 0; i < 6; ++i) p[B->parent].v[i] += p[b].v[i] + d->U[b].v[i] * d->invD[b] * u[b];
+    }
+    sv acc[MAXB];
+    for (int b = 0; b < nb; ++b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) {
+            const double* t = tau + B->dof;
+            double im = B->mass > 0 ? 1.0 / B->mass : 0.0;
+            out[B->dof + 0] = t[0] * im; out[B->dof + 1] = t[1] * im; out[B->dof + 2] = t[2] * im;
+            for (int i = 0; i < 3; ++i) out[B->dof + 3 + i] = d->IwInv[b][i][0] * t[3] + d->IwInv[b][i][1] * t[4] + d->IwInv[b][i][2] * t[5];
+            continue;
+        }
+        sv ap; memset(&ap, 0, sizeof(ap));
+        if (B->parent >= 0) ap = acc[B->parent];
+        double a = d->invD[b] * (u[b] - sv_dot(&d->U[b], &ap));
+        out[B->dof] = a;
+        for (int i = 0; i < 6; ++i) acc[b].v[i] = ap.v[i] + d->S[b].v[i] * a;
+    }
+}
+
+/* Jacobian row of "velocity of the point r on `body` along n" (body < 0: static, contributes nothing) */
+static void jac_point(const Model* m, const Kin* k, const Dyn* d, int body, v3 r, v3 n, double sign, double* J) {
+    if (body < 0) return;
+    const AvgBody* B = &m->body[body];
+    if (B->jtype == AVG_JOINT_FREE) {
+        v3 rn = vcross(vsub(r, k->p[body]), n);
+        J[B->dof + 0] += sign * n.x; J[B->dof + 1] += sign * n.y; J[B->dof + 2] += sign * n.z;
+        J[B->dof + 3] += sign * rn.x; J[B->dof + 4] += sign * rn.y; J[B->dof + 5] += sign * rn.z;
+        return;
+    }
+    sv f = sv_make(vcross(r, n), n);
+    for (int b = body; b >= 0; b = m->body[b].parent) J[m->body[b].dof] += sign * sv_dot(&d->S[b], &f);
+}
+static void jac_ang(const Model* m, const Dyn* d, int body, v3 n, double sign, double* J) {
+    if (body < 0) return;
+    const AvgBody* B = &m->body[body];
+    if (B->jtype == AVG_JOINT_FREE) { J[B->dof + 3] += sign * n.x; J[B->dof + 4] += sign * n.y; J[B->dof + 5] += sign * n.z; return; }
+    sv f = sv_make(n, V(0, 0, 0));
+    for (int b = body; b >= 0; b = m->body[b].parent) J[m->body[b].dof] += sign * sv_dot(&d->S[b], &f);
+}
+
+typedef struct {
+    double J[MAXD], W[MAXD];
+    double target;       /* desired change of J.v */
+    double lo, hi;
+    double diag, lambda;
+    int friction_of;     /* row index of the normal row for friction rows, else -1 */
+    double mu;
+} Row;
+
+static double limit_lo(const AvgDof* D, const double* env) { return (D->flags & AVG_DOF_HUMAN) ? D->lower * env[AVG_E_LIMIT_SCALE] : D->lower; }
+static double limit_hi(const AvgDof* D, const double* env) { return (D->flags & AVG_DOF_HUMAN) ? D->upper * env[AVG_E_LIMIT_SCALE] : D->upper; }
+
+static void finish_row(const Model* m, const Dyn* d, const double* qd, Row* r) {
+    aba_delta(m, d, r->J, r->W);
+    double diag = 0, u0 = 0;
+    for (int i = 0; i < m->h->n_dof; ++i) { diag += r->J[i] * r->W[i]; u0 += r->J[i] * qd[i]; }
+    r->diag = diag; r->lambda = 0;
+    r->target -= u0;
+}
+
+/* one physics sub-step = p.stepSimulation() with numSubSteps=0 (scratch_itch.py:258) */
+static void substep(const Model* m, double* env, Contact* contacts, int* ncontact) {
+    const AvgModelHeader* h = m->h;
+    int nd = h->n_dof, nb = h->n_body;
+    double dt = h->dt;
+    Kin k; Dyn* d = (Dyn*)malloc(sizeof(Dyn));
+    fk(m, env, &k);
+    int overflow = 0;
+    int nc = collide(m, &k, contacts, &overflow);
+    /* unconstrained velocity update */
+    double qdd[MAXD], qd[MAXD];
+    aba(m, &k, env, d, qdd);
+    for (int i = 0; i < nd; ++i) {
+        qd[i] = env[AVG_E_QD + i] + dt * qdd[i];
+    }
+    /* constraint rows, Bullet order: non-contact (motors, limits, fixed constraint), contact normals, friction */
+    Row* rows = (Row*)calloc(MAXR, sizeof(Row));
+    int nr = 0;
+    for (int i = 0; i < h->n_jdof; ++i) {          /* position motors, btMultiBodyJointMotor [UPSTREAM-BULLET] */
+        const AvgDof* D = &m->dof[i];
+        if (!(D->flags & AVG_DOF_MOTOR)) continue;
+        Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+        double kp = (D->flags & AVG_DOF_HUMAN) ? env[AVG_E_HUMAN_KP] : D->kp;
+        double maxf = (D->flags & AVG_DOF_HUMAN) ? h->task_f[AVG_TF_HUMAN_FORCE] * env[AVG_E_STRENGTH] : D->max_force;
+        double q = env[AVG_E_Q + m->body[D->body].qidx];
+        r->J[i] = 1.0;
+        r->target = kp * (env[AVG_E_MTARGET + i] - q) / dt + (1.0 - D->kd) * qd[i];   /* desired velocity */
+        r->lo = -maxf * dt; r->hi = maxf * dt; r->friction_of = -1;
+        finish_row(m, d, qd, r);
+    }
+    for (int i = 0; i < h->n_jdof; ++i) {          /* joint limits, only while violated [UPSTREAM-BULLET] */
+        const AvgDof* D = &m->dof[i];
+        if (!(D->flags & AVG_DOF_LIMIT)) continue;
+        double q = env[AVG_E_Q + m->body[D->body].qidx];
+        double pen[2] = {q - limit_lo(D, env), limit_hi(D, env) - q};
+        for (int s = 0; s < 2; ++s) {
+            if (pen[s] > 0 || nr >= MAXR) continue;
+            Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+            r->J[i] = s ? -1.0 : 1.0;
+            r->target = -pen[s] * h->erp / dt;
+            r->lo = 0; r->hi = 100.0; r->friction_of = -1;
+            finish_row(m, d, qd, r);
+        }
+    }
+    {                                               /* tool weld: btMultiBodyFixedConstraint, 6 rows */
+        v3 pa, pb; quat qa, qb;
+        frame_pose(m, &k, AVG_F_WELD_PARENT, &pa, &qa);
+        frame_pose(m, &k, AVG_F_TOOL_BASE, &pb, &qb);
+        quat dq = qmul(qa, qconj(qb));
+        if (dq.w < 0) { dq.x = -dq.x; dq.y = -dq.y; dq.z = -dq.z; dq.w = -dq.w; }
+        double s = sqrt(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
+        v3 rotv = V(0, 0, 0);
+        if (s > 1e-12) { double ang = 2.0 * atan2(s, dq.w); rotv = V(dq.x / s * ang, dq.y / s * ang, dq.z / s * ang); }
+        v3 perr = vsub(pa, pb);
+        double maxi = h->weld_max_force * dt;
+        for (int ax = 0; ax < 6 && nr < MAXR; ++ax) {
+            Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+            v3 e = V(ax % 3 == 0, ax % 3 == 1, ax % 3 == 2);
+            if (ax < 3) {
+                jac_point(m, &k, d, h->weld_body_a, pa, e, 1.0, r->J);
+                jac_point(m, &k, d, h->weld_body_b, pb, e, -1.0, r->J);
+                r->target = -vdot(perr, e) * h->erp / dt;
+            } else {
+                jac_ang(m, d, h->weld_body_a, e, 1.0, r->J);
+                jac_ang(m, d, h->weld_body_b, e, -1.0, r->J);
+                r->target = -vdot(rotv, e) * h->erp / dt;
+            }
+            r->lo = -maxi; r->hi = maxi; r->friction_of = -1;
+            finish_row(m, d, qd, r);
+        }
+    }
+    if (nc > (MAXR - nr) / 2) { overflow |= 2; nc = (MAXR - nr) / 2; }      /* flagged, never silent */
+    int first_contact_row = nr;
+    for (int c = 0; c < nc; ++c) {                  /* contact normals */
+        Contact* C = &contacts[c];
+        Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+        jac_point(m, &k, d, m->shape[C->sa].body, C->pa, C->n, 1.0, r->J);
+        jac_point(m, &k, d, m->shape[C->sb].body, C->pb, C->n, -1.0, r->J);
+        r->target = (C->dist > 0) ? -C->dist / dt : -C->dist * h->erp / dt;
+        r->lo = 0; r->hi = 1e30; r->friction_of = -1;
+        finish_row(m, d, qd, r);
+    }
+    for (int c = 0; c < nc; ++c) {                  /* one friction direction per contact [UPSTREAM-BULLET default] */
+        Contact* C = &contacts[c];
+        Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+        /* lateral relative velocity of the contact points before the solve */
+        double Jx[3][MAXD]; memset(Jx, 0, sizeof(Jx));
+        v3 vrel;
+        for (int ax = 0; ax < 3; ++ax) {
+            v3 e = V(ax == 0, ax == 1, ax == 2);
+            jac_point(m, &k, d, m->shape[C->sa].body, C->pa, e, 1.0, Jx[ax]);
+            jac_point(m, &k, d, m->shape[C->sb].body, C->pb, e, -1.0, Jx[ax]);
+        }
+        double vr[3] = {0, 0, 0};
+        for (int ax = 0; ax < 3; ++ax) for (int i = 0; i < nd; ++i) vr[ax] += Jx[ax][i] * qd[i];
+        vrel = V(vr[0], vr[1], vr[2]);
+        v3 lat = vsub(vrel, vscale(C->n, vdot(vrel, C->n)));
+        double ll = vnorm(lat);
+        v3 t;
+        if (ll > 1e-6) t = vscale(lat, 1.0 / ll);
+        else {                                      /* btPlaneSpace1 */
+            if (fabs(C->n.z) > 0.7071067811865476) { double a = C->n.y * C->n.y + C->n.z * C->n.z, kk = 1.0 / sqrt(a); t = V(0, -C->n.z * kk, C->n.y * kk); }
+            else { double a = C->n.x * C->n.x + C->n.y * C->n.y, kk = 1.0 / sqrt(a); t = V(-C->n.y * kk, C->n.x * kk, 0); }
+        }
+        for (int i = 0; i < nd; ++i) r->J[i] = t.x * Jx[0][i] + t.y * Jx[1][i] + t.z * Jx[2][i];
+        r->target = 0; r->lo = 0; r->hi = 0; r->friction_of = first_contact_row + c;
+        r->mu = (double)m->shape[C->sa].friction * (double)m->shape[C->sb].friction;
+        finish_row(m, d, qd, r);
+    }
+    /* projected Gauss-Seidel in velocity space, as btMultiBodyConstraintSolver */
+    double dv[MAXD]; memset(dv, 0, sizeof(dv));
+    for (int it = 0; it < h->solver_iters; ++it) {
+        double resid = 0;
+        for (int ri = 0; ri < nr; ++ri) {
+            Row* r = &rows[ri];
+            if (r->diag < 1e-12) continue;
+            double lo = r->lo, hi = r->hi;
+            if (r->friction_of >= 0) { double lim = r->mu * rows[r->friction_of].lambda; lo = -lim; hi = lim; }
+            double jdv = 0; for (int i = 0; i < nd; ++i) jdv += r->J[i] * dv[i];
+            double delta = (r->target - jdv) / r->diag;
+            double sum = r->lambda + delta;
+            if (sum < lo) sum = lo; if (sum > hi) sum = hi;
+            delta = sum - r->lambda; r->lambda = sum;
+            for (int i = 0; i < nd; ++i) dv[i] += r->W[i] * delta;
+            double rv = delta * r->diag; if (rv * rv > resid) resid = rv * rv;
+        }
+        if (resid <= h->residual_thr) break;
+    }
+    for (int c = 0; c < nc; ++c) contacts[c].lambda_n = rows[first_contact_row + c].lambda;
+    *ncontact = nc;
+    /* integrate (btMultiBody::stepPositionsMultiDof): semi-implicit Euler */
+    for (int i = 0; i < nd; ++i) {
+        double v = qd[i] + dv[i];
+        if (i < h->n_jdof) { if (v > h->max_vel) v = h->max_vel; if (v < -h->max_vel) v = -h->max_vel; }
+        env[AVG_E_QD + i] = v;
+    }
+    for (int b = 0; b < nb; ++b) {
+        const AvgBody* B = &m->body[b];
+        if (B->jtype == AVG_JOINT_FREE) {
+            double* q = env + AVG_E_Q + B->qidx; const double* v = env + AVG_E_QD + B->dof;
+            q[0] += dt * v[0]; q[1] += dt * v[1]; q[2] += dt * v[2];
+            v3 w = V(v[3], v[4], v[5]); double wn = vnorm(w);
+            quat cur = {q[3], q[4], q[5], q[6]};
+            if (wn * dt > 1e-12) cur = qmul(qaxis(vscale(w, 1.0 / wn), wn * dt), cur);
+            cur = qnormalize(cur);
+            q[3] = cur.x; q[4] = cur.y; q[5] = cur.z; q[6] = cur.w;
+        } else env[AVG_E_Q + B->qidx] += dt * env[AVG_E_QD + B->dof];
+    }
+    if (overflow) env[AVG_E_OVERFLOW] = (double)((int)env[AVG_E_OVERFLOW] | overflow);
+    free(rows); free(d);
+}
+
+/* env.py:389-410 */
+static void enforce_hard_limits(const Model* m, double* env) {
+    for (int i = 0; i < m->h->n_jdof; ++i) {
+        const AvgDof* D = &m->dof[i];
+        if (!(D->flags & AVG_DOF_HARD_LIMIT)) continue;
+        double* q = &env[AVG_E_Q + m->body[D->body].qidx];
+        double lo = limit_lo(D, env), hi = limit_hi(D, env);
+        if (*q < lo) { *q = lo; env[AVG_E_QD + i] = 0; }
+        else if (*q > hi) { *q = hi; env[AVG_E_QD + i] = 0; }
+    }
+}
+
+/* scratch_itch.py:289-293 */
+static void update_target(const Model* m, double* env) {
+    Kin k; fk(m, env, &k);
+    v3 p; quat q;
+    frame_pose(m, &k, (int)env[AVG_E_LIMB_FRAME], &p, &q);
+    v3 t = vadd(p, qrot(q, V(env[AVG_E_TARGET_ON_ARM], env[AVG_E_TARGET_ON_ARM + 1], env[AVG_E_TARGET_ON_ARM + 2])));
+    env[AVG_E_TARGET_POS] = t.x; env[AVG_E_TARGET_POS + 1] = t.y; env[AVG_E_TARGET_POS + 2] = t.z;
+}
+
+/* scratch_itch.py:104-128 */
+static void get_obs(const Model* m, const double* env, double tool_force, double total_force_on_human,
+                    double tool_force_at_target, double* obs) {
+    const AvgModelHeader* h = m->h;
+    Kin k; fk(m, env, &k);
+    v3 torso, tool, sh, el, wr, chest; quat tq, dummy;
+    frame_pose(m, &k, AVG_F_TORSO, &torso, &dummy);
+    frame_pose(m, &k, AVG_F_TOOL_TIP, &tool, &tq);
+    frame_pose(m, &k, AVG_F_SHOULDER, &sh, &dummy);
+    frame_pose(m, &k, AVG_F_ELBOW, &el, &dummy);
+    frame_pose(m, &k, AVG_F_WRIST, &wr, &dummy);
+    frame_pose(m, &k, AVG_F_CHEST, &chest, &dummy);
+    v3 tgt = V(env[AVG_E_TARGET_POS], env[AVG_E_TARGET_POS + 1], env[AVG_E_TARGET_POS + 2]);
+    int o = 0;
+#define PUT3(v) do { obs[o++] = (v).x; obs[o++] = (v).y; obs[o++] = (v).z; } while (0)
+    v3 t;
+    t = vsub(tool, torso); PUT3(t);
+    obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+    t = vsub(tool, tgt); PUT3(t);
+    t = vsub(tgt, torso); PUT3(t);
+    for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].action >= 0 && m->dof[i].action < h->n_action_robot) obs[o++] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+    t = vsub(sh, torso); PUT3(t);
+    t = vsub(el, torso); PUT3(t);
+    t = vsub(wr, torso); PUT3(t);
+    obs[o++] = tool_force;
+    if (h->human_control) {
+        t = vsub(tool, chest); PUT3(t);
+        obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+        t = vsub(tool, tgt); PUT3(t);
+        t = vsub(tgt, chest); PUT3(t);
+        double hq[10]; memset(hq, 0, sizeof(hq));
+        for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].human_slot >= 0) hq[m->dof[i].human_slot] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+        for (int i = 0; i < 10; ++i) obs[o++] = hq[i];
+        t = vsub(sh, chest); PUT3(t);
+        t = vsub(el, chest); PUT3(t);
+        t = vsub(wr, chest); PUT3(t);
+        obs[o++] = total_force_on_human; obs[o++] = tool_force_at_target;
+    }
+#undef PUT3
+}
+
+/* exported ---------------------------------------------------------------------------------------------------- */
+int avg_oracle_sizes(int* sizes) {
+    sizes[0] = (int)sizeof(AvgModelHeader); sizes[1] = (int)sizeof(AvgBody); sizes[2] = (int)sizeof(AvgDof);
+    sizes[3] = (int)sizeof(AvgShape); sizes[4] = (int)sizeof(AvgFrame); sizes[5] = (int)sizeof(AvgContact);
+    return 6;
+}
+
+/* initial observation, scratch_itch.py:268  (_get_obs([0],[0,0]) after generate_target) */
+int avg_oracle_reset_obs(const void* blob, double* env, double* obs) {
+    Model m; if (model_open(blob, &m)) return -1;
+    update_target(&m, env);
+    get_obs(&m, env, 0, 0, 0, obs);
+    return 0;
+}
+
+/* One env.step(action): take_step (env.py:274-351) + ScratchItchEnv.step (scratch_itch.py:53-82).
+ * out_info: [0] total_force_on_human, [1] task_success flag, [2] tool_force, [3] tool_force_at_target,
+ *           [4] reward_distance, [5] reward_action, [6] reward_force_scratch, [7] preferences_score
+ * contacts_out: AvgContactD records of the last sub-step (10 doubles each + 2 ints packed as doubles):
+ *           [sa, sb, pa(3), pb(3), n(3), dist, force] = 13 doubles */
+int avg_oracle_step(const void* blob, double* env, const float* action, double* obs, double* reward, double* out_info,
+                    double* contacts_out, int* ncontacts_out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    const AvgModelHeader* h = m.h;
+    int na = h->n_action_robot + h->n_action_human;
+    float act[64];
+    double raw_sq = 0;
+    for (int i = 0; i < na; ++i) {
+        float a = action[i];
+        raw_sq += (double)a * (double)a;                      /* reward_action uses the raw action, scratch_itch.py:64 */
+        if (a < -1.0f) a = -1.0f; if (a > 1.0f) a = 1.0f;      /* env.py:275 */
+        act[i] = a * h->action_scale;                         /* env.py:280 (float32 arithmetic like numpy) */
+    }
+    int human_active = h->human_control || env[AVG_E_TREMOR_ON] != 0.0;      /* env.py:307 */
+    /* robot targets, env.py:320-326 */
+    double ar[32], rpos[32]; int rdof[32], nrob = 0;
+    for (int i = 0; i < h->n_jdof; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) {
+        rdof[nrob] = i; ar[nrob] = act[m.dof[i].action]; rpos[nrob] = env[AVG_E_Q + m.body[m.dof[i].body].qidx]; nrob++;
+    }
+    /* human targets, env.py:307-318 */
+    double ah[10], hpos[10], hlo[10], hhi[10]; int hdof[10];
+    for (int s = 0; s < 10; ++s) { ah[s] = 0; hpos[s] = 0; hlo[s] = 0; hhi[s] = 0; hdof[s] = -1; }
+    if (human_active) {
+        for (int i = 0; i < h->n_jdof; ++i) if (m.dof[i].human_slot >= 0) {
+            int s = m.dof[i].human_slot; hdof[s] = i;
+            hpos[s] = env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+            hlo[s] = limit_lo(&m.dof[i], env); hhi[s] = limit_hi(&m.dof[i], env);
+        }
+        if (h->human_control) for (int s = 0; s < 10; ++s) ah[s] = act[h->n_action_robot + s];
+    }
+    for (int f = 0; f < h->substeps; ++f) {
+        for (int j = 0; j < nrob; ++j) {
+            const AvgDof* D = &m.dof[rdof[j]];
+            if (rpos[j] + ar[j] < D->rep_lower) ar[j] = 0;
+            if (rpos[j] + ar[j] > D->rep_upper) ar[j] = 0;
+            rpos[j] += ar[j];
+        }
+        if (human_active) {
+            for (int s = 0; s < 10; ++s) {
+                if (hpos[s] + ah[s] < hlo[s]) ah[s] = 0;
+                if (hpos[s] + ah[s] > hhi[s]) ah[s] = 0;
+            }
+            if (env[AVG_E_TREMOR_ON] != 0.0) {                 /* env.py:330-332 */
+                double sgn = (((int)env[AVG_E_ITERATION]) % 2 == 0) ? 1.0 : -1.0;
+                for (int s = 0; s < 10; ++s) {
+                    hpos[s] = env[AVG_E_TARGET_H + s] + env[AVG_E_TREMOR + s] * sgn;
+                    env[AVG_E_TARGET_H + s] += ah[s];
+                }
+            }
+            for (int s = 0; s < 10; ++s) hpos[s] += ah[s];
+        }
+    }
+    for (int j = 0; j < nrob; ++j) env[AVG_E_MTARGET + rdof[j]] = rpos[j];       /* env.py:335 */
+    if (human_active) {
+        for (int s = 0; s < 10; ++s) if (hdof[s] >= 0) env[AVG_E_MTARGET + hdof[s]] = hpos[s];   /* env.py:337 */
+        env[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
+    }
+    Contact contacts[MAXC]; int nc = 0;
+    for (int f = 0; f < h->substeps; ++f) {                    /* env.py:341-349 */
+        substep(&m, env, contacts, &nc);
+        /* enforce_realistic_human_joint_limits (env.py:353-387) is compiled in with the human-active variant */
+        enforce_hard_limits(&m, env);
+        update_target(&m, env);
+    }
+    env[AVG_E_ITERATION] += 1;                                 /* env.py:351 */
+
+    /* get_total_force, scratch_itch.py:84-102 */
+    double dt = h->dt;
+    double total_force_on_human = 0, tool_force = 0, tool_force_at_target = 0;
+    int have_tcp = 0; v3 tcp = V(0, 0, 0);
+    v3 tgt = V(env[AVG_E_TARGET_POS], env[AVG_E_TARGET_POS + 1], env[AVG_E_TARGET_POS + 2]);
+    for (int c = 0; c < nc; ++c) {
+        const AvgShape* sa = &m.shape[contacts[c].sa]; const AvgShape* sb = &m.shape[contacts[c].sb];
+        double force = contacts[c].lambda_n / dt;
+        int a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        int a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        int a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if (a_tool || b_tool) tool_force += force;
+        if ((a_tool && b_hum) || (b_tool && a_hum)) {
+            total_force_on_human += force;
+            int link_tool = a_tool ? sa->ref_link : sb->ref_link;
+            v3 pos_h = a_tool ? contacts[c].pb : contacts[c].pa;             /* positionOnB with B = human */
+            if (link_tool == 0 || link_tool == 1) {
+                if (vnorm(vsub(pos_h, tgt)) < h->task_f[AVG_TF_TARGET_RADIUS]) { tool_force_at_target += force; tcp = pos_h; have_tcp = 1; }
+            }
+        }
+        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;
+    }
+    /* end effector velocity: linear velocity of tool link 1 COM, scratch_itch.py:54 */
+    Kin k; fk(&m, env, &k);
+    v3 tip; quat tq; frame_pose(&m, &k, AVG_F_TOOL_TIP, &tip, &tq);
+    int tb = m.frame[AVG_F_TOOL_TIP].body;
+    const double* tv = env + AVG_E_QD + m.body[tb].dof;
+    v3 vt = vadd(V(tv[0], tv[1], tv[2]), vcross(V(tv[3], tv[4], tv[5]), vsub(tip, k.p[tb])));
+    double ee_vel = vnorm(vt);
+    get_obs(&m, env, tool_force, total_force_on_human, tool_force_at_target, obs);
+    /* human_preferences, env.py:412-448 (scratch itch terms) */
+    const float* tf = h->task_f;
+    double pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_at_target))
+                + tf[AVG_TF_C_HF] * (tool_force_at_target < tf[AVG_TF_FORCE_CAP] ? 0.0 : -tool_force_at_target);
+    double reward_distance = -vnorm(vsub(tgt, tip));
+    double reward_action = -raw_sq;
+    double reward_force_scratch = 0;
+    v3 prev = V(env[AVG_E_PREV_CONTACT], env[AVG_E_PREV_CONTACT + 1], env[AVG_E_PREV_CONTACT + 2]);
+    if (have_tcp && vnorm(vsub(tcp, prev)) > tf[AVG_TF_SCRATCH_MOVE] && tool_force_at_target < tf[AVG_TF_FORCE_CAP]) {
+        reward_force_scratch = tool_force_at_target;
+        env[AVG_E_PREV_CONTACT] = tcp.x; env[AVG_E_PREV_CONTACT + 1] = tcp.y; env[AVG_E_PREV_CONTACT + 2] = tcp.z;
+        env[AVG_E_TASK_SUCCESS] += 1;
+    }
+    *reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
+            + tf[AVG_TF_TOOL_FORCE_W] * tool_force_at_target + tf[AVG_TF_SCRATCH_W] * reward_force_scratch + pref;
+    env[AVG_E_EPISODE_RETURN] += *reward;
+    if (out_info) {
+        out_info[0] = total_force_on_human; out_info[1] = env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0 : 0.0;
+        out_info[2] = tool_force; out_info[3] = tool_force_at_target; out_info[4] = reward_distance;
+        out_info[5] = reward_action; out_info[6] = reward_force_scratch; out_info[7] = pref;
+    }
+    if (contacts_out && ncontacts_out) {
+        *ncontacts_out = nc;
+        for (int c = 0; c < nc; ++c) {
+            double* o = contacts_out + 13 * c;
+            o[0] = contacts[c].sa; o[1] = contacts[c].sb;
+            o[2] = contacts[c].pa.x; o[3] = contacts[c].pa.y; o[4] = contacts[c].pa.z;
+            o[5] = contacts[c].pb.x; o[6] = contacts[c].pb.y; o[7] = contacts[c].pb.z;
+            o[8] = contacts[c].n.x; o[9] = contacts[c].n.y; o[10] = contacts[c].n.z;
+            o[11] = contacts[c].dist; o[12] = contacts[c].lambda_n / dt;
+        }
+    }
+    return 0;
+}
+
+/* --- unit-test hooks (tests/test_oracle_*.py) ------------------------------------------------------------------ */
+/* forward kinematics of frame f -> pos(3), quat(4) */
+int avg_oracle_frame(const void* blob, const double* env, int f, double* out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Kin k; fk(&m, env, &k);
+    v3 p; quat q; frame_pose(&m, &k, f, &p, &q);
+    out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = q.x; out[4] = q.y; out[5] = q.z; out[6] = q.w;
+    return 0;
+}
+int avg_oracle_body_pose(const void* blob, const double* env, int b, double* out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Kin k; fk(&m, env, &k);
+    out[0] = k.p[b].x; out[1] = k.p[b].y; out[2] = k.p[b].z; out[3] = k.q[b].x; out[4] = k.q[b].y; out[5] = k.q[b].z; out[6] = k.q[b].w;
+    return 0;
+}
+/* unconstrained accelerations (ABA) and, column by column, M^-1 (n_dof x n_dof, row-major) */
+int avg_oracle_dynamics(const void* blob, const double* env, double* qdd, double* minv) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Kin k; fk(&m, env, &k);
+    Dyn* d = (Dyn*)malloc(sizeof(Dyn));
+    aba(&m, &k, env, d, qdd);
+    int nd = m.h->n_dof;
+    if (minv) for (int j = 0; j < nd; ++j) {
+        double tau[MAXD], col[MAXD]; memset(tau, 0, sizeof(tau)); tau[j] = 1.0;
+        aba_delta(&m, d, tau, col);
+        for (int i = 0; i < nd; ++i) minv[i * nd + j] = col[i];
+    }
+    free(d);
+    return 0;
+}
+/* contacts at the current configuration (no stepping) */
+int avg_oracle_collide(const void* blob, const double* env, double* contacts_out, int* ncontacts_out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Kin k; fk(&m, env, &k);
+    Contact contacts[MAXC]; int overflow = 0;
+    int nc = collide(&m, &k, contacts, &overflow);
+    *ncontacts_out = nc;
+    for (int c = 0; c < nc; ++c) {
+        double* o = contacts_out + 13 * c;
+        o[0] = contacts[c].sa; o[1] = contacts[c].sb;
+        o[2] = contacts[c].pa.x; o[3] = contacts[c].pa.y; o[4] = contacts[c].pa.z;
+        o[5] = contacts[c].pb.x; o[6] = contacts[c].pb.y; o[7] = contacts[c].pb.z;
+        o[8] = contacts[c].n.x; o[9] = contacts[c].n.y; o[10] = contacts[c].n.z;
+        o[11] = contacts[c].dist; o[12] = 0;
+    }
+    return overflow;
+}
+/* closest points between two shapes given explicit world poses (GJK unit tests): pose = pos(3)+quat(4) */
+int avg_oracle_shape_pair(const void* blob, int sa, const double* pose_a, int sb, const double* pose_b, double thr, double* out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    WShape A, B;
+    A.s = &m.shape[sa]; A.verts = m.vert + 3 * A.s->vert_off; A.planes = m.plane + 4 * A.s->plane_off;
+    B.s = &m.shape[sb]; B.verts = m.vert + 3 * B.s->vert_off; B.planes = m.plane + 4 * B.s->plane_off;
+    quat qa = {pose_a[3], pose_a[4], pose_a[5], pose_a[6]}, qb = {pose_b[3], pose_b[4], pose_b[5], pose_b[6]};
+    A.p = V(pose_a[0], pose_a[1], pose_a[2]); A.R = qmat(qnormalize(qa));
+    B.p = V(pose_b[0], pose_b[1], pose_b[2]); B.R = qmat(qnormalize(qb));
+    Contact c;
+    int hit = narrowphase(&A, &B, thr, &c);
+    if (hit) {
+        out[0] = c.pa.x; out[1] = c.pa.y; out[2] = c.pa.z; out[3] = c.pb.x; out[4] = c.pb.y; out[5] = c.pb.z;
+        out[6] = c.n.x; out[7] = c.n.y; out[8] = c.n.z; out[9] = c.dist;
+    }
+    return hit;
+}

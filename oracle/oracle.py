@@ -1,0 +1,123 @@
+"""ctypes wrapper of the CPU oracle (oracle/avg_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — may be imported from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs, never from the product package. PARITY UNPINNED (see the header of avg_oracle.c).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libavg_oracle.so")
+ENV_STRIDE = 192
+INT_SLOTS = (123, 152, 161, 166)     # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
+_DP = ctypes.POINTER(ctypes.c_double)
+_FP = ctypes.POINTER(ctypes.c_float)
+_IP = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "avg_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+def env_to_f64(env_f32: np.ndarray) -> np.ndarray:
+    """float32 device record (ints bit-cast) -> float64 oracle record (ints as numbers)."""
+    env_f32 = np.ascontiguousarray(env_f32, dtype=np.float32)
+    out = env_f32.astype(np.float64)
+    iv = env_f32.view(np.int32)
+    for s in INT_SLOTS:
+        out[..., s] = iv[..., s]
+    return out
+
+
+def env_to_f32(env_f64: np.ndarray) -> np.ndarray:
+    out = env_f64.astype(np.float32)
+    iv = out.view(np.int32)
+    for s in INT_SLOTS:
+        iv[..., s] = np.rint(env_f64[..., s]).astype(np.int32)
+    return out
+
+
+class Oracle:
+    def __init__(self, blob: bytes):
+        self.lib = ctypes.CDLL(build())
+        self.blob = ctypes.create_string_buffer(blob, len(blob))
+        from assistive_vr_gym_b200.compiler.blob import read_blob
+        self.model = read_blob(blob)
+        h = self.model["header"]
+        self.n_obs = int(h["n_obs_robot"] + h["n_obs_human"])
+        self.n_act = int(h["n_action_robot"] + h["n_action_human"])
+        self.n_dof = int(h["n_dof"])
+        L = self.lib
+        L.avg_oracle_step.restype = ctypes.c_int
+        L.avg_oracle_step.argtypes = [ctypes.c_void_p, _DP, _FP, _DP, _DP, _DP, _DP, _IP]
+        L.avg_oracle_reset_obs.argtypes = [ctypes.c_void_p, _DP, _DP]
+        L.avg_oracle_frame.argtypes = [ctypes.c_void_p, _DP, ctypes.c_int, _DP]
+        L.avg_oracle_body_pose.argtypes = [ctypes.c_void_p, _DP, ctypes.c_int, _DP]
+        L.avg_oracle_dynamics.argtypes = [ctypes.c_void_p, _DP, _DP, _DP]
+        L.avg_oracle_collide.argtypes = [ctypes.c_void_p, _DP, _DP, _IP]
+        L.avg_oracle_shape_pair.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP, ctypes.c_int, _DP, ctypes.c_double, _DP]
+        L.avg_oracle_sizes.argtypes = [_IP]
+
+    def sizes(self):
+        a = (ctypes.c_int * 8)()
+        n = self.lib.avg_oracle_sizes(a)
+        return list(a)[:n]
+
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(_DP)
+
+    def reset_obs(self, env: np.ndarray) -> np.ndarray:
+        obs = np.zeros(self.n_obs)
+        assert self.lib.avg_oracle_reset_obs(self.blob, self._dp(env), self._dp(obs)) == 0
+        return obs
+
+    def step(self, env: np.ndarray, action: np.ndarray):
+        """env: float64 [ENV_STRIDE] (modified in place). -> obs, reward, info[8], contacts[n,13]"""
+        assert env.dtype == np.float64 and env.flags.c_contiguous
+        act = np.ascontiguousarray(action, dtype=np.float32)
+        obs = np.zeros(self.n_obs)
+        rew = np.zeros(1)
+        info = np.zeros(8)
+        cont = np.zeros((16, 13))
+        nc = ctypes.c_int(0)
+        rc = self.lib.avg_oracle_step(self.blob, self._dp(env), act.ctypes.data_as(_FP), self._dp(obs), self._dp(rew),
+                                      self._dp(info), self._dp(cont), ctypes.byref(nc))
+        assert rc == 0
+        return obs, float(rew[0]), info, cont[:nc.value].copy()
+
+    def frame(self, env, f):
+        out = np.zeros(7)
+        self.lib.avg_oracle_frame(self.blob, self._dp(env), f, self._dp(out))
+        return out
+
+    def body_pose(self, env, b):
+        out = np.zeros(7)
+        self.lib.avg_oracle_body_pose(self.blob, self._dp(env), b, self._dp(out))
+        return out
+
+    def dynamics(self, env):
+        qdd = np.zeros(32)
+        minv = np.zeros((self.n_dof, self.n_dof))
+        self.lib.avg_oracle_dynamics(self.blob, self._dp(env), self._dp(qdd), self._dp(minv))
+        return qdd[:self.n_dof], minv
+
+    def collide(self, env):
+        cont = np.zeros((16, 13))
+        nc = ctypes.c_int(0)
+        self.lib.avg_oracle_collide(self.blob, self._dp(env), self._dp(cont), ctypes.byref(nc))
+        return cont[:nc.value].copy()
+
+    def shape_pair(self, sa, pose_a, sb, pose_b, thr=1e9):
+        out = np.zeros(10)
+        pa = np.ascontiguousarray(pose_a, dtype=np.float64); pb = np.ascontiguousarray(pose_b, dtype=np.float64)
+        hit = self.lib.avg_oracle_shape_pair(self.blob, sa, self._dp(pa), sb, self._dp(pb), float(thr), self._dp(out))
+        return hit, out
