@@ -1,0 +1,150 @@
+"""ctypes binding of the C-ABI in include/avg_b200.h (libavg_b200.so).
+
+This is the same stub a maintainer of the reference would add in place of `import pybullet as p` on the step path
+(INTEGRATION.md).  It fails loudly when the CUDA library is missing or no GPU is present: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavg_b200.so")
+
+EXPORTS = [
+    "avg_create", "avg_destroy", "avg_last_error", "avg_upload_model", "avg_set_state", "avg_get_state",
+    "avg_state_device_ptr", "avg_reset_obs", "avg_step", "avg_step_host", "avg_enable_debug", "avg_get_contacts",
+    "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
+    "avg_bytes_per_env_step",
+]
+
+CONTACT_DT = np.dtype([("shape_a", "<i4"), ("shape_b", "<i4"), ("pos_a", "<f4", 3), ("pos_b", "<f4", 3),
+                       ("normal", "<f4", 3), ("dist", "<f4"), ("force", "<f4"), ("pad", "<i4", 3)])
+assert CONTACT_DT.itemsize == 64
+MAX_CONTACT = 12
+
+
+class AvgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise AvgError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        from .build import build
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ip, fp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
+    lib.avg_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.avg_destroy.argtypes = [vp]
+    lib.avg_last_error.argtypes = [vp]; lib.avg_last_error.restype = ctypes.c_char_p
+    lib.avg_upload_model.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    lib.avg_set_state.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.avg_get_state.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_state_device_ptr.argtypes = [vp]; lib.avg_state_device_ptr.restype = vp
+    lib.avg_reset_obs.argtypes = [vp, vp, vp]
+    lib.avg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.avg_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.avg_enable_debug.argtypes = [vp, ctypes.c_int]
+    lib.avg_get_contacts.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.avg_get_reward_terms.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    for f in ("avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_bytes_per_env_step"):
+        getattr(lib, f).argtypes = [vp]
+    lib.avg_env_stride.argtypes = []
+    lib.avg_launch_count.argtypes = [vp]; lib.avg_launch_count.restype = ctypes.c_longlong
+    _lib = lib
+    return lib
+
+
+class Sim:
+    """Thin object wrapper of one AvgHandle (one GPU)."""
+
+    def __init__(self, n_env: int, device: int = 0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.avg_create(device, n_env, ctypes.byref(self.h))
+        if rc != 0:
+            raise AvgError(f"avg_create failed ({rc}): {self.lib.avg_last_error(None).decode()}")
+        self.n_env = n_env
+        self.device = device
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise AvgError(f"{what} failed ({rc}): {self.lib.avg_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.avg_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_model(self, variant: int, blob: bytes):
+        self._check(self.lib.avg_upload_model(self.h, variant, blob, len(blob)), "avg_upload_model")
+
+    def set_state(self, env: np.ndarray, variants: np.ndarray | None = None, begin: int = 0):
+        env = np.ascontiguousarray(env, dtype=np.float32)
+        v = None if variants is None else np.ascontiguousarray(variants, dtype=np.int32)
+        self._check(self.lib.avg_set_state(self.h, begin, env.shape[0], env.ctypes.data, None if v is None else v.ctypes.data),
+                    "avg_set_state")
+
+    def get_state(self, begin: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_env - begin if count is None else count
+        out = np.zeros((count, self.lib.avg_env_stride()), dtype=np.float32)
+        self._check(self.lib.avg_get_state(self.h, begin, count, out.ctypes.data), "avg_get_state")
+        return out
+
+    def reset_obs(self, obs_ptr: int, stream: int = 0):
+        self._check(self.lib.avg_reset_obs(self.h, obs_ptr, stream), "avg_reset_obs")
+
+    def step(self, act_ptr: int, obs_ptr: int, rew_ptr: int, done_ptr: int, info_ptr: int, stream: int = 0):
+        self._check(self.lib.avg_step(self.h, act_ptr, obs_ptr, rew_ptr, done_ptr, info_ptr, stream), "avg_step")
+
+    def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray, info: np.ndarray):
+        self._check(self.lib.avg_step_host(self.h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                           done.ctypes.data, info.ctypes.data), "avg_step_host")
+
+    def enable_debug(self, on: bool = True):
+        self._check(self.lib.avg_enable_debug(self.h, int(on)), "avg_enable_debug")
+
+    def get_contacts(self, begin: int = 0, count: int | None = None):
+        count = self.n_env - begin if count is None else count
+        c = np.zeros((count, MAX_CONTACT), dtype=CONTACT_DT)
+        n = np.zeros(count, dtype=np.int32)
+        self._check(self.lib.avg_get_contacts(self.h, begin, count, c.ctypes.data, n.ctypes.data), "avg_get_contacts")
+        return c, n
+
+    def get_reward_terms(self, begin: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_env - begin if count is None else count
+        t = np.zeros((count, 8), dtype=np.float32)
+        self._check(self.lib.avg_get_reward_terms(self.h, begin, count, t.ctypes.data), "avg_get_reward_terms")
+        return t
+
+    @property
+    def n_actions(self) -> int:
+        return self.lib.avg_num_actions(self.h)
+
+    @property
+    def n_obs(self) -> int:
+        return self.lib.avg_num_obs(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.avg_launch_count(self.h))
+
+    @property
+    def bytes_per_env_step(self) -> int:
+        return int(self.lib.avg_bytes_per_env_step(self.h))

@@ -84,105 +84,101 @@ def ik_dls(mb: MultiBodyDesc, ee_link: int, joints: List[int], lower, upper, tar
     return q, float(np.linalg.norm(target_pos - p)), float(min(dq1, dq2))
 
 
-class ScratchItchReset:
-    """Sampler of post-reset states for a list of compiled scenes (one per gender variant)."""
+def build_reset_data(scene: CompiledScene, rng: np.random.RandomState, ik_pool: int = 32) -> dict:
+    """Everything `sample_states` needs, as plain arrays (so it can run where the reference assets are absent).
 
-    def __init__(self, scenes: Dict[str, CompiledScene], seed: int = 1001, ik_pool: int = 32):
-        self.scenes = scenes
-        self.rng = np.random.RandomState(seed)
-        self.ik_pool_size = ik_pool
-        self._pool = None
+    Robot start poses: `scratch_itch.py:251-253` + `util.py:34-57` (IK with up to 40 random restarts, accepted when
+    position error and quaternion distance are < 0.03); the tool pose follows from `world_creation.py:331-337`.
+    """
+    robot, human = scene.multibodies[0], scene.multibodies[1]
+    joints = scene.robot_arm_joints
+    lower = np.array([robot.links[j].lower for j in joints])
+    upper = np.array([robot.links[j].upper for j in joints])
+    target_quat = X.quat_from_euler([0, np.pi / 2.0, 0])
+    pool_q, pool_tool = [], []
+    at = scene.attach[2][-1]
+    ip, iq = X.tf_inv(at.pos, at.quat)
+    while len(pool_q) < ik_pool:
+        target_pos = np.array([-0.5, 0, 0.8]) + rng.uniform(-0.05, 0.05, size=3)
+        best = None
+        for _ in range(40):                                            # max_ik_random_restarts
+            rest = rng.uniform(np.maximum(lower, -np.pi), np.minimum(upper, np.pi))
+            q, ep, eq = ik_dls(robot, 8, joints, lower, upper, target_pos, target_quat, rest)
+            if ep < 0.03 and eq < 0.03:                                # random_restart_threshold
+                best = q
+                break
+            if best is None:
+                best = q
+        qrob = {j: float(best[k]) for k, j in enumerate(joints)}
+        for j in (9, 11, 13):
+            qrob[j] = 1.0                                              # gripper open position, scratch_itch.py:254
+        ee_p, ee_q = robot.com_frames(qrob)[8]
+        base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
+        bp, bq = X.tf_mul(base_p, base_q, ip, iq)
+        pool_q.append(np.asarray(best)); pool_tool.append(np.concatenate([bp, bq]))
+    arm_qidx, arm_dof, fin_qidx, fin_dof, hum_qidx, hum_dof, hum_joint = [], [], [], [], [], [], []
+    tool_qidx = -1
+    for b in scene.bodies:
+        if b.art == 0 and b.jtype != 2:
+            if b.ref_joint in joints:
+                arm_qidx.append(b.qidx); arm_dof.append(b.dof)
+            else:
+                fin_qidx.append(b.qidx); fin_dof.append(b.dof)
+        elif b.art == 1:
+            hum_qidx.append(b.qidx); hum_dof.append(b.dof); hum_joint.append(b.ref_joint)
+        elif b.art == 2:
+            tool_qidx = b.qidx
+    hum_lower = np.array([human.links[j].lower for j in hum_joint])
+    hum_upper = np.array([human.links[j].upper for j in hum_joint])
+    hum_reset = np.array([scene.q_human_reset.get(j, 0.0) for j in hum_joint])
+    limb = human.dims["limb_dims"]
+    return dict(pool_q=np.asarray(pool_q), pool_tool=np.asarray(pool_tool), arm_qidx=np.asarray(arm_qidx),
+                arm_dof=np.asarray(arm_dof), fin_qidx=np.asarray(fin_qidx), fin_dof=np.asarray(fin_dof),
+                hum_qidx=np.asarray(hum_qidx), hum_dof=np.asarray(hum_dof), hum_joint=np.asarray(hum_joint),
+                hum_lower=hum_lower, hum_upper=hum_upper, hum_reset=hum_reset, tool_qidx=np.asarray(tool_qidx),
+                limb_dims=np.array([limb[9], limb[11]]), human_control=np.asarray(int(scene.human_control)))
 
-    # -- robot start pose pool (scratch_itch.py:251-253, util.py:34-57) --------------------------------------
-    def _build_pool(self):
-        scene = next(iter(self.scenes.values()))
-        robot = scene.multibodies[0]
-        joints = scene.robot_arm_joints
-        lower = np.array([robot.links[j].lower for j in joints])
-        upper = np.array([robot.links[j].upper for j in joints])
-        target_quat = X.quat_from_euler([0, np.pi / 2.0, 0])
-        pool = []
-        while len(pool) < self.ik_pool_size:
-            target_pos = np.array([-0.5, 0, 0.8]) + self.rng.uniform(-0.05, 0.05, size=3)
-            best = None
-            for _ in range(40):                                            # max_ik_random_restarts
-                rest = self.rng.uniform(np.maximum(lower, -np.pi), np.minimum(upper, np.pi))
-                q, ep, eq = ik_dls(robot, 8, joints, lower, upper, target_pos, target_quat, rest)
-                if ep < 0.03 and eq < 0.03:                                # random_restart_threshold
-                    best = q
-                    break
-                if best is None:
-                    best = q
-            pool.append(np.asarray(best))
-        self._pool = np.asarray(pool)
 
-    def sample(self, n: int, genders: List[str] | None = None) -> Tuple[np.ndarray, np.ndarray]:
-        """-> (env records [n, ENV_STRIDE] float32 with int fields bit-cast, variant index [n] int32)."""
-        if self._pool is None:
-            self._build_pool()
-        names = list(self.scenes.keys())
-        rng = self.rng
-        env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
-        env_i = env.view(np.int32)
-        variant = np.zeros(n, dtype=np.int32)
-        for e in range(n):
-            g = genders[e] if genders is not None else names[rng.randint(len(names))]      # scratch_itch.py:156
-            variant[e] = names.index(g)
-            sc = self.scenes[g]
-            robot, human, tool = sc.multibodies[0], sc.multibodies[1], sc.multibodies[2]
-            impairment = ["none", "limits", "weakness", "tremor"][rng.randint(4)]          # world_creation.py:67
-            limit_scale = rng.uniform(0.5, 1.0) if impairment == "limits" else 1.0           # :71
-            strength = rng.uniform(0.25, 1.0) if impairment == "weakness" else 1.0           # :72
-            tremor = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=10) if impairment == "tremor" else np.zeros(10)  # :141
-            # robot start pose
-            qa = self._pool[rng.randint(len(self._pool))]
-            # human pose, clamped into the scaled limits (world_creation.py:172)
-            qh = {}
-            for j in sc.human_joints:
-                l = human.links[j]
-                qh[j] = float(np.clip(sc.q_human_reset.get(j, 0.0), l.lower * limit_scale, l.upper * limit_scale))
-            # target on the arm (scratch_itch.py:275-281, util.py:112-132)
-            limb = [9, 11][rng.randint(2)]
-            length, radius = human.dims["limb_dims"][limb]
-            rl = rng.uniform(radius, length)
-            theta = rng.uniform(0, 2 * np.pi)
-            target_on_arm = np.array([-radius * np.sin(theta), -radius * np.cos(theta), -rl])
+def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, genders: np.ndarray | None = None):
+    """Post-reset env records for n environments. reset_data[v] = build_reset_data of variant v (0 male, 1 female).
 
-            # ---- fill the record
-            for bi, b in enumerate(sc.bodies):
-                if b.art == 0 and b.jtype != 2:
-                    if b.ref_joint in sc.robot_arm_joints:
-                        v = qa[sc.robot_arm_joints.index(b.ref_joint)]
-                    else:
-                        v = 1.0                                                             # gripper open, :254
-                    env[e, E_Q + b.qidx] = v
-                    env[e, E_MTARGET + b.dof] = v
-                elif b.art == 1:
-                    env[e, E_Q + b.qidx] = qh[b.ref_joint]
-                    env[e, E_MTARGET + b.dof] = qh[b.ref_joint]
-            # tool placed at the end effector (world_creation.py:331-337)
-            qrob = {j: float(qa[k]) for k, j in enumerate(sc.robot_arm_joints)}
-            for j in (9, 11, 13):
-                qrob[j] = 1.0
-            ee_p, ee_q = robot.com_frames(qrob)[8]
-            base_p, base_q = X.tf_mul(ee_p, ee_q, *sc.tool_offset)
-            at = sc.attach[2][-1]
-            ip, iq = X.tf_inv(at.pos, at.quat)
-            bp, bq = X.tf_mul(base_p, base_q, ip, iq)
-            tb = [b for b in sc.bodies if b.art == 2][0]
-            env[e, E_Q + tb.qidx:E_Q + tb.qidx + 3] = bp
-            env[e, E_Q + tb.qidx + 3:E_Q + tb.qidx + 7] = bq
-            env[e, E_STRENGTH] = strength
-            env[e, E_LIMIT_SCALE] = limit_scale
-            active = sc.human_control or impairment == "tremor"
-            env[e, E_HUMAN_KP] = 0.05 if active else 0.01          # scratch_itch.py:45 / :231
-            env[e, E_TREMOR_ON] = 1.0 if impairment == "tremor" else 0.0
-            env[e, E_TREMOR:E_TREMOR + 10] = tremor
-            th = np.zeros(10)
-            for j in sc.human_joints:
-                th[j - 4] = qh[j]
-            env[e, E_TARGET_H:E_TARGET_H + 10] = th                  # scratch_itch.py:235
-            env[e, E_TARGET_ON_ARM:E_TARGET_ON_ARM + 3] = target_on_arm
-            env_i[e, E_LIMB_FRAME] = F_SHOULDER if limb == 9 else F_ELBOW
-            # task state: zeros (task_success, prev_target_contact_pos, iteration), scratch_itch.py:147-148
-        return env, variant
+    Draw order per environment follows SURVEY.md App. C: gender (scratch_itch.py:156), impairment
+    (world_creation.py:67-72), tremor amplitudes (:141), start pose (pool entry), limb (scratch_itch.py:278), point on
+    the capsule (util.py:118,129).  -> (records [n, ENV_STRIDE] float32 with int slots bit-cast, variant [n] int32)
+    """
+    env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
+    env_i = env.view(np.int32)
+    variant = np.zeros(n, dtype=np.int32)
+    for e in range(n):
+        v = int(genders[e]) if genders is not None else int(rng.randint(len(reset_data)))
+        variant[e] = v
+        rd = reset_data[v]
+        impairment = int(rng.randint(4))                       # 0 none, 1 limits, 2 weakness, 3 tremor
+        limit_scale = rng.uniform(0.5, 1.0) if impairment == 1 else 1.0
+        strength = rng.uniform(0.25, 1.0) if impairment == 2 else 1.0
+        tremor = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=10) if impairment == 3 else np.zeros(10)
+        k = int(rng.randint(len(rd["pool_q"])))
+        qa = rd["pool_q"][k]
+        qh = np.clip(rd["hum_reset"], rd["hum_lower"] * limit_scale, rd["hum_upper"] * limit_scale)   # world_creation.py:172
+        limb = int(rng.randint(2))
+        length, radius = rd["limb_dims"][limb]
+        rl = rng.uniform(radius, length)
+        theta = rng.uniform(0, 2 * np.pi)
+        env[e, E_Q + rd["arm_qidx"]] = qa
+        env[e, E_MTARGET + rd["arm_dof"]] = qa
+        env[e, E_Q + rd["fin_qidx"]] = 1.0
+        env[e, E_MTARGET + rd["fin_dof"]] = 1.0
+        env[e, E_Q + rd["hum_qidx"]] = qh
+        env[e, E_MTARGET + rd["hum_dof"]] = qh
+        tq = int(rd["tool_qidx"])
+        env[e, E_Q + tq:E_Q + tq + 7] = rd["pool_tool"][k]
+        env[e, E_STRENGTH] = strength
+        env[e, E_LIMIT_SCALE] = limit_scale
+        active = bool(rd["human_control"]) or impairment == 3
+        env[e, E_HUMAN_KP] = 0.05 if active else 0.01          # scratch_itch.py:45 / :231
+        env[e, E_TREMOR_ON] = 1.0 if impairment == 3 else 0.0
+        env[e, E_TREMOR:E_TREMOR + 10] = tremor
+        env[e, E_TARGET_H + rd["hum_joint"] - 4] = qh           # scratch_itch.py:235
+        env[e, E_TARGET_ON_ARM:E_TARGET_ON_ARM + 3] = [-radius * np.sin(theta), -radius * np.cos(theta), -rl]
+        env_i[e, E_LIMB_FRAME] = F_SHOULDER if limb == 0 else F_ELBOW
+    return env, variant

@@ -304,6 +304,7 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
                    cfg["task_success_threshold"], hp["velocity_weight"], hp["force_nontarget_weight"],
                    hp["high_forces_weight"], hp["food_hit_weight"], hp["food_velocities_weight"],
                    0.025, 0.01, 10.0, 0.05, 1.0]
+    task_f[16:19] = [-0.3, -0.1, 0.7]       # reference point of the device spatial algebra (float32 conditioning)
     header = dict(task=0, n_body=n_body, n_ebody=0, n_dof=n_dof, n_jdof=n_jdof, n_free=n_free,
                   substeps=5, solver_iters=50,                             # env.py:16, scratch_itch.py:258
                   n_action_robot=7, n_action_human=10 if human_control else 0,

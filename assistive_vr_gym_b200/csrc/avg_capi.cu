@@ -1,0 +1,263 @@
+// avg_capi.cu — C-ABI (include/avg_b200.h) over the sm_100a kernels.  Host side in C++: handle, state arena,
+// model copies, pinned staging for the host-buffer step.  There is NO CPU fallback: every entry point that computes
+// launches a CUDA kernel or fails with an error code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "../../include/avg_b200.h"
+#include "../../include/avg_model.h"
+#include "avg_kernels.h"
+
+struct AvgHandle {
+    int device = 0;
+    int n_env = 0;
+    int n_act = 0, n_obs = 0, task = -1;
+    unsigned char* d_model[AVG_K_MAX_VARIANTS] = {nullptr, nullptr, nullptr, nullptr};
+    AvgModelHeader hdr[AVG_K_MAX_VARIANTS];
+    bool have[AVG_K_MAX_VARIANTS] = {false, false, false, false};
+    float* d_env = nullptr;
+    int32_t* d_variant = nullptr;
+    // debug taps
+    bool debug = false;
+    AvgContact* d_contacts = nullptr;
+    int32_t* d_ncontacts = nullptr;
+    float* d_terms = nullptr;
+    // staging for avg_step_host
+    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_info = nullptr;
+    uint8_t* h_done = nullptr;
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_info = nullptr;
+    uint8_t* d_done = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::string err;
+};
+
+static std::string g_create_error;
+
+#define AVG_CHECK(h, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+static int fail(AvgHandle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" {
+
+const char* avg_last_error(const AvgHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int avg_create(int device, int n_env, AvgHandle** out) {
+    if (!out || n_env <= 0) return fail(nullptr, -1, "avg_create: bad arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, -3, std::string("avg_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= count) return fail(nullptr, -1, "avg_create: device ordinal out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    AvgHandle* h = new AvgHandle();
+    h->device = device; h->n_env = n_env;
+    if (cudaMalloc(&h->d_env, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env) != cudaSuccess ||
+        cudaMalloc(&h->d_variant, sizeof(int32_t) * (size_t)n_env) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, -2, "avg_create: cudaMalloc of the state arena failed");
+    }
+    cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
+    cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
+    cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    *out = h;
+    return 0;
+}
+
+int avg_destroy(AvgHandle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
+    cudaFree(h->d_env); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes) {
+    if (!h || !blob) return -1;
+    if (variant < 0 || variant >= AVG_K_MAX_VARIANTS) return fail(h, -1, "avg_upload_model: variant out of range");
+    if (nbytes < sizeof(AvgModelHeader)) return fail(h, -1, "avg_upload_model: blob too small");
+    const AvgModelHeader* mh = (const AvgModelHeader*)blob;
+    if (mh->magic != AVG_MAGIC || mh->version != AVG_VERSION) return fail(h, -1, "avg_upload_model: bad magic/version");
+    if (mh->total_bytes != nbytes) return fail(h, -1, "avg_upload_model: size mismatch");
+    if (mh->n_body > AVG_MAX_BODY || mh->n_dof > AVG_MAX_DOF || mh->n_jdof > AVG_K_MAXJ || mh->n_mshape > AVG_K_MAXMS ||
+        mh->n_free > 2 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32)
+        return fail(h, -4, "avg_upload_model: model exceeds the warp-per-environment kernel limits");
+    if (mh->task != AVG_TASK_SCRATCH_ITCH) return fail(h, -4, "avg_upload_model: only the ScratchItch epilogue is built (round 1)");
+    const AvgBody* bodies = (const AvgBody*)((const char*)blob + mh->off_body);
+    for (int b = 0; b < mh->n_body; ++b) {
+        if (bodies[b].jtype != AVG_JOINT_FREE && (bodies[b].dof != b || b >= mh->n_jdof))
+            return fail(h, -4, "avg_upload_model: 1-DoF joint bodies must come first with dof == body index");
+        if (bodies[b].parent >= b) return fail(h, -4, "avg_upload_model: parents must precede children");
+    }
+    int na = mh->n_action_robot + mh->n_action_human, no = mh->n_obs_robot + mh->n_obs_human;
+    if (h->task >= 0 && (h->n_act != na || h->n_obs != no || h->task != mh->task))
+        return fail(h, -4, "avg_upload_model: variants of one handle must share task / action / observation widths");
+    cudaSetDevice(h->device);
+    cudaFree(h->d_model[variant]); h->d_model[variant] = nullptr;
+    AVG_CHECK(h, cudaMalloc(&h->d_model[variant], nbytes));
+    AVG_CHECK(h, cudaMemcpy(h->d_model[variant], blob, nbytes, cudaMemcpyHostToDevice));
+    h->hdr[variant] = *mh; h->have[variant] = true;
+    h->task = mh->task; h->n_act = na; h->n_obs = no;
+    return 0;
+}
+
+int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_records, const int32_t* variants) {
+    if (!h || !env_records) return -1;
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_set_state: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaMemcpy(h->d_env + (size_t)env_begin * AVG_ENV_STRIDE, env_records,
+                            sizeof(float) * AVG_ENV_STRIDE * (size_t)env_count, cudaMemcpyHostToDevice));
+    if (variants) {
+        for (int i = 0; i < env_count; ++i)
+            if (variants[i] < 0 || variants[i] >= AVG_K_MAX_VARIANTS || !h->have[variants[i]])
+                return fail(h, -1, "avg_set_state: variant without an uploaded model");
+        AVG_CHECK(h, cudaMemcpy(h->d_variant + env_begin, variants, sizeof(int32_t) * (size_t)env_count, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records) {
+    if (!h || !env_records) return -1;
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_state: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(env_records, h->d_env + (size_t)env_begin * AVG_ENV_STRIDE,
+                            sizeof(float) * AVG_ENV_STRIDE * (size_t)env_count, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
+
+static int fill_args(AvgHandle* h, AvgStepArgs& a) {
+    if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
+    a.variant = h->d_variant; a.env = h->d_env; a.n_env = h->n_env;
+    a.contacts = h->debug ? h->d_contacts : nullptr;
+    a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
+    a.terms = h->debug ? h->d_terms : nullptr;
+    return 0;
+}
+
+int avg_reset_obs(AvgHandle* h, float* obs, void* stream) {
+    if (!h || !obs) return -1;
+    cudaSetDevice(h->device);
+    AvgStepArgs a; memset(&a, 0, sizeof(a));
+    int rc = fill_args(h, a); if (rc) return rc;
+    a.obs = obs;
+    AVG_CHECK(h, avg_launch_reset_obs(a, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, float* info, void* stream) {
+    if (!h || !actions || !obs || !reward || !info) return -1;
+    cudaSetDevice(h->device);
+    AvgStepArgs a; memset(&a, 0, sizeof(a));
+    int rc = fill_args(h, a); if (rc) return rc;
+    a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
+    AVG_CHECK(h, avg_launch_step(a, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, float* info) {
+    if (!h || !actions || !obs || !reward || !info) return -1;
+    cudaSetDevice(h->device);
+    size_t n = (size_t)h->n_env;
+    if (!h->h_act) {
+        AVG_CHECK(h, cudaMallocHost(&h->h_act, sizeof(float) * n * h->n_act));
+        AVG_CHECK(h, cudaMallocHost(&h->h_obs, sizeof(float) * n * h->n_obs));
+        AVG_CHECK(h, cudaMallocHost(&h->h_rew, sizeof(float) * n));
+        AVG_CHECK(h, cudaMallocHost(&h->h_info, sizeof(float) * n * 2));
+        AVG_CHECK(h, cudaMallocHost(&h->h_done, n));
+        AVG_CHECK(h, cudaMalloc(&h->d_act, sizeof(float) * n * h->n_act));
+        AVG_CHECK(h, cudaMalloc(&h->d_obs, sizeof(float) * n * h->n_obs));
+        AVG_CHECK(h, cudaMalloc(&h->d_rew, sizeof(float) * n));
+        AVG_CHECK(h, cudaMalloc(&h->d_info, sizeof(float) * n * 2));
+        AVG_CHECK(h, cudaMalloc(&h->d_done, n));
+    }
+    memcpy(h->h_act, actions, sizeof(float) * n * h->n_act);
+    AVG_CHECK(h, cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * n * h->n_act, cudaMemcpyHostToDevice, h->stream));
+    int rc = avg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_info, h->stream);
+    if (rc) return rc;
+    AVG_CHECK(h, cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * n * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(h->h_info, h->d_info, sizeof(float) * n * 2, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaStreamSynchronize(h->stream));
+    memcpy(obs, h->h_obs, sizeof(float) * n * h->n_obs);
+    memcpy(reward, h->h_rew, sizeof(float) * n);
+    memcpy(info, h->h_info, sizeof(float) * n * 2);
+    if (done) memcpy(done, h->h_done, n);
+    return 0;
+}
+
+int avg_enable_debug(AvgHandle* h, int enable) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    if (enable && !h->d_contacts) {
+        AVG_CHECK(h, cudaMalloc(&h->d_contacts, sizeof(AvgContact) * AVG_MAX_CONTACT * (size_t)h->n_env));
+        AVG_CHECK(h, cudaMalloc(&h->d_ncontacts, sizeof(int32_t) * (size_t)h->n_env));
+        AVG_CHECK(h, cudaMalloc(&h->d_terms, sizeof(float) * 8 * (size_t)h->n_env));
+        cudaMemset(h->d_ncontacts, 0, sizeof(int32_t) * (size_t)h->n_env);
+    }
+    h->debug = enable != 0;
+    return 0;
+}
+
+int avg_get_contacts(AvgHandle* h, int env_begin, int env_count, void* contacts, int32_t* counts) {
+    if (!h || !contacts || !counts) return -1;
+    if (!h->d_contacts) return fail(h, -1, "avg_get_contacts: call avg_enable_debug first");
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_contacts: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(contacts, h->d_contacts + (size_t)env_begin * AVG_MAX_CONTACT,
+                            sizeof(AvgContact) * AVG_MAX_CONTACT * (size_t)env_count, cudaMemcpyDeviceToHost));
+    AVG_CHECK(h, cudaMemcpy(counts, h->d_ncontacts + env_begin, sizeof(int32_t) * (size_t)env_count, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int avg_get_reward_terms(AvgHandle* h, int env_begin, int env_count, float* terms) {
+    if (!h || !terms) return -1;
+    if (!h->d_terms) return fail(h, -1, "avg_get_reward_terms: call avg_enable_debug first");
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_reward_terms: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(terms, h->d_terms + (size_t)env_begin * 8, sizeof(float) * 8 * (size_t)env_count, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int avg_num_envs(const AvgHandle* h) { return h ? h->n_env : 0; }
+int avg_num_actions(const AvgHandle* h) { return h ? h->n_act : 0; }
+int avg_num_obs(const AvgHandle* h) { return h ? h->n_obs : 0; }
+int avg_env_stride(void) { return AVG_ENV_STRIDE; }
+long long avg_launch_count(const AvgHandle* h) { return h ? h->launches : 0; }
+
+int avg_bytes_per_env_step(const AvgHandle* h) {
+    if (!h) return 0;
+    /* state record read once (AVG_E_LAST floats used) + dynamic part written once + action + obs + reward + info + done;
+       mirrors the load/store loops of avg_step_kernel */
+    int read_state = AVG_ENV_STRIDE * 4;
+    int write_state = (AVG_E_STRENGTH + (AVG_E_TARGET_ON_ARM - AVG_E_TARGET_H) + (AVG_E_LAST - AVG_E_ITERATION)) * 4;
+    int io = h->n_act * 4 + h->n_obs * 4 + 4 + 8 + 1 + 4 /* variant id */;
+    return read_state + write_state + io;
+}
+
+}  // extern "C"

@@ -1,0 +1,1109 @@
+// avg_kernels.cu — sm_100a kernels of the batched Assistive-Gym simulator (ScratchItch path).
+//
+// One warp owns one environment for a whole env.step(): action -> motor targets (reference env.py:274-337),
+// frame_skip x { forward kinematics, collision, forward dynamics, constraint solve, integration, human hard limits }
+// (what the reference delegates to p.stepSimulation, env.py:341-349), then forces / reward / observation
+// (scratch_itch.py:53-128).  State is read from HBM once and written once per env-step.
+//
+// Lane mapping inside a warp:
+//   kinematics/dynamics : lane b = dynamic body b (1-DoF joint bodies first, so lane i is also velocity dof i)
+//   solver              : lane d = velocity dof d (delta-velocity component in a register), rows staged in smem,
+//                         J.dv by warp shuffles, strict row order (Gauss-Seidel semantics)
+//   collision           : lanes stride over the candidate pair table; one lane runs GJK for one candidate pair
+//
+// The math is NOT a transcription of the CPU oracle: forward dynamics is mass-matrix based (composite-rigid-body
+// inertia in a common frame, then an explicit inverse that the solver reuses for M^-1 J^T), whereas the oracle
+// runs the recursive articulated-body algorithm.  Both are Featherstone algorithms for the same equations.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/avg_model.h"
+#include "avg_math.cuh"
+#include "avg_kernels.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = AVG_K_WARPS_PER_BLOCK;
+constexpr int kMaxJ = AVG_K_MAXJ;          // 1-DoF joints per environment handled by this kernel
+constexpr int kMaxMS = AVG_K_MAXMS;        // moving shapes
+constexpr int kMaxCand = 64;               // narrowphase candidates per sub-step
+constexpr int kMaxC = AVG_MAX_CONTACT;
+constexpr int kMaxDense = 6 + 2 * kMaxC;   // weld rows + contact normal + friction rows
+constexpr int kMaxRows = AVG_MAX_ROWS;
+
+struct __align__(16) WarpSm {
+    float env[AVG_ENV_STRIDE];             // the environment record (q, qd, motor targets, parameters, task state)
+    float bp[32][3];                       // body frame origin (world)
+    float bq[32][4];                       // body orientation
+    float Minv[kMaxJ][kMaxJ + 1];          // joint-space inverse mass matrix (block diagonal per articulation)
+    float freeInv[2][12];                  // free bodies: [0] 1/m, [1..9] inverse world inertia
+    float J[kMaxDense][32];
+    float W[kMaxDense][32];
+    float r_tgt[kMaxRows], r_inv[kMaxRows], r_lo[kMaxRows], r_hi[kMaxRows], r_lam[kMaxRows], r_mu[kMaxRows];
+    int r_idx[kMaxRows];                   // (kind << 8) | index; kind 0: +e_i, 1: -e_i, 2: dense row
+    int r_par[kMaxRows];                   // friction rows: row index of their normal row, else -1
+    float sp[kMaxMS][3];                   // moving shapes: world position, rotation, AABB
+    float sR[kMaxMS][9];
+    float saabb[kMaxMS][6];
+    uint32_t cand[kMaxCand];
+    float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
+    int c_sa[kMaxC], c_sb[kMaxC];
+    float obs[64];
+};
+
+struct KM {                                // device view of a ModelBlob
+    const AvgModelHeader* h;
+    const AvgBody* body;
+    const AvgDof* dof;
+    const AvgShape* shape;
+    const float* vert;
+    const float* plane;
+    const uint32_t* pair;
+    const AvgFrame* frame;
+};
+
+__device__ __forceinline__ KM open_model(const unsigned char* blob) {
+    KM m;
+    m.h = reinterpret_cast<const AvgModelHeader*>(blob);
+    m.body = reinterpret_cast<const AvgBody*>(blob + m.h->off_body);
+    m.dof = reinterpret_cast<const AvgDof*>(blob + m.h->off_dof);
+    m.shape = reinterpret_cast<const AvgShape*>(blob + m.h->off_shape);
+    m.vert = reinterpret_cast<const float*>(blob + m.h->off_vert);
+    m.plane = reinterpret_cast<const float*>(blob + m.h->off_plane);
+    m.pair = reinterpret_cast<const uint32_t*>(blob + m.h->off_pair);
+    m.frame = reinterpret_cast<const AvgFrame*>(blob + m.h->off_frame);
+    return m;
+}
+
+__device__ __forceinline__ void body_pose(const WarpSm& s, int b, V3& p, Q4& q) {
+    if (b < 0) { p = mk3(0, 0, 0); q = mkq(0, 0, 0, 1); }
+    else { p = ld3(s.bp[b]); q = ldq(s.bq[b]); }
+}
+__device__ __forceinline__ void frame_pose(const KM& m, const WarpSm& s, int f, V3& p, Q4& q) {
+    const AvgFrame* F = &m.frame[f];
+    V3 bp; Q4 bq;
+    body_pose(s, F->body, bp, bq);
+    p = bp + qrot(bq, ld3(F->pos));
+    q = qnormalize(qmul(bq, ldq(F->quat)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward kinematics: every lane builds its body's transform relative to the parent body, then the chain products
+// are formed by pointer jumping over the parent array (log2(depth) shuffle rounds instead of a serial walk).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void fk_warp(const KM& m, WarpSm& s, int lane, int nb) {
+    V3 p = mk3(0, 0, 0); Q4 q = mkq(0, 0, 0, 1);
+    int anc = -1;
+    if (lane < nb) {
+        const AvgBody* B = &m.body[lane];
+        if (B->jtype == AVG_JOINT_FREE) {
+            const float* qq = s.env + AVG_E_Q + B->qidx;
+            p = ld3(qq); q = qnormalize(ldq(qq + 3));
+        } else {
+            V3 ax = ld3(B->axis);
+            float qv = s.env[AVG_E_Q + B->qidx];
+            Q4 jq = ldq(B->ta_quat);
+            V3 jp = ld3(B->ta_pos);
+            if (B->jtype == AVG_JOINT_REVOLUTE) jq = qmul(jq, qaxis(ax, qv));
+            else jp = jp + qrot(jq, ax * qv);
+            p = jp + qrot(jq, ld3(B->tb_pos));
+            q = qmul(jq, ldq(B->tb_quat));
+            anc = B->parent;
+        }
+    }
+    while (__any_sync(AVG_FULL, anc >= 0)) {
+        int src = anc >= 0 ? anc : lane;
+        V3 ap = shfl3(p, src); Q4 aq = shflq(q, src);
+        int aa = __shfl_sync(AVG_FULL, anc, src);
+        if (anc >= 0) { p = ap + qrot(aq, p); q = qmul(aq, q); anc = aa; }
+    }
+    if (lane < nb) {
+        q = qnormalize(q);
+        st3(s.bp[lane], p);
+        s.bq[lane][0] = q.x; s.bq[lane][1] = q.y; s.bq[lane][2] = q.z; s.bq[lane][3] = q.w;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Collision: support-function shapes, GJK closest points on the cores, margins added afterwards; one point per
+// shape pair (see DESIGN.md "narrowphase").  One lane per candidate pair.
+// ---------------------------------------------------------------------------------------------------------------
+struct WShape {
+    const AvgShape* s;
+    V3 p;
+    float R[9];
+    const float* verts;
+    const float* planes;
+};
+
+__device__ __forceinline__ void load_wshape(const KM& m, const WarpSm& s, int si, WShape& w) {
+    const AvgShape* S = &m.shape[si];
+    w.s = S; w.verts = m.vert + 3 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
+    if (si < m.h->n_mshape) {
+        w.p = ld3(s.sp[si]);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w.R[i] = s.sR[si][i];
+    } else {
+        w.p = ld3(S->pos);
+        M3 r = qmat(ldq(S->quat));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w.R[i] = r.m[i];
+    }
+}
+
+__device__ V3 support(const WShape& w, V3 d) {
+    const AvgShape* S = w.s;
+    V3 l = mtmul(w.R, d), r;
+    switch (S->type) {
+    case AVG_SHAPE_CAPSULE: r = mk3(0, 0, l.z >= 0 ? S->half[2] : -S->half[2]); break;
+    case AVG_SHAPE_BOX: {
+        float hx = S->half[0] - S->margin, hy = S->half[1] - S->margin, hz = S->half[2] - S->margin;
+        r = mk3(l.x >= 0 ? hx : -hx, l.y >= 0 ? hy : -hy, l.z >= 0 ? hz : -hz); break;
+    }
+    case AVG_SHAPE_CYLINDER: {
+        float rc = S->radius - S->margin, hc = S->half[2] - S->margin;
+        float n = sqrtf(l.x * l.x + l.y * l.y);
+        if (n > 1e-12f) r = mk3(rc * l.x / n, rc * l.y / n, l.z >= 0 ? hc : -hc);
+        else r = mk3(rc, 0, l.z >= 0 ? hc : -hc);
+        break;
+    }
+    case AVG_SHAPE_HULL: {
+        int best = 0; float bd = -3.0e38f;
+        const float* v = w.verts;
+        for (int i = 0; i < S->vert_cnt; ++i) {
+            float dd = fmaf(l.x, v[3 * i], fmaf(l.y, v[3 * i + 1], l.z * v[3 * i + 2]));
+            if (dd > bd) { bd = dd; best = i; }
+        }
+        r = mk3(v[3 * best], v[3 * best + 1], v[3 * best + 2]); break;
+    }
+    default: r = mk3(0, 0, 0);       // sphere core = its centre
+    }
+    return w.p + mmul(w.R, r);
+}
+
+struct Simplex { V3 w[4], a[4], b[4]; float lam[4]; int n; };
+
+__device__ void closest_tri(const V3& a, const V3& b, const V3& c, float lam[3], int& mask) {
+    V3 ab = b - a, ac = c - a, ap = -a;
+    float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) { lam[0] = 1; lam[1] = 0; lam[2] = 0; mask = 1; return; }
+    V3 bp = -b;
+    float d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) { lam[0] = 0; lam[1] = 1; lam[2] = 0; mask = 2; return; }
+    float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { float v = d1 / (d1 - d3); lam[0] = 1 - v; lam[1] = v; lam[2] = 0; mask = 3; return; }
+    V3 cp = -c;
+    float d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) { lam[0] = 0; lam[1] = 0; lam[2] = 1; mask = 4; return; }
+    float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { float w = d2 / (d2 - d6); lam[0] = 1 - w; lam[1] = 0; lam[2] = w; mask = 5; return; }
+    float va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); lam[0] = 0; lam[1] = 1 - w; lam[2] = w; mask = 6; return;
+    }
+    float den = 1.0f / (va + vb + vc);
+    lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2]; mask = 7;
+}
+
+// closest point of the simplex to the origin; returns true when the origin is enclosed
+__device__ bool simplex_closest(Simplex& s, V3& v) {
+    float lam[4] = {0, 0, 0, 0};
+    int mask = 0;
+    if (s.n == 1) { lam[0] = 1; mask = 1; }
+    else if (s.n == 2) {
+        V3 ab = s.w[1] - s.w[0];
+        float t = -dot(s.w[0], ab), den = dot(ab, ab);
+        if (t <= 0 || den <= 0) { lam[0] = 1; mask = 1; }
+        else if (t >= den) { lam[1] = 1; mask = 2; }
+        else { lam[1] = t / den; lam[0] = 1 - lam[1]; mask = 3; }
+    } else if (s.n == 3) {
+        float l3[3]; closest_tri(s.w[0], s.w[1], s.w[2], l3, mask);
+        lam[0] = l3[0]; lam[1] = l3[1]; lam[2] = l3[2];
+    } else {
+        const int F[4][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 3, 1}, {1, 2, 3, 0}};
+        float best = 3.0e38f; bool any = false;
+        for (int f = 0; f < 4; ++f) {
+            V3 a = s.w[F[f][0]], b = s.w[F[f][1]], c = s.w[F[f][2]], d = s.w[F[f][3]];
+            V3 n = cross(b - a, c - a);
+            float so = -dot(a, n), sd = dot(d - a, n);
+            if (sd == 0 || so * sd <= 0) {
+                float l3[3]; int km;
+                closest_tri(a, b, c, l3, km);
+                V3 p = a * l3[0] + b * l3[1] + c * l3[2];
+                float dd = dot(p, p);
+                if (dd < best) {
+                    best = dd; any = true;
+                    lam[0] = lam[1] = lam[2] = lam[3] = 0;
+                    lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
+                    mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
+                }
+            }
+        }
+        if (!any) return true;
+    }
+    int n = 0; V3 p = mk3(0, 0, 0);
+    for (int i = 0; i < s.n; ++i) if (mask & (1 << i)) {
+        s.w[n] = s.w[i]; s.a[n] = s.a[i]; s.b[n] = s.b[i]; s.lam[n] = lam[i];
+        p = p + s.w[i] * lam[i];
+        n++;
+    }
+    s.n = n; v = p;
+    return false;
+}
+
+// returns false: cores separated (dist, pa, pb valid); true: cores overlap.  Works relative to A's position to keep
+// float32 magnitudes small.
+__device__ bool gjk(const WShape& A, const WShape& B, float& dist, V3& pa, V3& pb) {
+    Simplex s; s.n = 0;
+    V3 org = A.p;
+    V3 v = A.p - B.p;
+    if (dot(v, v) < 1e-12f) v = mk3(1, 0, 0);
+    for (int it = 0; it < 32; ++it) {
+        V3 sa = support(A, -v) - org, sb = support(B, v) - org;
+        V3 w = sa - sb;
+        float vv = dot(v, v), vw = dot(v, w);
+        if (s.n > 0 && (vv - vw) <= 1e-5f * vv + 1e-10f) break;
+        bool dup = false;
+        for (int i = 0; i < s.n; ++i) { V3 d = s.w[i] - w; if (dot(d, d) < 1e-14f) dup = true; }
+        if (dup) break;
+        s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
+        if (simplex_closest(s, v)) return true;
+        if (dot(v, v) < 1e-12f) return true;
+    }
+    V3 a = mk3(0, 0, 0), b = mk3(0, 0, 0);
+    for (int i = 0; i < s.n; ++i) { a = a + s.a[i] * s.lam[i]; b = b + s.b[i] * s.lam[i]; }
+    pa = a + org; pb = b + org; dist = norm(v);
+    return false;
+}
+
+__device__ void sat_axis(const WShape& A, const WShape& B, V3 n, float& best, V3& bn, V3& bpa) {
+    float ln = norm(n);
+    if (ln < 1e-9f) return;
+    n = n * (1.0f / ln);
+    V3 sa = support(A, -n), sb = support(B, n);
+    float depth = dot(sb - sa, n);
+    if (depth < best) { best = depth; bn = n; bpa = sa; }
+}
+__device__ void shape_axes(const WShape& S, const WShape& O, float sign, const WShape& A, const WShape& B, float& best, V3& bn, V3& bpa) {
+    const AvgShape* s = S.s;
+    if (s->type == AVG_SHAPE_BOX || s->type == AVG_SHAPE_CYLINDER) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (s->type == AVG_SHAPE_CYLINDER && ax < 2) continue;
+            V3 n = mk3(S.R[ax], S.R[3 + ax], S.R[6 + ax]);
+            sat_axis(A, B, n * sign, best, bn, bpa);
+            sat_axis(A, B, n * (-sign), best, bn, bpa);
+        }
+        if (s->type == AVG_SHAPE_CYLINDER) {
+            V3 az = mk3(S.R[2], S.R[5], S.R[8]);
+            V3 d = O.p - S.p;
+            V3 rad = d - az * dot(d, az);
+            sat_axis(A, B, rad * sign, best, bn, bpa);
+        }
+    } else if (s->type == AVG_SHAPE_HULL) {
+        for (int i = 0; i < s->plane_cnt; ++i) {
+            V3 n = mmul(S.R, mk3(S.planes[4 * i], S.planes[4 * i + 1], S.planes[4 * i + 2]));
+            sat_axis(A, B, n * sign, best, bn, bpa);
+        }
+    }
+}
+
+// -> true when a contact (distance < thr) exists
+__device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa, V3& pb, V3& n, float& d) {
+    float ma = A.s->margin, mb = B.s->margin;
+    if (B.s->type == AVG_SHAPE_PLANE) {
+        V3 sp = support(A, mk3(0, 0, -1));
+        d = sp.z - ma;
+        if (d >= thr) return false;
+        n = mk3(0, 0, 1); pa = mk3(sp.x, sp.y, sp.z - ma); pb = mk3(sp.x, sp.y, 0);
+        return true;
+    }
+    float dist; V3 ca, cb;
+    if (!gjk(A, B, dist, ca, cb)) {
+        d = dist - ma - mb;
+        if (d >= thr) return false;
+        n = (ca - cb) * (1.0f / dist);
+        pa = ca - n * ma; pb = cb + n * mb;
+        return true;
+    }
+    float best = 3.0e38f; V3 bn = mk3(0, 0, 1), bpa = A.p;
+    shape_axes(A, B, -1.0f, A, B, best, bn, bpa);
+    shape_axes(B, A, +1.0f, A, B, best, bn, bpa);
+    sat_axis(A, B, A.p - B.p, best, bn, bpa);
+    if (best > 1.0e38f) best = 0;
+    n = bn; d = -best - ma - mb;
+    pa = bpa - n * ma; pb = bpa + n * best + n * mb;
+    return true;
+}
+
+__device__ void collide_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
+    const AvgModelHeader* h = m.h;
+    const int nms = h->n_mshape;
+    // world pose + AABB of the moving shapes
+    if (lane < nms) {
+        const AvgShape* S = &m.shape[lane];
+        V3 bp; Q4 bq;
+        body_pose(s, S->body, bp, bq);
+        V3 p = bp + qrot(bq, ld3(S->pos));
+        M3 R = qmat(qnormalize(qmul(bq, ldq(S->quat))));
+        st3(s.sp[lane], p);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s.sR[lane][i] = R.m[i];
+        V3 lc = ld3(S->aabb_c), lh = ld3(S->aabb_h);
+        V3 c = p + mmul(R.m, lc);
+        s.saabb[lane][0] = c.x; s.saabb[lane][1] = c.y; s.saabb[lane][2] = c.z;
+        s.saabb[lane][3] = fabsf(R.m[0]) * lh.x + fabsf(R.m[1]) * lh.y + fabsf(R.m[2]) * lh.z;
+        s.saabb[lane][4] = fabsf(R.m[3]) * lh.x + fabsf(R.m[4]) * lh.y + fabsf(R.m[5]) * lh.z;
+        s.saabb[lane][5] = fabsf(R.m[6]) * lh.x + fabsf(R.m[7]) * lh.y + fabsf(R.m[8]) * lh.z;
+    }
+    __syncwarp();
+    // broadphase over the pair table
+    int ncand = 0;
+    const int npair = h->n_pair;
+    for (int base = 0; base < npair; base += 32) {
+        int pi = base + lane;
+        bool hit = false;
+        uint32_t pr = 0;
+        if (pi < npair) {
+            pr = __ldg(&m.pair[pi]);
+            int a = pr & 0xffff, b = pr >> 16;
+            const AvgShape* SB = &m.shape[b];
+            float thr = fminf(__ldg(&m.shape[a].thr), __ldg(&SB->thr));
+            const float* A = s.saabb[a];
+            if (__ldg(&SB->type) == AVG_SHAPE_PLANE) hit = (A[2] - A[5]) <= thr;
+            else {
+                float bc0, bc1, bc2, bh0, bh1, bh2;
+                if (b < nms) { const float* Bq = s.saabb[b]; bc0 = Bq[0]; bc1 = Bq[1]; bc2 = Bq[2]; bh0 = Bq[3]; bh1 = Bq[4]; bh2 = Bq[5]; }
+                else { bc0 = __ldg(&SB->aabb_c[0]); bc1 = __ldg(&SB->aabb_c[1]); bc2 = __ldg(&SB->aabb_c[2]);
+                       bh0 = __ldg(&SB->aabb_h[0]); bh1 = __ldg(&SB->aabb_h[1]); bh2 = __ldg(&SB->aabb_h[2]); }
+                hit = fabsf(A[0] - bc0) <= A[3] + bh0 + thr && fabsf(A[1] - bc1) <= A[4] + bh1 + thr && fabsf(A[2] - bc2) <= A[5] + bh2 + thr;
+            }
+        }
+        unsigned bal = __ballot_sync(AVG_FULL, hit);
+        if (hit) {
+            int slot = ncand + __popc(bal & ((1u << lane) - 1));
+            if (slot < kMaxCand) s.cand[slot] = pr;
+        }
+        ncand += __popc(bal);
+    }
+    if (ncand > kMaxCand) { overflow |= 4; ncand = kMaxCand; }
+    __syncwarp();
+    // narrowphase: one lane per candidate, results compacted in pair order
+    int nc = 0;
+    for (int base = 0; base < ncand; base += 32) {
+        int ci = base + lane;
+        bool hit = false;
+        V3 pa, pb, n; float d = 0; int a = 0, b = 0;
+        if (ci < ncand) {
+            uint32_t pr = s.cand[ci];
+            a = pr & 0xffff; b = pr >> 16;
+            WShape A, B;
+            load_wshape(m, s, a, A); load_wshape(m, s, b, B);
+            float thr = fminf(A.s->thr, B.s->thr);
+            hit = narrowphase(A, B, thr, pa, pb, n, d);
+        }
+        unsigned bal = __ballot_sync(AVG_FULL, hit);
+        if (hit) {
+            int slot = nc + __popc(bal & ((1u << lane) - 1));
+            if (slot < kMaxC) {
+                st3(s.c_pa[slot], pa); st3(s.c_pb[slot], pb); st3(s.c_n[slot], n);
+                s.c_dist[slot] = d; s.c_lam[slot] = 0; s.c_sa[slot] = a; s.c_sb[slot] = b;
+            }
+        }
+        nc += __popc(bal);
+    }
+    if (nc > kMaxC) { overflow |= 1; nc = kMaxC; }
+    ncontact = nc;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dynamics
+// ---------------------------------------------------------------------------------------------------------------
+struct LaneDyn {
+    Sv S;             // motion subspace of this lane's joint (zero for free bodies / idle lanes)
+    uint32_t anc;     // ancestor-or-self mask
+};
+
+// Jacobian entry of lane `lane` (dof) for "velocity of world point r on `body` along n", sign applied.
+__device__ __forceinline__ float jac_point_lane(const KM& m, const WarpSm& s, const LaneDyn& L, int lane, int nj, int body,
+                                                V3 r, V3 n, V3 ref) {
+    if (body < 0) return 0.0f;
+    const AvgBody* B = &m.body[body];
+    if (B->jtype == AVG_JOINT_FREE) {
+        int k = lane - B->dof;
+        if (k < 0 || k >= 6) return 0.0f;
+        if (k < 3) return k == 0 ? n.x : (k == 1 ? n.y : n.z);
+        V3 rn = cross(r - ld3(s.bp[body]), n);
+        return k == 3 ? rn.x : (k == 4 ? rn.y : rn.z);
+    }
+    if (lane >= nj) return 0.0f;
+    if (!((B->anc_mask >> lane) & 1u)) return 0.0f;
+    return dot(L.S.a, cross(r - ref, n)) + dot(L.S.l, n);
+}
+__device__ __forceinline__ float jac_ang_lane(const KM& m, const LaneDyn& L, int lane, int nj, int body, V3 n) {
+    if (body < 0) return 0.0f;
+    const AvgBody* B = &m.body[body];
+    if (B->jtype == AVG_JOINT_FREE) {
+        int k = lane - B->dof;
+        if (k < 3 || k >= 6) return 0.0f;
+        return k == 3 ? n.x : (k == 4 ? n.y : n.z);
+    }
+    if (lane >= nj) return 0.0f;
+    if (!((B->anc_mask >> lane) & 1u)) return 0.0f;
+    return dot(L.S.a, n);
+}
+
+// W = M^-1 J^T for the dense row d (J already in smem), returns J.W (diag) and J.qd (u0) reduced over the warp
+__device__ __forceinline__ void finish_dense_row(const KM& m, WarpSm& s, int lane, int nj, int nd, int d, float qd, float& diag, float& u0) {
+    __syncwarp();
+    float w = 0.0f;
+    float jl = s.J[d][lane];
+    if (lane < nj) {
+        for (int j = 0; j < nj; ++j) w = fmaf(s.Minv[lane][j], s.J[d][j], w);
+    } else if (lane < nd) {
+        int fb = 0, k = lane - nj;
+        while (k >= 6) { k -= 6; fb++; }
+        int base = lane - k;
+        const float* fi = s.freeInv[fb];
+        if (k < 3) w = fi[0] * jl;
+        else { int r = k - 3; w = fi[1 + 3 * r] * s.J[d][base + 3] + fi[2 + 3 * r] * s.J[d][base + 4] + fi[3 + 3 * r] * s.J[d][base + 5]; }
+    }
+    s.W[d][lane] = w;
+    diag = warp_sum(jl * w);
+    u0 = warp_sum(jl * qd);
+}
+
+__device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
+    const AvgModelHeader* h = m.h;
+    const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
+    const float dt = h->dt;
+    const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
+
+    fk_warp(m, s, lane, nb);
+    collide_warp(m, s, lane, ncontact, overflow);
+
+    // ---- per-lane body quantities ------------------------------------------------------------------------------
+    LaneDyn L; L.S = mksv(mk3(0, 0, 0), mk3(0, 0, 0)); L.anc = 0;
+    float qd = (lane < nd) ? s.env[AVG_E_QD + lane] : 0.0f;
+    Inertia I; I.m = 0; I.h = mk3(0, 0, 0); I.xx = I.yy = I.zz = I.xy = I.xz = I.yz = 0;
+    float Ic[6] = {0, 0, 0, 0, 0, 0};        // world rotational inertia about the COM (xx, yy, zz, xy, xz, yz)
+    V3 c = mk3(0, 0, 0);
+    int parent = -1; bool is_joint = false, is_free = false;
+    V3 grav = mk3(0, 0, 0);
+    float mass = 0;
+    if (lane < nb) {
+        const AvgBody* B = &m.body[lane];
+        L.anc = B->anc_mask; parent = B->parent; mass = B->mass; grav = ld3(B->gravity);
+        V3 p = ld3(s.bp[lane]); Q4 q = ldq(s.bq[lane]);
+        M3 R = qmat(q);
+        float i0 = B->inertia[0], i1 = B->inertia[1], i2 = B->inertia[2];
+        Ic[0] = R.m[0] * R.m[0] * i0 + R.m[1] * R.m[1] * i1 + R.m[2] * R.m[2] * i2;
+        Ic[1] = R.m[3] * R.m[3] * i0 + R.m[4] * R.m[4] * i1 + R.m[5] * R.m[5] * i2;
+        Ic[2] = R.m[6] * R.m[6] * i0 + R.m[7] * R.m[7] * i1 + R.m[8] * R.m[8] * i2;
+        Ic[3] = R.m[0] * R.m[3] * i0 + R.m[1] * R.m[4] * i1 + R.m[2] * R.m[5] * i2;
+        Ic[4] = R.m[0] * R.m[6] * i0 + R.m[1] * R.m[7] * i1 + R.m[2] * R.m[8] * i2;
+        Ic[5] = R.m[3] * R.m[6] * i0 + R.m[4] * R.m[7] * i1 + R.m[5] * R.m[8] * i2;
+        c = p - ref;
+        if (B->jtype == AVG_JOINT_FREE) {
+            is_free = true;
+            // inverse world inertia for the solver
+            int fb = (B->dof - nj) / 6;
+            float j0 = i0 > 0 ? 1.0f / i0 : 0.0f, j1 = i1 > 0 ? 1.0f / i1 : 0.0f, j2 = i2 > 0 ? 1.0f / i2 : 0.0f;
+            float* fi = s.freeInv[fb];
+            fi[0] = mass > 0 ? 1.0f / mass : 0.0f;
+            fi[1] = R.m[0] * R.m[0] * j0 + R.m[1] * R.m[1] * j1 + R.m[2] * R.m[2] * j2;
+            fi[2] = R.m[0] * R.m[3] * j0 + R.m[1] * R.m[4] * j1 + R.m[2] * R.m[5] * j2;
+            fi[3] = R.m[0] * R.m[6] * j0 + R.m[1] * R.m[7] * j1 + R.m[2] * R.m[8] * j2;
+            fi[4] = fi[2];
+            fi[5] = R.m[3] * R.m[3] * j0 + R.m[4] * R.m[4] * j1 + R.m[5] * R.m[5] * j2;
+            fi[6] = R.m[3] * R.m[6] * j0 + R.m[4] * R.m[7] * j1 + R.m[5] * R.m[8] * j2;
+            fi[7] = fi[3]; fi[8] = fi[6];
+            fi[9] = R.m[6] * R.m[6] * j0 + R.m[7] * R.m[7] * j1 + R.m[8] * R.m[8] * j2;
+        } else {
+            is_joint = true;
+            // joint axis / origin from the body pose: axis_body = R(tb)^T axis, origin_body = -R(tb)^T tb_pos
+            Q4 tbq = ldq(B->tb_quat);
+            V3 ax_w = qrot(q, qrot_inv(tbq, ld3(B->axis)));
+            V3 org_w = p - qrot(q, qrot_inv(tbq, ld3(B->tb_pos)));
+            if (B->jtype == AVG_JOINT_REVOLUTE) L.S = mksv(ax_w, cross(org_w - ref, ax_w));
+            else L.S = mksv(mk3(0, 0, 0), ax_w);
+            I.m = mass; I.h = c * mass;
+            float cc = dot(c, c);
+            I.xx = Ic[0] + mass * (cc - c.x * c.x); I.yy = Ic[1] + mass * (cc - c.y * c.y); I.zz = Ic[2] + mass * (cc - c.z * c.z);
+            I.xy = Ic[3] - mass * c.x * c.y; I.xz = Ic[4] - mass * c.x * c.z; I.yz = Ic[5] - mass * c.y * c.z;
+        }
+    }
+    __syncwarp();
+
+    // ---- body velocities and velocity-product accelerations: path sums by pointer jumping -----------------------
+    Sv vj = L.S * (is_joint ? qd : 0.0f);
+    Sv V = vj;
+    {
+        int anc = is_joint ? parent : -1;
+        while (__any_sync(AVG_FULL, anc >= 0)) {
+            int src = anc >= 0 ? anc : lane;
+            Sv av = shflsv(V, src);
+            int aa = __shfl_sync(AVG_FULL, anc, src);
+            if (anc >= 0) { V = V + av; anc = aa; }
+        }
+    }
+    Sv Ab = crm(V, vj);
+    {
+        int anc = is_joint ? parent : -1;
+        while (__any_sync(AVG_FULL, anc >= 0)) {
+            int src = anc >= 0 ? anc : lane;
+            Sv av = shflsv(Ab, src);
+            int aa = __shfl_sync(AVG_FULL, anc, src);
+            if (anc >= 0) { Ab = Ab + av; anc = aa; }
+        }
+    }
+    // ---- body bias force: I Ab + V x* I V - external (gravity, Bullet velocity damping) -------------------------
+    Sv fb = mksv(mk3(0, 0, 0), mk3(0, 0, 0));
+    if (is_joint) {
+        Sv IV = inertia_mul(I, V);
+        fb = inertia_mul(I, Ab) + crf(V, IV);
+        V3 w = V.a;
+        V3 vc = V.l + cross(w, c);
+        V3 f = grav * mass - vc * (mass * (h->lin_damp + h->lin_damp * norm(vc)));
+        V3 Iw = mk3(Ic[0] * w.x + Ic[3] * w.y + Ic[4] * w.z, Ic[3] * w.x + Ic[1] * w.y + Ic[5] * w.z, Ic[4] * w.x + Ic[5] * w.y + Ic[2] * w.z);
+        V3 n = -(Iw * (h->ang_damp + h->ang_damp * norm(w)));
+        fb = fb - mksv(n + cross(c, f), f);
+    }
+    // ---- subtree sums (composite inertia, bias force) ------------------------------------------------------------
+    Inertia Ic_sub = I; Sv f_sub = fb;
+    for (int k = 0; k < nj; ++k) {
+        uint32_t mk = __shfl_sync(AVG_FULL, L.anc, k);
+        float m_k = __shfl_sync(AVG_FULL, I.m, k);
+        V3 h_k = shfl3(I.h, k);
+        float xx = __shfl_sync(AVG_FULL, I.xx, k), yy = __shfl_sync(AVG_FULL, I.yy, k), zz = __shfl_sync(AVG_FULL, I.zz, k);
+        float xy = __shfl_sync(AVG_FULL, I.xy, k), xz = __shfl_sync(AVG_FULL, I.xz, k), yz = __shfl_sync(AVG_FULL, I.yz, k);
+        Sv f_k = shflsv(fb, k);
+        if (k != lane && ((mk >> lane) & 1u) && is_joint) {
+            Ic_sub.m += m_k; Ic_sub.h = Ic_sub.h + h_k;
+            Ic_sub.xx += xx; Ic_sub.yy += yy; Ic_sub.zz += zz; Ic_sub.xy += xy; Ic_sub.xz += xz; Ic_sub.yz += yz;
+            f_sub = f_sub + f_k;
+        }
+    }
+    Sv F = inertia_mul(Ic_sub, L.S);          // composite inertia times own motion subspace
+    float Cb = dot(L.S, f_sub);               // generalized bias force of this lane's joint
+    // ---- joint-space mass matrix, M_ij = S_i . (Ic_j S_j) for i ancestor-or-self of j ----------------------------
+    for (int j = 0; j < nj; ++j) {
+        Sv Fj = shflsv(F, j), Sj = shflsv(L.S, j);
+        uint32_t mj = __shfl_sync(AVG_FULL, L.anc, j);
+        if (lane < nj) {
+            float v = 0.0f;
+            if ((mj >> lane) & 1u) v = dot(L.S, Fj);
+            else if ((L.anc >> j) & 1u) v = dot(Sj, F);
+            s.Minv[lane][j] = v;
+        }
+    }
+    __syncwarp();
+    // ---- in-place Gauss-Jordan inverse (symmetric positive definite, no pivoting); frozen dofs (M_kk ~ 0) give 0 --
+    for (int k = 0; k < nj; ++k) {
+        float p = s.Minv[k][k];
+        float ip = p > 1e-20f ? 1.0f / p : 0.0f;
+        __syncwarp();
+        for (int e = lane; e < nj * nj; e += 32) {
+            int i = e / nj, cidx = e - i * nj;
+            if (i != k && cidx != k) s.Minv[i][cidx] -= s.Minv[i][k] * s.Minv[k][cidx] * ip;
+        }
+        __syncwarp();
+        if (lane < nj && lane != k) {
+            float rk = s.Minv[k][lane] * ip, ck = s.Minv[lane][k] * (-ip);
+            s.Minv[k][lane] = rk; s.Minv[lane][k] = ck;
+        }
+        if (lane == k) s.Minv[k][k] = ip;
+        __syncwarp();
+    }
+    // ---- unconstrained velocity update: qd* = qd + dt M^-1 (-C) ---------------------------------------------------
+    float qdd = 0.0f;
+    for (int j = 0; j < nj; ++j) {
+        float cj = __shfl_sync(AVG_FULL, Cb, j);
+        if (lane < nj) qdd = fmaf(s.Minv[lane][j], -cj, qdd);
+    }
+    // free bodies (lane b computes, dof lanes pick up through smem scratch in s.obs)
+    if (is_free) {
+        const AvgBody* B = &m.body[lane];
+        const float* v6 = s.env + AVG_E_QD + B->dof;
+        V3 v = ld3(v6), w = ld3(v6 + 3);
+        V3 a = mass > 0 ? grav - v * (h->lin_damp + h->lin_damp * norm(v)) : mk3(0, 0, 0);
+        V3 Iw = mk3(Ic[0] * w.x + Ic[3] * w.y + Ic[4] * w.z, Ic[3] * w.x + Ic[1] * w.y + Ic[5] * w.z, Ic[4] * w.x + Ic[5] * w.y + Ic[2] * w.z);
+        V3 tau = -(Iw * (h->ang_damp + h->ang_damp * norm(w))) - cross(w, Iw);
+        const float* fi = s.freeInv[(B->dof - nj) / 6];
+        V3 al = mk3(fi[1] * tau.x + fi[2] * tau.y + fi[3] * tau.z, fi[4] * tau.x + fi[5] * tau.y + fi[6] * tau.z, fi[7] * tau.x + fi[8] * tau.y + fi[9] * tau.z);
+        float* o = s.obs + (B->dof - nj);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = al.x; o[4] = al.y; o[5] = al.z;
+    }
+    __syncwarp();
+    if (lane >= nj && lane < nd) qdd = s.obs[lane - nj];
+    __syncwarp();
+    qd = qd + dt * qdd;
+
+    // ---- constraint rows ------------------------------------------------------------------------------------------
+    int nr = 0;
+    // position motors: lane i prepares its own row, rows are appended in dof order
+    {
+        bool has = false; float tgt = 0, lo = 0, hi = 0;
+        if (lane < nj) {
+            const AvgDof* D = &m.dof[lane];
+            if (D->flags & AVG_DOF_MOTOR) {
+                has = true;
+                bool hum = D->flags & AVG_DOF_HUMAN;
+                float kp = hum ? s.env[AVG_E_HUMAN_KP] : D->kp;
+                float maxf = hum ? h->task_f[AVG_TF_HUMAN_FORCE] * s.env[AVG_E_STRENGTH] : D->max_force;
+                float q = s.env[AVG_E_Q + m.body[D->body].qidx];
+                tgt = kp * (s.env[AVG_E_MTARGET + lane] - q) / dt - D->kd * qd;
+                lo = -maxf * dt; hi = maxf * dt;
+            }
+        }
+        unsigned bal = __ballot_sync(AVG_FULL, has);
+        if (has) {
+            int r = nr + __popc(bal & ((1u << lane) - 1));
+            float diag = s.Minv[lane][lane];
+            s.r_tgt[r] = tgt; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f; s.r_lo[r] = lo; s.r_hi[r] = hi; s.r_lam[r] = 0;
+            s.r_mu[r] = 0; s.r_idx[r] = (0 << 8) | lane; s.r_par[r] = -1;
+        }
+        nr += __popc(bal);
+    }
+    // joint limits, only while violated; a dof can violate one side only, rows stay in dof order
+    {
+        bool has = false; float tgt = 0; int kind = 0;
+        if (lane < nj) {
+            const AvgDof* D = &m.dof[lane];
+            if (D->flags & AVG_DOF_LIMIT) {
+                float sc = (D->flags & AVG_DOF_HUMAN) ? s.env[AVG_E_LIMIT_SCALE] : 1.0f;
+                float q = s.env[AVG_E_Q + m.body[D->body].qidx];
+                float pen0 = q - D->lower * sc, pen1 = D->upper * sc - q;
+                if (pen0 <= 0) { has = true; kind = 0; tgt = -pen0 * h->erp / dt - qd; }
+                else if (pen1 <= 0) { has = true; kind = 1; tgt = -pen1 * h->erp / dt + qd; }
+            }
+        }
+        unsigned bal = __ballot_sync(AVG_FULL, has);
+        if (has) {
+            int r = nr + __popc(bal & ((1u << lane) - 1));
+            if (r < kMaxRows) {
+                float diag = s.Minv[lane][lane];
+                s.r_tgt[r] = tgt; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f; s.r_lo[r] = 0; s.r_hi[r] = 100.0f; s.r_lam[r] = 0;
+                s.r_mu[r] = 0; s.r_idx[r] = (kind << 8) | lane; s.r_par[r] = -1;
+            }
+        }
+        nr += __popc(bal);
+        if (nr > kMaxRows - 6) { overflow |= 2; nr = kMaxRows - 6; }
+    }
+    // tool weld, 6 dense rows
+    int ndense = 0;
+    {
+        V3 pa, pb; Q4 qa, qb;
+        frame_pose(m, s, AVG_F_WELD_PARENT, pa, qa);
+        frame_pose(m, s, AVG_F_TOOL_BASE, pb, qb);
+        Q4 dq = qmul(qa, qconj(qb));
+        if (dq.w < 0) dq = mkq(-dq.x, -dq.y, -dq.z, -dq.w);
+        float sn = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
+        V3 rotv = mk3(0, 0, 0);
+        if (sn > 1e-9f) { float ang = 2.0f * atan2f(sn, dq.w) / sn; rotv = mk3(dq.x * ang, dq.y * ang, dq.z * ang); }
+        V3 perr = pa - pb;
+        float maxi = h->weld_max_force * dt;
+        for (int ax = 0; ax < 6; ++ax) {
+            V3 e = mk3((ax % 3) == 0, (ax % 3) == 1, (ax % 3) == 2);
+            float jl, err;
+            if (ax < 3) {
+                jl = jac_point_lane(m, s, L, lane, nj, h->weld_body_a, pa, e, ref) - jac_point_lane(m, s, L, lane, nj, h->weld_body_b, pb, e, ref);
+                err = dot(perr, e);
+            } else {
+                jl = jac_ang_lane(m, L, lane, nj, h->weld_body_a, e) - jac_ang_lane(m, L, lane, nj, h->weld_body_b, e);
+                err = dot(rotv, e);
+            }
+            s.J[ndense][lane] = jl;
+            float diag, u0;
+            finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+            if (lane == 0) {
+                int r = nr;
+                s.r_tgt[r] = -err * h->erp / dt - u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
+                s.r_lo[r] = -maxi; s.r_hi[r] = maxi; s.r_lam[r] = 0; s.r_mu[r] = 0; s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = -1;
+            }
+            nr++; ndense++;
+        }
+    }
+    // contacts: normals first, then one friction row each (Bullet's row order)
+    int nc = ncontact;
+    if (nc > (kMaxRows - nr) / 2) { overflow |= 2; nc = (kMaxRows - nr) / 2; ncontact = nc; }
+    const int first_contact_row = nr;
+    for (int ci = 0; ci < nc; ++ci) {
+        V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
+        int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
+        float jl = jac_point_lane(m, s, L, lane, nj, ba, pa, n, ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, n, ref);
+        s.J[ndense][lane] = jl;
+        float diag, u0;
+        finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+        if (lane == 0) {
+            float dist = s.c_dist[ci];
+            int r = nr;
+            s.r_tgt[r] = (dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
+            s.r_lo[r] = 0; s.r_hi[r] = 1e30f; s.r_lam[r] = 0; s.r_mu[r] = 0; s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = -1;
+        }
+        nr++; ndense++;
+    }
+    for (int ci = 0; ci < nc; ++ci) {
+        V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
+        int sa = s.c_sa[ci], sb = s.c_sb[ci];
+        int ba = m.shape[sa].body, bb = m.shape[sb].body;
+        float jx = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(1, 0, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(1, 0, 0), ref);
+        float jy = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 1, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 1, 0), ref);
+        float jz = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 0, 1), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 0, 1), ref);
+        V3 vrel = mk3(warp_sum(jx * qd), warp_sum(jy * qd), warp_sum(jz * qd));
+        V3 lat = vrel - n * dot(vrel, n);
+        float ll = norm(lat);
+        V3 t;
+        if (ll > 1e-6f) t = lat * (1.0f / ll);
+        else if (fabsf(n.z) > 0.70710678f) { float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
+        else { float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
+        s.J[ndense][lane] = t.x * jx + t.y * jy + t.z * jz;
+        float diag, u0;
+        finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+        if (lane == 0) {
+            int r = nr;
+            s.r_tgt[r] = -u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
+            s.r_lo[r] = 0; s.r_hi[r] = 0; s.r_lam[r] = 0; s.r_mu[r] = m.shape[sa].friction * m.shape[sb].friction;
+            s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = first_contact_row + ci;
+        }
+        nr++; ndense++;
+    }
+    __syncwarp();
+
+    // ---- projected Gauss-Seidel, strict row order; dv lives in one register per lane ----------------------------
+    float dv = 0.0f;
+    const float thr = h->residual_thr;
+    for (int it = 0; it < h->solver_iters; ++it) {
+        float resid = 0.0f;
+        for (int r = 0; r < nr; ++r) {
+            float inv = s.r_inv[r];
+            if (inv == 0.0f) continue;
+            int idx = s.r_idx[r];
+            int kind = idx >> 8, i = idx & 0xff;
+            float jdv, wl;
+            if (kind == 2) {
+                wl = s.W[i][lane];
+                jdv = warp_sum(s.J[i][lane] * dv);
+            } else {
+                float sg = kind == 0 ? 1.0f : -1.0f;
+                jdv = sg * __shfl_sync(AVG_FULL, dv, i);
+                wl = lane < nj ? sg * s.Minv[i][lane] : 0.0f;
+            }
+            float lo = s.r_lo[r], hi = s.r_hi[r];
+            int par = s.r_par[r];
+            if (par >= 0) { float lim = s.r_mu[r] * s.r_lam[par]; lo = -lim; hi = lim; }
+            float lam = s.r_lam[r];
+            float delta = (s.r_tgt[r] - jdv) * inv;
+            float sum = fminf(fmaxf(lam + delta, lo), hi);
+            delta = sum - lam;
+            __syncwarp();
+            if (lane == 0) s.r_lam[r] = sum;
+            __syncwarp();
+            dv = fmaf(wl, delta, dv);
+            float rv = delta / inv;
+            resid = fmaxf(resid, rv * rv);
+        }
+        if (resid <= thr) break;
+    }
+    for (int ci = lane; ci < nc; ci += 32) s.c_lam[ci] = s.r_lam[first_contact_row + ci];
+
+    // ---- integrate ------------------------------------------------------------------------------------------------
+    float v = qd + dv;
+    if (lane < nj) v = fminf(fmaxf(v, -h->max_vel), h->max_vel);
+    __syncwarp();
+    if (lane < nd) s.env[AVG_E_QD + lane] = v;
+    __syncwarp();
+    if (lane < nb) {
+        const AvgBody* B = &m.body[lane];
+        if (B->jtype == AVG_JOINT_FREE) {
+            float* q = s.env + AVG_E_Q + B->qidx; const float* vv = s.env + AVG_E_QD + B->dof;
+            q[0] += dt * vv[0]; q[1] += dt * vv[1]; q[2] += dt * vv[2];
+            V3 w = ld3(vv + 3); float wn = norm(w);
+            Q4 cur = ldq(q + 3);
+            if (wn * dt > 1e-9f) cur = qmul(qaxis(w * (1.0f / wn), wn * dt), cur);
+            cur = qnormalize(cur);
+            q[3] = cur.x; q[4] = cur.y; q[5] = cur.z; q[6] = cur.w;
+        } else {
+            float qn = s.env[AVG_E_Q + B->qidx] + dt * v;
+            // enforce_hard_human_joint_limits, env.py:389-410
+            const AvgDof* D = &m.dof[lane];
+            if (D->flags & AVG_DOF_HARD_LIMIT) {
+                float sc = s.env[AVG_E_LIMIT_SCALE];
+                float lo = D->lower * sc, hi = D->upper * sc;
+                if (qn < lo) { qn = lo; s.env[AVG_E_QD + lane] = 0.0f; }
+                else if (qn > hi) { qn = hi; s.env[AVG_E_QD + lane] = 0.0f; }
+            }
+            s.env[AVG_E_Q + B->qidx] = qn;
+        }
+    }
+    __syncwarp();
+}
+
+}  // namespace
+
+// =================================================================================================================
+// The env-step kernel
+// =================================================================================================================
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_step_kernel(AvgStepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= a.n_env) return;
+    WarpSm& s = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    const int variant = a.variant ? a.variant[e] : 0;
+    const KM m = open_model(a.models[variant]);
+    const AvgModelHeader* h = m.h;
+    const int nj = h->n_jdof;
+
+    // ---- load the environment record (coalesced, once) ----------------------------------------------------------
+    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
+    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
+    __syncwarp();
+    int* env_i = reinterpret_cast<int*>(s.env);
+
+    // ---- action -> motor targets, env.py:274-337 ----------------------------------------------------------------
+    const int na = h->n_action_robot + h->n_action_human;
+    const float* act = a.actions + (size_t)e * na;
+    float raw_sq = 0.0f;
+    {
+        float av = lane < na ? act[lane] : 0.0f;
+        raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, scratch_itch.py:64
+    }
+    const bool human_active = h->human_control || s.env[AVG_E_TREMOR_ON] != 0.0f;
+    const bool tremor = s.env[AVG_E_TREMOR_ON] != 0.0f;
+    const int iteration = env_i[AVG_E_ITERATION];
+    if (lane < nj) {
+        const AvgDof* D = &m.dof[lane];
+        const int ai = D->action, slot = D->human_slot;
+        if (ai >= 0 && ai < h->n_action_robot) {
+            float av = fminf(fmaxf(act[ai], -1.0f), 1.0f) * h->action_scale;
+            float pos = s.env[AVG_E_Q + m.body[D->body].qidx];
+            for (int f = 0; f < h->substeps; ++f) {
+                if (pos + av < D->rep_lower) av = 0.0f;
+                if (pos + av > D->rep_upper) av = 0.0f;
+                pos += av;
+            }
+            s.env[AVG_E_MTARGET + lane] = pos;
+        } else if (slot >= 0 && human_active) {
+            float av = 0.0f;
+            if (h->human_control) av = fminf(fmaxf(act[h->n_action_robot + slot], -1.0f), 1.0f) * h->action_scale;
+            float sc = s.env[AVG_E_LIMIT_SCALE];
+            float lo = D->lower * sc, hi = D->upper * sc;
+            float pos = s.env[AVG_E_Q + m.body[D->body].qidx];
+            float tgt = s.env[AVG_E_TARGET_H + slot];
+            const float sgn = (iteration % 2 == 0) ? 1.0f : -1.0f;
+            for (int f = 0; f < h->substeps; ++f) {
+                if (pos + av < lo) av = 0.0f;
+                if (pos + av > hi) av = 0.0f;
+                if (tremor) { pos = tgt + s.env[AVG_E_TREMOR + slot] * sgn; tgt += av; }
+                pos += av;
+            }
+            s.env[AVG_E_TARGET_H + slot] = tgt;
+            s.env[AVG_E_MTARGET + lane] = pos;
+        }
+    }
+    __syncwarp();
+    if (human_active && lane == 0) s.env[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
+    __syncwarp();
+
+    // ---- frame_skip physics sub-steps, env.py:341-349 -----------------------------------------------------------
+    int ncontact = 0, overflow = 0;
+    for (int f = 0; f < h->substeps; ++f) substep_warp(m, s, lane, ncontact, overflow);
+
+    // ---- forces, reward, observation (scratch_itch.py:53-128) ---------------------------------------------------
+    fk_warp(m, s, lane, h->n_body);
+    V3 tgt; { V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
+    const float dt = h->dt;
+    const float* tf = h->task_f;
+    float total_force_on_human = 0, tool_force = 0, tool_force_at_target = 0;
+    bool have_tcp = false; V3 tcp = mk3(0, 0, 0);
+    for (int ci = 0; ci < ncontact; ++ci) {
+        const AvgShape* sa = &m.shape[s.c_sa[ci]]; const AvgShape* sb = &m.shape[s.c_sb[ci]];
+        float force = s.c_lam[ci] / dt;
+        bool a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        bool a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        bool a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if (a_tool || b_tool) tool_force += force;
+        if ((a_tool && b_hum) || (b_tool && a_hum)) {
+            total_force_on_human += force;
+            int link_tool = a_tool ? sa->ref_link : sb->ref_link;
+            V3 pos_h = a_tool ? ld3(s.c_pb[ci]) : ld3(s.c_pa[ci]);
+            if ((link_tool == 0 || link_tool == 1) && norm(pos_h - tgt) < tf[AVG_TF_TARGET_RADIUS]) {
+                tool_force_at_target += force; tcp = pos_h; have_tcp = true;
+            }
+        }
+        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;
+    }
+    V3 torso, tool, sh, el, wr, chest; Q4 tq, dq;
+    frame_pose(m, s, AVG_F_TORSO, torso, dq);
+    frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+    frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
+    frame_pose(m, s, AVG_F_ELBOW, el, dq);
+    frame_pose(m, s, AVG_F_WRIST, wr, dq);
+    frame_pose(m, s, AVG_F_CHEST, chest, dq);
+    float ee_vel;
+    {
+        int tb = m.frame[AVG_F_TOOL_TIP].body;
+        const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
+        V3 vt = ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb]));
+        ee_vel = norm(vt);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float* o = s.obs; int k = 0;
+        V3 t;
+        t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+        t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = tgt - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+        t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = tool_force;
+        if (h->human_control) {
+            t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+            t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = tgt - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            int hq0 = k;
+            for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
+            for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+            t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            o[k++] = total_force_on_human; o[k++] = tool_force_at_target;
+        }
+        // human_preferences (env.py:412-448) and reward (scratch_itch.py:62-72)
+        float pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_at_target))
+                   + tf[AVG_TF_C_HF] * (tool_force_at_target < tf[AVG_TF_FORCE_CAP] ? 0.0f : -tool_force_at_target);
+        float reward_distance = -norm(tgt - tool);
+        float reward_action = -raw_sq;
+        float reward_force_scratch = 0.0f;
+        V3 prev = ld3(s.env + AVG_E_PREV_CONTACT);
+        if (have_tcp && norm(tcp - prev) > tf[AVG_TF_SCRATCH_MOVE] && tool_force_at_target < tf[AVG_TF_FORCE_CAP]) {
+            reward_force_scratch = tool_force_at_target;
+            st3(s.env + AVG_E_PREV_CONTACT, tcp);
+            s.env[AVG_E_TASK_SUCCESS] += 1.0f;
+        }
+        float reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
+                     + tf[AVG_TF_TOOL_FORCE_W] * tool_force_at_target + tf[AVG_TF_SCRATCH_W] * reward_force_scratch + pref;
+        s.env[AVG_E_EPISODE_RETURN] += reward;
+        st3(s.env + AVG_E_TARGET_POS, tgt);
+        env_i[AVG_E_ITERATION] = iteration + 1;
+        env_i[AVG_E_OVERFLOW] |= overflow;
+        a.reward[e] = reward;
+        a.info[2 * e] = total_force_on_human;
+        a.info[2 * e + 1] = s.env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;
+        if (a.done) a.done[e] = 0;                            // the env itself never terminates, scratch_itch.py:78
+        if (a.terms) {
+            float* tr = a.terms + 8 * (size_t)e;
+            tr[0] = total_force_on_human; tr[1] = a.info[2 * e + 1]; tr[2] = tool_force; tr[3] = tool_force_at_target;
+            tr[4] = reward_distance; tr[5] = reward_action; tr[6] = reward_force_scratch; tr[7] = pref;
+        }
+    }
+    __syncwarp();
+    // ---- write back (coalesced) ---------------------------------------------------------------------------------
+    const int nobs = h->n_obs_robot + h->n_obs_human;
+    for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
+    for (int i = lane; i < AVG_E_LAST; i += 32)
+        if (i < AVG_E_STRENGTH || (i >= AVG_E_TARGET_H && i < AVG_E_TARGET_ON_ARM) || i >= AVG_E_ITERATION) grec[i] = s.env[i];
+    if (a.contacts) {
+        AvgContact* co = a.contacts + (size_t)e * kMaxC;
+        for (int ci = lane; ci < kMaxC; ci += 32) {
+            AvgContact c;
+            if (ci < ncontact) {
+                c.shape_a = s.c_sa[ci]; c.shape_b = s.c_sb[ci];
+                for (int k = 0; k < 3; ++k) { c.pos_a[k] = s.c_pa[ci][k]; c.pos_b[k] = s.c_pb[ci][k]; c.normal[k] = s.c_n[ci][k]; }
+                c.dist = s.c_dist[ci]; c.force = s.c_lam[ci] / dt;
+            } else { c.shape_a = -1; c.shape_b = -1; for (int k = 0; k < 3; ++k) { c.pos_a[k] = c.pos_b[k] = c.normal[k] = 0; } c.dist = 0; c.force = 0; }
+            c.pad[0] = c.pad[1] = c.pad[2] = 0;
+            co[ci] = c;
+        }
+        if (lane == 0) a.ncontacts[e] = ncontact;
+    }
+}
+
+// initial observation after reset (scratch_itch.py:268): FK + target + _get_obs([0],[0,0])
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_reset_obs_kernel(AvgStepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= a.n_env) return;
+    WarpSm& s = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    const int variant = a.variant ? a.variant[e] : 0;
+    const KM m = open_model(a.models[variant]);
+    const AvgModelHeader* h = m.h;
+    const int nj = h->n_jdof;
+    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
+    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
+    __syncwarp();
+    int* env_i = reinterpret_cast<int*>(s.env);
+    fk_warp(m, s, lane, h->n_body);
+    if (lane == 0) {
+        V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
+        V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
+        V3 torso, tool, sh, el, wr, chest; Q4 tq, dq;
+        frame_pose(m, s, AVG_F_TORSO, torso, dq);
+        frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+        frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
+        frame_pose(m, s, AVG_F_ELBOW, el, dq);
+        frame_pose(m, s, AVG_F_WRIST, wr, dq);
+        frame_pose(m, s, AVG_F_CHEST, chest, dq);
+        float* o = s.obs; int k = 0; V3 t;
+        t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+        t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = tgt - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+        t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = 0.0f;
+        if (h->human_control) {
+            t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+            t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = tgt - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            int hq0 = k;
+            for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
+            for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+            t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+            o[k++] = 0.0f; o[k++] = 0.0f;
+        }
+        st3(grec + AVG_E_TARGET_POS, tgt);
+    }
+    __syncwarp();
+    const int nobs = h->n_obs_robot + h->n_obs_human;
+    for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
+}
+
+size_t avg_kernel_smem_bytes() { return sizeof(WarpSm) * kWarpsPerBlock; }
+
+cudaError_t avg_launch_step(const AvgStepArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    size_t smem = avg_kernel_smem_bytes();
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(avg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess) return e1;
+        e1 = cudaFuncSetAttribute(avg_reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess) return e1;
+        configured = true;
+    }
+    int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    avg_step_kernel<<<blocks, 32 * kWarpsPerBlock, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream) {
+    size_t smem = avg_kernel_smem_bytes();
+    cudaError_t e1 = cudaFuncSetAttribute(avg_reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return e1;
+    int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    avg_reset_obs_kernel<<<blocks, 32 * kWarpsPerBlock, smem, stream>>>(a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's gym interface, batched over N environments resident on one GPU.
+
+Keeps the `assistive_gym` surface: ids `'<Task><Robot>[Human]-v0'` (reference
+`assistive_gym/__init__.py:4-344`), `seed`, `reset() -> obs`, `step(action) -> (obs, reward, done, info)` with the
+reference's observation layout (`scratch_itch.py:104-128`), reward (`:62-72`) and info keys (`:77`), and the
+`TimeLimit(200)` wrapper `gym.make` adds (`__init__.py:18-22`).  All arithmetic happens in the CUDA library behind
+`include/avg_b200.h`; PyTorch only owns the I/O tensors and the stream.
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import capi
+from .compiler.reset import sample_states
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+MAX_EPISODE_STEPS = 200      # reference __init__.py:21
+
+# ids registered by the reference for the tasks/robots this round compiles (reference __init__.py:16-50)
+REGISTRY: Dict[str, dict] = {
+    "ScratchItchJaco-v0": dict(task="scratch_itch", robot="jaco", human_control=False, data="ScratchItchJaco.npz"),
+    "ScratchItchJacoHuman-v0": dict(task="scratch_itch", robot="jaco", human_control=True, data="ScratchItchJacoHuman.npz"),
+}
+_ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")
+                      for r in ("PR2", "Jaco") for v in ("", "Human", "New")]
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not installed here): Box(-1, 1, (n,), float32), env.py:34-35."""
+
+    def __init__(self, n: int, seed: int = 0):
+        self.low = -np.ones(n, dtype=np.float32)
+        self.high = np.ones(n, dtype=np.float32)
+        self.shape = (n,)
+        self.dtype = np.float32
+        self._rng = np.random.RandomState(seed)
+
+    def sample(self) -> np.ndarray:
+        return self._rng.uniform(self.low, self.high).astype(np.float32)
+
+    def seed(self, s):
+        self._rng = np.random.RandomState(s)
+
+
+def load_env_data(name: str):
+    path = os.path.join(_DATA, name)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing: run tools/compile_models.py where the reference assets are available")
+    z = np.load(path)
+    blobs, resets = [], []
+    v = 0
+    while f"blob_{v}" in z:
+        blobs.append(z[f"blob_{v}"].tobytes())
+        pre = f"reset_{v}_"
+        resets.append({k[len(pre):]: z[k] for k in z.files if k.startswith(pre)})
+        v += 1
+    return blobs, resets
+
+
+class BatchedAssistiveEnv:
+    """N copies of one reference environment stepping in lock-step on one GPU."""
+
+    def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False):
+        if env_id not in REGISTRY:
+            if env_id in _ALL_REFERENCE_IDS:
+                raise NotImplementedError(f"{env_id}: registered by the reference but not compiled yet "
+                                          f"(built so far: {sorted(REGISTRY)})")
+            raise KeyError(f"unknown environment id {env_id}")
+        import torch
+        if not torch.cuda.is_available():
+            raise capi.AvgError("no CUDA device: the simulator has no CPU path")
+        self.torch = torch
+        self.spec = dict(REGISTRY[env_id]); self.env_id = env_id
+        self.num_envs = int(num_envs)
+        self.device_index = device
+        self.device = torch.device("cuda", device)
+        self.blobs, self.reset_data = load_env_data(self.spec["data"])
+        self.sim = capi.Sim(self.num_envs, device)
+        for v, b in enumerate(self.blobs):
+            self.sim.upload_model(v, b)
+        self.action_robot_len = 7
+        self.action_human_len = 10 if self.spec["human_control"] else 0
+        self.obs_robot_len = 30
+        self.obs_human_len = 34 if self.spec["human_control"] else 0
+        assert self.sim.n_actions == self.action_robot_len + self.action_human_len
+        assert self.sim.n_obs == self.obs_robot_len + self.obs_human_len
+        self.action_space = Box(self.sim.n_actions)
+        self.observation_space = Box(self.sim.n_obs)
+        self.auto_reset = auto_reset
+        self.seed(seed)
+        n = self.num_envs
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((n, self.sim.n_obs), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.done_dev = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self.info_dev = torch.zeros((n, 2), dtype=torch.float32, device=self.device)
+        self.elapsed = 0
+        self.variants: Optional[np.ndarray] = None
+        self._needs_reset = True
+
+    # -- reference API ------------------------------------------------------------------------------------------
+    def seed(self, seed=None):
+        """env.py:80-82"""
+        self.np_random = np.random.RandomState(seed)
+        return [seed]
+
+    def reset(self, genders: Optional[np.ndarray] = None):
+        """scratch_itch.py:130-273, batched: samples every env's post-reset state on the host and uploads it."""
+        env, variant = sample_states(self.reset_data, self.num_envs, self.np_random, genders)
+        self.set_state(env, variant)
+        return self.obs
+
+    def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None):
+        """Import explicit env records ("identical initial states" for parity runs)."""
+        self.variants = variant
+        self.sim.set_state(env, variant)
+        self.sim.reset_obs(self.obs.data_ptr(), self._stream())
+        self.elapsed = 0
+        self._needs_reset = False
+
+    def get_state(self) -> np.ndarray:
+        return self.sim.get_state()
+
+    def _stream(self) -> int:
+        return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def step(self, actions):
+        """-> (obs [N, D], reward [N], done [N] bool, info) as CUDA tensors; info follows scratch_itch.py:77."""
+        torch = self.torch
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32), device=self.device)
+        actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.dim() == 1:
+            actions = actions.unsqueeze(0)
+        if tuple(actions.shape) != (self.num_envs, self.sim.n_actions):
+            raise ValueError(f"expected actions of shape {(self.num_envs, self.sim.n_actions)}, got {tuple(actions.shape)}")
+        self.sim.step(actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done_dev.data_ptr(),
+                      self.info_dev.data_ptr(), self._stream())
+        self.elapsed += 1
+        timeout = self.elapsed >= MAX_EPISODE_STEPS                 # gym TimeLimit, __init__.py:21
+        done = self.done_dev.bool() | timeout
+        info = {"total_force_on_human": self.info_dev[:, 0], "task_success": self.info_dev[:, 1].to(torch.int32),
+                "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
+                "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len,
+                "TimeLimit.truncated": timeout}
+        if timeout:
+            if self.auto_reset:
+                info["terminal_observation"] = self.obs.clone()
+                self.reset()
+            else:
+                self._needs_reset = False      # like gym, stepping past the limit is the caller's business
+        return self.obs, self.reward, done, info
+
+    def step_host(self, actions: np.ndarray):
+        """Same step with NumPy buffers through avg_step_host (host<->device copies included)."""
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.sim.n_actions)
+        if not hasattr(self, "_h_obs"):
+            self._h_obs = np.zeros((self.num_envs, self.sim.n_obs), dtype=np.float32)
+            self._h_rew = np.zeros(self.num_envs, dtype=np.float32)
+            self._h_done = np.zeros(self.num_envs, dtype=np.uint8)
+            self._h_info = np.zeros((self.num_envs, 2), dtype=np.float32)
+        self.sim.step_host(a, self._h_obs, self._h_rew, self._h_done, self._h_info)
+        self.elapsed += 1
+        timeout = self.elapsed >= MAX_EPISODE_STEPS
+        info = {"total_force_on_human": self._h_info[:, 0], "task_success": self._h_info[:, 1].astype(np.int32),
+                "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
+                "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len}
+        return self._h_obs, self._h_rew, self._h_done.astype(bool) | timeout, info
+
+    def render(self):
+        """env.py:613-620 opens the PyBullet GUI; rendering is out of scope for the batched simulator."""
+        return None
+
+    def close(self):
+        self.sim.close()
+
+
+class AssistiveEnvNumpy:
+    """`num_envs=1` view with the reference's exact return types: float64 1-D obs, python float reward, bool done,
+    info dict of scalars (scratch_itch.py:77-82) — what `examples/random_actions.py` expects."""
+
+    def __init__(self, env_id: str, device: int = 0, seed: int = 1001):
+        self.env = BatchedAssistiveEnv(env_id, num_envs=1, device=device, seed=seed)
+        self.action_space = self.env.action_space
+        self.observation_space = self.env.observation_space
+
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
+    def reset(self):
+        return self.env.reset()[0].double().cpu().numpy()
+
+    def step(self, action):
+        obs, rew, done, info = self.env.step_host(np.asarray(action, dtype=np.float32)[None])
+        out_info = {k: (v if np.isscalar(v) else (float(v[0]) if v.dtype.kind == "f" else int(v[0]))) for k, v in info.items()}
+        return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), out_info
+
+    def render(self):
+        return None
+
+    def close(self):
+        self.env.close()
+
+
+def make(env_id: str, num_envs: Optional[int] = None, device: int = 0, seed: int = 1001, **kw):
+    """`gym.make` replacement.  num_envs=None -> reference-typed single environment; otherwise the batched env."""
+    if num_envs is None:
+        return AssistiveEnvNumpy(env_id, device=device, seed=seed)
+    return BatchedAssistiveEnv(env_id, num_envs=num_envs, device=device, seed=seed, **kw)

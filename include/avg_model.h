@@ -17,7 +17,7 @@
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
 #define AVG_MAX_EBODY   8   /* env-static bodies (pose given per environment)             */
-#define AVG_MAX_CONTACT 16  /* contact points kept per sub-step                           */
+#define AVG_MAX_CONTACT 12  /* contact points kept per sub-step                           */
 #define AVG_MAX_ROWS   64   /* constraint rows per sub-step (2 per lane)                  */
 #define AVG_MAX_HULL_VERTS 48
 

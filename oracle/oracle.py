@@ -87,7 +87,7 @@ class Oracle:
         obs = np.zeros(self.n_obs)
         rew = np.zeros(1)
         info = np.zeros(8)
-        cont = np.zeros((16, 13))
+        cont = np.zeros((12, 13))
         nc = ctypes.c_int(0)
         rc = self.lib.avg_oracle_step(self.blob, self._dp(env), act.ctypes.data_as(_FP), self._dp(obs), self._dp(rew),
                                       self._dp(info), self._dp(cont), ctypes.byref(nc))
@@ -111,7 +111,7 @@ class Oracle:
         return qdd[:self.n_dof], minv
 
     def collide(self, env):
-        cont = np.zeros((16, 13))
+        cont = np.zeros((12, 13))
         nc = ctypes.c_int(0)
         self.lib.avg_oracle_collide(self.blob, self._dp(env), self._dp(cont), ctypes.byref(nc))
         return cont[:nc.value].copy()
