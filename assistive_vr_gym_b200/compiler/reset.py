@@ -142,43 +142,53 @@ def build_reset_data(scene: CompiledScene, rng: np.random.RandomState, ik_pool: 
 def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, genders: np.ndarray | None = None):
     """Post-reset env records for n environments. reset_data[v] = build_reset_data of variant v (0 male, 1 female).
 
-    Draw order per environment follows SURVEY.md App. C: gender (scratch_itch.py:156), impairment
-    (world_creation.py:67-72), tremor amplitudes (:141), start pose (pool entry), limb (scratch_itch.py:278), point on
-    the capsule (util.py:118,129).  -> (records [n, ENV_STRIDE] float32 with int slots bit-cast, variant [n] int32)
+    The quantities drawn per environment are those of SURVEY.md App. C: gender (scratch_itch.py:156), impairment and
+    its parameters (world_creation.py:67-72), tremor amplitudes (:141), start pose (a pool entry), limb
+    (scratch_itch.py:278) and the point on the capsule (util.py:118,129).  Draws are vectorised over environments, so
+    the stream order differs from the reference's per-episode order (exact RNG parity is out of reach anyway, App. C).
+    -> (records [n, ENV_STRIDE] float32 with int slots bit-cast, variant [n] int32)
     """
     env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
     env_i = env.view(np.int32)
-    variant = np.zeros(n, dtype=np.int32)
-    for e in range(n):
-        v = int(genders[e]) if genders is not None else int(rng.randint(len(reset_data)))
-        variant[e] = v
+    nv = len(reset_data)
+    variant = (np.asarray(genders, dtype=np.int32) if genders is not None else rng.randint(nv, size=n).astype(np.int32))
+    impairment = rng.randint(4, size=n)                        # 0 none, 1 limits, 2 weakness, 3 tremor
+    limit_scale = np.where(impairment == 1, rng.uniform(0.5, 1.0, size=n), 1.0)
+    strength = np.where(impairment == 2, rng.uniform(0.25, 1.0, size=n), 1.0)
+    tremor = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=(n, 10)) * (impairment == 3)[:, None]
+    limb = rng.randint(2, size=n)
+    u_len = rng.uniform(0.0, 1.0, size=n)
+    theta = rng.uniform(0, 2 * np.pi, size=n)
+    pool_pick = rng.randint(1 << 30, size=n)
+    for v in range(nv):
+        idx = np.nonzero(variant == v)[0]
+        if idx.size == 0:
+            continue
         rd = reset_data[v]
-        impairment = int(rng.randint(4))                       # 0 none, 1 limits, 2 weakness, 3 tremor
-        limit_scale = rng.uniform(0.5, 1.0) if impairment == 1 else 1.0
-        strength = rng.uniform(0.25, 1.0) if impairment == 2 else 1.0
-        tremor = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=10) if impairment == 3 else np.zeros(10)
-        k = int(rng.randint(len(rd["pool_q"])))
+        k = pool_pick[idx] % len(rd["pool_q"])
         qa = rd["pool_q"][k]
-        qh = np.clip(rd["hum_reset"], rd["hum_lower"] * limit_scale, rd["hum_upper"] * limit_scale)   # world_creation.py:172
-        limb = int(rng.randint(2))
-        length, radius = rd["limb_dims"][limb]
-        rl = rng.uniform(radius, length)
-        theta = rng.uniform(0, 2 * np.pi)
-        env[e, E_Q + rd["arm_qidx"]] = qa
-        env[e, E_MTARGET + rd["arm_dof"]] = qa
-        env[e, E_Q + rd["fin_qidx"]] = 1.0
-        env[e, E_MTARGET + rd["fin_dof"]] = 1.0
-        env[e, E_Q + rd["hum_qidx"]] = qh
-        env[e, E_MTARGET + rd["hum_dof"]] = qh
+        ls = limit_scale[idx][:, None]
+        qh = np.clip(rd["hum_reset"][None, :], rd["hum_lower"][None, :] * ls, rd["hum_upper"][None, :] * ls)   # world_creation.py:172
+        length = rd["limb_dims"][limb[idx], 0]; radius = rd["limb_dims"][limb[idx], 1]
+        rl = radius + u_len[idx] * (length - radius)            # uniform(radius, length), util.py:118
+        env[np.ix_(idx, E_Q + rd["arm_qidx"])] = qa
+        env[np.ix_(idx, E_MTARGET + rd["arm_dof"])] = qa
+        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = 1.0
+        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = 1.0
+        env[np.ix_(idx, E_Q + rd["hum_qidx"])] = qh
+        env[np.ix_(idx, E_MTARGET + rd["hum_dof"])] = qh
         tq = int(rd["tool_qidx"])
-        env[e, E_Q + tq:E_Q + tq + 7] = rd["pool_tool"][k]
-        env[e, E_STRENGTH] = strength
-        env[e, E_LIMIT_SCALE] = limit_scale
-        active = bool(rd["human_control"]) or impairment == 3
-        env[e, E_HUMAN_KP] = 0.05 if active else 0.01          # scratch_itch.py:45 / :231
-        env[e, E_TREMOR_ON] = 1.0 if impairment == 3 else 0.0
-        env[e, E_TREMOR:E_TREMOR + 10] = tremor
-        env[e, E_TARGET_H + rd["hum_joint"] - 4] = qh           # scratch_itch.py:235
-        env[e, E_TARGET_ON_ARM:E_TARGET_ON_ARM + 3] = [-radius * np.sin(theta), -radius * np.cos(theta), -rl]
-        env_i[e, E_LIMB_FRAME] = F_SHOULDER if limb == 0 else F_ELBOW
+        env[idx, E_Q + tq:E_Q + tq + 7] = rd["pool_tool"][k]
+        active = bool(rd["human_control"]) | (impairment[idx] == 3)
+        env[idx, E_HUMAN_KP] = np.where(active, 0.05, 0.01)     # scratch_itch.py:45 / :231
+        env[np.ix_(idx, E_TARGET_H + rd["hum_joint"] - 4)] = qh   # scratch_itch.py:235
+        th = theta[idx]
+        env[idx, E_TARGET_ON_ARM + 0] = -radius * np.sin(th)
+        env[idx, E_TARGET_ON_ARM + 1] = -radius * np.cos(th)
+        env[idx, E_TARGET_ON_ARM + 2] = -rl
+    env[:, E_STRENGTH] = strength
+    env[:, E_LIMIT_SCALE] = limit_scale
+    env[:, E_TREMOR_ON] = (impairment == 3)
+    env[:, E_TREMOR:E_TREMOR + 10] = tremor
+    env_i[:, E_LIMB_FRAME] = np.where(limb == 0, F_SHOULDER, F_ELBOW)
     return env, variant

@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the ScratchItchJaco-v0 hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
+
+A "step" is one env.step() of every environment of the batch (take_step + 5 physics sub-steps + reward/obs), with
+synthetic uniform random actions (seed 0) and random-reset initial states (seed 1001).  `value` is measured with the
+state, actions and outputs resident in HBM (CUDA events on the launch stream, max over ranks); `e2e` is the same
+metric through the reference-facing host-buffer call (avg_step_host: NumPy actions in, NumPy obs/reward/done/info out,
+host<->device copies inside the timed region).  Environments are sharded over ranks with no data-path collective
+("weak" scaling, fixed envs per GPU); NCCL is used only for the barrier, the max-time reduction and the episode
+statistics.  `--impl reference` times the CPU oracle port of the path (the reference's own arithmetic lives in the
+pybullet extension, which is not installable here) on all host cores for the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_ID = "ScratchItchJaco-v0"
+METRIC = "env-steps/sec (ScratchItchJaco, 1/2/4/8 B200) vs PyBullet on host cores"
+UNIT = "env-steps/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _oracle_worker(args):
+    blob, recs, actions = args
+    from oracle.oracle import Oracle
+    o = Oracle(blob)
+    t0 = time.perf_counter()
+    n = 0
+    for e in range(len(recs)):
+        rec = recs[e].copy()
+        for t in range(actions.shape[0]):
+            o.step(rec, actions[t, e])
+            n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_oracle_throughput(envs_per_core: int, steps: int, cores: int | None = None):
+    """Times the CPU oracle (kind 'port') on `cores` processes; returns (env-steps/s, cores, sample text)."""
+    import multiprocessing as mp
+    from assistive_vr_gym_b200.envs import load_env_data
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from oracle.oracle import env_to_f64, build
+    build()
+    cores = cores or os.cpu_count() or 1
+    blobs, resets = load_env_data("ScratchItchJaco.npz")
+    rng = np.random.RandomState(1001)
+    jobs = []
+    for c in range(cores):
+        env, variant = sample_states(resets, envs_per_core, rng, genders=np.full(envs_per_core, c % len(blobs)))
+        acts = np.random.RandomState(c).uniform(-1, 1, (steps, envs_per_core, 7)).astype(np.float32)
+        jobs.append((blobs[c % len(blobs)], env_to_f64(env), acts))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return total / busy, cores, f"{cores} processes x {envs_per_core} envs x {steps} steps of {ENV_ID} (random actions), {wall:.1f} s wall"
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    # bounded sample: ~steps*envs sized so that each measured step lasts a few seconds in total
+    cores = os.cpu_count() or 1
+    per_core, steps = 16, 200                      # one bench "step" = 16 full 200-step episodes per core
+    vals = []
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_throughput(1, 20, cores)
+    reps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        v, c, sample = cpu_oracle_throughput(per_core, steps, cores)
+        vals.append(v)
+    ms_per = (time.perf_counter() - t0) * 1e3 / reps
+    value = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID}, random actions, CPU oracle port of the path (PyBullet itself is not installable here)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f", median of {reps}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--envs-per-gpu", type=int, default=196608)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from assistive_vr_gym_b200 import make
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    E = args.envs_per_gpu
+    env = make(ENV_ID, num_envs=E, device=local_rank, seed=1001 + rank)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(rank)
+    ring = [torch.rand((E, 7), device=dev, generator=gen) * 2 - 1 for _ in range(8)]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for w in range(max(args.warmup, 3)):
+        env.step(ring[w % 8])
+    env.elapsed = 0
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = env.sim.launch_count
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    stats = torch.zeros(4, device=dev)
+    for k in range(args.steps):
+        obs, rew, done, info = env.step(ring[k % 8])
+        env.elapsed = 0                              # keep the timed window free of TimeLimit resets
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.sim.launch_count - launches0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    # episode statistics: the only collective of the path (NCCL all-reduce of a 4-float vector)
+    stats[0] = rew.sum(); stats[1] = info["task_success"].sum(); stats[2] = info["total_force_on_human"].sum(); stats[3] = float(E)
+    t = torch.tensor([ms], device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    value = E * world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer API (bounded to keep the run short) ----------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    a_host = [np.random.RandomState(100 + rank + i).uniform(-1, 1, (E, 7)).astype(np.float32) for i in range(2)]
+    env.step_host(a_host[0]); env.elapsed = 0
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        o, r, d, i = env.step_host(a_host[k % 2]); env.elapsed = 0
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    te = torch.tensor([e2e_ms], device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = E * world * e2e_steps / (float(te.item()) * 1e-3)
+    h2d = E * 7 * 4
+    d2h = E * (env.sim.n_obs * 4 + 4 + 8 + 1)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        bpe = env.sim.bytes_per_env_step
+        launch_ms = ms / max(1, launches)
+        achieved = bpe * E / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{ENV_ID}, {E} envs/GPU, uniform random actions (seed 0), random-reset states (seed 1001), "
+                                       f"5 sub-steps x 50 PGS iterations per env-step",
+                           "envs_per_gpu": E, "l2": "state + I/O per GPU = %.0f MB > 126 MB L2 (inputs larger than L2)" % ((E * (768 + 37 * 4 + 13)) / 1e6),
+                           "parallelism": f"env-sharded x{world}, no step-path collective"},
+                "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": peak_src, "bytes_per_env_step": bpe,
+                             "note": "latency/FP32-issue bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks"},
+                "clocks": sampler.summary(),
+                "episode_stats": {"mean_reward_last_step": float(stats[0] / stats[3]), "task_success": float(stats[1]),
+                                  "mean_force_on_human": float(stats[2] / stats[3])}}
+        if not args.no_cpu_baseline and world == 1:
+            v, c, sample = cpu_oracle_throughput(16, 200)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
