@@ -8,7 +8,7 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 3
+AVG_VERSION = 4
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -29,6 +29,7 @@ SHAPE_DT = np.dtype([
     ("friction", "<f4"), ("thr", "<f4"), ("aabb_c", "<f4", 3), ("aabb_h", "<f4", 3), ("pad", "<i4", 4),
 ])
 FRAME_DT = np.dtype([("body", "<i4"), ("pos", "<f4", 3), ("quat", "<f4", 4)])
+BPS_DT = np.dtype([("c", "<f4", 3), ("h", "<f4", 3), ("thr", "<f4"), ("mask", "<u4")])
 HEADER_DT = np.dtype([
     ("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("task", "<i4"),
     ("n_body", "<i4"), ("n_ebody", "<i4"), ("n_dof", "<i4"), ("n_jdof", "<i4"), ("n_free", "<i4"),
@@ -40,7 +41,8 @@ HEADER_DT = np.dtype([
     ("action_scale", "<f4"), ("weld_max_force", "<f4"), ("weld_body_a", "<i4"), ("weld_body_b", "<i4"),
     ("task_f", "<f4", 32),
     ("off_body", "<u4"), ("off_dof", "<u4"), ("off_shape", "<u4"), ("off_vert", "<u4"), ("off_plane", "<u4"),
-    ("off_pair", "<u4"), ("off_frame", "<u4"), ("pad", "<u4", 8),
+    ("off_pair", "<u4"), ("off_frame", "<u4"), ("off_bps", "<u4"), ("off_bpm", "<u4"),
+    ("n_block", "<i4"), ("block_start", "<i4", 4), ("pad", "<u4", 1),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
 
@@ -100,6 +102,30 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     for i, (b, p, q) in enumerate(scene.frames):
         frames[i]["body"] = b; frames[i]["pos"] = p; frames[i]["quat"] = q
 
+    # broadphase tables (same pair set as `pairs`, organised for the device loop)
+    nms = scene.n_mshape
+    bps = np.zeros(len(scene.shapes) - nms, dtype=BPS_DT)
+    bpm = np.zeros(nms, dtype="<u4")
+    for i in range(nms, len(scene.shapes)):
+        bps[i - nms]["c"] = shapes[i]["aabb_c"]; bps[i - nms]["h"] = shapes[i]["aabb_h"]; bps[i - nms]["thr"] = shapes[i]["thr"]
+    for a, b in scene.pairs:
+        if b >= nms:
+            bps[b - nms]["mask"] |= np.uint32(1 << a)
+        else:
+            assert b > a
+            bpm[a] |= np.uint32(1 << b)
+    # diagonal blocks of the mass matrix: consecutive joint dofs of one articulation
+    starts = []
+    last_art = None
+    for i, b in enumerate(scene.bodies):
+        if b.jtype == JOINT_FREE:
+            continue
+        if b.art != last_art:
+            starts.append(b.dof); last_art = b.art
+    n_block = len(starts)
+    assert n_block <= 3
+    starts = starts + [int(scene.header["n_jdof"])] * (4 - n_block)
+
     hdr = np.zeros(1, dtype=HEADER_DT)
     h = hdr[0]
     h["magic"] = AVG_MAGIC; h["version"] = AVG_VERSION
@@ -110,10 +136,11 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
         h[k] = v
     h["n_shape"] = len(shapes); h["n_mshape"] = scene.n_mshape; h["n_vert"] = len(verts); h["n_plane"] = len(planes)
     h["n_pair"] = len(pairs); h["n_frame"] = len(frames)
+    h["n_block"] = n_block; h["block_start"] = starts
     off = _align(HEADER_DT.itemsize)
     sections = []
     for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
-                      ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames)):
+                      ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm)):
         h[name] = off
         sections.append((off, arr.tobytes()))
         off = _align(off + arr.nbytes)
@@ -136,4 +163,6 @@ def read_blob(blob: bytes) -> dict:
     out["planes"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_plane"]), offset=int(h["off_plane"])).reshape(-1, 4)
     out["pairs"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_pair"]), offset=int(h["off_pair"]))
     out["frames"] = np.frombuffer(blob, dtype=FRAME_DT, count=int(h["n_frame"]), offset=int(h["off_frame"]))
+    out["bps"] = np.frombuffer(blob, dtype=BPS_DT, count=int(h["n_shape"] - h["n_mshape"]), offset=int(h["off_bps"]))
+    out["bpm"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_mshape"]), offset=int(h["off_bpm"]))
     return out

@@ -53,8 +53,8 @@ class ShapeDesc:
         elif self.kind == SHAPE_HULL:
             m = 0.001 if margin_in_aabb else 0.0
             return self.verts.min(0) - m, self.verts.max(0) + m
-        else:
-            h = np.full(3, 1e3)
+        else:                       # ground plane = the reference's 30 x 30 x 10 box centred at z = -5 (plane.urdf)
+            return np.array([-15.0, -15.0, -10.0]), np.array([15.0, 15.0, 0.0])
         return -h, h
 
 

@@ -20,6 +20,12 @@
 #include "avg_math.cuh"
 #include "avg_kernels.h"
 
+// Phase alignment: the warps of a block enter collision / dynamics / solver together so that the SM's instruction
+// cache serves one phase at a time (the fused kernel is far larger than the 32 KB L1.5 I-cache).
+#ifndef AVG_PHASE_SYNC
+#define AVG_PHASE_SYNC() __syncthreads()
+#endif
+
 namespace {
 
 constexpr int kWarpsPerBlock = AVG_K_WARPS_PER_BLOCK;
@@ -38,12 +44,11 @@ struct __align__(16) WarpSm {
     float freeInv[2][12];                  // free bodies: [0] 1/m, [1..9] inverse world inertia
     float J[kMaxDense][32];
     float W[kMaxDense][32];
-    float r_tgt[kMaxRows], r_inv[kMaxRows], r_lo[kMaxRows], r_hi[kMaxRows], r_lam[kMaxRows], r_mu[kMaxRows];
-    int r_idx[kMaxRows];                   // (kind << 8) | index; kind 0: +e_i, 1: -e_i, 2: dense row
-    int r_par[kMaxRows];                   // friction rows: row index of their normal row, else -1
-    float sp[kMaxMS][3];                   // moving shapes: world position, rotation, AABB
+    float4 r_a[kMaxRows];                  // per row: target velocity change, 1/diag, lower, upper impulse bound
+    float4 r_b[kMaxRows];                  // per row: diag, friction coefficient, index (int), normal row of a friction row (int)
+    float sp[kMaxMS][3];                   // moving shapes: world position, rotation, AABB (centre, half extents, thr, pad)
     float sR[kMaxMS][9];
-    float saabb[kMaxMS][6];
+    float4 saabb[kMaxMS][2];
     uint32_t cand[kMaxCand];
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
     int c_sa[kMaxC], c_sb[kMaxC];
@@ -59,6 +64,8 @@ struct KM {                                // device view of a ModelBlob
     const float* plane;
     const uint32_t* pair;
     const AvgFrame* frame;
+    const AvgBpStatic* bps;
+    const uint32_t* bpm;
 };
 
 __device__ __forceinline__ KM open_model(const unsigned char* blob) {
@@ -71,6 +78,8 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     m.plane = reinterpret_cast<const float*>(blob + m.h->off_plane);
     m.pair = reinterpret_cast<const uint32_t*>(blob + m.h->off_pair);
     m.frame = reinterpret_cast<const AvgFrame*>(blob + m.h->off_frame);
+    m.bps = reinterpret_cast<const AvgBpStatic*>(blob + m.h->off_bps);
+    m.bpm = reinterpret_cast<const uint32_t*>(blob + m.h->off_bpm);
     return m;
 }
 
@@ -78,7 +87,7 @@ __device__ __forceinline__ void body_pose(const WarpSm& s, int b, V3& p, Q4& q) 
     if (b < 0) { p = mk3(0, 0, 0); q = mkq(0, 0, 0, 1); }
     else { p = ld3(s.bp[b]); q = ldq(s.bq[b]); }
 }
-__device__ __forceinline__ void frame_pose(const KM& m, const WarpSm& s, int f, V3& p, Q4& q) {
+__device__ __noinline__ void frame_pose(const KM& m, const WarpSm& s, int f, V3& p, Q4& q) {
     const AvgFrame* F = &m.frame[f];
     V3 bp; Q4 bq;
     body_pose(s, F->body, bp, bq);
@@ -90,7 +99,7 @@ __device__ __forceinline__ void frame_pose(const KM& m, const WarpSm& s, int f, 
 // Forward kinematics: every lane builds its body's transform relative to the parent body, then the chain products
 // are formed by pointer jumping over the parent array (log2(depth) shuffle rounds instead of a serial walk).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void fk_warp(const KM& m, WarpSm& s, int lane, int nb) {
+__device__ __noinline__ void fk_warp(const KM& m, WarpSm& s, int lane, int nb) {
     V3 p = mk3(0, 0, 0); Q4 q = mkq(0, 0, 0, 1);
     int anc = -1;
     if (lane < nb) {
@@ -151,7 +160,7 @@ __device__ __forceinline__ void load_wshape(const KM& m, const WarpSm& s, int si
     }
 }
 
-__device__ V3 support(const WShape& w, V3 d) {
+__device__ __noinline__ V3 support(const WShape& w, V3 d) {
     const AvgShape* S = w.s;
     V3 l = mtmul(w.R, d), r;
     switch (S->type) {
@@ -170,6 +179,7 @@ __device__ V3 support(const WShape& w, V3 d) {
     case AVG_SHAPE_HULL: {
         int best = 0; float bd = -3.0e38f;
         const float* v = w.verts;
+#pragma unroll 4
         for (int i = 0; i < S->vert_cnt; ++i) {
             float dd = fmaf(l.x, v[3 * i], fmaf(l.y, v[3 * i + 1], l.z * v[3 * i + 2]));
             if (dd > bd) { bd = dd; best = i; }
@@ -253,11 +263,12 @@ __device__ bool simplex_closest(Simplex& s, V3& v) {
 
 // returns false: cores separated (dist, pa, pb valid); true: cores overlap.  Works relative to A's position to keep
 // float32 magnitudes small.
-__device__ bool gjk(const WShape& A, const WShape& B, float& dist, V3& pa, V3& pb) {
+__device__ __noinline__ bool gjk(const WShape& A, const WShape& B, float& dist, V3& pa, V3& pb) {
     Simplex s; s.n = 0;
     V3 org = A.p;
     V3 v = A.p - B.p;
     if (dot(v, v) < 1e-12f) v = mk3(1, 0, 0);
+#pragma unroll 1
     for (int it = 0; it < 32; ++it) {
         V3 sa = support(A, -v) - org, sb = support(B, v) - org;
         V3 w = sa - sb;
@@ -335,7 +346,7 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
     return true;
 }
 
-__device__ void collide_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
+__device__ __noinline__ void collide_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
     const AvgModelHeader* h = m.h;
     const int nms = h->n_mshape;
     // world pose + AABB of the moving shapes
@@ -350,43 +361,84 @@ __device__ void collide_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         for (int i = 0; i < 9; ++i) s.sR[lane][i] = R.m[i];
         V3 lc = ld3(S->aabb_c), lh = ld3(S->aabb_h);
         V3 c = p + mmul(R.m, lc);
-        s.saabb[lane][0] = c.x; s.saabb[lane][1] = c.y; s.saabb[lane][2] = c.z;
-        s.saabb[lane][3] = fabsf(R.m[0]) * lh.x + fabsf(R.m[1]) * lh.y + fabsf(R.m[2]) * lh.z;
-        s.saabb[lane][4] = fabsf(R.m[3]) * lh.x + fabsf(R.m[4]) * lh.y + fabsf(R.m[5]) * lh.z;
-        s.saabb[lane][5] = fabsf(R.m[6]) * lh.x + fabsf(R.m[7]) * lh.y + fabsf(R.m[8]) * lh.z;
+        s.saabb[lane][0] = make_float4(c.x, c.y, c.z, fabsf(R.m[0]) * lh.x + fabsf(R.m[1]) * lh.y + fabsf(R.m[2]) * lh.z);
+        s.saabb[lane][1] = make_float4(fabsf(R.m[3]) * lh.x + fabsf(R.m[4]) * lh.y + fabsf(R.m[5]) * lh.z,
+                                       fabsf(R.m[6]) * lh.x + fabsf(R.m[7]) * lh.y + fabsf(R.m[8]) * lh.z, S->thr, 0.0f);
     }
     __syncwarp();
-    // broadphase over the pair table
+    // broadphase.  Static shapes: one lane per static shape (its AABB, threshold and the bit mask of moving shapes it
+    // may touch arrive in two coalesced 16-byte loads), moving-shape AABBs are broadcast from shared memory.
     int ncand = 0;
-    const int npair = h->n_pair;
-    for (int base = 0; base < npair; base += 32) {
-        int pi = base + lane;
-        bool hit = false;
-        uint32_t pr = 0;
-        if (pi < npair) {
-            pr = __ldg(&m.pair[pi]);
-            int a = pr & 0xffff, b = pr >> 16;
-            const AvgShape* SB = &m.shape[b];
-            float thr = fminf(__ldg(&m.shape[a].thr), __ldg(&SB->thr));
-            const float* A = s.saabb[a];
-            if (__ldg(&SB->type) == AVG_SHAPE_PLANE) hit = (A[2] - A[5]) <= thr;
-            else {
-                float bc0, bc1, bc2, bh0, bh1, bh2;
-                if (b < nms) { const float* Bq = s.saabb[b]; bc0 = Bq[0]; bc1 = Bq[1]; bc2 = Bq[2]; bh0 = Bq[3]; bh1 = Bq[4]; bh2 = Bq[5]; }
-                else { bc0 = __ldg(&SB->aabb_c[0]); bc1 = __ldg(&SB->aabb_c[1]); bc2 = __ldg(&SB->aabb_c[2]);
-                       bh0 = __ldg(&SB->aabb_h[0]); bh1 = __ldg(&SB->aabb_h[1]); bh2 = __ldg(&SB->aabb_h[2]); }
-                hit = fabsf(A[0] - bc0) <= A[3] + bh0 + thr && fabsf(A[1] - bc1) <= A[4] + bh1 + thr && fabsf(A[2] - bc2) <= A[5] + bh2 + thr;
+    const int nstat = h->n_shape - nms;
+    for (int base = 0; base < nstat; base += 32) {
+        const int si = base + lane;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 0, 0);
+        uint32_t mask = 0;
+        if (si < nstat) {
+            const float4* rp = reinterpret_cast<const float4*>(&m.bps[si]);
+            r0 = __ldg(rp); r1 = __ldg(rp + 1);
+            mask = __float_as_uint(r1.w);
+        }
+        for (int a = 0; a < nms; ++a) {
+            const float4 a0 = s.saabb[a][0], a1 = s.saabb[a][1];
+            const float thr = fminf(a1.z, r1.z);
+            bool hit = ((mask >> a) & 1u) && fabsf(a0.x - r0.x) <= a0.w + r0.w + thr && fabsf(a0.y - r0.y) <= a1.x + r1.x + thr &&
+                       fabsf(a0.z - r0.z) <= a1.y + r1.y + thr;
+            unsigned bal = __ballot_sync(AVG_FULL, hit);
+            if (bal) {
+                if (hit) {
+                    int slot = ncand + __popc(bal & ((1u << lane) - 1));
+                    if (slot < kMaxCand) s.cand[slot] = (uint32_t)a | ((uint32_t)(nms + si) << 16);
+                }
+                ncand += __popc(bal);
             }
         }
-        unsigned bal = __ballot_sync(AVG_FULL, hit);
-        if (hit) {
-            int slot = ncand + __popc(bal & ((1u << lane) - 1));
-            if (slot < kMaxCand) s.cand[slot] = pr;
+    }
+    // moving-moving pairs: lane b against every a < b allowed by the filter masks
+    {
+        float4 b0 = make_float4(0, 0, 0, 0), b1 = make_float4(0, 0, 0, 0);
+        if (lane < nms) { b0 = s.saabb[lane][0]; b1 = s.saabb[lane][1]; }
+        for (int a = 0; a < nms; ++a) {
+            const uint32_t mask = __ldg(&m.bpm[a]);
+            if (mask == 0) continue;
+            const float4 a0 = s.saabb[a][0], a1 = s.saabb[a][1];
+            const float thr = fminf(a1.z, b1.z);
+            bool hit = lane < nms && ((mask >> lane) & 1u) && fabsf(a0.x - b0.x) <= a0.w + b0.w + thr &&
+                       fabsf(a0.y - b0.y) <= a1.x + b1.x + thr && fabsf(a0.z - b0.z) <= a1.y + b1.y + thr;
+            unsigned bal = __ballot_sync(AVG_FULL, hit);
+            if (bal) {
+                if (hit) {
+                    int slot = ncand + __popc(bal & ((1u << lane) - 1));
+                    if (slot < kMaxCand) s.cand[slot] = (uint32_t)a | ((uint32_t)lane << 16);
+                }
+                ncand += __popc(bal);
+            }
         }
-        ncand += __popc(bal);
     }
     if (ncand > kMaxCand) { overflow |= 4; ncand = kMaxCand; }
     __syncwarp();
+    // canonical order = pair-table order: ascending (moving shape a, other shape b); rank by counting (lists are short)
+    {
+        uint32_t mine[2]; int rank[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            int ci = lane + 32 * t;
+            mine[t] = ci < ncand ? s.cand[ci] : 0u; rank[t] = 0;
+        }
+        for (int j = 0; j < ncand; ++j) {
+            uint32_t o = s.cand[j];
+            uint32_t ko = ((o & 0xffffu) << 16) | (o >> 16);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint32_t km = ((mine[t] & 0xffffu) << 16) | (mine[t] >> 16);
+                rank[t] += ko < km;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) if (lane + 32 * t < ncand) s.cand[rank[t]] = mine[t];
+        __syncwarp();
+    }
     // narrowphase: one lane per candidate, results compacted in pair order
     int nc = 0;
     for (int base = 0; base < ncand; base += 32) {
@@ -425,7 +477,7 @@ struct LaneDyn {
 };
 
 // Jacobian entry of lane `lane` (dof) for "velocity of world point r on `body` along n", sign applied.
-__device__ __forceinline__ float jac_point_lane(const KM& m, const WarpSm& s, const LaneDyn& L, int lane, int nj, int body,
+__device__ __noinline__ float jac_point_lane(const KM& m, const WarpSm& s, const LaneDyn& L, int lane, int nj, int body,
                                                 V3 r, V3 n, V3 ref) {
     if (body < 0) return 0.0f;
     const AvgBody* B = &m.body[body];
@@ -454,7 +506,7 @@ __device__ __forceinline__ float jac_ang_lane(const KM& m, const LaneDyn& L, int
 }
 
 // W = M^-1 J^T for the dense row d (J already in smem), returns J.W (diag) and J.qd (u0) reduced over the warp
-__device__ __forceinline__ void finish_dense_row(const KM& m, WarpSm& s, int lane, int nj, int nd, int d, float qd, float& diag, float& u0) {
+__device__ __noinline__ void finish_dense_row(const KM& m, WarpSm& s, int lane, int nj, int nd, int d, float qd, float& diag, float& u0) {
     __syncwarp();
     float w = 0.0f;
     float jl = s.J[d][lane];
@@ -473,7 +525,7 @@ __device__ __forceinline__ void finish_dense_row(const KM& m, WarpSm& s, int lan
     u0 = warp_sum(jl * qd);
 }
 
-__device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
+__device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow, int& solver_iters) {
     const AvgModelHeader* h = m.h;
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
@@ -481,6 +533,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
 
     fk_warp(m, s, lane, nb);
     collide_warp(m, s, lane, ncontact, overflow);
+    AVG_PHASE_SYNC();
 
     // ---- per-lane body quantities ------------------------------------------------------------------------------
     LaneDyn L; L.S = mksv(mk3(0, 0, 0), mk3(0, 0, 0)); L.anc = 0;
@@ -571,6 +624,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
     }
     // ---- subtree sums (composite inertia, bias force) ------------------------------------------------------------
     Inertia Ic_sub = I; Sv f_sub = fb;
+#pragma unroll 1
     for (int k = 0; k < nj; ++k) {
         uint32_t mk = __shfl_sync(AVG_FULL, L.anc, k);
         float m_k = __shfl_sync(AVG_FULL, I.m, k);
@@ -587,6 +641,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
     Sv F = inertia_mul(Ic_sub, L.S);          // composite inertia times own motion subspace
     float Cb = dot(L.S, f_sub);               // generalized bias force of this lane's joint
     // ---- joint-space mass matrix, M_ij = S_i . (Ic_j S_j) for i ancestor-or-self of j ----------------------------
+#pragma unroll 1
     for (int j = 0; j < nj; ++j) {
         Sv Fj = shflsv(F, j), Sj = shflsv(L.S, j);
         uint32_t mj = __shfl_sync(AVG_FULL, L.anc, j);
@@ -598,22 +653,31 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         }
     }
     __syncwarp();
-    // ---- in-place Gauss-Jordan inverse (symmetric positive definite, no pivoting); frozen dofs (M_kk ~ 0) give 0 --
-    for (int k = 0; k < nj; ++k) {
-        float p = s.Minv[k][k];
-        float ip = p > 1e-20f ? 1.0f / p : 0.0f;
-        __syncwarp();
-        for (int e = lane; e < nj * nj; e += 32) {
-            int i = e / nj, cidx = e - i * nj;
-            if (i != k && cidx != k) s.Minv[i][cidx] -= s.Minv[i][k] * s.Minv[k][cidx] * ip;
+    // ---- in-place Gauss-Jordan inverse of the block-diagonal mass matrix (one block per articulation, SPD, no
+    //      pivoting).  Lane c owns column c; the blocks are swept concurrently; frozen dofs (M_kk ~ 0) invert to 0.
+    {
+        int bs = 0, be = 0, maxblk = 0;
+        for (int b = 0; b < h->n_block; ++b) {
+            const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
+            if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
+            maxblk = max(maxblk, b1 - b0);
         }
-        __syncwarp();
-        if (lane < nj && lane != k) {
-            float rk = s.Minv[k][lane] * ip, ck = s.Minv[lane][k] * (-ip);
-            s.Minv[k][lane] = rk; s.Minv[lane][k] = ck;
+        for (int kk = 0; kk < maxblk; ++kk) {
+            const int k = bs + kk;
+            const bool act = k < be;
+            float ip = 0.0f, mkc = 0.0f;
+            if (act) { const float p = s.Minv[k][k]; ip = p > 1e-20f ? 1.0f / p : 0.0f; mkc = s.Minv[k][lane]; }
+            if (act && lane != k) {
+                const float f = mkc * ip;
+                for (int i = bs; i < be; ++i) if (i != k) s.Minv[i][lane] = fmaf(-s.Minv[i][k], f, s.Minv[i][lane]);
+            }
+            __syncwarp();
+            if (act) {
+                if (lane != k) { s.Minv[k][lane] = mkc * ip; s.Minv[lane][k] *= -ip; }
+                else s.Minv[k][k] = ip;
+            }
+            __syncwarp();
         }
-        if (lane == k) s.Minv[k][k] = ip;
-        __syncwarp();
     }
     // ---- unconstrained velocity update: qd* = qd + dt M^-1 (-C) ---------------------------------------------------
     float qdd = 0.0f;
@@ -660,8 +724,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         if (has) {
             int r = nr + __popc(bal & ((1u << lane) - 1));
             float diag = s.Minv[lane][lane];
-            s.r_tgt[r] = tgt; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f; s.r_lo[r] = lo; s.r_hi[r] = hi; s.r_lam[r] = 0;
-            s.r_mu[r] = 0; s.r_idx[r] = (0 << 8) | lane; s.r_par[r] = -1;
+            s.r_a[r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float(lane), __int_as_float(-1));
         }
         nr += __popc(bal);
     }
@@ -683,14 +746,14 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
             int r = nr + __popc(bal & ((1u << lane) - 1));
             if (r < kMaxRows) {
                 float diag = s.Minv[lane][lane];
-                s.r_tgt[r] = tgt; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f; s.r_lo[r] = 0; s.r_hi[r] = 100.0f; s.r_lam[r] = 0;
-                s.r_mu[r] = 0; s.r_idx[r] = (kind << 8) | lane; s.r_par[r] = -1;
+                s.r_a[r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 100.0f); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((kind << 8) | lane), __int_as_float(-1));
             }
         }
         nr += __popc(bal);
         if (nr > kMaxRows - 6) { overflow |= 2; nr = kMaxRows - 6; }
     }
     // tool weld, 6 dense rows
+    const int ns = nr;                       // rows [0, ns) are unit rows (+-e_i), rows [ns, nr) are dense
     int ndense = 0;
     {
         V3 pa, pb; Q4 qa, qb;
@@ -703,6 +766,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         if (sn > 1e-9f) { float ang = 2.0f * atan2f(sn, dq.w) / sn; rotv = mk3(dq.x * ang, dq.y * ang, dq.z * ang); }
         V3 perr = pa - pb;
         float maxi = h->weld_max_force * dt;
+#pragma unroll 1
         for (int ax = 0; ax < 6; ++ax) {
             V3 e = mk3((ax % 3) == 0, (ax % 3) == 1, (ax % 3) == 2);
             float jl, err;
@@ -718,8 +782,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
             finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
             if (lane == 0) {
                 int r = nr;
-                s.r_tgt[r] = -err * h->erp / dt - u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
-                s.r_lo[r] = -maxi; s.r_hi[r] = maxi; s.r_lam[r] = 0; s.r_mu[r] = 0; s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = -1;
+                s.r_a[r] = make_float4(-err * h->erp / dt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, -maxi, maxi); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
             }
             nr++; ndense++;
         }
@@ -728,6 +791,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
     int nc = ncontact;
     if (nc > (kMaxRows - nr) / 2) { overflow |= 2; nc = (kMaxRows - nr) / 2; ncontact = nc; }
     const int first_contact_row = nr;
+#pragma unroll 1
     for (int ci = 0; ci < nc; ++ci) {
         V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
         int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
@@ -738,11 +802,11 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         if (lane == 0) {
             float dist = s.c_dist[ci];
             int r = nr;
-            s.r_tgt[r] = (dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
-            s.r_lo[r] = 0; s.r_hi[r] = 1e30f; s.r_lam[r] = 0; s.r_mu[r] = 0; s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = -1;
+            s.r_a[r] = make_float4((dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 1e30f); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
         }
         nr++; ndense++;
     }
+#pragma unroll 1
     for (int ci = 0; ci < nc; ++ci) {
         V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
         int sa = s.c_sa[ci], sb = s.c_sb[ci];
@@ -762,51 +826,79 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
         if (lane == 0) {
             int r = nr;
-            s.r_tgt[r] = -u0; s.r_inv[r] = diag > 1e-12f ? 1.0f / diag : 0.0f;
-            s.r_lo[r] = 0; s.r_hi[r] = 0; s.r_lam[r] = 0; s.r_mu[r] = m.shape[sa].friction * m.shape[sb].friction;
-            s.r_idx[r] = (2 << 8) | ndense; s.r_par[r] = first_contact_row + ci;
+            s.r_a[r] = make_float4(-u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 0.0f); s.r_b[r] = make_float4(diag, m.shape[sa].friction * m.shape[sb].friction, __int_as_float((2 << 8) | ndense), __int_as_float(first_contact_row + ci));
         }
         nr++; ndense++;
     }
     __syncwarp();
 
-    // ---- projected Gauss-Seidel, strict row order; dv lives in one register per lane ----------------------------
-    float dv = 0.0f;
+    AVG_PHASE_SYNC();
+    // ---- projected Gauss-Seidel, strict row order (unit rows, dense bilateral/normal rows, friction rows).
+    //      dv lives in one register per lane; the accumulated impulse of row r lives in lane r%32 (slot r/32).
+    float dv = 0.0f, lam0 = 0.0f, lam1 = 0.0f;
     const float thr = h->residual_thr;
+    const int nfr = first_contact_row + nc;    // first friction row
+    int iters = 0;
     for (int it = 0; it < h->solver_iters; ++it) {
         float resid = 0.0f;
-        for (int r = 0; r < nr; ++r) {
-            float inv = s.r_inv[r];
-            if (inv == 0.0f) continue;
-            int idx = s.r_idx[r];
-            int kind = idx >> 8, i = idx & 0xff;
-            float jdv, wl;
-            if (kind == 2) {
-                wl = s.W[i][lane];
-                jdv = warp_sum(s.J[i][lane] * dv);
-            } else {
-                float sg = kind == 0 ? 1.0f : -1.0f;
-                jdv = sg * __shfl_sync(AVG_FULL, dv, i);
-                wl = lane < nj ? sg * s.Minv[i][lane] : 0.0f;
-            }
-            float lo = s.r_lo[r], hi = s.r_hi[r];
-            int par = s.r_par[r];
-            if (par >= 0) { float lim = s.r_mu[r] * s.r_lam[par]; lo = -lim; hi = lim; }
-            float lam = s.r_lam[r];
-            float delta = (s.r_tgt[r] - jdv) * inv;
-            float sum = fminf(fmaxf(lam + delta, lo), hi);
+#pragma unroll 2
+        for (int r = 0; r < ns; ++r) {
+            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
+            const int idx = __float_as_int(rb.z), i = idx & 0xff;
+            const float sg = (idx >> 8) ? -1.0f : 1.0f;
+            const float jdv = sg * __shfl_sync(AVG_FULL, dv, i);
+            const float wl = lane < nj ? sg * s.Minv[i][lane] : 0.0f;
+            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
+            float delta = (ra.x - jdv) * ra.y;
+            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
             delta = sum - lam;
-            __syncwarp();
-            if (lane == 0) s.r_lam[r] = sum;
-            __syncwarp();
+            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
             dv = fmaf(wl, delta, dv);
-            float rv = delta / inv;
+            const float rv = delta * rb.x;
             resid = fmaxf(resid, rv * rv);
         }
+#pragma unroll 1
+        for (int r = ns; r < nfr; ++r) {
+            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
+            const int d = r - ns;
+            const float jdv = warp_sum(s.J[d][lane] * dv);
+            const float wl = s.W[d][lane];
+            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
+            float delta = (ra.x - jdv) * ra.y;
+            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
+            delta = sum - lam;
+            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
+            dv = fmaf(wl, delta, dv);
+            const float rv = delta * rb.x;
+            resid = fmaxf(resid, rv * rv);
+        }
+#pragma unroll 1
+        for (int r = nfr; r < nr; ++r) {
+            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
+            const int d = r - ns, par = __float_as_int(rb.w);
+            const float jdv = warp_sum(s.J[d][lane] * dv);
+            const float wl = s.W[d][lane];
+            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
+            const float lim = rb.y * __shfl_sync(AVG_FULL, par < 32 ? lam0 : lam1, par & 31);
+            float delta = (ra.x - jdv) * ra.y;
+            const float sum = fminf(fmaxf(lam + delta, -lim), lim);
+            delta = sum - lam;
+            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
+            dv = fmaf(wl, delta, dv);
+            const float rv = delta * rb.x;
+            resid = fmaxf(resid, rv * rv);
+        }
+        iters++;
         if (resid <= thr) break;
     }
-    for (int ci = lane; ci < nc; ci += 32) s.c_lam[ci] = s.r_lam[first_contact_row + ci];
+    solver_iters += iters;
+    for (int ci = 0; ci < nc; ++ci) {
+        const int r = first_contact_row + ci;
+        const float l = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
+        if (lane == 0) s.c_lam[ci] = l;
+    }
 
+    AVG_PHASE_SYNC();
     // ---- integrate ------------------------------------------------------------------------------------------------
     float v = qd + dv;
     if (lane < nj) v = fminf(fmaxf(v, -h->max_vel), h->max_vel);
@@ -848,8 +940,9 @@ __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_step_kernel(AvgStepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= a.n_env) return;
+    const int e_raw = blockIdx.x * kWarpsPerBlock + warp;
+    const bool live = e_raw < a.n_env;
+    const int e = live ? e_raw : a.n_env - 1;           // tail warps shadow the last env (no stores) to keep barriers uniform
     WarpSm& s = reinterpret_cast<WarpSm*>(smem_raw)[warp];
     const int variant = a.variant ? a.variant[e] : 0;
     const KM m = open_model(a.models[variant]);
@@ -909,7 +1002,8 @@ avg_step_kernel(AvgStepArgs a) {
 
     // ---- frame_skip physics sub-steps, env.py:341-349 -----------------------------------------------------------
     int ncontact = 0, overflow = 0;
-    for (int f = 0; f < h->substeps; ++f) substep_warp(m, s, lane, ncontact, overflow);
+    int solver_iters = 0;
+    for (int f = 0; f < h->substeps; ++f) substep_warp(m, s, lane, ncontact, overflow, solver_iters);
 
     // ---- forces, reward, observation (scratch_itch.py:53-128) ---------------------------------------------------
     fk_warp(m, s, lane, h->n_body);
@@ -950,6 +1044,7 @@ avg_step_kernel(AvgStepArgs a) {
         ee_vel = norm(vt);
     }
     __syncwarp();
+    if (!live) return;                                   // no block-wide barrier below this point
     if (lane == 0) {
         float* o = s.obs; int k = 0;
         V3 t;
@@ -993,6 +1088,7 @@ avg_step_kernel(AvgStepArgs a) {
         st3(s.env + AVG_E_TARGET_POS, tgt);
         env_i[AVG_E_ITERATION] = iteration + 1;
         env_i[AVG_E_OVERFLOW] |= overflow;
+        env_i[AVG_E_SOLVER_ITERS] = solver_iters;
         a.reward[e] = reward;
         a.info[2 * e] = total_force_on_human;
         a.info[2 * e + 1] = s.env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;

@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 3u
+#define AVG_VERSION 4u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -83,6 +83,13 @@ typedef struct AvgShape {         /* 32 x 4 bytes */
     int32_t  pad[4];
 } AvgShape;
 
+typedef struct AvgBpStatic {      /* 8 x 4 bytes: broadphase record of one static shape (same pairs as the pair table) */
+    float    c[3];                /* world AABB centre                                                      */
+    float    h[3];                /* world AABB half extents                                                */
+    float    thr;                 /* contact-breaking threshold of the shape                                */
+    uint32_t mask;                /* bit a: moving shape a may collide with this shape                      */
+} AvgBpStatic;
+
 typedef struct AvgFrame {         /* 8 x 4 bytes: a frame rigidly attached to a body */
     int32_t  body;                /* dyn body, n_body+e, or -1 (world)                                       */
     float    pos[3];
@@ -123,7 +130,11 @@ typedef struct AvgModelHeader {
     int32_t  weld_body_a, weld_body_b;   /* dyn body indices (robot EE composite, tool)                      */
     float    task_f[32];          /* task constants, see AVG_TF_*                                             */
     uint32_t off_body, off_dof, off_shape, off_vert, off_plane, off_pair, off_frame;
-    uint32_t pad[8];
+    uint32_t off_bps;             /* AvgBpStatic[n_shape - n_mshape]: broadphase records of the static shapes  */
+    uint32_t off_bpm;             /* uint32[n_mshape]: bit b of entry a = moving pair (a, b), b > a, may collide */
+    int32_t  n_block;             /* diagonal blocks of the joint-space mass matrix (one per articulation)     */
+    int32_t  block_start[4];      /* first dof of each block; block_start[n_block] = n_jdof                    */
+    uint32_t pad[1];
 } AvgModelHeader;
 
 /* task_f indices (config.ini + task files) */
@@ -159,7 +170,8 @@ enum {
     AVG_E_TARGET_POS = 162, /* [3] derived each sub-step, kept for inspection */
     AVG_E_EPISODE_RETURN = 165,
     AVG_E_OVERFLOW = 166,   /* int: bit0 contact overflow, bit1 row overflow (never silently dropped)          */
-    AVG_E_LAST = 167
+    AVG_E_SOLVER_ITERS = 167, /* int: PGS iterations executed in the last env-step (diagnostic) */
+    AVG_E_LAST = 168
 };
 
 /* one reported contact point (parity / debug), 16 floats */

@@ -19,6 +19,7 @@ oracles = [Oracle(b) for b in env.blobs]
 recs = [env_to_f64(state[e]).copy() for e in range(n_env)]
 rng = np.random.RandomState(0)
 lines = []
+shown = 0
 d0 = max(float(np.abs(oracles[int(env.variants[e])].reset_obs(recs[e]) - obs0[e]).max()) for e in range(n_env))
 lines.append(f"reset obs max diff {d0:.3e}")
 for t in range(steps):
@@ -40,6 +41,16 @@ for t in range(steps):
         gp = sorted((int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :ncont[e]])
         op = sorted((int(c[0]), int(c[1])) for c in ocont)
         nc_tot += len(op)
+        derr = float(np.abs(recs[e][:64] - st[e, :64]).max())
+        if t == 0 and len(op) > 0 and derr > 1e-3 and shown < 4:
+            shown += 1
+            lines.append(f"  == env {e} step 0 state err {derr:.3e} variant {int(env.variants[e])} iters gpu {int(st.view(np.int32)[e,167])}")
+            for c in cont[e, :ncont[e]]:
+                lines.append(f"     gpu  ({int(c['shape_a'])},{int(c['shape_b'])}) pa {np.round(c['pos_a'],5)} pb {np.round(c['pos_b'],5)} n {np.round(c['normal'],5)} d {c['dist']:.6f} f {c['force']:.5f}")
+            for c in ocont:
+                lines.append(f"     orcl ({int(c[0])},{int(c[1])}) pa {np.round(c[2:5],5)} pb {np.round(c[5:8],5)} n {np.round(c[8:11],5)} d {c[11]:.6f} f {c[12]:.5f}")
+            lines.append(f"     dq  {np.round(recs[e][:24] - st[e, :24],4)}")
+            lines.append(f"     dqd {np.round(recs[e][32:55] - st[e, 32:55],4)}")
         if gp != op:
             mism += 1
             lines.append(f"  step {t} env {e}: contact sets differ gpu={gp} oracle={op}")
