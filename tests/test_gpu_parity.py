@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the committed golden fixture.
+
+Tolerances (float32 device arithmetic vs float64 oracle; SURVEY.md §8c proposal):
+  contact-free trajectories, 10 env-steps = 50 sub-steps: |dq| <= 1e-4 rad, |dqd| <= 1e-3 rad/s, |dreward| <= 1e-3
+  single sub-step with contacts: |dq| <= 1e-4, |dqd| <= 2e-3, contact-pair sets identical
+Contact dynamics are chaotic (discontinuous hard-limit teleports, feature switches of the closest points), so
+multi-step trajectories WITH contacts are characterised by the divergence curve in profiles/, not by a tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_Q, TOL_QD, TOL_R = 1e-4, 1e-3, 1e-3
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def make_env(n, seed=3, env_id="ScratchItchJaco-v0"):
+    from assistive_vr_gym_b200 import make
+    env = make(env_id, num_envs=n, device=0, seed=seed)
+    env.sim.enable_debug(True)
+    return env
+
+
+def test_extension_is_loaded(torch_cuda):
+    from assistive_vr_gym_b200 import capi
+    lib = capi.load_library(build_if_missing=False)
+    assert os.path.basename(capi.LIB_PATH) == "libavg_b200.so" and lib is not None
+
+
+def test_reset_observation_matches_oracle(torch_cuda, oracles):
+    from oracle.oracle import env_to_f64
+    env = make_env(64)
+    obs = env.reset().cpu().numpy()
+    st = env.get_state()
+    for e in range(64):
+        o = oracles[int(env.variants[e])]
+        assert np.abs(o.reset_obs(env_to_f64(st[e]).copy()) - obs[e]).max() < 1e-5
+    env.close()
+
+
+def test_contact_free_trajectories_match_oracle(torch_cuda, oracles):
+    """10 env-steps of random actions; every env whose oracle AND GPU trajectories stay contact-free must agree."""
+    torch = torch_cuda
+    from oracle.oracle import env_to_f64
+    n, T = 96, 10
+    env = make_env(n, seed=5)
+    env.reset()
+    st0 = env.get_state()
+    recs = [env_to_f64(st0[e]).copy() for e in range(n)]
+    clean = np.ones(n, dtype=bool)
+    rng = np.random.RandomState(0)
+    worst = np.zeros(3)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
+        st = env.get_state(); cont, ncont = env.sim.get_contacts()
+        rew = rew.cpu().numpy(); obs = obs.cpu().numpy()
+        for e in range(n):
+            oobs, orew, oinfo, oc = oracles[int(env.variants[e])].step(recs[e], a[e])
+            if len(oc) or ncont[e]:
+                clean[e] = False
+            if clean[e]:
+                worst = np.maximum(worst, [np.abs(recs[e][:32] - st[e, :32]).max(), np.abs(recs[e][32:64] - st[e, 32:64]).max(),
+                                           abs(orew - rew[e])])
+                assert np.abs(oobs - obs[e]).max() < 1e-3
+    assert clean.sum() >= n // 3, "too few contact-free environments to be meaningful"
+    assert worst[0] <= TOL_Q and worst[1] <= TOL_QD and worst[2] <= TOL_R, worst
+    assert int(st.view(np.int32)[:, 166].max()) == 0          # no overflow flags
+    env.close()
+
+
+def test_single_substep_with_contacts_matches_oracle(torch_cuda, env_data):
+    """frame_skip patched to 1: contact sets bit-exact, state within tolerance, also for envs in contact."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import capi
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from oracle.oracle import Oracle, env_to_f64
+    from helpers import patch_blob
+    blobs, resets = env_data
+    pb = [patch_blob(b, header={"substeps": 1, "residual_thr": 0.0}) for b in blobs]
+    n = 256
+    env0, variant = sample_states(resets, n, np.random.RandomState(3))
+    sim = capi.Sim(n, 0)
+    for v, b in enumerate(pb):
+        sim.upload_model(v, b)
+    sim.enable_debug(True)
+    sim.set_state(env0, variant)
+    obs = torch.zeros((n, 30), device="cuda"); rew = torch.zeros(n, device="cuda"); info = torch.zeros((n, 2), device="cuda")
+    done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    a = np.random.RandomState(0).uniform(-1, 1, (n, 7)).astype(np.float32)
+    act = torch.as_tensor(a, device="cuda")
+    sim.step(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), info.data_ptr(), 0)
+    torch.cuda.synchronize()
+    st = sim.get_state(); cont, nc = sim.get_contacts(); terms = sim.get_reward_terms()
+    oracles = [Oracle(b) for b in pb]
+    in_contact = 0
+    for e in range(n):
+        rec = env_to_f64(env0[e]).copy()
+        o = oracles[int(variant[e])]
+        oobs, orew, oinfo, ocont = o.step(rec, a[e])
+        gp = [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :nc[e]]]
+        op = [(int(c[0]), int(c[1])) for c in ocont]
+        # a pair may legitimately flip when its distance sits within float32 noise of the contact threshold
+        borderline = any(abs(c[11] - min(float(o.model["shapes"][int(c[0])]["thr"]), float(o.model["shapes"][int(c[1])]["thr"]))) < 2e-6 for c in ocont)
+        if not borderline:
+            assert gp == op, (e, gp, op)                    # same pairs, same (pair-table) order
+        if op:
+            in_contact += 1
+            for cg, co in zip(cont[e, :nc[e]], ocont):
+                assert abs(float(cg["dist"]) - co[11]) < 5e-5
+                assert abs(float(cg["force"]) - co[12]) < 5e-3 * max(1.0, abs(co[12]))
+        assert np.abs(rec[:32] - st[e, :32]).max() < 1e-4, e
+        assert np.abs(rec[32:64] - st[e, 32:64]).max() < 2e-3, e
+        assert abs(orew - float(rew[e])) < 1e-3
+        assert np.abs(oinfo[:8] - terms[e]).max() < 5e-3 * max(1.0, np.abs(oinfo).max())
+        assert int(oinfo[1]) == int(terms[e, 1])            # task_success flag (reward-term index) exact
+    assert in_contact >= 10
+    sim.close()
+
+
+def test_golden_fixture_on_gpu(torch_cuda):
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLD, "ScratchItchJaco_oracle.npz"))
+    n = g["env"].shape[0]
+    env = make_env(n)
+    env.set_state(g["env"], g["variant"])
+    assert np.abs(env.obs.cpu().numpy() - g["obs0"]).max() < 1e-5
+    clean = np.ones(n, dtype=bool)
+    for t in range(g["actions"].shape[0]):
+        obs, rew, done, info = env.step(torch.as_tensor(g["actions"][t], device="cuda"))
+        cont, nc = env.sim.get_contacts()
+        clean &= (g["ncontacts"][t] == 0) & (nc == 0)
+        st = env.get_state()
+        sel = clean
+        if sel.any():
+            assert np.abs(st[sel, :32] - g["states"][t][sel, :32]).max() < TOL_Q
+            assert np.abs(rew.cpu().numpy()[sel] - g["reward"][t][sel]).max() < TOL_R
+    assert clean.sum() >= 3
+    env.close()
+
+
+def test_human_active_variant_matches_oracle(torch_cuda):
+    """ScratchItchJacoHuman-v0: 17 actions, 64 observations (scratch_itch.py:18,124)."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200.envs import load_env_data
+    from oracle.oracle import Oracle, env_to_f64
+    blobs, _ = load_env_data("ScratchItchJacoHuman.npz")
+    oracles = [Oracle(b) for b in blobs]
+    n = 48
+    env = make_env(n, seed=9, env_id="ScratchItchJacoHuman-v0")
+    obs0 = env.reset().cpu().numpy()
+    assert obs0.shape == (n, 64)
+    st0 = env.get_state()
+    recs = [env_to_f64(st0[e]).copy() for e in range(n)]
+    rng = np.random.RandomState(1)
+    clean = np.ones(n, dtype=bool)
+    for t in range(5):
+        a = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
+        st = env.get_state(); cont, nc = env.sim.get_contacts(); obs = obs.cpu().numpy()
+        for e in range(n):
+            oobs, orew, oinfo, oc = oracles[int(env.variants[e])].step(recs[e], a[e])
+            if len(oc) or nc[e]:
+                clean[e] = False
+            if clean[e]:
+                assert np.abs(recs[e][:32] - st[e, :32]).max() < TOL_Q
+                assert np.abs(oobs - obs[e]).max() < 1e-3
+    assert clean.sum() >= n // 4
+    env.close()

@@ -1,0 +1,120 @@
+"""Size-independent properties of the CUDA path at BASELINE sizes, ragged sizes, and the host-buffer entry point."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _run(torch, n, steps, seed=1, replicate=False):
+    from assistive_vr_gym_b200 import make
+    env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=seed)
+    env.reset()
+    if replicate:                                    # every env = env 0
+        st = env.get_state()
+        env.set_state(np.repeat(st[:1], n, axis=0), np.repeat(env.variants[:1], n))
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    outs = []
+    for t in range(steps):
+        a = torch.rand((1 if replicate else n, 7), device="cuda", generator=gen) * 2 - 1
+        if replicate:
+            a = a.expand(n, 7).contiguous()
+        obs, rew, done, info = env.step(a)
+        outs.append((obs.clone(), rew.clone()))
+    st = env.get_state()
+    env.close()
+    return outs, st
+
+
+@pytest.mark.parametrize("n", [1, 3, 33, 130])
+def test_ragged_batch_sizes(torch_cuda, n):
+    """Batch sizes that are not multiples of the warps-per-block: every env is stepped, none twice."""
+    outs, st = _run(torch_cuda, n, 2)
+    assert st.shape[0] == n and np.all(st.view(np.int32)[:, 152] == 2)           # iteration counter
+    assert np.isfinite(st).all()
+
+
+def test_determinism_and_replication_at_scale(torch_cuda):
+    """32768 envs (config 5's per-box size): identical envs give bit-identical outputs; reruns are bit-identical."""
+    torch = torch_cuda
+    n = 32768
+    o1, s1 = _run(torch, n, 3, replicate=True)
+    for obs, rew in o1:
+        assert torch.equal(obs, obs[:1].expand_as(obs)) and torch.equal(rew, rew[:1].expand_as(rew))
+    o2, s2 = _run(torch, n, 3, replicate=True)
+    assert np.array_equal(s1, s2)
+
+
+def test_state_invariants_at_scale(torch_cuda):
+    torch = torch_cuda
+    n = 65536
+    outs, st = _run(torch, n, 5, seed=2)
+    iv = st.view(np.int32)
+    assert np.isfinite(st[:, :64]).all() and np.isfinite(outs[-1][0].cpu().numpy()).all()
+    assert np.abs(np.linalg.norm(st[:, 20:24], axis=1) - 1).max() < 1e-4          # tool quaternion stays unit
+    assert np.all(iv[:, 166] & 3 == 0)                                            # no contact / row overflow
+    assert np.all(iv[:, 152] == 5) and np.all(iv[:, 167] <= 5 * 50)
+    # human joints never leave their (scaled) limits: enforce_hard_human_joint_limits, env.py:389-410
+    from assistive_vr_gym_b200.envs import load_env_data
+    _, resets = load_env_data("ScratchItchJaco.npz")
+    rd = resets[0]
+    hq = st[:, rd["hum_qidx"]]; ls = st[:, 97][:, None]
+    assert np.all(hq >= rd["hum_lower"][None] * ls - 1e-5) and np.all(hq <= rd["hum_upper"][None] * ls + 1e-5)
+    # the weld keeps the tool at the end effector
+    obs = outs[-1][0].cpu().numpy()
+    assert np.percentile(np.linalg.norm(obs[:, 0:3], axis=1), 99) < 1.2
+
+
+def test_step_host_equals_device_step(torch_cuda):
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 257
+    a = np.random.RandomState(0).uniform(-1, 1, (3, n, 7)).astype(np.float32)
+    e1 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e1.reset()
+    e2 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e2.reset()
+    for t in range(3):
+        o1, r1, d1, i1 = e1.step(torch.as_tensor(a[t], device="cuda"))
+        o2, r2, d2, i2 = e2.step_host(a[t])
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(i1["task_success"].cpu().numpy(), i2["task_success"])
+    e1.close(); e2.close()
+
+
+def test_reference_shaped_single_env(torch_cuda):
+    """examples/random_actions.py shape: make -> reset -> step(action_space.sample()) with the reference's types."""
+    from assistive_vr_gym_b200 import make
+    env = make("ScratchItchJaco-v0")
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.shape == (30,)
+    obs, reward, done, info = env.step(env.action_space.sample())
+    assert obs.shape == (30,) and isinstance(reward, float) and done is False
+    assert set(info) >= {"total_force_on_human", "task_success", "action_robot_len", "action_human_len", "obs_robot_len", "obs_human_len"}
+    assert info["action_robot_len"] == 7 and info["obs_robot_len"] == 30 and info["task_success"] in (0, 1)
+    env.close()
+
+
+def test_time_limit(torch_cuda):
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    env = make("ScratchItchJaco-v0", num_envs=4)
+    env.reset()
+    a = torch.zeros((4, 7), device="cuda")
+    for t in range(200):
+        obs, rew, done, info = env.step(a)
+        assert bool(done.any()) == (t == 199)        # TimeLimit(200), __init__.py:21; the env itself never terminates
+    env.close()
+
+
+def test_unknown_ids():
+    from assistive_vr_gym_b200 import make
+    with pytest.raises(NotImplementedError):
+        make("FeedingPR2-v0", num_envs=1)
+    with pytest.raises(KeyError):
+        make("NoSuchEnv-v0", num_envs=1)

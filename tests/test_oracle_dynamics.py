@@ -101,7 +101,7 @@ def test_position_motor_reaches_target_velocity(env_data, states):
     o = Oracle(blob)
     rec = states[3].copy()
     q0 = rec[:7].copy()
-    act = np.array([0.5, -0.5, 0.2, 0, 0, 0, 0], dtype=np.float32)     # small enough that the 1 N m clamp is inactive
+    act = np.array([0.1, -0.1, 0.2, 0, 0, 0, 0], dtype=np.float32)     # small enough that the 1 N m clamp is inactive
     o.step(rec, act)
     target = q0 + np.clip(act, -1, 1).astype(np.float32) * np.float32(0.05) * 1      # frame_skip patched to 1
     expect = 0.05 * (target - q0) / 0.02
