@@ -164,7 +164,7 @@ __device__ __noinline__ V3 support(const WShape& w, V3 d) {
     const AvgShape* S = w.s;
     V3 l = mtmul(w.R, d), r;
     switch (S->type) {
-    case AVG_SHAPE_CAPSULE: r = mk3(0, 0, l.z >= 0 ? S->half[2] : -S->half[2]); break;
+    case AVG_SHAPE_CAPSULE: r = mk3(0, 0, l.z > 1e-9f ? S->half[2] : (l.z < -1e-9f ? -S->half[2] : 0.0f)); break;
     case AVG_SHAPE_BOX: {
         float hx = S->half[0] - S->margin, hy = S->half[1] - S->margin, hz = S->half[2] - S->margin;
         r = mk3(l.x >= 0 ? hx : -hx, l.y >= 0 ? hy : -hy, l.z >= 0 ? hz : -hz); break;
@@ -293,7 +293,13 @@ __device__ void sat_axis(const WShape& A, const WShape& B, V3 n, float& best, V3
     n = n * (1.0f / ln);
     V3 sa = support(A, -n), sb = support(B, n);
     float depth = dot(sb - sa, n);
-    if (depth < best) { best = depth; bn = n; bpa = sa; }
+    if (depth < best) {
+        // anchor the witness on the round shape when there is one: a polytope's support point along a face normal
+        // is not unique
+        const bool ra = A.s->type == AVG_SHAPE_SPHERE || A.s->type == AVG_SHAPE_CAPSULE;
+        const bool rb = B.s->type == AVG_SHAPE_SPHERE || B.s->type == AVG_SHAPE_CAPSULE;
+        best = depth; bn = n; bpa = (rb && !ra) ? sb - n * depth : sa;
+    }
 }
 __device__ void shape_axes(const WShape& S, const WShape& O, float sign, const WShape& A, const WShape& B, float& best, V3& bn, V3& bpa) {
     const AvgShape* s = S.s;

@@ -198,7 +198,7 @@ static v3 support(const WShape* w, v3 d) {
     v3 l = mtmulv(&w->R, d), r;
     switch (s->type) {
     case AVG_SHAPE_SPHERE: r = V(0, 0, 0); break;
-    case AVG_SHAPE_CAPSULE: r = V(0, 0, l.z >= 0 ? s->half[2] : -s->half[2]); break;
+    case AVG_SHAPE_CAPSULE: r = V(0, 0, l.z > 1e-9 ? s->half[2] : (l.z < -1e-9 ? -s->half[2] : 0.0)); break;
     case AVG_SHAPE_BOX: {
         double hx = s->half[0] - s->margin, hy = s->half[1] - s->margin, hz = s->half[2] - s->margin;
         r = V(l.x >= 0 ? hx : -hx, l.y >= 0 ? hy : -hy, l.z >= 0 ? hz : -hz); break;
@@ -325,13 +325,19 @@ static int gjk(const WShape* A, const WShape* B, double* dist, v3* pa, v3* pb) {
 }
 
 /* deep-penetration fallback: smallest overlap among face-normal / centre axes evaluated with support functions */
+static int is_round(const WShape* S) { return S->s->type == AVG_SHAPE_SPHERE || S->s->type == AVG_SHAPE_CAPSULE; }
+/* bpa = core witness on A.  The witness is anchored on the round shape (sphere / capsule core) when there is one,
+ * because the support point of a polytope along a face normal is not unique (any vertex of the face). */
 static void sat_axis(const WShape* A, const WShape* B, v3 n, double* best, v3* bn, v3* bpa) {
     double ln = vnorm(n);
     if (ln < 1e-12) return;
     n = vscale(n, 1.0 / ln);
     v3 sa = support(A, vneg(n)), sb = support(B, n);
     double depth = vdot(sb, n) - vdot(sa, n);
-    if (depth < *best) { *best = depth; *bn = n; *bpa = sa; }
+    if (depth < *best) {
+        *best = depth; *bn = n;
+        *bpa = (is_round(B) && !is_round(A)) ? vsub(sb, vscale(n, depth)) : sa;
+    }
 }
 static void shape_axes(const WShape* S, const WShape* O, double sign, const WShape* A, const WShape* B, double* best, v3* bn, v3* bpa) {
     const AvgShape* s = S->s;
