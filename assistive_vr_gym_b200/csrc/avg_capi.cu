@@ -17,6 +17,8 @@ struct AvgHandle {
     AvgModelHeader hdr[AVG_K_MAX_VARIANTS];
     bool have[AVG_K_MAX_VARIANTS] = {false, false, false, false};
     float* d_env = nullptr;
+    float* d_scratch = nullptr;
+    int substeps = 5;
     int32_t* d_variant = nullptr;
     // debug taps
     bool debug = false;
@@ -65,12 +67,14 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     AvgHandle* h = new AvgHandle();
     h->device = device; h->n_env = n_env;
     if (cudaMalloc(&h->d_env, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env) != cudaSuccess ||
-        cudaMalloc(&h->d_variant, sizeof(int32_t) * (size_t)n_env) != cudaSuccess) {
+        cudaMalloc(&h->d_variant, sizeof(int32_t) * (size_t)n_env) != cudaSuccess ||
+        cudaMalloc(&h->d_scratch, sizeof(float) * AVG_S_STRIDE * (size_t)n_env) != cudaSuccess) {
         delete h;
         return fail(nullptr, -2, "avg_create: cudaMalloc of the state arena failed");
     }
     cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
     cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
+    cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     *out = h;
     return 0;
@@ -81,7 +85,7 @@ int avg_destroy(AvgHandle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
-    cudaFree(h->d_env); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
+    cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -114,7 +118,9 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     AVG_CHECK(h, cudaMalloc(&h->d_model[variant], nbytes));
     AVG_CHECK(h, cudaMemcpy(h->d_model[variant], blob, nbytes, cudaMemcpyHostToDevice));
     h->hdr[variant] = *mh; h->have[variant] = true;
-    h->task = mh->task; h->n_act = na; h->n_obs = no;
+    if (h->task >= 0 && h->substeps != mh->substeps && variant != 0)
+        return fail(h, -4, "avg_upload_model: variants of one handle must share frame_skip");
+    h->task = mh->task; h->n_act = na; h->n_obs = no; h->substeps = mh->substeps;
     return 0;
 }
 
@@ -148,7 +154,7 @@ float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 static int fill_args(AvgHandle* h, AvgStepArgs& a) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
-    a.variant = h->d_variant; a.env = h->d_env; a.n_env = h->n_env;
+    a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env;
     a.contacts = h->debug ? h->d_contacts : nullptr;
     a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
     a.terms = h->debug ? h->d_terms : nullptr;
@@ -172,8 +178,8 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     AvgStepArgs a; memset(&a, 0, sizeof(a));
     int rc = fill_args(h, a); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
-    AVG_CHECK(h, avg_launch_step(a, (cudaStream_t)stream));
-    h->launches++;
+    AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
+    h->launches += avg_kernels_per_step(h->substeps);
     return 0;
 }
 

@@ -1,15 +1,28 @@
 // avg_kernels.cu — sm_100a kernels of the batched Assistive-Gym simulator (ScratchItch path).
 //
-// One warp owns one environment for a whole env.step(): action -> motor targets (reference env.py:274-337),
-// frame_skip x { forward kinematics, collision, forward dynamics, constraint solve, integration, human hard limits }
-// (what the reference delegates to p.stepSimulation, env.py:341-349), then forces / reward / observation
-// (scratch_itch.py:53-128).  State is read from HBM once and written once per env-step.
+// One warp owns one environment.  An env.step() (reference AssistiveEnv.take_step, env.py:274-351, followed by
+// ScratchItchEnv.step, scratch_itch.py:53-128) is a short pipeline of kernels on one stream:
+//
+//   avg_prologue_kernel   action -> limit-masked motor targets (env.py:275-337)
+//   frame_skip x {                                               (what the reference delegates to p.stepSimulation)
+//     avg_collide_kernel  forward kinematics, broadphase, GJK narrowphase              -> contact list
+//     avg_dynamics_kernel forward kinematics, mass matrix, bias forces, M^-1, qd*,
+//                         constraint rows (motors, limits, weld, contacts) + M^-1 J^T   -> row arena
+//     avg_solve_kernel    projected Gauss-Seidel, integration, human hard limits (env.py:389-410)
+//   }
+//   avg_epilogue_kernel   forces, reward, observation, info (scratch_itch.py:53-128)
+//
+// The phases are separate kernels on purpose: fused, the step was > 400 KB of SASS, far beyond the 32 KB L1.5
+// instruction cache, and ncu attributed most stalls to instruction fetch (profiles/).  Split, every kernel has a
+// small footprint and its own register / shared-memory budget (the solver runs at ~3x the occupancy of the fused
+// kernel), and the hand-off through HBM costs ~10 KB per env and sub-step against a ~6.5 TB/s budget.
 //
 // Lane mapping inside a warp:
 //   kinematics/dynamics : lane b = dynamic body b (1-DoF joint bodies first, so lane i is also velocity dof i)
-//   solver              : lane d = velocity dof d (delta-velocity component in a register), rows staged in smem,
-//                         J.dv by warp shuffles, strict row order (Gauss-Seidel semantics)
-//   collision           : lanes stride over the candidate pair table; one lane runs GJK for one candidate pair
+//   solver              : lane d = velocity dof d (delta-velocity in a register); rows staged in shared memory;
+//                         J.dv by warp shuffles; accumulated impulses in registers (row r in lane r%32); strict
+//                         row order (Gauss-Seidel semantics)
+//   collision           : one lane per static shape in the broadphase, one lane per candidate pair in GJK
 //
 // The math is NOT a transcription of the CPU oracle: forward dynamics is mass-matrix based (composite-rigid-body
 // inertia in a common frame, then an explicit inverse that the solver reuses for M^-1 J^T), whereas the oracle
@@ -20,40 +33,16 @@
 #include "avg_math.cuh"
 #include "avg_kernels.h"
 
-// Phase alignment: the warps of a block enter collision / dynamics / solver together so that the SM's instruction
-// cache serves one phase at a time (the fused kernel is far larger than the 32 KB L1.5 I-cache).
-#ifndef AVG_PHASE_SYNC
-#define AVG_PHASE_SYNC() __syncthreads()
-#endif
-
 namespace {
 
 constexpr int kWarpsPerBlock = AVG_K_WARPS_PER_BLOCK;
-constexpr int kMaxJ = AVG_K_MAXJ;          // 1-DoF joints per environment handled by this kernel
+constexpr int kMaxJ = AVG_K_MAXJ;          // 1-DoF joints per environment handled by these kernels
 constexpr int kMaxMS = AVG_K_MAXMS;        // moving shapes
 constexpr int kMaxCand = 64;               // narrowphase candidates per sub-step
 constexpr int kMaxC = AVG_MAX_CONTACT;
-constexpr int kMaxDense = 6 + 2 * kMaxC;   // weld rows + contact normal + friction rows
+constexpr int kMaxDense = AVG_S_MAXDENSE;  // weld rows + contact normal + friction rows
 constexpr int kMaxRows = AVG_MAX_ROWS;
-
-struct __align__(16) WarpSm {
-    float env[AVG_ENV_STRIDE];             // the environment record (q, qd, motor targets, parameters, task state)
-    float bp[32][3];                       // body frame origin (world)
-    float bq[32][4];                       // body orientation
-    float Minv[kMaxJ][kMaxJ + 1];          // joint-space inverse mass matrix (block diagonal per articulation)
-    float freeInv[2][12];                  // free bodies: [0] 1/m, [1..9] inverse world inertia
-    float J[kMaxDense][32];
-    float W[kMaxDense][32];
-    float4 r_a[kMaxRows];                  // per row: target velocity change, 1/diag, lower, upper impulse bound
-    float4 r_b[kMaxRows];                  // per row: diag, friction coefficient, index (int), normal row of a friction row (int)
-    float sp[kMaxMS][3];                   // moving shapes: world position, rotation, AABB (centre, half extents, thr, pad)
-    float sR[kMaxMS][9];
-    float4 saabb[kMaxMS][2];
-    uint32_t cand[kMaxCand];
-    float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
-    int c_sa[kMaxC], c_sb[kMaxC];
-    float obs[64];
-};
+constexpr int kSmDense = 14;               // dense rows staged in shared memory by the solver (weld + 4 contacts)
 
 struct KM {                                // device view of a ModelBlob
     const AvgModelHeader* h;
@@ -83,11 +72,46 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     return m;
 }
 
-__device__ __forceinline__ void body_pose(const WarpSm& s, int b, V3& p, Q4& q) {
+// ---- per-kernel shared memory (one instance per warp).  Member names are shared so the device functions below can
+//      be templated on the struct.
+struct __align__(16) SmCollide {
+    float q[32];                           // position coordinates of the env record
+    float bp[32][3]; float bq[32][4];      // body poses
+    float sp[kMaxMS][3]; float sR[kMaxMS][9]; float4 saabb[kMaxMS][2];
+    uint32_t cand[kMaxCand];
+    float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
+    int c_sa[kMaxC], c_sb[kMaxC];
+};
+struct __align__(16) SmDyn {
+    float env[AVG_ENV_STRIDE];
+    float bp[32][3]; float bq[32][4];
+    float Minv[kMaxJ][kMaxJ + 1];
+    float freeInv[2][12];
+    float Jrow[32];
+    float tmp[32];
+    float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC];
+    int c_sa[kMaxC], c_sb[kMaxC];
+};
+struct __align__(16) SmSolve {
+    float Minv[kMaxJ][kMaxJ + 1];
+    float J[kSmDense][32];
+    float W[kSmDense][32];
+    float4 r_a[kMaxRows];
+    float4 r_b[kMaxRows];
+};
+struct __align__(16) SmEpi {
+    float env[AVG_ENV_STRIDE];
+    float bp[32][3]; float bq[32][4];
+    float obs[64];
+};
+
+template <class SM>
+__device__ __forceinline__ void body_pose(const SM& s, int b, V3& p, Q4& q) {
     if (b < 0) { p = mk3(0, 0, 0); q = mkq(0, 0, 0, 1); }
     else { p = ld3(s.bp[b]); q = ldq(s.bq[b]); }
 }
-__device__ __noinline__ void frame_pose(const KM& m, const WarpSm& s, int f, V3& p, Q4& q) {
+template <class SM>
+__device__ __noinline__ void frame_pose(const KM& m, const SM& s, int f, V3& p, Q4& q) {
     const AvgFrame* F = &m.frame[f];
     V3 bp; Q4 bq;
     body_pose(s, F->body, bp, bq);
@@ -98,18 +122,20 @@ __device__ __noinline__ void frame_pose(const KM& m, const WarpSm& s, int f, V3&
 // ---------------------------------------------------------------------------------------------------------------
 // Forward kinematics: every lane builds its body's transform relative to the parent body, then the chain products
 // are formed by pointer jumping over the parent array (log2(depth) shuffle rounds instead of a serial walk).
+// qpos = position coordinates (AVG_E_Q block of the env record).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void fk_warp(const KM& m, WarpSm& s, int lane, int nb) {
+template <class SM>
+__device__ void fk_warp(const KM& m, SM& s, const float* qpos, int lane, int nb) {
     V3 p = mk3(0, 0, 0); Q4 q = mkq(0, 0, 0, 1);
     int anc = -1;
     if (lane < nb) {
         const AvgBody* B = &m.body[lane];
         if (B->jtype == AVG_JOINT_FREE) {
-            const float* qq = s.env + AVG_E_Q + B->qidx;
+            const float* qq = qpos + B->qidx;
             p = ld3(qq); q = qnormalize(ldq(qq + 3));
         } else {
             V3 ax = ld3(B->axis);
-            float qv = s.env[AVG_E_Q + B->qidx];
+            float qv = qpos[B->qidx];
             Q4 jq = ldq(B->ta_quat);
             V3 jp = ld3(B->ta_pos);
             if (B->jtype == AVG_JOINT_REVOLUTE) jq = qmul(jq, qaxis(ax, qv));
@@ -145,7 +171,8 @@ struct WShape {
     const float* planes;
 };
 
-__device__ __forceinline__ void load_wshape(const KM& m, const WarpSm& s, int si, WShape& w) {
+template <class SM>
+__device__ __forceinline__ void load_wshape(const KM& m, const SM& s, int si, WShape& w) {
     const AvgShape* S = &m.shape[si];
     w.s = S; w.verts = m.vert + 3 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
     if (si < m.h->n_mshape) {
@@ -352,7 +379,8 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
     return true;
 }
 
-__device__ __noinline__ void collide_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow) {
+template <class SM>
+__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow) {
     const AvgModelHeader* h = m.h;
     const int nms = h->n_mshape;
     // world pose + AABB of the moving shapes
@@ -475,7 +503,7 @@ __device__ __noinline__ void collide_warp(const KM& m, WarpSm& s, int lane, int&
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Dynamics
+// Dynamics helpers
 // ---------------------------------------------------------------------------------------------------------------
 struct LaneDyn {
     Sv S;             // motion subspace of this lane's joint (zero for free bodies / idle lanes)
@@ -483,7 +511,8 @@ struct LaneDyn {
 };
 
 // Jacobian entry of lane `lane` (dof) for "velocity of world point r on `body` along n", sign applied.
-__device__ __noinline__ float jac_point_lane(const KM& m, const WarpSm& s, const LaneDyn& L, int lane, int nj, int body,
+template <class SM>
+__device__ __noinline__ float jac_point_lane(const KM& m, const SM& s, const LaneDyn& L, int lane, int nj, int body,
                                                 V3 r, V3 n, V3 ref) {
     if (body < 0) return 0.0f;
     const AvgBody* B = &m.body[body];
@@ -511,35 +540,146 @@ __device__ __forceinline__ float jac_ang_lane(const KM& m, const LaneDyn& L, int
     return dot(L.S.a, n);
 }
 
-// W = M^-1 J^T for the dense row d (J already in smem), returns J.W (diag) and J.qd (u0) reduced over the warp
-__device__ __noinline__ void finish_dense_row(const KM& m, WarpSm& s, int lane, int nj, int nd, int d, float qd, float& diag, float& u0) {
+// W = M^-1 J^T for the dense row d whose Jacobian sits in s.Jrow; J and W are written to the scratch arena.
+// Returns J.W (diag) and J.qd (u0) reduced over the warp.
+template <class SM>
+__device__ __noinline__ void finish_dense_row(SM& s, float* __restrict__ gJ, float* __restrict__ gW, int lane, int nj, int nd, int d,
+                                              float qd, float& diag, float& u0) {
     __syncwarp();
     float w = 0.0f;
-    float jl = s.J[d][lane];
+    const float jl = s.Jrow[lane];
     if (lane < nj) {
-        for (int j = 0; j < nj; ++j) w = fmaf(s.Minv[lane][j], s.J[d][j], w);
+        for (int j = 0; j < nj; ++j) w = fmaf(s.Minv[lane][j], s.Jrow[j], w);
     } else if (lane < nd) {
         int fb = 0, k = lane - nj;
         while (k >= 6) { k -= 6; fb++; }
-        int base = lane - k;
+        const int base = lane - k;
         const float* fi = s.freeInv[fb];
         if (k < 3) w = fi[0] * jl;
-        else { int r = k - 3; w = fi[1 + 3 * r] * s.J[d][base + 3] + fi[2 + 3 * r] * s.J[d][base + 4] + fi[3 + 3 * r] * s.J[d][base + 5]; }
+        else { const int r = k - 3; w = fi[1 + 3 * r] * s.Jrow[base + 3] + fi[2 + 3 * r] * s.Jrow[base + 4] + fi[3 + 3 * r] * s.Jrow[base + 5]; }
     }
-    s.W[d][lane] = w;
+    gJ[d * 32 + lane] = jl; gW[d * 32 + lane] = w;
     diag = warp_sum(jl * w);
     u0 = warp_sum(jl * qd);
+    __syncwarp();
 }
 
-__device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, int& overflow, int& solver_iters) {
+}  // namespace
+
+#define AVG_KERNEL_PREAMBLE(SMTYPE)                                                             \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                                    \
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                  \
+    const int e = blockIdx.x * kWarpsPerBlock + warp;                                            \
+    if (e >= a.n_env) return;                                                                    \
+    SMTYPE& s = reinterpret_cast<SMTYPE*>(smem_raw)[warp];                                       \
+    const int variant = a.variant ? a.variant[e] : 0;                                            \
+    const KM m = open_model(a.models[variant]);                                                  \
+    const AvgModelHeader* h = m.h;                                                               \
+    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;                                            \
+    float* scr = a.scratch + (size_t)e * AVG_S_STRIDE;                                           \
+    (void)lane; (void)s; (void)h; (void)grec; (void)scr;
+
+// =================================================================================================================
+// action -> motor targets, env.py:274-337 (one lane per dof; no shared memory)
+// =================================================================================================================
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_prologue_kernel(AvgStepArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= a.n_env) return;
+    const int variant = a.variant ? a.variant[e] : 0;
+    const KM m = open_model(a.models[variant]);
     const AvgModelHeader* h = m.h;
+    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
+    int* scr_i = reinterpret_cast<int*>(a.scratch + (size_t)e * AVG_S_STRIDE);
+    const int nj = h->n_jdof;
+    const int na = h->n_action_robot + h->n_action_human;
+    const float* act = a.actions + (size_t)e * na;
+    const bool tremor = grec[AVG_E_TREMOR_ON] != 0.0f;
+    const bool human_active = h->human_control || tremor;
+    const int iteration = reinterpret_cast<const int*>(grec)[AVG_E_ITERATION];
+    if (lane < nj) {
+        const AvgDof* D = &m.dof[lane];
+        const int ai = D->action, slot = D->human_slot;
+        if (ai >= 0 && ai < h->n_action_robot) {
+            float av = fminf(fmaxf(act[ai], -1.0f), 1.0f) * h->action_scale;
+            float pos = grec[AVG_E_Q + m.body[D->body].qidx];
+            for (int f = 0; f < h->substeps; ++f) {
+                if (pos + av < D->rep_lower) av = 0.0f;
+                if (pos + av > D->rep_upper) av = 0.0f;
+                pos += av;
+            }
+            grec[AVG_E_MTARGET + lane] = pos;
+        } else if (slot >= 0 && human_active) {
+            float av = 0.0f;
+            if (h->human_control) av = fminf(fmaxf(act[h->n_action_robot + slot], -1.0f), 1.0f) * h->action_scale;
+            const float sc = grec[AVG_E_LIMIT_SCALE];
+            const float lo = D->lower * sc, hi = D->upper * sc;
+            float pos = grec[AVG_E_Q + m.body[D->body].qidx];
+            float tgt = grec[AVG_E_TARGET_H + slot];
+            const float sgn = (iteration % 2 == 0) ? 1.0f : -1.0f;
+            for (int f = 0; f < h->substeps; ++f) {
+                if (pos + av < lo) av = 0.0f;
+                if (pos + av > hi) av = 0.0f;
+                if (tremor) { pos = tgt + grec[AVG_E_TREMOR + slot] * sgn; tgt += av; }
+                pos += av;
+            }
+            grec[AVG_E_TARGET_H + slot] = tgt;
+            grec[AVG_E_MTARGET + lane] = pos;
+        }
+    }
+    if (lane == 0) {
+        if (human_active) grec[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
+        scr_i[AVG_S_ITERS] = 0; scr_i[AVG_S_OVERFLOW] = 0;
+    }
+}
+
+// =================================================================================================================
+// forward kinematics + collision -> contact list in the scratch arena
+// =================================================================================================================
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_collide_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmCollide)
+    s.q[lane] = grec[AVG_E_Q + lane];
+    __syncwarp();
+    fk_warp(m, s, s.q, lane, h->n_body);
+    int nc = 0, overflow = 0;
+    collide_warp(m, s, lane, nc, overflow);
+    int* scr_i = reinterpret_cast<int*>(scr);
+    if (lane < nc) {
+        float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
+        c[0] = s.c_pa[lane][0]; c[1] = s.c_pa[lane][1]; c[2] = s.c_pa[lane][2];
+        c[3] = s.c_pb[lane][0]; c[4] = s.c_pb[lane][1]; c[5] = s.c_pb[lane][2];
+        c[6] = s.c_n[lane][0]; c[7] = s.c_n[lane][1]; c[8] = s.c_n[lane][2];
+        c[9] = s.c_dist[lane]; c[10] = __int_as_float(s.c_sa[lane]); c[11] = __int_as_float(s.c_sb[lane]); c[12] = 0.0f;
+    }
+    if (lane == 0) { scr_i[AVG_S_NC] = nc; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
+}
+
+// =================================================================================================================
+// dynamics + constraint rows -> row arena
+// =================================================================================================================
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_dynamics_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmDyn)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
     const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
-
-    fk_warp(m, s, lane, nb);
-    collide_warp(m, s, lane, ncontact, overflow);
-    AVG_PHASE_SYNC();
+    int* scr_i = reinterpret_cast<int*>(scr);
+    for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
+    int ncontact = scr_i[AVG_S_NC];
+    int overflow = 0;
+    if (lane < ncontact) {
+        const float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
+        s.c_pa[lane][0] = c[0]; s.c_pa[lane][1] = c[1]; s.c_pa[lane][2] = c[2];
+        s.c_pb[lane][0] = c[3]; s.c_pb[lane][1] = c[4]; s.c_pb[lane][2] = c[5];
+        s.c_n[lane][0] = c[6]; s.c_n[lane][1] = c[7]; s.c_n[lane][2] = c[8];
+        s.c_dist[lane] = c[9]; s.c_sa[lane] = __float_as_int(c[10]); s.c_sb[lane] = __float_as_int(c[11]);
+    }
+    __syncwarp();
+    fk_warp(m, s, s.env + AVG_E_Q, lane, nb);
+    float4* g_rows = reinterpret_cast<float4*>(scr + AVG_S_ROWS);
+    float* gJ = scr + AVG_S_J; float* gW = scr + AVG_S_W;
 
     // ---- per-lane body quantities ------------------------------------------------------------------------------
     LaneDyn L; L.S = mksv(mk3(0, 0, 0), mk3(0, 0, 0)); L.anc = 0;
@@ -701,11 +841,11 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         V3 tau = -(Iw * (h->ang_damp + h->ang_damp * norm(w))) - cross(w, Iw);
         const float* fi = s.freeInv[(B->dof - nj) / 6];
         V3 al = mk3(fi[1] * tau.x + fi[2] * tau.y + fi[3] * tau.z, fi[4] * tau.x + fi[5] * tau.y + fi[6] * tau.z, fi[7] * tau.x + fi[8] * tau.y + fi[9] * tau.z);
-        float* o = s.obs + (B->dof - nj);
+        float* o = s.tmp + (B->dof - nj);
         o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = al.x; o[4] = al.y; o[5] = al.z;
     }
     __syncwarp();
-    if (lane >= nj && lane < nd) qdd = s.obs[lane - nj];
+    if (lane >= nj && lane < nd) qdd = s.tmp[lane - nj];
     __syncwarp();
     qd = qd + dt * qdd;
 
@@ -730,7 +870,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         if (has) {
             int r = nr + __popc(bal & ((1u << lane) - 1));
             float diag = s.Minv[lane][lane];
-            s.r_a[r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float(lane), __int_as_float(-1));
+            g_rows[2 * r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float(lane), __int_as_float(-1));
         }
         nr += __popc(bal);
     }
@@ -752,7 +892,7 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
             int r = nr + __popc(bal & ((1u << lane) - 1));
             if (r < kMaxRows) {
                 float diag = s.Minv[lane][lane];
-                s.r_a[r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 100.0f); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((kind << 8) | lane), __int_as_float(-1));
+                g_rows[2 * r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 100.0f); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((kind << 8) | lane), __int_as_float(-1));
             }
         }
         nr += __popc(bal);
@@ -783,12 +923,12 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
                 jl = jac_ang_lane(m, L, lane, nj, h->weld_body_a, e) - jac_ang_lane(m, L, lane, nj, h->weld_body_b, e);
                 err = dot(rotv, e);
             }
-            s.J[ndense][lane] = jl;
+            s.Jrow[lane] = jl;
             float diag, u0;
-            finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+            finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
             if (lane == 0) {
                 int r = nr;
-                s.r_a[r] = make_float4(-err * h->erp / dt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, -maxi, maxi); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
+                g_rows[2 * r] = make_float4(-err * h->erp / dt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, -maxi, maxi); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
             }
             nr++; ndense++;
         }
@@ -802,13 +942,13 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
         int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
         float jl = jac_point_lane(m, s, L, lane, nj, ba, pa, n, ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, n, ref);
-        s.J[ndense][lane] = jl;
+        s.Jrow[lane] = jl;
         float diag, u0;
-        finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+        finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
         if (lane == 0) {
             float dist = s.c_dist[ci];
             int r = nr;
-            s.r_a[r] = make_float4((dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 1e30f); s.r_b[r] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
+            g_rows[2 * r] = make_float4((dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 1e30f); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
         }
         nr++; ndense++;
     }
@@ -827,23 +967,58 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         if (ll > 1e-6f) t = lat * (1.0f / ll);
         else if (fabsf(n.z) > 0.70710678f) { float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
         else { float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
-        s.J[ndense][lane] = t.x * jx + t.y * jy + t.z * jz;
+        s.Jrow[lane] = t.x * jx + t.y * jy + t.z * jz;
         float diag, u0;
-        finish_dense_row(m, s, lane, nj, nd, ndense, qd, diag, u0);
+        finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
         if (lane == 0) {
             int r = nr;
-            s.r_a[r] = make_float4(-u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 0.0f); s.r_b[r] = make_float4(diag, m.shape[sa].friction * m.shape[sb].friction, __int_as_float((2 << 8) | ndense), __int_as_float(first_contact_row + ci));
+            g_rows[2 * r] = make_float4(-u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 0.0f); g_rows[2 * r + 1] = make_float4(diag, m.shape[sa].friction * m.shape[sb].friction, __int_as_float((2 << 8) | ndense), __int_as_float(first_contact_row + ci));
         }
         nr++; ndense++;
     }
     __syncwarp();
 
-    AVG_PHASE_SYNC();
+
+    // ---- hand-off to the solver -----------------------------------------------------------------------------------
+    if (lane < nd) scr[AVG_S_QD + lane] = qd;
+    for (int i = 0; i < nj; ++i) if (lane < nj) scr[AVG_S_MINV + i * kMaxJ + lane] = s.Minv[i][lane];
+    if (lane == 0) {
+        scr_i[AVG_S_NR] = nr; scr_i[AVG_S_NS] = ns; scr_i[AVG_S_NFR] = first_contact_row + nc; scr_i[AVG_S_FCR] = first_contact_row;
+        scr_i[AVG_S_NCS] = nc;
+        if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow;
+    }
+}
+
+// =================================================================================================================
+// projected Gauss-Seidel + integration + human hard limits
+// =================================================================================================================
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_solve_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmSolve)
+    const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
+    const float dt = h->dt;
+    int* scr_i = reinterpret_cast<int*>(scr);
+    const int nr = scr_i[AVG_S_NR], ns = scr_i[AVG_S_NS], nfr = scr_i[AVG_S_NFR], first_contact_row = scr_i[AVG_S_FCR];
+    const int nc = scr_i[AVG_S_NCS];
+    const int ndense = nr - ns;
+    const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
+    // stage rows: coalesced loads from the arena
+    for (int i = 0; i < nj; ++i) if (lane < nj) s.Minv[i][lane] = scr[AVG_S_MINV + i * kMaxJ + lane];
+    for (int d = 0; d < min(ndense, kSmDense); ++d) { s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
+    {
+        const float4* g_rows = reinterpret_cast<const float4*>(scr + AVG_S_ROWS);
+        for (int i = lane; i < 2 * nr; i += 32) {
+            const float4 v = g_rows[i];
+            if (i & 1) s.r_b[i >> 1] = v; else s.r_a[i >> 1] = v;
+        }
+    }
+    const float qd = lane < nd ? scr[AVG_S_QD + lane] : 0.0f;
+    __syncwarp();
+
     // ---- projected Gauss-Seidel, strict row order (unit rows, dense bilateral/normal rows, friction rows).
     //      dv lives in one register per lane; the accumulated impulse of row r lives in lane r%32 (slot r/32).
     float dv = 0.0f, lam0 = 0.0f, lam1 = 0.0f;
     const float thr = h->residual_thr;
-    const int nfr = first_contact_row + nc;    // first friction row
     int iters = 0;
     for (int it = 0; it < h->solver_iters; ++it) {
         float resid = 0.0f;
@@ -867,8 +1042,8 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         for (int r = ns; r < nfr; ++r) {
             const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
             const int d = r - ns;
-            const float jdv = warp_sum(s.J[d][lane] * dv);
-            const float wl = s.W[d][lane];
+            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
+            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
             const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
             float delta = (ra.x - jdv) * ra.y;
             const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
@@ -882,8 +1057,8 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         for (int r = nfr; r < nr; ++r) {
             const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
             const int d = r - ns, par = __float_as_int(rb.w);
-            const float jdv = warp_sum(s.J[d][lane] * dv);
-            const float wl = s.W[d][lane];
+            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
+            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
             const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
             const float lim = rb.y * __shfl_sync(AVG_FULL, par < 32 ? lam0 : lam1, par & 31);
             float delta = (ra.x - jdv) * ra.y;
@@ -897,144 +1072,61 @@ __device__ void substep_warp(const KM& m, WarpSm& s, int lane, int& ncontact, in
         iters++;
         if (resid <= thr) break;
     }
-    solver_iters += iters;
+
+    // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
     for (int ci = 0; ci < nc; ++ci) {
         const int r = first_contact_row + ci;
         const float l = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
-        if (lane == 0) s.c_lam[ci] = l;
+        if (lane == 0) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci + 12] = l;
     }
+    if (lane == 0) scr_i[AVG_S_ITERS] += iters;
 
-    AVG_PHASE_SYNC();
-    // ---- integrate ------------------------------------------------------------------------------------------------
+    // ---- integrate (semi-implicit Euler) + enforce_hard_human_joint_limits (env.py:389-410) -----------------------
     float v = qd + dv;
     if (lane < nj) v = fminf(fmaxf(v, -h->max_vel), h->max_vel);
-    __syncwarp();
-    if (lane < nd) s.env[AVG_E_QD + lane] = v;
-    __syncwarp();
     if (lane < nb) {
         const AvgBody* B = &m.body[lane];
-        if (B->jtype == AVG_JOINT_FREE) {
-            float* q = s.env + AVG_E_Q + B->qidx; const float* vv = s.env + AVG_E_QD + B->dof;
-            q[0] += dt * vv[0]; q[1] += dt * vv[1]; q[2] += dt * vv[2];
-            V3 w = ld3(vv + 3); float wn = norm(w);
+        if (B->jtype != AVG_JOINT_FREE) {
+            float qn = grec[AVG_E_Q + B->qidx] + dt * v;
+            const AvgDof* D = &m.dof[lane];
+            if (D->flags & AVG_DOF_HARD_LIMIT) {
+                const float sc = grec[AVG_E_LIMIT_SCALE];
+                const float lo = D->lower * sc, hi = D->upper * sc;
+                if (qn < lo) { qn = lo; v = 0.0f; }
+                else if (qn > hi) { qn = hi; v = 0.0f; }
+            }
+            grec[AVG_E_Q + B->qidx] = qn;
+        }
+    }
+    if (lane < nd) grec[AVG_E_QD + lane] = v;
+    // free bodies: the body's lane gathers its six velocity components from the dof lanes
+    {
+        int fdof = -1, fq = 0;
+        if (lane < nb && m.body[lane].jtype == AVG_JOINT_FREE) { fdof = m.body[lane].dof; fq = m.body[lane].qidx; }
+        const int src = fdof >= 0 ? fdof : 0;
+        const float v0 = __shfl_sync(AVG_FULL, v, src), v1 = __shfl_sync(AVG_FULL, v, (src + 1) & 31), v2 = __shfl_sync(AVG_FULL, v, (src + 2) & 31);
+        const float w0 = __shfl_sync(AVG_FULL, v, (src + 3) & 31), w1 = __shfl_sync(AVG_FULL, v, (src + 4) & 31), w2 = __shfl_sync(AVG_FULL, v, (src + 5) & 31);
+        if (fdof >= 0) {
+            float* q = grec + AVG_E_Q + fq;
+            q[0] += dt * v0; q[1] += dt * v1; q[2] += dt * v2;
+            V3 w = mk3(w0, w1, w2); float wn = norm(w);
             Q4 cur = ldq(q + 3);
             if (wn * dt > 1e-9f) cur = qmul(qaxis(w * (1.0f / wn), wn * dt), cur);
             cur = qnormalize(cur);
             q[3] = cur.x; q[4] = cur.y; q[5] = cur.z; q[6] = cur.w;
-        } else {
-            float qn = s.env[AVG_E_Q + B->qidx] + dt * v;
-            // enforce_hard_human_joint_limits, env.py:389-410
-            const AvgDof* D = &m.dof[lane];
-            if (D->flags & AVG_DOF_HARD_LIMIT) {
-                float sc = s.env[AVG_E_LIMIT_SCALE];
-                float lo = D->lower * sc, hi = D->upper * sc;
-                if (qn < lo) { qn = lo; s.env[AVG_E_QD + lane] = 0.0f; }
-                else if (qn > hi) { qn = hi; s.env[AVG_E_QD + lane] = 0.0f; }
-            }
-            s.env[AVG_E_Q + B->qidx] = qn;
         }
     }
-    __syncwarp();
 }
 
-}  // namespace
-
 // =================================================================================================================
-// The env-step kernel
+// forces, reward, observation, info (scratch_itch.py:53-128)
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
-avg_step_kernel(AvgStepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e_raw = blockIdx.x * kWarpsPerBlock + warp;
-    const bool live = e_raw < a.n_env;
-    const int e = live ? e_raw : a.n_env - 1;           // tail warps shadow the last env (no stores) to keep barriers uniform
-    WarpSm& s = reinterpret_cast<WarpSm*>(smem_raw)[warp];
-    const int variant = a.variant ? a.variant[e] : 0;
-    const KM m = open_model(a.models[variant]);
+namespace {
+// ScratchItchEnv._get_obs, scratch_itch.py:104-128 (lane 0 fills s.obs)
+template <class SM>
+__device__ void fill_obs(const KM& m, SM& s, V3 tgt, float tool_force, float total_force_on_human, float tool_force_at_target) {
     const AvgModelHeader* h = m.h;
     const int nj = h->n_jdof;
-
-    // ---- load the environment record (coalesced, once) ----------------------------------------------------------
-    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
-    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
-    __syncwarp();
-    int* env_i = reinterpret_cast<int*>(s.env);
-
-    // ---- action -> motor targets, env.py:274-337 ----------------------------------------------------------------
-    const int na = h->n_action_robot + h->n_action_human;
-    const float* act = a.actions + (size_t)e * na;
-    float raw_sq = 0.0f;
-    {
-        float av = lane < na ? act[lane] : 0.0f;
-        raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, scratch_itch.py:64
-    }
-    const bool human_active = h->human_control || s.env[AVG_E_TREMOR_ON] != 0.0f;
-    const bool tremor = s.env[AVG_E_TREMOR_ON] != 0.0f;
-    const int iteration = env_i[AVG_E_ITERATION];
-    if (lane < nj) {
-        const AvgDof* D = &m.dof[lane];
-        const int ai = D->action, slot = D->human_slot;
-        if (ai >= 0 && ai < h->n_action_robot) {
-            float av = fminf(fmaxf(act[ai], -1.0f), 1.0f) * h->action_scale;
-            float pos = s.env[AVG_E_Q + m.body[D->body].qidx];
-            for (int f = 0; f < h->substeps; ++f) {
-                if (pos + av < D->rep_lower) av = 0.0f;
-                if (pos + av > D->rep_upper) av = 0.0f;
-                pos += av;
-            }
-            s.env[AVG_E_MTARGET + lane] = pos;
-        } else if (slot >= 0 && human_active) {
-            float av = 0.0f;
-            if (h->human_control) av = fminf(fmaxf(act[h->n_action_robot + slot], -1.0f), 1.0f) * h->action_scale;
-            float sc = s.env[AVG_E_LIMIT_SCALE];
-            float lo = D->lower * sc, hi = D->upper * sc;
-            float pos = s.env[AVG_E_Q + m.body[D->body].qidx];
-            float tgt = s.env[AVG_E_TARGET_H + slot];
-            const float sgn = (iteration % 2 == 0) ? 1.0f : -1.0f;
-            for (int f = 0; f < h->substeps; ++f) {
-                if (pos + av < lo) av = 0.0f;
-                if (pos + av > hi) av = 0.0f;
-                if (tremor) { pos = tgt + s.env[AVG_E_TREMOR + slot] * sgn; tgt += av; }
-                pos += av;
-            }
-            s.env[AVG_E_TARGET_H + slot] = tgt;
-            s.env[AVG_E_MTARGET + lane] = pos;
-        }
-    }
-    __syncwarp();
-    if (human_active && lane == 0) s.env[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
-    __syncwarp();
-
-    // ---- frame_skip physics sub-steps, env.py:341-349 -----------------------------------------------------------
-    int ncontact = 0, overflow = 0;
-    int solver_iters = 0;
-    for (int f = 0; f < h->substeps; ++f) substep_warp(m, s, lane, ncontact, overflow, solver_iters);
-
-    // ---- forces, reward, observation (scratch_itch.py:53-128) ---------------------------------------------------
-    fk_warp(m, s, lane, h->n_body);
-    V3 tgt; { V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
-    const float dt = h->dt;
-    const float* tf = h->task_f;
-    float total_force_on_human = 0, tool_force = 0, tool_force_at_target = 0;
-    bool have_tcp = false; V3 tcp = mk3(0, 0, 0);
-    for (int ci = 0; ci < ncontact; ++ci) {
-        const AvgShape* sa = &m.shape[s.c_sa[ci]]; const AvgShape* sb = &m.shape[s.c_sb[ci]];
-        float force = s.c_lam[ci] / dt;
-        bool a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
-        bool a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
-        bool a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
-        if (a_tool || b_tool) tool_force += force;
-        if ((a_tool && b_hum) || (b_tool && a_hum)) {
-            total_force_on_human += force;
-            int link_tool = a_tool ? sa->ref_link : sb->ref_link;
-            V3 pos_h = a_tool ? ld3(s.c_pb[ci]) : ld3(s.c_pa[ci]);
-            if ((link_tool == 0 || link_tool == 1) && norm(pos_h - tgt) < tf[AVG_TF_TARGET_RADIUS]) {
-                tool_force_at_target += force; tcp = pos_h; have_tcp = true;
-            }
-        }
-        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;
-    }
     V3 torso, tool, sh, el, wr, chest; Q4 tq, dq;
     frame_pose(m, s, AVG_F_TORSO, torso, dq);
     frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
@@ -1042,83 +1134,124 @@ avg_step_kernel(AvgStepArgs a) {
     frame_pose(m, s, AVG_F_ELBOW, el, dq);
     frame_pose(m, s, AVG_F_WRIST, wr, dq);
     frame_pose(m, s, AVG_F_CHEST, chest, dq);
-    float ee_vel;
-    {
-        int tb = m.frame[AVG_F_TOOL_TIP].body;
-        const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
-        V3 vt = ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb]));
-        ee_vel = norm(vt);
-    }
-    __syncwarp();
-    if (!live) return;                                   // no block-wide barrier below this point
-    if (lane == 0) {
-        float* o = s.obs; int k = 0;
-        V3 t;
-        t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    float* o = s.obs; int k = 0;
+    V3 t;
+    t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+    t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    t = tgt - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+    t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = tool_force;
+    if (h->human_control) {
+        t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
         o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
         t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = tgt - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
-        t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        o[k++] = tool_force;
-        if (h->human_control) {
-            t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
-            t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = tgt - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            int hq0 = k;
-            for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
-            for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
-            t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            o[k++] = total_force_on_human; o[k++] = tool_force_at_target;
+        t = tgt - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        const int hq0 = k;
+        for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
+        for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+        t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = total_force_on_human; o[k++] = tool_force_at_target;
+    }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_epilogue_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmEpi)
+    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
+    __syncwarp();
+    int* env_i = reinterpret_cast<int*>(s.env);
+    const int* scr_i = reinterpret_cast<const int*>(scr);
+    const int na = h->n_action_robot + h->n_action_human;
+    const float* act = a.actions + (size_t)e * na;
+    float raw_sq;
+    {
+        const float av = lane < na ? act[lane] : 0.0f;
+        raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, scratch_itch.py:64
+    }
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    V3 tgt; { V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
+    const float dt = h->dt;
+    const float* tf = h->task_f;
+    const int ncontact = scr_i[AVG_S_NCS];
+    // get_total_force, scratch_itch.py:84-102
+    float total_force_on_human = 0, tool_force = 0, tool_force_at_target = 0;
+    bool have_tcp = false; V3 tcp = mk3(0, 0, 0);
+    for (int ci = 0; ci < ncontact; ++ci) {
+        const float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci;
+        const AvgShape* sa = &m.shape[__float_as_int(c[10])]; const AvgShape* sb = &m.shape[__float_as_int(c[11])];
+        const float force = c[12] / dt;
+        const bool a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        const bool a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        const bool a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if (a_tool || b_tool) tool_force += force;
+        if ((a_tool && b_hum) || (b_tool && a_hum)) {
+            total_force_on_human += force;
+            const int link_tool = a_tool ? sa->ref_link : sb->ref_link;
+            const V3 pos_h = a_tool ? ld3(c + 3) : ld3(c);
+            if ((link_tool == 0 || link_tool == 1) && norm(pos_h - tgt) < tf[AVG_TF_TARGET_RADIUS]) {
+                tool_force_at_target += force; tcp = pos_h; have_tcp = true;
+            }
         }
+        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;
+    }
+    if (lane == 0) {
+        fill_obs(m, s, tgt, tool_force, total_force_on_human, tool_force_at_target);
+        V3 tool; Q4 tq; frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+        const int tb = m.frame[AVG_F_TOOL_TIP].body;
+        const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
+        const float ee_vel = norm(ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb])));       // scratch_itch.py:54
         // human_preferences (env.py:412-448) and reward (scratch_itch.py:62-72)
-        float pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_at_target))
-                   + tf[AVG_TF_C_HF] * (tool_force_at_target < tf[AVG_TF_FORCE_CAP] ? 0.0f : -tool_force_at_target);
-        float reward_distance = -norm(tgt - tool);
-        float reward_action = -raw_sq;
+        const float pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_at_target))
+                         + tf[AVG_TF_C_HF] * (tool_force_at_target < tf[AVG_TF_FORCE_CAP] ? 0.0f : -tool_force_at_target);
+        const float reward_distance = -norm(tgt - tool);
+        const float reward_action = -raw_sq;
         float reward_force_scratch = 0.0f;
-        V3 prev = ld3(s.env + AVG_E_PREV_CONTACT);
+        float task_success = s.env[AVG_E_TASK_SUCCESS];
+        const V3 prev = ld3(s.env + AVG_E_PREV_CONTACT);
         if (have_tcp && norm(tcp - prev) > tf[AVG_TF_SCRATCH_MOVE] && tool_force_at_target < tf[AVG_TF_FORCE_CAP]) {
             reward_force_scratch = tool_force_at_target;
-            st3(s.env + AVG_E_PREV_CONTACT, tcp);
-            s.env[AVG_E_TASK_SUCCESS] += 1.0f;
+            st3(grec + AVG_E_PREV_CONTACT, tcp);
+            task_success += 1.0f;
+            grec[AVG_E_TASK_SUCCESS] = task_success;
         }
-        float reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
-                     + tf[AVG_TF_TOOL_FORCE_W] * tool_force_at_target + tf[AVG_TF_SCRATCH_W] * reward_force_scratch + pref;
-        s.env[AVG_E_EPISODE_RETURN] += reward;
-        st3(s.env + AVG_E_TARGET_POS, tgt);
-        env_i[AVG_E_ITERATION] = iteration + 1;
-        env_i[AVG_E_OVERFLOW] |= overflow;
-        env_i[AVG_E_SOLVER_ITERS] = solver_iters;
+        const float reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
+                           + tf[AVG_TF_TOOL_FORCE_W] * tool_force_at_target + tf[AVG_TF_SCRATCH_W] * reward_force_scratch + pref;
+        int* grec_i = reinterpret_cast<int*>(grec);
+        grec[AVG_E_EPISODE_RETURN] = s.env[AVG_E_EPISODE_RETURN] + reward;
+        st3(grec + AVG_E_TARGET_POS, tgt);
+        grec_i[AVG_E_ITERATION] = env_i[AVG_E_ITERATION] + 1;                               // env.py:351
+        grec_i[AVG_E_OVERFLOW] = env_i[AVG_E_OVERFLOW] | scr_i[AVG_S_OVERFLOW];
+        grec_i[AVG_E_SOLVER_ITERS] = scr_i[AVG_S_ITERS];
         a.reward[e] = reward;
+        const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;
         a.info[2 * e] = total_force_on_human;
-        a.info[2 * e + 1] = s.env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;
+        a.info[2 * e + 1] = success;
         if (a.done) a.done[e] = 0;                            // the env itself never terminates, scratch_itch.py:78
         if (a.terms) {
             float* tr = a.terms + 8 * (size_t)e;
-            tr[0] = total_force_on_human; tr[1] = a.info[2 * e + 1]; tr[2] = tool_force; tr[3] = tool_force_at_target;
+            tr[0] = total_force_on_human; tr[1] = success; tr[2] = tool_force; tr[3] = tool_force_at_target;
             tr[4] = reward_distance; tr[5] = reward_action; tr[6] = reward_force_scratch; tr[7] = pref;
         }
     }
     __syncwarp();
-    // ---- write back (coalesced) ---------------------------------------------------------------------------------
     const int nobs = h->n_obs_robot + h->n_obs_human;
     for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
-    for (int i = lane; i < AVG_E_LAST; i += 32)
-        if (i < AVG_E_STRENGTH || (i >= AVG_E_TARGET_H && i < AVG_E_TARGET_ON_ARM) || i >= AVG_E_ITERATION) grec[i] = s.env[i];
     if (a.contacts) {
         AvgContact* co = a.contacts + (size_t)e * kMaxC;
         for (int ci = lane; ci < kMaxC; ci += 32) {
             AvgContact c;
             if (ci < ncontact) {
-                c.shape_a = s.c_sa[ci]; c.shape_b = s.c_sb[ci];
-                for (int k = 0; k < 3; ++k) { c.pos_a[k] = s.c_pa[ci][k]; c.pos_b[k] = s.c_pb[ci][k]; c.normal[k] = s.c_n[ci][k]; }
-                c.dist = s.c_dist[ci]; c.force = s.c_lam[ci] / dt;
+                const float* g = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci;
+                c.shape_a = __float_as_int(g[10]); c.shape_b = __float_as_int(g[11]);
+                for (int k = 0; k < 3; ++k) { c.pos_a[k] = g[k]; c.pos_b[k] = g[3 + k]; c.normal[k] = g[6 + k]; }
+                c.dist = g[9]; c.force = g[12] / dt;
             } else { c.shape_a = -1; c.shape_b = -1; for (int k = 0; k < 3; ++k) { c.pos_a[k] = c.pos_b[k] = c.normal[k] = 0; } c.dist = 0; c.force = 0; }
             c.pad[0] = c.pad[1] = c.pad[2] = 0;
             co[ci] = c;
@@ -1130,53 +1263,15 @@ avg_step_kernel(AvgStepArgs a) {
 // initial observation after reset (scratch_itch.py:268): FK + target + _get_obs([0],[0,0])
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_reset_obs_kernel(AvgStepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= a.n_env) return;
-    WarpSm& s = reinterpret_cast<WarpSm*>(smem_raw)[warp];
-    const int variant = a.variant ? a.variant[e] : 0;
-    const KM m = open_model(a.models[variant]);
-    const AvgModelHeader* h = m.h;
-    const int nj = h->n_jdof;
-    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
+    AVG_KERNEL_PREAMBLE(SmEpi)
     for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
     __syncwarp();
-    int* env_i = reinterpret_cast<int*>(s.env);
-    fk_warp(m, s, lane, h->n_body);
+    const int* env_i = reinterpret_cast<const int*>(s.env);
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
     if (lane == 0) {
         V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
-        V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
-        V3 torso, tool, sh, el, wr, chest; Q4 tq, dq;
-        frame_pose(m, s, AVG_F_TORSO, torso, dq);
-        frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
-        frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
-        frame_pose(m, s, AVG_F_ELBOW, el, dq);
-        frame_pose(m, s, AVG_F_WRIST, wr, dq);
-        frame_pose(m, s, AVG_F_CHEST, chest, dq);
-        float* o = s.obs; int k = 0; V3 t;
-        t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
-        t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = tgt - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
-        t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-        o[k++] = 0.0f;
-        if (h->human_control) {
-            t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
-            t = tool - tgt; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = tgt - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            int hq0 = k;
-            for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
-            for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
-            t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
-            o[k++] = 0.0f; o[k++] = 0.0f;
-        }
+        const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
+        fill_obs(m, s, tgt, 0.0f, 0.0f, 0.0f);
         st3(grec + AVG_E_TARGET_POS, tgt);
     }
     __syncwarp();
@@ -1184,28 +1279,45 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
 }
 
-size_t avg_kernel_smem_bytes() { return sizeof(WarpSm) * kWarpsPerBlock; }
+// =================================================================================================================
+// host-side launch helpers
+// =================================================================================================================
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
-cudaError_t avg_launch_step(const AvgStepArgs& a, cudaStream_t stream) {
+int avg_kernels_per_step(int substeps) { return 2 + 3 * substeps; }
+
+cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
     static bool configured = false;
-    size_t smem = avg_kernel_smem_bytes();
+    const size_t sm_col = sizeof(SmCollide) * kWarpsPerBlock, sm_dyn = sizeof(SmDyn) * kWarpsPerBlock;
+    const size_t sm_sol = sizeof(SmSolve) * kWarpsPerBlock, sm_epi = sizeof(SmEpi) * kWarpsPerBlock;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(avg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e1 != cudaSuccess) return e1;
-        e1 = cudaFuncSetAttribute(avg_reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e1 != cudaSuccess) return e1;
+        cudaError_t e1;
+        if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_dynamics_kernel, sm_dyn)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_solve_kernel, sm_sol)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
     }
-    int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    avg_step_kernel<<<blocks, 32 * kWarpsPerBlock, smem, stream>>>(a);
+    const int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock, threads = 32 * kWarpsPerBlock;
+    avg_prologue_kernel<<<blocks, threads, 0, stream>>>(a);
+    for (int f = 0; f < substeps; ++f) {
+        avg_collide_kernel<<<blocks, threads, sm_col, stream>>>(a);
+        avg_dynamics_kernel<<<blocks, threads, sm_dyn, stream>>>(a);
+        avg_solve_kernel<<<blocks, threads, sm_sol, stream>>>(a);
+    }
+    avg_epilogue_kernel<<<blocks, threads, sm_epi, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream) {
-    size_t smem = avg_kernel_smem_bytes();
-    cudaError_t e1 = cudaFuncSetAttribute(avg_reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t sm_epi = sizeof(SmEpi) * kWarpsPerBlock;
+    cudaError_t e1 = set_smem(avg_reset_obs_kernel, sm_epi);
     if (e1 != cudaSuccess) return e1;
-    int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    avg_reset_obs_kernel<<<blocks, 32 * kWarpsPerBlock, smem, stream>>>(a);
+    const int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    avg_reset_obs_kernel<<<blocks, 32 * kWarpsPerBlock, sm_epi, stream>>>(a);
     return cudaGetLastError();
 }

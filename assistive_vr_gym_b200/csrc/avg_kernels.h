@@ -5,14 +5,34 @@
 #include "../../include/avg_model.h"
 
 #define AVG_K_WARPS_PER_BLOCK 4
-#define AVG_K_MAXJ 24      /* 1-DoF joints per environment supported by the warp-per-environment kernel */
+#define AVG_K_MAXJ 24      /* 1-DoF joints per environment supported by the warp-per-environment kernels */
 #define AVG_K_MAXMS 24     /* moving collision shapes per environment */
 #define AVG_K_MAX_VARIANTS 4
+
+/* Scratch arena: per-environment hand-off between the kernels of one sub-step (floats; ints bit-cast). */
+#define AVG_S_MAXDENSE (6 + 2 * AVG_MAX_CONTACT)
+#define AVG_S_NC 0            /* contacts found by avg_collide_kernel                       */
+#define AVG_S_NR 1            /* constraint rows                                             */
+#define AVG_S_NS 2            /* rows [0, NS) are unit rows (+-e_i), the rest are dense      */
+#define AVG_S_NFR 3           /* first friction row                                          */
+#define AVG_S_FCR 4           /* first contact (normal) row                                  */
+#define AVG_S_NCS 5           /* contacts that received rows                                 */
+#define AVG_S_OVERFLOW 6
+#define AVG_S_ITERS 7         /* solver iterations accumulated over the env-step            */
+#define AVG_S_QD 8            /* [32] velocities after the unconstrained update             */
+#define AVG_S_CONTACT 40      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
+#define AVG_S_CONTACT_STRIDE 14
+#define AVG_S_ROWS (AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * AVG_MAX_CONTACT)            /* [64][2] float4 */
+#define AVG_S_MINV (AVG_S_ROWS + 8 * AVG_MAX_ROWS)                                       /* [MAXJ][MAXJ]   */
+#define AVG_S_J (AVG_S_MINV + AVG_K_MAXJ * AVG_K_MAXJ)                                  /* [MAXDENSE][32] */
+#define AVG_S_W (AVG_S_J + 32 * AVG_S_MAXDENSE)
+#define AVG_S_STRIDE (AVG_S_W + 32 * AVG_S_MAXDENSE)
 
 struct AvgStepArgs {
     const unsigned char* models[AVG_K_MAX_VARIANTS];   // device ModelBlobs
     const int32_t* variant;                            // [n_env] model variant per environment (may be null)
     float* env;                                        // [n_env][AVG_ENV_STRIDE]
+    float* scratch;                                    // [n_env][AVG_S_STRIDE]
     const float* actions;                              // [n_env][n_action]
     float* obs;                                        // [n_env][n_obs]
     float* reward;                                     // [n_env]
@@ -24,6 +44,6 @@ struct AvgStepArgs {
     int n_env;
 };
 
-size_t avg_kernel_smem_bytes();
-cudaError_t avg_launch_step(const AvgStepArgs& a, cudaStream_t stream);
+int avg_kernels_per_step(int substeps);
+cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
