@@ -288,9 +288,10 @@ __device__ bool simplex_closest(Simplex& s, V3& v) {
     return false;
 }
 
-// returns false: cores separated (dist, pa, pb valid); true: cores overlap.  Works relative to A's position to keep
-// float32 magnitudes small.
-__device__ __noinline__ bool gjk(const WShape& A, const WShape& B, float& dist, V3& pa, V3& pb) {
+// returns 0: cores separated (dist, pa, pb valid); 1: cores overlap; 2: separated by more than maxdist (early out: every
+// support plane gives the lower bound v.w/|v| on the distance, so well-separated candidates leave after 1-2 iterations).
+// Works relative to A's position to keep float32 magnitudes small.
+__device__ __noinline__ int gjk(const WShape& A, const WShape& B, float maxdist, float& dist, V3& pa, V3& pb) {
     Simplex s; s.n = 0;
     V3 org = A.p;
     V3 v = A.p - B.p;
@@ -300,18 +301,19 @@ __device__ __noinline__ bool gjk(const WShape& A, const WShape& B, float& dist, 
         V3 sa = support(A, -v) - org, sb = support(B, v) - org;
         V3 w = sa - sb;
         float vv = dot(v, v), vw = dot(v, w);
+        if (vw > 0.0f && vw * vw > maxdist * maxdist * vv) return 2;
         if (s.n > 0 && (vv - vw) <= 1e-5f * vv + 1e-10f) break;
         bool dup = false;
         for (int i = 0; i < s.n; ++i) { V3 d = s.w[i] - w; if (dot(d, d) < 1e-14f) dup = true; }
         if (dup) break;
         s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
-        if (simplex_closest(s, v)) return true;
-        if (dot(v, v) < 1e-12f) return true;
+        if (simplex_closest(s, v)) return 1;
+        if (dot(v, v) < 1e-12f) return 1;
     }
     V3 a = mk3(0, 0, 0), b = mk3(0, 0, 0);
     for (int i = 0; i < s.n; ++i) { a = a + s.a[i] * s.lam[i]; b = b + s.b[i] * s.lam[i]; }
     pa = a + org; pb = b + org; dist = norm(v);
-    return false;
+    return 0;
 }
 
 __device__ void sat_axis(const WShape& A, const WShape& B, V3 n, float& best, V3& bn, V3& bpa) {
@@ -362,7 +364,9 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
         return true;
     }
     float dist; V3 ca, cb;
-    if (!gjk(A, B, dist, ca, cb)) {
+    const int g = gjk(A, B, thr + ma + mb, dist, ca, cb);
+    if (g == 2) return false;
+    if (g == 0) {
         d = dist - ma - mb;
         if (d >= thr) return false;
         n = (ca - cb) * (1.0f / dist);
@@ -569,7 +573,7 @@ __device__ __noinline__ void finish_dense_row(SM& s, float* __restrict__ gJ, flo
 #define AVG_KERNEL_PREAMBLE(SMTYPE)                                                             \
     extern __shared__ __align__(16) unsigned char smem_raw[];                                    \
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                  \
-    const int e = blockIdx.x * kWarpsPerBlock + warp;                                            \
+    const int e = blockIdx.x * (blockDim.x >> 5) + warp;                                         \
     if (e >= a.n_env) return;                                                                    \
     SMTYPE& s = reinterpret_cast<SMTYPE*>(smem_raw)[warp];                                       \
     const int variant = a.variant ? a.variant[e] : 0;                                            \
@@ -585,7 +589,7 @@ __device__ __noinline__ void finish_dense_row(SM& s, float* __restrict__ gJ, flo
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_prologue_kernel(AvgStepArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    const int e = blockIdx.x * (blockDim.x >> 5) + warp;
     if (e >= a.n_env) return;
     const int variant = a.variant ? a.variant[e] : 0;
     const KM m = open_model(a.models[variant]);
@@ -1289,10 +1293,14 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 
 int avg_kernels_per_step(int substeps) { return 2 + 3 * substeps; }
 
+// warps (= environments) per block, per kernel.  The solver uses one warp per block: its iteration count varies per
+// environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
+constexpr int kWpbCollide = 4, kWpbDyn = 4, kWpbSolve = 1, kWpbEpi = 4, kWpbPro = 4;
+
 cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
     static bool configured = false;
-    const size_t sm_col = sizeof(SmCollide) * kWarpsPerBlock, sm_dyn = sizeof(SmDyn) * kWarpsPerBlock;
-    const size_t sm_sol = sizeof(SmSolve) * kWarpsPerBlock, sm_epi = sizeof(SmEpi) * kWarpsPerBlock;
+    const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
+    const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
     if (!configured) {
         cudaError_t e1;
         if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
@@ -1302,22 +1310,22 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
     }
-    const int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock, threads = 32 * kWarpsPerBlock;
-    avg_prologue_kernel<<<blocks, threads, 0, stream>>>(a);
+    auto grid = [&](int wpb) { return (a.n_env + wpb - 1) / wpb; };
+    avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
     for (int f = 0; f < substeps; ++f) {
-        avg_collide_kernel<<<blocks, threads, sm_col, stream>>>(a);
-        avg_dynamics_kernel<<<blocks, threads, sm_dyn, stream>>>(a);
-        avg_solve_kernel<<<blocks, threads, sm_sol, stream>>>(a);
+        avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+        avg_dynamics_kernel<<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        avg_solve_kernel<<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
     }
-    avg_epilogue_kernel<<<blocks, threads, sm_epi, stream>>>(a);
+    avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream) {
-    const size_t sm_epi = sizeof(SmEpi) * kWarpsPerBlock;
+    const size_t sm_epi = sizeof(SmEpi) * kWpbEpi;
     cudaError_t e1 = set_smem(avg_reset_obs_kernel, sm_epi);
     if (e1 != cudaSuccess) return e1;
-    const int blocks = (a.n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    avg_reset_obs_kernel<<<blocks, 32 * kWarpsPerBlock, sm_epi, stream>>>(a);
+    const int blocks = (a.n_env + kWpbEpi - 1) / kWpbEpi;
+    avg_reset_obs_kernel<<<blocks, 32 * kWpbEpi, sm_epi, stream>>>(a);
     return cudaGetLastError();
 }
