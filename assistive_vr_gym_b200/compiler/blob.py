@@ -8,7 +8,7 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 4
+AVG_VERSION = 5
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -96,6 +96,7 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
             c, h = _world_aabb(d, s.pos, s.quat)
             r["aabb_c"] = c; r["aabb_h"] = h
     verts = np.concatenate(verts, axis=0).astype("<f4") if verts else np.zeros((0, 3), "<f4")
+    verts = np.concatenate([verts, np.zeros((len(verts), 1), "<f4")], axis=1)          # padded to float4 for 16-byte loads
     planes = np.concatenate(planes, axis=0).astype("<f4") if planes else np.zeros((0, 4), "<f4")
     pairs = (scene.pairs[:, 0].astype("<u4") | (scene.pairs[:, 1].astype("<u4") << 16)).astype("<u4")
     frames = np.zeros(len(scene.frames), dtype=FRAME_DT)
@@ -159,7 +160,7 @@ def read_blob(blob: bytes) -> dict:
     out["bodies"] = np.frombuffer(blob, dtype=BODY_DT, count=int(h["n_body"]), offset=int(h["off_body"]))
     out["dofs"] = np.frombuffer(blob, dtype=DOF_DT, count=int(h["n_dof"]), offset=int(h["off_dof"]))
     out["shapes"] = np.frombuffer(blob, dtype=SHAPE_DT, count=int(h["n_shape"]), offset=int(h["off_shape"]))
-    out["verts"] = np.frombuffer(blob, dtype="<f4", count=3 * int(h["n_vert"]), offset=int(h["off_vert"])).reshape(-1, 3)
+    out["verts"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_vert"]), offset=int(h["off_vert"])).reshape(-1, 4)[:, :3]
     out["planes"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_plane"]), offset=int(h["off_plane"])).reshape(-1, 4)
     out["pairs"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_pair"]), offset=int(h["off_pair"]))
     out["frames"] = np.frombuffer(blob, dtype=FRAME_DT, count=int(h["n_frame"]), offset=int(h["off_frame"]))

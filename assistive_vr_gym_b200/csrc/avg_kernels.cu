@@ -174,7 +174,7 @@ struct WShape {
 template <class SM>
 __device__ __forceinline__ void load_wshape(const KM& m, const SM& s, int si, WShape& w) {
     const AvgShape* S = &m.shape[si];
-    w.s = S; w.verts = m.vert + 3 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
+    w.s = S; w.verts = m.vert + 4 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
     if (si < m.h->n_mshape) {
         w.p = ld3(s.sp[si]);
 #pragma unroll
@@ -204,14 +204,15 @@ __device__ __noinline__ V3 support(const WShape& w, V3 d) {
         break;
     }
     case AVG_SHAPE_HULL: {
-        int best = 0; float bd = -3.0e38f;
-        const float* v = w.verts;
+        float bd = -3.0e38f; float4 bv = make_float4(0, 0, 0, 0);
+        const float4* v = reinterpret_cast<const float4*>(w.verts);
 #pragma unroll 4
         for (int i = 0; i < S->vert_cnt; ++i) {
-            float dd = fmaf(l.x, v[3 * i], fmaf(l.y, v[3 * i + 1], l.z * v[3 * i + 2]));
-            if (dd > bd) { bd = dd; best = i; }
+            const float4 p = __ldg(v + i);
+            const float dd = fmaf(l.x, p.x, fmaf(l.y, p.y, l.z * p.z));
+            if (dd > bd) { bd = dd; bv = p; }
         }
-        r = mk3(v[3 * best], v[3 * best + 1], v[3 * best + 2]); break;
+        r = mk3(bv.x, bv.y, bv.z); break;
     }
     default: r = mk3(0, 0, 0);       // sphere core = its centre
     }
@@ -641,7 +642,7 @@ avg_prologue_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // forward kinematics + collision -> contact list in the scratch arena
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, 5)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     s.q[lane] = grec[AVG_E_Q + lane];
@@ -663,7 +664,7 @@ avg_collide_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, 5)
 avg_dynamics_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmDyn)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;

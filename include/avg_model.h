@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 4u
+#define AVG_VERSION 5u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -74,7 +74,7 @@ typedef struct AvgShape {         /* 32 x 4 bytes */
     float    radius;              /* sphere / capsule / cylinder                                            */
     float    half[3];             /* box half extents; capsule / cylinder: half[2] = half length            */
     float    margin;              /* rounding radius added around the GJK core                              */
-    int32_t  vert_off, vert_cnt;  /* hull vertices (shape frame)                                            */
+    int32_t  vert_off, vert_cnt;  /* hull vertices (shape frame), stored as float4 (x, y, z, 0)              */
     int32_t  plane_off, plane_cnt;/* hull face planes (n, d), n.x <= d inside                               */
     float    friction;
     float    thr;                 /* contact-breaking threshold of the owning link's compound               */

@@ -174,7 +174,7 @@ typedef struct {
 
 static void shape_world(const Model* m, const Kin* k, int si, WShape* w) {
     const AvgShape* s = &m->shape[si];
-    w->s = s; w->verts = m->vert + 3 * s->vert_off; w->planes = m->plane + 4 * s->plane_off;
+    w->s = s; w->verts = m->vert + 4 * s->vert_off; w->planes = m->plane + 4 * s->plane_off;
     if (s->body < 0) { w->p = f3(s->pos); w->R = qmat(qf(s->quat)); }
     else {
         w->p = vadd(k->p[s->body], qrot(k->q[s->body], f3(s->pos)));
@@ -213,10 +213,10 @@ static v3 support(const WShape* w, v3 d) {
     case AVG_SHAPE_HULL: {
         int best = 0; double bd = -1e300;
         for (int i = 0; i < s->vert_cnt; ++i) {
-            double dd = l.x * w->verts[3 * i] + l.y * w->verts[3 * i + 1] + l.z * w->verts[3 * i + 2];
+            double dd = l.x * w->verts[4 * i] + l.y * w->verts[4 * i + 1] + l.z * w->verts[4 * i + 2];
             if (dd > bd) { bd = dd; best = i; }
         }
-        r = V(w->verts[3 * best], w->verts[3 * best + 1], w->verts[3 * best + 2]); break;
+        r = V(w->verts[4 * best], w->verts[4 * best + 1], w->verts[4 * best + 2]); break;
     }
     default: r = V(0, 0, 0);
     }
@@ -1063,8 +1063,8 @@ int avg_oracle_collide(const void* blob, const double* env, double* contacts_out
 int avg_oracle_shape_pair(const void* blob, int sa, const double* pose_a, int sb, const double* pose_b, double thr, double* out) {
     Model m; if (model_open(blob, &m)) return -1;
     WShape A, B;
-    A.s = &m.shape[sa]; A.verts = m.vert + 3 * A.s->vert_off; A.planes = m.plane + 4 * A.s->plane_off;
-    B.s = &m.shape[sb]; B.verts = m.vert + 3 * B.s->vert_off; B.planes = m.plane + 4 * B.s->plane_off;
+    A.s = &m.shape[sa]; A.verts = m.vert + 4 * A.s->vert_off; A.planes = m.plane + 4 * A.s->plane_off;
+    B.s = &m.shape[sb]; B.verts = m.vert + 4 * B.s->vert_off; B.planes = m.plane + 4 * B.s->plane_off;
     quat qa = {pose_a[3], pose_a[4], pose_a[5], pose_a[6]}, qb = {pose_b[3], pose_b[4], pose_b[5], pose_b[6]};
     A.p = V(pose_a[0], pose_a[1], pose_a[2]); A.R = qmat(qnormalize(qa));
     B.p = V(pose_b[0], pose_b[1], pose_b[2]); B.R = qmat(qnormalize(qb));
