@@ -96,8 +96,9 @@ struct __align__(16) SmSolve {
     float Minv[kMaxJ][kMaxJ + 1];
     float J[kSmDense][32];
     float W[kSmDense][32];
-    float4 r_a[kMaxRows];
-    float4 r_b[kMaxRows];
+    float4 um[32][2];                      // motor row of dof i: {target, 1/diag, lo, hi}, {diag, sign, -, -}
+    float4 ul[32][2];                      // limit row of dof i (null row when the limit is not violated)
+    float4 rd[kMaxDense][2];               // dense rows: {target, 1/diag, lo, hi}, {diag, mu, index, normal row}
 };
 struct __align__(16) SmEpi {
     float env[AVG_ENV_STRIDE];
@@ -683,7 +684,6 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
     __syncwarp();
     fk_warp(m, s, s.env + AVG_E_Q, lane, nb);
-    float4* g_rows = reinterpret_cast<float4*>(scr + AVG_S_ROWS);
     float* gJ = scr + AVG_S_J; float* gW = scr + AVG_S_W;
 
     // ---- per-lane body quantities ------------------------------------------------------------------------------
@@ -855,56 +855,40 @@ avg_dynamics_kernel(AvgStepArgs a) {
     qd = qd + dt * qdd;
 
     // ---- constraint rows ------------------------------------------------------------------------------------------
-    int nr = 0;
-    // position motors: lane i prepares its own row, rows are appended in dof order
+    // Unit rows (+-e_i) are stored per dof: a motor row and at most one limit row (a dof can violate one side only).
+    // Rows of different articulations do not couple (block-diagonal M^-1), so the solver sweeps the blocks
+    // concurrently; inside a block the order is Bullet's: motors in dof order, then limits in dof order.
+    int nlim;
     {
-        bool has = false; float tgt = 0, lo = 0, hi = 0;
+        float4 ma = make_float4(0, 0, 0, 0), mb = make_float4(0, 0, 0, 0), la = ma, lb = ma;
+        bool has_lim = false;
         if (lane < nj) {
             const AvgDof* D = &m.dof[lane];
-            if (D->flags & AVG_DOF_MOTOR) {
-                has = true;
-                bool hum = D->flags & AVG_DOF_HUMAN;
-                float kp = hum ? s.env[AVG_E_HUMAN_KP] : D->kp;
-                float maxf = hum ? h->task_f[AVG_TF_HUMAN_FORCE] * s.env[AVG_E_STRENGTH] : D->max_force;
-                float q = s.env[AVG_E_Q + m.body[D->body].qidx];
-                tgt = kp * (s.env[AVG_E_MTARGET + lane] - q) / dt - D->kd * qd;
-                lo = -maxf * dt; hi = maxf * dt;
+            const float diag = s.Minv[lane][lane];
+            const float inv = diag > 1e-12f ? 1.0f / diag : 0.0f;
+            const float q = s.env[AVG_E_Q + m.body[D->body].qidx];
+            if (D->flags & AVG_DOF_MOTOR) {        // btMultiBodyJointMotor: velocity target kp (q*-q)/dt - kd qd, clamp force*dt
+                const bool hum = D->flags & AVG_DOF_HUMAN;
+                const float kp = hum ? s.env[AVG_E_HUMAN_KP] : D->kp;
+                const float maxf = hum ? h->task_f[AVG_TF_HUMAN_FORCE] * s.env[AVG_E_STRENGTH] : D->max_force;
+                ma = make_float4(kp * (s.env[AVG_E_MTARGET + lane] - q) / dt - D->kd * qd, inv, -maxf * dt, maxf * dt);
+                mb = make_float4(diag, 1.0f, 0.0f, 0.0f);
+            }
+            if (D->flags & AVG_DOF_LIMIT) {        // btMultiBodyJointLimitConstraint: only while violated, [0, 100]
+                const float sc = (D->flags & AVG_DOF_HUMAN) ? s.env[AVG_E_LIMIT_SCALE] : 1.0f;
+                const float pen0 = q - D->lower * sc, pen1 = D->upper * sc - q;
+                if (pen0 <= 0) { has_lim = true; la = make_float4(-pen0 * h->erp / dt - qd, inv, 0.0f, 100.0f); lb = make_float4(diag, 1.0f, 0.0f, 0.0f); }
+                else if (pen1 <= 0) { has_lim = true; la = make_float4(-pen1 * h->erp / dt + qd, inv, 0.0f, 100.0f); lb = make_float4(diag, -1.0f, 0.0f, 0.0f); }
             }
         }
-        unsigned bal = __ballot_sync(AVG_FULL, has);
-        if (has) {
-            int r = nr + __popc(bal & ((1u << lane) - 1));
-            float diag = s.Minv[lane][lane];
-            g_rows[2 * r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float(lane), __int_as_float(-1));
-        }
-        nr += __popc(bal);
+        float4* g_um = reinterpret_cast<float4*>(scr + AVG_S_ROWS_M);
+        float4* g_ul = reinterpret_cast<float4*>(scr + AVG_S_ROWS_L);
+        g_um[2 * lane] = ma; g_um[2 * lane + 1] = mb;
+        g_ul[2 * lane] = la; g_ul[2 * lane + 1] = lb;
+        nlim = __popc(__ballot_sync(AVG_FULL, has_lim));
     }
-    // joint limits, only while violated; a dof can violate one side only, rows stay in dof order
-    {
-        bool has = false; float tgt = 0; int kind = 0;
-        if (lane < nj) {
-            const AvgDof* D = &m.dof[lane];
-            if (D->flags & AVG_DOF_LIMIT) {
-                float sc = (D->flags & AVG_DOF_HUMAN) ? s.env[AVG_E_LIMIT_SCALE] : 1.0f;
-                float q = s.env[AVG_E_Q + m.body[D->body].qidx];
-                float pen0 = q - D->lower * sc, pen1 = D->upper * sc - q;
-                if (pen0 <= 0) { has = true; kind = 0; tgt = -pen0 * h->erp / dt - qd; }
-                else if (pen1 <= 0) { has = true; kind = 1; tgt = -pen1 * h->erp / dt + qd; }
-            }
-        }
-        unsigned bal = __ballot_sync(AVG_FULL, has);
-        if (has) {
-            int r = nr + __popc(bal & ((1u << lane) - 1));
-            if (r < kMaxRows) {
-                float diag = s.Minv[lane][lane];
-                g_rows[2 * r] = make_float4(tgt, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 100.0f); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((kind << 8) | lane), __int_as_float(-1));
-            }
-        }
-        nr += __popc(bal);
-        if (nr > kMaxRows - 6) { overflow |= 2; nr = kMaxRows - 6; }
-    }
+    float4* g_rows = reinterpret_cast<float4*>(scr + AVG_S_ROWS_D);      // dense rows, indexed by dense row number
     // tool weld, 6 dense rows
-    const int ns = nr;                       // rows [0, ns) are unit rows (+-e_i), rows [ns, nr) are dense
     int ndense = 0;
     {
         V3 pa, pb; Q4 qa, qb;
@@ -932,16 +916,15 @@ avg_dynamics_kernel(AvgStepArgs a) {
             float diag, u0;
             finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
             if (lane == 0) {
-                int r = nr;
+                const int r = ndense;
                 g_rows[2 * r] = make_float4(-err * h->erp / dt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, -maxi, maxi); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
             }
-            nr++; ndense++;
+            ndense++;
         }
     }
     // contacts: normals first, then one friction row each (Bullet's row order)
-    int nc = ncontact;
-    if (nc > (kMaxRows - nr) / 2) { overflow |= 2; nc = (kMaxRows - nr) / 2; ncontact = nc; }
-    const int first_contact_row = nr;
+    const int nc = ncontact;                   // kMaxDense = 6 + 2 * AVG_MAX_CONTACT always has room
+    const int first_contact_row = ndense;
 #pragma unroll 1
     for (int ci = 0; ci < nc; ++ci) {
         V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
@@ -952,10 +935,10 @@ avg_dynamics_kernel(AvgStepArgs a) {
         finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
         if (lane == 0) {
             float dist = s.c_dist[ci];
-            int r = nr;
+            const int r = ndense;
             g_rows[2 * r] = make_float4((dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 1e30f); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
         }
-        nr++; ndense++;
+        ndense++;
     }
 #pragma unroll 1
     for (int ci = 0; ci < nc; ++ci) {
@@ -976,10 +959,10 @@ avg_dynamics_kernel(AvgStepArgs a) {
         float diag, u0;
         finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
         if (lane == 0) {
-            int r = nr;
+            const int r = ndense;
             g_rows[2 * r] = make_float4(-u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 0.0f); g_rows[2 * r + 1] = make_float4(diag, m.shape[sa].friction * m.shape[sb].friction, __int_as_float((2 << 8) | ndense), __int_as_float(first_contact_row + ci));
         }
-        nr++; ndense++;
+        ndense++;
     }
     __syncwarp();
 
@@ -988,7 +971,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     if (lane < nd) scr[AVG_S_QD + lane] = qd;
     for (int i = 0; i < nj; ++i) if (lane < nj) scr[AVG_S_MINV + i * kMaxJ + lane] = s.Minv[i][lane];
     if (lane == 0) {
-        scr_i[AVG_S_NR] = nr; scr_i[AVG_S_NS] = ns; scr_i[AVG_S_NFR] = first_contact_row + nc; scr_i[AVG_S_FCR] = first_contact_row;
+        scr_i[AVG_S_NR] = ndense; scr_i[AVG_S_NS] = nlim; scr_i[AVG_S_NFR] = first_contact_row + nc; scr_i[AVG_S_FCR] = first_contact_row;
         scr_i[AVG_S_NCS] = nc;
         if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow;
     }
@@ -1003,73 +986,100 @@ avg_solve_kernel(AvgStepArgs a) {
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
     int* scr_i = reinterpret_cast<int*>(scr);
-    const int nr = scr_i[AVG_S_NR], ns = scr_i[AVG_S_NS], nfr = scr_i[AVG_S_NFR], first_contact_row = scr_i[AVG_S_FCR];
+    const int ndense = scr_i[AVG_S_NR], nlim = scr_i[AVG_S_NS], nfr = scr_i[AVG_S_NFR], first_contact_row = scr_i[AVG_S_FCR];
     const int nc = scr_i[AVG_S_NCS];
-    const int ndense = nr - ns;
     const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
     // stage rows: coalesced loads from the arena
     for (int i = 0; i < nj; ++i) if (lane < nj) s.Minv[i][lane] = scr[AVG_S_MINV + i * kMaxJ + lane];
     for (int d = 0; d < min(ndense, kSmDense); ++d) { s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
     {
-        const float4* g_rows = reinterpret_cast<const float4*>(scr + AVG_S_ROWS);
-        for (int i = lane; i < 2 * nr; i += 32) {
-            const float4 v = g_rows[i];
-            if (i & 1) s.r_b[i >> 1] = v; else s.r_a[i >> 1] = v;
-        }
+        const float4* g_um = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_M);
+        const float4* g_ul = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_L);
+        const float4* g_rd = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_D);
+        s.um[lane][0] = g_um[2 * lane]; s.um[lane][1] = g_um[2 * lane + 1];
+        if (nlim) { s.ul[lane][0] = g_ul[2 * lane]; s.ul[lane][1] = g_ul[2 * lane + 1]; }
+        for (int i = lane; i < 2 * ndense; i += 32) s.rd[i >> 1][i & 1] = g_rd[i];
     }
     const float qd = lane < nd ? scr[AVG_S_QD + lane] : 0.0f;
+    // block of this lane's dof
+    int bs = lane, be = lane, maxblk = 0;
+    for (int b = 0; b < h->n_block; ++b) {
+        const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
+        if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
+        maxblk = max(maxblk, b1 - b0);
+    }
     __syncwarp();
 
-    // ---- projected Gauss-Seidel, strict row order (unit rows, dense bilateral/normal rows, friction rows).
-    //      dv lives in one register per lane; the accumulated impulse of row r lives in lane r%32 (slot r/32).
-    float dv = 0.0f, lam0 = 0.0f, lam1 = 0.0f;
+    // ---- projected Gauss-Seidel.  dv lives in one register per lane.  Unit rows: the articulation blocks are swept
+    //      concurrently (they do not couple), in Bullet's order inside a block; their impulses live in the lane of
+    //      their dof.  Dense rows (weld, contact normals, friction) follow in strict order; impulse of dense row d in
+    //      lane d.
+    float dv = 0.0f, lamM = 0.0f, lamL = 0.0f, lamD = 0.0f;
     const float thr = h->residual_thr;
     int iters = 0;
     for (int it = 0; it < h->solver_iters; ++it) {
         float resid = 0.0f;
 #pragma unroll 2
-        for (int r = 0; r < ns; ++r) {
-            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
-            const int idx = __float_as_int(rb.z), i = idx & 0xff;
-            const float sg = (idx >> 8) ? -1.0f : 1.0f;
-            const float jdv = sg * __shfl_sync(AVG_FULL, dv, i);
-            const float wl = lane < nj ? sg * s.Minv[i][lane] : 0.0f;
-            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
+        for (int t = 0; t < maxblk; ++t) {
+            const int i = bs + t < be ? bs + t : lane;           // idle lanes point at themselves with a null row
+            const bool act = bs + t < be;
+            const float4 ra = s.um[i][0]; const float diag = s.um[i][1].x;
+            const float jdv = __shfl_sync(AVG_FULL, dv, i);
+            const float lam = __shfl_sync(AVG_FULL, lamM, i);
+            const float wl = act ? s.Minv[i][lane] : 0.0f;
+            float delta = act ? (ra.x - jdv) * ra.y : 0.0f;
+            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
+            delta = act ? sum - lam : 0.0f;
+            if (lane == i && act) lamM = sum;
+            dv = fmaf(wl, delta, dv);
+            const float rv = delta * diag;
+            resid = fmaxf(resid, rv * rv);
+        }
+        if (nlim) {
+            for (int t = 0; t < maxblk; ++t) {
+                const int i = bs + t < be ? bs + t : lane;
+                const bool act = bs + t < be;
+                const float4 ra = s.ul[i][0]; const float4 rb = s.ul[i][1];
+                const float sg = rb.y;
+                const float jdv = sg * __shfl_sync(AVG_FULL, dv, i);
+                const float lam = __shfl_sync(AVG_FULL, lamL, i);
+                const float wl = act ? sg * s.Minv[i][lane] : 0.0f;
+                float delta = act ? (ra.x - jdv) * ra.y : 0.0f;
+                const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
+                delta = act ? sum - lam : 0.0f;
+                if (lane == i && act) lamL = sum;
+                dv = fmaf(wl, delta, dv);
+                const float rv = delta * rb.x;
+                resid = fmaxf(resid, rv * rv);
+            }
+        }
+        resid = warp_max(resid);                                   // blocks ran in different lanes
+#pragma unroll 1
+        for (int d = 0; d < nfr; ++d) {
+            const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
+            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
+            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
+            const float lam = __shfl_sync(AVG_FULL, lamD, d);
             float delta = (ra.x - jdv) * ra.y;
             const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
             delta = sum - lam;
-            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
+            if (lane == d) lamD = sum;
             dv = fmaf(wl, delta, dv);
             const float rv = delta * rb.x;
             resid = fmaxf(resid, rv * rv);
         }
 #pragma unroll 1
-        for (int r = ns; r < nfr; ++r) {
-            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
-            const int d = r - ns;
+        for (int d = nfr; d < ndense; ++d) {
+            const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
+            const int par = __float_as_int(rb.w);
             const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
             const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
-            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
-            float delta = (ra.x - jdv) * ra.y;
-            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
-            delta = sum - lam;
-            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
-            dv = fmaf(wl, delta, dv);
-            const float rv = delta * rb.x;
-            resid = fmaxf(resid, rv * rv);
-        }
-#pragma unroll 1
-        for (int r = nfr; r < nr; ++r) {
-            const float4 ra = s.r_a[r]; const float4 rb = s.r_b[r];
-            const int d = r - ns, par = __float_as_int(rb.w);
-            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
-            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
-            const float lam = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
-            const float lim = rb.y * __shfl_sync(AVG_FULL, par < 32 ? lam0 : lam1, par & 31);
+            const float lam = __shfl_sync(AVG_FULL, lamD, d);
+            const float lim = rb.y * __shfl_sync(AVG_FULL, lamD, par);
             float delta = (ra.x - jdv) * ra.y;
             const float sum = fminf(fmaxf(lam + delta, -lim), lim);
             delta = sum - lam;
-            if (lane == (r & 31)) { if (r < 32) lam0 = sum; else lam1 = sum; }
+            if (lane == d) lamD = sum;
             dv = fmaf(wl, delta, dv);
             const float rv = delta * rb.x;
             resid = fmaxf(resid, rv * rv);
@@ -1079,11 +1089,8 @@ avg_solve_kernel(AvgStepArgs a) {
     }
 
     // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
-    for (int ci = 0; ci < nc; ++ci) {
-        const int r = first_contact_row + ci;
-        const float l = __shfl_sync(AVG_FULL, r < 32 ? lam0 : lam1, r & 31);
-        if (lane == 0) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci + 12] = l;
-    }
+    if (lane >= first_contact_row && lane < first_contact_row + nc)
+        scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * (lane - first_contact_row) + 12] = lamD;
     if (lane == 0) scr_i[AVG_S_ITERS] += iters;
 
     // ---- integrate (semi-implicit Euler) + enforce_hard_human_joint_limits (env.py:389-410) -----------------------

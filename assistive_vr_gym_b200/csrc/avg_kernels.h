@@ -12,18 +12,20 @@
 /* Scratch arena: per-environment hand-off between the kernels of one sub-step (floats; ints bit-cast). */
 #define AVG_S_MAXDENSE (6 + 2 * AVG_MAX_CONTACT)
 #define AVG_S_NC 0            /* contacts found by avg_collide_kernel                       */
-#define AVG_S_NR 1            /* constraint rows                                             */
-#define AVG_S_NS 2            /* rows [0, NS) are unit rows (+-e_i), the rest are dense      */
-#define AVG_S_NFR 3           /* first friction row                                          */
-#define AVG_S_FCR 4           /* first contact (normal) row                                  */
+#define AVG_S_NR 1            /* dense constraint rows (weld, contact normals, friction)    */
+#define AVG_S_NS 2            /* joint-limit rows active in this sub-step                    */
+#define AVG_S_NFR 3           /* first friction row (dense index)                            */
+#define AVG_S_FCR 4           /* first contact normal row (dense index)                      */
 #define AVG_S_NCS 5           /* contacts that received rows                                 */
 #define AVG_S_OVERFLOW 6
 #define AVG_S_ITERS 7         /* solver iterations accumulated over the env-step            */
 #define AVG_S_QD 8            /* [32] velocities after the unconstrained update             */
 #define AVG_S_CONTACT 40      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
 #define AVG_S_CONTACT_STRIDE 14
-#define AVG_S_ROWS (AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * AVG_MAX_CONTACT)            /* [64][2] float4 */
-#define AVG_S_MINV (AVG_S_ROWS + 8 * AVG_MAX_ROWS)                                       /* [MAXJ][MAXJ]   */
+#define AVG_S_ROWS_M (AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * AVG_MAX_CONTACT)          /* [32][2] float4: motor row per dof */
+#define AVG_S_ROWS_L (AVG_S_ROWS_M + 8 * 32)                                             /* [32][2] float4: limit row per dof */
+#define AVG_S_ROWS_D (AVG_S_ROWS_L + 8 * 32)                                             /* [MAXDENSE][2] float4              */
+#define AVG_S_MINV (AVG_S_ROWS_D + 8 * AVG_S_MAXDENSE)                                   /* [MAXJ][MAXJ]   */
 #define AVG_S_J (AVG_S_MINV + AVG_K_MAXJ * AVG_K_MAXJ)                                  /* [MAXDENSE][32] */
 #define AVG_S_W (AVG_S_J + 32 * AVG_S_MAXDENSE)
 #define AVG_S_STRIDE (AVG_S_W + 32 * AVG_S_MAXDENSE)
