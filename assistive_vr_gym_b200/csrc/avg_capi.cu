@@ -19,6 +19,7 @@ struct AvgHandle {
     float* d_env = nullptr;
     float* d_scratch = nullptr;
     int substeps = 5;
+    int maxblk = 0;
     int32_t* d_variant = nullptr;
     // debug taps
     bool debug = false;
@@ -121,6 +122,11 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     if (h->task >= 0 && h->substeps != mh->substeps && variant != 0)
         return fail(h, -4, "avg_upload_model: variants of one handle must share frame_skip");
     h->task = mh->task; h->n_act = na; h->n_obs = no; h->substeps = mh->substeps;
+    for (int b = 0; b < mh->n_block; ++b) {
+        int sz = mh->block_start[b + 1] - mh->block_start[b];
+        if (sz > 16) return fail(h, -4, "avg_upload_model: articulation with more than 16 dofs (solver register block)");
+        if (sz > h->maxblk) h->maxblk = sz;
+    }
     return 0;
 }
 
@@ -154,7 +160,7 @@ float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 static int fill_args(AvgHandle* h, AvgStepArgs& a) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
-    a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env;
+    a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     a.contacts = h->debug ? h->d_contacts : nullptr;
     a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
     a.terms = h->debug ? h->d_terms : nullptr;

@@ -42,7 +42,8 @@ constexpr int kMaxCand = 64;               // narrowphase candidates per sub-ste
 constexpr int kMaxC = AVG_MAX_CONTACT;
 constexpr int kMaxDense = AVG_S_MAXDENSE;  // weld rows + contact normal + friction rows
 constexpr int kMaxRows = AVG_MAX_ROWS;
-constexpr int kSmDense = 14;               // dense rows staged in shared memory by the solver (weld + 4 contacts)
+constexpr int kSmDense = 10;               // dense rows staged in shared memory by the solver (weld + 2 contacts); more spill to L1
+constexpr int kMaxBlk = 16;                // largest articulation (diagonal block of M^-1) the solver keeps in registers
 
 struct KM {                                // device view of a ModelBlob
     const AvgModelHeader* h;
@@ -93,11 +94,10 @@ struct __align__(16) SmDyn {
     int c_sa[kMaxC], c_sb[kMaxC];
 };
 struct __align__(16) SmSolve {
-    float Minv[kMaxJ][kMaxJ + 1];
     float J[kSmDense][32];
     float W[kSmDense][32];
-    float4 um[32][2];                      // motor row of dof i: {target, 1/diag, lo, hi}, {diag, sign, -, -}
-    float4 ul[32][2];                      // limit row of dof i (null row when the limit is not violated)
+    float4 um[32];                         // motor row of dof i: {target, 1/diag, hi (lo = -hi), diag}
+    float4 ul[32];                         // limit row of dof i: {target, 1/diag, diag, sign}; 1/diag = 0 when not violated
     float4 rd[kMaxDense][2];               // dense rows: {target, 1/diag, lo, hi}, {diag, mu, index, normal row}
 };
 struct __align__(16) SmEpi {
@@ -860,7 +860,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     // concurrently; inside a block the order is Bullet's: motors in dof order, then limits in dof order.
     int nlim;
     {
-        float4 ma = make_float4(0, 0, 0, 0), mb = make_float4(0, 0, 0, 0), la = ma, lb = ma;
+        float4 ma = make_float4(0, 0, 0, 0), la = ma;
         bool has_lim = false;
         if (lane < nj) {
             const AvgDof* D = &m.dof[lane];
@@ -871,20 +871,18 @@ avg_dynamics_kernel(AvgStepArgs a) {
                 const bool hum = D->flags & AVG_DOF_HUMAN;
                 const float kp = hum ? s.env[AVG_E_HUMAN_KP] : D->kp;
                 const float maxf = hum ? h->task_f[AVG_TF_HUMAN_FORCE] * s.env[AVG_E_STRENGTH] : D->max_force;
-                ma = make_float4(kp * (s.env[AVG_E_MTARGET + lane] - q) / dt - D->kd * qd, inv, -maxf * dt, maxf * dt);
-                mb = make_float4(diag, 1.0f, 0.0f, 0.0f);
+                ma = make_float4(kp * (s.env[AVG_E_MTARGET + lane] - q) / dt - D->kd * qd, inv, maxf * dt, diag);
             }
             if (D->flags & AVG_DOF_LIMIT) {        // btMultiBodyJointLimitConstraint: only while violated, [0, 100]
                 const float sc = (D->flags & AVG_DOF_HUMAN) ? s.env[AVG_E_LIMIT_SCALE] : 1.0f;
                 const float pen0 = q - D->lower * sc, pen1 = D->upper * sc - q;
-                if (pen0 <= 0) { has_lim = true; la = make_float4(-pen0 * h->erp / dt - qd, inv, 0.0f, 100.0f); lb = make_float4(diag, 1.0f, 0.0f, 0.0f); }
-                else if (pen1 <= 0) { has_lim = true; la = make_float4(-pen1 * h->erp / dt + qd, inv, 0.0f, 100.0f); lb = make_float4(diag, -1.0f, 0.0f, 0.0f); }
+                if (pen0 <= 0) { has_lim = true; la = make_float4(-pen0 * h->erp / dt - qd, inv, diag, 1.0f); }
+                else if (pen1 <= 0) { has_lim = true; la = make_float4(-pen1 * h->erp / dt + qd, inv, diag, -1.0f); }
             }
         }
         float4* g_um = reinterpret_cast<float4*>(scr + AVG_S_ROWS_M);
         float4* g_ul = reinterpret_cast<float4*>(scr + AVG_S_ROWS_L);
-        g_um[2 * lane] = ma; g_um[2 * lane + 1] = mb;
-        g_ul[2 * lane] = la; g_ul[2 * lane + 1] = lb;
+        g_um[lane] = ma; g_ul[lane] = la;
         nlim = __popc(__ballot_sync(AVG_FULL, has_lim));
     }
     float4* g_rows = reinterpret_cast<float4*>(scr + AVG_S_ROWS_D);      // dense rows, indexed by dense row number
@@ -980,7 +978,8 @@ avg_dynamics_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+template <int MAXBLK>
+__global__ void __launch_bounds__(32, 32)
 avg_solve_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmSolve)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
@@ -990,67 +989,61 @@ avg_solve_kernel(AvgStepArgs a) {
     const int nc = scr_i[AVG_S_NCS];
     const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
     // stage rows: coalesced loads from the arena
-    for (int i = 0; i < nj; ++i) if (lane < nj) s.Minv[i][lane] = scr[AVG_S_MINV + i * kMaxJ + lane];
     for (int d = 0; d < min(ndense, kSmDense); ++d) { s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
     {
         const float4* g_um = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_M);
         const float4* g_ul = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_L);
         const float4* g_rd = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_D);
-        s.um[lane][0] = g_um[2 * lane]; s.um[lane][1] = g_um[2 * lane + 1];
-        if (nlim) { s.ul[lane][0] = g_ul[2 * lane]; s.ul[lane][1] = g_ul[2 * lane + 1]; }
+        s.um[lane] = g_um[lane];
+        if (nlim) s.ul[lane] = g_ul[lane];
         for (int i = lane; i < 2 * ndense; i += 32) s.rd[i >> 1][i & 1] = g_rd[i];
     }
     const float qd = lane < nd ? scr[AVG_S_QD + lane] : 0.0f;
-    // block of this lane's dof
-    int bs = lane, be = lane, maxblk = 0;
+    // block of this lane's dof, and this lane's column of the block of M^-1 (registers)
+    int bs = lane, be = lane;
     for (int b = 0; b < h->n_block; ++b) {
         const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
         if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
-        maxblk = max(maxblk, b1 - b0);
     }
+    float mcol[MAXBLK];
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) mcol[t] = (bs + t < be) ? scr[AVG_S_MINV + (bs + t) * kMaxJ + lane] : 0.0f;
     __syncwarp();
 
     // ---- projected Gauss-Seidel.  dv lives in one register per lane.  Unit rows: the articulation blocks are swept
     //      concurrently (they do not couple), in Bullet's order inside a block; their impulses live in the lane of
-    //      their dof.  Dense rows (weld, contact normals, friction) follow in strict order; impulse of dense row d in
-    //      lane d.
+    //      their dof; the lane's column of M^-1 sits in registers.  Dense rows (weld, contact normals, friction)
+    //      follow in strict order; impulse of dense row d in lane d.
     float dv = 0.0f, lamM = 0.0f, lamL = 0.0f, lamD = 0.0f;
     const float thr = h->residual_thr;
     int iters = 0;
     for (int it = 0; it < h->solver_iters; ++it) {
         float resid = 0.0f;
-#pragma unroll 2
-        for (int t = 0; t < maxblk; ++t) {
-            const int i = bs + t < be ? bs + t : lane;           // idle lanes point at themselves with a null row
+#pragma unroll
+        for (int t = 0; t < MAXBLK; ++t) {
             const bool act = bs + t < be;
-            const float4 ra = s.um[i][0]; const float diag = s.um[i][1].x;
+            const int i = act ? bs + t : lane;                   // idle lanes point at themselves (mcol = 0: no effect)
+            const float4 ra = s.um[i];
             const float jdv = __shfl_sync(AVG_FULL, dv, i);
             const float lam = __shfl_sync(AVG_FULL, lamM, i);
-            const float wl = act ? s.Minv[i][lane] : 0.0f;
-            float delta = act ? (ra.x - jdv) * ra.y : 0.0f;
-            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
-            delta = act ? sum - lam : 0.0f;
-            if (lane == i && act) lamM = sum;
-            dv = fmaf(wl, delta, dv);
-            const float rv = delta * diag;
-            resid = fmaxf(resid, rv * rv);
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -ra.z), ra.z);
+            const float delta = sum - lam;
+            dv = fmaf(mcol[t], delta, dv);
+            if (lane == i && act) { lamM = sum; const float rv = delta * ra.w; resid = fmaxf(resid, rv * rv); }
         }
         if (nlim) {
-            for (int t = 0; t < maxblk; ++t) {
-                const int i = bs + t < be ? bs + t : lane;
+#pragma unroll
+            for (int t = 0; t < MAXBLK; ++t) {
                 const bool act = bs + t < be;
-                const float4 ra = s.ul[i][0]; const float4 rb = s.ul[i][1];
-                const float sg = rb.y;
+                const int i = act ? bs + t : lane;
+                const float4 ra = s.ul[i];
+                const float sg = ra.w;
                 const float jdv = sg * __shfl_sync(AVG_FULL, dv, i);
                 const float lam = __shfl_sync(AVG_FULL, lamL, i);
-                const float wl = act ? sg * s.Minv[i][lane] : 0.0f;
-                float delta = act ? (ra.x - jdv) * ra.y : 0.0f;
-                const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
-                delta = act ? sum - lam : 0.0f;
-                if (lane == i && act) lamL = sum;
-                dv = fmaf(wl, delta, dv);
-                const float rv = delta * rb.x;
-                resid = fmaxf(resid, rv * rv);
+                const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), 0.0f), 100.0f);
+                const float delta = sum - lam;
+                dv = fmaf(sg * mcol[t], delta, dv);
+                if (lane == i && act) { lamL = sum; const float rv = delta * ra.z; resid = fmaxf(resid, rv * rv); }
             }
         }
         resid = warp_max(resid);                                   // blocks ran in different lanes
@@ -1313,7 +1306,10 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         cudaError_t e1;
         if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_dynamics_kernel, sm_dyn)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_solve_kernel, sm_sol)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_solve_kernel<8>, sm_sol)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_solve_kernel<10>, sm_sol)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_solve_kernel<12>, sm_sol)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_solve_kernel<16>, sm_sol)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
@@ -1323,7 +1319,10 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
     for (int f = 0; f < substeps; ++f) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
         avg_dynamics_kernel<<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
-        avg_solve_kernel<<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+        if (a.maxblk <= 8) avg_solve_kernel<8><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+        else if (a.maxblk <= 10) avg_solve_kernel<10><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+        else if (a.maxblk <= 12) avg_solve_kernel<12><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+        else avg_solve_kernel<16><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
     }
     avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     return cudaGetLastError();

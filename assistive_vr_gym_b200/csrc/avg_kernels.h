@@ -44,6 +44,7 @@ struct AvgStepArgs {
     AvgContact* contacts;                              // [n_env][AVG_MAX_CONTACT] (may be null)
     int32_t* ncontacts;                                // [n_env]
     int n_env;
+    int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
 };
 
 int avg_kernels_per_step(int substeps);
