@@ -102,7 +102,7 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     if (mh->magic != AVG_MAGIC || mh->version != AVG_VERSION) return fail(h, -1, "avg_upload_model: bad magic/version");
     if (mh->total_bytes != nbytes) return fail(h, -1, "avg_upload_model: size mismatch");
     if (mh->n_body > AVG_MAX_BODY || mh->n_dof > AVG_MAX_DOF || mh->n_jdof > AVG_K_MAXJ || mh->n_mshape > AVG_K_MAXMS ||
-        mh->n_free > 2 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32)
+        mh->n_free > 2 || mh->n_shape - mh->n_mshape > 256 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32)
         return fail(h, -4, "avg_upload_model: model exceeds the warp-per-environment kernel limits");
     if (mh->task != AVG_TASK_SCRATCH_ITCH) return fail(h, -4, "avg_upload_model: only the ScratchItch epilogue is built (round 1)");
     const AvgBody* bodies = (const AvgBody*)((const char*)blob + mh->off_body);

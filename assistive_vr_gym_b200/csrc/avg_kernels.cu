@@ -80,6 +80,7 @@ struct __align__(16) SmCollide {
     float bp[32][3]; float bq[32][4];      // body poses
     float sp[kMaxMS][3]; float sR[kMaxMS][9]; float4 saabb[kMaxMS][2];
     uint32_t cand[kMaxCand];
+    uint8_t near_idx[256];                 // static shapes (index) that overlap the union box of the moving shapes
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
     int c_sa[kMaxC], c_sb[kMaxC];
 };
@@ -410,11 +411,45 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
     // may touch arrive in two coalesced 16-byte loads), moving-shape AABBs are broadcast from shared memory.
     int ncand = 0;
     const int nstat = h->n_shape - nms;
+    // (a) union box of the moving shapes (their thresholds included); static shapes outside it are dropped at once and
+    //     the survivors are compacted, so the pair loop below runs over ~1/3 of the static set
+    float ulo[3], uhi[3];
+    {
+        const bool v = lane < nms;
+        const float4 b0 = v ? s.saabb[lane][0] : make_float4(0, 0, 0, 0), b1 = v ? s.saabb[lane][1] : make_float4(0, 0, 0, 0);
+        const float c[3] = {b0.x, b0.y, b0.z}, hh[3] = {b0.w + b1.z, b1.x + b1.z, b1.y + b1.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float lo = v ? c[k] - hh[k] : 3.0e38f, hi = v ? c[k] + hh[k] : -3.0e38f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(AVG_FULL, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(AVG_FULL, hi, o)); }
+            ulo[k] = lo; uhi[k] = hi;
+        }
+    }
+    int nnear = 0;
     for (int base = 0; base < nstat; base += 32) {
         const int si = base + lane;
+        bool near = false;
+        if (si < nstat) {
+            const float4* rp = reinterpret_cast<const float4*>(&m.bps[si]);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            near = r0.x + r0.w >= ulo[0] && r0.x - r0.w <= uhi[0] && r0.y + r1.x >= ulo[1] && r0.y - r1.x <= uhi[1] &&
+                   r0.z + r1.y >= ulo[2] && r0.z - r1.y <= uhi[2];
+        }
+        const unsigned bal = __ballot_sync(AVG_FULL, near);
+        if (near) s.near_idx[nnear + __popc(bal & ((1u << lane) - 1))] = (uint8_t)si;
+        nnear += __popc(bal);
+    }
+    __syncwarp();
+    // (b) one lane per surviving static shape (AABB, threshold and the bit mask of moving shapes it may touch arrive in
+    //     two 16-byte loads); moving-shape AABBs are broadcast from shared memory
+    for (int base = 0; base < nnear; base += 32) {
+        const int k = base + lane;
+        int si = 0;
         float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 0, 0);
         uint32_t mask = 0;
-        if (si < nstat) {
+        if (k < nnear) {
+            si = s.near_idx[k];
             const float4* rp = reinterpret_cast<const float4*>(&m.bps[si]);
             r0 = __ldg(rp); r1 = __ldg(rp + 1);
             mask = __float_as_uint(r1.w);
