@@ -87,9 +87,7 @@ struct __align__(16) SmCollide {
 struct __align__(16) SmDyn {
     float env[AVG_ENV_STRIDE];
     float bp[32][3]; float bq[32][4];
-    float Minv[kMaxJ][kMaxJ + 1];
     float freeInv[2][12];
-    float Jrow[32];
     float tmp[32];
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC];
     int c_sa[kMaxC], c_sb[kMaxC];
@@ -581,30 +579,6 @@ __device__ __forceinline__ float jac_ang_lane(const KM& m, const LaneDyn& L, int
     return dot(L.S.a, n);
 }
 
-// W = M^-1 J^T for the dense row d whose Jacobian sits in s.Jrow; J and W are written to the scratch arena.
-// Returns J.W (diag) and J.qd (u0) reduced over the warp.
-template <class SM>
-__device__ __noinline__ void finish_dense_row(SM& s, float* __restrict__ gJ, float* __restrict__ gW, int lane, int nj, int nd, int d,
-                                              float qd, float& diag, float& u0) {
-    __syncwarp();
-    float w = 0.0f;
-    const float jl = s.Jrow[lane];
-    if (lane < nj) {
-        for (int j = 0; j < nj; ++j) w = fmaf(s.Minv[lane][j], s.Jrow[j], w);
-    } else if (lane < nd) {
-        int fb = 0, k = lane - nj;
-        while (k >= 6) { k -= 6; fb++; }
-        const int base = lane - k;
-        const float* fi = s.freeInv[fb];
-        if (k < 3) w = fi[0] * jl;
-        else { const int r = k - 3; w = fi[1 + 3 * r] * s.Jrow[base + 3] + fi[2 + 3 * r] * s.Jrow[base + 4] + fi[3 + 3 * r] * s.Jrow[base + 5]; }
-    }
-    gJ[d * 32 + lane] = jl; gW[d * 32 + lane] = w;
-    diag = warp_sum(jl * w);
-    u0 = warp_sum(jl * qd);
-    __syncwarp();
-}
-
 }  // namespace
 
 #define AVG_KERNEL_PREAMBLE(SMTYPE)                                                             \
@@ -700,6 +674,7 @@ avg_collide_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
+template <int MAXBLK>
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, 5)
 avg_dynamics_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmDyn)
@@ -826,50 +801,53 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
     Sv F = inertia_mul(Ic_sub, L.S);          // composite inertia times own motion subspace
     float Cb = dot(L.S, f_sub);               // generalized bias force of this lane's joint
-    // ---- joint-space mass matrix, M_ij = S_i . (Ic_j S_j) for i ancestor-or-self of j ----------------------------
-#pragma unroll 1
-    for (int j = 0; j < nj; ++j) {
-        Sv Fj = shflsv(F, j), Sj = shflsv(L.S, j);
-        uint32_t mj = __shfl_sync(AVG_FULL, L.anc, j);
-        if (lane < nj) {
-            float v = 0.0f;
-            if ((mj >> lane) & 1u) v = dot(L.S, Fj);
-            else if ((L.anc >> j) & 1u) v = dot(Sj, F);
-            s.Minv[lane][j] = v;
-        }
+    // ---- joint-space mass matrix in registers: lane c keeps column c of its articulation's diagonal block,
+    //      mc[t] = M[bs+t][c] = S_row . (Ic_deeper S_deeper) (symmetric), one block per articulation -----------------
+    int bs = lane, be = lane;
+    for (int b = 0; b < h->n_block; ++b) {
+        const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
+        if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
     }
-    __syncwarp();
-    // ---- in-place Gauss-Jordan inverse of the block-diagonal mass matrix (one block per articulation, SPD, no
-    //      pivoting).  Lane c owns column c; the blocks are swept concurrently; frozen dofs (M_kk ~ 0) invert to 0.
-    {
-        int bs = 0, be = 0, maxblk = 0;
-        for (int b = 0; b < h->n_block; ++b) {
-            const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
-            if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
-            maxblk = max(maxblk, b1 - b0);
-        }
-        for (int kk = 0; kk < maxblk; ++kk) {
-            const int k = bs + kk;
-            const bool act = k < be;
-            float ip = 0.0f, mkc = 0.0f;
-            if (act) { const float p = s.Minv[k][k]; ip = p > 1e-20f ? 1.0f / p : 0.0f; mkc = s.Minv[k][lane]; }
-            if (act && lane != k) {
-                const float f = mkc * ip;
-                for (int i = bs; i < be; ++i) if (i != k) s.Minv[i][lane] = fmaf(-s.Minv[i][k], f, s.Minv[i][lane]);
-            }
-            __syncwarp();
-            if (act) {
-                if (lane != k) { s.Minv[k][lane] = mkc * ip; s.Minv[lane][k] *= -ip; }
-                else s.Minv[k][k] = ip;
-            }
-            __syncwarp();
-        }
+    float mc[MAXBLK];
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) {
+        const bool valid = bs + t < be;
+        const int j = valid ? bs + t : lane;
+        const Sv Fj = shflsv(F, j), Sj = shflsv(L.S, j);
+        const uint32_t mj = __shfl_sync(AVG_FULL, L.anc, j);
+        float v = 0.0f;
+        if ((mj >> lane) & 1u) v = dot(L.S, Fj);            // this lane's joint is an ancestor-or-self of j
+        else if ((L.anc >> j) & 1u) v = dot(Sj, F);         // j is an ancestor of this lane's joint
+        mc[t] = valid ? v : 0.0f;
     }
+    // ---- in-place Gauss-Jordan inverse (SPD, no pivoting), all blocks swept concurrently; the pivot column comes from
+    //      the pivot's lane by shuffle; frozen dofs (M_kk ~ 0) invert to 0 -------------------------------------------
+#pragma unroll
+    for (int kk = 0; kk < MAXBLK; ++kk) {
+        const bool act = bs + kk < be;
+        const int k = act ? bs + kk : lane;
+        const float p = __shfl_sync(AVG_FULL, mc[kk], k);
+        const float ip = p > 1e-20f ? 1.0f / p : 0.0f;
+        const float mkc = mc[kk];
+        const float f = mkc * ip;
+#pragma unroll
+        for (int t = 0; t < MAXBLK; ++t) {
+            if (t == kk) continue;
+            const float mik = __shfl_sync(AVG_FULL, mc[t], k);
+            if (act) mc[t] = (lane != k) ? fmaf(-mik, f, mc[t]) : -mc[t] * ip;
+        }
+        if (act) mc[kk] = (lane != k) ? f : ip;
+    }
+    float mdiag = 0.0f;
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) if (bs + t == lane) mdiag = mc[t];
     // ---- unconstrained velocity update: qd* = qd + dt M^-1 (-C) ---------------------------------------------------
     float qdd = 0.0f;
-    for (int j = 0; j < nj; ++j) {
-        float cj = __shfl_sync(AVG_FULL, Cb, j);
-        if (lane < nj) qdd = fmaf(s.Minv[lane][j], -cj, qdd);
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) {
+        const int j = bs + t < be ? bs + t : lane;
+        const float cj = __shfl_sync(AVG_FULL, Cb, j);
+        qdd = fmaf(mc[t], -cj, qdd);
     }
     // free bodies (lane b computes, dof lanes pick up through smem scratch in s.obs)
     if (is_free) {
@@ -899,7 +877,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
         bool has_lim = false;
         if (lane < nj) {
             const AvgDof* D = &m.dof[lane];
-            const float diag = s.Minv[lane][lane];
+            const float diag = mdiag;
             const float inv = diag > 1e-12f ? 1.0f / diag : 0.0f;
             const float q = s.env[AVG_E_Q + m.body[D->body].qidx];
             if (D->flags & AVG_DOF_MOTOR) {        // btMultiBodyJointMotor: velocity target kp (q*-q)/dt - kd qd, clamp force*dt
@@ -921,88 +899,96 @@ avg_dynamics_kernel(AvgStepArgs a) {
         nlim = __popc(__ballot_sync(AVG_FULL, has_lim));
     }
     float4* g_rows = reinterpret_cast<float4*>(scr + AVG_S_ROWS_D);      // dense rows, indexed by dense row number
-    // tool weld, 6 dense rows
-    int ndense = 0;
+    // ---- dense rows in Bullet's order: tool weld (btMultiBodyFixedConstraint, 3 + 3 rows), contact normals, then one
+    //      friction row per contact.  One loop, so the M^-1 J^T code exists once. -------------------------------------
+    V3 wpa, wpb, perr, rotv;
     {
-        V3 pa, pb; Q4 qa, qb;
-        frame_pose(m, s, AVG_F_WELD_PARENT, pa, qa);
-        frame_pose(m, s, AVG_F_TOOL_BASE, pb, qb);
+        Q4 qa, qb;
+        frame_pose(m, s, AVG_F_WELD_PARENT, wpa, qa);
+        frame_pose(m, s, AVG_F_TOOL_BASE, wpb, qb);
         Q4 dq = qmul(qa, qconj(qb));
         if (dq.w < 0) dq = mkq(-dq.x, -dq.y, -dq.z, -dq.w);
-        float sn = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
-        V3 rotv = mk3(0, 0, 0);
-        if (sn > 1e-9f) { float ang = 2.0f * atan2f(sn, dq.w) / sn; rotv = mk3(dq.x * ang, dq.y * ang, dq.z * ang); }
-        V3 perr = pa - pb;
-        float maxi = h->weld_max_force * dt;
+        const float sn = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
+        rotv = mk3(0, 0, 0);
+        if (sn > 1e-9f) { const float ang = 2.0f * atan2f(sn, dq.w) / sn; rotv = mk3(dq.x * ang, dq.y * ang, dq.z * ang); }
+        perr = wpa - wpb;
+    }
+    const float maxi = h->weld_max_force * dt;
+    const int nc = ncontact;                   // kMaxDense = 6 + 2 * AVG_MAX_CONTACT always has room
+    const int first_contact_row = 6;
+    const int ndense = 6 + 2 * nc;
+    // free-body lanes: which free body, which component
+    int fbi = 0, fk = -1, fbase = lane;
+    if (lane >= nj && lane < nd) { fk = lane - nj; while (fk >= 6) { fk -= 6; fbi++; } fbase = lane - fk; }
 #pragma unroll 1
-        for (int ax = 0; ax < 6; ++ax) {
-            V3 e = mk3((ax % 3) == 0, (ax % 3) == 1, (ax % 3) == 2);
-            float jl, err;
-            if (ax < 3) {
-                jl = jac_point_lane(m, s, L, lane, nj, h->weld_body_a, pa, e, ref) - jac_point_lane(m, s, L, lane, nj, h->weld_body_b, pb, e, ref);
+    for (int d = 0; d < ndense; ++d) {
+        float jl, tgt, lo, hi, mu = 0.0f;
+        int par = -1;
+        if (d < 6) {
+            const V3 e = mk3((d % 3) == 0, (d % 3) == 1, (d % 3) == 2);
+            float err;
+            if (d < 3) {
+                jl = jac_point_lane(m, s, L, lane, nj, h->weld_body_a, wpa, e, ref) - jac_point_lane(m, s, L, lane, nj, h->weld_body_b, wpb, e, ref);
                 err = dot(perr, e);
             } else {
                 jl = jac_ang_lane(m, L, lane, nj, h->weld_body_a, e) - jac_ang_lane(m, L, lane, nj, h->weld_body_b, e);
                 err = dot(rotv, e);
             }
-            s.Jrow[lane] = jl;
-            float diag, u0;
-            finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
-            if (lane == 0) {
-                const int r = ndense;
-                g_rows[2 * r] = make_float4(-err * h->erp / dt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, -maxi, maxi); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
+            tgt = -err * h->erp / dt; lo = -maxi; hi = maxi;
+        } else if (d < 6 + nc) {
+            const int ci = d - 6;
+            const V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
+            const int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
+            jl = jac_point_lane(m, s, L, lane, nj, ba, pa, n, ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, n, ref);
+            const float dist = s.c_dist[ci];
+            tgt = dist > 0 ? -dist / dt : -dist * h->erp / dt;       // speculative margin / ERP push
+            lo = 0.0f; hi = 1e30f;
+        } else {
+            const int ci = d - 6 - nc;
+            const V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
+            const int sa = s.c_sa[ci], sb = s.c_sb[ci];
+            const int ba = m.shape[sa].body, bb = m.shape[sb].body;
+            const float jx = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(1, 0, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(1, 0, 0), ref);
+            const float jy = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 1, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 1, 0), ref);
+            const float jz = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 0, 1), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 0, 1), ref);
+            const V3 vrel = mk3(warp_sum(jx * qd), warp_sum(jy * qd), warp_sum(jz * qd));
+            const V3 lat = vrel - n * dot(vrel, n);
+            const float ll = norm(lat);
+            V3 t;
+            if (ll > 1e-6f) t = lat * (1.0f / ll);
+            else if (fabsf(n.z) > 0.70710678f) { const float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
+            else { const float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
+            jl = t.x * jx + t.y * jy + t.z * jz;
+            tgt = 0.0f; lo = 0.0f; hi = 0.0f; mu = m.shape[sa].friction * m.shape[sb].friction; par = first_contact_row + ci;
+        }
+        // W = M^-1 J^T: joint lanes use their register column of M^-1, free-body lanes the inverse mass / inertia
+        float w = 0.0f;
+#pragma unroll
+        for (int t = 0; t < MAXBLK; ++t) {
+            const int j = bs + t < be ? bs + t : lane;
+            w = fmaf(mc[t], __shfl_sync(AVG_FULL, jl, j), w);
+        }
+        {
+            const float j3 = __shfl_sync(AVG_FULL, jl, (fbase + 3) & 31), j4 = __shfl_sync(AVG_FULL, jl, (fbase + 4) & 31), j5 = __shfl_sync(AVG_FULL, jl, (fbase + 5) & 31);
+            if (fk >= 0) {
+                const float* fi = s.freeInv[fbi];
+                if (fk < 3) w = fi[0] * jl;
+                else { const int r = fk - 3; w = fi[1 + 3 * r] * j3 + fi[2 + 3 * r] * j4 + fi[3 + 3 * r] * j5; }
             }
-            ndense++;
         }
-    }
-    // contacts: normals first, then one friction row each (Bullet's row order)
-    const int nc = ncontact;                   // kMaxDense = 6 + 2 * AVG_MAX_CONTACT always has room
-    const int first_contact_row = ndense;
-#pragma unroll 1
-    for (int ci = 0; ci < nc; ++ci) {
-        V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
-        int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
-        float jl = jac_point_lane(m, s, L, lane, nj, ba, pa, n, ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, n, ref);
-        s.Jrow[lane] = jl;
-        float diag, u0;
-        finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
+        gJ[d * 32 + lane] = jl; gW[d * 32 + lane] = w;
+        const float diag = warp_sum(jl * w);
+        const float u0 = warp_sum(jl * qd);
         if (lane == 0) {
-            float dist = s.c_dist[ci];
-            const int r = ndense;
-            g_rows[2 * r] = make_float4((dist > 0 ? -dist / dt : -dist * h->erp / dt) - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 1e30f); g_rows[2 * r + 1] = make_float4(diag, 0.0f, __int_as_float((2 << 8) | ndense), __int_as_float(-1));
+            g_rows[2 * d] = make_float4(tgt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi);
+            g_rows[2 * d + 1] = make_float4(diag, mu, __int_as_float(d), __int_as_float(par));
         }
-        ndense++;
     }
-#pragma unroll 1
-    for (int ci = 0; ci < nc; ++ci) {
-        V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
-        int sa = s.c_sa[ci], sb = s.c_sb[ci];
-        int ba = m.shape[sa].body, bb = m.shape[sb].body;
-        float jx = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(1, 0, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(1, 0, 0), ref);
-        float jy = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 1, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 1, 0), ref);
-        float jz = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 0, 1), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 0, 1), ref);
-        V3 vrel = mk3(warp_sum(jx * qd), warp_sum(jy * qd), warp_sum(jz * qd));
-        V3 lat = vrel - n * dot(vrel, n);
-        float ll = norm(lat);
-        V3 t;
-        if (ll > 1e-6f) t = lat * (1.0f / ll);
-        else if (fabsf(n.z) > 0.70710678f) { float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
-        else { float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
-        s.Jrow[lane] = t.x * jx + t.y * jy + t.z * jz;
-        float diag, u0;
-        finish_dense_row(s, gJ, gW, lane, nj, nd, ndense, qd, diag, u0);
-        if (lane == 0) {
-            const int r = ndense;
-            g_rows[2 * r] = make_float4(-u0, diag > 1e-12f ? 1.0f / diag : 0.0f, 0.0f, 0.0f); g_rows[2 * r + 1] = make_float4(diag, m.shape[sa].friction * m.shape[sb].friction, __int_as_float((2 << 8) | ndense), __int_as_float(first_contact_row + ci));
-        }
-        ndense++;
-    }
-    __syncwarp();
-
 
     // ---- hand-off to the solver -----------------------------------------------------------------------------------
     if (lane < nd) scr[AVG_S_QD + lane] = qd;
-    for (int i = 0; i < nj; ++i) if (lane < nj) scr[AVG_S_MINV + i * kMaxJ + lane] = s.Minv[i][lane];
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) scr[AVG_S_MINV + t * 32 + lane] = mc[t];       // [t][lane]: row bs(lane)+t, column lane
     if (lane == 0) {
         scr_i[AVG_S_NR] = ndense; scr_i[AVG_S_NS] = nlim; scr_i[AVG_S_NFR] = first_contact_row + nc; scr_i[AVG_S_FCR] = first_contact_row;
         scr_i[AVG_S_NCS] = nc;
@@ -1042,7 +1028,7 @@ avg_solve_kernel(AvgStepArgs a) {
     }
     float mcol[MAXBLK];
 #pragma unroll
-    for (int t = 0; t < MAXBLK; ++t) mcol[t] = (bs + t < be) ? scr[AVG_S_MINV + (bs + t) * kMaxJ + lane] : 0.0f;
+    for (int t = 0; t < MAXBLK; ++t) mcol[t] = scr[AVG_S_MINV + t * 32 + lane];
     __syncwarp();
 
     // ---- projected Gauss-Seidel.  dv lives in one register per lane.  Unit rows: the articulation blocks are swept
@@ -1340,7 +1326,10 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
     if (!configured) {
         cudaError_t e1;
         if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_dynamics_kernel, sm_dyn)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_dynamics_kernel<8>, sm_dyn)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_dynamics_kernel<12>, sm_dyn)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_dynamics_kernel<16>, sm_dyn)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_solve_kernel<8>, sm_sol)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_solve_kernel<10>, sm_sol)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_solve_kernel<12>, sm_sol)) != cudaSuccess) return e1;
@@ -1353,7 +1342,10 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
     for (int f = 0; f < substeps; ++f) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
-        avg_dynamics_kernel<<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        else if (a.maxblk <= 12) avg_dynamics_kernel<12><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        else avg_dynamics_kernel<16><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         if (a.maxblk <= 8) avg_solve_kernel<8><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         else if (a.maxblk <= 10) avg_solve_kernel<10><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         else if (a.maxblk <= 12) avg_solve_kernel<12><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
