@@ -8,7 +8,7 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 5
+AVG_VERSION = 6
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -42,9 +42,35 @@ HEADER_DT = np.dtype([
     ("task_f", "<f4", 32),
     ("off_body", "<u4"), ("off_dof", "<u4"), ("off_shape", "<u4"), ("off_vert", "<u4"), ("off_plane", "<u4"),
     ("off_pair", "<u4"), ("off_frame", "<u4"), ("off_bps", "<u4"), ("off_bpm", "<u4"),
-    ("n_block", "<i4"), ("block_start", "<i4", 4), ("pad", "<u4", 1),
+    ("n_block", "<i4"), ("block_start", "<i4", 4), ("off_bcap", "<u4"),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
+
+
+def bounding_capsule(d) -> tuple:
+    """(p0, p1, r) in the shape frame: a capsule that contains the shape including its collision margin.  Used by the
+    device narrowphase as a cheap conservative cull before GJK (elongated robot links have fat AABBs)."""
+    from .mbody import SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_CYLINDER, SHAPE_HULL
+    z = np.zeros(3)
+    if d.kind == SHAPE_SPHERE:
+        return z, z, float(d.radius)
+    if d.kind in (SHAPE_CAPSULE, SHAPE_CYLINDER):
+        hl = float(d.half[2])
+        return np.array([0, 0, -hl]), np.array([0, 0, hl]), float(d.radius)
+    if d.kind == SHAPE_BOX:
+        k = int(np.argmax(d.half))
+        a = np.zeros(3); a[k] = d.half[k]
+        others = [d.half[i] for i in range(3) if i != k]
+        return -a, a, float(np.hypot(*others))
+    if d.kind == SHAPE_HULL:
+        v = np.asarray(d.verts, dtype=np.float64)
+        c = v.mean(0)
+        w, V = np.linalg.eigh(np.cov((v - c).T))
+        a = V[:, -1]
+        t = (v - c) @ a
+        perp = np.linalg.norm((v - c) - np.outer(t, a), axis=1)
+        return c + a * t.min(), c + a * t.max(), float(perp.max() + 0.001)
+    return z, z, 1e9                     # plane: never culled
 
 
 def _align(n: int, a: int = 16) -> int:
@@ -115,6 +141,14 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
         else:
             assert b > a
             bpm[a] |= np.uint32(1 << b)
+    # bounding capsules: shape frame for moving shapes, world frame for static ones
+    bcap = np.zeros((len(scene.shapes), 8), dtype="<f4")
+    for i, sh in enumerate(scene.shapes):
+        p0, p1, r = bounding_capsule(sh.desc)
+        if sh.body < 0:
+            R = X.quat_to_mat(sh.quat)
+            p0 = R @ p0 + sh.pos; p1 = R @ p1 + sh.pos
+        bcap[i, 0:3] = p0; bcap[i, 3] = r; bcap[i, 4:7] = p1
     # diagonal blocks of the mass matrix: consecutive joint dofs of one articulation
     starts = []
     last_art = None
@@ -141,7 +175,8 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     off = _align(HEADER_DT.itemsize)
     sections = []
     for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
-                      ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm)):
+                      ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm),
+                      ("off_bcap", bcap)):
         h[name] = off
         sections.append((off, arr.tobytes()))
         off = _align(off + arr.nbytes)

@@ -56,6 +56,7 @@ struct KM {                                // device view of a ModelBlob
     const AvgFrame* frame;
     const AvgBpStatic* bps;
     const uint32_t* bpm;
+    const float4* bcap;
 };
 
 __device__ __forceinline__ KM open_model(const unsigned char* blob) {
@@ -70,6 +71,7 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     m.frame = reinterpret_cast<const AvgFrame*>(blob + m.h->off_frame);
     m.bps = reinterpret_cast<const AvgBpStatic*>(blob + m.h->off_bps);
     m.bpm = reinterpret_cast<const uint32_t*>(blob + m.h->off_bpm);
+    m.bcap = reinterpret_cast<const float4*>(blob + m.h->off_bcap);
     return m;
 }
 
@@ -79,6 +81,7 @@ struct __align__(16) SmCollide {
     float q[32];                           // position coordinates of the env record
     float bp[32][3]; float bq[32][4];      // body poses
     float sp[kMaxMS][3]; float sR[kMaxMS][9]; float4 saabb[kMaxMS][2];
+    float4 scap[kMaxMS][2];                // bounding capsules of the moving shapes, world frame
     uint32_t cand[kMaxCand];
     uint8_t near_idx[256];                 // static shapes (index) that overlap the union box of the moving shapes
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
@@ -385,7 +388,7 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
 }
 
 template <class SM>
-__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow) {
+__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow, int& ncand_out) {
     const AvgModelHeader* h = m.h;
     const int nms = h->n_mshape;
     // world pose + AABB of the moving shapes
@@ -403,6 +406,9 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         s.saabb[lane][0] = make_float4(c.x, c.y, c.z, fabsf(R.m[0]) * lh.x + fabsf(R.m[1]) * lh.y + fabsf(R.m[2]) * lh.z);
         s.saabb[lane][1] = make_float4(fabsf(R.m[3]) * lh.x + fabsf(R.m[4]) * lh.y + fabsf(R.m[5]) * lh.z,
                                        fabsf(R.m[6]) * lh.x + fabsf(R.m[7]) * lh.y + fabsf(R.m[8]) * lh.z, S->thr, 0.0f);
+        const float4 c0 = __ldg(&m.bcap[2 * lane]), c1 = __ldg(&m.bcap[2 * lane + 1]);
+        const V3 w0 = p + mmul(R.m, mk3(c0.x, c0.y, c0.z)), w1 = p + mmul(R.m, mk3(c1.x, c1.y, c1.z));
+        s.scap[lane][0] = make_float4(w0.x, w0.y, w0.z, c0.w); s.scap[lane][1] = make_float4(w1.x, w1.y, w1.z, 0.0f);
     }
     __syncwarp();
     // broadphase.  Static shapes: one lane per static shape (its AABB, threshold and the bit mask of moving shapes it
@@ -489,6 +495,7 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         }
     }
     if (ncand > kMaxCand) { overflow |= 4; ncand = kMaxCand; }
+    ncand_out = ncand;
     __syncwarp();
     // canonical order = pair-table order: ascending (moving shape a, other shape b); rank by counting (lists are short)
     {
@@ -510,6 +517,57 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 2; ++t) if (lane + 32 * t < ncand) s.cand[rank[t]] = mine[t];
+        __syncwarp();
+    }
+    // bounding-capsule cull (conservative): segment-segment distance minus radii against the pair threshold.  Elongated
+    // links have fat AABBs; this removes most candidates before the much more expensive GJK.  Order is preserved.
+    {
+        uint32_t keep[2]; bool ok[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int ci = lane + 32 * t;
+            ok[t] = false; keep[t] = 0;
+            if (ci < ncand) {
+                const uint32_t pr = s.cand[ci];
+                const int a = pr & 0xffff, b = pr >> 16;
+                keep[t] = pr;
+                const float4 a0 = s.scap[a][0], a1 = s.scap[a][1];
+                float4 b0, b1;
+                if (b < nms) { b0 = s.scap[b][0]; b1 = s.scap[b][1]; }
+                else { b0 = __ldg(&m.bcap[2 * b]); b1 = __ldg(&m.bcap[2 * b + 1]); }
+                const float thr = fminf(__ldg(&m.shape[a].thr), __ldg(&m.shape[b].thr));
+                // closest distance between segments [a0,a1] and [b0,b1] (Ericson 5.1.9)
+                const V3 p1 = mk3(a0.x, a0.y, a0.z), p2 = mk3(b0.x, b0.y, b0.z);
+                const V3 d1 = mk3(a1.x, a1.y, a1.z) - p1, d2 = mk3(b1.x, b1.y, b1.z) - p2, r = p1 - p2;
+                const float aa = dot(d1, d1), ee = dot(d2, d2), ff = dot(d2, r);
+                float sc = 0.0f, tc = 0.0f;
+                if (aa <= 1e-12f && ee <= 1e-12f) { }
+                else if (aa <= 1e-12f) tc = fminf(fmaxf(ff / ee, 0.0f), 1.0f);
+                else {
+                    const float cc = dot(d1, r);
+                    if (ee <= 1e-12f) sc = fminf(fmaxf(-cc / aa, 0.0f), 1.0f);
+                    else {
+                        const float bb = dot(d1, d2), den = aa * ee - bb * bb;
+                        sc = den > 1e-12f ? fminf(fmaxf((bb * ff - cc * ee) / den, 0.0f), 1.0f) : 0.0f;
+                        tc = (bb * sc + ff) / ee;
+                        if (tc < 0.0f) { tc = 0.0f; sc = fminf(fmaxf(-cc / aa, 0.0f), 1.0f); }
+                        else if (tc > 1.0f) { tc = 1.0f; sc = fminf(fmaxf((bb - cc) / aa, 0.0f), 1.0f); }
+                    }
+                }
+                const V3 dd = (p1 + d1 * sc) - (p2 + d2 * tc);
+                const float lim = a0.w + b0.w + thr + 1e-5f;
+                ok[t] = dot(dd, dd) <= lim * lim;
+            }
+        }
+        __syncwarp();
+        int nk = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const unsigned bal = __ballot_sync(AVG_FULL, ok[t]);
+            if (ok[t]) s.cand[nk + __popc(bal & ((1u << lane) - 1))] = keep[t];
+            nk += __popc(bal);
+        }
+        ncand = nk;
         __syncwarp();
     }
     // narrowphase: one lane per candidate, results compacted in pair order
@@ -645,7 +703,7 @@ avg_prologue_kernel(AvgStepArgs a) {
     }
     if (lane == 0) {
         if (human_active) grec[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
-        scr_i[AVG_S_ITERS] = 0; scr_i[AVG_S_OVERFLOW] = 0;
+        scr_i[AVG_S_ITERS] = 0; scr_i[AVG_S_OVERFLOW] = 0; scr_i[AVG_S_NCAND] = 0;
     }
 }
 
@@ -658,8 +716,8 @@ avg_collide_kernel(AvgStepArgs a) {
     s.q[lane] = grec[AVG_E_Q + lane];
     __syncwarp();
     fk_warp(m, s, s.q, lane, h->n_body);
-    int nc = 0, overflow = 0;
-    collide_warp(m, s, lane, nc, overflow);
+    int nc = 0, overflow = 0, ncand = 0;
+    collide_warp(m, s, lane, nc, overflow, ncand);
     int* scr_i = reinterpret_cast<int*>(scr);
     if (lane < nc) {
         float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
@@ -668,7 +726,7 @@ avg_collide_kernel(AvgStepArgs a) {
         c[6] = s.c_n[lane][0]; c[7] = s.c_n[lane][1]; c[8] = s.c_n[lane][2];
         c[9] = s.c_dist[lane]; c[10] = __int_as_float(s.c_sa[lane]); c[11] = __int_as_float(s.c_sb[lane]); c[12] = 0.0f;
     }
-    if (lane == 0) { scr_i[AVG_S_NC] = nc; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
+    if (lane == 0) { scr_i[AVG_S_NC] = nc; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
 }
 
 // =================================================================================================================
@@ -1255,6 +1313,7 @@ avg_epilogue_kernel(AvgStepArgs a) {
         grec_i[AVG_E_ITERATION] = env_i[AVG_E_ITERATION] + 1;                               // env.py:351
         grec_i[AVG_E_OVERFLOW] = env_i[AVG_E_OVERFLOW] | scr_i[AVG_S_OVERFLOW];
         grec_i[AVG_E_SOLVER_ITERS] = scr_i[AVG_S_ITERS];
+        grec_i[AVG_E_NCAND] = scr_i[AVG_S_NCAND];
         a.reward[e] = reward;
         const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;
         a.info[2 * e] = total_force_on_human;

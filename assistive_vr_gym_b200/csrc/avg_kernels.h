@@ -19,8 +19,9 @@
 #define AVG_S_NCS 5           /* contacts that received rows                                 */
 #define AVG_S_OVERFLOW 6
 #define AVG_S_ITERS 7         /* solver iterations accumulated over the env-step            */
-#define AVG_S_QD 8            /* [32] velocities after the unconstrained update             */
-#define AVG_S_CONTACT 40      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
+#define AVG_S_NCAND 8         /* narrowphase candidates accumulated over the env-step (diagnostic) */
+#define AVG_S_QD 16           /* [32] velocities after the unconstrained update             */
+#define AVG_S_CONTACT 48      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
 #define AVG_S_CONTACT_STRIDE 14
 #define AVG_S_ROWS_M (AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * AVG_MAX_CONTACT)          /* [32][2] float4: motor row per dof */
 #define AVG_S_ROWS_L (AVG_S_ROWS_M + 8 * 32)                                             /* [32][2] float4: limit row per dof */

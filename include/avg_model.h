@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 5u
+#define AVG_VERSION 6u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -134,7 +134,7 @@ typedef struct AvgModelHeader {
     uint32_t off_bpm;             /* uint32[n_mshape]: bit b of entry a = moving pair (a, b), b > a, may collide */
     int32_t  n_block;             /* diagonal blocks of the joint-space mass matrix (one per articulation)     */
     int32_t  block_start[4];      /* first dof of each block; block_start[n_block] = n_jdof                    */
-    uint32_t pad[1];
+    uint32_t off_bcap;            /* float[n_shape][8]: bounding capsule p0(3), r, p1(3), 0 — shape frame (moving) or world (static) */
 } AvgModelHeader;
 
 /* task_f indices (config.ini + task files) */
@@ -171,7 +171,8 @@ enum {
     AVG_E_EPISODE_RETURN = 165,
     AVG_E_OVERFLOW = 166,   /* int: bit0 contact overflow, bit1 row overflow (never silently dropped)          */
     AVG_E_SOLVER_ITERS = 167, /* int: PGS iterations executed in the last env-step (diagnostic) */
-    AVG_E_LAST = 168
+    AVG_E_NCAND = 168,       /* int: narrowphase candidate pairs examined in the last env-step (diagnostic) */
+    AVG_E_LAST = 169
 };
 
 /* one reported contact point (parity / debug), 16 floats */

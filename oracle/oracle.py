@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libavg_oracle.so")
 ENV_STRIDE = 192
-INT_SLOTS = (123, 152, 161, 166, 167)    # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
+INT_SLOTS = (123, 152, 161, 166, 167, 168)    # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
 _DP = ctypes.POINTER(ctypes.c_double)
 _FP = ctypes.POINTER(ctypes.c_float)
 _IP = ctypes.POINTER(ctypes.c_int)
