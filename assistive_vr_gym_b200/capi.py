@@ -17,7 +17,7 @@ EXPORTS = [
     "avg_create", "avg_destroy", "avg_last_error", "avg_upload_model", "avg_set_state", "avg_get_state",
     "avg_state_device_ptr", "avg_reset_obs", "avg_step", "avg_step_host", "avg_enable_debug", "avg_get_contacts",
     "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
-    "avg_bytes_per_env_step",
+    "avg_bytes_per_env_step", "avg_arm_limit_logits",
 ]
 
 CONTACT_DT = np.dtype([("shape_a", "<i4"), ("shape_b", "<i4"), ("pos_a", "<f4", 3), ("pos_b", "<f4", 3),
@@ -57,6 +57,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_enable_debug.argtypes = [vp, ctypes.c_int]
     lib.avg_get_contacts.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.avg_get_reward_terms.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_arm_limit_logits.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
     for f in ("avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_bytes_per_env_step"):
         getattr(lib, f).argtypes = [vp]
     lib.avg_env_stride.argtypes = []
@@ -132,6 +133,9 @@ class Sim:
         t = np.zeros((count, 8), dtype=np.float32)
         self._check(self.lib.avg_get_reward_terms(self.h, begin, count, t.ctypes.data), "avg_get_reward_terms")
         return t
+
+    def arm_limit_logits(self, variant: int, q4_ptr: int, out_ptr: int, n: int, stream: int = 0):
+        self._check(self.lib.avg_arm_limit_logits(self.h, variant, q4_ptr, out_ptr, n, stream), "avg_arm_limit_logits")
 
     @property
     def n_actions(self) -> int:

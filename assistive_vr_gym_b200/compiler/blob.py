@@ -8,7 +8,7 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 6
+AVG_VERSION = 7
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -43,6 +43,7 @@ HEADER_DT = np.dtype([
     ("off_body", "<u4"), ("off_dof", "<u4"), ("off_shape", "<u4"), ("off_vert", "<u4"), ("off_plane", "<u4"),
     ("off_pair", "<u4"), ("off_frame", "<u4"), ("off_bps", "<u4"), ("off_bpm", "<u4"),
     ("n_block", "<i4"), ("block_start", "<i4", 4), ("off_bcap", "<u4"),
+    ("off_mlp", "<u4"), ("n_mlp", "<i4"), ("mlp_dof", "<i4", 4), ("pad2", "<u4", 2),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
 
@@ -161,6 +162,19 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     assert n_block <= 3
     starts = starts + [int(scene.header["n_jdof"])] * (4 - n_block)
 
+    # arm-limit classifier weights (human-active ids only)
+    mlp = np.zeros(0, dtype="<f4")
+    mlp_dof = [-1, -1, -1, -1]
+    if getattr(scene, "mlp_layers", None):
+        parts = []
+        for k, bb in scene.mlp_layers:
+            parts += [np.asarray(k, dtype="<f4").ravel(), np.asarray(bb, dtype="<f4").ravel()]
+        mlp = np.concatenate(parts)
+        assert mlp.size == 8705
+        for b in scene.bodies:
+            if b.art == 1 and b.ref_joint in (7, 8, 9, 10):
+                mlp_dof[b.ref_joint - 7] = b.dof
+
     hdr = np.zeros(1, dtype=HEADER_DT)
     h = hdr[0]
     h["magic"] = AVG_MAGIC; h["version"] = AVG_VERSION
@@ -172,11 +186,12 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     h["n_shape"] = len(shapes); h["n_mshape"] = scene.n_mshape; h["n_vert"] = len(verts); h["n_plane"] = len(planes)
     h["n_pair"] = len(pairs); h["n_frame"] = len(frames)
     h["n_block"] = n_block; h["block_start"] = starts
+    h["n_mlp"] = mlp.size; h["mlp_dof"] = mlp_dof
     off = _align(HEADER_DT.itemsize)
     sections = []
     for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
                       ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm),
-                      ("off_bcap", bcap)):
+                      ("off_bcap", bcap), ("off_mlp", mlp)):
         h[name] = off
         sections.append((off, arr.tobytes()))
         off = _align(off + arr.nbytes)
@@ -201,4 +216,5 @@ def read_blob(blob: bytes) -> dict:
     out["frames"] = np.frombuffer(blob, dtype=FRAME_DT, count=int(h["n_frame"]), offset=int(h["off_frame"]))
     out["bps"] = np.frombuffer(blob, dtype=BPS_DT, count=int(h["n_shape"] - h["n_mshape"]), offset=int(h["off_bps"]))
     out["bpm"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_mshape"]), offset=int(h["off_bpm"]))
+    out["mlp"] = np.frombuffer(blob, dtype="<f4", count=int(h["n_mlp"]), offset=int(h["off_mlp"]))
     return out

@@ -317,6 +317,10 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
                           frames=frames, dofs=dofs, header=header, robot_arm_joints=robot_arm,
                           human_joints=list(range(7, 14)), q_human_reset=q_human,
                           tool_offset=(tool_pos_offset, tool_orient_offset))
+    scene.mlp_layers = None
+    if human_control:      # env.py:67: realistic_arm_limits_model.h5, used by enforce_realistic_human_joint_limits (env.py:353-387)
+        from .h5lite import load_keras_dense_stack
+        scene.mlp_layers = load_keras_dense_stack(os.path.join(assets_dir, 'realistic_arm_limits_model.h5'))
     scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape)
     if verbose:
         print(scene.info)

@@ -256,6 +256,17 @@ int avg_get_reward_terms(AvgHandle* h, int env_begin, int env_count, float* term
     return 0;
 }
 
+int avg_arm_limit_logits(AvgHandle* h, int variant, const float* q4, float* logits, int n, void* stream) {
+    if (!h || !q4 || !logits || n < 0) return -1;
+    if (variant < 0 || variant >= AVG_K_MAX_VARIANTS || !h->have[variant]) return fail(h, -1, "avg_arm_limit_logits: variant without an uploaded model");
+    if (h->hdr[variant].n_mlp <= 0) return fail(h, -4, "avg_arm_limit_logits: this model carries no arm-limit classifier (human-active ids only)");
+    cudaSetDevice(h->device);
+    if (n == 0) return 0;
+    AVG_CHECK(h, avg_launch_arm_limit(h->d_model[variant], q4, logits, n, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
 int avg_num_envs(const AvgHandle* h) { return h ? h->n_env : 0; }
 int avg_num_actions(const AvgHandle* h) { return h ? h->n_act : 0; }
 int avg_num_obs(const AvgHandle* h) { return h ? h->n_obs : 0; }

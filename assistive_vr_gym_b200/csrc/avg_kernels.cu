@@ -57,6 +57,7 @@ struct KM {                                // device view of a ModelBlob
     const AvgBpStatic* bps;
     const uint32_t* bpm;
     const float4* bcap;
+    const float* mlp;
 };
 
 __device__ __forceinline__ KM open_model(const unsigned char* blob) {
@@ -72,6 +73,7 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     m.bps = reinterpret_cast<const AvgBpStatic*>(blob + m.h->off_bps);
     m.bpm = reinterpret_cast<const uint32_t*>(blob + m.h->off_bpm);
     m.bcap = reinterpret_cast<const float4*>(blob + m.h->off_bcap);
+    m.mlp = m.h->n_mlp > 0 ? reinterpret_cast<const float*>(blob + m.h->off_mlp) : nullptr;
     return m;
 }
 
@@ -1054,6 +1056,38 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
 }
 
+// enforce_realistic_human_joint_limits, env.py:353-371: Dense 4 -> 64 tanh -> 64 tanh -> 64 tanh -> 1; lane u evaluates
+// hidden units u and u + 32, activations are exchanged by shuffles, weight rows are read coalesced (L1-resident).
+// Returns the logit (class 1 <=> logit > 0), identical in every lane.
+__device__ __forceinline__ void arm_limit_inputs(float tz, float tx, float ty, float qe, float x[4]) {
+    const float twopi = 6.28318530717958647692f;                                 // env.py:360-363 (Python % semantics)
+    x[0] = fmodf(-tz + twopi, twopi); if (x[0] < 0) x[0] += twopi;
+    x[1] = fmodf(tx + twopi, twopi); if (x[1] < 0) x[1] += twopi;
+    x[2] = -ty;
+    x[3] = fmodf(-qe + twopi, twopi); if (x[3] < 0) x[3] += twopi;
+}
+__device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, const float x[4], int lane) {
+    const float* W1 = w; const float* b1 = W1 + 256; const float* W2 = b1 + 64; const float* b2 = W2 + 4096;
+    const float* W3 = b2 + 64; const float* b3 = W3 + 4096; const float* W4 = b3 + 64; const float* b4 = W4 + 64;
+    float a0 = __ldg(b1 + lane), a1 = __ldg(b1 + lane + 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a0 = fmaf(x[k], __ldg(W1 + k * 64 + lane), a0); a1 = fmaf(x[k], __ldg(W1 + k * 64 + lane + 32), a1); }
+    float h0 = tanhf(a0), h1 = tanhf(a1);
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+        const float* W = layer == 0 ? W2 : W3; const float* bb = layer == 0 ? b2 : b3;
+        a0 = __ldg(bb + lane); a1 = __ldg(bb + lane + 32);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const float u = __shfl_sync(AVG_FULL, h0, j), v = __shfl_sync(AVG_FULL, h1, j);
+            a0 = fmaf(u, __ldg(W + j * 64 + lane), a0); a1 = fmaf(u, __ldg(W + j * 64 + lane + 32), a1);
+            a0 = fmaf(v, __ldg(W + (j + 32) * 64 + lane), a0); a1 = fmaf(v, __ldg(W + (j + 32) * 64 + lane + 32), a1);
+        }
+        h0 = tanhf(a0); h1 = tanhf(a1);
+    }
+    return warp_sum(h0 * __ldg(W4 + lane) + h1 * __ldg(W4 + lane + 32)) + __ldg(b4);
+}
+
 // =================================================================================================================
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
@@ -1165,22 +1199,37 @@ avg_solve_kernel(AvgStepArgs a) {
         scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * (lane - first_contact_row) + 12] = lamD;
     if (lane == 0) scr_i[AVG_S_ITERS] += iters;
 
-    // ---- integrate (semi-implicit Euler) + enforce_hard_human_joint_limits (env.py:389-410) -----------------------
+    // ---- integrate (semi-implicit Euler), enforce_realistic_human_joint_limits (env.py:353-371, human-active ids),
+    //      enforce_hard_human_joint_limits (env.py:389-410) -----------------------------------------------------------
     float v = qd + dv;
     if (lane < nj) v = fminf(fmaxf(v, -h->max_vel), h->max_vel);
-    if (lane < nb) {
-        const AvgBody* B = &m.body[lane];
-        if (B->jtype != AVG_JOINT_FREE) {
-            float qn = grec[AVG_E_Q + B->qidx] + dt * v;
-            const AvgDof* D = &m.dof[lane];
-            if (D->flags & AVG_DOF_HARD_LIMIT) {
-                const float sc = grec[AVG_E_LIMIT_SCALE];
-                const float lo = D->lower * sc, hi = D->upper * sc;
-                if (qn < lo) { qn = lo; v = 0.0f; }
-                else if (qn > hi) { qn = hi; v = 0.0f; }
-            }
-            grec[AVG_E_Q + B->qidx] = qn;
+    const bool is_jlane = lane < nb && m.body[lane].jtype != AVG_JOINT_FREE;
+    float qn = 0.0f;
+    if (is_jlane) qn = grec[AVG_E_Q + m.body[lane].qidx] + dt * v;
+    if (h->human_control && m.mlp && h->mlp_dof[0] >= 0) {
+        float q4[4], x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q4[k] = __shfl_sync(AVG_FULL, qn, h->mlp_dof[k]);
+        arm_limit_inputs(q4[0], q4[1], q4[2], q4[3], x);
+        const float logit = arm_limit_logit_warp(m.mlp, x, lane);
+        int* grec_i = reinterpret_cast<int*>(grec);
+        if (logit > 0.0f) {
+            if (lane < 4) grec[AVG_E_VALID_POSE + lane] = q4[0] * (lane == 0) + q4[1] * (lane == 1) + q4[2] * (lane == 2) + q4[3] * (lane == 3);
+            if (lane == 0) grec_i[AVG_E_HAS_VALID] = 1;
+        } else if (grec_i[AVG_E_HAS_VALID] != 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (lane == h->mlp_dof[k]) { qn = grec[AVG_E_VALID_POSE + k]; v = 0.0f; }
         }
+    }
+    if (is_jlane) {
+        const AvgDof* D = &m.dof[lane];
+        if (D->flags & AVG_DOF_HARD_LIMIT) {
+            const float sc = grec[AVG_E_LIMIT_SCALE];
+            const float lo = D->lower * sc, hi = D->upper * sc;
+            if (qn < lo) { qn = lo; v = 0.0f; }
+            else if (qn > hi) { qn = hi; v = 0.0f; }
+        }
+        grec[AVG_E_Q + m.body[lane].qidx] = qn;
     }
     if (lane < nd) grec[AVG_E_QD + lane] = v;
     // free bodies: the body's lane gathers its six velocity components from the dof lanes
@@ -1364,6 +1413,19 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
 }
 
+// parity tap for the arm-limit classifier: raw joint angles (tz, tx, ty, qe) of joints 7..10 -> logit, one warp per pose
+__global__ void __launch_bounds__(128)
+avg_arm_limit_kernel(const unsigned char* blob, const float* __restrict__ q4, float* __restrict__ logits, int n) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const KM m = open_model(blob);
+    if (!m.mlp) { if (lane == 0) logits[i] = 0.0f; return; }
+    float x[4];
+    arm_limit_inputs(q4[4 * i], q4[4 * i + 1], q4[4 * i + 2], q4[4 * i + 3], x);
+    const float lg = arm_limit_logit_warp(m.mlp, x, lane);
+    if (lane == 0) logits[i] = lg;
+}
+
 // =================================================================================================================
 // host-side launch helpers
 // =================================================================================================================
@@ -1411,6 +1473,11 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         else avg_solve_kernel<16><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
     }
     avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream) {
+    avg_arm_limit_kernel<<<(n + 3) / 4, 128, 0, stream>>>(blob, q4, logits, n);
     return cudaGetLastError();
 }
 

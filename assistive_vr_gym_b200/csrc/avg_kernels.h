@@ -51,3 +51,4 @@ struct AvgStepArgs {
 int avg_kernels_per_step(int substeps);
 cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
+cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);

@@ -68,6 +68,12 @@ int avg_get_contacts(AvgHandle* h, int env_begin, int env_count, void* contacts,
  * reward_distance, reward_action, reward_force_scratch, preferences_score. */
 int avg_get_reward_terms(AvgHandle* h, int env_begin, int env_count, float* terms);
 
+/* Parity tap for enforce_realistic_human_joint_limits (env.py:353-371), which the step applies after every sub-step
+ * of the human-active ids: replaces human_limits_model.predict_classes (env.py:364).  q4: DEVICE [n][4] raw joint
+ * angles (tz, tx, ty, qe) of human joints 7..10; logits: DEVICE [n], class 1 (valid pose) <=> logit > 0.
+ * Asynchronous on `stream`. */
+int avg_arm_limit_logits(AvgHandle* h, int variant, const float* q4, float* logits, int n, void* stream);
+
 /* Shape queries. */
 int avg_num_envs(const AvgHandle* h);
 int avg_num_actions(const AvgHandle* h);

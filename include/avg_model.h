@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 6u
+#define AVG_VERSION 7u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -135,6 +135,10 @@ typedef struct AvgModelHeader {
     int32_t  n_block;             /* diagonal blocks of the joint-space mass matrix (one per articulation)     */
     int32_t  block_start[4];      /* first dof of each block; block_start[n_block] = n_jdof                    */
     uint32_t off_bcap;            /* float[n_shape][8]: bounding capsule p0(3), r, p1(3), 0 — shape frame (moving) or world (static) */
+    uint32_t off_mlp;             /* arm-limit classifier (env.py:353-387): W1[4][64] b1[64] W2[64][64] b2 W3[64][64] b3 W4[64] b4   */
+    int32_t  n_mlp;               /* 8705 floats when present (human-active ids), else 0                                        */
+    int32_t  mlp_dof[4];          /* velocity dofs of human joints 7, 8, 9, 10 (tz, tx, ty, qe)                                  */
+    uint32_t pad2[2];
 } AvgModelHeader;
 
 /* task_f indices (config.ini + task files) */

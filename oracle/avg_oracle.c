@@ -6,6 +6,7 @@
  * (SURVEY.md §4, §8c).  What is restated below therefore has two kinds of source:
  *   (1) code that IS in the reference tree and is followed line by line (cited per function):
  *       AssistiveEnv.take_step            env.py:274-351
+ *       enforce_realistic_human_joint_limits env.py:353-387 (right arm; the left-arm block never fires in sim ids)
  *       enforce_hard_human_joint_limits   env.py:389-410
  *       human_preferences                 env.py:412-448
  *       ScratchItchEnv.step/reward        scratch_itch.py:30-82
@@ -89,6 +90,7 @@ typedef struct {
     const float* plane;
     const uint32_t* pair;
     const AvgFrame* frame;
+    const float* mlp;
 } Model;
 
 static int model_open(const void* blob, Model* m) {
@@ -104,6 +106,7 @@ static int model_open(const void* blob, Model* m) {
     m->plane = (const float*)(b + h->off_plane);
     m->pair = (const uint32_t*)(b + h->off_pair);
     m->frame = (const AvgFrame*)(b + h->off_frame);
+    m->mlp = h->n_mlp > 0 ? (const float*)(b + h->off_mlp) : 0;
     return 0;
 }
 
@@ -799,6 +802,38 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
     free(rows); free(d);
 }
 
+/* env.py:353-371: Keras Sequential Dense 4 -> 64 tanh -> 64 tanh -> 64 tanh -> 1 sigmoid on the remapped right-arm
+ * angles; class 1 (sigmoid > 0.5 <=> logit > 0) remembers the pose, class 0 restores the last valid pose with zero
+ * velocity.  Weights come from realistic_arm_limits_model.h5 via the model compiler. */
+static double pymod(double a, double m) { double r = fmod(a, m); if (r < 0) r += m; return r; }
+static double arm_limit_logit(const float* w, const double x[4]) {
+    const float* W1 = w; const float* b1 = W1 + 256; const float* W2 = b1 + 64; const float* b2 = W2 + 4096;
+    const float* W3 = b2 + 64; const float* b3 = W3 + 4096; const float* W4 = b3 + 64; const float* b4 = W4 + 64;
+    double h1[64], h2[64], h3[64];
+    for (int u = 0; u < 64; ++u) { double a = b1[u]; for (int k = 0; k < 4; ++k) a += x[k] * W1[k * 64 + u]; h1[u] = tanh(a); }
+    for (int u = 0; u < 64; ++u) { double a = b2[u]; for (int k = 0; k < 64; ++k) a += h1[k] * W2[k * 64 + u]; h2[u] = tanh(a); }
+    for (int u = 0; u < 64; ++u) { double a = b3[u]; for (int k = 0; k < 64; ++k) a += h2[k] * W3[k * 64 + u]; h3[u] = tanh(a); }
+    double a = b4[0]; for (int k = 0; k < 64; ++k) a += h3[k] * W4[k];
+    return a;
+}
+static void enforce_realistic_limits(const Model* m, double* env) {
+    const AvgModelHeader* h = m->h;
+    if (!m->mlp || !h->human_control) return;
+    double q[4];
+    for (int k = 0; k < 4; ++k) { if (h->mlp_dof[k] < 0) return; q[k] = env[AVG_E_Q + m->body[m->dof[h->mlp_dof[k]].body].qidx]; }
+    const double twopi = 2.0 * 3.14159265358979323846;
+    double x[4] = {pymod(-q[0] + twopi, twopi), pymod(q[1] + twopi, twopi), -q[2], pymod(-q[3] + twopi, twopi)};   /* env.py:360-363 */
+    if (arm_limit_logit(m->mlp, x) > 0.0) {
+        for (int k = 0; k < 4; ++k) env[AVG_E_VALID_POSE + k] = q[k];
+        env[AVG_E_HAS_VALID] = 1;
+    } else if (env[AVG_E_HAS_VALID] != 0) {
+        for (int k = 0; k < 4; ++k) {
+            env[AVG_E_Q + m->body[m->dof[h->mlp_dof[k]].body].qidx] = env[AVG_E_VALID_POSE + k];
+            env[AVG_E_QD + h->mlp_dof[k]] = 0;
+        }
+    }
+}
+
 /* env.py:389-410 */
 static void enforce_hard_limits(const Model* m, double* env) {
     for (int i = 0; i < m->h->n_jdof; ++i) {
@@ -941,7 +976,7 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
     Contact contacts[MAXC]; int nc = 0;
     for (int f = 0; f < h->substeps; ++f) {                    /* env.py:341-349 */
         substep(&m, env, contacts, &nc);
-        /* enforce_realistic_human_joint_limits (env.py:353-387) is compiled in with the human-active variant */
+        enforce_realistic_limits(&m, env);                     /* env.py:343-344, human_control only */
         enforce_hard_limits(&m, env);
         update_target(&m, env);
     }
@@ -1058,6 +1093,15 @@ int avg_oracle_collide(const void* blob, const double* env, double* contacts_out
         o[11] = contacts[c].dist; o[12] = 0;
     }
     return overflow;
+}
+/* arm-limit classifier logit for raw joint angles (tz, tx, ty, qe) */
+int avg_oracle_arm_limit(const void* blob, const double* q, double* logit) {
+    Model m; if (model_open(blob, &m)) return -1;
+    if (!m.mlp) return -2;
+    const double twopi = 2.0 * 3.14159265358979323846;
+    double x[4] = {pymod(-q[0] + twopi, twopi), pymod(q[1] + twopi, twopi), -q[2], pymod(-q[3] + twopi, twopi)};
+    *logit = arm_limit_logit(m.mlp, x);
+    return 0;
 }
 /* closest points between two shapes given explicit world poses (GJK unit tests): pose = pos(3)+quat(4) */
 int avg_oracle_shape_pair(const void* blob, int sa, const double* pose_a, int sb, const double* pose_b, double thr, double* out) {

@@ -65,6 +65,7 @@ class Oracle:
         L.avg_oracle_collide.argtypes = [ctypes.c_void_p, _DP, _DP, _IP]
         L.avg_oracle_shape_pair.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP, ctypes.c_int, _DP, ctypes.c_double, _DP]
         L.avg_oracle_sizes.argtypes = [_IP]
+        L.avg_oracle_arm_limit.argtypes = [ctypes.c_void_p, _DP, _DP]
 
     def sizes(self):
         a = (ctypes.c_int * 8)()
@@ -115,6 +116,12 @@ class Oracle:
         nc = ctypes.c_int(0)
         self.lib.avg_oracle_collide(self.blob, self._dp(env), self._dp(cont), ctypes.byref(nc))
         return cont[:nc.value].copy()
+
+    def arm_limit_logit(self, q4):
+        q = np.ascontiguousarray(q4, dtype=np.float64); out = np.zeros(1)
+        rc = self.lib.avg_oracle_arm_limit(self.blob, self._dp(q), self._dp(out))
+        assert rc == 0, rc
+        return float(out[0])
 
     def shape_pair(self, sa, pose_a, sb, pose_b, thr=1e9):
         out = np.zeros(10)
