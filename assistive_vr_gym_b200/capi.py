@@ -11,13 +11,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavg_b200.so")
+LIB_PATH = os.environ.get("AVG_B200_LIB") or os.path.join(_HERE, "libavg_b200.so")   # override: A/B builds during tuning
 
 EXPORTS = [
     "avg_create", "avg_destroy", "avg_last_error", "avg_upload_model", "avg_set_state", "avg_get_state",
     "avg_state_device_ptr", "avg_reset_obs", "avg_step", "avg_step_host", "avg_enable_debug", "avg_get_contacts",
     "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
-    "avg_bytes_per_env_step", "avg_arm_limit_logits",
+    "avg_bytes_per_env_step", "avg_arm_limit_logits", "avg_alloc_host", "avg_free_host",
 ]
 
 CONTACT_DT = np.dtype([("shape_a", "<i4"), ("shape_b", "<i4"), ("pos_a", "<f4", 3), ("pos_b", "<f4", 3),
@@ -57,6 +57,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_enable_debug.argtypes = [vp, ctypes.c_int]
     lib.avg_get_contacts.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.avg_get_reward_terms.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.avg_free_host.argtypes = [vp]
     lib.avg_arm_limit_logits.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
     for f in ("avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_bytes_per_env_step"):
         getattr(lib, f).argtypes = [vp]
@@ -64,6 +66,29 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_launch_count.argtypes = [vp]; lib.avg_launch_count.restype = ctypes.c_longlong
     _lib = lib
     return lib
+
+
+class PinnedArray:
+    """NumPy view of page-locked host memory from avg_alloc_host (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        self.ptr = ctypes.c_void_p()
+        if self.lib.avg_alloc_host(max(nbytes, 1), ctypes.byref(self.ptr)) != 0:
+            raise AvgError("avg_alloc_host failed")
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        self.array[...] = 0
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self.lib.avg_free_host(self.ptr); self.ptr = None
+        except Exception:
+            pass
 
 
 class Sim:

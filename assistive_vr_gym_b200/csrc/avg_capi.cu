@@ -3,6 +3,7 @@
 // launches a CUDA kernel or fails with an error code.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include "../../include/avg_b200.h"
@@ -33,6 +34,7 @@ struct AvgHandle {
     uint8_t* d_done = nullptr;
     cudaStream_t stream = nullptr;
     long long launches = 0;
+    unsigned long long* d_hist = nullptr;              // AVG_DBG & 32 (development aid)
     std::string err;
 };
 
@@ -85,6 +87,21 @@ int avg_destroy(AvgHandle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->d_hist) {
+        static unsigned long long hh[3 * 32 * 256];
+        cudaMemcpy(hh, h->d_hist, sizeof(hh), cudaMemcpyDeviceToHost);
+        unsigned long long tot[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < 32 * 256; ++i) tot[k] += hh[k * 8192 + i];
+        fprintf(stderr, "[avg narrowphase histogram] candidates %llu, GJK calls %llu, GJK iterations %llu\n", tot[0], tot[1], tot[2]);
+        for (int r = 0; r < 25; ++r) {
+            int best = -1; unsigned long long bv = 0;
+            for (int i = 0; i < 8192; ++i) if (hh[2 * 8192 + i] + hh[i] > bv) { bv = hh[2 * 8192 + i] + hh[i]; best = i; }
+            if (best < 0) break;
+            fprintf(stderr, "  pair (%d, %d): candidates %llu, GJK calls %llu, iterations %llu\n", best >> 8, best & 255, hh[best], hh[8192 + best], hh[2 * 8192 + best]);
+            hh[best] = 0; hh[2 * 8192 + best] = 0;
+        }
+        cudaFree(h->d_hist);
+    }
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
@@ -136,6 +153,8 @@ int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_r
     cudaSetDevice(h->device);
     AVG_CHECK(h, cudaMemcpy(h->d_env + (size_t)env_begin * AVG_ENV_STRIDE, env_records,
                             sizeof(float) * AVG_ENV_STRIDE * (size_t)env_count, cudaMemcpyHostToDevice));
+    /* a new state starts with an empty separating-axis cache (and clean hand-off slots) */
+    AVG_CHECK(h, cudaMemset(h->d_scratch + (size_t)env_begin * AVG_S_STRIDE, 0, sizeof(float) * AVG_S_STRIDE * (size_t)env_count));
     if (variants) {
         for (int i = 0; i < env_count; ++i)
             if (variants[i] < 0 || variants[i] >= AVG_K_MAX_VARIANTS || !h->have[variants[i]])
@@ -161,6 +180,12 @@ static int fill_args(AvgHandle* h, AvgStepArgs& a) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
+    { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
+    if ((a.dbg & 32) && !h->d_hist) {
+        cudaMalloc(&h->d_hist, sizeof(unsigned long long) * 3 * 32 * 256);
+        cudaMemset(h->d_hist, 0, sizeof(unsigned long long) * 3 * 32 * 256);
+    }
+    a.dbg_hist = h->d_hist;
     a.contacts = h->debug ? h->d_contacts : nullptr;
     a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
     a.terms = h->debug ? h->d_terms : nullptr;
@@ -189,35 +214,60 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     return 0;
 }
 
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int avg_alloc_host(size_t nbytes, void** out) {
+    if (!out) return -1;
+    return cudaMallocHost(out, nbytes) == cudaSuccess ? 0 : -2;
+}
+int avg_free_host(void* p) { return cudaFreeHost(p) == cudaSuccess ? 0 : -2; }
+
 int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, float* info) {
     if (!h || !actions || !obs || !reward || !info) return -1;
     cudaSetDevice(h->device);
     size_t n = (size_t)h->n_env;
-    if (!h->h_act) {
-        AVG_CHECK(h, cudaMallocHost(&h->h_act, sizeof(float) * n * h->n_act));
-        AVG_CHECK(h, cudaMallocHost(&h->h_obs, sizeof(float) * n * h->n_obs));
-        AVG_CHECK(h, cudaMallocHost(&h->h_rew, sizeof(float) * n));
-        AVG_CHECK(h, cudaMallocHost(&h->h_info, sizeof(float) * n * 2));
-        AVG_CHECK(h, cudaMallocHost(&h->h_done, n));
+    if (!h->d_act) {
         AVG_CHECK(h, cudaMalloc(&h->d_act, sizeof(float) * n * h->n_act));
         AVG_CHECK(h, cudaMalloc(&h->d_obs, sizeof(float) * n * h->n_obs));
         AVG_CHECK(h, cudaMalloc(&h->d_rew, sizeof(float) * n));
         AVG_CHECK(h, cudaMalloc(&h->d_info, sizeof(float) * n * 2));
         AVG_CHECK(h, cudaMalloc(&h->d_done, n));
     }
-    memcpy(h->h_act, actions, sizeof(float) * n * h->n_act);
-    AVG_CHECK(h, cudaMemcpyAsync(h->d_act, h->h_act, sizeof(float) * n * h->n_act, cudaMemcpyHostToDevice, h->stream));
+    /* Caller buffers that are page-locked (avg_alloc_host, cudaHostRegister, torch pin_memory) are used in place;
+       pageable ones go through the handle's pinned staging buffers. */
+    const bool direct = is_pinned_host(actions) && is_pinned_host(obs) && is_pinned_host(reward) && is_pinned_host(info) &&
+                        (!done || is_pinned_host(done));
+    if (!direct && !h->h_act) {
+        AVG_CHECK(h, cudaMallocHost(&h->h_act, sizeof(float) * n * h->n_act));
+        AVG_CHECK(h, cudaMallocHost(&h->h_obs, sizeof(float) * n * h->n_obs));
+        AVG_CHECK(h, cudaMallocHost(&h->h_rew, sizeof(float) * n));
+        AVG_CHECK(h, cudaMallocHost(&h->h_info, sizeof(float) * n * 2));
+        AVG_CHECK(h, cudaMallocHost(&h->h_done, n));
+    }
+    const float* src_act = actions;
+    float *dst_obs = obs, *dst_rew = reward, *dst_info = info; uint8_t* dst_done = done;
+    if (!direct) {
+        memcpy(h->h_act, actions, sizeof(float) * n * h->n_act);
+        src_act = h->h_act; dst_obs = h->h_obs; dst_rew = h->h_rew; dst_info = h->h_info; dst_done = h->h_done;
+    }
+    AVG_CHECK(h, cudaMemcpyAsync(h->d_act, src_act, sizeof(float) * n * h->n_act, cudaMemcpyHostToDevice, h->stream));
     int rc = avg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_info, h->stream);
     if (rc) return rc;
-    AVG_CHECK(h, cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * n * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
-    AVG_CHECK(h, cudaMemcpyAsync(h->h_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-    AVG_CHECK(h, cudaMemcpyAsync(h->h_info, h->d_info, sizeof(float) * n * 2, cudaMemcpyDeviceToHost, h->stream));
-    AVG_CHECK(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(dst_obs, h->d_obs, sizeof(float) * n * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(dst_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    AVG_CHECK(h, cudaMemcpyAsync(dst_info, h->d_info, sizeof(float) * n * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (dst_done) AVG_CHECK(h, cudaMemcpyAsync(dst_done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
     AVG_CHECK(h, cudaStreamSynchronize(h->stream));
-    memcpy(obs, h->h_obs, sizeof(float) * n * h->n_obs);
-    memcpy(reward, h->h_rew, sizeof(float) * n);
-    memcpy(info, h->h_info, sizeof(float) * n * 2);
-    if (done) memcpy(done, h->h_done, n);
+    if (!direct) {
+        memcpy(obs, h->h_obs, sizeof(float) * n * h->n_obs);
+        memcpy(reward, h->h_rew, sizeof(float) * n);
+        memcpy(info, h->h_info, sizeof(float) * n * 2);
+        if (done) memcpy(done, h->h_done, n);
+    }
     return 0;
 }
 

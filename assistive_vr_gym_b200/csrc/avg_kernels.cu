@@ -29,9 +29,18 @@
 // runs the recursive articulated-body algorithm.  Both are Featherstone algorithms for the same equations.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "../../include/avg_model.h"
 #include "avg_math.cuh"
 #include "avg_kernels.h"
+
+#ifndef AVG_OCC_COLLIDE
+#define AVG_OCC_COLLIDE 5
+#endif
+#ifndef AVG_OCC_DYN
+#define AVG_OCC_DYN 5
+#endif
 
 namespace {
 
@@ -85,6 +94,8 @@ struct __align__(16) SmCollide {
     float sp[kMaxMS][3]; float sR[kMaxMS][9]; float4 saabb[kMaxMS][2];
     float4 scap[kMaxMS][2];                // bounding capsules of the moving shapes, world frame
     uint32_t cand[kMaxCand];
+    float4 sep[3][AVG_S_NSEPMAX];          // separation certificates of the previous sub-step (see collide_warp)
+    float sq[kMaxMS][4];                   // world orientation of the moving shapes
     uint8_t near_idx[256];                 // static shapes (index) that overlap the union box of the moving shapes
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
     int c_sa[kMaxC], c_sb[kMaxC];
@@ -100,8 +111,8 @@ struct __align__(16) SmDyn {
 struct __align__(16) SmSolve {
     float J[kSmDense][32];
     float W[kSmDense][32];
-    float4 um[32];                         // motor row of dof i: {target, 1/diag, hi (lo = -hi), diag}
-    float4 ul[32];                         // limit row of dof i: {target, 1/diag, diag, sign}; 1/diag = 0 when not violated
+    float4 um[4][kMaxBlk];                 // motor row of dof block_start[g] + t: {target, 1/diag, hi (lo = -hi), diag}; zero when absent
+    float4 ul[4][kMaxBlk];                 // limit row, same indexing: {target, 1/diag, diag, sign}; 1/diag = 0 when not violated
     float4 rd[kMaxDense][2];               // dense rows: {target, 1/diag, lo, hi}, {diag, mu, index, normal row}
 };
 struct __align__(16) SmEpi {
@@ -297,28 +308,36 @@ __device__ bool simplex_closest(Simplex& s, V3& v) {
 // returns 0: cores separated (dist, pa, pb valid); 1: cores overlap; 2: separated by more than maxdist (early out: every
 // support plane gives the lower bound v.w/|v| on the distance, so well-separated candidates leave after 1-2 iterations).
 // Works relative to A's position to keep float32 magnitudes small.
-__device__ __noinline__ int gjk(const WShape& A, const WShape& B, float maxdist, float& dist, V3& pa, V3& pb) {
+// vout / gap: on return 0 or 2, a direction along which the cores are separated and the support-plane lower bound of
+// their distance along it (gap <= 0: no valid bound).
+__device__ __noinline__ int gjk(const WShape& A, const WShape& B, float maxdist, float& dist, V3& pa, V3& pb, V3& vout, float& gap, int& iters) {
     Simplex s; s.n = 0;
+    gap = 0.0f;
+    bool fresh = false;
     V3 org = A.p;
     V3 v = A.p - B.p;
     if (dot(v, v) < 1e-12f) v = mk3(1, 0, 0);
 #pragma unroll 1
     for (int it = 0; it < 32; ++it) {
+        iters = it + 1;
         V3 sa = support(A, -v) - org, sb = support(B, v) - org;
         V3 w = sa - sb;
         float vv = dot(v, v), vw = dot(v, w);
-        if (vw > 0.0f && vw * vw > maxdist * maxdist * vv) return 2;
+        gap = vw * rsqrtf(vv); fresh = true;
+        if (vw > 0.0f && vw * vw > maxdist * maxdist * vv) { vout = v; return 2; }
         if (s.n > 0 && (vv - vw) <= 1e-5f * vv + 1e-10f) break;
         bool dup = false;
         for (int i = 0; i < s.n; ++i) { V3 d = s.w[i] - w; if (dot(d, d) < 1e-14f) dup = true; }
         if (dup) break;
+        fresh = false;
         s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
         if (simplex_closest(s, v)) return 1;
         if (dot(v, v) < 1e-12f) return 1;
     }
     V3 a = mk3(0, 0, 0), b = mk3(0, 0, 0);
     for (int i = 0; i < s.n; ++i) { a = a + s.a[i] * s.lam[i]; b = b + s.b[i] * s.lam[i]; }
-    pa = a + org; pb = b + org; dist = norm(v);
+    pa = a + org; pb = b + org; dist = norm(v); vout = v;
+    if (!fresh) gap = 0.0f;                  // v moved after the last support evaluation: no bound for it
     return 0;
 }
 
@@ -360,8 +379,10 @@ __device__ void shape_axes(const WShape& S, const WShape& O, float sign, const W
 }
 
 // -> true when a contact (distance < thr) exists
-__device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa, V3& pb, V3& n, float& d) {
+// sepv / have_sep: when no contact is reported and GJK proved the separation along a direction, that direction
+__device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa, V3& pb, V3& n, float& d, V3& sepv, float& sepgap, bool& have_sep, int& iters) {
     float ma = A.s->margin, mb = B.s->margin;
+    have_sep = false;
     if (B.s->type == AVG_SHAPE_PLANE) {
         V3 sp = support(A, mk3(0, 0, -1));
         d = sp.z - ma;
@@ -370,11 +391,11 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
         return true;
     }
     float dist; V3 ca, cb;
-    const int g = gjk(A, B, thr + ma + mb, dist, ca, cb);
-    if (g == 2) return false;
+    const int g = gjk(A, B, thr + ma + mb, dist, ca, cb, sepv, sepgap, iters);
+    if (g == 2) { have_sep = true; return false; }
     if (g == 0) {
         d = dist - ma - mb;
-        if (d >= thr) return false;
+        if (d >= thr) { have_sep = sepgap > 0.0f; return false; }
         n = (ca - cb) * (1.0f / dist);
         pa = ca - n * ma; pb = cb + n * mb;
         return true;
@@ -390,7 +411,7 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
 }
 
 template <class SM>
-__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow, int& ncand_out) {
+__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow, int& ncand_out, int nsep, float* gsep_f, int& nsep_out, int dbg, unsigned long long* hist) {
     const AvgModelHeader* h = m.h;
     const int nms = h->n_mshape;
     // world pose + AABB of the moving shapes
@@ -399,8 +420,10 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         V3 bp; Q4 bq;
         body_pose(s, S->body, bp, bq);
         V3 p = bp + qrot(bq, ld3(S->pos));
-        M3 R = qmat(qnormalize(qmul(bq, ldq(S->quat))));
+        const Q4 sq = qnormalize(qmul(bq, ldq(S->quat)));
+        M3 R = qmat(sq);
         st3(s.sp[lane], p);
+        s.sq[lane][0] = sq.x; s.sq[lane][1] = sq.y; s.sq[lane][2] = sq.z; s.sq[lane][3] = sq.w;
 #pragma unroll
         for (int i = 0; i < 9; ++i) s.sR[lane][i] = R.m[i];
         V3 lc = ld3(S->aabb_c), lh = ld3(S->aabb_h);
@@ -448,7 +471,23 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
     }
     __syncwarp();
     // (b) one lane per surviving static shape (AABB, threshold and the bit mask of moving shapes it may touch arrive in
-    //     two 16-byte loads); moving-shape AABBs are broadcast from shared memory
+    //     two 16-byte loads); moving-shape AABBs are broadcast from shared memory.  Each lane first collects its hits
+    //     in a bit mask (independent iterations, no votes inside the loop), then the warp compacts them with one
+    //     prefix sum over the per-lane counts.  Order does not matter here: candidates are ranked below.
+    auto emit = [&](uint32_t hm, uint32_t other) {
+        const int cnt = __popc(hm);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(AVG_FULL, inc, o); if (lane >= o) inc += v; }
+        int slot = ncand + inc - cnt;
+        while (hm) {
+            const int a = __ffs(hm) - 1; hm &= hm - 1;
+            if (slot < kMaxCand) s.cand[slot] = (uint32_t)a | (other << 16);
+            ++slot;
+        }
+        ncand += __shfl_sync(AVG_FULL, inc, 31);
+    };
+    if (dbg & 2) nnear = 0;
     for (int base = 0; base < nnear; base += 32) {
         const int k = base + lane;
         int si = 0;
@@ -460,41 +499,33 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
             r0 = __ldg(rp); r1 = __ldg(rp + 1);
             mask = __float_as_uint(r1.w);
         }
+        uint32_t hm = 0;
+#pragma unroll 4
         for (int a = 0; a < nms; ++a) {
             const float4 a0 = s.saabb[a][0], a1 = s.saabb[a][1];
             const float thr = fminf(a1.z, r1.z);
-            bool hit = ((mask >> a) & 1u) && fabsf(a0.x - r0.x) <= a0.w + r0.w + thr && fabsf(a0.y - r0.y) <= a1.x + r1.x + thr &&
-                       fabsf(a0.z - r0.z) <= a1.y + r1.y + thr;
-            unsigned bal = __ballot_sync(AVG_FULL, hit);
-            if (bal) {
-                if (hit) {
-                    int slot = ncand + __popc(bal & ((1u << lane) - 1));
-                    if (slot < kMaxCand) s.cand[slot] = (uint32_t)a | ((uint32_t)(nms + si) << 16);
-                }
-                ncand += __popc(bal);
-            }
+            const bool hit = fabsf(a0.x - r0.x) <= a0.w + r0.w + thr && fabsf(a0.y - r0.y) <= a1.x + r1.x + thr &&
+                             fabsf(a0.z - r0.z) <= a1.y + r1.y + thr;
+            hm |= (hit ? 1u : 0u) << a;
         }
+        emit(hm & mask, (uint32_t)(nms + si));
     }
-    // moving-moving pairs: lane b against every a < b allowed by the filter masks
-    {
+    // moving-moving pairs: lane b against every a < b allowed by the filter masks (bit b of bpm[a])
+    if (!(dbg & 8)) {
         float4 b0 = make_float4(0, 0, 0, 0), b1 = make_float4(0, 0, 0, 0);
         if (lane < nms) { b0 = s.saabb[lane][0]; b1 = s.saabb[lane][1]; }
+        uint32_t hm = 0, allowed = 0;
+#pragma unroll 4
         for (int a = 0; a < nms; ++a) {
             const uint32_t mask = __ldg(&m.bpm[a]);
-            if (mask == 0) continue;
             const float4 a0 = s.saabb[a][0], a1 = s.saabb[a][1];
             const float thr = fminf(a1.z, b1.z);
-            bool hit = lane < nms && ((mask >> lane) & 1u) && fabsf(a0.x - b0.x) <= a0.w + b0.w + thr &&
-                       fabsf(a0.y - b0.y) <= a1.x + b1.x + thr && fabsf(a0.z - b0.z) <= a1.y + b1.y + thr;
-            unsigned bal = __ballot_sync(AVG_FULL, hit);
-            if (bal) {
-                if (hit) {
-                    int slot = ncand + __popc(bal & ((1u << lane) - 1));
-                    if (slot < kMaxCand) s.cand[slot] = (uint32_t)a | ((uint32_t)lane << 16);
-                }
-                ncand += __popc(bal);
-            }
+            const bool hit = fabsf(a0.x - b0.x) <= a0.w + b0.w + thr && fabsf(a0.y - b0.y) <= a1.x + b1.x + thr &&
+                             fabsf(a0.z - b0.z) <= a1.y + b1.y + thr;
+            hm |= (hit ? 1u : 0u) << a;
+            allowed |= ((mask >> lane) & 1u) << a;
         }
+        emit(lane < nms ? (hm & allowed) : 0u, (uint32_t)lane);
     }
     if (ncand > kMaxCand) { overflow |= 4; ncand = kMaxCand; }
     ncand_out = ncand;
@@ -572,19 +603,78 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         ncand = nk;
         __syncwarp();
     }
-    // narrowphase: one lane per candidate, results compacted in pair order
-    int nc = 0;
+    // narrowphase: one lane per candidate, results compacted in pair order.
+    // Separation certificates (temporal coherence).  Most candidates that survive the culls are close but not touching,
+    // sub-step after sub-step (hand against its own finger tips, arm over the armrest).  When GJK proves a pair
+    // separated along a direction v by at least g (support-plane bound, the predicate of its own early-out), the arena
+    // remembers, in A's frame, v, g and the pose of B relative to A.  Next sub-step the pair is rejected
+    //   (1) without touching the shapes when g minus a bound on how far B's points can have moved in A's frame
+    //       (translation + chord of the rotation x bounding radius) still exceeds the contact distance, else
+    //   (2) by one support-plane test along the remembered direction, which renews the certificate.
+    // Both are sufficient conditions for "no contact"; a pair that fails them runs the full GJK, so certificates can
+    // only skip work, never change a contact.
+    int nc = 0, nnew = 0;
+    if (dbg & 1) ncand = 0;
+    float4* gsep = reinterpret_cast<float4*>(gsep_f);
     for (int base = 0; base < ncand; base += 32) {
         int ci = base + lane;
-        bool hit = false;
+        bool hit = false, have_sep = false;
         V3 pa, pb, n; float d = 0; int a = 0, b = 0;
+        uint32_t pr = 0;
+        float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0;
         if (ci < ncand) {
-            uint32_t pr = s.cand[ci];
+            pr = s.cand[ci];
             a = pr & 0xffff; b = pr >> 16;
             WShape A, B;
             load_wshape(m, s, a, A); load_wshape(m, s, b, B);
-            float thr = fminf(A.s->thr, B.s->thr);
-            hit = narrowphase(A, B, thr, pa, pb, n, d);
+            const float thr = fminf(A.s->thr, B.s->thr);
+            bool culled = false;
+            int gi = 0, how = 0;
+            if (B.s->type != AVG_SHAPE_PLANE) {
+                const Q4 qa = ldq(s.sq[a]);
+                const Q4 qb = b < nms ? ldq(s.sq[b]) : ldq(B.s->quat);
+                const V3 prel = qrot_inv(qa, B.p - A.p);
+                const Q4 qrel = qmul(qconj(qa), qb);
+                const float md = thr + A.s->margin + B.s->margin;
+                int f = -1;
+                for (int e = 0; e < nsep; ++e) if (__float_as_uint(s.sep[0][e].w) == pr) f = e;
+                if (f >= 0) {
+                    const float4 e0 = s.sep[0][f], e1 = s.sep[1][f], e2 = s.sep[2][f];
+                    const V3 dp = prel - mk3(e1.x, e1.y, e1.z);
+                    const float sg = (qrel.x * e2.x + qrel.y * e2.y + qrel.z * e2.z + qrel.w * e2.w) < 0.0f ? -1.0f : 1.0f;
+                    const float dx = qrel.x - sg * e2.x, dy = qrel.y - sg * e2.y, dz = qrel.z - sg * e2.z, dw = qrel.w - sg * e2.w;
+                    const float chord = 2.0f * sqrtf(dx * dx + dy * dy + dz * dz + dw * dw);     // >= 2 sin(angle / 2)
+                    const float4 c0 = __ldg(&m.bcap[2 * b]), c1 = __ldg(&m.bcap[2 * b + 1]);
+                    const V3 o = b < nms ? mk3(0, 0, 0) : ld3(B.s->pos);
+                    const float rb = fmaxf(norm(mk3(c0.x, c0.y, c0.z) - o), norm(mk3(c1.x, c1.y, c1.z) - o)) + c0.w;
+                    if (e1.w - (norm(dp) + chord * rb) > md + 1e-5f) { culled = true; have_sep = true; k0 = e0; k1 = e1; k2 = e2; how = 1; }
+                    else {
+                        const V3 v = qrot(qa, mk3(e0.x, e0.y, e0.z));
+                        const V3 w = support(A, -v) - support(B, v);
+                        const float vv = dot(v, v), vw = dot(v, w);
+                        if (vw > 0.0f && vw * vw > md * md * vv) {
+                            culled = true; have_sep = true; how = 2;
+                            k0 = e0; k1 = make_float4(prel.x, prel.y, prel.z, vw * rsqrtf(vv)); k2 = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
+                        }
+                    }
+                }
+                if (!culled) {
+                    V3 sepv = mk3(0, 0, 0); float sepgap = 0.0f;
+                    hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, have_sep, gi);
+                    if (have_sep) {
+                        const V3 va = qrot_inv(qa, sepv);
+                        k0 = make_float4(va.x, va.y, va.z, __uint_as_float(pr));
+                        k1 = make_float4(prel.x, prel.y, prel.z, sepgap); k2 = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
+                    }
+                }
+            } else {
+                V3 sepv; float sepgap; bool hs;
+                hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, hs, gi);
+            }
+            if (hist) {
+                const int k = (a & 31) * 256 + (b & 255);
+                atomicAdd(hist + k, 1ull); if (how == 2) atomicAdd(hist + 8192 + k, 1ull); atomicAdd(hist + 16384 + k, (unsigned long long)gi);
+            }
         }
         unsigned bal = __ballot_sync(AVG_FULL, hit);
         if (hit) {
@@ -595,7 +685,14 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
             }
         }
         nc += __popc(bal);
+        const unsigned bsep = __ballot_sync(AVG_FULL, have_sep);
+        if (have_sep) {
+            const int slot = nnew + __popc(bsep & ((1u << lane) - 1));
+            if (slot < AVG_S_NSEPMAX) { gsep[slot] = k0; gsep[AVG_S_NSEPMAX + slot] = k1; gsep[2 * AVG_S_NSEPMAX + slot] = k2; }
+        }
+        nnew += __popc(bsep);
     }
+    nsep_out = min(nnew, AVG_S_NSEPMAX);
     if (nc > kMaxC) { overflow |= 1; nc = kMaxC; }
     ncontact = nc;
     __syncwarp();
@@ -712,15 +809,18 @@ avg_prologue_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // forward kinematics + collision -> contact list in the scratch arena
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, 5)
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     s.q[lane] = grec[AVG_E_Q + lane];
     __syncwarp();
     fk_warp(m, s, s.q, lane, h->n_body);
-    int nc = 0, overflow = 0, ncand = 0;
-    collide_warp(m, s, lane, nc, overflow, ncand);
+    int nc = 0, overflow = 0, ncand = 0, nsep_out = 0;
     int* scr_i = reinterpret_cast<int*>(scr);
+    float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
+    int nsep = (a.dbg & 16) ? 0 : min(max(scr_i[AVG_S_NSEP], 0), AVG_S_NSEPMAX);
+    if (lane < nsep) { s.sep[0][lane] = gsep[lane]; s.sep[1][lane] = gsep[AVG_S_NSEPMAX + lane]; s.sep[2][lane] = gsep[2 * AVG_S_NSEPMAX + lane]; }
+    if (!(a.dbg & 4)) collide_warp(m, s, lane, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.dbg, (a.dbg & 32) ? a.dbg_hist : nullptr);
     if (lane < nc) {
         float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
         c[0] = s.c_pa[lane][0]; c[1] = s.c_pa[lane][1]; c[2] = s.c_pa[lane][2];
@@ -728,14 +828,14 @@ avg_collide_kernel(AvgStepArgs a) {
         c[6] = s.c_n[lane][0]; c[7] = s.c_n[lane][1]; c[8] = s.c_n[lane][2];
         c[9] = s.c_dist[lane]; c[10] = __int_as_float(s.c_sa[lane]); c[11] = __int_as_float(s.c_sb[lane]); c[12] = 0.0f;
     }
-    if (lane == 0) { scr_i[AVG_S_NC] = nc; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
+    if (lane == 0) { scr_i[AVG_S_NC] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
 }
 
 // =================================================================================================================
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
 template <int MAXBLK>
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, 5)
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_DYN)
 avg_dynamics_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmDyn)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
@@ -1102,96 +1202,117 @@ avg_solve_kernel(AvgStepArgs a) {
     const int nc = scr_i[AVG_S_NCS];
     const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
     // stage rows: coalesced loads from the arena
-    for (int d = 0; d < min(ndense, kSmDense); ++d) { s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
+    for (int d = 0; d < min(ndense, kSmDense); ++d) { if (d >= 6) s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
     {
-        const float4* g_um = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_M);
-        const float4* g_ul = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_L);
         const float4* g_rd = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_D);
-        s.um[lane] = g_um[lane];
-        if (nlim) s.ul[lane] = g_ul[lane];
         for (int i = lane; i < 2 * ndense; i += 32) s.rd[i >> 1][i & 1] = g_rd[i];
     }
     const float qd = lane < nd ? scr[AVG_S_QD + lane] : 0.0f;
-    // block of this lane's dof, and this lane's column of the block of M^-1 (registers)
-    int bs = lane, be = lane;
+    // block of this lane's dof, and this lane's column of the block of M^-1 (registers).  Unit rows are staged per
+    // block (group 3 = lanes without a joint dof: all-zero rows), so the sweep addresses them with immediates.
+    int bs = lane, grp = 3;
     for (int b = 0; b < h->n_block; ++b) {
         const int b0 = h->block_start[b], b1 = h->block_start[b + 1];
-        if (lane >= b0 && lane < b1) { bs = b0; be = b1; }
+        if (lane >= b0 && lane < b1) { bs = b0; grp = b; }
     }
+    {
+        const float4 z4 = make_float4(0, 0, 0, 0);
+        float4* um0 = &s.um[0][0]; float4* ul0 = &s.ul[0][0];
+        for (int i = lane; i < 4 * kMaxBlk; i += 32) { um0[i] = z4; ul0[i] = z4; }
+        __syncwarp();
+        if (lane < nj) {
+            s.um[grp][lane - bs] = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_M)[lane];
+            if (nlim) s.ul[grp][lane - bs] = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_L)[lane];
+        }
+    }
+    const float4* umg = s.um[grp]; const float4* ulg = s.ul[grp];
+    const int lt = lane - bs;
     float mcol[MAXBLK];
 #pragma unroll
     for (int t = 0; t < MAXBLK; ++t) mcol[t] = scr[AVG_S_MINV + t * 32 + lane];
     __syncwarp();
 
     // ---- projected Gauss-Seidel.  dv lives in one register per lane.  Unit rows: the articulation blocks are swept
-    //      concurrently (they do not couple), in Bullet's order inside a block; their impulses live in the lane of
-    //      their dof; the lane's column of M^-1 sits in registers.  Dense rows (weld, contact normals, friction)
-    //      follow in strict order; impulse of dense row d in lane d.
-    float dv = 0.0f, lamM = 0.0f, lamL = 0.0f, lamD = 0.0f;
-    const float thr = h->residual_thr;
+    //      concurrently (they do not couple), in Bullet's order inside a block.  Every lane of a block evaluates the
+    //      block's current row (same inputs, same result), so motor impulses are replicated in registers and need
+    //      neither an owner lane nor a shuffle; the lane's column of M^-1 sits in registers.  Slots past the end of a
+    //      block hold all-zero rows (1/diag = 0), which makes their delta exactly 0.
+    //      Dense rows follow in strict order: the six weld rows unrolled with J, W and impulses in registers, then
+    //      the contact rows (rare) from shared memory / the arena with the impulse of row d in lane d.
+    float dv = 0.0f, lamL = 0.0f, lamD = 0.0f;
+    float lamM[MAXBLK], lamW[6], jw[6];
+#pragma unroll
+    for (int t = 0; t < MAXBLK; ++t) lamM[t] = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { lamW[d] = 0.0f; jw[d] = gJ[d * 32 + lane]; }
+    const float thr = sqrtf(h->residual_thr);                        // on |delta impulse| * diag (Bullet squares both sides)
     int iters = 0;
     for (int it = 0; it < h->solver_iters; ++it) {
         float resid = 0.0f;
 #pragma unroll
         for (int t = 0; t < MAXBLK; ++t) {
-            const bool act = bs + t < be;
-            const int i = act ? bs + t : lane;                   // idle lanes point at themselves (mcol = 0: no effect)
-            const float4 ra = s.um[i];
-            const float jdv = __shfl_sync(AVG_FULL, dv, i);
-            const float lam = __shfl_sync(AVG_FULL, lamM, i);
-            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -ra.z), ra.z);
-            const float delta = sum - lam;
+            const float4 ra = umg[t];
+            const float jdv = __shfl_sync(AVG_FULL, dv, bs + t);
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lamM[t]), -ra.z), ra.z);
+            const float delta = sum - lamM[t];
+            lamM[t] = sum;
             dv = fmaf(mcol[t], delta, dv);
-            if (lane == i && act) { lamM = sum; const float rv = delta * ra.w; resid = fmaxf(resid, rv * rv); }
+            resid = fmaxf(resid, fabsf(delta) * ra.w);
         }
         if (nlim) {
 #pragma unroll
             for (int t = 0; t < MAXBLK; ++t) {
-                const bool act = bs + t < be;
-                const int i = act ? bs + t : lane;
-                const float4 ra = s.ul[i];
+                const float4 ra = ulg[t];
                 const float sg = ra.w;
-                const float jdv = sg * __shfl_sync(AVG_FULL, dv, i);
-                const float lam = __shfl_sync(AVG_FULL, lamL, i);
+                const float jdv = sg * __shfl_sync(AVG_FULL, dv, bs + t);
+                const float lam = __shfl_sync(AVG_FULL, lamL, bs + t);
                 const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), 0.0f), 100.0f);
                 const float delta = sum - lam;
                 dv = fmaf(sg * mcol[t], delta, dv);
-                if (lane == i && act) { lamL = sum; const float rv = delta * ra.z; resid = fmaxf(resid, rv * rv); }
+                if (lt == t) lamL = sum;
+                resid = fmaxf(resid, fabsf(delta) * ra.z);
             }
         }
-        resid = warp_max(resid);                                   // blocks ran in different lanes
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const float4 ra = s.rd[d][0];                            // {target, 1/diag, -max, +max}
+            const float jdv = warp_sum(jw[d] * dv);
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lamW[d]), ra.z), ra.w);
+            const float delta = sum - lamW[d];
+            lamW[d] = sum;
+            dv = fmaf(s.W[d][lane], delta, dv);
+            resid = fmaxf(resid, fabsf(delta) * s.rd[d][1].x);
+        }
 #pragma unroll 1
-        for (int d = 0; d < nfr; ++d) {
+        for (int d = 6; d < nfr; ++d) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
-            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
-            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
+            const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
+            const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
+            const float jdv = warp_sum(*jp * dv);
             const float lam = __shfl_sync(AVG_FULL, lamD, d);
-            float delta = (ra.x - jdv) * ra.y;
-            const float sum = fminf(fmaxf(lam + delta, ra.z), ra.w);
-            delta = sum - lam;
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), ra.z), ra.w);
+            const float delta = sum - lam;
             if (lane == d) lamD = sum;
-            dv = fmaf(wl, delta, dv);
-            const float rv = delta * rb.x;
-            resid = fmaxf(resid, rv * rv);
+            dv = fmaf(*wp, delta, dv);
+            resid = fmaxf(resid, fabsf(delta) * rb.x);
         }
 #pragma unroll 1
         for (int d = nfr; d < ndense; ++d) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
             const int par = __float_as_int(rb.w);
-            const float jdv = warp_sum((d < kSmDense ? s.J[d][lane] : gJ[d * 32 + lane]) * dv);
-            const float wl = (d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane]);
+            const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
+            const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
+            const float jdv = warp_sum(*jp * dv);
             const float lam = __shfl_sync(AVG_FULL, lamD, d);
             const float lim = rb.y * __shfl_sync(AVG_FULL, lamD, par);
-            float delta = (ra.x - jdv) * ra.y;
-            const float sum = fminf(fmaxf(lam + delta, -lim), lim);
-            delta = sum - lam;
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -lim), lim);
+            const float delta = sum - lam;
             if (lane == d) lamD = sum;
-            dv = fmaf(wl, delta, dv);
-            const float rv = delta * rb.x;
-            resid = fmaxf(resid, rv * rv);
+            dv = fmaf(*wp, delta, dv);
+            resid = fmaxf(resid, fabsf(delta) * rb.x);
         }
         iters++;
-        if (resid <= thr) break;
+        if (!__any_sync(AVG_FULL, resid > thr)) break;              // blocks ran in different lanes
     }
 
     // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
@@ -1440,6 +1561,19 @@ int avg_kernels_per_step(int substeps) { return 2 + 3 * substeps; }
 // environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
 constexpr int kWpbCollide = 4, kWpbDyn = 4, kWpbSolve = 1, kWpbEpi = 4, kWpbPro = 4;
 
+// AVG_KERNEL_TIMES=1 in the environment: every launch of the step is bracketed by CUDA events and the per-kernel totals
+// are printed to stderr every 8 steps (a development aid; it serialises the host with the stream, so never set it for
+// a measurement of the step itself).
+namespace {
+struct KernelTimes {
+    bool on = false, init = false;
+    cudaEvent_t ev[64];
+    double ms[5] = {0, 0, 0, 0, 0};
+    int steps = 0;
+};
+KernelTimes g_kt;
+}  // namespace
+
 cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
     static bool configured = false;
     const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
@@ -1458,21 +1592,45 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
+        const char* kt = getenv("AVG_KERNEL_TIMES");
+        g_kt.on = kt && kt[0] == '1' && 3 * substeps + 3 <= 64;
     }
+    int nev = 0;
+    if (g_kt.on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
+    auto mark = [&]() { if (g_kt.on) cudaEventRecord(g_kt.ev[nev++], stream); };
     auto grid = [&](int wpb) { return (a.n_env + wpb - 1) / wpb; };
+    mark();
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
+    mark();
     for (int f = 0; f < substeps; ++f) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+        mark();
         if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         else if (a.maxblk <= 12) avg_dynamics_kernel<12><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         else avg_dynamics_kernel<16><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+        mark();
         if (a.maxblk <= 8) avg_solve_kernel<8><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         else if (a.maxblk <= 10) avg_solve_kernel<10><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         else if (a.maxblk <= 12) avg_solve_kernel<12><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         else avg_solve_kernel<16><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+        mark();
     }
     avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
+    mark();
+    if (g_kt.on) {
+        cudaEventSynchronize(g_kt.ev[nev - 1]);
+        auto el = [&](int i) { float t = 0; cudaEventElapsedTime(&t, g_kt.ev[i], g_kt.ev[i + 1]); return (double)t; };
+        g_kt.ms[0] += el(0);
+        for (int f = 0; f < substeps; ++f) { g_kt.ms[1] += el(1 + 3 * f); g_kt.ms[2] += el(2 + 3 * f); g_kt.ms[3] += el(3 + 3 * f); }
+        g_kt.ms[4] += el(1 + 3 * substeps);
+        if (++g_kt.steps % 8 == 0) {
+            const double tot = g_kt.ms[0] + g_kt.ms[1] + g_kt.ms[2] + g_kt.ms[3] + g_kt.ms[4];
+            fprintf(stderr, "[avg kernel times, %d steps, %d envs] prologue %.3f collide %.3f dynamics %.3f solve %.3f epilogue %.3f ms/step (total %.3f)\n",
+                    g_kt.steps, a.n_env, g_kt.ms[0] / g_kt.steps, g_kt.ms[1] / g_kt.steps, g_kt.ms[2] / g_kt.steps, g_kt.ms[3] / g_kt.steps,
+                    g_kt.ms[4] / g_kt.steps, tot / g_kt.steps);
+        }
+    }
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 #define AVG_S_OVERFLOW 6
 #define AVG_S_ITERS 7         /* solver iterations accumulated over the env-step            */
 #define AVG_S_NCAND 8         /* narrowphase candidates accumulated over the env-step (diagnostic) */
+#define AVG_S_NSEP 9          /* entries of the separating-axis cache (persists across sub-steps and env-steps) */
 #define AVG_S_QD 16           /* [32] velocities after the unconstrained update             */
 #define AVG_S_CONTACT 48      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
 #define AVG_S_CONTACT_STRIDE 14
@@ -29,7 +30,9 @@
 #define AVG_S_MINV (AVG_S_ROWS_D + 8 * AVG_S_MAXDENSE)                                   /* [MAXJ][MAXJ]   */
 #define AVG_S_J (AVG_S_MINV + AVG_K_MAXJ * AVG_K_MAXJ)                                  /* [MAXDENSE][32] */
 #define AVG_S_W (AVG_S_J + 32 * AVG_S_MAXDENSE)
-#define AVG_S_STRIDE (AVG_S_W + 32 * AVG_S_MAXDENSE)
+#define AVG_S_SEP (AVG_S_W + 32 * AVG_S_MAXDENSE)     /* [3][AVG_S_NSEPMAX] float4: separation certificates, see collide_warp */
+#define AVG_S_NSEPMAX 32
+#define AVG_S_STRIDE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)
 
 struct AvgStepArgs {
     const unsigned char* models[AVG_K_MAX_VARIANTS];   // device ModelBlobs
@@ -46,6 +49,8 @@ struct AvgStepArgs {
     int32_t* ncontacts;                                // [n_env]
     int n_env;
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
+    int dbg;                                           // development switches (AVG_DBG), 0 in production
+    unsigned long long* dbg_hist;                      // AVG_DBG & 32: [3][32][256] narrowphase histogram per (moving shape, other shape): candidates, GJK calls, GJK iterations
 };
 
 int avg_kernels_per_step(int substeps);

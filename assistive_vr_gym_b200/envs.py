@@ -161,10 +161,10 @@ class BatchedAssistiveEnv:
         """Same step with NumPy buffers through avg_step_host (host<->device copies included)."""
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.sim.n_actions)
         if not hasattr(self, "_h_obs"):
-            self._h_obs = np.zeros((self.num_envs, self.sim.n_obs), dtype=np.float32)
-            self._h_rew = np.zeros(self.num_envs, dtype=np.float32)
-            self._h_done = np.zeros(self.num_envs, dtype=np.uint8)
-            self._h_info = np.zeros((self.num_envs, 2), dtype=np.float32)
+            # results land in page-locked arrays owned by the env (returned as views, like self.obs on the device)
+            self._pinned = [capi.PinnedArray((self.num_envs, self.sim.n_obs), np.float32), capi.PinnedArray((self.num_envs,), np.float32),
+                            capi.PinnedArray((self.num_envs,), np.uint8), capi.PinnedArray((self.num_envs, 2), np.float32)]
+            self._h_obs, self._h_rew, self._h_done, self._h_info = (p.array for p in self._pinned)
         self.sim.step_host(a, self._h_obs, self._h_rew, self._h_done, self._h_info)
         self.elapsed += 1
         timeout = self.elapsed >= MAX_EPISODE_STEPS
@@ -172,6 +172,12 @@ class BatchedAssistiveEnv:
                 "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
                 "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len}
         return self._h_obs, self._h_rew, self._h_done.astype(bool) | timeout, info
+
+    def pinned_actions(self) -> np.ndarray:
+        """A page-locked [N, A] float32 array: actions written here reach the GPU without a staging copy."""
+        if not hasattr(self, "_pinned_act"):
+            self._pinned_act = capi.PinnedArray((self.num_envs, self.sim.n_actions), np.float32)
+        return self._pinned_act.array
 
     def render(self):
         """env.py:613-620 opens the PyBullet GUI; rendering is out of scope for the batched simulator."""

@@ -211,7 +211,11 @@ def main():
 
     # ---- end-to-end through the host-buffer API (bounded to keep the run short) ----------------------------------
     e2e_steps = max(3, min(args.steps, 10))
-    a_host = [np.random.RandomState(100 + rank + i).uniform(-1, 1, (E, 7)).astype(np.float32) for i in range(2)]
+    from assistive_vr_gym_b200 import capi
+    a_pin = [capi.PinnedArray((E, 7), np.float32) for _ in range(2)]          # page-locked action buffers (a caller writes its
+    for i, p in enumerate(a_pin):                                              # policy output here; results come back in the
+        p.array[...] = np.random.RandomState(100 + rank + i).uniform(-1, 1, (E, 7)).astype(np.float32)   # env's own pinned arrays)
+    a_host = [p.array for p in a_pin]
     env.step_host(a_host[0]); env.elapsed = 0
     barrier()
     t0 = time.perf_counter()

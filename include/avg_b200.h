@@ -54,10 +54,15 @@ int avg_reset_obs(AvgHandle* h, float* obs, void* stream);
  * (total_force_on_human, task_success flag).  Asynchronous on `stream`. */
 int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, float* info, void* stream);
 
-/* Same step with HOST buffers (what a NumPy caller like the reference's examples/random_actions.py holds): stages
- * through pinned memory, host->device copy of the actions, the step, device->host copy of obs/reward/done/info,
- * and returns after the results are in the host buffers. */
+/* Same step with HOST buffers (what a NumPy caller like the reference's examples/random_actions.py holds):
+ * host->device copy of the actions, the step, device->host copy of obs/reward/done/info, and returns after the
+ * results are in the host buffers.  Page-locked caller buffers (avg_alloc_host, cudaHostRegister, torch pin_memory)
+ * are copied in place; pageable ones are staged through pinned memory owned by the handle. */
 int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, float* info);
+/* Page-locked host memory for the buffers of avg_step_host (replaces nothing in the reference: PyBullet returns
+ * fresh Python tuples; a batched caller wants stable I/O arrays). */
+int avg_alloc_host(size_t nbytes, void** out);
+int avg_free_host(void* p);
 
 /* Parity / debug taps (replace getContactPoints and the per-term prints of the reference): when enabled the step
  * also records the last sub-step's contact points and the reward terms. */

@@ -1,4 +1,6 @@
 """Size-independent properties of the CUDA path at BASELINE sizes, ragged sizes, and the host-buffer entry point."""
+import os
+
 import numpy as np
 import pytest
 
@@ -118,3 +120,31 @@ def test_unknown_ids():
         make("FeedingPR2-v0", num_envs=1)
     with pytest.raises(KeyError):
         make("NoSuchEnv-v0", num_envs=1)
+
+
+def test_separating_axis_cache_only_skips_work(torch_cuda):
+    """The collide kernel's temporal cache (pair -> last separating direction) may reject a candidate early but must
+    never change a contact: trajectories with the cache disabled (AVG_DBG bit 4) are bit-identical."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n, T = 4096, 12
+    rng = np.random.RandomState(5)
+    acts = rng.uniform(-1, 1, (T, n, 7)).astype(np.float32)
+    out = []
+    for dbg in ("16", "0"):
+        os.environ["AVG_DBG"] = dbg
+        try:
+            env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=21)
+            env.sim.enable_debug(True)
+            env.reset()
+            ncont = 0
+            for t in range(T):
+                env.step(torch.as_tensor(acts[t], device="cuda"))
+                ncont += int(env.sim.get_contacts()[1].sum())
+            out.append((env.get_state().copy(), env.reward.cpu().numpy().copy(), ncont))
+            env.close()
+        finally:
+            os.environ.pop("AVG_DBG", None)
+    assert out[0][2] == out[1][2] and out[0][2] > 100            # contacts happened and are the same in number
+    assert np.array_equal(out[0][0][:, :64], out[1][0][:, :64])  # q, qd bit-identical
+    assert np.array_equal(out[0][1], out[1][1])

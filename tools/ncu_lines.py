@@ -32,6 +32,7 @@ agg = {}
 tot_s = tot_i = 0
 for r in rows[hi + 1:]:
     if len(r) <= iins: continue
+    if r[ia] == "Address": break          # the page repeats itself per matching result: keep the first
     a = int(r[ia], 16)
     if base is None: base = a
     key = line_of.get(a - base)
