@@ -8,14 +8,14 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 7
+AVG_VERSION = 8
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
     ("parent", "<i4"), ("jtype", "<i4"), ("dof", "<i4"), ("qidx", "<i4"),
     ("ta_pos", "<f4", 3), ("ta_quat", "<f4", 4), ("axis", "<f4", 3), ("tb_pos", "<f4", 3), ("tb_quat", "<f4", 4),
     ("mass", "<f4"), ("inertia", "<f4", 3), ("gravity", "<f4", 3), ("anc_mask", "<u4"),
-    ("ref_body", "<i4"), ("ref_joint", "<i4"), ("pad", "<i4"),
+    ("ref_body", "<i4"), ("ref_joint", "<i4"), ("sub_end", "<i4"),
 ])
 DOF_DT = np.dtype([
     ("body", "<i4"), ("flags", "<u4"), ("lower", "<f4"), ("upper", "<f4"), ("rep_lower", "<f4"), ("rep_upper", "<f4"),
@@ -94,6 +94,11 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
             p = scene.bodies[p].parent
         r["anc_mask"] = mask
         r["ref_body"] = scene.multibodies[b.art].ref_body; r["ref_joint"] = b.ref_joint
+    # depth-first order: the subtree of body i is the contiguous range [i, sub_end) (the dynamics kernel sums over it)
+    for i in range(nb):
+        sub = [j for j in range(nb) if (int(bodies[j]["anc_mask"]) >> i) & 1]
+        assert sub == list(range(i, i + len(sub))), f"bodies are not in depth-first order at body {i}: {sub}"
+        bodies[i]["sub_end"] = i + len(sub)
     dofs = np.zeros(len(scene.dofs), dtype=DOF_DT)
     for i, d in enumerate(scene.dofs):
         for k in ("body", "flags", "lower", "upper", "rep_lower", "rep_upper", "kp", "kd", "max_force", "action",

@@ -127,6 +127,10 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
         if (bodies[b].jtype != AVG_JOINT_FREE && (bodies[b].dof != b || b >= mh->n_jdof))
             return fail(h, -4, "avg_upload_model: 1-DoF joint bodies must come first with dof == body index");
         if (bodies[b].parent >= b) return fail(h, -4, "avg_upload_model: parents must precede children");
+        int cnt = 0; bool contiguous = true;
+        for (int j = 0; j < mh->n_body; ++j)
+            if ((bodies[j].anc_mask >> b) & 1u) { cnt++; if (j < b || j >= bodies[b].sub_end) contiguous = false; }
+        if (!contiguous || cnt != bodies[b].sub_end - b) return fail(h, -4, "avg_upload_model: bodies must be in depth-first order (sub_end)");
     }
     int na = mh->n_action_robot + mh->n_action_human, no = mh->n_obs_robot + mh->n_obs_human;
     if (h->task >= 0 && (h->n_act != na || h->n_obs != no || h->task != mh->task))

@@ -105,6 +105,7 @@ struct __align__(16) SmDyn {
     float bp[32][3]; float bq[32][4];
     float freeInv[2][12];
     float tmp[32];
+    float4 sub[kMaxJ][4];                  // per joint body: inertia about the reference point (10 floats) + bias force (6)
     float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC];
     int c_sa[kMaxC], c_sb[kMaxC];
 };
@@ -706,36 +707,6 @@ struct LaneDyn {
     uint32_t anc;     // ancestor-or-self mask
 };
 
-// Jacobian entry of lane `lane` (dof) for "velocity of world point r on `body` along n", sign applied.
-template <class SM>
-__device__ __noinline__ float jac_point_lane(const KM& m, const SM& s, const LaneDyn& L, int lane, int nj, int body,
-                                                V3 r, V3 n, V3 ref) {
-    if (body < 0) return 0.0f;
-    const AvgBody* B = &m.body[body];
-    if (B->jtype == AVG_JOINT_FREE) {
-        int k = lane - B->dof;
-        if (k < 0 || k >= 6) return 0.0f;
-        if (k < 3) return k == 0 ? n.x : (k == 1 ? n.y : n.z);
-        V3 rn = cross(r - ld3(s.bp[body]), n);
-        return k == 3 ? rn.x : (k == 4 ? rn.y : rn.z);
-    }
-    if (lane >= nj) return 0.0f;
-    if (!((B->anc_mask >> lane) & 1u)) return 0.0f;
-    return dot(L.S.a, cross(r - ref, n)) + dot(L.S.l, n);
-}
-__device__ __forceinline__ float jac_ang_lane(const KM& m, const LaneDyn& L, int lane, int nj, int body, V3 n) {
-    if (body < 0) return 0.0f;
-    const AvgBody* B = &m.body[body];
-    if (B->jtype == AVG_JOINT_FREE) {
-        int k = lane - B->dof;
-        if (k < 3 || k >= 6) return 0.0f;
-        return k == 3 ? n.x : (k == 4 ? n.y : n.z);
-    }
-    if (lane >= nj) return 0.0f;
-    if (!((B->anc_mask >> lane) & 1u)) return 0.0f;
-    return dot(L.S.a, n);
-}
-
 }  // namespace
 
 #define AVG_KERNEL_PREAMBLE(SMTYPE)                                                             \
@@ -943,21 +914,27 @@ avg_dynamics_kernel(AvgStepArgs a) {
         V3 n = -(Iw * (h->ang_damp + h->ang_damp * norm(w)));
         fb = fb - mksv(n + cross(c, f), f);
     }
-    // ---- subtree sums (composite inertia, bias force) ------------------------------------------------------------
+    // ---- subtree sums (composite inertia, bias force).  Bodies are in depth-first order, so the subtree of body i is
+    //      the lane range [i, sub_end): every lane stages its 16 values in shared memory and adds up its own range ------
     Inertia Ic_sub = I; Sv f_sub = fb;
-#pragma unroll 1
-    for (int k = 0; k < nj; ++k) {
-        uint32_t mk = __shfl_sync(AVG_FULL, L.anc, k);
-        float m_k = __shfl_sync(AVG_FULL, I.m, k);
-        V3 h_k = shfl3(I.h, k);
-        float xx = __shfl_sync(AVG_FULL, I.xx, k), yy = __shfl_sync(AVG_FULL, I.yy, k), zz = __shfl_sync(AVG_FULL, I.zz, k);
-        float xy = __shfl_sync(AVG_FULL, I.xy, k), xz = __shfl_sync(AVG_FULL, I.xz, k), yz = __shfl_sync(AVG_FULL, I.yz, k);
-        Sv f_k = shflsv(fb, k);
-        if (k != lane && ((mk >> lane) & 1u) && is_joint) {
-            Ic_sub.m += m_k; Ic_sub.h = Ic_sub.h + h_k;
-            Ic_sub.xx += xx; Ic_sub.yy += yy; Ic_sub.zz += zz; Ic_sub.xy += xy; Ic_sub.xz += xz; Ic_sub.yz += yz;
-            f_sub = f_sub + f_k;
+    {
+        int sub_end = 0;
+        if (is_joint) {
+            sub_end = m.body[lane].sub_end;
+            s.sub[lane][0] = make_float4(I.m, I.h.x, I.h.y, I.h.z);
+            s.sub[lane][1] = make_float4(I.xx, I.yy, I.zz, I.xy);
+            s.sub[lane][2] = make_float4(I.xz, I.yz, fb.a.x, fb.a.y);
+            s.sub[lane][3] = make_float4(fb.a.z, fb.l.x, fb.l.y, fb.l.z);
         }
+        __syncwarp();
+        for (int j = lane + 1; j < sub_end; ++j) {
+            const float4 v0 = s.sub[j][0], v1 = s.sub[j][1], v2 = s.sub[j][2], v3 = s.sub[j][3];
+            Ic_sub.m += v0.x; Ic_sub.h.x += v0.y; Ic_sub.h.y += v0.z; Ic_sub.h.z += v0.w;
+            Ic_sub.xx += v1.x; Ic_sub.yy += v1.y; Ic_sub.zz += v1.z; Ic_sub.xy += v1.w;
+            Ic_sub.xz += v2.x; Ic_sub.yz += v2.y; f_sub.a.x += v2.z; f_sub.a.y += v2.w;
+            f_sub.a.z += v3.x; f_sub.l.x += v3.y; f_sub.l.y += v3.z; f_sub.l.z += v3.w;
+        }
+        __syncwarp();
     }
     Sv F = inertia_mul(Ic_sub, L.S);          // composite inertia times own motion subspace
     float Cb = dot(L.S, f_sub);               // generalized bias force of this lane's joint
@@ -1080,46 +1057,59 @@ avg_dynamics_kernel(AvgStepArgs a) {
     // free-body lanes: which free body, which component
     int fbi = 0, fk = -1, fbase = lane;
     if (lane >= nj && lane < nd) { fk = lane - nj; while (fk >= 6) { fk -= 6; fbi++; } fbase = lane - fk; }
+    // This lane's column of the Jacobian of (linear velocity of world point r on `body`, angular velocity of `body`):
+    // every row through that point is a dot product with it, so the six weld rows cost two evaluations and a contact
+    // (normal + friction) two more.
+    auto jcol = [&](int body, V3 r, V3& cl, V3& cw) {
+        cl = mk3(0, 0, 0); cw = mk3(0, 0, 0);
+        if (body < 0) return;
+        const AvgBody* B = &m.body[body];
+        if (B->jtype == AVG_JOINT_FREE) {
+            const int k = lane - B->dof;
+            if (k >= 0 && k < 3) cl = mk3(k == 0, k == 1, k == 2);
+            else if (k >= 3 && k < 6) { cw = mk3(k == 3, k == 4, k == 5); cl = cross(cw, r - ld3(s.bp[body])); }
+        } else if (lane < nj && ((B->anc_mask >> lane) & 1u)) { cw = L.S.a; cl = L.S.l + cross(L.S.a, r - ref); }
+    };
+    V3 wcl, wcw;
+    {
+        V3 la, wa, lb, wb;
+        jcol(h->weld_body_a, wpa, la, wa); jcol(h->weld_body_b, wpb, lb, wb);
+        wcl = la - lb; wcw = wa - wb;
+    }
 #pragma unroll 1
     for (int d = 0; d < ndense; ++d) {
         float jl, tgt, lo, hi, mu = 0.0f;
         int par = -1;
         if (d < 6) {
-            const V3 e = mk3((d % 3) == 0, (d % 3) == 1, (d % 3) == 2);
-            float err;
-            if (d < 3) {
-                jl = jac_point_lane(m, s, L, lane, nj, h->weld_body_a, wpa, e, ref) - jac_point_lane(m, s, L, lane, nj, h->weld_body_b, wpb, e, ref);
-                err = dot(perr, e);
-            } else {
-                jl = jac_ang_lane(m, L, lane, nj, h->weld_body_a, e) - jac_ang_lane(m, L, lane, nj, h->weld_body_b, e);
-                err = dot(rotv, e);
-            }
+            const int ax = d < 3 ? d : d - 3;
+            const V3 c = d < 3 ? wcl : wcw, ev = d < 3 ? perr : rotv;
+            jl = ax == 0 ? c.x : (ax == 1 ? c.y : c.z);
+            const float err = ax == 0 ? ev.x : (ax == 1 ? ev.y : ev.z);
             tgt = -err * h->erp / dt; lo = -maxi; hi = maxi;
-        } else if (d < 6 + nc) {
-            const int ci = d - 6;
-            const V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
-            const int ba = m.shape[s.c_sa[ci]].body, bb = m.shape[s.c_sb[ci]].body;
-            jl = jac_point_lane(m, s, L, lane, nj, ba, pa, n, ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, n, ref);
-            const float dist = s.c_dist[ci];
-            tgt = dist > 0 ? -dist / dt : -dist * h->erp / dt;       // speculative margin / ERP push
-            lo = 0.0f; hi = 1e30f;
         } else {
-            const int ci = d - 6 - nc;
+            const bool fric = d >= 6 + nc;
+            const int ci = fric ? d - 6 - nc : d - 6;
             const V3 pa = ld3(s.c_pa[ci]), pb = ld3(s.c_pb[ci]), n = ld3(s.c_n[ci]);
             const int sa = s.c_sa[ci], sb = s.c_sb[ci];
-            const int ba = m.shape[sa].body, bb = m.shape[sb].body;
-            const float jx = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(1, 0, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(1, 0, 0), ref);
-            const float jy = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 1, 0), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 1, 0), ref);
-            const float jz = jac_point_lane(m, s, L, lane, nj, ba, pa, mk3(0, 0, 1), ref) - jac_point_lane(m, s, L, lane, nj, bb, pb, mk3(0, 0, 1), ref);
-            const V3 vrel = mk3(warp_sum(jx * qd), warp_sum(jy * qd), warp_sum(jz * qd));
-            const V3 lat = vrel - n * dot(vrel, n);
-            const float ll = norm(lat);
-            V3 t;
-            if (ll > 1e-6f) t = lat * (1.0f / ll);
-            else if (fabsf(n.z) > 0.70710678f) { const float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
-            else { const float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
-            jl = t.x * jx + t.y * jy + t.z * jz;
-            tgt = 0.0f; lo = 0.0f; hi = 0.0f; mu = m.shape[sa].friction * m.shape[sb].friction; par = first_contact_row + ci;
+            V3 la, wa, lb, wb;
+            jcol(m.shape[sa].body, pa, la, wa); jcol(m.shape[sb].body, pb, lb, wb);
+            const V3 cc = la - lb;
+            if (!fric) {
+                jl = dot(cc, n);
+                const float dist = s.c_dist[ci];
+                tgt = dist > 0 ? -dist / dt : -dist * h->erp / dt;       // speculative margin / ERP push
+                lo = 0.0f; hi = 1e30f;
+            } else {
+                const V3 vrel = mk3(warp_sum(cc.x * qd), warp_sum(cc.y * qd), warp_sum(cc.z * qd));
+                const V3 lat = vrel - n * dot(vrel, n);
+                const float ll = norm(lat);
+                V3 t;
+                if (ll > 1e-6f) t = lat * (1.0f / ll);
+                else if (fabsf(n.z) > 0.70710678f) { const float k = rsqrtf(n.y * n.y + n.z * n.z); t = mk3(0, -n.z * k, n.y * k); }
+                else { const float k = rsqrtf(n.x * n.x + n.y * n.y); t = mk3(-n.y * k, n.x * k, 0); }
+                jl = dot(cc, t);
+                tgt = 0.0f; lo = 0.0f; hi = 0.0f; mu = m.shape[sa].friction * m.shape[sb].friction; par = first_contact_row + ci;
+            }
         }
         // W = M^-1 J^T: joint lanes use their register column of M^-1, free-body lanes the inverse mass / inertia
         float w = 0.0f;

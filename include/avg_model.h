@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 7u
+#define AVG_VERSION 8u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -50,7 +50,7 @@ typedef struct AvgBody {          /* 32 x 4 bytes */
     uint32_t anc_mask;            /* bit k: body k is this body or one of its ancestors                     */
     int32_t  ref_body;
     int32_t  ref_joint;
-    int32_t  pad;
+    int32_t  sub_end;             /* bodies are in depth-first order: the subtree of body i is [i, sub_end)      */
 } AvgBody;
 
 typedef struct AvgDof {           /* 16 x 4 bytes, one per velocity dof */

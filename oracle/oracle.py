@@ -21,8 +21,8 @@ _IP = ctypes.POINTER(ctypes.c_int)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "avg_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "avg_oracle.c"), os.path.join(_HERE, "..", "include", "avg_model.h")]
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(p) for p in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB
 
