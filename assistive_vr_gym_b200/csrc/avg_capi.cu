@@ -11,6 +11,7 @@
 #include "avg_kernels.h"
 
 struct AvgHandle {
+    int slot = -1;                                     // row of the kernels' constant-memory model table
     int device = 0;
     int n_env = 0;
     int n_act = 0, n_obs = 0, task = -1;
@@ -39,6 +40,7 @@ struct AvgHandle {
 };
 
 static std::string g_create_error;
+static bool g_slot_used[AVG_K_MAX_HANDLES];
 
 #define AVG_CHECK(h, call)                                                                     \
     do {                                                                                       \
@@ -67,11 +69,15 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     if (device < 0 || device >= count) return fail(nullptr, -1, "avg_create: device ordinal out of range");
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    int slot = -1;
+    for (int i = 0; i < AVG_K_MAX_HANDLES && slot < 0; ++i) if (!g_slot_used[i]) slot = i;
+    if (slot < 0) return fail(nullptr, -5, "avg_create: too many live handles in this process (AVG_K_MAX_HANDLES)");
     AvgHandle* h = new AvgHandle();
-    h->device = device; h->n_env = n_env;
+    h->device = device; h->n_env = n_env; h->slot = slot; g_slot_used[slot] = true;
     if (cudaMalloc(&h->d_env, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env) != cudaSuccess ||
         cudaMalloc(&h->d_variant, sizeof(int32_t) * (size_t)n_env) != cudaSuccess ||
         cudaMalloc(&h->d_scratch, sizeof(float) * AVG_S_STRIDE * (size_t)n_env) != cudaSuccess) {
+        g_slot_used[slot] = false;
         delete h;
         return fail(nullptr, -2, "avg_create: cudaMalloc of the state arena failed");
     }
@@ -107,6 +113,7 @@ int avg_destroy(AvgHandle* h) {
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->slot >= 0) g_slot_used[h->slot] = false;
     delete h;
     return 0;
 }
@@ -140,6 +147,9 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     AVG_CHECK(h, cudaMalloc(&h->d_model[variant], nbytes));
     AVG_CHECK(h, cudaMemcpy(h->d_model[variant], blob, nbytes, cudaMemcpyHostToDevice));
     h->hdr[variant] = *mh; h->have[variant] = true;
+    AVG_CHECK(h, avg_register_model(h->slot, variant, h->d_model[variant], mh));
+    if (variant == 0)                                  /* variants without their own model fall back to variant 0 */
+        for (int v = 1; v < AVG_K_MAX_VARIANTS; ++v) if (!h->have[v]) AVG_CHECK(h, avg_register_model(h->slot, v, h->d_model[0], mh));
     if (h->task >= 0 && h->substeps != mh->substeps && variant != 0)
         return fail(h, -4, "avg_upload_model: variants of one handle must share frame_skip");
     h->task = mh->task; h->n_act = na; h->n_obs = no; h->substeps = mh->substeps;
@@ -183,6 +193,7 @@ float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 static int fill_args(AvgHandle* h, AvgStepArgs& a) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
+    a.slot = h->slot;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
     if ((a.dbg & 32) && !h->d_hist) {

@@ -69,6 +69,10 @@ struct KM {                                // device view of a ModelBlob
     const float* mlp;
 };
 
+// Section pointers per (handle slot, variant), resolved on the host when a model is uploaded: a warp reads its model
+// view with one constant-memory access instead of chasing header offsets through global memory.
+__constant__ KM c_models[AVG_K_MAX_HANDLES][AVG_K_MAX_VARIANTS];
+
 __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     KM m;
     m.h = reinterpret_cast<const AvgModelHeader*>(blob);
@@ -716,7 +720,7 @@ struct LaneDyn {
     if (e >= a.n_env) return;                                                                    \
     SMTYPE& s = reinterpret_cast<SMTYPE*>(smem_raw)[warp];                                       \
     const int variant = a.variant ? a.variant[e] : 0;                                            \
-    const KM m = open_model(a.models[variant]);                                                  \
+    const KM m = c_models[a.slot][variant];                                                      \
     const AvgModelHeader* h = m.h;                                                               \
     float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;                                            \
     float* scr = a.scratch + (size_t)e * AVG_S_STRIDE;                                           \
@@ -731,7 +735,7 @@ avg_prologue_kernel(AvgStepArgs a) {
     const int e = blockIdx.x * (blockDim.x >> 5) + warp;
     if (e >= a.n_env) return;
     const int variant = a.variant ? a.variant[e] : 0;
-    const KM m = open_model(a.models[variant]);
+    const KM m = c_models[a.slot][variant];
     const AvgModelHeader* h = m.h;
     float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
     int* scr_i = reinterpret_cast<int*>(a.scratch + (size_t)e * AVG_S_STRIDE);
@@ -786,6 +790,11 @@ avg_collide_kernel(AvgStepArgs a) {
     s.q[lane] = grec[AVG_E_Q + lane];
     __syncwarp();
     fk_warp(m, s, s.q, lane, h->n_body);
+    if (lane < h->n_body) {                  // the dynamics kernel of this sub-step reuses the poses
+        float4* gp = reinterpret_cast<float4*>(scr + AVG_S_POSE) + 2 * lane;
+        gp[0] = make_float4(s.bp[lane][0], s.bp[lane][1], s.bp[lane][2], 0.0f);
+        gp[1] = make_float4(s.bq[lane][0], s.bq[lane][1], s.bq[lane][2], s.bq[lane][3]);
+    }
     int nc = 0, overflow = 0, ncand = 0, nsep_out = 0;
     int* scr_i = reinterpret_cast<int*>(scr);
     float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
@@ -824,7 +833,13 @@ avg_dynamics_kernel(AvgStepArgs a) {
         s.c_dist[lane] = c[9]; s.c_sa[lane] = __float_as_int(c[10]); s.c_sb[lane] = __float_as_int(c[11]);
     }
     __syncwarp();
-    fk_warp(m, s, s.env + AVG_E_Q, lane, nb);
+    if (lane < nb) {                         // body poses: forward kinematics was done by the collide kernel
+        const float4* gp = reinterpret_cast<const float4*>(scr + AVG_S_POSE) + 2 * lane;
+        const float4 p4 = gp[0], q4 = gp[1];
+        s.bp[lane][0] = p4.x; s.bp[lane][1] = p4.y; s.bp[lane][2] = p4.z;
+        s.bq[lane][0] = q4.x; s.bq[lane][1] = q4.y; s.bq[lane][2] = q4.z; s.bq[lane][3] = q4.w;
+    }
+    __syncwarp();
     float* gJ = scr + AVG_S_J; float* gW = scr + AVG_S_W;
 
     // ---- per-lane body quantities ------------------------------------------------------------------------------
@@ -1622,6 +1637,24 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         }
     }
     return cudaGetLastError();
+}
+
+cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blob, const AvgModelHeader* hh) {
+    if (slot < 0 || slot >= AVG_K_MAX_HANDLES || variant < 0 || variant >= AVG_K_MAX_VARIANTS) return cudaErrorInvalidValue;
+    KM m;
+    m.h = reinterpret_cast<const AvgModelHeader*>(d_blob);
+    m.body = reinterpret_cast<const AvgBody*>(d_blob + hh->off_body);
+    m.dof = reinterpret_cast<const AvgDof*>(d_blob + hh->off_dof);
+    m.shape = reinterpret_cast<const AvgShape*>(d_blob + hh->off_shape);
+    m.vert = reinterpret_cast<const float*>(d_blob + hh->off_vert);
+    m.plane = reinterpret_cast<const float*>(d_blob + hh->off_plane);
+    m.pair = reinterpret_cast<const uint32_t*>(d_blob + hh->off_pair);
+    m.frame = reinterpret_cast<const AvgFrame*>(d_blob + hh->off_frame);
+    m.bps = reinterpret_cast<const AvgBpStatic*>(d_blob + hh->off_bps);
+    m.bpm = reinterpret_cast<const uint32_t*>(d_blob + hh->off_bpm);
+    m.bcap = reinterpret_cast<const float4*>(d_blob + hh->off_bcap);
+    m.mlp = hh->n_mlp > 0 ? reinterpret_cast<const float*>(d_blob + hh->off_mlp) : nullptr;
+    return cudaMemcpyToSymbol(c_models, &m, sizeof(KM), sizeof(KM) * ((size_t)slot * AVG_K_MAX_VARIANTS + variant));
 }
 
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream) {

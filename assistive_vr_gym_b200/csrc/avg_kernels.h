@@ -32,9 +32,13 @@
 #define AVG_S_W (AVG_S_J + 32 * AVG_S_MAXDENSE)
 #define AVG_S_SEP (AVG_S_W + 32 * AVG_S_MAXDENSE)     /* [3][AVG_S_NSEPMAX] float4: separation certificates, see collide_warp */
 #define AVG_S_NSEPMAX 32
-#define AVG_S_STRIDE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)
+#define AVG_S_POSE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)   /* [32][8] body poses (pos, pad, quat) from the collide kernel's forward kinematics */
+#define AVG_S_STRIDE (AVG_S_POSE + 8 * 32)
+
+#define AVG_K_MAX_HANDLES 16   /* handles per process that can hold models at the same time (constant-memory table slots) */
 
 struct AvgStepArgs {
+    int slot;                                          // row of the constant-memory model table (avg_register_model)
     const unsigned char* models[AVG_K_MAX_VARIANTS];   // device ModelBlobs
     const int32_t* variant;                            // [n_env] model variant per environment (may be null)
     float* env;                                        // [n_env][AVG_ENV_STRIDE]
@@ -57,3 +61,5 @@ int avg_kernels_per_step(int substeps);
 cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
+/* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */
+cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blob, const AvgModelHeader* host_header);
