@@ -35,7 +35,7 @@ struct AvgHandle {
     uint8_t* d_done = nullptr;
     cudaStream_t stream = nullptr;
     long long launches = 0;
-    unsigned long long* d_hist = nullptr;              // AVG_DBG & 32 (development aid)
+    AvgNpItem* d_npq = nullptr; int* d_npc = nullptr; int np_capacity = 0, np_phase = 0;   // narrowphase work queue
     std::string err;
 };
 
@@ -84,6 +84,12 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
     cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
     cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
+    h->np_capacity = n_env * 4 + 4096;                 /* ~3 candidates per environment and sub-step survive the culls; overflow is flagged */
+    if (cudaMalloc(&h->d_npq, sizeof(AvgNpItem) * (size_t)h->np_capacity) != cudaSuccess || cudaMalloc(&h->d_npc, 2 * sizeof(int)) != cudaSuccess) {
+        g_slot_used[slot] = false; delete h;
+        return fail(nullptr, -2, "avg_create: cudaMalloc of the narrowphase queue failed");
+    }
+    cudaMemset(h->d_npc, 0, 2 * sizeof(int));
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     *out = h;
     return 0;
@@ -93,21 +99,7 @@ int avg_destroy(AvgHandle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    if (h->d_hist) {
-        static unsigned long long hh[3 * 32 * 256];
-        cudaMemcpy(hh, h->d_hist, sizeof(hh), cudaMemcpyDeviceToHost);
-        unsigned long long tot[3] = {0, 0, 0};
-        for (int k = 0; k < 3; ++k) for (int i = 0; i < 32 * 256; ++i) tot[k] += hh[k * 8192 + i];
-        fprintf(stderr, "[avg narrowphase histogram] candidates %llu, GJK calls %llu, GJK iterations %llu\n", tot[0], tot[1], tot[2]);
-        for (int r = 0; r < 25; ++r) {
-            int best = -1; unsigned long long bv = 0;
-            for (int i = 0; i < 8192; ++i) if (hh[2 * 8192 + i] + hh[i] > bv) { bv = hh[2 * 8192 + i] + hh[i]; best = i; }
-            if (best < 0) break;
-            fprintf(stderr, "  pair (%d, %d): candidates %llu, GJK calls %llu, iterations %llu\n", best >> 8, best & 255, hh[best], hh[8192 + best], hh[2 * 8192 + best]);
-            hh[best] = 0; hh[2 * 8192 + best] = 0;
-        }
-        cudaFree(h->d_hist);
-    }
+    cudaFree(h->d_npq); cudaFree(h->d_npc);
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
@@ -196,11 +188,7 @@ static int fill_args(AvgHandle* h, AvgStepArgs& a) {
     a.slot = h->slot;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
-    if ((a.dbg & 32) && !h->d_hist) {
-        cudaMalloc(&h->d_hist, sizeof(unsigned long long) * 3 * 32 * 256);
-        cudaMemset(h->d_hist, 0, sizeof(unsigned long long) * 3 * 32 * 256);
-    }
-    a.dbg_hist = h->d_hist;
+    a.np_queue = h->d_npq; a.np_count = h->d_npc; a.np_capacity = h->np_capacity; a.np_phase = h->np_phase;
     a.contacts = h->debug ? h->d_contacts : nullptr;
     a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
     a.terms = h->debug ? h->d_terms : nullptr;
@@ -225,6 +213,7 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     int rc = fill_args(h, a); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
+    h->np_phase = a.np_phase;
     h->launches += avg_kernels_per_step(h->substeps);
     return 0;
 }

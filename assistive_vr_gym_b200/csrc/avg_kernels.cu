@@ -101,8 +101,6 @@ struct __align__(16) SmCollide {
     float4 sep[3][AVG_S_NSEPMAX];          // separation certificates of the previous sub-step (see collide_warp)
     float sq[kMaxMS][4];                   // world orientation of the moving shapes
     uint8_t near_idx[256];                 // static shapes (index) that overlap the union box of the moving shapes
-    float c_pa[kMaxC][3], c_pb[kMaxC][3], c_n[kMaxC][3], c_dist[kMaxC], c_lam[kMaxC];
-    int c_sa[kMaxC], c_sb[kMaxC];
 };
 struct __align__(16) SmDyn {
     float env[AVG_ENV_STRIDE];
@@ -416,7 +414,8 @@ __device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa,
 }
 
 template <class SM>
-__device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& overflow, int& ncand_out, int nsep, float* gsep_f, int& nsep_out, int dbg, unsigned long long* hist) {
+__device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& ncontact, int& overflow, int& ncand_out, int nsep, float* gsep_f, int& nsep_out,
+                             AvgNpItem* np_queue, int* np_count, int np_capacity, int dbg) {
     const AvgModelHeader* h = m.h;
     const int nms = h->n_mshape;
     // world pose + AABB of the moving shapes
@@ -608,98 +607,89 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int& ncontact, int& o
         ncand = nk;
         __syncwarp();
     }
-    // narrowphase: one lane per candidate, results compacted in pair order.
-    // Separation certificates (temporal coherence).  Most candidates that survive the culls are close but not touching,
-    // sub-step after sub-step (hand against its own finger tips, arm over the armrest).  When GJK proves a pair
-    // separated along a direction v by at least g (support-plane bound, the predicate of its own early-out), the arena
-    // remembers, in A's frame, v, g and the pose of B relative to A.  Next sub-step the pair is rejected
-    //   (1) without touching the shapes when g minus a bound on how far B's points can have moved in A's frame
+    // Hand-off to the narrowphase kernel, with separation certificates (temporal coherence).
+    // Most candidates that survive the culls are close but not touching, sub-step after sub-step (hand against its own
+    // finger tips, arm over the armrest).  When GJK proves a pair separated along a direction v by at least g
+    // (support-plane bound, the predicate of its own early-out), the arena remembers, in A's frame, v, g and the pose of
+    // B relative to A.  Next sub-step the pair is rejected
+    //   (1) here, without touching the shapes, when g minus a bound on how far B's points can have moved in A's frame
     //       (translation + chord of the rotation x bounding radius) still exceeds the contact distance, else
-    //   (2) by one support-plane test along the remembered direction, which renews the certificate.
+    //   (2) in the narrowphase kernel by one support-plane test along the remembered direction (renews the certificate).
     // Both are sufficient conditions for "no contact"; a pair that fails them runs the full GJK, so certificates can
-    // only skip work, never change a contact.
-    int nc = 0, nnew = 0;
-    if (dbg & 1) ncand = 0;
+    // only skip work, never change a contact.  Everything not rejected by (1) is queued: one work item per pair for the
+    // narrowphase kernel (one THREAD per item there, instead of one lane of an otherwise idle warp here), with a result
+    // slot in pair order and a slot of the new certificate list to fill in.
+    int ncarry = 0, nq = 0;
     float4* gsep = reinterpret_cast<float4*>(gsep_f);
-    for (int base = 0; base < ncand; base += 32) {
-        int ci = base + lane;
-        bool hit = false, have_sep = false;
-        V3 pa, pb, n; float d = 0; int a = 0, b = 0;
-        uint32_t pr = 0;
+    uint32_t qpair[2] = {0, 0}; int qslot[2] = {-1, -1}; float4 qhint[2];
+    if (dbg & 1) ncand = 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int ci = lane + 32 * t;
+        bool carried = false, queued = false;
         float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0;
+        qhint[t] = k0;
         if (ci < ncand) {
-            pr = s.cand[ci];
-            a = pr & 0xffff; b = pr >> 16;
-            WShape A, B;
-            load_wshape(m, s, a, A); load_wshape(m, s, b, B);
-            const float thr = fminf(A.s->thr, B.s->thr);
-            bool culled = false;
-            int gi = 0, how = 0;
-            if (B.s->type != AVG_SHAPE_PLANE) {
-                const Q4 qa = ldq(s.sq[a]);
-                const Q4 qb = b < nms ? ldq(s.sq[b]) : ldq(B.s->quat);
-                const V3 prel = qrot_inv(qa, B.p - A.p);
-                const Q4 qrel = qmul(qconj(qa), qb);
-                const float md = thr + A.s->margin + B.s->margin;
+            const uint32_t pr = s.cand[ci];
+            const int a = pr & 0xffff, b = pr >> 16;
+            const AvgShape* SA = &m.shape[a]; const AvgShape* SB = &m.shape[b];
+            queued = true; qpair[t] = pr;
+            if (SB->type != AVG_SHAPE_PLANE) {
                 int f = -1;
                 for (int e = 0; e < nsep; ++e) if (__float_as_uint(s.sep[0][e].w) == pr) f = e;
                 if (f >= 0) {
                     const float4 e0 = s.sep[0][f], e1 = s.sep[1][f], e2 = s.sep[2][f];
-                    const V3 dp = prel - mk3(e1.x, e1.y, e1.z);
-                    const float sg = (qrel.x * e2.x + qrel.y * e2.y + qrel.z * e2.z + qrel.w * e2.w) < 0.0f ? -1.0f : 1.0f;
-                    const float dx = qrel.x - sg * e2.x, dy = qrel.y - sg * e2.y, dz = qrel.z - sg * e2.z, dw = qrel.w - sg * e2.w;
-                    const float chord = 2.0f * sqrtf(dx * dx + dy * dy + dz * dz + dw * dw);     // >= 2 sin(angle / 2)
-                    const float4 c0 = __ldg(&m.bcap[2 * b]), c1 = __ldg(&m.bcap[2 * b + 1]);
-                    const V3 o = b < nms ? mk3(0, 0, 0) : ld3(B.s->pos);
-                    const float rb = fmaxf(norm(mk3(c0.x, c0.y, c0.z) - o), norm(mk3(c1.x, c1.y, c1.z) - o)) + c0.w;
-                    if (e1.w - (norm(dp) + chord * rb) > md + 1e-5f) { culled = true; have_sep = true; k0 = e0; k1 = e1; k2 = e2; how = 1; }
-                    else {
-                        const V3 v = qrot(qa, mk3(e0.x, e0.y, e0.z));
-                        const V3 w = support(A, -v) - support(B, v);
-                        const float vv = dot(v, v), vw = dot(v, w);
-                        if (vw > 0.0f && vw * vw > md * md * vv) {
-                            culled = true; have_sep = true; how = 2;
-                            k0 = e0; k1 = make_float4(prel.x, prel.y, prel.z, vw * rsqrtf(vv)); k2 = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
-                        }
+                    qhint[t] = e0;
+                    if (e1.w > 0.0f) {
+                        const Q4 qa = ldq(s.sq[a]);
+                        const Q4 qb = b < nms ? ldq(s.sq[b]) : ldq(SB->quat);
+                        const V3 pbw = b < nms ? ld3(s.sp[b]) : ld3(SB->pos);
+                        const V3 prel = qrot_inv(qa, pbw - ld3(s.sp[a]));
+                        const Q4 qrel = qmul(qconj(qa), qb);
+                        const float md = fminf(SA->thr, SB->thr) + SA->margin + SB->margin;
+                        const V3 dp = prel - mk3(e1.x, e1.y, e1.z);
+                        const float sg = (qrel.x * e2.x + qrel.y * e2.y + qrel.z * e2.z + qrel.w * e2.w) < 0.0f ? -1.0f : 1.0f;
+                        const float dx = qrel.x - sg * e2.x, dy = qrel.y - sg * e2.y, dz = qrel.z - sg * e2.z, dw = qrel.w - sg * e2.w;
+                        const float chord = 2.0f * sqrtf(dx * dx + dy * dy + dz * dz + dw * dw);     // >= 2 sin(angle / 2)
+                        const float4 c0 = __ldg(&m.bcap[2 * b]), c1 = __ldg(&m.bcap[2 * b + 1]);
+                        const V3 o = b < nms ? mk3(0, 0, 0) : ld3(SB->pos);
+                        const float rb = fmaxf(norm(mk3(c0.x, c0.y, c0.z) - o), norm(mk3(c1.x, c1.y, c1.z) - o)) + c0.w;
+                        if (e1.w - (norm(dp) + chord * rb) > md + 1e-5f) { carried = true; queued = false; k0 = e0; k1 = e1; k2 = e2; }
                     }
                 }
-                if (!culled) {
-                    V3 sepv = mk3(0, 0, 0); float sepgap = 0.0f;
-                    hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, have_sep, gi);
-                    if (have_sep) {
-                        const V3 va = qrot_inv(qa, sepv);
-                        k0 = make_float4(va.x, va.y, va.z, __uint_as_float(pr));
-                        k1 = make_float4(prel.x, prel.y, prel.z, sepgap); k2 = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
-                    }
-                }
-            } else {
-                V3 sepv; float sepgap; bool hs;
-                hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, hs, gi);
-            }
-            if (hist) {
-                const int k = (a & 31) * 256 + (b & 255);
-                atomicAdd(hist + k, 1ull); if (how == 2) atomicAdd(hist + 8192 + k, 1ull); atomicAdd(hist + 16384 + k, (unsigned long long)gi);
             }
         }
-        unsigned bal = __ballot_sync(AVG_FULL, hit);
-        if (hit) {
-            int slot = nc + __popc(bal & ((1u << lane) - 1));
-            if (slot < kMaxC) {
-                st3(s.c_pa[slot], pa); st3(s.c_pb[slot], pb); st3(s.c_n[slot], n);
-                s.c_dist[slot] = d; s.c_lam[slot] = 0; s.c_sa[slot] = a; s.c_sb[slot] = b;
-            }
-        }
-        nc += __popc(bal);
-        const unsigned bsep = __ballot_sync(AVG_FULL, have_sep);
-        if (have_sep) {
-            const int slot = nnew + __popc(bsep & ((1u << lane) - 1));
+        const unsigned bc = __ballot_sync(AVG_FULL, carried), bq = __ballot_sync(AVG_FULL, queued);
+        if (carried) {
+            const int slot = ncarry + __popc(bc & ((1u << lane) - 1));
             if (slot < AVG_S_NSEPMAX) { gsep[slot] = k0; gsep[AVG_S_NSEPMAX + slot] = k1; gsep[2 * AVG_S_NSEPMAX + slot] = k2; }
         }
-        nnew += __popc(bsep);
+        if (queued) qslot[t] = nq + __popc(bq & ((1u << lane) - 1));
+        ncarry += __popc(bc); nq += __popc(bq);
     }
-    nsep_out = min(nnew, AVG_S_NSEPMAX);
-    if (nc > kMaxC) { overflow |= 1; nc = kMaxC; }
-    ncontact = nc;
+    ncarry = min(ncarry, AVG_S_NSEPMAX);
+    if (nq > AVG_S_NQMAX) { overflow |= 1; nq = AVG_S_NQMAX; }
+    // reserve queue space for the warp's items, write them, and seed the certificate slots they will fill in
+    int qbase = 0;
+    if (lane == 0 && nq > 0) qbase = atomicAdd(np_count, nq);
+    qbase = __shfl_sync(AVG_FULL, qbase, 0);
+    if (qbase + nq > np_capacity) { overflow |= 1; nq = max(0, min(nq, np_capacity - qbase)); }
+    int ncert = 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (qslot[t] >= 0 && qslot[t] < nq) {
+            const int cs = ncarry + qslot[t] < AVG_S_NSEPMAX ? ncarry + qslot[t] : -1;
+            if (cs >= 0) {                        // direction hint (or none), gap <= 0: not a certificate until the narrowphase says so
+                gsep[cs] = make_float4(qhint[t].x, qhint[t].y, qhint[t].z, __uint_as_float(0xffffffffu));
+                gsep[AVG_S_NSEPMAX + cs] = make_float4(0, 0, 0, 0);
+            }
+            AvgNpItem it; it.env = env_index; it.pair = qpair[t]; it.slot = qslot[t]; it.cert = cs;
+            np_queue[qbase + qslot[t]] = it;
+        }
+    }
+    ncert = min(ncarry + nq, AVG_S_NSEPMAX);
+    nsep_out = ncert;
+    ncontact = nq;                                // number of queued candidates (results arrive from the narrowphase kernel)
     __syncwarp();
 }
 
@@ -800,15 +790,75 @@ avg_collide_kernel(AvgStepArgs a) {
     float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
     int nsep = (a.dbg & 16) ? 0 : min(max(scr_i[AVG_S_NSEP], 0), AVG_S_NSEPMAX);
     if (lane < nsep) { s.sep[0][lane] = gsep[lane]; s.sep[1][lane] = gsep[AVG_S_NSEPMAX + lane]; s.sep[2][lane] = gsep[2 * AVG_S_NSEPMAX + lane]; }
-    if (!(a.dbg & 4)) collide_warp(m, s, lane, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.dbg, (a.dbg & 32) ? a.dbg_hist : nullptr);
-    if (lane < nc) {
-        float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
-        c[0] = s.c_pa[lane][0]; c[1] = s.c_pa[lane][1]; c[2] = s.c_pa[lane][2];
-        c[3] = s.c_pb[lane][0]; c[4] = s.c_pb[lane][1]; c[5] = s.c_pb[lane][2];
-        c[6] = s.c_n[lane][0]; c[7] = s.c_n[lane][1]; c[8] = s.c_n[lane][2];
-        c[9] = s.c_dist[lane]; c[10] = __int_as_float(s.c_sa[lane]); c[11] = __int_as_float(s.c_sb[lane]); c[12] = 0.0f;
+    if (!(a.dbg & 4)) collide_warp(m, s, lane, e, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.np_queue, a.np_count + (a.np_phase & 1),
+                                   a.np_capacity, a.dbg);
+    if (lane == 0) { scr_i[AVG_S_NQ] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
+}
+
+// =================================================================================================================
+// narrowphase: one thread per queued candidate pair (GJK / SAT / plane), results into the environment's result slots
+// =================================================================================================================
+namespace {
+__device__ __forceinline__ void np_load_shape(const KM& m, const float* scr, int si, WShape& w, Q4& q) {
+    const AvgShape* S = &m.shape[si];
+    w.s = S; w.verts = m.vert + 4 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
+    if (si < m.h->n_mshape) {
+        const float4* gp = reinterpret_cast<const float4*>(scr + AVG_S_POSE) + 2 * S->body;
+        const float4 p4 = gp[0], q4 = gp[1];
+        const Q4 bq = mkq(q4.x, q4.y, q4.z, q4.w);
+        w.p = mk3(p4.x, p4.y, p4.z) + qrot(bq, ld3(S->pos));
+        q = qnormalize(qmul(bq, ldq(S->quat)));
+    } else { w.p = ld3(S->pos); q = ldq(S->quat); }
+    const M3 r = qmat(q);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w.R[i] = r.m[i];
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+avg_narrow_kernel(AvgStepArgs a) {
+    const int count = min(a.np_count[a.np_phase & 1], a.np_capacity);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    if (tid == 0) a.np_count[(a.np_phase + 1) & 1] = 0;          // the counter of the next sub-step (idle during this kernel)
+    for (int i = tid; i < count; i += nthreads) {
+        const AvgNpItem it = a.np_queue[i];
+        const int variant = a.variant ? a.variant[it.env] : 0;
+        const KM m = c_models[a.slot][variant];
+        float* scr = a.scratch + (size_t)it.env * AVG_S_STRIDE;
+        const int sa = it.pair & 0xffff, sb = it.pair >> 16;
+        WShape A, B; Q4 qa, qb;
+        np_load_shape(m, scr, sa, A, qa); np_load_shape(m, scr, sb, B, qb);
+        const float thr = fminf(A.s->thr, B.s->thr);
+        float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
+        V3 pa = mk3(0, 0, 0), pb = pa, n = pa; float d = 0.0f;
+        bool hit = false, have_sep = false, done = false;
+        V3 sepv = mk3(0, 0, 0); float sepgap = 0.0f;
+        if (it.cert >= 0 && B.s->type != AVG_SHAPE_PLANE) {
+            const float4 hint = gsep[it.cert];
+            const V3 va = mk3(hint.x, hint.y, hint.z);
+            if (dot(va, va) > 0.0f) {                                // (2) support-plane test along the remembered direction
+                const V3 v = qrot(qa, va);
+                const V3 w = support(A, -v) - support(B, v);
+                const float vv = dot(v, v), vw = dot(v, w), md = thr + A.s->margin + B.s->margin;
+                if (vw > 0.0f && vw * vw > md * md * vv) { done = true; have_sep = true; sepv = v; sepgap = vw * rsqrtf(vv); }
+            }
+        }
+        if (!done) { int gi = 0; hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, have_sep, gi); }
+        if (it.cert >= 0) {
+            if (have_sep && sepgap > 0.0f) {
+                const V3 va = qrot_inv(qa, sepv), prel = qrot_inv(qa, B.p - A.p);
+                const Q4 qrel = qmul(qconj(qa), qb);
+                gsep[it.cert] = make_float4(va.x, va.y, va.z, __uint_as_float(it.pair));
+                gsep[AVG_S_NSEPMAX + it.cert] = make_float4(prel.x, prel.y, prel.z, sepgap);
+                gsep[2 * AVG_S_NSEPMAX + it.cert] = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
+            }                                                        // else the slot keeps the "no certificate" seed of the collide kernel
+        }
+        float4* r = reinterpret_cast<float4*>(scr + AVG_S_NPRES) + 4 * it.slot;
+        r[0] = make_float4(pa.x, pa.y, pa.z, pb.x);
+        r[1] = make_float4(pb.y, pb.z, n.x, n.y);
+        r[2] = make_float4(n.z, d, __int_as_float(sa), __int_as_float(sb));
+        r[3] = make_float4(hit ? 1.0f : 0.0f, 0, 0, 0);
     }
-    if (lane == 0) { scr_i[AVG_S_NC] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
 }
 
 // =================================================================================================================
@@ -823,14 +873,30 @@ avg_dynamics_kernel(AvgStepArgs a) {
     const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
     int* scr_i = reinterpret_cast<int*>(scr);
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
-    int ncontact = scr_i[AVG_S_NC];
     int overflow = 0;
-    if (lane < ncontact) {
-        const float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
-        s.c_pa[lane][0] = c[0]; s.c_pa[lane][1] = c[1]; s.c_pa[lane][2] = c[2];
-        s.c_pb[lane][0] = c[3]; s.c_pb[lane][1] = c[4]; s.c_pb[lane][2] = c[5];
-        s.c_n[lane][0] = c[6]; s.c_n[lane][1] = c[7]; s.c_n[lane][2] = c[8];
-        s.c_dist[lane] = c[9]; s.c_sa[lane] = __float_as_int(c[10]); s.c_sb[lane] = __float_as_int(c[11]);
+    // contacts: the hits among the narrowphase results, compacted in pair order; the list is also written to the arena
+    // for the solver (impulses) and the epilogue
+    int ncontact;
+    {
+        const int nq = scr_i[AVG_S_NQ];
+        const float4* r = reinterpret_cast<const float4*>(scr + AVG_S_NPRES) + 4 * lane;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
+        bool hit = false;
+        if (lane < nq) { hit = r[3].x != 0.0f; if (hit) { r0 = r[0]; r1 = r[1]; r2 = r[2]; } }
+        const unsigned bal = __ballot_sync(AVG_FULL, hit);
+        ncontact = __popc(bal);
+        if (ncontact > kMaxC) { overflow |= 1; ncontact = kMaxC; }
+        const int slot = __popc(bal & ((1u << lane) - 1));
+        if (hit && slot < kMaxC) {
+            s.c_pa[slot][0] = r0.x; s.c_pa[slot][1] = r0.y; s.c_pa[slot][2] = r0.z;
+            s.c_pb[slot][0] = r0.w; s.c_pb[slot][1] = r1.x; s.c_pb[slot][2] = r1.y;
+            s.c_n[slot][0] = r1.z; s.c_n[slot][1] = r1.w; s.c_n[slot][2] = r2.x;
+            s.c_dist[slot] = r2.y; s.c_sa[slot] = __float_as_int(r2.z); s.c_sb[slot] = __float_as_int(r2.w);
+            float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * slot;
+            c[0] = r0.x; c[1] = r0.y; c[2] = r0.z; c[3] = r0.w; c[4] = r1.x; c[5] = r1.y; c[6] = r1.z; c[7] = r1.w; c[8] = r2.x;
+            c[9] = r2.y; c[10] = r2.z; c[11] = r2.w; c[12] = 0.0f;
+        }
+        if (lane == 0) scr_i[AVG_S_NC] = ncontact;
     }
     __syncwarp();
     if (lane < nb) {                         // body poses: forward kinematics was done by the collide kernel
@@ -1560,7 +1626,7 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-int avg_kernels_per_step(int substeps) { return 2 + 3 * substeps; }
+int avg_kernels_per_step(int substeps) { return 2 + 4 * substeps; }
 
 // warps (= environments) per block, per kernel.  The solver uses one warp per block: its iteration count varies per
 // environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
@@ -1579,7 +1645,7 @@ struct KernelTimes {
 KernelTimes g_kt;
 }  // namespace
 
-cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
+cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream) {
     static bool configured = false;
     const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
     const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
@@ -1604,11 +1670,14 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
     if (g_kt.on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
     auto mark = [&]() { if (g_kt.on) cudaEventRecord(g_kt.ev[nev++], stream); };
     auto grid = [&](int wpb) { return (a.n_env + wpb - 1) / wpb; };
+    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 8);
     mark();
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
     mark();
     for (int f = 0; f < substeps; ++f) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+        avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
+        a.np_phase ^= 1;
         mark();
         if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);

@@ -21,6 +21,7 @@
 #define AVG_S_ITERS 7         /* solver iterations accumulated over the env-step            */
 #define AVG_S_NCAND 8         /* narrowphase candidates accumulated over the env-step (diagnostic) */
 #define AVG_S_NSEP 9          /* entries of the separating-axis cache (persists across sub-steps and env-steps) */
+#define AVG_S_NQ 10           /* candidates of this sub-step handed to the narrowphase kernel */
 #define AVG_S_QD 16           /* [32] velocities after the unconstrained update             */
 #define AVG_S_CONTACT 48      /* [AVG_MAX_CONTACT][14]: pa, pb, n, dist, shape a, shape b, impulse, pad */
 #define AVG_S_CONTACT_STRIDE 14
@@ -33,9 +34,19 @@
 #define AVG_S_SEP (AVG_S_W + 32 * AVG_S_MAXDENSE)     /* [3][AVG_S_NSEPMAX] float4: separation certificates, see collide_warp */
 #define AVG_S_NSEPMAX 32
 #define AVG_S_POSE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)   /* [32][8] body poses (pos, pad, quat) from the collide kernel's forward kinematics */
-#define AVG_S_STRIDE (AVG_S_POSE + 8 * 32)
+#define AVG_S_NPRES (AVG_S_POSE + 8 * 32)             /* [AVG_S_NQMAX][16] narrowphase results of the queued candidates: pa, pb, n, dist, shape a, shape b, hit */
+#define AVG_S_NQMAX 32
+#define AVG_S_STRIDE (AVG_S_NPRES + 16 * AVG_S_NQMAX)
 
 #define AVG_K_MAX_HANDLES 16   /* handles per process that can hold models at the same time (constant-memory table slots) */
+
+/* One candidate pair that survived the culls of the collide kernel and needs the exact narrowphase. */
+struct AvgNpItem {
+    int32_t env;
+    uint32_t pair;        /* moving shape a | other shape b << 16 */
+    int32_t slot;         /* result slot in the environment's AVG_S_NPRES array */
+    int32_t cert;         /* slot in the environment's certificate cache to fill in (or -1) */
+};
 
 struct AvgStepArgs {
     int slot;                                          // row of the constant-memory model table (avg_register_model)
@@ -54,11 +65,14 @@ struct AvgStepArgs {
     int n_env;
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
     int dbg;                                           // development switches (AVG_DBG), 0 in production
-    unsigned long long* dbg_hist;                      // AVG_DBG & 32: [3][32][256] narrowphase histogram per (moving shape, other shape): candidates, GJK calls, GJK iterations
+    AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
+    int* np_count;                                     // [2] item counters, used alternately (np_phase), reset by the narrowphase kernel
+    int np_capacity;
+    int np_phase;                                      // running sub-step index & 1
 };
 
 int avg_kernels_per_step(int substeps);
-cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
+cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream);   /* advances a.np_phase by `substeps` */
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
 /* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */
