@@ -35,7 +35,10 @@ struct AvgHandle {
     uint8_t* d_done = nullptr;
     cudaStream_t stream = nullptr;
     long long launches = 0;
-    AvgNpItem* d_npq = nullptr; int* d_npc = nullptr; int np_capacity = 0, np_phase = 0;   // narrowphase work queue
+    // narrowphase work queues: set 0 for avg_step and even chunks of avg_step_host, set 1 for odd chunks (second stream)
+    AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0, np_phase[2] = {0, 0};
+    cudaStream_t stream2 = nullptr;
+    unsigned long long* d_cnt = nullptr;               // AVG_DBG & 32 (development aid)
     std::string err;
 };
 
@@ -84,13 +87,17 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
     cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
     cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
-    h->np_capacity = n_env * 4 + 4096;                 /* ~3 candidates per environment and sub-step survive the culls; overflow is flagged */
-    if (cudaMalloc(&h->d_npq, sizeof(AvgNpItem) * (size_t)h->np_capacity) != cudaSuccess || cudaMalloc(&h->d_npc, 2 * sizeof(int)) != cudaSuccess) {
-        g_slot_used[slot] = false; delete h;
-        return fail(nullptr, -2, "avg_create: cudaMalloc of the narrowphase queue failed");
+    h->np_capacity = n_env * 12 + 4096;                /* 1-6 candidates per environment and sub-step survive the culls (more late in
+                                                          random-action episodes); overflow is flagged, never silent */
+    for (int k = 0; k < 2; ++k) {
+        if (cudaMalloc(&h->d_npq[k], sizeof(AvgNpItem) * (size_t)h->np_capacity) != cudaSuccess || cudaMalloc(&h->d_npc[k], 2 * sizeof(int)) != cudaSuccess) {
+            g_slot_used[slot] = false; delete h;
+            return fail(nullptr, -2, "avg_create: cudaMalloc of the narrowphase queue failed");
+        }
+        cudaMemset(h->d_npc[k], 0, 2 * sizeof(int));
     }
-    cudaMemset(h->d_npc, 0, 2 * sizeof(int));
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     *out = h;
     return 0;
 }
@@ -99,7 +106,13 @@ int avg_destroy(AvgHandle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->d_npq); cudaFree(h->d_npc);
+    if (h->d_cnt) {
+        unsigned long long c[8]; cudaMemcpy(c, h->d_cnt, 64, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[avg narrowphase counters] items %llu, rejected by the plane test %llu, GJK calls %llu, GJK iterations %llu, SAT fallbacks %llu, contacts %llu, cycles/item mean %llu max %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[0] ? c[6] / c[0] : 0ull, c[7]);
+        cudaFree(h->d_cnt);
+    }
+    for (int k = 0; k < 2; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
@@ -182,13 +195,16 @@ int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records
 
 float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
-static int fill_args(AvgHandle* h, AvgStepArgs& a) {
+static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset = 0) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
     a.slot = h->slot;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
-    a.np_queue = h->d_npq; a.np_count = h->d_npc; a.np_capacity = h->np_capacity; a.np_phase = h->np_phase;
+    a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity; a.np_phase = h->np_phase[qset];
+    a.env_begin = 0; a.env_end = h->n_env;
+    if ((a.dbg & 32) && !h->d_cnt) { cudaMalloc(&h->d_cnt, 64); cudaMemset(h->d_cnt, 0, 64); }
+    a.dbg_counters = (a.dbg & 32) ? h->d_cnt : nullptr;
     a.contacts = h->debug ? h->d_contacts : nullptr;
     a.ncontacts = h->debug ? h->d_ncontacts : nullptr;
     a.terms = h->debug ? h->d_terms : nullptr;
@@ -213,7 +229,7 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     int rc = fill_args(h, a); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-    h->np_phase = a.np_phase;
+    h->np_phase[0] = a.np_phase;
     h->launches += avg_kernels_per_step(h->substeps);
     return 0;
 }
@@ -258,14 +274,32 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
         memcpy(h->h_act, actions, sizeof(float) * n * h->n_act);
         src_act = h->h_act; dst_obs = h->h_obs; dst_rew = h->h_rew; dst_info = h->h_info; dst_done = h->h_done;
     }
-    AVG_CHECK(h, cudaMemcpyAsync(h->d_act, src_act, sizeof(float) * n * h->n_act, cudaMemcpyHostToDevice, h->stream));
-    int rc = avg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_info, h->stream);
-    if (rc) return rc;
-    AVG_CHECK(h, cudaMemcpyAsync(dst_obs, h->d_obs, sizeof(float) * n * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
-    AVG_CHECK(h, cudaMemcpyAsync(dst_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-    AVG_CHECK(h, cudaMemcpyAsync(dst_info, h->d_info, sizeof(float) * n * 2, cudaMemcpyDeviceToHost, h->stream));
-    if (dst_done) AVG_CHECK(h, cudaMemcpyAsync(dst_done, h->d_done, n, cudaMemcpyDeviceToHost, h->stream));
+    /* The batch is stepped in chunks that alternate between two streams, so the device->host copy of one chunk's
+       results (and the host->device copy of the next chunk's actions) overlaps the kernels of the other chunk. */
+    int n_chunks = h->n_env >= 16384 ? 4 : 1;
+    { const char* c = getenv("AVG_CHUNKS"); if (c && atoi(c) > 0) n_chunks = atoi(c); }
+    const int per = ((h->n_env + n_chunks - 1) / n_chunks + 3) & ~3;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = c * per, b1 = (c + 1) * per < h->n_env ? (c + 1) * per : h->n_env;
+        if (b0 >= b1) break;
+        const size_t cnt = (size_t)(b1 - b0);
+        const int qs = c & 1;
+        cudaStream_t st = qs ? h->stream2 : h->stream;
+        AVG_CHECK(h, cudaMemcpyAsync(h->d_act + (size_t)b0 * h->n_act, src_act + (size_t)b0 * h->n_act, sizeof(float) * cnt * h->n_act, cudaMemcpyHostToDevice, st));
+        AvgStepArgs a; memset(&a, 0, sizeof(a));
+        int rc = fill_args(h, a, qs); if (rc) return rc;
+        a.actions = h->d_act; a.obs = h->d_obs; a.reward = h->d_rew; a.done = h->d_done; a.info = h->d_info;
+        a.env_begin = b0; a.env_end = b1;
+        AVG_CHECK(h, avg_launch_step(a, h->substeps, st));
+        h->np_phase[qs] = a.np_phase;
+        h->launches += avg_kernels_per_step(h->substeps);
+        AVG_CHECK(h, cudaMemcpyAsync(dst_obs + (size_t)b0 * h->n_obs, h->d_obs + (size_t)b0 * h->n_obs, sizeof(float) * cnt * h->n_obs, cudaMemcpyDeviceToHost, st));
+        AVG_CHECK(h, cudaMemcpyAsync(dst_rew + b0, h->d_rew + b0, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
+        AVG_CHECK(h, cudaMemcpyAsync(dst_info + 2 * (size_t)b0, h->d_info + 2 * (size_t)b0, sizeof(float) * cnt * 2, cudaMemcpyDeviceToHost, st));
+        if (dst_done) AVG_CHECK(h, cudaMemcpyAsync(dst_done + b0, h->d_done + b0, cnt, cudaMemcpyDeviceToHost, st));
+    }
     AVG_CHECK(h, cudaStreamSynchronize(h->stream));
+    AVG_CHECK(h, cudaStreamSynchronize(h->stream2));
     if (!direct) {
         memcpy(obs, h->h_obs, sizeof(float) * n * h->n_obs);
         memcpy(reward, h->h_rew, sizeof(float) * n);

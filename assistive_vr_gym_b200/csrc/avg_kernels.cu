@@ -47,7 +47,8 @@ namespace {
 constexpr int kWarpsPerBlock = AVG_K_WARPS_PER_BLOCK;
 constexpr int kMaxJ = AVG_K_MAXJ;          // 1-DoF joints per environment handled by these kernels
 constexpr int kMaxMS = AVG_K_MAXMS;        // moving shapes
-constexpr int kMaxCand = 64;               // narrowphase candidates per sub-step
+constexpr int kCandPerLane = 4;
+constexpr int kMaxCand = 32 * kCandPerLane; // broadphase candidates per sub-step (before the bounding-capsule cull)
 constexpr int kMaxC = AVG_MAX_CONTACT;
 constexpr int kMaxDense = AVG_S_MAXDENSE;  // weld rows + contact normal + friction rows
 constexpr int kMaxRows = AVG_MAX_ROWS;
@@ -97,7 +98,8 @@ struct __align__(16) SmCollide {
     float bp[32][3]; float bq[32][4];      // body poses
     float sp[kMaxMS][3]; float sR[kMaxMS][9]; float4 saabb[kMaxMS][2];
     float4 scap[kMaxMS][2];                // bounding capsules of the moving shapes, world frame
-    uint32_t cand[kMaxCand];
+    uint32_t cand[kMaxCand], cand2[kMaxCand];         // broadphase candidates (unordered) / survivors of the culls in pair order
+    uint8_t candf[kMaxCand];                          // per ordered candidate: certificate-cache entry with a direction hint, 254 none, 255 not queued
     float4 sep[3][AVG_S_NSEPMAX];          // separation certificates of the previous sub-step (see collide_warp)
     float sq[kMaxMS][4];                   // world orientation of the moving shapes
     uint8_t near_idx[256];                 // static shapes (index) that overlap the union box of the moving shapes
@@ -308,109 +310,159 @@ __device__ bool simplex_closest(Simplex& s, V3& v) {
     return false;
 }
 
-// returns 0: cores separated (dist, pa, pb valid); 1: cores overlap; 2: separated by more than maxdist (early out: every
-// support plane gives the lower bound v.w/|v| on the distance, so well-separated candidates leave after 1-2 iterations).
-// Works relative to A's position to keep float32 magnitudes small.
-// vout / gap: on return 0 or 2, a direction along which the cores are separated and the support-plane lower bound of
-// their distance along it (gap <= 0: no valid bound).
-__device__ __noinline__ int gjk(const WShape& A, const WShape& B, float maxdist, float& dist, V3& pa, V3& pb, V3& vout, float& gap, int& iters) {
+// GJK return codes: 0 cores separated (dist, pa, pb valid); 1 cores overlap; 2 separated by more than maxdist (early
+// out: every support plane gives the lower bound v.w/|v| on the distance, so well-separated candidates leave after 1-2
+// iterations).  Works relative to A's position to keep float32 magnitudes small.
+// Support mapping for a converged warp whose lanes hold DIFFERENT shapes (one candidate pair per thread in the
+// narrowphase kernel).  Closed-form shapes are evaluated by their own lane.  Hull scans -- the only long loops of GJK --
+// are served by the whole warp, one requesting lane at a time: the request (vertex array, direction) is broadcast,
+// lane i looks at vertices i, i + 32, ..., the warp agrees on the largest dot product (lowest vertex index among
+// equals, exactly what a serial scan returns) and the requester takes the vertex.  Reads are coalesced and a 48-vertex
+// scan costs ~45 warp instructions instead of ~500 divergent ones.
+__device__ __noinline__ V3 support_any(const WShape& w, V3 d, bool active, int lane) {
+    const bool hull = active && w.s->type == AVG_SHAPE_HULL;
+    V3 res = mk3(0, 0, 0);
+    if (active && !hull) res = support(w, d);
+    unsigned req = __ballot_sync(AVG_FULL, hull);
+    if (req == 0) return res;
+    const V3 l = hull ? mtmul(w.R, d) : mk3(0, 0, 0);
+    const unsigned long long vp = hull ? reinterpret_cast<unsigned long long>(w.verts) : 0ull;
+    const int nv = hull ? w.s->vert_cnt : 0;
+    while (req) {
+        const int src = __ffs(req) - 1; req &= req - 1;
+        const float4* v = reinterpret_cast<const float4*>(__shfl_sync(AVG_FULL, vp, src));
+        const int n = __shfl_sync(AVG_FULL, nv, src);
+        const float lx = __shfl_sync(AVG_FULL, l.x, src), ly = __shfl_sync(AVG_FULL, l.y, src), lz = __shfl_sync(AVG_FULL, l.z, src);
+        float bd = -3.0e38f; int bi = 0x7fffffff;
+        for (int i = lane; i < n; i += 32) {
+            const float4 p = __ldg(v + i);
+            const float dd = fmaf(lx, p.x, fmaf(ly, p.y, lz * p.z));
+            if (dd > bd) { bd = dd; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(AVG_FULL, bd, o); const int oi = __shfl_xor_sync(AVG_FULL, bi, o);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == src) { const float4 bv = __ldg(v + bi); res = w.p + mmul(w.R, mk3(bv.x, bv.y, bv.z)); }
+    }
+    return res;
+}
+
+// GJK for a converged warp, one pair per lane, iterations in lockstep (same arithmetic per lane as gjk()).  `active`
+// lanes run; the return codes are those of gjk(); inactive lanes return -1.
+__device__ __noinline__ int gjk_lockstep(const WShape& A, const WShape& B, bool active, int lane, float maxdist, float& dist, V3& pa, V3& pb,
+                                         V3& vout, float& gap, int& iters) {
     Simplex s; s.n = 0;
     gap = 0.0f;
     bool fresh = false;
-    V3 org = A.p;
+    int result = -1;
+    const V3 org = A.p;
     V3 v = A.p - B.p;
     if (dot(v, v) < 1e-12f) v = mk3(1, 0, 0);
+    bool run = active;
 #pragma unroll 1
     for (int it = 0; it < 32; ++it) {
-        iters = it + 1;
-        V3 sa = support(A, -v) - org, sb = support(B, v) - org;
-        V3 w = sa - sb;
-        float vv = dot(v, v), vw = dot(v, w);
-        gap = vw * rsqrtf(vv); fresh = true;
-        if (vw > 0.0f && vw * vw > maxdist * maxdist * vv) { vout = v; return 2; }
-        if (s.n > 0 && (vv - vw) <= 1e-5f * vv + 1e-10f) break;
-        bool dup = false;
-        for (int i = 0; i < s.n; ++i) { V3 d = s.w[i] - w; if (dot(d, d) < 1e-14f) dup = true; }
-        if (dup) break;
-        fresh = false;
-        s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
-        if (simplex_closest(s, v)) return 1;
-        if (dot(v, v) < 1e-12f) return 1;
+        if (!__any_sync(AVG_FULL, run)) break;
+        const V3 sa = support_any(A, -v, run, lane) - org, sb = support_any(B, v, run, lane) - org;
+        if (run) {
+            iters = it + 1;
+            const V3 w = sa - sb;
+            const float vv = dot(v, v), vw = dot(v, w);
+            gap = vw * rsqrtf(vv); fresh = true;
+            if (vw > 0.0f && vw * vw > maxdist * maxdist * vv) { vout = v; result = 2; run = false; }
+            else if (s.n > 0 && (vv - vw) <= 1e-5f * vv + 1e-10f) { result = 0; run = false; }
+            else {
+                bool dup = false;
+                for (int i = 0; i < s.n; ++i) { V3 d = s.w[i] - w; if (dot(d, d) < 1e-14f) dup = true; }
+                if (dup) { result = 0; run = false; }
+                else {
+                    fresh = false;
+                    const bool first = s.n == 0;
+                    s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
+                    if (simplex_closest(s, v) || dot(v, v) < 1e-12f) { result = 1; run = false; }
+                    // float32 termination: |v| must shrink from one simplex to the next; once rounding stops it (near-touching
+                    // cores, where the relative test above drowns in the noise of the support points) further
+                    // iterations only cycle through the same vertices until the cap
+                    else if (!first && dot(v, v) >= vv * (1.0f - 1e-6f)) { result = 0; run = false; }
+                }
+            }
+        }
     }
-    V3 a = mk3(0, 0, 0), b = mk3(0, 0, 0);
-    for (int i = 0; i < s.n; ++i) { a = a + s.a[i] * s.lam[i]; b = b + s.b[i] * s.lam[i]; }
-    pa = a + org; pb = b + org; dist = norm(v); vout = v;
-    if (!fresh) gap = 0.0f;                  // v moved after the last support evaluation: no bound for it
-    return 0;
+    if (active && result < 0) result = 0;                        // iteration cap: report the current closest points
+    if (result == 0) {
+        V3 a = mk3(0, 0, 0), b = mk3(0, 0, 0);
+        for (int i = 0; i < s.n; ++i) { a = a + s.a[i] * s.lam[i]; b = b + s.b[i] * s.lam[i]; }
+        pa = a + org; pb = b + org; dist = norm(v); vout = v;
+        if (!fresh) gap = 0.0f;              // v moved after the last support evaluation: no bound for it
+    }
+    return result;
 }
 
-__device__ void sat_axis(const WShape& A, const WShape& B, V3 n, float& best, V3& bn, V3& bpa) {
-    float ln = norm(n);
-    if (ln < 1e-9f) return;
-    n = n * (1.0f / ln);
-    V3 sa = support(A, -n), sb = support(B, n);
-    float depth = dot(sb - sa, n);
-    if (depth < best) {
-        // anchor the witness on the round shape when there is one: a polytope's support point along a face normal
-        // is not unique
-        const bool ra = A.s->type == AVG_SHAPE_SPHERE || A.s->type == AVG_SHAPE_CAPSULE;
-        const bool rb = B.s->type == AVG_SHAPE_SPHERE || B.s->type == AVG_SHAPE_CAPSULE;
-        best = depth; bn = n; bpa = (rb && !ra) ? sb - n * depth : sa;
-    }
+// Number of candidate axes a shape contributes to the face-normal SAT, and the k-th of them (world frame, not
+// normalised), in the order of shape_axes(): boxes +-x, +-y, +-z; cylinders +-z then the radial direction towards the
+// other shape; hulls their face normals.  sign = -1 when S is A, +1 when S is B.
+__device__ __forceinline__ int sat_axis_count(const WShape& S) {
+    const int t = S.s->type;
+    return t == AVG_SHAPE_BOX ? 6 : (t == AVG_SHAPE_CYLINDER ? 3 : (t == AVG_SHAPE_HULL ? S.s->plane_cnt : 0));
 }
-__device__ void shape_axes(const WShape& S, const WShape& O, float sign, const WShape& A, const WShape& B, float& best, V3& bn, V3& bpa) {
-    const AvgShape* s = S.s;
-    if (s->type == AVG_SHAPE_BOX || s->type == AVG_SHAPE_CYLINDER) {
-        for (int ax = 0; ax < 3; ++ax) {
-            if (s->type == AVG_SHAPE_CYLINDER && ax < 2) continue;
-            V3 n = mk3(S.R[ax], S.R[3 + ax], S.R[6 + ax]);
-            sat_axis(A, B, n * sign, best, bn, bpa);
-            sat_axis(A, B, n * (-sign), best, bn, bpa);
-        }
-        if (s->type == AVG_SHAPE_CYLINDER) {
-            V3 az = mk3(S.R[2], S.R[5], S.R[8]);
-            V3 d = O.p - S.p;
-            V3 rad = d - az * dot(d, az);
-            sat_axis(A, B, rad * sign, best, bn, bpa);
-        }
-    } else if (s->type == AVG_SHAPE_HULL) {
-        for (int i = 0; i < s->plane_cnt; ++i) {
-            V3 n = mmul(S.R, mk3(S.planes[4 * i], S.planes[4 * i + 1], S.planes[4 * i + 2]));
-            sat_axis(A, B, n * sign, best, bn, bpa);
-        }
-    }
+__device__ __forceinline__ V3 sat_axis_dir(const WShape& S, const WShape& O, float sign, int k) {
+    const int t = S.s->type;
+    if (t == AVG_SHAPE_HULL) return mmul(S.R, mk3(S.planes[4 * k], S.planes[4 * k + 1], S.planes[4 * k + 2])) * sign;
+    if (t == AVG_SHAPE_BOX) { const int ax = k >> 1; return mk3(S.R[ax], S.R[3 + ax], S.R[6 + ax]) * ((k & 1) ? -sign : sign); }
+    const V3 az = mk3(S.R[2], S.R[5], S.R[8]);                   // cylinder
+    if (k < 2) return az * (k ? -sign : sign);
+    const V3 d = O.p - S.p;
+    return (d - az * dot(d, az)) * sign;
 }
 
-// -> true when a contact (distance < thr) exists
-// sepv / have_sep: when no contact is reported and GJK proved the separation along a direction, that direction
-__device__ bool narrowphase(const WShape& A, const WShape& B, float thr, V3& pa, V3& pb, V3& n, float& d, V3& sepv, float& sepgap, bool& have_sep, int& iters) {
-    float ma = A.s->margin, mb = B.s->margin;
-    have_sep = false;
-    if (B.s->type == AVG_SHAPE_PLANE) {
-        V3 sp = support(A, mk3(0, 0, -1));
-        d = sp.z - ma;
-        if (d >= thr) return false;
-        n = mk3(0, 0, 1); pa = mk3(sp.x, sp.y, sp.z - ma); pb = mk3(sp.x, sp.y, 0);
-        return true;
+// Face-normal SAT (cores overlap; DESIGN.md "deep penetration") for a converged warp with one pair per lane: the lanes
+// that need it are served one at a time, the requester's two shapes are broadcast and the candidate axes are spread
+// over the lanes (every lane scans the same vertices at the same time: broadcast loads).  The winner is the smallest
+// depth, lowest axis index among equals -- the result of the serial scan in shape_axes()/sat_axis().
+__device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool need, int lane, float& best_out, V3& bn_out, V3& bpa_out) {
+    unsigned req = __ballot_sync(AVG_FULL, need);
+    while (req) {
+        const int src = __ffs(req) - 1; req &= req - 1;
+        WShape a, b;
+        a.s = reinterpret_cast<const AvgShape*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(A.s), src));
+        b.s = reinterpret_cast<const AvgShape*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(B.s), src));
+        a.verts = reinterpret_cast<const float*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(A.verts), src));
+        b.verts = reinterpret_cast<const float*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(B.verts), src));
+        a.planes = reinterpret_cast<const float*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(A.planes), src));
+        b.planes = reinterpret_cast<const float*>(__shfl_sync(AVG_FULL, reinterpret_cast<unsigned long long>(B.planes), src));
+        a.p = shfl3(A.p, src); b.p = shfl3(B.p, src);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { a.R[i] = __shfl_sync(AVG_FULL, A.R[i], src); b.R[i] = __shfl_sync(AVG_FULL, B.R[i], src); }
+        const int ka = sat_axis_count(a), kb = sat_axis_count(b), K = ka + kb + 1;
+        float best = 3.0e38f; int bk = 0x7fffffff; V3 bn = mk3(0, 0, 1), bsa = a.p, bsb = a.p;
+        for (int k = lane; k < K; k += 32) {
+            V3 n = k < ka ? sat_axis_dir(a, b, -1.0f, k) : (k < ka + kb ? sat_axis_dir(b, a, 1.0f, k - ka) : a.p - b.p);
+            const float ln = norm(n);
+            if (ln < 1e-9f) continue;
+            n = n * (1.0f / ln);
+            const V3 sa = support(a, -n), sb = support(b, n);
+            const float depth = dot(sb - sa, n);
+            if (depth < best) { best = depth; bk = k; bn = n; bsa = sa; bsb = sb; }
+        }
+        float wbest = best; int wk = bk;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(AVG_FULL, wbest, o); const int ok = __shfl_xor_sync(AVG_FULL, wk, o);
+            if (od < wbest || (od == wbest && ok < wk)) { wbest = od; wk = ok; }
+        }
+        const int win = __ffs(__ballot_sync(AVG_FULL, bk == wk && wk != 0x7fffffff)) - 1;
+        const int w = win < 0 ? 0 : win;
+        const V3 n = shfl3(bn, w), sa = shfl3(bsa, w), sb = shfl3(bsb, w);
+        if (lane == src) {
+            // anchor the witness on the round shape when there is one: a polytope's support point along a face normal
+            // is not unique
+            const bool ra = A.s->type == AVG_SHAPE_SPHERE || A.s->type == AVG_SHAPE_CAPSULE;
+            const bool rb = B.s->type == AVG_SHAPE_SPHERE || B.s->type == AVG_SHAPE_CAPSULE;
+            if (win >= 0) { best_out = wbest; bn_out = n; bpa_out = (rb && !ra) ? sb - n * wbest : sa; }
+            else { best_out = 3.0e38f; bn_out = mk3(0, 0, 1); bpa_out = A.p; }
+        }
     }
-    float dist; V3 ca, cb;
-    const int g = gjk(A, B, thr + ma + mb, dist, ca, cb, sepv, sepgap, iters);
-    if (g == 2) { have_sep = true; return false; }
-    if (g == 0) {
-        d = dist - ma - mb;
-        if (d >= thr) { have_sep = sepgap > 0.0f; return false; }
-        n = (ca - cb) * (1.0f / dist);
-        pa = ca - n * ma; pb = cb + n * mb;
-        return true;
-    }
-    float best = 3.0e38f; V3 bn = mk3(0, 0, 1), bpa = A.p;
-    shape_axes(A, B, -1.0f, A, B, best, bn, bpa);
-    shape_axes(B, A, +1.0f, A, B, best, bn, bpa);
-    sat_axis(A, B, A.p - B.p, best, bn, bpa);
-    if (best > 1.0e38f) best = 0;
-    n = bn; d = -best - ma - mb;
-    pa = bpa - n * ma; pb = bpa + n * best + n * mb;
-    return true;
 }
 
 template <class SM>
@@ -534,40 +586,18 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
     if (ncand > kMaxCand) { overflow |= 4; ncand = kMaxCand; }
     ncand_out = ncand;
     __syncwarp();
-    // canonical order = pair-table order: ascending (moving shape a, other shape b); rank by counting (lists are short)
-    {
-        uint32_t mine[2]; int rank[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            int ci = lane + 32 * t;
-            mine[t] = ci < ncand ? s.cand[ci] : 0u; rank[t] = 0;
-        }
-        for (int j = 0; j < ncand; ++j) {
-            uint32_t o = s.cand[j];
-            uint32_t ko = ((o & 0xffffu) << 16) | (o >> 16);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                uint32_t km = ((mine[t] & 0xffffu) << 16) | (mine[t] >> 16);
-                rank[t] += ko < km;
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) if (lane + 32 * t < ncand) s.cand[rank[t]] = mine[t];
-        __syncwarp();
-    }
     // bounding-capsule cull (conservative): segment-segment distance minus radii against the pair threshold.  Elongated
-    // links have fat AABBs; this removes most candidates before the much more expensive GJK.  Order is preserved.
+    // links have fat AABBs; this removes most candidates before the much more expensive GJK.  One slab of 32
+    // candidates at a time, survivors compacted in place.
     {
-        uint32_t keep[2]; bool ok[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int ci = lane + 32 * t;
-            ok[t] = false; keep[t] = 0;
+        int nk = 0;
+#pragma unroll 1
+        for (int base = 0; base < ncand; base += 32) {
+            const int ci = base + lane;
+            bool ok = false; uint32_t pr = 0;
             if (ci < ncand) {
-                const uint32_t pr = s.cand[ci];
+                pr = s.cand[ci];
                 const int a = pr & 0xffff, b = pr >> 16;
-                keep[t] = pr;
                 const float4 a0 = s.scap[a][0], a1 = s.scap[a][1];
                 float4 b0, b1;
                 if (b < nms) { b0 = s.scap[b][0]; b1 = s.scap[b][1]; }
@@ -593,20 +623,30 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
                 }
                 const V3 dd = (p1 + d1 * sc) - (p2 + d2 * tc);
                 const float lim = a0.w + b0.w + thr + 1e-5f;
-                ok[t] = dot(dd, dd) <= lim * lim;
+                ok = dot(dd, dd) <= lim * lim;
             }
-        }
-        __syncwarp();
-        int nk = 0;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const unsigned bal = __ballot_sync(AVG_FULL, ok[t]);
-            if (ok[t]) s.cand[nk + __popc(bal & ((1u << lane) - 1))] = keep[t];
+            __syncwarp();
+            const unsigned bal = __ballot_sync(AVG_FULL, ok);
+            if (ok) s.cand[nk + __popc(bal & ((1u << lane) - 1))] = pr;      // nk <= base: never ahead of the slab being read
             nk += __popc(bal);
+            __syncwarp();
         }
         ncand = nk;
-        __syncwarp();
     }
+    // canonical order = pair-table order: ascending (moving shape a, other shape b); rank by counting (the list is short)
+#pragma unroll 1
+    for (int base = 0; base < ncand; base += 32) {
+        const int ci = base + lane;
+        const uint32_t mine = ci < ncand ? s.cand[ci] : 0u;
+        const uint32_t km = ((mine & 0xffffu) << 16) | (mine >> 16);
+        int rank = 0;
+        for (int j = 0; j < ncand; ++j) {
+            const uint32_t o = s.cand[j];
+            rank += (((o & 0xffffu) << 16) | (o >> 16)) < km;
+        }
+        if (ci < ncand) s.cand2[rank] = mine;
+    }
+    __syncwarp();
     // Hand-off to the narrowphase kernel, with separation certificates (temporal coherence).
     // Most candidates that survive the culls are close but not touching, sub-step after sub-step (hand against its own
     // finger tips, arm over the armrest).  When GJK proves a pair separated along a direction v by at least g
@@ -621,25 +661,24 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
     // slot in pair order and a slot of the new certificate list to fill in.
     int ncarry = 0, nq = 0;
     float4* gsep = reinterpret_cast<float4*>(gsep_f);
-    uint32_t qpair[2] = {0, 0}; int qslot[2] = {-1, -1}; float4 qhint[2];
     if (dbg & 1) ncand = 0;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int ci = lane + 32 * t;
+    // pass A: decide per candidate (carried by its certificate / queued), carried certificates move to the front of the
+    // new list; the decision and the cache entry that holds a direction hint are kept in shared memory for pass B
+#pragma unroll 1
+    for (int base = 0; base < ncand; base += 32) {
+        const int ci = base + lane;
         bool carried = false, queued = false;
         float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0;
-        qhint[t] = k0;
+        int f = -1;
         if (ci < ncand) {
-            const uint32_t pr = s.cand[ci];
+            const uint32_t pr = s.cand2[ci];
             const int a = pr & 0xffff, b = pr >> 16;
             const AvgShape* SA = &m.shape[a]; const AvgShape* SB = &m.shape[b];
-            queued = true; qpair[t] = pr;
+            queued = true;
             if (SB->type != AVG_SHAPE_PLANE) {
-                int f = -1;
                 for (int e = 0; e < nsep; ++e) if (__float_as_uint(s.sep[0][e].w) == pr) f = e;
                 if (f >= 0) {
                     const float4 e0 = s.sep[0][f], e1 = s.sep[1][f], e2 = s.sep[2][f];
-                    qhint[t] = e0;
                     if (e1.w > 0.0f) {
                         const Q4 qa = ldq(s.sq[a]);
                         const Q4 qb = b < nms ? ldq(s.sq[b]) : ldq(SB->quat);
@@ -658,37 +697,46 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
                     }
                 }
             }
+            s.candf[ci] = (uint8_t)(queued ? (f >= 0 ? f : 254) : 255);           // 255: carried, 254: queued without a hint
         }
         const unsigned bc = __ballot_sync(AVG_FULL, carried), bq = __ballot_sync(AVG_FULL, queued);
         if (carried) {
             const int slot = ncarry + __popc(bc & ((1u << lane) - 1));
             if (slot < AVG_S_NSEPMAX) { gsep[slot] = k0; gsep[AVG_S_NSEPMAX + slot] = k1; gsep[2 * AVG_S_NSEPMAX + slot] = k2; }
         }
-        if (queued) qslot[t] = nq + __popc(bq & ((1u << lane) - 1));
         ncarry += __popc(bc); nq += __popc(bq);
     }
     ncarry = min(ncarry, AVG_S_NSEPMAX);
     if (nq > AVG_S_NQMAX) { overflow |= 1; nq = AVG_S_NQMAX; }
-    // reserve queue space for the warp's items, write them, and seed the certificate slots they will fill in
+    // pass B: reserve queue space for the warp's items, write them, and seed the certificate slots they will fill in
     int qbase = 0;
     if (lane == 0 && nq > 0) qbase = atomicAdd(np_count, nq);
     qbase = __shfl_sync(AVG_FULL, qbase, 0);
     if (qbase + nq > np_capacity) { overflow |= 1; nq = max(0, min(nq, np_capacity - qbase)); }
-    int ncert = 0;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        if (qslot[t] >= 0 && qslot[t] < nq) {
-            const int cs = ncarry + qslot[t] < AVG_S_NSEPMAX ? ncarry + qslot[t] : -1;
-            if (cs >= 0) {                        // direction hint (or none), gap <= 0: not a certificate until the narrowphase says so
-                gsep[cs] = make_float4(qhint[t].x, qhint[t].y, qhint[t].z, __uint_as_float(0xffffffffu));
-                gsep[AVG_S_NSEPMAX + cs] = make_float4(0, 0, 0, 0);
+    __syncwarp();
+    {
+        int qn = 0;
+#pragma unroll 1
+        for (int base = 0; base < ncand; base += 32) {
+            const int ci = base + lane;
+            const int fcode = ci < ncand ? s.candf[ci] : 255;
+            const bool queued = fcode != 255;
+            const unsigned bq = __ballot_sync(AVG_FULL, queued);
+            const int qslot = qn + __popc(bq & ((1u << lane) - 1));
+            if (queued && qslot < nq) {
+                const int cs = ncarry + qslot < AVG_S_NSEPMAX ? ncarry + qslot : -1;
+                if (cs >= 0) {                    // direction hint (or none), gap <= 0: not a certificate until the narrowphase says so
+                    const float4 hint = fcode < 254 ? s.sep[0][fcode] : make_float4(0, 0, 0, 0);
+                    gsep[cs] = make_float4(hint.x, hint.y, hint.z, __uint_as_float(0xffffffffu));
+                    gsep[AVG_S_NSEPMAX + cs] = make_float4(0, 0, 0, 0);
+                }
+                AvgNpItem it; it.env = env_index; it.pair = s.cand2[ci]; it.slot = qslot; it.cert = cs;
+                np_queue[qbase + qslot] = it;
             }
-            AvgNpItem it; it.env = env_index; it.pair = qpair[t]; it.slot = qslot[t]; it.cert = cs;
-            np_queue[qbase + qslot[t]] = it;
+            qn += __popc(bq);
         }
     }
-    ncert = min(ncarry + nq, AVG_S_NSEPMAX);
-    nsep_out = ncert;
+    nsep_out = min(ncarry + nq, AVG_S_NSEPMAX);
     ncontact = nq;                                // number of queued candidates (results arrive from the narrowphase kernel)
     __syncwarp();
 }
@@ -706,8 +754,8 @@ struct LaneDyn {
 #define AVG_KERNEL_PREAMBLE(SMTYPE)                                                             \
     extern __shared__ __align__(16) unsigned char smem_raw[];                                    \
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                  \
-    const int e = blockIdx.x * (blockDim.x >> 5) + warp;                                         \
-    if (e >= a.n_env) return;                                                                    \
+    const int e = a.env_begin + blockIdx.x * (blockDim.x >> 5) + warp;                           \
+    if (e >= a.env_end) return;                                                                  \
     SMTYPE& s = reinterpret_cast<SMTYPE*>(smem_raw)[warp];                                       \
     const int variant = a.variant ? a.variant[e] : 0;                                            \
     const KM m = c_models[a.slot][variant];                                                      \
@@ -722,8 +770,8 @@ struct LaneDyn {
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_prologue_kernel(AvgStepArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (e >= a.n_env) return;
+    const int e = a.env_begin + blockIdx.x * (blockDim.x >> 5) + warp;
+    if (e >= a.env_end) return;
     const int variant = a.variant ? a.variant[e] : 0;
     const KM m = c_models[a.slot][variant];
     const AvgModelHeader* h = m.h;
@@ -817,47 +865,94 @@ __device__ __forceinline__ void np_load_shape(const KM& m, const float* scr, int
 
 __global__ void __launch_bounds__(128)
 avg_narrow_kernel(AvgStepArgs a) {
+    // one THREAD per work item; the 32 items of a warp advance through the certificate test and the GJK iterations in
+    // lockstep so that hull support scans can be served by the whole warp (support_any)
     const int count = min(a.np_count[a.np_phase & 1], a.np_capacity);
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    if (tid == 0) a.np_count[(a.np_phase + 1) & 1] = 0;          // the counter of the next sub-step (idle during this kernel)
-    for (int i = tid; i < count; i += nthreads) {
-        const AvgNpItem it = a.np_queue[i];
-        const int variant = a.variant ? a.variant[it.env] : 0;
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.np_count[(a.np_phase + 1) & 1] = 0;   // the counter of the next sub-step (idle during this kernel)
+    for (int base = wid * 32; base < count; base += nwarps * 32) {
+        const int i = base + lane;
+        const bool valid = i < count;
+        const long long t_begin = a.dbg_counters ? clock64() : 0;
+        AvgNpItem it; it.env = 0; it.pair = 0; it.slot = 0; it.cert = -1;
+        if (valid) it = a.np_queue[i];
+        const int variant = (valid && a.variant) ? a.variant[it.env] : 0;
         const KM m = c_models[a.slot][variant];
         float* scr = a.scratch + (size_t)it.env * AVG_S_STRIDE;
         const int sa = it.pair & 0xffff, sb = it.pair >> 16;
         WShape A, B; Q4 qa, qb;
         np_load_shape(m, scr, sa, A, qa); np_load_shape(m, scr, sb, B, qb);
-        const float thr = fminf(A.s->thr, B.s->thr);
+        const float thr = fminf(A.s->thr, B.s->thr), ma = A.s->margin, mb = B.s->margin;
+        const bool plane = B.s->type == AVG_SHAPE_PLANE;
         float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
         V3 pa = mk3(0, 0, 0), pb = pa, n = pa; float d = 0.0f;
-        bool hit = false, have_sep = false, done = false;
+        bool hit = false, have_sep = false, done = !valid;
         V3 sepv = mk3(0, 0, 0); float sepgap = 0.0f;
-        if (it.cert >= 0 && B.s->type != AVG_SHAPE_PLANE) {
-            const float4 hint = gsep[it.cert];
-            const V3 va = mk3(hint.x, hint.y, hint.z);
-            if (dot(va, va) > 0.0f) {                                // (2) support-plane test along the remembered direction
-                const V3 v = qrot(qa, va);
-                const V3 w = support(A, -v) - support(B, v);
-                const float vv = dot(v, v), vw = dot(v, w), md = thr + A.s->margin + B.s->margin;
+        int gi = 0;
+        // (2) support-plane test along the remembered direction; ground-plane pairs: one support along -z
+        {
+            V3 v = mk3(0, 0, -1);
+            bool test = false;
+            if (valid && !plane && it.cert >= 0) {
+                const float4 hint = gsep[it.cert];
+                const V3 va = mk3(hint.x, hint.y, hint.z);
+                if (dot(va, va) > 0.0f) { v = qrot(qa, va); test = true; }
+            }
+            const V3 s1 = support_any(A, plane ? v : -v, (test || plane) && valid, lane);
+            const V3 s2 = support_any(B, v, test, lane);
+            if (test) {
+                const V3 w = s1 - s2;
+                const float vv = dot(v, v), vw = dot(v, w), md = thr + ma + mb;
                 if (vw > 0.0f && vw * vw > md * md * vv) { done = true; have_sep = true; sepv = v; sepgap = vw * rsqrtf(vv); }
             }
+            if (valid && plane) {                                     // narrowphase(): half-space of plane.urdf's box
+                done = true;
+                d = s1.z - ma;
+                if (d < thr) { hit = true; n = mk3(0, 0, 1); pa = mk3(s1.x, s1.y, s1.z - ma); pb = mk3(s1.x, s1.y, 0); }
+            }
         }
-        if (!done) { int gi = 0; hit = narrowphase(A, B, thr, pa, pb, n, d, sepv, sepgap, have_sep, gi); }
-        if (it.cert >= 0) {
-            if (have_sep && sepgap > 0.0f) {
+        // GJK on the cores, margins added afterwards (narrowphase())
+        {
+            float dist = 0.0f; V3 ca = pa, cb = pb;
+            const int g = gjk_lockstep(A, B, !done, lane, thr + ma + mb, dist, ca, cb, sepv, sepgap, gi);
+            if (g == 2) have_sep = true;
+            else if (g == 0) {
+                d = dist - ma - mb;
+                if (d >= thr) have_sep = sepgap > 0.0f;
+                else { hit = true; n = (ca - cb) * (1.0f / dist); pa = ca - n * ma; pb = cb + n * mb; }
+            }
+            float best = 3.0e38f; V3 bn = mk3(0, 0, 1), bpa = A.p;
+            sat_served(A, B, g == 1, lane, best, bn, bpa);          // cores overlap: face-normal SAT (rare)
+            if (g == 1) {
+                gi |= 1 << 16;
+                if (best > 1.0e38f) best = 0;
+                hit = true; n = bn; d = -best - ma - mb;
+                pa = bpa - n * ma; pb = bpa + n * best + n * mb;
+            }
+        }
+        if (valid) {
+            if (a.dbg_counters) {
+                atomicAdd(a.dbg_counters, 1ull); if (have_sep && gi == 0) atomicAdd(a.dbg_counters + 1, 1ull);
+                if (gi) { atomicAdd(a.dbg_counters + 2, 1ull); atomicAdd(a.dbg_counters + 3, (unsigned long long)(gi & 0xffff)); if (gi >> 16) atomicAdd(a.dbg_counters + 4, 1ull); }
+                if (hit) atomicAdd(a.dbg_counters + 5, 1ull);
+                const unsigned long long cyc = (unsigned long long)(clock64() - t_begin);
+                atomicAdd(a.dbg_counters + 6, cyc); atomicMax(a.dbg_counters + 7, cyc);
+            }
+            if (it.cert >= 0 && have_sep && sepgap > 0.0f) {
                 const V3 va = qrot_inv(qa, sepv), prel = qrot_inv(qa, B.p - A.p);
                 const Q4 qrel = qmul(qconj(qa), qb);
                 gsep[it.cert] = make_float4(va.x, va.y, va.z, __uint_as_float(it.pair));
                 gsep[AVG_S_NSEPMAX + it.cert] = make_float4(prel.x, prel.y, prel.z, sepgap);
                 gsep[2 * AVG_S_NSEPMAX + it.cert] = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
             }                                                        // else the slot keeps the "no certificate" seed of the collide kernel
+            float4* r = reinterpret_cast<float4*>(scr + AVG_S_NPRES) + 4 * it.slot;
+            r[0] = make_float4(pa.x, pa.y, pa.z, pb.x);
+            r[1] = make_float4(pb.y, pb.z, n.x, n.y);
+            r[2] = make_float4(n.z, d, __int_as_float(sa), __int_as_float(sb));
+            r[3] = make_float4(hit ? 1.0f : 0.0f, 0, 0, 0);
         }
-        float4* r = reinterpret_cast<float4*>(scr + AVG_S_NPRES) + 4 * it.slot;
-        r[0] = make_float4(pa.x, pa.y, pa.z, pb.x);
-        r[1] = make_float4(pb.y, pb.z, n.x, n.y);
-        r[2] = make_float4(n.z, d, __int_as_float(sa), __int_as_float(sb));
-        r[3] = make_float4(hit ? 1.0f : 0.0f, 0, 0, 0);
+        __syncwarp();
     }
 }
 
@@ -1639,7 +1734,7 @@ namespace {
 struct KernelTimes {
     bool on = false, init = false;
     cudaEvent_t ev[64];
-    double ms[5] = {0, 0, 0, 0, 0};
+    double ms[6] = {0, 0, 0, 0, 0, 0};
     int steps = 0;
 };
 KernelTimes g_kt;
@@ -1664,18 +1759,22 @@ cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream) {
         if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
         const char* kt = getenv("AVG_KERNEL_TIMES");
-        g_kt.on = kt && kt[0] == '1' && 3 * substeps + 3 <= 64;
+        g_kt.on = kt && kt[0] == '1' && 4 * substeps + 3 <= 64;
     }
+    const bool kt_on = g_kt.on && a.env_begin == 0 && a.env_end == a.n_env;     // whole-batch launches only
     int nev = 0;
-    if (g_kt.on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
-    auto mark = [&]() { if (g_kt.on) cudaEventRecord(g_kt.ev[nev++], stream); };
-    auto grid = [&](int wpb) { return (a.n_env + wpb - 1) / wpb; };
-    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 8);
+    if (kt_on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
+    auto mark = [&]() { if (kt_on) cudaEventRecord(g_kt.ev[nev++], stream); };
+    const int n_range = a.env_end - a.env_begin;
+    if (n_range <= 0) return cudaSuccess;
+    auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
+    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 16);     // grid-stride over the queue, one thread per work item
     mark();
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
     mark();
     for (int f = 0; f < substeps; ++f) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+        mark();
         avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
         a.np_phase ^= 1;
         mark();
@@ -1692,17 +1791,17 @@ cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream) {
     }
     avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     mark();
-    if (g_kt.on) {
+    if (kt_on) {
         cudaEventSynchronize(g_kt.ev[nev - 1]);
         auto el = [&](int i) { float t = 0; cudaEventElapsedTime(&t, g_kt.ev[i], g_kt.ev[i + 1]); return (double)t; };
         g_kt.ms[0] += el(0);
-        for (int f = 0; f < substeps; ++f) { g_kt.ms[1] += el(1 + 3 * f); g_kt.ms[2] += el(2 + 3 * f); g_kt.ms[3] += el(3 + 3 * f); }
-        g_kt.ms[4] += el(1 + 3 * substeps);
-        if (++g_kt.steps % 8 == 0) {
-            const double tot = g_kt.ms[0] + g_kt.ms[1] + g_kt.ms[2] + g_kt.ms[3] + g_kt.ms[4];
-            fprintf(stderr, "[avg kernel times, %d steps, %d envs] prologue %.3f collide %.3f dynamics %.3f solve %.3f epilogue %.3f ms/step (total %.3f)\n",
-                    g_kt.steps, a.n_env, g_kt.ms[0] / g_kt.steps, g_kt.ms[1] / g_kt.steps, g_kt.ms[2] / g_kt.steps, g_kt.ms[3] / g_kt.steps,
-                    g_kt.ms[4] / g_kt.steps, tot / g_kt.steps);
+        for (int f = 0; f < substeps; ++f) { g_kt.ms[1] += el(1 + 4 * f); g_kt.ms[5] += el(2 + 4 * f); g_kt.ms[2] += el(3 + 4 * f); g_kt.ms[3] += el(4 + 4 * f); }
+        g_kt.ms[4] += el(1 + 4 * substeps);
+        if (++g_kt.steps % 8 == 0) {                 // mean over the last 8 steps
+            const double tot = g_kt.ms[0] + g_kt.ms[1] + g_kt.ms[2] + g_kt.ms[3] + g_kt.ms[4] + g_kt.ms[5];
+            fprintf(stderr, "[avg kernel times, steps %d-%d, %d envs] prologue %.3f collide %.3f narrow %.3f dynamics %.3f solve %.3f epilogue %.3f ms/step (total %.3f)\n",
+                    g_kt.steps - 8, g_kt.steps - 1, a.n_env, g_kt.ms[0] / 8, g_kt.ms[1] / 8, g_kt.ms[5] / 8, g_kt.ms[2] / 8, g_kt.ms[3] / 8, g_kt.ms[4] / 8, tot / 8);
+            for (int i = 0; i < 6; ++i) g_kt.ms[i] = 0;
         }
     }
     return cudaGetLastError();
@@ -1735,7 +1834,7 @@ cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream) {
     const size_t sm_epi = sizeof(SmEpi) * kWpbEpi;
     cudaError_t e1 = set_smem(avg_reset_obs_kernel, sm_epi);
     if (e1 != cudaSuccess) return e1;
-    const int blocks = (a.n_env + kWpbEpi - 1) / kWpbEpi;
+    const int blocks = (a.env_end - a.env_begin + kWpbEpi - 1) / kWpbEpi;
     avg_reset_obs_kernel<<<blocks, 32 * kWpbEpi, sm_epi, stream>>>(a);
     return cudaGetLastError();
 }

@@ -62,13 +62,15 @@ struct AvgStepArgs {
     float* terms;                                      // [n_env][8]  reward terms for parity tests (may be null)
     AvgContact* contacts;                              // [n_env][AVG_MAX_CONTACT] (may be null)
     int32_t* ncontacts;                                // [n_env]
-    int n_env;
+    int n_env;                                         // environments of the handle
+    int env_begin, env_end;                            // range stepped by this launch sequence (avg_step: all; avg_step_host: one chunk)
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
     int dbg;                                           // development switches (AVG_DBG), 0 in production
     AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
     int* np_count;                                     // [2] item counters, used alternately (np_phase), reset by the narrowphase kernel
     int np_capacity;
     int np_phase;                                      // running sub-step index & 1
+    unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)
 };
 
 int avg_kernels_per_step(int substeps);

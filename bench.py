@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=196608)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-episode", action="store_true", help="skip the extra whole-episode (200-step) throughput measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,7 +175,11 @@ def main():
     env = make(ENV_ID, num_envs=E, device=local_rank, seed=1001 + rank)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
-    ring = [torch.rand((E, 7), device=dev, generator=gen) * 2 - 1 for _ in range(8)]
+    # fresh i.i.d. actions for every step (reference examples/random_actions.py samples anew each step; a short ring
+    # reused cyclically would give every arm a constant drift and pile the batch up against limits and obstacles)
+    n_ring = max(args.warmup, 3) + args.steps
+    ring = [torch.rand((E, 7), device=dev, generator=gen) * 2 - 1 for _ in range(min(n_ring, 256))]
+    act_ep = torch.empty((E, 7), device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -183,8 +188,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for w in range(max(args.warmup, 3)):
-        env.step(ring[w % 8])
+    W = max(args.warmup, 3)
+    for w in range(W):
+        env.step(ring[w % len(ring)])
     env.elapsed = 0
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
@@ -193,7 +199,7 @@ def main():
     ev0.record(stream)
     stats = torch.zeros(4, device=dev)
     for k in range(args.steps):
-        obs, rew, done, info = env.step(ring[k % 8])
+        obs, rew, done, info = env.step(ring[(W + k) % len(ring)])
         env.elapsed = 0                              # keep the timed window free of TimeLimit resets
     ev1.record(stream)
     barrier()
@@ -230,16 +236,39 @@ def main():
     h2d = E * 7 * 4
     d2h = E * (env.sim.n_obs * 4 + 4 + 8 + 1)
 
+    # ---- whole-episode throughput (extra, not the headline): random-action episodes get slower as arms wander into
+    #      contact (more candidate pairs, PGS sweeps up to the 50-iteration cap), so the steps right after reset flatter
+    #      the simulator; this is the mean over a full TimeLimit(200) episode from a fresh reset -----------------------
+    episode = None
+    if not args.no_episode:
+        env.reset()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(200):
+            act_ep.uniform_(-1, 1, generator=gen)            # one tiny RNG kernel per step inside the timed region
+            env.step(act_ep); env.elapsed = 0
+        e1.record(stream)
+        barrier()
+        tep = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            dist.all_reduce(tep, op=dist.ReduceOp.MAX)
+        episode = {"value": E * world * 200 / (float(tep.item()) * 1e-3), "unit": UNIT, "steps": 200,
+                   "note": "mean over a full 200-step random-action episode from reset (device-resident I/O)"}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpe = env.sim.bytes_per_env_step
-        launch_ms = ms / max(1, launches)
-        achieved = bpe * E / (launch_ms * 1e-3) / 1e9
-        traffic = None
+        # one "launch" of the path = the kernel sequence of one env-step (prologue, 5 x {collide, narrowphase, dynamics,
+        # solve}, epilogue); its algorithmic bytes are per env-step, its duration the step time
+        achieved = bpe * E / (ms / args.steps * 1e-3) / 1e9
+        traffic = None; prof = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                prof = json.load(open(tp))
+                traffic = prof.get("dram_bytes_per_step_per_env", None)
+                traffic = traffic * E if traffic is not None else None
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -252,11 +281,15 @@ def main():
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "peak_source": peak_src, "bytes_per_env_step": bpe,
-                             "note": "latency/FP32-issue bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks"},
+                             "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernels of one env-step" % (launches // max(1, args.steps)),
+                             "issue_slots": prof.get("issue_slots"),
+                             "note": "issue/latency bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks; "
+                                     "issue_slots (from the committed ncu launch list) is the roof that binds"},
                 "clocks": sampler.summary(),
                 "episode_stats": {"mean_reward_last_step": float(stats[0] / stats[3]), "task_success": float(stats[1]),
                                   "mean_force_on_human": float(stats[2] / stats[3])}}
+        if episode is not None:
+            line["episode"] = episode
         if not args.no_cpu_baseline and world == 1:
             v, c, sample = cpu_oracle_throughput(16, 200)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}
