@@ -192,3 +192,101 @@ def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, ge
     env[:, E_TREMOR:E_TREMOR + 10] = tremor
     env_i[:, E_LIMB_FRAME] = np.where(limb == 0, F_SHOULDER, F_ELBOW)
     return env, variant
+
+
+# ---- device reset (include/avg_model.h AvgResetTable, csrc avg_reset_kernel) ------------------------------------------
+RESET_POOL = 64
+RESET_TABLE_DT = np.dtype([
+    ("n_pool", "<i4"), ("n_arm", "<i4"), ("n_fin", "<i4"), ("n_hum", "<i4"), ("tool_qidx", "<i4"), ("human_control", "<i4"), ("pad", "<i4", 2),
+    ("pool_q", "<f4", (RESET_POOL, 8)), ("pool_tool", "<f4", (RESET_POOL, 8)),
+    ("arm_qidx", "<i4", 8), ("arm_dof", "<i4", 8), ("fin_qidx", "<i4", 8), ("fin_dof", "<i4", 8),
+    ("hum_qidx", "<i4", 8), ("hum_dof", "<i4", 8), ("hum_joint", "<i4", 8),
+    ("hum_lower", "<f4", 8), ("hum_upper", "<f4", 8), ("hum_reset", "<f4", 8), ("limb_dims", "<f4", (2, 2)),
+])
+
+
+def reset_table_bytes(rd: dict) -> bytes:
+    """One variant's `build_reset_data` as the AvgResetTable the device sampler reads."""
+    t = np.zeros(1, dtype=RESET_TABLE_DT)[0]
+    n_pool = min(len(rd["pool_q"]), RESET_POOL)
+    t["n_pool"] = n_pool; t["n_arm"] = len(rd["arm_qidx"]); t["n_fin"] = len(rd["fin_qidx"]); t["n_hum"] = len(rd["hum_qidx"])
+    t["tool_qidx"] = int(rd["tool_qidx"]); t["human_control"] = int(rd["human_control"])
+    t["pool_q"][:n_pool, :rd["pool_q"].shape[1]] = rd["pool_q"][:n_pool]
+    t["pool_tool"][:n_pool, :7] = rd["pool_tool"][:n_pool]
+    for k in ("arm_qidx", "arm_dof", "fin_qidx", "fin_dof", "hum_qidx", "hum_dof", "hum_joint", "hum_lower", "hum_upper", "hum_reset"):
+        t[k][:len(rd[k])] = rd[k]
+    t["limb_dims"] = rd["limb_dims"]
+    return t.tobytes()
+
+
+def _mix(h: np.ndarray) -> np.ndarray:
+    h = h ^ (h >> np.uint32(16)); h = h * np.uint32(0x85ebca6b); h = h ^ (h >> np.uint32(13)); h = h * np.uint32(0xc2b2ae35)
+    return h ^ (h >> np.uint32(16))
+
+
+def reset_u32(seed: int, env: np.ndarray, episode: np.ndarray, k: int) -> np.ndarray:
+    """AVG_RNG_MIX chain of include/avg_model.h (draw k of episode `episode` of environment `env`)."""
+    with np.errstate(over="ignore"):
+        h = np.full(env.shape, seed & 0xffffffff, dtype=np.uint32)
+        h = _mix(h) ^ (env.astype(np.uint32) * np.uint32(0x9e3779b9))
+        h = _mix(h) ^ (episode.astype(np.uint32) * np.uint32(0x7f4a7c15))
+        h = _mix(h) ^ np.uint32((k * 0x94d049bb) & 0xffffffff)
+        return _mix(h)
+
+
+def reset_u01(seed, env, episode, k) -> np.ndarray:
+    return (reset_u32(seed, env, episode, k) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.ndarray):
+    """Host mirror of avg_reset_kernel: the records the device writes for environments 0..n-1 starting their
+    `episode`-th episode under `seed` (float32 arithmetic in the kernel's order)."""
+    f32 = np.float32
+    env_idx = np.arange(n)
+    env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
+    env_i = env.view(np.int32)
+    nv = len(reset_data)
+    variant = (reset_u32(seed, env_idx, episode, 0) % np.uint32(nv)).astype(np.int32)
+    impairment = (reset_u32(seed, env_idx, episode, 1) & np.uint32(3)).astype(np.int32)
+    limit_scale = np.where(impairment == 1, f32(0.5) + f32(0.5) * reset_u01(seed, env_idx, episode, 2), f32(1.0)).astype(f32)
+    strength = np.where(impairment == 2, f32(0.25) + f32(0.75) * reset_u01(seed, env_idx, episode, 3), f32(1.0)).astype(f32)
+    deg10 = f32(0.17453292519943295)
+    tremor = np.stack([(f32(2.0) * reset_u01(seed, env_idx, episode, 4 + j) - f32(1.0)) * deg10 for j in range(10)], axis=1)
+    tremor = np.where((impairment == 3)[:, None], tremor, f32(0.0)).astype(f32)
+    limb = (reset_u32(seed, env_idx, episode, 14) & np.uint32(1)).astype(np.int32)
+    u_len = reset_u01(seed, env_idx, episode, 15)
+    theta = f32(6.283185307179586) * reset_u01(seed, env_idx, episode, 16)
+    pick = reset_u32(seed, env_idx, episode, 17)
+    for v in range(nv):
+        idx = np.nonzero(variant == v)[0]
+        if idx.size == 0:
+            continue
+        rd = reset_data[v]
+        n_pool = min(len(rd["pool_q"]), RESET_POOL)
+        k = (pick[idx] % np.uint32(n_pool)).astype(np.int64)
+        qa = rd["pool_q"][k].astype(f32)
+        ls = limit_scale[idx][:, None]
+        qh = np.minimum(np.maximum(rd["hum_reset"].astype(f32)[None, :], rd["hum_lower"].astype(f32)[None, :] * ls), rd["hum_upper"].astype(f32)[None, :] * ls)
+        length = rd["limb_dims"].astype(f32)[limb[idx], 0]; radius = rd["limb_dims"].astype(f32)[limb[idx], 1]
+        rl = radius + u_len[idx] * (length - radius)
+        env[np.ix_(idx, E_Q + rd["arm_qidx"])] = qa
+        env[np.ix_(idx, E_MTARGET + rd["arm_dof"])] = qa
+        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = 1.0
+        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = 1.0
+        env[np.ix_(idx, E_Q + rd["hum_qidx"])] = qh
+        env[np.ix_(idx, E_MTARGET + rd["hum_dof"])] = qh
+        tq = int(rd["tool_qidx"])
+        env[idx, E_Q + tq:E_Q + tq + 7] = rd["pool_tool"][k].astype(f32)
+        active = bool(rd["human_control"]) | (impairment[idx] == 3)
+        env[idx, E_HUMAN_KP] = np.where(active, f32(0.05), f32(0.01))
+        env[np.ix_(idx, E_TARGET_H + rd["hum_joint"] - 4)] = qh
+        th = theta[idx]
+        env[idx, E_TARGET_ON_ARM + 0] = -radius * np.sin(th, dtype=f32)
+        env[idx, E_TARGET_ON_ARM + 1] = -radius * np.cos(th, dtype=f32)
+        env[idx, E_TARGET_ON_ARM + 2] = -rl
+    env[:, E_STRENGTH] = strength
+    env[:, E_LIMIT_SCALE] = limit_scale
+    env[:, E_TREMOR_ON] = (impairment == 3)
+    env[:, E_TREMOR:E_TREMOR + 10] = tremor
+    env_i[:, E_LIMB_FRAME] = np.where(limb == 0, F_SHOULDER, F_ELBOW)
+    return env, variant

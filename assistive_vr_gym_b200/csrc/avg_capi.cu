@@ -23,6 +23,8 @@ struct AvgHandle {
     int substeps = 5;
     int maxblk = 0;
     int32_t* d_variant = nullptr;
+    int32_t* d_episode = nullptr;                      // episodes started per environment (device reset counter)
+    AvgResetTable* d_rtab[AVG_K_MAX_VARIANTS] = {nullptr, nullptr, nullptr, nullptr};
     // debug taps
     bool debug = false;
     AvgContact* d_contacts = nullptr;
@@ -86,6 +88,7 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     }
     cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
     cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
+    if (cudaMalloc(&h->d_episode, sizeof(int32_t) * (size_t)n_env) == cudaSuccess) cudaMemset(h->d_episode, 0, sizeof(int32_t) * (size_t)n_env);
     cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
     h->np_capacity = n_env * 12 + 4096;                /* 1-6 candidates per environment and sub-step survive the culls (more late in
                                                           random-action episodes); overflow is flagged, never silent */
@@ -113,7 +116,8 @@ int avg_destroy(AvgHandle* h) {
     }
     for (int k = 0; k < 2; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
     if (h->stream2) cudaStreamDestroy(h->stream2);
-    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) cudaFree(h->d_model[v]);
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) { cudaFree(h->d_model[v]); cudaFree(h->d_rtab[v]); }
+    cudaFree(h->d_episode);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
@@ -195,7 +199,42 @@ int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records
 
 float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
-static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset = 0) {
+static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset);
+
+int avg_upload_reset_table(AvgHandle* h, int variant, const void* table, size_t nbytes) {
+    if (!h || !table) return -1;
+    if (variant < 0 || variant >= AVG_K_MAX_VARIANTS || !h->have[variant]) return fail(h, -1, "avg_upload_reset_table: upload the model of this variant first");
+    if (nbytes != sizeof(AvgResetTable)) return fail(h, -1, "avg_upload_reset_table: size mismatch (AvgResetTable)");
+    const AvgResetTable* t = (const AvgResetTable*)table;
+    if (t->n_pool <= 0 || t->n_pool > AVG_RESET_POOL || t->n_arm > 8 || t->n_fin > 8 || t->n_hum > 8) return fail(h, -1, "avg_upload_reset_table: counts out of range");
+    cudaSetDevice(h->device);
+    if (!h->d_rtab[variant]) AVG_CHECK(h, cudaMalloc(&h->d_rtab[variant], sizeof(AvgResetTable)));
+    AVG_CHECK(h, cudaMemcpy(h->d_rtab[variant], table, sizeof(AvgResetTable), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    AvgResetArgs r; memset(&r, 0, sizeof(r));
+    int nv = 0;
+    while (nv < AVG_K_MAX_VARIANTS && h->d_rtab[nv]) { r.tables[nv] = h->d_rtab[nv]; nv++; }
+    if (nv == 0) return fail(h, -1, "avg_reset: no reset table uploaded (avg_upload_reset_table)");
+    r.n_variants = nv; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
+    r.mask = mask; r.n_env = h->n_env; r.seed = seed;
+    AVG_CHECK(h, avg_launch_reset(r, (cudaStream_t)stream));
+    h->launches++;
+    if (obs) {
+        AvgStepArgs a; memset(&a, 0, sizeof(a));
+        int rc = fill_args(h, a, 0); if (rc) return rc;
+        a.obs = obs; a.mask = mask;
+        AVG_CHECK(h, avg_launch_reset_obs(a, (cudaStream_t)stream));
+        h->launches++;
+    }
+    return 0;
+}
+
+static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
     a.slot = h->slot;
@@ -215,7 +254,7 @@ int avg_reset_obs(AvgHandle* h, float* obs, void* stream) {
     if (!h || !obs) return -1;
     cudaSetDevice(h->device);
     AvgStepArgs a; memset(&a, 0, sizeof(a));
-    int rc = fill_args(h, a); if (rc) return rc;
+    int rc = fill_args(h, a, 0); if (rc) return rc;
     a.obs = obs;
     AVG_CHECK(h, avg_launch_reset_obs(a, (cudaStream_t)stream));
     h->launches++;
@@ -226,7 +265,7 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     if (!h || !actions || !obs || !reward || !info) return -1;
     cudaSetDevice(h->device);
     AvgStepArgs a; memset(&a, 0, sizeof(a));
-    int rc = fill_args(h, a); if (rc) return rc;
+    int rc = fill_args(h, a, 0); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
     h->np_phase[0] = a.np_phase;

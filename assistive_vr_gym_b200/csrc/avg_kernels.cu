@@ -1685,6 +1685,7 @@ avg_epilogue_kernel(AvgStepArgs a) {
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_reset_obs_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmEpi)
+    if (a.mask && !a.mask[e]) return;
     for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
     __syncwarp();
     const int* env_i = reinterpret_cast<const int*>(s.env);
@@ -1698,6 +1699,71 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     __syncwarp();
     const int nobs = h->n_obs_robot + h->n_obs_human;
     for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
+}
+
+// Episode reset on the device: the random draws of ScratchItchEnv.reset (scratch_itch.py:155-162,230-256,275-287),
+// create_new_world (world_creation.py:66-72) and setup_human_joints (world_creation.py:136-141,172) restated as in
+// compiler/reset.py sample_states(), with counter-based random numbers (AVG_RNG_MIX) so that any subset of
+// environments can be reset without a host round trip.  One thread per environment.
+namespace {
+__device__ __forceinline__ uint32_t reset_u32(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
+    uint32_t h = seed;
+    AVG_RNG_MIX(h); h ^= env * 0x9e3779b9u;
+    AVG_RNG_MIX(h); h ^= episode * 0x7f4a7c15u;
+    AVG_RNG_MIX(h); h ^= k * 0x94d049bbu;
+    AVG_RNG_MIX(h);
+    return h;
+}
+__device__ __forceinline__ float reset_u01(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
+    return (float)(reset_u32(seed, env, episode, k) >> 8) * (1.0f / 16777216.0f);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+avg_reset_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env) return;
+    if (r.mask && !r.mask[e]) return;
+    const uint32_t ep = (uint32_t)(r.episode[e] + 1);
+    r.episode[e] = (int32_t)ep;
+    const uint32_t sd = r.seed, ue = (uint32_t)e;
+    const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)r.n_variants);                      // gender, scratch_itch.py:156
+    const AvgResetTable* T = r.tables[v];
+    const int impairment = (int)(reset_u32(sd, ue, ep, 1) & 3u);                                  // none, limits, weakness, tremor
+    const float limit_scale = impairment == 1 ? 0.5f + 0.5f * reset_u01(sd, ue, ep, 2) : 1.0f;    // world_creation.py:70
+    const float strength = impairment == 2 ? 0.25f + 0.75f * reset_u01(sd, ue, ep, 3) : 1.0f;     // world_creation.py:71
+    float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    int* rec_i = reinterpret_cast<int*>(rec);
+    for (int i = 0; i < AVG_ENV_STRIDE; ++i) rec[i] = 0.0f;
+    const int k = (int)(reset_u32(sd, ue, ep, 17) % (uint32_t)T->n_pool);
+    for (int j = 0; j < T->n_arm; ++j) { rec[AVG_E_Q + T->arm_qidx[j]] = T->pool_q[k][j]; rec[AVG_E_MTARGET + T->arm_dof[j]] = T->pool_q[k][j]; }
+    for (int j = 0; j < T->n_fin; ++j) { rec[AVG_E_Q + T->fin_qidx[j]] = 1.0f; rec[AVG_E_MTARGET + T->fin_dof[j]] = 1.0f; }
+    for (int j = 0; j < T->n_hum; ++j) {
+        const float q = fminf(fmaxf(T->hum_reset[j], T->hum_lower[j] * limit_scale), T->hum_upper[j] * limit_scale);   // world_creation.py:172
+        rec[AVG_E_Q + T->hum_qidx[j]] = q; rec[AVG_E_MTARGET + T->hum_dof[j]] = q;
+        rec[AVG_E_TARGET_H + T->hum_joint[j] - 4] = q;                                            // scratch_itch.py:235
+    }
+    for (int j = 0; j < 7; ++j) rec[AVG_E_Q + T->tool_qidx + j] = T->pool_tool[k][j];
+    const float deg10 = 0.17453292519943295f;
+    for (int j = 0; j < 10; ++j) rec[AVG_E_TREMOR + j] = impairment == 3 ? (2.0f * reset_u01(sd, ue, ep, 4 + j) - 1.0f) * deg10 : 0.0f;   // world_creation.py:141
+    const int limb = (int)(reset_u32(sd, ue, ep, 14) & 1u);                                       // scratch_itch.py:278
+    const float length = T->limb_dims[limb][0], radius = T->limb_dims[limb][1];
+    const float rl = radius + reset_u01(sd, ue, ep, 15) * (length - radius);                      // util.py:118
+    const float th = 6.283185307179586f * reset_u01(sd, ue, ep, 16);
+    float sn, cs; sincosf(th, &sn, &cs);
+    rec[AVG_E_TARGET_ON_ARM + 0] = -radius * sn; rec[AVG_E_TARGET_ON_ARM + 1] = -radius * cs; rec[AVG_E_TARGET_ON_ARM + 2] = -rl;
+    rec_i[AVG_E_LIMB_FRAME] = limb == 0 ? AVG_F_SHOULDER : AVG_F_ELBOW;
+    rec[AVG_E_STRENGTH] = strength; rec[AVG_E_LIMIT_SCALE] = limit_scale;
+    rec[AVG_E_TREMOR_ON] = impairment == 3 ? 1.0f : 0.0f;
+    rec[AVG_E_HUMAN_KP] = (T->human_control || impairment == 3) ? 0.05f : 0.01f;                 // scratch_itch.py:45 / :231
+    r.variant[e] = v;
+    int* scr_i = reinterpret_cast<int*>(r.scratch + (size_t)e * AVG_S_STRIDE);
+    scr_i[AVG_S_NSEP] = 0; scr_i[AVG_S_NC] = 0; scr_i[AVG_S_NCS] = 0; scr_i[AVG_S_NQ] = 0;    // no certificates / contacts carried over
+}
+
+cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream) {
+    avg_reset_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    return cudaGetLastError();
 }
 
 // parity tap for the arm-limit classifier: raw joint angles (tz, tx, ty, qe) of joints 7..10 -> logit, one warp per pose

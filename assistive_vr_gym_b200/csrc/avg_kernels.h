@@ -70,6 +70,7 @@ struct AvgStepArgs {
     int* np_count;                                     // [2] item counters, used alternately (np_phase), reset by the narrowphase kernel
     int np_capacity;
     int np_phase;                                      // running sub-step index & 1
+    const uint8_t* mask;                               // reset paths: environments to touch (null = all)
     unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)
 };
 
@@ -79,3 +80,14 @@ cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
 /* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */
 cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blob, const AvgModelHeader* host_header);
+/* Device-side episode reset (reference ScratchItchEnv.reset draws): rewrites the records of the masked environments from
+ * the per-variant reset tables, bumps their episode counters, empties their scratch state. */
+struct AvgResetArgs {
+    const AvgResetTable* tables[AVG_K_MAX_VARIANTS];
+    int n_variants;
+    float* env; float* scratch; int32_t* variant; int32_t* episode;
+    const uint8_t* mask;
+    int n_env;
+    uint32_t seed;
+};
+cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream);

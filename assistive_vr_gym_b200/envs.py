@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import capi
-from .compiler.reset import sample_states
+from .compiler.reset import reset_table_bytes, sample_states
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 MAX_EPISODE_STEPS = 200      # reference __init__.py:21
@@ -82,6 +82,7 @@ class BatchedAssistiveEnv:
         self.sim = capi.Sim(self.num_envs, device)
         for v, b in enumerate(self.blobs):
             self.sim.upload_model(v, b)
+            self.sim.upload_reset_table(v, reset_table_bytes(self.reset_data[v]))
         self.action_robot_len = 7
         self.action_human_len = 10 if self.spec["human_control"] else 0
         self.obs_robot_len = 30
@@ -112,6 +113,25 @@ class BatchedAssistiveEnv:
         """scratch_itch.py:130-273, batched: samples every env's post-reset state on the host and uploads it."""
         env, variant = sample_states(self.reset_data, self.num_envs, self.np_random, genders)
         self.set_state(env, variant)
+        return self.obs
+
+    def reset_device(self, mask=None, seed: Optional[int] = None):
+        """Reset on the GPU (avg_reset): `mask` = CUDA bool/uint8 tensor [N] of environments to restart (None = all).
+        No host round trip, so it can follow a step directly (per-environment auto-reset for training loops); the
+        draws are those of `reset()` but from the counter-based generator of the device sampler."""
+        torch = self.torch
+        if seed is None:
+            seed = int(self.np_random.randint(1 << 31)) if not hasattr(self, "_device_seed") else self._device_seed
+        self._device_seed = seed
+        mptr = 0
+        if mask is not None:
+            self._mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = self._mask.data_ptr()
+        self.sim.reset_device(mptr, seed, self.obs.data_ptr(), self._stream())
+        if mask is None:
+            self.elapsed = 0
+        self.variants = None          # now lives on the device only
+        self._needs_reset = False
         return self.obs
 
     def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None):

@@ -42,6 +42,16 @@ int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records
 /* Device pointer of the state arena ([n_env][AVG_ENV_STRIDE] floats) for zero-copy inspection. */
 float* avg_state_device_ptr(AvgHandle* h);
 
+/* Episode reset on the device: replaces ScratchItchEnv.reset (scratch_itch.py:130-273) for the environments whose byte
+ * in `mask` (DEVICE, [n_env], NULL = all) is non-zero, without a host round trip: gender, impairment and its
+ * parameters (world_creation.py:66-72), tremor amplitudes (:141), a start pose from the variant's pool of IK solutions
+ * (scratch_itch.py:251-253), limb and the target point on it (scratch_itch.py:278, util.py:118,129), with
+ * counter-based random numbers keyed by (seed, environment, episode count).  Needs avg_upload_reset_table for every
+ * variant (HOST pointer to an AvgResetTable, include/avg_model.h).  obs (DEVICE, may be NULL) receives the initial
+ * observation of the reset environments; other rows are left alone.  Asynchronous on `stream`. */
+int avg_upload_reset_table(AvgHandle* h, int variant, const void* table, size_t nbytes);
+int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void* stream);
+
 /* Initial observation after reset, ScratchItchEnv._get_obs([0],[0,0]) (scratch_itch.py:268).  obs is a DEVICE
  * pointer [n_env][n_obs].  Asynchronous on `stream`. */
 int avg_reset_obs(AvgHandle* h, float* obs, void* stream);

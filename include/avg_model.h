@@ -179,6 +179,27 @@ enum {
     AVG_E_LAST = 169
 };
 
+/* ---- episode reset on the device (reference ScratchItchEnv.reset random draws) ----
+ * Per model variant, what the sampler needs as plain arrays (written by compiler/reset.py: reset_table_bytes()). */
+#define AVG_RESET_POOL 64
+typedef struct AvgResetTable {
+    int32_t n_pool, n_arm, n_fin, n_hum;
+    int32_t tool_qidx, human_control, pad[2];
+    float   pool_q[AVG_RESET_POOL][8];    /* robot arm joint positions of an IK start pose (scratch_itch.py:251-253, util.py:34-57) */
+    float   pool_tool[AVG_RESET_POOL][8]; /* tool base pose (pos, quat, pad) that goes with it (world_creation.py:331-337)          */
+    int32_t arm_qidx[8], arm_dof[8];      /* position / velocity slots of the 7 arm joints                                          */
+    int32_t fin_qidx[8], fin_dof[8];      /* gripper joints, opened to 1.0 (scratch_itch.py:254)                                    */
+    int32_t hum_qidx[8], hum_dof[8], hum_joint[8];   /* dynamic human joints (reference joint index 7..13)                          */
+    float   hum_lower[8], hum_upper[8], hum_reset[8];
+    float   limb_dims[2][2];              /* (length, radius) of upper arm and forearm (scratch_itch.py:277-280)                     */
+} AvgResetTable;
+
+/* Counter-based random numbers of the device reset: draw k of episode `episode` of environment `env` under `seed`.
+ * A 32-bit mix (murmur3 finaliser over a running hash); the numpy mirror in compiler/reset.py computes the same bits.
+ * Draw indices: 0 gender, 1 impairment, 2 limit scale, 3 strength, 4..13 tremor, 14 limb, 15 point along the limb,
+ * 16 angle around the limb, 17 start pose. */
+#define AVG_RNG_MIX(h) do { (h) ^= (h) >> 16; (h) *= 0x85ebca6bu; (h) ^= (h) >> 13; (h) *= 0xc2b2ae35u; (h) ^= (h) >> 16; } while (0)
+
 /* one reported contact point (parity / debug), 16 floats */
 typedef struct AvgContact {
     int32_t shape_a, shape_b;     /* shape indices, A is the moving shape listed first in the pair table        */
