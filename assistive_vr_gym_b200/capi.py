@@ -18,6 +18,7 @@ EXPORTS = [
     "avg_state_device_ptr", "avg_reset_obs", "avg_step", "avg_step_host", "avg_enable_debug", "avg_get_contacts",
     "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
     "avg_bytes_per_env_step", "avg_arm_limit_logits", "avg_alloc_host", "avg_free_host", "avg_upload_reset_table", "avg_reset",
+    "avg_upload_policy", "avg_policy_act",
 ]
 
 CONTACT_DT = np.dtype([("shape_a", "<i4"), ("shape_b", "<i4"), ("pos_a", "<f4", 3), ("pos_b", "<f4", 3),
@@ -59,6 +60,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_get_reward_terms.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.avg_upload_reset_table.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
     lib.avg_reset.argtypes = [vp, vp, ctypes.c_uint32, vp, vp]
+    lib.avg_upload_policy.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+    lib.avg_policy_act.argtypes = [vp, vp, vp, vp]
     lib.avg_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.avg_free_host.argtypes = [vp]
     lib.avg_arm_limit_logits.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
@@ -141,6 +144,12 @@ class Sim:
     def reset_device(self, mask_ptr: int, seed: int, obs_ptr: int, stream: int = 0):
         """avg_reset: mask_ptr = device uint8[n_env] or 0 (all)."""
         self._check(self.lib.avg_reset(self.h, mask_ptr or None, seed & 0xffffffff, obs_ptr or None, stream), "avg_reset")
+
+    def upload_policy(self, blob: bytes):
+        self._check(self.lib.avg_upload_policy(self.h, blob, len(blob)), "avg_upload_policy")
+
+    def policy_act(self, obs_ptr: int, act_ptr: int, stream: int = 0):
+        self._check(self.lib.avg_policy_act(self.h, obs_ptr, act_ptr, stream), "avg_policy_act")
 
     def reset_obs(self, obs_ptr: int, stream: int = 0):
         self._check(self.lib.avg_reset_obs(self.h, obs_ptr, stream), "avg_reset_obs")

@@ -23,6 +23,7 @@ struct AvgHandle {
     int substeps = 5;
     int maxblk = 0;
     int32_t* d_variant = nullptr;
+    unsigned char* d_policy = nullptr;                 // uploaded policy blob (avg_upload_policy)
     int32_t* d_episode = nullptr;                      // episodes started per environment (device reset counter)
     AvgResetTable* d_rtab[AVG_K_MAX_VARIANTS] = {nullptr, nullptr, nullptr, nullptr};
     // debug taps
@@ -117,7 +118,7 @@ int avg_destroy(AvgHandle* h) {
     for (int k = 0; k < 2; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
     if (h->stream2) cudaStreamDestroy(h->stream2);
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) { cudaFree(h->d_model[v]); cudaFree(h->d_rtab[v]); }
-    cudaFree(h->d_episode);
+    cudaFree(h->d_episode); cudaFree(h->d_policy);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
@@ -200,6 +201,32 @@ int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records
 float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset);
+
+int avg_upload_policy(AvgHandle* h, const void* blob, size_t nbytes) {
+    if (!h || !blob) return -1;
+    if (h->task < 0) return fail(h, -1, "avg_upload_policy: upload a model first");
+    if (nbytes < sizeof(AvgPolicyHeader)) return fail(h, -1, "avg_upload_policy: blob too small");
+    const AvgPolicyHeader* ph = (const AvgPolicyHeader*)blob;
+    if (ph->magic != AVG_POLICY_MAGIC) return fail(h, -1, "avg_upload_policy: bad magic");
+    if (ph->n_in <= 0 || ph->n_in > 64 || ph->n_in > h->n_obs || ph->n_out <= 0 || ph->n_out > 32 || ph->n_out > h->n_act)
+        return fail(h, -1, "avg_upload_policy: observation / action widths do not fit this environment");
+    const size_t need = sizeof(AvgPolicyHeader) + sizeof(float) * ((size_t)2 * ph->n_in + (size_t)ph->n_in * 64 + 64 + 4096 + 64 + (size_t)64 * ph->n_out + ph->n_out);
+    if (nbytes != need) return fail(h, -1, "avg_upload_policy: size mismatch");
+    cudaSetDevice(h->device);
+    cudaFree(h->d_policy); h->d_policy = nullptr;
+    AVG_CHECK(h, cudaMalloc(&h->d_policy, nbytes));
+    AVG_CHECK(h, cudaMemcpy(h->d_policy, blob, nbytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int avg_policy_act(AvgHandle* h, const float* obs, float* actions, void* stream) {
+    if (!h || !obs || !actions) return -1;
+    if (!h->d_policy) return fail(h, -1, "avg_policy_act: no policy uploaded (avg_upload_policy)");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, avg_launch_policy(h->d_policy, obs, actions, h->n_env, h->n_obs, h->n_act, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
 
 int avg_upload_reset_table(AvgHandle* h, int variant, const void* table, size_t nbytes) {
     if (!h || !table) return -1;

@@ -1766,6 +1766,52 @@ cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Policy inference (reference enjoy_vr.py:106-113 with the default a2c_ppo_acktr MLP actor): one warp per environment.
+// Lane u owns hidden units u and u + 32; inputs and activations travel by shuffle; weight rows are read coalesced and
+// stay L1/L2-resident (the whole policy is ~27 KB).
+__global__ void __launch_bounds__(128)
+avg_policy_kernel(const unsigned char* __restrict__ blob, const float* __restrict__ obs, float* __restrict__ actions, int n_env, int n_obs, int n_act) {
+    const int lane = threadIdx.x & 31, e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n_env) return;
+    const AvgPolicyHeader* ph = reinterpret_cast<const AvgPolicyHeader*>(blob);
+    const int n_in = ph->n_in, n_out = ph->n_out;
+    const float* mean = reinterpret_cast<const float*>(blob + sizeof(AvgPolicyHeader));
+    const float* var = mean + n_in;
+    const float* W1 = var + n_in; const float* b1 = W1 + n_in * 64;
+    const float* W2 = b1 + 64; const float* b2 = W2 + 4096;
+    const float* W3 = b2 + 64; const float* b3 = W3 + 64 * n_out;
+    // VecNormalize: clip((obs - mean) / sqrt(var + eps), -clip, clip)
+    float x0 = 0.0f, x1 = 0.0f;
+    if (lane < n_in) x0 = fminf(fmaxf((obs[(size_t)e * n_obs + lane] - __ldg(mean + lane)) * rsqrtf(__ldg(var + lane) + ph->eps), -ph->clip_obs), ph->clip_obs);
+    if (lane + 32 < n_in) x1 = fminf(fmaxf((obs[(size_t)e * n_obs + lane + 32] - __ldg(mean + lane + 32)) * rsqrtf(__ldg(var + lane + 32) + ph->eps), -ph->clip_obs), ph->clip_obs);
+    float a0 = __ldg(b1 + lane), a1 = __ldg(b1 + lane + 32);
+    for (int k = 0; k < n_in; ++k) {
+        const float xk = __shfl_sync(AVG_FULL, k < 32 ? x0 : x1, k & 31);
+        a0 = fmaf(xk, __ldg(W1 + k * 64 + lane), a0); a1 = fmaf(xk, __ldg(W1 + k * 64 + lane + 32), a1);
+    }
+    float h0 = tanhf(a0), h1 = tanhf(a1);
+    a0 = __ldg(b2 + lane); a1 = __ldg(b2 + lane + 32);
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const float u = __shfl_sync(AVG_FULL, h0, j), v = __shfl_sync(AVG_FULL, h1, j);
+        a0 = fmaf(u, __ldg(W2 + j * 64 + lane), a0); a1 = fmaf(u, __ldg(W2 + j * 64 + lane + 32), a1);
+        a0 = fmaf(v, __ldg(W2 + (j + 32) * 64 + lane), a0); a1 = fmaf(v, __ldg(W2 + (j + 32) * 64 + lane + 32), a1);
+    }
+    h0 = tanhf(a0); h1 = tanhf(a1);
+    float out = lane < n_out ? __ldg(b3 + lane) : 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const float u = __shfl_sync(AVG_FULL, h0, j), v = __shfl_sync(AVG_FULL, h1, j);
+        if (lane < n_out) out = fmaf(v, __ldg(W3 + (j + 32) * n_out + lane), fmaf(u, __ldg(W3 + j * n_out + lane), out));
+    }
+    if (lane < n_act) actions[(size_t)e * n_act + lane] = lane < n_out ? out : 0.0f;        // enjoy_vr.py:112-113: the human half is zero
+}
+
+cudaError_t avg_launch_policy(const unsigned char* policy_blob, const float* obs, float* actions, int n_env, int n_obs, int n_act, cudaStream_t stream) {
+    avg_policy_kernel<<<(n_env + 3) / 4, 128, 0, stream>>>(policy_blob, obs, actions, n_env, n_obs, n_act);
+    return cudaGetLastError();
+}
+
 // parity tap for the arm-limit classifier: raw joint angles (tz, tx, ty, qe) of joints 7..10 -> logit, one warp per pose
 __global__ void __launch_bounds__(128)
 avg_arm_limit_kernel(const unsigned char* blob, const float* __restrict__ q4, float* __restrict__ logits, int n) {

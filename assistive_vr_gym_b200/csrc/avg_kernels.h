@@ -91,3 +91,5 @@ struct AvgResetArgs {
     uint32_t seed;
 };
 cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream);
+/* Policy inference for on-device rollouts: obs [n_env][n_obs] -> actions [n_env][n_act] (enjoy_vr.py:106-113). */
+cudaError_t avg_launch_policy(const unsigned char* policy_blob, const float* obs, float* actions, int n_env, int n_obs, int n_act, cudaStream_t stream);

@@ -134,6 +134,24 @@ class BatchedAssistiveEnv:
         self._needs_reset = False
         return self.obs
 
+    def set_policy(self, blob: bytes):
+        """Upload a policy (assistive_vr_gym_b200.policy) for `act()` / `rollout()`."""
+        self.sim.upload_policy(blob)
+        if not hasattr(self, "actions_dev"):
+            self.actions_dev = self.torch.zeros((self.num_envs, self.sim.n_actions), dtype=self.torch.float32, device=self.device)
+
+    def act(self):
+        """Deterministic policy action for the current observations (enjoy_vr.py:106-113), on the device."""
+        self.sim.policy_act(self.obs.data_ptr(), self.actions_dev.data_ptr(), self._stream())
+        return self.actions_dev
+
+    def rollout(self, n_steps: int):
+        """`n_steps` of act -> step without leaving the GPU (the loop of enjoy_vr.py:105-117)."""
+        out = None
+        for _ in range(n_steps):
+            out = self.step(self.act())
+        return out
+
     def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None):
         """Import explicit env records ("identical initial states" for parity runs)."""
         self.variants = variant

@@ -256,6 +256,29 @@ def main():
         episode = {"value": E * world * 200 / (float(tep.item()) * 1e-3), "unit": UNIT, "steps": 200,
                    "note": "mean over a full 200-step random-action episode from reset (device-resident I/O)"}
 
+    # ---- synthetic-policy rollout (extra): obs -> MLP actor -> action -> step, all on the device, from a fresh reset
+    #      (north_star asks for random-action AND policy rollouts; no checkpoint ships with the reference) ---
+    policy = None
+    if not args.no_episode:
+        from assistive_vr_gym_b200.policy import synthetic_policy
+        blob, _ = synthetic_policy(env.obs_robot_len, env.action_robot_len, seed=0)
+        env.set_policy(blob)
+        env.reset()
+        env.rollout(3); env.elapsed = 0
+        barrier()
+        p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for k in range(50):
+            env.step(env.act()); env.elapsed = 0
+        p1.record(stream)
+        barrier()
+        tpo = torch.tensor([p0.elapsed_time(p1)], device=dev)
+        if distributed:
+            dist.all_reduce(tpo, op=dist.ReduceOp.MAX)
+        policy = {"value": E * world * 50 / (float(tpo.item()) * 1e-3), "unit": UNIT, "steps": 50,
+                  "note": "synthetic-policy rollout: orthogonal-init 30-64-64-7 tanh actor on VecNormalize'd observations, inference fused on "
+                          "the device (avg_policy_act), steps 3-52 after reset"}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpe = env.sim.bytes_per_env_step
@@ -290,6 +313,8 @@ def main():
                                   "mean_force_on_human": float(stats[2] / stats[3])}}
         if episode is not None:
             line["episode"] = episode
+        if policy is not None:
+            line["policy_rollout"] = policy
         if not args.no_cpu_baseline and world == 1:
             v, c, sample = cpu_oracle_throughput(16, 200)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}

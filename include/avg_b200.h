@@ -83,6 +83,14 @@ int avg_get_contacts(AvgHandle* h, int env_begin, int env_count, void* contacts,
  * reward_distance, reward_action, reward_force_scratch, preferences_score. */
 int avg_get_reward_terms(AvgHandle* h, int env_begin, int env_count, float* terms);
 
+/* Policy inference for rollouts that never leave the GPU: replaces `actor_critic.act(obs, ..., deterministic=True)` on
+ * VecNormalize'd observations (enjoy_vr.py:77-113) for the default a2c_ppo_acktr MLP actor.  avg_upload_policy takes a
+ * HOST blob (AvgPolicyHeader + float32 arrays, include/avg_model.h); avg_policy_act maps obs (DEVICE [n_env][n_obs]) to
+ * actions (DEVICE [n_env][n_action]; columns beyond the policy's outputs are zero, enjoy_vr.py:112-113).
+ * Asynchronous on `stream`. */
+int avg_upload_policy(AvgHandle* h, const void* blob, size_t nbytes);
+int avg_policy_act(AvgHandle* h, const float* obs, float* actions, void* stream);
+
 /* Parity tap for enforce_realistic_human_joint_limits (env.py:353-371), which the step applies after every sub-step
  * of the human-active ids: replaces human_limits_model.predict_classes (env.py:364).  q4: DEVICE [n][4] raw joint
  * angles (tz, tx, ty, qe) of human joints 7..10; logits: DEVICE [n], class 1 (valid pose) <=> logit > 0.

@@ -200,6 +200,21 @@ typedef struct AvgResetTable {
  * 16 angle around the limb, 17 start pose. */
 #define AVG_RNG_MIX(h) do { (h) ^= (h) >> 16; (h) *= 0x85ebca6bu; (h) ^= (h) >> 13; (h) *= 0xc2b2ae35u; (h) ^= (h) >> 16; } while (0)
 
+/* ---- policy for on-device rollouts (reference enjoy_vr.py:77-117: actor_critic.act on VecNormalize'd observations) ----
+ * The default a2c_ppo_acktr actor: observations normalised with the running statistics (clip +-10), two tanh layers of
+ * 64 units, a linear mean layer; deterministic action = the mean.  Blob = this header, then float32 arrays
+ * ob_mean[n_in], ob_var[n_in], W1[n_in][64], b1[64], W2[64][64], b2[64], W3[64][n_out], b3[n_out]. */
+#define AVG_POLICY_MAGIC 0x4c505641u  /* "AVPL" */
+#define AVG_POLICY_HIDDEN 64
+typedef struct AvgPolicyHeader {
+    uint32_t magic;
+    int32_t  n_in;                /* leading observation columns the policy reads (obs_robot_len, enjoy_vr.py:92,117) */
+    int32_t  n_out;               /* leading action columns it writes (action_robot_len); the rest are zero (enjoy_vr.py:112-113) */
+    float    clip_obs;            /* 10.0 (VecNormalize clipob) */
+    float    eps;                 /* 1e-8 (VecNormalize epsilon) */
+    int32_t  pad[3];
+} AvgPolicyHeader;
+
 /* one reported contact point (parity / debug), 16 floats */
 typedef struct AvgContact {
     int32_t shape_a, shape_b;     /* shape indices, A is the moving shape listed first in the pair table        */
