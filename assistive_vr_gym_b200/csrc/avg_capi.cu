@@ -39,7 +39,7 @@ struct AvgHandle {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     // narrowphase work queues: set 0 for avg_step and even chunks of avg_step_host, set 1 for odd chunks (second stream)
-    AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0, np_phase[2] = {0, 0};
+    AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0;
     cudaStream_t stream2 = nullptr;
     unsigned long long* d_cnt = nullptr;               // AVG_DBG & 32 (development aid)
     std::string err;
@@ -267,7 +267,7 @@ static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset) {
     a.slot = h->slot;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
-    a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity; a.np_phase = h->np_phase[qset];
+    a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity;
     a.env_begin = 0; a.env_end = h->n_env;
     if ((a.dbg & 32) && !h->d_cnt) { cudaMalloc(&h->d_cnt, 64); cudaMemset(h->d_cnt, 0, 64); }
     a.dbg_counters = (a.dbg & 32) ? h->d_cnt : nullptr;
@@ -295,7 +295,6 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     int rc = fill_args(h, a, 0); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-    h->np_phase[0] = a.np_phase;
     h->launches += avg_kernels_per_step(h->substeps);
     return 0;
 }
@@ -357,7 +356,6 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
         a.actions = h->d_act; a.obs = h->d_obs; a.reward = h->d_rew; a.done = h->d_done; a.info = h->d_info;
         a.env_begin = b0; a.env_end = b1;
         AVG_CHECK(h, avg_launch_step(a, h->substeps, st));
-        h->np_phase[qs] = a.np_phase;
         h->launches += avg_kernels_per_step(h->substeps);
         AVG_CHECK(h, cudaMemcpyAsync(dst_obs + (size_t)b0 * h->n_obs, h->d_obs + (size_t)b0 * h->n_obs, sizeof(float) * cnt * h->n_obs, cudaMemcpyDeviceToHost, st));
         AVG_CHECK(h, cudaMemcpyAsync(dst_rew + b0, h->d_rew + b0, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));

@@ -838,7 +838,7 @@ avg_collide_kernel(AvgStepArgs a) {
     float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
     int nsep = (a.dbg & 16) ? 0 : min(max(scr_i[AVG_S_NSEP], 0), AVG_S_NSEPMAX);
     if (lane < nsep) { s.sep[0][lane] = gsep[lane]; s.sep[1][lane] = gsep[AVG_S_NSEPMAX + lane]; s.sep[2][lane] = gsep[2 * AVG_S_NSEPMAX + lane]; }
-    if (!(a.dbg & 4)) collide_warp(m, s, lane, e, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.np_queue, a.np_count + (a.np_phase & 1),
+    if (!(a.dbg & 4)) collide_warp(m, s, lane, e, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.np_queue, a.np_count,
                                    a.np_capacity, a.dbg);
     if (lane == 0) { scr_i[AVG_S_NQ] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
 }
@@ -867,10 +867,9 @@ __global__ void __launch_bounds__(128)
 avg_narrow_kernel(AvgStepArgs a) {
     // one THREAD per work item; the 32 items of a warp advance through the certificate test and the GJK iterations in
     // lockstep so that hull support scans can be served by the whole warp (support_any)
-    const int count = min(a.np_count[a.np_phase & 1], a.np_capacity);
+    const int count = min(a.np_count[0], a.np_capacity);
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.np_count[(a.np_phase + 1) & 1] = 0;   // the counter of the next sub-step (idle during this kernel)
     for (int base = wid * 32; base < count; base += nwarps * 32) {
         const int i = base + lane;
         const bool valid = i < count;
@@ -969,6 +968,8 @@ avg_dynamics_kernel(AvgStepArgs a) {
     int* scr_i = reinterpret_cast<int*>(scr);
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
     int overflow = 0;
+    // the narrowphase queue has been drained by the kernel before this one; empty it for the next sub-step's collide kernel
+    if (e == a.env_begin && lane == 0) a.np_count[0] = 0;
     // contacts: the hits among the narrowphase results, compacted in pair order; the list is also written to the arena
     // for the solver (impulses) and the epilogue
     int ncontact;
@@ -1852,7 +1853,7 @@ struct KernelTimes {
 KernelTimes g_kt;
 }  // namespace
 
-cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream) {
+cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
     static bool configured = false;
     const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
     const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
@@ -1888,7 +1889,6 @@ cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream) {
         avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
         mark();
         avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
-        a.np_phase ^= 1;
         mark();
         if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
         else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);

@@ -67,15 +67,14 @@ struct AvgStepArgs {
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
     int dbg;                                           // development switches (AVG_DBG), 0 in production
     AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
-    int* np_count;                                     // [2] item counters, used alternately (np_phase), reset by the narrowphase kernel
+    int* np_count;                                     // item counter: filled by the collide kernel, read by the narrowphase kernel, zeroed by the dynamics kernel
     int np_capacity;
-    int np_phase;                                      // running sub-step index & 1
     const uint8_t* mask;                               // reset paths: environments to touch (null = all)
     unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)
 };
 
 int avg_kernels_per_step(int substeps);
-cudaError_t avg_launch_step(AvgStepArgs& a, int substeps, cudaStream_t stream);   /* advances a.np_phase by `substeps` */
+cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
 /* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */

@@ -148,3 +148,35 @@ def test_separating_axis_cache_only_skips_work(torch_cuda):
     assert out[0][2] == out[1][2] and out[0][2] > 100            # contacts happened and are the same in number
     assert np.array_equal(out[0][0][:, :64], out[1][0][:, :64])  # q, qd bit-identical
     assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_step_is_cuda_graph_capturable(torch_cuda):
+    """the step is a fixed launch sequence on one stream with no hidden synchronisation, so it can be
+    captured once and replayed; replays are bit-identical to eager steps."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 4096
+    acts = torch.rand((6, n, 7), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 2 - 1
+    ref = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=31); ref.reset()
+    env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=31); env.reset()
+    for t in range(2):                                         # warm-up outside the capture (function attributes, lazy state)
+        ref.step(acts[t]); env.step(acts[t])
+    static_act = torch.zeros((n, 7), device="cuda")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        static_act.copy_(acts[2])
+        side.synchronize()
+        g.capture_begin()
+        env.sim.step(static_act.data_ptr(), env.obs.data_ptr(), env.reward.data_ptr(), env.done_dev.data_ptr(), env.info_dev.data_ptr(),
+                     int(torch.cuda.current_stream().cuda_stream))
+        g.capture_end()
+    for t in range(2, 6):
+        static_act.copy_(acts[t])
+        g.replay()
+        ref.step(acts[t])
+    torch.cuda.synchronize()
+    assert torch.equal(env.obs, ref.obs) and torch.equal(env.reward, ref.reward)
+    assert np.array_equal(env.get_state()[:, :64], ref.get_state()[:, :64])
+    env.close(); ref.close()
