@@ -8,7 +8,7 @@ from .mbody import JOINT_FREE, SHAPE_HULL
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 8
+AVG_VERSION = 9
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -43,7 +43,8 @@ HEADER_DT = np.dtype([
     ("off_body", "<u4"), ("off_dof", "<u4"), ("off_shape", "<u4"), ("off_vert", "<u4"), ("off_plane", "<u4"),
     ("off_pair", "<u4"), ("off_frame", "<u4"), ("off_bps", "<u4"), ("off_bpm", "<u4"),
     ("n_block", "<i4"), ("block_start", "<i4", 4), ("off_bcap", "<u4"),
-    ("off_mlp", "<u4"), ("n_mlp", "<i4"), ("mlp_dof", "<i4", 4), ("pad2", "<u4", 2),
+    ("off_mlp", "<u4"), ("n_mlp", "<i4"), ("mlp_dof", "<i4", 4),
+    ("off_target", "<u4"), ("n_target", "<i4"), ("n_target_upper", "<i4"), ("pad2", "<u4", 3),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
 
@@ -180,6 +181,16 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
             if b.art == 1 and b.ref_joint in (7, 8, 9, 10):
                 mlp_dof[b.ref_joint - 7] = b.dof
 
+    # BedBathing wiping targets (bed_bathing.py:360-379)
+    tgt = np.zeros((0, 4), dtype="<f4")
+    n_target_upper = 0
+    if getattr(scene, "targets", None) is not None:
+        up, fo = scene.targets
+        n_target_upper = len(up)
+        tgt = np.zeros((len(up) + len(fo), 4), dtype="<f4")
+        tgt[:len(up), :3] = up; tgt[len(up):, :3] = fo
+        assert len(tgt) <= 160
+
     hdr = np.zeros(1, dtype=HEADER_DT)
     h = hdr[0]
     h["magic"] = AVG_MAGIC; h["version"] = AVG_VERSION
@@ -192,11 +203,12 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     h["n_pair"] = len(pairs); h["n_frame"] = len(frames)
     h["n_block"] = n_block; h["block_start"] = starts
     h["n_mlp"] = mlp.size; h["mlp_dof"] = mlp_dof
+    h["n_target"] = len(tgt); h["n_target_upper"] = n_target_upper
     off = _align(HEADER_DT.itemsize)
     sections = []
     for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
                       ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm),
-                      ("off_bcap", bcap), ("off_mlp", mlp)):
+                      ("off_bcap", bcap), ("off_mlp", mlp), ("off_target", tgt)):
         h[name] = off
         sections.append((off, arr.tobytes()))
         off = _align(off + arr.nbytes)
@@ -222,4 +234,5 @@ def read_blob(blob: bytes) -> dict:
     out["bps"] = np.frombuffer(blob, dtype=BPS_DT, count=int(h["n_shape"] - h["n_mshape"]), offset=int(h["off_bps"]))
     out["bpm"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_mshape"]), offset=int(h["off_bpm"]))
     out["mlp"] = np.frombuffer(blob, dtype="<f4", count=int(h["n_mlp"]), offset=int(h["off_mlp"]))
+    out["targets"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_target"]), offset=int(h["off_target"])).reshape(-1, 4)[:, :3]
     return out

@@ -27,6 +27,7 @@ E_STRENGTH, E_LIMIT_SCALE, E_HUMAN_KP, E_TREMOR_ON = 96, 97, 98, 99
 E_TREMOR, E_TARGET_H, E_TARGET_ON_ARM, E_LIMB_FRAME, E_EBODY = 100, 110, 120, 123, 124
 E_ITERATION, E_TASK_SUCCESS, E_PREV_CONTACT, E_VALID_POSE, E_HAS_VALID, E_TARGET_POS = 152, 153, 154, 157, 161, 162
 E_EPISODE_RETURN, E_OVERFLOW = 165, 166
+E_TARGET_MASK = 170
 F_SHOULDER, F_ELBOW = 5, 6
 
 
@@ -71,15 +72,22 @@ def ik_dls(mb: MultiBodyDesc, ee_link: int, joints: List[int], lower, upper, tar
     q = np.array(q0, dtype=np.float64)
     for _ in range(iters):
         p, r, J = ee_pose_and_jacobian(mb, dict(zip(joints, q)), ee_link, joints)
-        e = np.concatenate([target_pos - p, _rot_err(target_quat, r)])
-        if np.linalg.norm(e[:3]) < 1e-4 and np.linalg.norm(e[3:]) < 1e-3:
-            break
-        dq = J.T @ np.linalg.solve(J @ J.T + damping ** 2 * np.eye(6), e)
+        if target_quat is None:                       # position-only IK (calculateInverseKinematics without targetOrientation)
+            e = target_pos - p; J = J[:3]
+            if np.linalg.norm(e) < 1e-4:
+                break
+        else:
+            e = np.concatenate([target_pos - p, _rot_err(target_quat, r)])
+            if np.linalg.norm(e[:3]) < 1e-4 and np.linalg.norm(e[3:]) < 1e-3:
+                break
+        dq = J.T @ np.linalg.solve(J @ J.T + damping ** 2 * np.eye(len(e)), e)
         n = np.max(np.abs(dq))
         if n > 0.3:
             dq *= 0.3 / n
         q = np.clip(q + dq, lower, upper)
     p, r, _ = ee_pose_and_jacobian(mb, dict(zip(joints, q)), ee_link, joints)
+    if target_quat is None:
+        return q, float(np.linalg.norm(target_pos - p)), 0.0
     dq1 = np.linalg.norm(target_quat - r); dq2 = np.linalg.norm(target_quat + r)
     return q, float(np.linalg.norm(target_pos - p)), float(min(dq1, dq2))
 
@@ -151,8 +159,12 @@ def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, ge
     env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
     env_i = env.view(np.int32)
     nv = len(reset_data)
-    variant = (np.asarray(genders, dtype=np.int32) if genders is not None else rng.randint(nv, size=n).astype(np.int32))
+    task = int(reset_data[0].get("task", 0))
+    npg = max(nv // 2, 1)                                      # variants per gender (BedBathing: one per robot base pose)
+    gender = (np.asarray(genders, dtype=np.int32) if genders is not None else rng.randint(min(nv, 2), size=n).astype(np.int32))
     impairment = rng.randint(4, size=n)                        # 0 none, 1 limits, 2 weakness, 3 tremor
+    if task == 1:
+        impairment[:] = 0                                      # human_impairment='none', bed_bathing.py:198
     limit_scale = np.where(impairment == 1, rng.uniform(0.5, 1.0, size=n), 1.0)
     strength = np.where(impairment == 2, rng.uniform(0.25, 1.0, size=n), 1.0)
     tremor = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=(n, 10)) * (impairment == 3)[:, None]
@@ -160,21 +172,23 @@ def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, ge
     u_len = rng.uniform(0.0, 1.0, size=n)
     theta = rng.uniform(0, 2 * np.pi, size=n)
     pool_pick = rng.randint(1 << 30, size=n)
+    variant = (gender * npg + pool_pick % npg).astype(np.int32)
     for v in range(nv):
         idx = np.nonzero(variant == v)[0]
         if idx.size == 0:
             continue
         rd = reset_data[v]
-        k = pool_pick[idx] % len(rd["pool_q"])
+        k = (pool_pick[idx] // npg) % len(rd["pool_q"])
         qa = rd["pool_q"][k]
+        fin_open = float(rd.get("fin_open", 1.0))
         ls = limit_scale[idx][:, None]
         qh = np.clip(rd["hum_reset"][None, :], rd["hum_lower"][None, :] * ls, rd["hum_upper"][None, :] * ls)   # world_creation.py:172
         length = rd["limb_dims"][limb[idx], 0]; radius = rd["limb_dims"][limb[idx], 1]
         rl = radius + u_len[idx] * (length - radius)            # uniform(radius, length), util.py:118
         env[np.ix_(idx, E_Q + rd["arm_qidx"])] = qa
         env[np.ix_(idx, E_MTARGET + rd["arm_dof"])] = qa
-        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = 1.0
-        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = 1.0
+        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = fin_open
+        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = fin_open
         env[np.ix_(idx, E_Q + rd["hum_qidx"])] = qh
         env[np.ix_(idx, E_MTARGET + rd["hum_dof"])] = qh
         tq = int(rd["tool_qidx"])
@@ -182,6 +196,9 @@ def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, ge
         active = bool(rd["human_control"]) | (impairment[idx] == 3)
         env[idx, E_HUMAN_KP] = np.where(active, 0.05, 0.01)     # scratch_itch.py:45 / :231
         env[np.ix_(idx, E_TARGET_H + rd["hum_joint"] - 4)] = qh   # scratch_itch.py:235
+        if task == 1:
+            env_i[np.ix_(idx, E_TARGET_MASK + np.arange(5))] = target_mask_words(int(rd["n_target"]))[None, :]   # bed_bathing.py:369-379
+            continue
         th = theta[idx]
         env[idx, E_TARGET_ON_ARM + 0] = -radius * np.sin(th)
         env[idx, E_TARGET_ON_ARM + 1] = -radius * np.cos(th)
@@ -190,18 +207,27 @@ def sample_states(reset_data: List[dict], n: int, rng: np.random.RandomState, ge
     env[:, E_LIMIT_SCALE] = limit_scale
     env[:, E_TREMOR_ON] = (impairment == 3)
     env[:, E_TREMOR:E_TREMOR + 10] = tremor
-    env_i[:, E_LIMB_FRAME] = np.where(limb == 0, F_SHOULDER, F_ELBOW)
+    env_i[:, E_LIMB_FRAME] = F_SHOULDER if task == 1 else np.where(limb == 0, F_SHOULDER, F_ELBOW)
     return env, variant
+
+
+def target_mask_words(n_target: int) -> np.ndarray:
+    """AVG_E_TARGET_MASK words with the first n_target bits set (every wiping target still alive)."""
+    w = np.zeros(5, dtype=np.uint32)
+    for t in range(n_target):
+        w[t >> 5] |= np.uint32(1 << (t & 31))
+    return w.view(np.int32)
 
 
 # ---- device reset (include/avg_model.h AvgResetTable, csrc avg_reset_kernel) ------------------------------------------
 RESET_POOL = 64
 RESET_TABLE_DT = np.dtype([
-    ("n_pool", "<i4"), ("n_arm", "<i4"), ("n_fin", "<i4"), ("n_hum", "<i4"), ("tool_qidx", "<i4"), ("human_control", "<i4"), ("pad", "<i4", 2),
+    ("n_pool", "<i4"), ("n_arm", "<i4"), ("n_fin", "<i4"), ("n_hum", "<i4"), ("tool_qidx", "<i4"), ("human_control", "<i4"), ("task", "<i4"), ("n_target", "<i4"),
     ("pool_q", "<f4", (RESET_POOL, 8)), ("pool_tool", "<f4", (RESET_POOL, 8)),
     ("arm_qidx", "<i4", 8), ("arm_dof", "<i4", 8), ("fin_qidx", "<i4", 8), ("fin_dof", "<i4", 8),
     ("hum_qidx", "<i4", 8), ("hum_dof", "<i4", 8), ("hum_joint", "<i4", 8),
     ("hum_lower", "<f4", 8), ("hum_upper", "<f4", 8), ("hum_reset", "<f4", 8), ("limb_dims", "<f4", (2, 2)),
+    ("fin_open", "<f4"), ("pad_f", "<f4", 3),
 ])
 
 
@@ -216,6 +242,7 @@ def reset_table_bytes(rd: dict) -> bytes:
     for k in ("arm_qidx", "arm_dof", "fin_qidx", "fin_dof", "hum_qidx", "hum_dof", "hum_joint", "hum_lower", "hum_upper", "hum_reset"):
         t[k][:len(rd[k])] = rd[k]
     t["limb_dims"] = rd["limb_dims"]
+    t["task"] = int(rd.get("task", 0)); t["n_target"] = int(rd.get("n_target", 0)); t["fin_open"] = float(rd.get("fin_open", 1.0))
     return t.tobytes()
 
 
@@ -246,8 +273,12 @@ def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.
     env = np.zeros((n, ENV_STRIDE), dtype=np.float32)
     env_i = env.view(np.int32)
     nv = len(reset_data)
-    variant = (reset_u32(seed, env_idx, episode, 0) % np.uint32(nv)).astype(np.int32)
+    task = int(reset_data[0].get("task", 0))
+    npg = max(nv // 2, 1)
+    gender = (reset_u32(seed, env_idx, episode, 0) % np.uint32(min(nv, 2))).astype(np.int32)
     impairment = (reset_u32(seed, env_idx, episode, 1) & np.uint32(3)).astype(np.int32)
+    if task == 1:
+        impairment[:] = 0
     limit_scale = np.where(impairment == 1, f32(0.5) + f32(0.5) * reset_u01(seed, env_idx, episode, 2), f32(1.0)).astype(f32)
     strength = np.where(impairment == 2, f32(0.25) + f32(0.75) * reset_u01(seed, env_idx, episode, 3), f32(1.0)).astype(f32)
     deg10 = f32(0.17453292519943295)
@@ -257,13 +288,15 @@ def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.
     u_len = reset_u01(seed, env_idx, episode, 15)
     theta = f32(6.283185307179586) * reset_u01(seed, env_idx, episode, 16)
     pick = reset_u32(seed, env_idx, episode, 17)
+    variant = (gender * npg + (pick % np.uint32(npg)).astype(np.int32)).astype(np.int32)
     for v in range(nv):
         idx = np.nonzero(variant == v)[0]
         if idx.size == 0:
             continue
         rd = reset_data[v]
         n_pool = min(len(rd["pool_q"]), RESET_POOL)
-        k = (pick[idx] % np.uint32(n_pool)).astype(np.int64)
+        k = ((pick[idx] // np.uint32(npg)) % np.uint32(n_pool)).astype(np.int64)
+        fin_open = f32(rd.get("fin_open", 1.0))
         qa = rd["pool_q"][k].astype(f32)
         ls = limit_scale[idx][:, None]
         qh = np.minimum(np.maximum(rd["hum_reset"].astype(f32)[None, :], rd["hum_lower"].astype(f32)[None, :] * ls), rd["hum_upper"].astype(f32)[None, :] * ls)
@@ -271,8 +304,8 @@ def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.
         rl = radius + u_len[idx] * (length - radius)
         env[np.ix_(idx, E_Q + rd["arm_qidx"])] = qa
         env[np.ix_(idx, E_MTARGET + rd["arm_dof"])] = qa
-        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = 1.0
-        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = 1.0
+        env[np.ix_(idx, E_Q + rd["fin_qidx"])] = fin_open
+        env[np.ix_(idx, E_MTARGET + rd["fin_dof"])] = fin_open
         env[np.ix_(idx, E_Q + rd["hum_qidx"])] = qh
         env[np.ix_(idx, E_MTARGET + rd["hum_dof"])] = qh
         tq = int(rd["tool_qidx"])
@@ -280,6 +313,9 @@ def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.
         active = bool(rd["human_control"]) | (impairment[idx] == 3)
         env[idx, E_HUMAN_KP] = np.where(active, f32(0.05), f32(0.01))
         env[np.ix_(idx, E_TARGET_H + rd["hum_joint"] - 4)] = qh
+        if task == 1:
+            env_i[np.ix_(idx, E_TARGET_MASK + np.arange(5))] = target_mask_words(int(rd["n_target"]))[None, :]
+            continue
         th = theta[idx]
         env[idx, E_TARGET_ON_ARM + 0] = -radius * np.sin(th, dtype=f32)
         env[idx, E_TARGET_ON_ARM + 1] = -radius * np.cos(th, dtype=f32)
@@ -288,5 +324,122 @@ def sample_states_hashed(reset_data: List[dict], n: int, seed: int, episode: np.
     env[:, E_LIMIT_SCALE] = limit_scale
     env[:, E_TREMOR_ON] = (impairment == 3)
     env[:, E_TREMOR:E_TREMOR + 10] = tremor
-    env_i[:, E_LIMB_FRAME] = np.where(limb == 0, F_SHOULDER, F_ELBOW)
+    env_i[:, E_LIMB_FRAME] = F_SHOULDER if task == 1 else np.where(limb == 0, F_SHOULDER, F_ELBOW)
     return env, variant
+
+
+# =====================================================================================================================
+# BedBathing: robot base placement (reference AssistiveEnv.position_robot_toc, env.py:486-585) and the reset tables
+# =====================================================================================================================
+def joint_limited_weighting(q, lower, upper) -> np.ndarray:
+    """env.py:466-477"""
+    phi, lam = 0.5, 0.05
+    w = []
+    for qi, l, u in zip(q, lower, upper):
+        qr = 0.5 * (u - l)
+        w.append(max(1.0 - np.power(phi, (qr - np.abs(qr - qi + l)) / (lam * qr) + 1), 0.001))
+    return np.diag(w)
+
+
+def toc_search_jaco(robot: MultiBodyDesc, joints: List[int], start_pos, start_quat, goal_points, rng: np.random.RandomState,
+                    pos_offset, attempts: int = 100, random_rotation: float = 30.0, random_position: float = 0.1,
+                    max_ik_iterations: int = 200, ee_link: int = 8):
+    """`position_robot_toc` for a single-arm robot (env.py:486-585 as called at bed_bathing.py:325): `attempts` random
+    base poses (x in [-random_position, 0], y in +-random_position, yaw in +-random_rotation deg); a pose is usable when
+    IK reaches the start pose (position and orientation within 0.03, util.py:70); its score is (goals reached,
+    sum of joint-limit-weighted kinematic isotropy).  PyBullet's IK is replaced by our damped-least-squares solver
+    and the 5-step self-contact test of `ik_jlwki(step_sim=True)` (util.py:62-67) is not applied.
+    -> (random_pos xy, yaw, start joint angles)"""
+    lower = np.array([robot.links[j].lower for j in joints]); upper = np.array([robot.links[j].upper for j in joints])
+    ik_lo = np.where(lower > upper, -2 * np.pi, lower); ik_hi = np.where(lower > upper, 2 * np.pi, upper)     # util.py:86-88
+    best = None
+    it = 0
+    while it < attempts or best is None:
+        it += 1
+        rp = np.array([rng.uniform(-random_position, 0.0), rng.uniform(-random_position, random_position), 0.0])
+        yaw = np.deg2rad(rng.uniform(-random_rotation, random_rotation))
+        robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.asarray(pos_offset, float) + rp
+        robot.base_quat = X.quat_from_euler([0, 0, yaw])
+        reached, manip, q_start = 0, 0.0, None
+        for j, (tp, tq) in enumerate([(start_pos, start_quat)] + [(g, None) for g in goal_points]):
+            rest = rng.uniform(ik_lo, ik_hi)
+            q, ep, eq = ik_dls(robot, ee_link, joints, ik_lo, ik_hi, np.asarray(tp, float), tq, rest, iters=max_ik_iterations)
+            ok = ep < 0.03 and (tq is None or eq < 0.03)
+            if ok:
+                _, _, J = ee_pose_and_jacobian(robot, dict(zip(joints, q)), ee_link, joints)
+                W = joint_limited_weighting(q, lower, upper)
+                JWJ = J @ W @ J.T
+                det = max(np.linalg.det(JWJ), 0.0)
+                manip += np.power(det, 1.0 / 6.0) / (np.trace(JWJ) / 6.0)
+                reached += 1
+                if j == 0:
+                    q_start = q
+            elif j == 0:
+                reached = -1
+                break
+        if reached > 0 and (best is None or reached > best[0] or (reached == best[0] and manip > best[1])):
+            best = (reached, manip, rp[:2].copy(), yaw, q_start)
+    return best[2], best[3], best[4], best[0]
+
+
+def build_reset_data_bed_bathing(scene: CompiledScene, q_start: np.ndarray) -> dict:
+    """Reset table input of one BedBathing play variant (= one robot base pose): arm at the IK start pose
+    (env.py:571-572), fingers at 1.1 (bed_bathing.py:327), wiper in the gripper (world_creation.py:331-337), every
+    wiping target alive (bed_bathing.py:369-379)."""
+    robot = scene.multibodies[0]
+    joints = scene.robot_arm_joints
+    at = scene.attach[2][-1]
+    ip, iq = X.tf_inv(at.pos, at.quat)
+    qrob = {j: float(q_start[k]) for k, j in enumerate(joints)}
+    for j in (9, 11, 13):
+        qrob[j] = float(scene.finger_open)
+    ee_p, ee_q = robot.com_frames(qrob)[8]
+    base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
+    bp, bq = X.tf_mul(base_p, base_q, ip, iq)
+    arm_qidx, arm_dof, fin_qidx, fin_dof = [], [], [], []
+    tool_qidx = -1
+    for b in scene.bodies:
+        if b.art == 0 and b.jtype != 2:
+            if b.ref_joint in joints:
+                arm_qidx.append(b.qidx); arm_dof.append(b.dof)
+            else:
+                fin_qidx.append(b.qidx); fin_dof.append(b.dof)
+        elif b.art == 2:
+            tool_qidx = b.qidx
+    zi = np.zeros(0, dtype=np.int64); zf = np.zeros(0)
+    return dict(pool_q=np.asarray([q_start]), pool_tool=np.asarray([np.concatenate([bp, bq])]), arm_qidx=np.asarray(arm_qidx),
+                arm_dof=np.asarray(arm_dof), fin_qidx=np.asarray(fin_qidx), fin_dof=np.asarray(fin_dof),
+                hum_qidx=zi, hum_dof=zi, hum_joint=zi, hum_lower=zf, hum_upper=zf, hum_reset=zf,
+                tool_qidx=np.asarray(tool_qidx), limb_dims=np.zeros((2, 2)), human_control=np.asarray(0),
+                task=np.asarray(1), n_target=np.asarray(scene.info["n_target"]), fin_open=np.asarray(float(scene.finger_open)))
+
+
+def bed_bathing_settle_record(scene: CompiledScene) -> np.ndarray:
+    """Env record at the start of the reference's settle loop (bed_bathing.py:284-290): human right arm at the preset.
+    The robot stands 2.8 m away (world_creation.py:288) and cannot influence the arm; it is parked upright (joints 2, 4, 6 at pi, inside
+    their limits) with the wiper in its gripper instead of the reference's all-zero pose (env.py:450-453), which violates
+    the Jaco's joint limits and has its links interpenetrating by centimetres."""
+    env = np.zeros(ENV_STRIDE, dtype=np.float32)
+    robot = scene.multibodies[0]
+    qrob = {}
+    for b in scene.bodies:
+        if b.jtype == 2:
+            continue
+        if b.art == 0:
+            park = dict(zip(scene.robot_arm_joints, [0.0, np.pi, 0.0, np.pi, 0.0, np.pi, 0.0]))
+            v = float(scene.finger_open) if b.ref_joint in (9, 11, 13) else park.get(b.ref_joint, 0.0)
+            qrob[b.ref_joint] = v
+        else:
+            v = float(scene.q_human_reset.get(b.ref_joint, 0.0))
+        env[E_Q + b.qidx] = v; env[E_MTARGET + b.dof] = v
+    at = scene.attach[2][-1]
+    ip, iq = X.tf_inv(at.pos, at.quat)
+    ee_p, ee_q = robot.com_frames(qrob)[8]
+    base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
+    bp, bq = X.tf_mul(base_p, base_q, ip, iq)
+    for b in scene.bodies:
+        if b.art == 2:
+            env[E_Q + b.qidx:E_Q + b.qidx + 7] = np.concatenate([bp, bq])
+    env[E_STRENGTH] = 1.0; env[E_LIMIT_SCALE] = 1.0; env[E_HUMAN_KP] = 0.0
+    env.view(np.int32)[E_LIMB_FRAME] = F_SHOULDER
+    return env

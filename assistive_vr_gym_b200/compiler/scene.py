@@ -145,6 +145,98 @@ def _world_aabb(s: ShapeDesc, pos, quat):
     return R @ c + pos, np.abs(R) @ h
 
 
+def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], frozen_sets: Dict[int, set], setup_dof,
+              cross_pair_ok, robot: MultiBodyDesc, human: MultiBodyDesc):
+    """Common part of every scene recipe: multibodies -> dynamic bodies (depth-first, joint bodies first), velocity dofs,
+    compiled shapes (moving first) and the filtered collision-pair table.
+
+    q_presets / frozen_sets: per multibody index, joint presets and the joints the reference freezes; setup_dof(body, dof)
+    fills motors / action slots of a joint dof; cross_pair_ok(shape_a, shape_b) is the `setCollisionFilterPair` rule
+    between different multibodies.  Pairs inside one multibody follow Bullet: never a link with its parent, robot with
+    URDF_USE_SELF_COLLISION (world_creation.py:282), human by its filter matrix (human_creation.py:279-294), nothing else.
+    """
+    bodies: List[DynBody] = []
+    attach: List[Dict[int, Attached]] = []
+    for k, mb in enumerate(mbs):
+        b, a = reduce_bodies(mb, k, q_presets.get(k, {}), frozen_sets.get(k, set()), len(bodies))
+        bodies.extend(b); attach.append(a)
+    n_body = len(bodies)
+    assert n_body <= 32
+
+    # -- dofs -----------------------------------------------------------------------------------------------
+    dofs: List[dict] = []
+    qidx = 0
+    for bi, b in enumerate(bodies):
+        if b.jtype == JOINT_FREE:
+            continue
+        b.dof = len(dofs); b.qidx = qidx; qidx += 1
+        d = dict(body=bi, flags=0, lower=b.lower, upper=b.upper, rep_lower=b.lower, rep_upper=b.upper,
+                 kp=0.0, kd=1.0, max_force=0.0, action=-1, human_slot=-1, init_target=0.0)
+        if b.limit_enforced:
+            d["flags"] |= 1
+        setup_dof(b, d)
+        dofs.append(d)
+    n_jdof = len(dofs)
+    n_free = 0
+    for bi, b in enumerate(bodies):
+        if b.jtype == JOINT_FREE:
+            b.dof = len(dofs); b.qidx = qidx; qidx += 7
+            for _ in range(6):
+                dofs.append(dict(body=bi, flags=0, lower=0.0, upper=-1.0, rep_lower=0.0, rep_upper=-1.0, kp=0.0, kd=0.0,
+                                 max_force=0.0, action=-1, human_slot=-1, init_target=0.0))
+            n_free += 1
+    n_dof = len(dofs)
+    assert n_dof <= 32 and qidx <= 32
+
+    # -- shapes ---------------------------------------------------------------------------------------------
+    shapes: List[CompiledShape] = []
+    for k, mb in enumerate(mbs):
+        for li in [-1] + list(range(len(mb.links))):
+            link = mb.link(li)
+            if not link.shapes:
+                continue
+            thr = link_contact_threshold(link)
+            at = attach[k][li]
+            for s in link.shapes:
+                p, q = X.tf_mul(at.pos, at.quat, s.pos, s.quat)
+                shapes.append(CompiledShape(desc=s, body=at.body, pos=p, quat=q, ref_body=mb.ref_body, ref_link=li,
+                                            thr=thr, margin=_shape_margin(s), mb_index=k))
+    shapes.sort(key=lambda s: 0 if s.body >= 0 else 1)       # moving shapes first (stable)
+    n_mshape = sum(1 for s in shapes if s.body >= 0)
+
+    # -- collision pairs ------------------------------------------------------------------------------------
+    def link_parent(mb: MultiBodyDesc, li: int) -> int:
+        return mb.links[li].parent if li >= 0 else -2
+
+    pairs = []
+    for ia in range(n_mshape):
+        a = shapes[ia]
+        for ib in range(len(shapes)):
+            b = shapes[ib]
+            if ib == ia or (b.body >= 0 and ib < ia):
+                continue                                      # unordered pairs once; moving A first
+            if a.body == b.body:
+                continue
+            if a.mb_index == b.mb_index:
+                mb = mbs[a.mb_index]
+                if a.ref_link == b.ref_link:
+                    continue
+                if link_parent(mb, a.ref_link) == b.ref_link or link_parent(mb, b.ref_link) == a.ref_link:
+                    continue                                  # Bullet never collides a link with its parent
+                if mb is robot:
+                    pass                                      # URDF_USE_SELF_COLLISION, world_creation.py:282
+                elif mb is human:
+                    if not human_self_collision_enabled(a.ref_link, b.ref_link):
+                        continue
+                else:
+                    continue                                  # tool / furniture: no self collision flag
+            elif not cross_pair_ok(a, b):
+                continue
+            pairs.append((ia, ib))
+    pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+    return bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs
+
+
 def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,
                        verbose: bool = False) -> CompiledScene:
     if robot_type != "jaco":
@@ -182,26 +274,7 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
     robot_arm = [1, 2, 3, 4, 5, 6, 7]                                     # world_creation.py:283
     fingers = [9, 11, 13]                                                 # world_creation.py:320
 
-    bodies: List[DynBody] = []
-    attach: List[Dict[int, Attached]] = []
-    for k, mb in enumerate(mbs):
-        frozen = frozen_h if mb is human else set()
-        b, a = reduce_bodies(mb, k, q_human if mb is human else {}, frozen, len(bodies))
-        bodies.extend(b); attach.append(a)
-    n_body = len(bodies)
-    assert n_body <= 32
-
-    # -- dofs -----------------------------------------------------------------------------------------------
-    dofs: List[dict] = []
-    qidx = 0
-    for bi, b in enumerate(bodies):
-        if b.jtype == JOINT_FREE:
-            continue
-        b.dof = len(dofs); b.qidx = qidx; qidx += 1
-        d = dict(body=bi, flags=0, lower=b.lower, upper=b.upper, rep_lower=b.lower, rep_upper=b.upper,
-                 kp=0.0, kd=1.0, max_force=0.0, action=-1, human_slot=-1, init_target=0.0)
-        if b.limit_enforced:
-            d["flags"] |= 1
+    def setup_dof(b: DynBody, d: dict) -> None:
         if b.art == 0:
             if b.ref_joint in robot_arm:
                 d.update(kp=cfg["robot_gains"], max_force=cfg["robot_forces"], action=robot_arm.index(b.ref_joint))
@@ -215,68 +288,16 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
             d["flags"] |= 2 | 4 | 8
             if human_control:
                 d["action"] = 7 + slot
-        dofs.append(d)
-    n_jdof = len(dofs)
-    n_free = 0
-    for bi, b in enumerate(bodies):
-        if b.jtype == JOINT_FREE:
-            b.dof = len(dofs); b.qidx = qidx; qidx += 7
-            for _ in range(6):
-                dofs.append(dict(body=bi, flags=0, lower=0.0, upper=-1.0, rep_lower=0.0, rep_upper=-1.0, kp=0.0, kd=0.0,
-                                 max_force=0.0, action=-1, human_slot=-1, init_target=0.0))
-            n_free += 1
-    n_dof = len(dofs)
-    assert n_dof <= 32 and qidx <= 32
-
-    # -- shapes ---------------------------------------------------------------------------------------------
-    shapes: List[CompiledShape] = []
-    for k, mb in enumerate(mbs):
-        for li in [-1] + list(range(len(mb.links))):
-            link = mb.link(li)
-            if not link.shapes:
-                continue
-            thr = link_contact_threshold(link)
-            at = attach[k][li]
-            for s in link.shapes:
-                p, q = X.tf_mul(at.pos, at.quat, s.pos, s.quat)
-                shapes.append(CompiledShape(desc=s, body=at.body, pos=p, quat=q, ref_body=mb.ref_body, ref_link=li,
-                                            thr=thr, margin=_shape_margin(s), mb_index=k))
-    shapes.sort(key=lambda s: 0 if s.body >= 0 else 1)       # moving shapes first (stable)
-    n_mshape = sum(1 for s in shapes if s.body >= 0)
-
-    # -- collision pairs ------------------------------------------------------------------------------------
-    def link_parent(mb: MultiBodyDesc, li: int) -> int:
-        return mb.links[li].parent if li >= 0 else -2
 
     tool_filtered_robot_links = set(range(7, 15))             # world_creation.py:352-354 (jaco)
-    pairs = []
-    for ia in range(n_mshape):
-        a = shapes[ia]
-        for ib in range(len(shapes)):
-            b = shapes[ib]
-            if ib == ia or (b.body >= 0 and ib < ia):
-                continue                                      # unordered pairs once; moving A first
-            if a.body == b.body:
-                continue
-            if a.mb_index == b.mb_index:
-                mb = mbs[a.mb_index]
-                if a.ref_link == b.ref_link:
-                    continue
-                if link_parent(mb, a.ref_link) == b.ref_link or link_parent(mb, b.ref_link) == a.ref_link:
-                    continue                                  # Bullet never collides a link with its parent
-                if mb is robot:
-                    pass                                      # URDF_USE_SELF_COLLISION, world_creation.py:282
-                elif mb is human:
-                    if not human_self_collision_enabled(a.ref_link, b.ref_link):
-                        continue
-                else:
-                    continue                                  # tool / furniture: no self collision flag
-            else:
-                ms = {a.mb_index: a, b.mb_index: b}
-                if 0 in ms and 2 in ms and ms[0].ref_link in tool_filtered_robot_links:
-                    continue
-            pairs.append((ia, ib))
-    pairs = np.asarray(pairs, dtype=np.int32)
+
+    def cross_pair_ok(a: CompiledShape, b: CompiledShape) -> bool:
+        ms = {a.mb_index: a, b.mb_index: b}
+        return not (0 in ms and 2 in ms and ms[0].ref_link in tool_filtered_robot_links)
+
+    bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs = _assemble(
+        mbs, {1: q_human}, {1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
+    n_body = len(bodies); n_dof = len(dofs)
 
     # -- frames of interest ----------------------------------------------------------------------------------
     def com_frame(k: int, li: int):
@@ -322,6 +343,237 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
         from .h5lite import load_keras_dense_stack
         scene.mlp_layers = load_keras_dense_stack(os.path.join(assets_dir, 'realistic_arm_limits_model.h5'))
     scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape)
+    if verbose:
+        print(scene.info)
+    return scene
+
+
+# =====================================================================================================================
+# BedBathing (reference bed_bathing.py:155-358)
+# =====================================================================================================================
+CONFIG["bed_bathing"] = dict(robot_forces=1.0, robot_gains=0.05, distance_weight=1.0, action_weight=0.01,
+                             wiping_reward_weight=5.0, task_success_threshold=0.3)          # config.ini:12-18
+
+# Pose of the human's right arm (joints 7..13) after the reference's 100-step settle onto the mattress
+# (bed_bathing.py:286-292).  Produced by OUR device kernels from the 'settle' stage of this recipe with
+# tools/settle_bed_bathing.py on a B200 and committed as data; None until that has been run.
+SETTLED_ARM_Q: Dict[str, Optional[List[float]]] = {"male": None, "female": None}
+_SETTLE_FILE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "bed_bathing_settle.json")
+
+
+def load_settled_arm_q() -> Dict[str, Optional[List[float]]]:
+    """data/bed_bathing_settle.json (written by tools/settle_bed_bathing.py from a run of the CUDA kernels)."""
+    import json
+    if os.path.exists(_SETTLE_FILE):
+        with open(_SETTLE_FILE) as f:
+            d = json.load(f)
+        for g in ("male", "female"):
+            SETTLED_ARM_Q[g] = [float(x) for x in d[g]["arm_q"]]
+    return SETTLED_ARM_Q
+
+
+def _static_body(name: str, shapes: List[ShapeDesc], pos, quat, ref_body: int = REF_FURNITURE) -> MultiBodyDesc:
+    """`p.createMultiBody(baseMass=0, baseCollisionShapeIndex=...)`: a massless base with collision shapes."""
+    base = LinkDesc(-1, -1, "base", np.zeros(3), I4.copy(), np.zeros(3), 0.0, np.zeros(3), I4.copy(), shapes=shapes, name=name)
+    mb = MultiBodyDesc(name=name, ref_body=ref_body, base=base, links=[])
+    mb.base_pos = np.asarray(pos, float); mb.base_quat = np.asarray(quat, float); mb.fixed_base = True
+    return mb
+
+
+def _mesh_shapes(path: str, scale, friction: float, single_hull: bool = False) -> List[ShapeDesc]:
+    """`p.createCollisionShape(GEOM_MESH, fileName, meshScale)`: one convex hull per `o` group of the file."""
+    key = (path, tuple(float(x) for x in scale), single_hull)
+    if key not in _hull_cache:
+        groups = load_mesh_hulls(path)
+        if single_hull:
+            groups = [np.concatenate(groups, axis=0)]
+        pieces = []
+        for grp in groups:
+            v, pl, err = prepare_hull(grp * np.asarray(scale, float))
+            hull_errors[os.path.basename(path)] = max(hull_errors.get(os.path.basename(path), 0.0), err)
+            pieces.append((v, pl))
+        _hull_cache[key] = pieces
+    return [ShapeDesc(SHAPE_HULL, np.zeros(3), I4.copy(), verts=v, planes=pl, friction=friction, ref_link=-1)
+            for v, pl in _hull_cache[key]]
+
+
+def capsule_points(p1, p2, radius: float, distance_between_points: float = 0.05, position_scale: float = 1.0) -> np.ndarray:
+    """Reference `Util.capsule_points` (util.py:134-167): rings of points around a capsule's cylinder."""
+    p1, p2 = np.asarray(p1, float), np.asarray(p2, float)
+    axis = (p2 - p1) / np.linalg.norm(p2 - p1)
+    m = int(np.argmax(np.abs(axis)))                         # util.py:169-177 orthogonal_vector
+    y = np.zeros(3); y[(m + 1) % 3] = 1.0
+    ortho = np.cross(axis, y); ortho /= np.linalg.norm(ortho)
+    normal = np.cross(axis, ortho)
+    sections = int(np.linalg.norm(p2 - p1) / distance_between_points)
+    pts = []
+    for i in range(sections):
+        section_pos = (p2 - p1) / (sections + 1) * (i + 1)
+        theta_dist = distance_between_points / radius
+        for j in range(int(2 * np.pi * radius / distance_between_points)):
+            th = theta_dist * j
+            pts.append(p1 + section_pos * position_scale + radius * np.cos(th) * ortho + radius * np.sin(th) * normal)
+    return np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+
+
+def bed_bathing_targets(gender: str, hipbone_to_mouth_height: float):
+    """`BedBathingEnv.generate_targets` (bed_bathing.py:360-370): (points on the upper arm, points on the forearm), each in
+    the COM frame of human link 9 / 11."""
+    if gender == "male":
+        hmhs = hipbone_to_mouth_height / 0.6
+        ul, ur, fl, fr = 0.279, 0.043, 0.257, 0.033
+    else:
+        hmhs = hipbone_to_mouth_height / 0.54
+        ul, ur, fl, fr = 0.264, 0.0355, 0.234, 0.027
+    up = capsule_points([0, 0, 0], [0, 0, -ul], ur, 0.03, hmhs)
+    fo = capsule_points([0, 0, 0], [0, 0, -fl], fr, 0.03, hmhs)
+    return up, fo
+
+
+def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,
+                      stage: str = "play", arm_q: Optional[List[float]] = None,
+                      base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False) -> CompiledScene:
+    """BedBathing<Robot>-v0 (bed_bathing.py:155-358).
+
+    stage 'settle': the world as it is during `for _ in range(100): p.stepSimulation()` (bed_bathing.py:286-292) -- human
+    base fixed over the bed, right arm (joints 7..13) dynamic under gravity (0, 0, -1), every human joint with a
+    velocity motor of 0.1 N m (world_creation.py:164-167), bed parts with friction 5; the robot parked where
+    `init_jaco` puts it (world_creation.py:288).
+    stage 'play': the world the episode steps in -- the whole human static at the settled pose `arm_q`
+    (human_controllable_joint_indices == [] makes every joint static, bed_bathing.py:294-295 + world_creation.py:157-161),
+    robot base at the pose chosen by `position_robot_toc` (random_pos x, y and yaw = `base_xy_yaw`, env.py:511-513,
+    bed_bathing.py:325), nightstand under it (bed_bathing.py:330-338), gravity off for robot / human / tool (:341-344).
+    """
+    if robot_type != "jaco":
+        raise NotImplementedError("round 1 compiles the Jaco recipe only")
+    if human_control:
+        raise NotImplementedError("BedBathingJacoHuman-v0 (dynamic arm during play) is next")
+    cfg = CONFIG["bed_bathing"]
+    deg = np.deg2rad
+    play = stage == "play"
+    robot = urdf_to_multibody(os.path.join(assets_dir, "jaco", "j2s7s300_gym.urdf"), REF_ROBOT, "jaco")
+    robot.fixed_base = True
+    if play:
+        rx, ry, yaw = base_xy_yaw
+        robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.array([0.1, 0.55, 0.6]) + np.array([rx, ry, 0.0])   # env.py:513, bed_bathing.py:325
+        robot.base_quat = X.quat_from_euler([0, 0, yaw])
+    else:
+        robot.base_pos = np.array([-2.0, -2.0, 0.975]); robot.base_quat = I4.copy()                      # world_creation.py:288
+    h2m = 0.6 if gender == "male" else 0.54                                                               # bed_bathing.py:196
+    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
+    human.base_pos = np.array([0.0, 0.0, 0.7]); human.base_quat = X.quat_from_euler([deg(-30), 0, 0])     # bed_bathing.py:203
+    human.gravity = np.array([0.0, 0.0, 0.0 if play else -1.0])                                           # :289 / :343
+    tool = urdf_to_multibody(os.path.join(assets_dir, "bed_bathing", "wiper.urdf"), REF_TOOL, "wiper")
+    tool.fixed_base = False
+    bed_friction = 5.0                                                                                    # bed_bathing.py:282-283
+    y_offset = -0.53
+    m0 = _static_body("mattress0", [ShapeDesc(SHAPE_BOX, np.array([0, 0, 0.15 / 2.0]), I4.copy(), half=np.array([0.88, 1.25, 0.15]) / 2.0,
+                                              friction=bed_friction)], [0, y_offset, 0.4], I4)            # :214-216
+    m1 = _static_body("mattress1", [ShapeDesc(SHAPE_BOX, np.array([0, 0.7 / 2.0, 0]), I4.copy(), half=np.array([0.88, 0.7, 0.15]) / 2.0,
+                                              friction=bed_friction)], [0, 1.25 / 2.0 + y_offset, 0.4 + 0.15 / 2.0],
+                      X.quat_from_euler([deg(60), 0, 0]))                                                 # :218-220
+    frame = _static_body("bed_frame", _mesh_shapes(os.path.join(assets_dir, "bed", "hospital_bed_frame_vhacd.obj"), [1, 1.2, 1], bed_friction),
+                         [0, y_offset + 0.45, 0.42], X.quat_from_euler([np.pi / 2.0, 0, -np.pi / 2.0]))   # :223-227
+    plane = _static_body("plane", [ShapeDesc(SHAPE_PLANE, np.zeros(3), I4.copy(), friction=1.0, ref_link=-1)], [0, 0, 0], I4, REF_PLANE)
+    mbs = [robot, human, tool, m0, m1, frame]
+    if play:
+        ns = 0.275                                                                                        # :331-338
+        nightstand = _static_body("nightstand", _mesh_shapes(os.path.join(assets_dir, "nightstand", "nightstand.obj"), [ns] * 3, 0.5,
+                                                             single_hull=True),
+                                  np.array([-0.85, 0.12, 0.0]) + np.array([base_xy_yaw[0], base_xy_yaw[1], 0.0]),
+                                  X.quat_from_euler([np.pi / 2.0, 0, 0]))
+        mbs.append(nightstand)
+    mbs.append(plane)
+
+    # -- joint presets and frozen joints ----------------------------------------------------------------------
+    q_human = {7: deg(50), 8: deg(-50), 17: deg(-30), 28: deg(-60), 35: deg(-60)}                         # bed_bathing.py:284
+    arm = list(range(7, 14))
+    if play:
+        if arm_q is None:
+            arm_q = load_settled_arm_q()[gender]
+        if arm_q is None:
+            raise RuntimeError("no settled arm pose: run tools/settle_bed_bathing.py on a GPU box first")
+        for j, v in zip(arm, arm_q):
+            q_human[j] = float(v)
+    for l in human.links:
+        if l.jtype == "revolute":
+            q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))       # world_creation.py:169
+    frozen_h = {l.ref_index for l in human.links if play or l.ref_index not in range(4, 14)}             # :285 non_static_joints / :294
+    robot_arm = [1, 2, 3, 4, 5, 6, 7]
+    fingers = [9, 11, 13]
+    finger_open = 1.1                                                                                     # bed_bathing.py:327
+
+    def setup_dof(b: DynBody, d: dict) -> None:
+        if b.art == 0:
+            if b.ref_joint in robot_arm:
+                d.update(kp=cfg["robot_gains"], max_force=cfg["robot_forces"], action=robot_arm.index(b.ref_joint))
+                d["flags"] |= 2
+            elif b.ref_joint in fingers:
+                d.update(kp=0.05, max_force=500.0, init_target=finger_open)                               # world_creation.py:328
+                d["flags"] |= 2
+        elif b.art == 1:
+            d.update(kp=0.0, kd=1.0, max_force=0.1)               # VELOCITY_CONTROL, target 0, force 0.1 (world_creation.py:164-167)
+            d["flags"] |= 2
+
+    tool_filtered_robot_links = set(range(7, 15))                                                         # world_creation.py:352-354
+    bed_filtered_human_links = set(range(28, 42)) | {0, 1, 2, 3}                                          # bed_bathing.py:231-234
+    bed_mbs = {3, 4, 5}
+
+    def cross_pair_ok(a: CompiledShape, b: CompiledShape) -> bool:
+        ms = {a.mb_index: a, b.mb_index: b}
+        if 0 in ms and 2 in ms and ms[0].ref_link in tool_filtered_robot_links:
+            return False
+        if 1 in ms and (set(ms) & bed_mbs) and ms[1].ref_link in bed_filtered_human_links:
+            return False
+        return True
+
+    bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs = _assemble(
+        mbs, {1: q_human}, {1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
+    n_body = len(bodies); n_dof = len(dofs)
+
+    def com_frame(k: int, li: int):
+        at = attach[k][li]
+        link = mbs[k].link(li)
+        p, q = X.tf_mul(at.pos, at.quat, link.inertial_pos, link.inertial_quat)
+        return (at.body, p, q)
+
+    tool_pos_offset = np.array([-0.01, 0.0, 0.03])                                                        # bed_bathing.py:328
+    tool_orient_offset = X.quat_from_euler([0, -np.pi / 2.0, 0])
+    ee = com_frame(0, 8)
+    weld_parent = (ee[0],) + X.tf_mul(ee[1], ee[2], tool_pos_offset, tool_orient_offset)
+    frames = [
+        com_frame(2, 1),            # AVG_F_TOOL_TIP: wiper link 1 (cloth) COM, bed_bathing.py:54,131
+        com_frame(2, -1),           # AVG_F_TOOL_BASE
+        weld_parent,                # AVG_F_WELD_PARENT
+        com_frame(0, 0),            # AVG_F_TORSO: robot link 0 COM, bed_bathing.py:130
+        com_frame(1, 3),            # AVG_F_CHEST: human link 3, bed_bathing.py:137
+        com_frame(1, 9), com_frame(1, 11), com_frame(1, 13),       # :143-145
+    ]
+    up, fo = bed_bathing_targets(gender, h2m)
+    hp = CONFIG["human_preferences"]
+    task_f = np.zeros(32, dtype=np.float32)
+    n_target = len(up) + len(fo)
+    task_f[:15] = [cfg["distance_weight"], cfg["action_weight"], 0.0, cfg["wiping_reward_weight"],
+                   n_target * cfg["task_success_threshold"], hp["velocity_weight"], hp["force_nontarget_weight"],
+                   hp["high_forces_weight"], hp["food_hit_weight"], hp["food_velocities_weight"],
+                   0.025, 0.0, 10.0, 0.05, 1.0]
+    task_f[15] = 4.0                        # getClosestPoints query distance, bed_bathing.py:61
+    task_f[16:19] = [-0.4, 0.0, 0.9]        # reference point of the device spatial algebra (float32 conditioning)
+    header = dict(task=1, n_body=n_body, n_ebody=0, n_dof=n_dof, n_jdof=n_jdof, n_free=n_free,
+                  substeps=5, solver_iters=50,                             # env.py:16, bed_bathing.py:340
+                  n_action_robot=7, n_action_human=0, n_obs_robot=24, n_obs_human=0, human_control=0,
+                  dt=0.02, erp=0.2, lin_damp=0.04, ang_damp=0.04, residual_thr=1e-7, max_vel=100.0,
+                  action_scale=0.05, weld_max_force=500.0,
+                  weld_body_a=weld_parent[0], weld_body_b=frames[1][0], task_f=task_f)
+    scene = CompiledScene(task="bed_bathing", robot_type=robot_type, gender=gender, human_control=human_control,
+                          multibodies=mbs, bodies=bodies, attach=attach, shapes=shapes, n_mshape=n_mshape, pairs=pairs,
+                          frames=frames, dofs=dofs, header=header, robot_arm_joints=robot_arm,
+                          human_joints=[] if play else arm, q_human_reset=q_human,
+                          tool_offset=(tool_pos_offset, tool_orient_offset))
+    scene.mlp_layers = None
+    scene.targets = (up, fo)
+    scene.finger_open = finger_open
+    scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape, n_target=n_target)
     if verbose:
         print(scene.info)
     return scene

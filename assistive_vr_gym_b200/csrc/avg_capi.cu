@@ -138,7 +138,9 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     if (mh->n_body > AVG_MAX_BODY || mh->n_dof > AVG_MAX_DOF || mh->n_jdof > AVG_K_MAXJ || mh->n_mshape > AVG_K_MAXMS ||
         mh->n_free > 2 || mh->n_shape - mh->n_mshape > 256 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32)
         return fail(h, -4, "avg_upload_model: model exceeds the warp-per-environment kernel limits");
-    if (mh->task != AVG_TASK_SCRATCH_ITCH) return fail(h, -4, "avg_upload_model: only the ScratchItch epilogue is built (round 1)");
+    if (mh->task != AVG_TASK_SCRATCH_ITCH && mh->task != AVG_TASK_BED_BATHING)
+        return fail(h, -4, "avg_upload_model: only the ScratchItch and BedBathing epilogues are built (round 1)");
+    if (mh->n_target < 0 || mh->n_target > AVG_MAX_TARGET) return fail(h, -4, "avg_upload_model: too many wiping targets");
     const AvgBody* bodies = (const AvgBody*)((const char*)blob + mh->off_body);
     for (int b = 0; b < mh->n_body; ++b) {
         if (bodies[b].jtype != AVG_JOINT_FREE && (bodies[b].dof != b || b >= mh->n_jdof))
@@ -247,7 +249,7 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
     int nv = 0;
     while (nv < AVG_K_MAX_VARIANTS && h->d_rtab[nv]) { r.tables[nv] = h->d_rtab[nv]; nv++; }
     if (nv == 0) return fail(h, -1, "avg_reset: no reset table uploaded (avg_upload_reset_table)");
-    r.n_variants = nv; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
+    r.n_variants = nv; r.n_per_gender = nv >= 2 ? nv / 2 : 1; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
     r.mask = mask; r.n_env = h->n_env; r.seed = seed;
     AVG_CHECK(h, avg_launch_reset(r, (cudaStream_t)stream));
     h->launches++;
@@ -264,7 +266,7 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
-    a.slot = h->slot;
+    a.slot = h->slot; a.task = h->task;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
     a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity;

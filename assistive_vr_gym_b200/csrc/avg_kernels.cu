@@ -68,6 +68,7 @@ struct KM {                                // device view of a ModelBlob
     const uint32_t* bpm;
     const float4* bcap;
     const float* mlp;
+    const float4* target;                  // BedBathing wiping targets (bed_bathing.py:360-379)
 };
 
 // Section pointers per (handle slot, variant), resolved on the host when a model is uploaded: a warp reads its model
@@ -88,6 +89,7 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     m.bpm = reinterpret_cast<const uint32_t*>(blob + m.h->off_bpm);
     m.bcap = reinterpret_cast<const float4*>(blob + m.h->off_bcap);
     m.mlp = m.h->n_mlp > 0 ? reinterpret_cast<const float*>(blob + m.h->off_mlp) : nullptr;
+    m.target = m.h->n_target > 0 ? reinterpret_cast<const float4*>(blob + m.h->off_target) : nullptr;
     return m;
 }
 
@@ -124,6 +126,14 @@ struct __align__(16) SmEpi {
     float env[AVG_ENV_STRIDE];
     float bp[32][3]; float bq[32][4];
     float obs[64];
+};
+struct __align__(16) SmEpiBB {             // BedBathing epilogue: + the tool / human shape lists of the closest-point query
+    float env[AVG_ENV_STRIDE];
+    float bp[32][3]; float bq[32][4];
+    float obs[64];
+    float4 tcap[8][2];                     // bounding capsules of the tool shapes, world frame
+    uint8_t tool_idx[8];
+    uint8_t hum_idx[120];
 };
 
 template <class SM>
@@ -1682,6 +1692,268 @@ avg_epilogue_kernel(AvgStepArgs a) {
     }
 }
 
+// =================================================================================================================
+// BedBathing epilogue (bed_bathing.py:53-153): get_total_force with the wiping targets, closest tool-human distance,
+// human_preferences, reward, observation, info
+// =================================================================================================================
+namespace {
+// bed_bathing.py:129-147 (robot half of the observation)
+template <class SM>
+__device__ void fill_obs_bb(const KM& m, SM& s, float tool_force) {
+    const AvgModelHeader* h = m.h;
+    const int nj = h->n_jdof;
+    V3 torso, tool, sh, el, wr; Q4 tq, dq;
+    frame_pose(m, s, AVG_F_TORSO, torso, dq);
+    frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+    frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
+    frame_pose(m, s, AVG_F_ELBOW, el, dq);
+    frame_pose(m, s, AVG_F_WRIST, wr, dq);
+    float* o = s.obs; int k = 0;
+    V3 t;
+    t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+    for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+    t = sh - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = tool_force;
+}
+
+// world pose of any shape from the body poses of an epilogue's forward kinematics
+template <class SM>
+__device__ __forceinline__ void epi_load_shape(const KM& m, const SM& s, int si, WShape& w) {
+    const AvgShape* S = &m.shape[si];
+    w.s = S; w.verts = m.vert + 4 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
+    Q4 q;
+    if (S->body >= 0) {
+        const Q4 bq = ldq(s.bq[S->body]);
+        w.p = ld3(s.bp[S->body]) + qrot(bq, ld3(S->pos));
+        q = qnormalize(qmul(bq, ldq(S->quat)));
+    } else { w.p = ld3(S->pos); q = ldq(S->quat); }
+    const M3 r = qmat(q);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w.R[i] = r.m[i];
+}
+// bounding capsule of a shape in the world frame (the blob stores it in the shape frame for moving shapes)
+template <class SM>
+__device__ __forceinline__ void epi_world_capsule(const KM& m, const SM& s, int si, float4& c0, float4& c1) {
+    c0 = __ldg(&m.bcap[2 * si]); c1 = __ldg(&m.bcap[2 * si + 1]);
+    const AvgShape* S = &m.shape[si];
+    if (S->body >= 0) {
+        const Q4 bq = ldq(s.bq[S->body]);
+        const V3 sp = ld3(s.bp[S->body]) + qrot(bq, ld3(S->pos));
+        const Q4 sq = qnormalize(qmul(bq, ldq(S->quat)));
+        const V3 p0 = sp + qrot(sq, mk3(c0.x, c0.y, c0.z)), p1 = sp + qrot(sq, mk3(c1.x, c1.y, c1.z));
+        c0 = make_float4(p0.x, p0.y, p0.z, c0.w); c1 = make_float4(p1.x, p1.y, p1.z, 0.0f);
+    }
+}
+// closest distance between segments [p1, p1 + d1] and [p2, p2 + d2] (Ericson 5.1.9)
+__device__ __forceinline__ float seg_seg_distance(V3 p1, V3 d1, V3 p2, V3 d2) {
+    const V3 r = p1 - p2;
+    const float aa = dot(d1, d1), ee = dot(d2, d2), ff = dot(d2, r);
+    float sc = 0.0f, tc = 0.0f;
+    if (aa <= 1e-12f && ee <= 1e-12f) { }
+    else if (aa <= 1e-12f) tc = fminf(fmaxf(ff / ee, 0.0f), 1.0f);
+    else {
+        const float cc = dot(d1, r);
+        if (ee <= 1e-12f) sc = fminf(fmaxf(-cc / aa, 0.0f), 1.0f);
+        else {
+            const float bb = dot(d1, d2), den = aa * ee - bb * bb;
+            sc = den > 1e-12f ? fminf(fmaxf((bb * ff - cc * ee) / den, 0.0f), 1.0f) : 0.0f;
+            tc = (bb * sc + ff) / ee;
+            if (tc < 0.0f) { tc = 0.0f; sc = fminf(fmaxf(-cc / aa, 0.0f), 1.0f); }
+            else if (tc > 1.0f) { tc = 1.0f; sc = fminf(fmaxf((bb - cc) / aa, 0.0f), 1.0f); }
+        }
+    }
+    return norm((p1 + d1 * sc) - (p2 + d2 * tc));
+}
+// lower bound on the distance of (tool shape ti, human shape hi) from their bounding capsules
+template <class SM>
+__device__ __forceinline__ float bb_pair_bound(const KM& m, const SM& s, int ti, int hi) {
+    const float4 a0 = s.tcap[ti][0], a1 = s.tcap[ti][1];
+    float4 b0, b1; epi_world_capsule(m, s, s.hum_idx[hi], b0, b1);
+    const V3 p1 = mk3(a0.x, a0.y, a0.z), p2 = mk3(b0.x, b0.y, b0.z);
+    return seg_seg_distance(p1, mk3(a1.x, a1.y, a1.z) - p1, p2, mk3(b1.x, b1.y, b1.z) - p2) - a0.w - b0.w - 1e-5f;
+}
+// exact narrowphase distance (narrowphase() of the oracle: GJK on the cores minus the margins, face-normal SAT when the
+// cores overlap) of one pair per lane; lanes with active == false only serve the hull scans.  3e38 when the pair is
+// farther apart than `bound`.
+template <class SM>
+__device__ float bb_pair_distance(const KM& m, const SM& s, int ti, int hi, bool active, float bound, int lane) {
+    WShape A, B;
+    epi_load_shape(m, s, s.tool_idx[ti], A); epi_load_shape(m, s, s.hum_idx[hi], B);
+    const float ma = A.s->margin, mb = B.s->margin;
+    float dist = 0.0f, gap = 0.0f; V3 ca = A.p, cb = B.p, vout = mk3(0, 0, 0); int gi = 0;
+    const int g = gjk_lockstep(A, B, active, lane, bound + ma + mb, dist, ca, cb, vout, gap, gi);
+    float best = 3.0e38f; V3 bn = mk3(0, 0, 1), bpa = A.p;
+    sat_served(A, B, g == 1, lane, best, bn, bpa);
+    if (g == 0) return dist - ma - mb;
+    if (g == 1) return -(best > 1.0e38f ? 0.0f : best) - ma - mb;
+    return 3.0e38f;
+}
+
+__device__ void dump_contacts(const AvgStepArgs& a, int e, const float* scr, int ncontact, float dt, int lane) {
+    AvgContact* co = a.contacts + (size_t)e * kMaxC;
+    for (int ci = lane; ci < kMaxC; ci += 32) {
+        AvgContact c;
+        if (ci < ncontact) {
+            const float* g = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci;
+            c.shape_a = __float_as_int(g[10]); c.shape_b = __float_as_int(g[11]);
+            for (int k = 0; k < 3; ++k) { c.pos_a[k] = g[k]; c.pos_b[k] = g[3 + k]; c.normal[k] = g[6 + k]; }
+            c.dist = g[9]; c.force = g[12] / dt;
+        } else { c.shape_a = -1; c.shape_b = -1; for (int k = 0; k < 3; ++k) { c.pos_a[k] = c.pos_b[k] = c.normal[k] = 0; } c.dist = 0; c.force = 0; }
+        c.pad[0] = c.pad[1] = c.pad[2] = 0;
+        co[ci] = c;
+    }
+    if (lane == 0) a.ncontacts[e] = ncontact;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_epilogue_bb_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmEpiBB)
+    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
+    __syncwarp();
+    int* env_i = reinterpret_cast<int*>(s.env);
+    const int* scr_i = reinterpret_cast<const int*>(scr);
+    const int na = h->n_action_robot + h->n_action_human;
+    const float* act = a.actions + (size_t)e * na;
+    float raw_sq;
+    {
+        const float av = lane < na ? act[lane] : 0.0f;
+        raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, bed_bathing.py:62
+    }
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    const float dt = h->dt;
+    const float* tf = h->task_f;
+    const int ncontact = scr_i[AVG_S_NCS];
+    // ---- get_total_force, bed_bathing.py:77-127.  Lane w holds word w of the alive-target bitmap; in round r of a
+    //      sweep over the targets lane l looks at target 32 r + l, i.e. bit l of word r.
+    uint32_t mask_w = lane < 5 ? (uint32_t)env_i[AVG_E_TARGET_MASK + lane] : 0u;
+    V3 up_p, fo_p; Q4 up_q, fo_q;
+    frame_pose(m, s, AVG_F_SHOULDER, up_p, up_q);            // human link 9 / 11 COM frames, bed_bathing.py:383,389
+    frame_pose(m, s, AVG_F_ELBOW, fo_p, fo_q);
+    const int n_target = h->n_target, n_upper = h->n_target_upper;
+    const float radius = tf[AVG_TF_TARGET_RADIUS];
+    float tool_force = 0, tool_force_on_human = 0, total_force_on_human = 0;
+    int new_points = 0;
+    for (int ci = 0; ci < ncontact; ++ci) {
+        const float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci;
+        const AvgShape* sa = &m.shape[__float_as_int(c[10])]; const AvgShape* sb = &m.shape[__float_as_int(c[11])];
+        const float force = c[12] / dt;
+        const bool a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        const bool a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        const bool a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if (a_tool || b_tool) tool_force += force;                                           // :83-85
+        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;             // :90-91
+        if ((a_tool && b_hum) || (b_tool && a_hum)) {                                        // :92-125
+            total_force_on_human += force;
+            const int link_tool = a_tool ? sa->ref_link : sb->ref_link;
+            const int link_hum = a_tool ? sb->ref_link : sa->ref_link;
+            if (link_tool != 1) continue;
+            tool_force_on_human += force;
+            if (link_hum < 0) continue;                                                      // :100-101
+            const V3 pos_h = a_tool ? ld3(c + 3) : ld3(c);                                   // positionOnB, B = human
+            for (int r = 0; r * 32 < n_target; ++r) {
+                const int t = r * 32 + lane;
+                const uint32_t word = __shfl_sync(AVG_FULL, mask_w, r);
+                bool wiped = false;
+                if (t < n_target && ((word >> lane) & 1u)) {
+                    const float4 tp = __ldg(&m.target[t]);
+                    const V3 tw = t < n_upper ? up_p + qrot(up_q, mk3(tp.x, tp.y, tp.z)) : fo_p + qrot(fo_q, mk3(tp.x, tp.y, tp.z));
+                    wiped = norm(pos_h - tw) < radius;
+                }
+                const unsigned bal = __ballot_sync(AVG_FULL, wiped);
+                if (lane == r) mask_w &= ~bal;
+                new_points += __popc(bal);
+            }
+        }
+    }
+    // ---- reward_distance: min closest-point distance over (tool link, human link) pairs, bed_bathing.py:61.  Every pair
+    //      has a lower bound from its bounding capsules; the pair with the smallest bound is measured first and only
+    //      pairs whose bound beats the best exact distance so far go through GJK (one pair per lane, lockstep).
+    int nt = 0, nh = 0;
+    for (int base = 0; base < h->n_shape; base += 32) {
+        const int si = base + lane;
+        const int rb = si < h->n_shape ? m.shape[si].ref_body : -1;
+        const unsigned bt = __ballot_sync(AVG_FULL, rb == AVG_REF_TOOL), bh = __ballot_sync(AVG_FULL, rb == AVG_REF_HUMAN);
+        if (rb == AVG_REF_TOOL) { const int k = nt + __popc(bt & ((1u << lane) - 1)); if (k < 8) s.tool_idx[k] = (uint8_t)si; }
+        if (rb == AVG_REF_HUMAN) { const int k = nh + __popc(bh & ((1u << lane) - 1)); if (k < 120) s.hum_idx[k] = (uint8_t)si; }
+        nt += __popc(bt); nh += __popc(bh);
+    }
+    nt = min(nt, 8); nh = min(nh, 120);
+    __syncwarp();
+    if (lane < nt) { float4 c0, c1; epi_world_capsule(m, s, s.tool_idx[lane], c0, c1); s.tcap[lane][0] = c0; s.tcap[lane][1] = c1; }
+    __syncwarp();
+    const int npair = nt * nh;
+    float closest = tf[AVG_TF_CLOSEST_RANGE];
+    if (npair > 0) {
+        float lb_min = 3.0e38f; int p_min = 0x7fffffff;
+        for (int p = lane; p < npair; p += 32) {
+            const float lb = bb_pair_bound(m, s, p / nh, p % nh);
+            if (lb < lb_min) { lb_min = lb; p_min = p; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ol = __shfl_xor_sync(AVG_FULL, lb_min, o); const int op = __shfl_xor_sync(AVG_FULL, p_min, o);
+            if (ol < lb_min || (ol == lb_min && op < p_min)) { lb_min = ol; p_min = op; }
+        }
+        const int p0 = p_min;
+        float best = bb_pair_distance(m, s, p0 / nh, p0 % nh, lane == 0, 3.0e37f, lane);
+        best = __shfl_sync(AVG_FULL, best, 0);
+        int p = lane;
+        while (true) {
+            while (p < npair && (p == p0 || bb_pair_bound(m, s, p / nh, p % nh) >= best)) p += 32;
+            const bool active = p < npair;
+            if (!__any_sync(AVG_FULL, active)) break;
+            const int pp = active ? p : 0;
+            const float d = bb_pair_distance(m, s, pp / nh, pp % nh, active, best, lane);
+            float mine = active ? fminf(best, d) : best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine = fminf(mine, __shfl_xor_sync(AVG_FULL, mine, o));
+            best = mine;
+            p += 32;
+        }
+        closest = fminf(closest, best);
+    }
+    if (lane < 5) reinterpret_cast<uint32_t*>(grec)[AVG_E_TARGET_MASK + lane] = mask_w;
+    if (lane == 0) {
+        fill_obs_bb(m, s, tool_force);
+        V3 tool; Q4 tq; frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+        const int tb = m.frame[AVG_F_TOOL_TIP].body;
+        const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
+        const float ee_vel = norm(ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb])));       // bed_bathing.py:54
+        const float pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_on_human))
+                         + tf[AVG_TF_C_HF] * (tool_force_on_human < tf[AVG_TF_FORCE_CAP] ? 0.0f : -tool_force_on_human);   // env.py:412-448
+        const float reward_distance = -closest;
+        const float reward_action = -raw_sq;
+        const float task_success = s.env[AVG_E_TASK_SUCCESS] + (float)new_points;
+        grec[AVG_E_TASK_SUCCESS] = task_success;
+        const float reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
+                           + tf[AVG_TF_SCRATCH_W] * (float)new_points + pref;                // bed_bathing.py:65
+        int* grec_i = reinterpret_cast<int*>(grec);
+        grec[AVG_E_EPISODE_RETURN] = s.env[AVG_E_EPISODE_RETURN] + reward;
+        grec_i[AVG_E_ITERATION] = env_i[AVG_E_ITERATION] + 1;                               // env.py:351
+        grec_i[AVG_E_OVERFLOW] = env_i[AVG_E_OVERFLOW] | scr_i[AVG_S_OVERFLOW];
+        grec_i[AVG_E_SOLVER_ITERS] = scr_i[AVG_S_ITERS];
+        grec_i[AVG_E_NCAND] = scr_i[AVG_S_NCAND];
+        a.reward[e] = reward;
+        const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;          // bed_bathing.py:72
+        a.info[2 * e] = total_force_on_human;
+        a.info[2 * e + 1] = success;
+        if (a.done) a.done[e] = 0;
+        if (a.terms) {
+            float* tr = a.terms + 8 * (size_t)e;
+            tr[0] = total_force_on_human; tr[1] = success; tr[2] = tool_force; tr[3] = tool_force_on_human;
+            tr[4] = reward_distance; tr[5] = reward_action; tr[6] = (float)new_points; tr[7] = pref;
+        }
+    }
+    __syncwarp();
+    const int nobs = h->n_obs_robot + h->n_obs_human;
+    for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
+    if (a.contacts) dump_contacts(a, e, scr, ncontact, dt, lane);
+}
+
 // initial observation after reset (scratch_itch.py:268): FK + target + _get_obs([0],[0,0])
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_reset_obs_kernel(AvgStepArgs a) {
@@ -1692,10 +1964,13 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     const int* env_i = reinterpret_cast<const int*>(s.env);
     fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
     if (lane == 0) {
-        V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
-        const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
-        fill_obs(m, s, tgt, 0.0f, 0.0f, 0.0f);
-        st3(grec + AVG_E_TARGET_POS, tgt);
+        if (h->task == AVG_TASK_BED_BATHING) fill_obs_bb(m, s, 0.0f);                        // bed_bathing.py:350
+        else {
+            V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
+            const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
+            fill_obs(m, s, tgt, 0.0f, 0.0f, 0.0f);
+            st3(grec + AVG_E_TARGET_POS, tgt);
+        }
     }
     __syncwarp();
     const int nobs = h->n_obs_robot + h->n_obs_human;
@@ -1728,17 +2003,21 @@ avg_reset_kernel(AvgResetArgs r) {
     const uint32_t ep = (uint32_t)(r.episode[e] + 1);
     r.episode[e] = (int32_t)ep;
     const uint32_t sd = r.seed, ue = (uint32_t)e;
-    const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)r.n_variants);                      // gender, scratch_itch.py:156
+    // gender (scratch_itch.py:156, bed_bathing.py:191); BedBathing: x one variant per robot base pose (env.py:511-513)
+    const uint32_t pick = reset_u32(sd, ue, ep, 17);
+    const int npg = r.n_per_gender;
+    const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)min(r.n_variants, 2)) * npg + (int)(pick % (uint32_t)npg);
     const AvgResetTable* T = r.tables[v];
-    const int impairment = (int)(reset_u32(sd, ue, ep, 1) & 3u);                                  // none, limits, weakness, tremor
+    const bool bb = T->task == AVG_TASK_BED_BATHING;                                              // human_impairment='none', bed_bathing.py:198
+    const int impairment = bb ? 0 : (int)(reset_u32(sd, ue, ep, 1) & 3u);                         // none, limits, weakness, tremor
     const float limit_scale = impairment == 1 ? 0.5f + 0.5f * reset_u01(sd, ue, ep, 2) : 1.0f;    // world_creation.py:70
     const float strength = impairment == 2 ? 0.25f + 0.75f * reset_u01(sd, ue, ep, 3) : 1.0f;     // world_creation.py:71
     float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
     int* rec_i = reinterpret_cast<int*>(rec);
     for (int i = 0; i < AVG_ENV_STRIDE; ++i) rec[i] = 0.0f;
-    const int k = (int)(reset_u32(sd, ue, ep, 17) % (uint32_t)T->n_pool);
+    const int k = (int)((pick / (uint32_t)npg) % (uint32_t)T->n_pool);
     for (int j = 0; j < T->n_arm; ++j) { rec[AVG_E_Q + T->arm_qidx[j]] = T->pool_q[k][j]; rec[AVG_E_MTARGET + T->arm_dof[j]] = T->pool_q[k][j]; }
-    for (int j = 0; j < T->n_fin; ++j) { rec[AVG_E_Q + T->fin_qidx[j]] = 1.0f; rec[AVG_E_MTARGET + T->fin_dof[j]] = 1.0f; }
+    for (int j = 0; j < T->n_fin; ++j) { rec[AVG_E_Q + T->fin_qidx[j]] = T->fin_open; rec[AVG_E_MTARGET + T->fin_dof[j]] = T->fin_open; }
     for (int j = 0; j < T->n_hum; ++j) {
         const float q = fminf(fmaxf(T->hum_reset[j], T->hum_lower[j] * limit_scale), T->hum_upper[j] * limit_scale);   // world_creation.py:172
         rec[AVG_E_Q + T->hum_qidx[j]] = q; rec[AVG_E_MTARGET + T->hum_dof[j]] = q;
@@ -1747,13 +2026,21 @@ avg_reset_kernel(AvgResetArgs r) {
     for (int j = 0; j < 7; ++j) rec[AVG_E_Q + T->tool_qidx + j] = T->pool_tool[k][j];
     const float deg10 = 0.17453292519943295f;
     for (int j = 0; j < 10; ++j) rec[AVG_E_TREMOR + j] = impairment == 3 ? (2.0f * reset_u01(sd, ue, ep, 4 + j) - 1.0f) * deg10 : 0.0f;   // world_creation.py:141
-    const int limb = (int)(reset_u32(sd, ue, ep, 14) & 1u);                                       // scratch_itch.py:278
-    const float length = T->limb_dims[limb][0], radius = T->limb_dims[limb][1];
-    const float rl = radius + reset_u01(sd, ue, ep, 15) * (length - radius);                      // util.py:118
-    const float th = 6.283185307179586f * reset_u01(sd, ue, ep, 16);
-    float sn, cs; sincosf(th, &sn, &cs);
-    rec[AVG_E_TARGET_ON_ARM + 0] = -radius * sn; rec[AVG_E_TARGET_ON_ARM + 1] = -radius * cs; rec[AVG_E_TARGET_ON_ARM + 2] = -rl;
-    rec_i[AVG_E_LIMB_FRAME] = limb == 0 ? AVG_F_SHOULDER : AVG_F_ELBOW;
+    if (bb) {                                                                                     // every wiping target alive, bed_bathing.py:369-379
+        for (int w = 0; w < 5; ++w) {
+            const int nbit = min(max(T->n_target - 32 * w, 0), 32);
+            reinterpret_cast<uint32_t*>(rec)[AVG_E_TARGET_MASK + w] = nbit == 32 ? 0xffffffffu : ((1u << nbit) - 1u);
+        }
+        rec_i[AVG_E_LIMB_FRAME] = AVG_F_SHOULDER;
+    } else {
+        const int limb = (int)(reset_u32(sd, ue, ep, 14) & 1u);                                   // scratch_itch.py:278
+        const float length = T->limb_dims[limb][0], radius = T->limb_dims[limb][1];
+        const float rl = radius + reset_u01(sd, ue, ep, 15) * (length - radius);                  // util.py:118
+        const float th = 6.283185307179586f * reset_u01(sd, ue, ep, 16);
+        float sn, cs; sincosf(th, &sn, &cs);
+        rec[AVG_E_TARGET_ON_ARM + 0] = -radius * sn; rec[AVG_E_TARGET_ON_ARM + 1] = -radius * cs; rec[AVG_E_TARGET_ON_ARM + 2] = -rl;
+        rec_i[AVG_E_LIMB_FRAME] = limb == 0 ? AVG_F_SHOULDER : AVG_F_ELBOW;
+    }
     rec[AVG_E_STRENGTH] = strength; rec[AVG_E_LIMIT_SCALE] = limit_scale;
     rec[AVG_E_TREMOR_ON] = impairment == 3 ? 1.0f : 0.0f;
     rec[AVG_E_HUMAN_KP] = (T->human_control || impairment == 3) ? 0.05f : 0.01f;                 // scratch_itch.py:45 / :231
@@ -1869,6 +2156,7 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         if ((e1 = set_smem(avg_solve_kernel<12>, sm_sol)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_solve_kernel<16>, sm_sol)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
+        if ((e1 = set_smem(avg_epilogue_bb_kernel, sizeof(SmEpiBB) * kWpbEpi)) != cudaSuccess) return e1;
         if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
         configured = true;
         const char* kt = getenv("AVG_KERNEL_TIMES");
@@ -1901,7 +2189,8 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
         else avg_solve_kernel<16><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
         mark();
     }
-    avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
+    if (a.task == AVG_TASK_BED_BATHING) avg_epilogue_bb_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sizeof(SmEpiBB) * kWpbEpi, stream>>>(a);
+    else avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     mark();
     if (kt_on) {
         cudaEventSynchronize(g_kt.ev[nev - 1]);
@@ -1934,6 +2223,7 @@ cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blo
     m.bpm = reinterpret_cast<const uint32_t*>(d_blob + hh->off_bpm);
     m.bcap = reinterpret_cast<const float4*>(d_blob + hh->off_bcap);
     m.mlp = hh->n_mlp > 0 ? reinterpret_cast<const float*>(d_blob + hh->off_mlp) : nullptr;
+    m.target = hh->n_target > 0 ? reinterpret_cast<const float4*>(d_blob + hh->off_target) : nullptr;
     return cudaMemcpyToSymbol(c_models, &m, sizeof(KM), sizeof(KM) * ((size_t)slot * AVG_K_MAX_VARIANTS + variant));
 }
 

@@ -7,7 +7,7 @@
 #define AVG_K_WARPS_PER_BLOCK 4
 #define AVG_K_MAXJ 24      /* 1-DoF joints per environment supported by the warp-per-environment kernels */
 #define AVG_K_MAXMS 24     /* moving collision shapes per environment */
-#define AVG_K_MAX_VARIANTS 4
+#define AVG_K_MAX_VARIANTS 16  /* model variants per handle: gender (x robot base pose for BedBathing) */
 
 /* Scratch arena: per-environment hand-off between the kernels of one sub-step (floats; ints bit-cast). */
 #define AVG_S_MAXDENSE (6 + 2 * AVG_MAX_CONTACT)
@@ -66,6 +66,7 @@ struct AvgStepArgs {
     int env_begin, env_end;                            // range stepped by this launch sequence (avg_step: all; avg_step_host: one chunk)
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
     int dbg;                                           // development switches (AVG_DBG), 0 in production
+    int task;                                          // AVG_TASK_* of the uploaded models: selects the epilogue / reset-observation kernel
     AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
     int* np_count;                                     // item counter: filled by the collide kernel, read by the narrowphase kernel, zeroed by the dynamics kernel
     int np_capacity;
@@ -84,6 +85,7 @@ cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blo
 struct AvgResetArgs {
     const AvgResetTable* tables[AVG_K_MAX_VARIANTS];
     int n_variants;
+    int n_per_gender;                                  // variants per gender (1 ScratchItch; BedBathing: one per robot base pose)
     float* env; float* scratch; int32_t* variant; int32_t* episode;
     const uint8_t* mask;
     int n_env;

@@ -24,7 +24,10 @@ MAX_EPISODE_STEPS = 200      # reference __init__.py:21
 REGISTRY: Dict[str, dict] = {
     "ScratchItchJaco-v0": dict(task="scratch_itch", robot="jaco", human_control=False, data="ScratchItchJaco.npz"),
     "ScratchItchJacoHuman-v0": dict(task="scratch_itch", robot="jaco", human_control=True, data="ScratchItchJacoHuman.npz"),
+    # reference __init__.py:103-108; observation 24 wide (bed_bathing.py:19,147)
+    "BedBathingJaco-v0": dict(task="bed_bathing", robot="jaco", human_control=False, data="BedBathingJaco.npz"),
 }
+_OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19
 _ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")
                       for r in ("PR2", "Jaco") for v in ("", "Human", "New")]
 
@@ -85,8 +88,8 @@ class BatchedAssistiveEnv:
             self.sim.upload_reset_table(v, reset_table_bytes(self.reset_data[v]))
         self.action_robot_len = 7
         self.action_human_len = 10 if self.spec["human_control"] else 0
-        self.obs_robot_len = 30
-        self.obs_human_len = 34 if self.spec["human_control"] else 0
+        self.obs_robot_len = _OBS_LEN[self.spec["task"]][0]
+        self.obs_human_len = _OBS_LEN[self.spec["task"]][1] if self.spec["human_control"] else 0
         assert self.sim.n_actions == self.action_robot_len + self.action_human_len
         assert self.sim.n_obs == self.obs_robot_len + self.obs_human_len
         self.action_space = Box(self.sim.n_actions)

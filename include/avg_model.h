@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 8u
+#define AVG_VERSION 9u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
@@ -138,8 +138,13 @@ typedef struct AvgModelHeader {
     uint32_t off_mlp;             /* arm-limit classifier (env.py:353-387): W1[4][64] b1[64] W2[64][64] b2 W3[64][64] b3 W4[64] b4   */
     int32_t  n_mlp;               /* 8705 floats when present (human-active ids), else 0                                        */
     int32_t  mlp_dof[4];          /* velocity dofs of human joints 7, 8, 9, 10 (tz, tx, ty, qe)                                  */
-    uint32_t pad2[2];
+    uint32_t off_target;          /* BedBathing wiping targets (bed_bathing.py:360-379): float4[n_target] = position in the COM frame of
+                                     human link 9 (entries [0, n_target_upper), frame AVG_F_SHOULDER) or link 11 (the rest, AVG_F_ELBOW) */
+    int32_t  n_target;            /* total_target_count (129 male / 91 female), 0 for other tasks; <= AVG_MAX_TARGET                     */
+    int32_t  n_target_upper;
+    uint32_t pad2[3];
 } AvgModelHeader;
+#define AVG_MAX_TARGET 160
 
 /* task_f indices (config.ini + task files) */
 enum {
@@ -149,8 +154,11 @@ enum {
     AVG_TF_SCRATCH_MOVE,         /* 0.01,  scratch_itch.py:66 */
     AVG_TF_FORCE_CAP,            /* 10,    scratch_itch.py:66 */
     AVG_TF_HUMAN_KP_ACTIVE,      /* human_gains passed to take_step (0.05), scratch_itch.py:45 */
-    AVG_TF_HUMAN_FORCE           /* human_forces (1.0) */
+    AVG_TF_HUMAN_FORCE,          /* human_forces (1.0) */
+    AVG_TF_CLOSEST_RANGE         /* BedBathing: getClosestPoints query distance (4.0), bed_bathing.py:61 */
 };
+/* BedBathing reuses AVG_TF_SCRATCH_W for wiping_reward_weight (config.ini:17) and AVG_TF_SUCCESS_THR for
+ * total_target_count * task_success_threshold (bed_bathing.py:72). */
 
 /* ---- per-environment record: AVG_ENV_STRIDE floats (int fields stored as int32 in the same slots) ---- */
 #define AVG_ENV_STRIDE 192
@@ -176,7 +184,8 @@ enum {
     AVG_E_OVERFLOW = 166,   /* int: bit0 contact overflow, bit1 row overflow (never silently dropped)          */
     AVG_E_SOLVER_ITERS = 167, /* int: PGS iterations executed in the last env-step (diagnostic) */
     AVG_E_NCAND = 168,       /* int: narrowphase candidate pairs examined in the last env-step (diagnostic) */
-    AVG_E_LAST = 169
+    AVG_E_TARGET_MASK = 170, /* [5] uint32: BedBathing targets not yet wiped, bit t of word t/32 (bed_bathing.py:111-125 shrink the lists) */
+    AVG_E_LAST = 175
 };
 
 /* ---- episode reset on the device (reference ScratchItchEnv.reset random draws) ----
@@ -184,7 +193,9 @@ enum {
 #define AVG_RESET_POOL 64
 typedef struct AvgResetTable {
     int32_t n_pool, n_arm, n_fin, n_hum;
-    int32_t tool_qidx, human_control, pad[2];
+    int32_t tool_qidx, human_control;
+    int32_t task;                         /* AVG_TASK_*                                                                            */
+    int32_t n_target;                     /* BedBathing: bits set in AVG_E_TARGET_MASK at reset (bed_bathing.py:369-379)           */
     float   pool_q[AVG_RESET_POOL][8];    /* robot arm joint positions of an IK start pose (scratch_itch.py:251-253, util.py:34-57) */
     float   pool_tool[AVG_RESET_POOL][8]; /* tool base pose (pos, quat, pad) that goes with it (world_creation.py:331-337)          */
     int32_t arm_qidx[8], arm_dof[8];      /* position / velocity slots of the 7 arm joints                                          */
@@ -192,6 +203,8 @@ typedef struct AvgResetTable {
     int32_t hum_qidx[8], hum_dof[8], hum_joint[8];   /* dynamic human joints (reference joint index 7..13)                          */
     float   hum_lower[8], hum_upper[8], hum_reset[8];
     float   limb_dims[2][2];              /* (length, radius) of upper arm and forearm (scratch_itch.py:277-280)                     */
+    float   fin_open;                     /* gripper open position: 1.0 ScratchItch (scratch_itch.py:254), 1.1 BedBathing (bed_bathing.py:327) */
+    float   pad_f[3];
 } AvgResetTable;
 
 /* Counter-based random numbers of the device reset: draw k of episode `episode` of environment `env` under `seed`.

@@ -91,6 +91,7 @@ typedef struct {
     const uint32_t* pair;
     const AvgFrame* frame;
     const float* mlp;
+    const float* target;     /* BedBathing wiping targets, float4 per target */
 } Model;
 
 static int model_open(const void* blob, Model* m) {
@@ -107,6 +108,7 @@ static int model_open(const void* blob, Model* m) {
     m->pair = (const uint32_t*)(b + h->off_pair);
     m->frame = (const AvgFrame*)(b + h->off_frame);
     m->mlp = h->n_mlp > 0 ? (const float*)(b + h->off_mlp) : 0;
+    m->target = h->n_target > 0 ? (const float*)(b + h->off_target) : 0;
     return 0;
 }
 
@@ -896,6 +898,111 @@ static void get_obs(const Model* m, const double* env, double tool_force, double
 #undef PUT3
 }
 
+/* ---- BedBathing (bed_bathing.py) ------------------------------------------------------------------------------ */
+/* world position of wiping target t: frame of human link 9 (upper arm) or 11 (forearm) applied to the point on the limb,
+ * bed_bathing.py:382-394 */
+static v3 bb_target_world(const Model* m, const Kin* k, int t) {
+    v3 p; quat q;
+    frame_pose(m, k, t < m->h->n_target_upper ? AVG_F_SHOULDER : AVG_F_ELBOW, &p, &q);
+    return vadd(p, qrot(q, V(m->target[4 * t], m->target[4 * t + 1], m->target[4 * t + 2])));
+}
+/* min over every (tool link, human link) pair of the closest-point distance, bed_bathing.py:61
+ * (p.getClosestPoints(tool, human, distance=4.0): one point per pair of collision shapes closer than 4 m) */
+static double bb_closest_tool_human(const Model* m, const Kin* k) {
+    int ns = m->h->n_shape;
+    double best = 1e300;
+    double range = m->h->task_f[AVG_TF_CLOSEST_RANGE];
+    for (int a = 0; a < ns; ++a) {
+        if (m->shape[a].ref_body != AVG_REF_TOOL) continue;
+        WShape wa; shape_world(m, k, a, &wa);
+        for (int b = 0; b < ns; ++b) {
+            if (m->shape[b].ref_body != AVG_REF_HUMAN) continue;
+            WShape wb; shape_world(m, k, b, &wb);
+            Contact c;
+            if (narrowphase(&wa, &wb, range, &c) && c.dist < best) best = c.dist;
+        }
+    }
+    return best;
+}
+/* bed_bathing.py:129-153 (robot half; the human half belongs to the human-active ids) */
+static void bb_get_obs(const Model* m, const double* env, double tool_force, double* obs) {
+    const AvgModelHeader* h = m->h;
+    Kin k; fk(m, env, &k);
+    v3 torso, tool, sh, el, wr; quat tq, dummy;
+    frame_pose(m, &k, AVG_F_TORSO, &torso, &dummy);
+    frame_pose(m, &k, AVG_F_TOOL_TIP, &tool, &tq);
+    frame_pose(m, &k, AVG_F_SHOULDER, &sh, &dummy);
+    frame_pose(m, &k, AVG_F_ELBOW, &el, &dummy);
+    frame_pose(m, &k, AVG_F_WRIST, &wr, &dummy);
+    int o = 0;
+    v3 t;
+    t = vsub(tool, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+    for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].action >= 0 && m->dof[i].action < h->n_action_robot) obs[o++] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+    t = vsub(sh, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    t = vsub(el, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    t = vsub(wr, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    obs[o++] = tool_force;
+}
+/* The part of BedBathingEnv.step after take_step (bed_bathing.py:53-75) with get_total_force (:77-127).
+ * out_info: [0] total_force_on_human, [1] task_success flag, [2] tool_force, [3] tool_force_on_human,
+ *           [4] reward_distance, [5] reward_action, [6] new_contact_points, [7] preferences_score */
+static void bb_finish_step(const Model* m, double* env, const Contact* contacts, int nc, double raw_sq, double* obs,
+                           double* reward, double* out_info) {
+    const AvgModelHeader* h = m->h;
+    const float* tf = h->task_f;
+    double dt = h->dt;
+    Kin k; fk(m, env, &k);
+    double tool_force = 0, tool_force_on_human = 0, total_force_on_human = 0;
+    int new_contact_points = 0;
+    for (int c = 0; c < nc; ++c) {
+        const AvgShape* sa = &m->shape[contacts[c].sa]; const AvgShape* sb = &m->shape[contacts[c].sb];
+        double force = contacts[c].lambda_n / dt;
+        int a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        int a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        int a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if (a_tool || b_tool) tool_force += force;                                         /* :83-85 */
+        if ((a_rob && b_hum) || (b_rob && a_hum)) total_force_on_human += force;           /* :90-91 */
+        if ((a_tool && b_hum) || (b_tool && a_hum)) {                                      /* :92-125 */
+            total_force_on_human += force;
+            int link_tool = a_tool ? sa->ref_link : sb->ref_link;
+            int link_hum = a_tool ? sb->ref_link : sa->ref_link;
+            v3 pos_h = a_tool ? contacts[c].pb : contacts[c].pa;                           /* positionOnB, B = human */
+            if (link_tool == 1) {
+                tool_force_on_human += force;
+                if (link_hum < 0) continue;                                                /* :100-101 (human base) */
+                for (int t = 0; t < h->n_target; ++t) {
+                    int w = AVG_E_TARGET_MASK + (t >> 5);
+                    uint32_t bits = (uint32_t)env[w];
+                    if (!(bits & (1u << (t & 31)))) continue;
+                    if (vnorm(vsub(pos_h, bb_target_world(m, &k, t))) < tf[AVG_TF_TARGET_RADIUS]) {
+                        new_contact_points += 1;
+                        env[AVG_E_TASK_SUCCESS] += 1;
+                        env[w] = (double)(bits & ~(1u << (t & 31)));
+                    }
+                }
+            }
+        }
+    }
+    v3 tip; quat tq; frame_pose(m, &k, AVG_F_TOOL_TIP, &tip, &tq);
+    int tb = m->frame[AVG_F_TOOL_TIP].body;
+    const double* tv = env + AVG_E_QD + m->body[tb].dof;
+    double ee_vel = vnorm(vadd(V(tv[0], tv[1], tv[2]), vcross(V(tv[3], tv[4], tv[5]), vsub(tip, k.p[tb]))));   /* :54 */
+    bb_get_obs(m, env, tool_force, obs);
+    double pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_on_human))
+                + tf[AVG_TF_C_HF] * (tool_force_on_human < tf[AVG_TF_FORCE_CAP] ? 0.0 : -tool_force_on_human);   /* env.py:412-448 */
+    double reward_distance = -bb_closest_tool_human(m, &k);                               /* :61 */
+    double reward_action = -raw_sq;
+    *reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action
+            + tf[AVG_TF_SCRATCH_W] * new_contact_points + pref;                            /* :65 */
+    env[AVG_E_EPISODE_RETURN] += *reward;
+    if (out_info) {
+        out_info[0] = total_force_on_human; out_info[1] = env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0 : 0.0;
+        out_info[2] = tool_force; out_info[3] = tool_force_on_human; out_info[4] = reward_distance;
+        out_info[5] = reward_action; out_info[6] = new_contact_points; out_info[7] = pref;
+    }
+}
+
 /* exported ---------------------------------------------------------------------------------------------------- */
 int avg_oracle_sizes(int* sizes) {
     sizes[0] = (int)sizeof(AvgModelHeader); sizes[1] = (int)sizeof(AvgBody); sizes[2] = (int)sizeof(AvgDof);
@@ -906,6 +1013,7 @@ int avg_oracle_sizes(int* sizes) {
 /* initial observation, scratch_itch.py:268  (_get_obs([0],[0,0]) after generate_target) */
 int avg_oracle_reset_obs(const void* blob, double* env, double* obs) {
     Model m; if (model_open(blob, &m)) return -1;
+    if (m.h->task == AVG_TASK_BED_BATHING) { bb_get_obs(&m, env, 0, obs); return 0; }     /* bed_bathing.py:350 */
     update_target(&m, env);
     get_obs(&m, env, 0, 0, 0, obs);
     return 0;
@@ -974,16 +1082,20 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
         env[AVG_E_HUMAN_KP] = h->task_f[AVG_TF_HUMAN_KP_ACTIVE];
     }
     Contact contacts[MAXC]; int nc = 0;
+    const double dt = h->dt;
     for (int f = 0; f < h->substeps; ++f) {                    /* env.py:341-349 */
         substep(&m, env, contacts, &nc);
         enforce_realistic_limits(&m, env);                     /* env.py:343-344, human_control only */
         enforce_hard_limits(&m, env);
-        update_target(&m, env);
+        if (h->task == AVG_TASK_SCRATCH_ITCH) update_target(&m, env);
     }
     env[AVG_E_ITERATION] += 1;                                 /* env.py:351 */
+    if (h->task == AVG_TASK_BED_BATHING) {
+        bb_finish_step(&m, env, contacts, nc, raw_sq, obs, reward, out_info);
+        goto report_contacts;
+    }
 
     /* get_total_force, scratch_itch.py:84-102 */
-    double dt = h->dt;
     double total_force_on_human = 0, tool_force = 0, tool_force_at_target = 0;
     int have_tcp = 0; v3 tcp = V(0, 0, 0);
     v3 tgt = V(env[AVG_E_TARGET_POS], env[AVG_E_TARGET_POS + 1], env[AVG_E_TARGET_POS + 2]);
@@ -1033,6 +1145,7 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
         out_info[2] = tool_force; out_info[3] = tool_force_at_target; out_info[4] = reward_distance;
         out_info[5] = reward_action; out_info[6] = reward_force_scratch; out_info[7] = pref;
     }
+report_contacts:
     if (contacts_out && ncontacts_out) {
         *ncontacts_out = nc;
         for (int c = 0; c < nc; ++c) {

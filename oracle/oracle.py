@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libavg_oracle.so")
 ENV_STRIDE = 192
 INT_SLOTS = (123, 152, 161, 166, 167, 168)    # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
+UINT_SLOTS = (170, 171, 172, 173, 174)        # AVG_E_TARGET_MASK words (BedBathing)
 _DP = ctypes.POINTER(ctypes.c_double)
 _FP = ctypes.POINTER(ctypes.c_float)
 _IP = ctypes.POINTER(ctypes.c_int)
@@ -34,6 +35,9 @@ def env_to_f64(env_f32: np.ndarray) -> np.ndarray:
     iv = env_f32.view(np.int32)
     for s in INT_SLOTS:
         out[..., s] = iv[..., s]
+    uv = env_f32.view(np.uint32)
+    for s in UINT_SLOTS:
+        out[..., s] = uv[..., s]
     return out
 
 
@@ -42,6 +46,9 @@ def env_to_f32(env_f64: np.ndarray) -> np.ndarray:
     iv = out.view(np.int32)
     for s in INT_SLOTS:
         iv[..., s] = np.rint(env_f64[..., s]).astype(np.int32)
+    uv = out.view(np.uint32)
+    for s in UINT_SLOTS:
+        uv[..., s] = np.rint(env_f64[..., s]).astype(np.uint32)
     return out
 
 

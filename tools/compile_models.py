@@ -13,17 +13,71 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from assistive_vr_gym_b200.compiler.blob import scene_to_blob          # noqa: E402
-from assistive_vr_gym_b200.compiler.reset import build_reset_data      # noqa: E402
-from assistive_vr_gym_b200.compiler.scene import build_scratch_itch    # noqa: E402
+from assistive_vr_gym_b200.compiler import xform as X                  # noqa: E402
+from assistive_vr_gym_b200.compiler.reset import (build_reset_data, build_reset_data_bed_bathing, bed_bathing_settle_record,  # noqa: E402
+                                                  toc_search_jaco)
+from assistive_vr_gym_b200.compiler.scene import (build_scratch_itch, build_bed_bathing, load_settled_arm_q,  # noqa: E402
+                                                  urdf_to_multibody)
+
+
+def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
+    """BedBathingJaco-v0 in two stages.  Stage 1 (always): the 'settle' worlds of both genders + their start records ->
+    BedBathingJacoSettle.npz; tools/settle_bed_bathing.py runs them for 100 sub-steps on a GPU and writes the settled
+    arm pose to data/bed_bathing_settle.json.  Stage 2 (when that file exists): per gender `n_base` robot base poses from
+    the task-oriented-configuration search (env.py:486-585), one play variant each -> BedBathingJaco.npz."""
+    payload = {}
+    for v, gender in enumerate(("male", "female")):
+        scene = build_bed_bathing(assets, "jaco", gender, stage="settle")
+        blob = scene_to_blob(scene)
+        payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+        payload[f"init_{v}"] = bed_bathing_settle_record(scene)
+        payload[f"arm_qidx_{v}"] = np.asarray([b.qidx for b in scene.bodies if b.art == 1], dtype=np.int32)
+        print("settle", gender, scene.info["n_pairs"], "pairs", len(blob), "bytes")
+    np.savez_compressed(os.path.join(out_dir, "BedBathingJacoSettle.npz"), **payload)
+    print("wrote BedBathingJacoSettle.npz")
+    settled = load_settled_arm_q()
+    if settled["male"] is None or settled["female"] is None:
+        print("no data/bed_bathing_settle.json yet: run tools/settle_bed_bathing.py on a GPU box, then re-run this tool")
+        return
+    payload = {}
+    rng = np.random.RandomState(1001)
+    robot = urdf_to_multibody(os.path.join(assets, "jaco", "j2s7s300_gym.urdf"), 0, "jaco")
+    v = 0
+    for gender in ("male", "female"):
+        probe = build_bed_bathing(assets, "jaco", gender, stage="play", arm_q=settled[gender])
+        cf = probe.multibodies[1].com_frames(probe.q_human_reset)
+        goals = [cf[9][0], cf[11][0], cf[13][0]]                              # shoulder, elbow, wrist: bed_bathing.py:303-305,325
+        for k in range(n_base):
+            xy, yaw, q_start, reached = toc_search_jaco(robot, [1, 2, 3, 4, 5, 6, 7], np.array([-0.5, -0.1, 1.0]),
+                                                        X.quat_from_euler([0, np.pi / 2.0, 0]), goals, rng, [0.1, 0.55, 0.6],
+                                                        attempts=attempts)
+            scene = build_bed_bathing(assets, "jaco", gender, stage="play", arm_q=settled[gender],
+                                      base_xy_yaw=(float(xy[0]), float(xy[1]), float(yaw)))
+            blob = scene_to_blob(scene)
+            payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+            rd = build_reset_data_bed_bathing(scene, q_start)
+            for key, a in rd.items():
+                payload[f"reset_{v}_{key}"] = a
+            print("play", gender, k, "base", np.round(xy, 3), "yaw", round(float(yaw), 3), "goals reached", reached,
+                  scene.info["n_pairs"], "pairs", len(blob), "bytes")
+            v += 1
+    np.savez_compressed(os.path.join(out_dir, "BedBathingJaco.npz"), **payload)
+    print("wrote BedBathingJaco.npz")
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--assets", default="/root/reference/assistive_gym/envs/assets")
     ap.add_argument("--pool", type=int, default=64)
+    ap.add_argument("--only", default="", help="scratch_itch | bed_bathing (default: both)")
+    ap.add_argument("--bases", type=int, default=8, help="BedBathing: robot base poses (model variants) per gender")
+    ap.add_argument("--attempts", type=int, default=100, help="BedBathing: base poses tried per TOC search (env.py:486)")
     args = ap.parse_args()
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data")
     os.makedirs(out_dir, exist_ok=True)
-    for human_control in (False, True):
+    if args.only in ("", "bed_bathing"):
+        compile_bed_bathing(args.assets, out_dir, args.bases, args.attempts)
+    for human_control in ((False, True) if args.only in ("", "scratch_itch") else ()):
         payload = {}
         rng = np.random.RandomState(1001)              # env.py:53 default seed
         for v, gender in enumerate(("male", "female")):
