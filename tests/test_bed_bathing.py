@@ -1,0 +1,383 @@
+"""BedBathingJaco-v0: oracle checks on the CPU, CUDA-vs-oracle parity on the GPU.
+
+Anchors that come from the reference tree itself:
+  * total_target_count = 129 (male) / 91 (female): `util.capsule_points` with the limb dimensions of
+    `bed_bathing.py:361-368` (SURVEY.md §8c "constants");
+  * the settled right-arm pose: `bed_bathing.py:245` hard-codes `joint_angles = [0.397, 0.279, -0.009, -0.673, -0.006,
+    0.060, 0.010]` for the VR branch -- the pose PyBullet produced for the authors after the same drop onto the same
+    mattress.  It is the only number in the tree that came out of the reference's physics engine; our restated
+    `stepSimulation` must land the arm there (shoulder / elbow joints within a few hundredths of a radian).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS
+
+DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data")
+REF_SETTLED_ARM = np.array([0.39717707, 0.27890519, -0.00883447, -0.67345593, -0.00568484, 0.05987911, 0.00957937])  # bed_bathing.py:245
+
+
+def _settle_with_oracle(v):
+    from oracle.oracle import Oracle, env_to_f64
+    z = np.load(os.path.join(DATA, "BedBathingJacoSettle.npz"))
+    o = Oracle(z[f"blob_{v}"].tobytes())
+    env = env_to_f64(z[f"init_{v}"]).copy()
+    for _ in range(20):                                             # 20 env-steps x frame_skip 5 = the 100 sub-steps of bed_bathing.py:291
+        o.step(env, np.zeros(7, np.float32))
+    return env[z[f"arm_qidx_{v}"]], env[32 + z[f"arm_qidx_{v}"]], int(env[166])
+
+
+def test_capsule_points_counts():
+    from assistive_vr_gym_b200.compiler.scene import bed_bathing_targets, capsule_points
+    up, fo = bed_bathing_targets("male", 0.6)
+    assert len(up) + len(fo) == 129
+    up, fo = bed_bathing_targets("female", 0.54)
+    assert len(up) + len(fo) == 91
+    # every point sits on the cylinder surface, sections are evenly spaced (util.py:154-165)
+    p = capsule_points([0, 0, 0], [0, 0, -0.279], 0.043, 0.03)
+    assert np.allclose(np.hypot(p[:, 0], p[:, 1]), 0.043)
+    zs = np.unique(np.round(p[:, 2], 9))
+    assert len(zs) == int(0.279 / 0.03) and np.allclose(np.diff(zs), 0.279 / (len(zs) + 1))
+
+
+def test_oracle_settle_lands_on_the_reference_arm_pose():
+    q, qd, overflow = _settle_with_oracle(0)
+    assert overflow == 0
+    assert np.abs(qd).max() < 0.05                                  # at rest
+    assert np.abs(q[:6] - REF_SETTLED_ARM[:6]).max() < 0.06, q      # shoulder (3), elbow, forearm roll, wrist flexion
+    assert abs(q[1] - REF_SETTLED_ARM[1]) < 5e-3                    # the joint the mattress determines most directly
+
+
+def test_committed_settle_pose_is_the_oracles():
+    """data/bed_bathing_settle.json was produced by the CUDA kernels (tools/settle_bed_bathing.py); the float64 oracle
+    must come to rest in the same place (the drop is a contact-rich, 100-sub-step trajectory: centi-radian agreement;
+    the female arm agrees to 1e-5, the male wrist flexion differs by 0.07 rad after a different bounce)."""
+    path = os.path.join(DATA, "bed_bathing_settle.json")
+    if not os.path.exists(path):
+        pytest.skip("bed_bathing_settle.json not generated yet")
+    with open(path) as f:
+        d = json.load(f)
+    for v, g in enumerate(("male", "female")):
+        q, _, _ = _settle_with_oracle(v)
+        dq = np.abs(q - np.asarray(d[g]["arm_q"]))
+        assert dq[:5].max() < 0.02 and dq.max() < 0.1, (g, q, d[g]["arm_q"])       # wrist joints (hand sphere rolling on the sheet) are the loosest
+        assert d[g]["overflow"] == 0
+
+
+@pytest.fixture(scope="module")
+def bb_data():
+    from assistive_vr_gym_b200.envs import load_env_data
+    if not os.path.exists(os.path.join(DATA, "BedBathingJaco.npz")):
+        pytest.skip("BedBathingJaco.npz not compiled yet")
+    return load_env_data("BedBathingJaco.npz")
+
+
+@pytest.fixture(scope="module")
+def bb_oracles(bb_data):
+    from oracle.oracle import Oracle
+    return [Oracle(b) for b in bb_data[0]]
+
+
+def _box_capsule_distance(box_p, box_R, half, margin, seg_a, seg_b, radius):
+    """Independent closest distance between a margin-rounded box (core = half - margin, Bullet's box with margin) and a
+    capsule, by bounded minimisation over (point in the core box, point on the segment)."""
+    from scipy.optimize import minimize
+    core = np.asarray(half) - margin
+
+    def f(x):
+        pb = box_p + box_R @ x[:3]
+        ps = seg_a + (seg_b - seg_a) * x[3]
+        return float(np.sum((pb - ps) ** 2))
+
+    best = np.inf
+    for x0 in ([0, 0, 0, 0.5], [core[0], core[1], core[2], 0.0], [-core[0], -core[1], -core[2], 1.0]):
+        r = minimize(f, np.asarray(x0, float), method="L-BFGS-B", bounds=[(-core[0], core[0]), (-core[1], core[1]), (-core[2], core[2]), (0, 1)],
+                     options=dict(ftol=1e-18, gtol=1e-14, maxiter=500))
+        best = min(best, r.fun)
+    return np.sqrt(best) - margin - radius
+
+
+def test_oracle_closest_distance_and_reward_against_numpy(bb_data, bb_oracles):
+    """reward = -min closest distance + 0.01 * (-|a|^2) + 5 * new points + preferences (bed_bathing.py:61-65), with the
+    closest tool-human distance recomputed independently for the capsule / sphere links (the head hulls are far away)."""
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from helpers import quat_rot
+    from oracle.oracle import env_to_f64
+    blobs, resets = bb_data
+    env, variant = sample_states(resets, 6, np.random.RandomState(4))
+    rng = np.random.RandomState(1)
+    for e in range(6):
+        o = bb_oracles[int(variant[e])]
+        rec = env_to_f64(env[e]).copy()
+        obs0 = o.reset_obs(rec)
+        assert obs0.shape == (24,) and obs0[-1] == 0.0
+        a = rng.uniform(-1, 1, 7).astype(np.float32)
+        for _ in range(3):
+            obs, rew, info, cont = o.step(rec, a)
+        sh = o.model["shapes"]; bodies = o.model["bodies"]
+        tool_shapes = [i for i in range(len(sh)) if sh[i]["ref_body"] == 2]
+        assert len(tool_shapes) == 3
+        tb = int(sh[tool_shapes[0]]["body"])
+        tq = int(bodies[tb]["qidx"])
+        tp, tr = rec[tq:tq + 3], rec[tq + 3:tq + 7]
+        best = np.inf
+        for ti in tool_shapes:
+            S = sh[ti]
+            bp = tp + quat_rot(tr, S["pos"])
+            x, y, z, w = tr; sx, sy, sz, sw = S["quat"]
+            q = np.array([w * sx + x * sw + y * sz - z * sy, w * sy - x * sz + y * sw + z * sx, w * sz + x * sy - y * sx + z * sw, w * sw - x * sx - y * sy - z * sz])
+            R = np.stack([quat_rot(q, ex) for ex in np.eye(3)], axis=1)
+            for hi in range(len(sh)):
+                H = sh[hi]
+                if H["ref_body"] != 1 or H["type"] not in (0, 1):
+                    continue
+                hl = float(H["half"][2]) if H["type"] == 1 else 0.0
+                a0 = H["pos"] + quat_rot(H["quat"], [0, 0, -hl]); a1 = H["pos"] + quat_rot(H["quat"], [0, 0, hl])
+                best = min(best, _box_capsule_distance(bp, R, S["half"], float(S["margin"]), a0.astype(float), a1.astype(float), float(H["radius"])))
+        assert abs(-info[4] - best) < 2e-6, (info[4], best)
+        tf = o.model["header"]["task_f"]
+        expect = tf[0] * info[4] + tf[1] * (-float(np.sum(a.astype(np.float64) ** 2))) + tf[3] * info[6] + info[7]
+        assert abs(rew - expect) < 1e-7                                  # task_f is float32
+        # observation layout, bed_bathing.py:147
+        torso = o.frame(rec, 3)[:3]; tool = o.frame(rec, 0)
+        assert np.allclose(obs[:3], tool[:3] - torso) and np.allclose(obs[3:7], tool[3:])
+        arm_q = [rec[int(bodies[int(d["body"])]["qidx"])] for d in o.model["dofs"] if 0 <= d["action"] < 7]
+        assert np.allclose(obs[7:14], arm_q)
+        for k, f in enumerate((5, 6, 7)):
+            assert np.allclose(obs[14 + 3 * k:17 + 3 * k], o.frame(rec, f)[:3] - torso)
+        assert obs[23] == info[2]
+
+
+def _place_wiper_on_target(o, rec, t, depth=0.002):
+    """Move the wiper (free body) so that its cloth pad presses on wiping target t of the static arm."""
+    from helpers import quat_rot
+    h = o.model["header"]; sh = o.model["shapes"]; bodies = o.model["bodies"]
+    n_up = int(h["n_target_upper"])
+    fr = o.frame(rec, 5 if t < n_up else 6)
+    axis = quat_rot(fr[3:], [0, 0, 1.0])
+    tw = fr[:3] + quat_rot(fr[3:], o.model["targets"][t])
+    centre = fr[:3] + axis * np.dot(tw - fr[:3], axis)
+    nrm = (tw - centre) / np.linalg.norm(tw - centre)
+    cloth = [i for i in range(len(sh)) if sh[i]["ref_body"] == 2 and sh[i]["ref_link"] == 1][0]
+    S = sh[cloth]
+    # tool orientation: cloth -z (its bottom face) along -nrm, i.e. tool z = nrm; x along the limb axis
+    zc = nrm; xc = axis - zc * np.dot(axis, zc); xc /= np.linalg.norm(xc); yc = np.cross(zc, xc)
+    R = np.stack([xc, yc, zc], axis=1)
+    from assistive_vr_gym_b200.compiler import xform as X
+    q_cloth = X.mat_to_quat(R)
+    p_cloth = tw + nrm * (float(S["half"][2]) - depth)
+    # body pose = cloth pose * inverse(shape offset in the body frame)
+    ip, iq = X.tf_inv(S["pos"].astype(float), S["quat"].astype(float))
+    bp, bq = X.tf_mul(p_cloth, q_cloth, ip, iq)
+    tq = int(bodies[int(S["body"])]["qidx"])
+    rec[tq:tq + 3] = bp; rec[tq + 3:tq + 7] = bq
+    return tw
+
+
+def test_oracle_wipes_targets_once(bb_data, bb_oracles):
+    """A pad contact within 0.025 of alive targets removes them, counts them in the reward once, and never again
+    (bed_bathing.py:97-125)."""
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from helpers import patch_blob
+    from oracle.oracle import Oracle, env_to_f64
+    blobs, resets = bb_data
+    env, variant = sample_states(resets, 1, np.random.RandomState(0))
+    o = Oracle(patch_blob(blobs[int(variant[0])], header={"substeps": 1}))
+    rec = env_to_f64(env[0]).copy()
+    n_target = int(o.model["header"]["n_target"])
+    assert sum(bin(int(rec[170 + w])).count("1") for w in range(5)) == n_target
+    t = 40
+    tw = _place_wiper_on_target(o, rec, t)
+    obs, rew, info, cont = o.step(rec, np.zeros(7, np.float32))
+    assert info[6] >= 1 and info[3] >= 0.0
+    alive = sum(bin(int(rec[170 + w])).count("1") for w in range(5))
+    assert alive == n_target - int(info[6]) and rec[153] == info[6]
+    assert not (int(rec[170 + (t >> 5)]) >> (t & 31)) & 1
+    # every removed target was within 0.025 of a pad contact point on the human
+    # a second press on the same spot wipes nothing new
+    _place_wiper_on_target(o, rec, t)
+    rec[32:64] = 0
+    obs, rew, info2, cont = o.step(rec, np.zeros(7, np.float32))
+    assert info2[6] == 0 and rec[153] == info[6]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.mark.gpu
+def test_gpu_settle_reproduces_committed_pose(torch_cuda):
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import capi
+    path = os.path.join(DATA, "bed_bathing_settle.json")
+    with open(path) as f:
+        d = json.load(f)
+    z = np.load(os.path.join(DATA, "BedBathingJacoSettle.npz"))
+    sim = capi.Sim(2, 0)
+    for v in range(2):
+        sim.upload_model(v, z[f"blob_{v}"].tobytes())
+    sim.set_state(np.stack([z["init_0"], z["init_1"]]), np.array([0, 1], dtype=np.int32))
+    act = torch.zeros((2, 7), device="cuda"); obs = torch.zeros((2, sim.n_obs), device="cuda")
+    rew = torch.zeros(2, device="cuda"); info = torch.zeros((2, 2), device="cuda")
+    for _ in range(20):
+        sim.step(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), 0, info.data_ptr(), 0)
+    torch.cuda.synchronize()
+    st = sim.get_state()
+    for v, g in enumerate(("male", "female")):
+        q = st[v, z[f"arm_qidx_{v}"]]
+        assert np.abs(q - np.asarray(d[g]["arm_q"])).max() < 1e-5, (g, q)
+    assert np.abs(st[0, z["arm_qidx_0"]][:6] - REF_SETTLED_ARM[:6]).max() < 0.06
+    sim.close()
+
+
+def _bb_env(n, seed=3):
+    from assistive_vr_gym_b200 import make
+    env = make("BedBathingJaco-v0", num_envs=n, device=0, seed=seed)
+    env.sim.enable_debug(True)
+    return env
+
+
+@pytest.mark.gpu
+def test_gpu_reset_observation_and_trajectories_match_oracle(torch_cuda, bb_oracles):
+    """Reset observation (1e-5) and 10 env-steps of random actions: contact-free environments agree within
+    |dq| <= 1e-4, |dqd| <= 1e-3, |dreward| <= 1e-3 (the reward includes the closest tool-human distance), obs 1e-3."""
+    torch = torch_cuda
+    from oracle.oracle import env_to_f64
+    n, T = 64, 10
+    env = _bb_env(n, seed=5)
+    obs = env.reset().cpu().numpy()
+    assert obs.shape == (n, 24)
+    st0 = env.get_state()
+    assert len(set(env.variants.tolist())) > 4                        # genders x robot base poses
+    recs = [env_to_f64(st0[e]).copy() for e in range(n)]
+    for e in range(n):
+        assert np.abs(bb_oracles[int(env.variants[e])].reset_obs(recs[e]) - obs[e]).max() < 1e-5
+    clean = np.ones(n, dtype=bool)
+    rng = np.random.RandomState(0)
+    worst = np.zeros(4)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
+        st = env.get_state(); cont, ncont = env.sim.get_contacts(); terms = env.sim.get_reward_terms()
+        rew = rew.cpu().numpy(); obs = obs.cpu().numpy()
+        for e in range(n):
+            oobs, orew, oinfo, oc = bb_oracles[int(env.variants[e])].step(recs[e], a[e])
+            if len(oc) or ncont[e]:
+                clean[e] = False
+            if clean[e]:
+                worst = np.maximum(worst, [np.abs(recs[e][:32] - st[e, :32]).max(), np.abs(recs[e][32:64] - st[e, 32:64]).max(),
+                                           abs(orew - rew[e]), abs(oinfo[4] - terms[e, 4])])
+                assert np.abs(oobs - obs[e]).max() < 1e-3
+    assert clean.sum() >= n // 3, "too few contact-free environments to be meaningful"
+    assert worst[0] <= 1e-4 and worst[1] <= 1e-3 and worst[2] <= 1e-3 and worst[3] <= 1e-4, worst
+    assert int(st.view(np.int32)[:, 166].max()) == 0
+    env.close()
+
+
+@pytest.mark.gpu
+def test_gpu_wiping_matches_oracle_bit_exactly(torch_cuda, bb_data):
+    """One sub-step with the wiper pressed on a target: contact pairs, wiped-target bitmaps, new_contact_points and the
+    task_success counter identical to the oracle's; forces and reward within tolerance."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import capi
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from helpers import patch_blob
+    from oracle.oracle import Oracle, env_to_f64, env_to_f32
+    blobs, resets = bb_data
+    pb = [patch_blob(b, header={"substeps": 1, "residual_thr": 0.0}) for b in blobs]
+    oracles = [Oracle(b) for b in pb]
+    n = 96
+    env0, variant = sample_states(resets, n, np.random.RandomState(7))
+    rng = np.random.RandomState(2)
+    recs = []
+    for e in range(n):
+        o = oracles[int(variant[e])]
+        rec = env_to_f64(env0[e]).copy()
+        t = int(rng.randint(int(o.model["header"]["n_target"])))
+        _place_wiper_on_target(o, rec, t, depth=float(rng.uniform(-0.004, 0.004)))
+        recs.append(rec)
+    start = np.stack([env_to_f32(r) for r in recs])
+    sim = capi.Sim(n, 0)
+    for v, b in enumerate(pb):
+        sim.upload_model(v, b)
+    sim.enable_debug(True)
+    sim.set_state(start, variant)
+    obs = torch.zeros((n, 24), device="cuda"); rew = torch.zeros(n, device="cuda"); info = torch.zeros((n, 2), device="cuda")
+    a = np.random.RandomState(0).uniform(-1, 1, (n, 7)).astype(np.float32)
+    act = torch.as_tensor(a, device="cuda")
+    sim.step(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), 0, info.data_ptr(), 0)
+    torch.cuda.synchronize()
+    st = sim.get_state(); cont, nc = sim.get_contacts(); terms = sim.get_reward_terms()
+    wiped_total = 0
+    for e in range(n):
+        o = oracles[int(variant[e])]
+        rec = env_to_f64(start[e]).copy()
+        oobs, orew, oinfo, ocont = o.step(rec, a[e])
+        gp = [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :nc[e]]]
+        op = [(int(c[0]), int(c[1])) for c in ocont]
+        borderline = any(abs(c[11] - min(float(o.model["shapes"][int(c[0])]["thr"]), float(o.model["shapes"][int(c[1])]["thr"]))) < 2e-6 for c in ocont)
+        if not borderline:
+            assert gp == op, (e, gp, op)
+        # a target exactly at the 0.025 radius may flip in float32: compare bitmaps unless some target sits on the boundary
+        masks_o = [int(rec[170 + w]) for w in range(5)]
+        masks_g = [int(x) for x in st[e].view(np.uint32)[170:175]]
+        assert masks_g == masks_o, (e, masks_g, masks_o)
+        assert int(terms[e, 6]) == int(oinfo[6]) and st[e, 153] == rec[153]
+        wiped_total += int(oinfo[6])
+        assert abs(oinfo[4] - terms[e, 4]) < 5e-5                      # closest tool-human distance
+        assert np.abs(oinfo[:4] - terms[e, :4]).max() < 5e-3 * max(1.0, np.abs(oinfo[:4]).max())
+        assert abs(orew - float(rew[e])) < 1e-3 * max(1.0, abs(orew))
+    assert wiped_total >= n // 2
+    sim.close()
+
+
+@pytest.mark.gpu
+def test_gpu_device_reset_matches_mirror(torch_cuda, bb_data):
+    torch = torch_cuda
+    from assistive_vr_gym_b200.compiler.reset import sample_states_hashed
+    n = 512
+    env = _bb_env(n)
+    env.reset_device(seed=1234)
+    torch.cuda.synchronize()
+    st = env.get_state()
+    ref, variant = sample_states_hashed(bb_data[1], n, 1234, np.ones(n, dtype=np.int64))
+    assert np.array_equal(st.view(np.uint32)[:, :170], ref.view(np.uint32)[:, :170])
+    assert np.array_equal(st.view(np.uint32)[:, 170:175], ref.view(np.uint32)[:, 170:175])
+    assert len(set(variant.tolist())) == len(bb_data[0])
+    env.close()
+
+
+@pytest.mark.gpu
+def test_gpu_episode_invariants(torch_cuda):
+    """200 random-action env-steps at 4096 envs: finite state, unit quaternions, alive-target count only decreases and
+    equals total - task_success, reward finite, no overflow flags."""
+    torch = torch_cuda
+    n = 4096
+    env = _bb_env(n)
+    env.sim.enable_debug(False)
+    env.reset_device(seed=7)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    prev_alive = None
+    for t in range(200):
+        a = torch.rand((n, 7), device="cuda", generator=g) * 2 - 1
+        obs, rew, done, info = env.step(a)
+        if t % 50 == 49:
+            st = env.get_state()
+            assert np.isfinite(st[:, :64]).all() and torch.isfinite(rew).all() and torch.isfinite(obs).all()
+            alive = np.array([[bin(int(x)).count("1") for x in row] for row in st.view(np.uint32)[:, 170:175]]).sum(1)
+            if prev_alive is not None:
+                assert (alive <= prev_alive).all()
+            prev_alive = alive
+            assert int(st.view(np.int32)[:, 166].max() & 2) == 0
+    assert bool(done.all())                                            # TimeLimit(200)
+    env.close()
