@@ -250,6 +250,52 @@ __device__ __noinline__ V3 support(const WShape& w, V3 d) {
     return w.p + mmul(w.R, r);
 }
 
+// Supporting FEATURE of the core in world direction d (|d| = 1): centroid of the core points whose support value is within
+// kFeatTol of the maximum, and the feature's size class (1 vertex, 2 edge, >= 4 face).  Penetration witnesses come from
+// here: the arg-max vertex of a polytope along one of its own face normals is decided by rounding noise, the centroid of
+// the tied vertices is not (same rule as support_feature() of the oracle).  Serial; only the rare SAT path calls it.
+constexpr float kFeatTol = 1e-4f;
+__device__ __noinline__ V3 support_feature(const WShape& w, V3 d, int& count) {
+    const AvgShape* S = w.s;
+    const V3 l = mtmul(w.R, d);
+    V3 r = mk3(0, 0, 0);
+    int cnt = 1;
+    switch (S->type) {
+    case AVG_SHAPE_CAPSULE:
+        if (fabsf(l.z) <= kFeatTol) cnt = 2; else r = mk3(0, 0, l.z > 0 ? S->half[2] : -S->half[2]);
+        break;
+    case AVG_SHAPE_BOX: {
+        const float hx = S->half[0] - S->margin, hy = S->half[1] - S->margin, hz = S->half[2] - S->margin;
+        if (fabsf(l.x) <= kFeatTol) cnt *= 2; else r.x = l.x > 0 ? hx : -hx;
+        if (fabsf(l.y) <= kFeatTol) cnt *= 2; else r.y = l.y > 0 ? hy : -hy;
+        if (fabsf(l.z) <= kFeatTol) cnt *= 2; else r.z = l.z > 0 ? hz : -hz;
+        break;
+    }
+    case AVG_SHAPE_CYLINDER: {
+        const float rc = S->radius - S->margin, hc = S->half[2] - S->margin;
+        const float n = sqrtf(l.x * l.x + l.y * l.y);
+        if (fabsf(l.z) <= kFeatTol) cnt *= 2; else r.z = l.z > 0 ? hc : -hc;
+        if (n > kFeatTol) { r.x = rc * l.x / n; r.y = rc * l.y / n; } else cnt *= 8;
+        break;
+    }
+    case AVG_SHAPE_HULL: {
+        const float4* v = reinterpret_cast<const float4*>(w.verts);
+        float bd = -3.0e38f;
+        for (int i = 0; i < S->vert_cnt; ++i) { const float4 p = __ldg(v + i); bd = fmaxf(bd, fmaf(l.x, p.x, fmaf(l.y, p.y, l.z * p.z))); }
+        V3 acc = mk3(0, 0, 0); cnt = 0;
+        for (int i = 0; i < S->vert_cnt; ++i) {
+            const float4 p = __ldg(v + i);
+            if (fmaf(l.x, p.x, fmaf(l.y, p.y, l.z * p.z)) >= bd - kFeatTol) { acc = acc + mk3(p.x, p.y, p.z); cnt++; }
+        }
+        r = acc * (1.0f / (float)max(cnt, 1));
+        break;
+    }
+    default: break;                  // sphere: its centre
+    }
+    count = cnt;
+    return w.p + mmul(w.R, r);
+}
+
 struct Simplex { V3 w[4], a[4], b[4]; float lam[4]; int n; };
 
 __device__ void closest_tri(const V3& a, const V3& b, const V3& c, float lam[3], int& mask) {
@@ -445,7 +491,7 @@ __device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool n
 #pragma unroll
         for (int i = 0; i < 9; ++i) { a.R[i] = __shfl_sync(AVG_FULL, A.R[i], src); b.R[i] = __shfl_sync(AVG_FULL, B.R[i], src); }
         const int ka = sat_axis_count(a), kb = sat_axis_count(b), K = ka + kb + 1;
-        float best = 3.0e38f; int bk = 0x7fffffff; V3 bn = mk3(0, 0, 1), bsa = a.p, bsb = a.p;
+        float best = 3.0e38f; int bk = 0x7fffffff; V3 bn = mk3(0, 0, 1);
         for (int k = lane; k < K; k += 32) {
             V3 n = k < ka ? sat_axis_dir(a, b, -1.0f, k) : (k < ka + kb ? sat_axis_dir(b, a, 1.0f, k - ka) : a.p - b.p);
             const float ln = norm(n);
@@ -453,7 +499,7 @@ __device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool n
             n = n * (1.0f / ln);
             const V3 sa = support(a, -n), sb = support(b, n);
             const float depth = dot(sb - sa, n);
-            if (depth < best) { best = depth; bk = k; bn = n; bsa = sa; bsb = sb; }
+            if (depth < best) { best = depth; bk = k; bn = n; }
         }
         float wbest = best; int wk = bk;
 #pragma unroll
@@ -463,13 +509,18 @@ __device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool n
         }
         const int win = __ffs(__ballot_sync(AVG_FULL, bk == wk && wk != 0x7fffffff)) - 1;
         const int w = win < 0 ? 0 : win;
-        const V3 n = shfl3(bn, w), sa = shfl3(bsa, w), sb = shfl3(bsb, w);
+        const V3 n = shfl3(bn, w);
         if (lane == src) {
-            // anchor the witness on the round shape when there is one: a polytope's support point along a face normal
-            // is not unique
+            // witness on A's core: from the round shape when there is one, otherwise from the smaller supporting feature
+            // (sat_axis() of the oracle)
             const bool ra = A.s->type == AVG_SHAPE_SPHERE || A.s->type == AVG_SHAPE_CAPSULE;
             const bool rb = B.s->type == AVG_SHAPE_SPHERE || B.s->type == AVG_SHAPE_CAPSULE;
-            if (win >= 0) { best_out = wbest; bn_out = n; bpa_out = (rb && !ra) ? sb - n * wbest : sa; }
+            if (win >= 0) {
+                int ca, cb;
+                const V3 fa = support_feature(A, -n, ca), fb = support_feature(B, n, cb);
+                best_out = wbest; bn_out = n;
+                bpa_out = (rb && !ra) ? fb - n * wbest : (ra ? fa : (ca <= cb ? fa : fb - n * wbest));
+            }
             else { best_out = 3.0e38f; bn_out = mk3(0, 0, 1); bpa_out = A.p; }
         }
     }
@@ -1784,7 +1835,8 @@ __device__ float bb_pair_distance(const KM& m, const SM& s, int ti, int hi, bool
     epi_load_shape(m, s, s.tool_idx[ti], A); epi_load_shape(m, s, s.hum_idx[hi], B);
     const float ma = A.s->margin, mb = B.s->margin;
     float dist = 0.0f, gap = 0.0f; V3 ca = A.p, cb = B.p, vout = mk3(0, 0, 0); int gi = 0;
-    const int g = gjk_lockstep(A, B, active, lane, bound + ma + mb, dist, ca, cb, vout, gap, gi);
+    // cores farther apart than bound + margins cannot beat `bound`; with a negative bound any separated cores qualify
+    const int g = gjk_lockstep(A, B, active, lane, fmaxf(bound + ma + mb, 0.0f), dist, ca, cb, vout, gap, gi);
     float best = 3.0e38f; V3 bn = mk3(0, 0, 1), bpa = A.p;
     sat_served(A, B, g == 1, lane, best, bn, bpa);
     if (g == 0) return dist - ma - mb;
@@ -1903,7 +1955,9 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
         best = __shfl_sync(AVG_FULL, best, 0);
         int p = lane;
         while (true) {
-            while (p < npair && (p == p0 || bb_pair_bound(m, s, p / nh, p % nh) >= best)) p += 32;
+            // the capsule bound is a bound on separation; once the best pair penetrates (face-normal SAT depths are not
+            // minimal translations) only pairs whose bounding capsules are apart can be skipped
+            while (p < npair && (p == p0 || bb_pair_bound(m, s, p / nh, p % nh) >= fmaxf(best, 0.0f))) p += 32;
             const bool active = p < npair;
             if (!__any_sync(AVG_FULL, active)) break;
             const int pp = active ? p : 0;

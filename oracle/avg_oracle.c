@@ -228,6 +228,51 @@ static v3 support(const WShape* w, v3 d) {
     return vadd(w->p, mmulv(&w->R, r));
 }
 
+/* Supporting FEATURE of the core of shape w in world direction d (|d| = 1): centroid of every core point whose support
+ * value lies within FEAT_TOL of the maximum, and the feature's size class (1 vertex, 2 edge, 4 or more face).  A
+ * polytope's support point along one of its own face normals is not unique -- which vertex of the face wins the arg-max is
+ * decided by rounding noise -- so penetration witnesses are taken from the feature centroid, which float32 and float64
+ * agree on. */
+#define FEAT_TOL 1e-4
+static v3 support_feature(const WShape* w, v3 d, int* count) {
+    const AvgShape* s = w->s;
+    v3 l = mtmulv(&w->R, d), r;
+    int cnt = 1;
+    switch (s->type) {
+    case AVG_SHAPE_CAPSULE:
+        if (fabs(l.z) <= FEAT_TOL) { r = V(0, 0, 0); cnt = 2; } else r = V(0, 0, l.z > 0 ? s->half[2] : -s->half[2]);
+        break;
+    case AVG_SHAPE_BOX: {
+        double hh[3] = {s->half[0] - s->margin, s->half[1] - s->margin, s->half[2] - s->margin}, ll[3] = {l.x, l.y, l.z}, rr[3];
+        for (int k = 0; k < 3; ++k) { if (fabs(ll[k]) <= FEAT_TOL) { rr[k] = 0; cnt *= 2; } else rr[k] = ll[k] > 0 ? hh[k] : -hh[k]; }
+        r = V(rr[0], rr[1], rr[2]); break;
+    }
+    case AVG_SHAPE_CYLINDER: {
+        double rc = s->radius - s->margin, hc = s->half[2] - s->margin;
+        double n = sqrt(l.x * l.x + l.y * l.y);
+        double z = 0; if (fabs(l.z) <= FEAT_TOL) cnt *= 2; else z = l.z > 0 ? hc : -hc;
+        if (n > FEAT_TOL) r = V(rc * l.x / n, rc * l.y / n, z); else { r = V(0, 0, z); cnt *= 8; }
+        break;
+    }
+    case AVG_SHAPE_HULL: {
+        double bd = -1e300;
+        for (int i = 0; i < s->vert_cnt; ++i) {
+            double dd = l.x * w->verts[4 * i] + l.y * w->verts[4 * i + 1] + l.z * w->verts[4 * i + 2];
+            if (dd > bd) bd = dd;
+        }
+        v3 acc = V(0, 0, 0); cnt = 0;
+        for (int i = 0; i < s->vert_cnt; ++i) {
+            double dd = l.x * w->verts[4 * i] + l.y * w->verts[4 * i + 1] + l.z * w->verts[4 * i + 2];
+            if (dd >= bd - FEAT_TOL) { acc = vadd(acc, V(w->verts[4 * i], w->verts[4 * i + 1], w->verts[4 * i + 2])); cnt++; }
+        }
+        r = vscale(acc, 1.0 / (cnt > 0 ? cnt : 1)); break;
+    }
+    default: r = V(0, 0, 0);       /* sphere: its centre */
+    }
+    *count = cnt;
+    return vadd(w->p, mmulv(&w->R, r));
+}
+
 typedef struct { v3 w[4], a[4], b[4]; double lam[4]; int n; } Simplex;
 
 /* closest point to the origin on the simplex; reduces the simplex to the supporting feature, fills lam.
@@ -331,8 +376,7 @@ static int gjk(const WShape* A, const WShape* B, double* dist, v3* pa, v3* pb) {
 
 /* deep-penetration fallback: smallest overlap among face-normal / centre axes evaluated with support functions */
 static int is_round(const WShape* S) { return S->s->type == AVG_SHAPE_SPHERE || S->s->type == AVG_SHAPE_CAPSULE; }
-/* bpa = core witness on A.  The witness is anchored on the round shape (sphere / capsule core) when there is one,
- * because the support point of a polytope along a face normal is not unique (any vertex of the face). */
+/* bpa = core witness on A, see support_feature(). */
 static void sat_axis(const WShape* A, const WShape* B, v3 n, double* best, v3* bn, v3* bpa) {
     double ln = vnorm(n);
     if (ln < 1e-12) return;
@@ -341,7 +385,13 @@ static void sat_axis(const WShape* A, const WShape* B, v3 n, double* best, v3* b
     double depth = vdot(sb, n) - vdot(sa, n);
     if (depth < *best) {
         *best = depth; *bn = n;
-        *bpa = (is_round(B) && !is_round(A)) ? vsub(sb, vscale(n, depth)) : sa;
+        /* witness on A's core: from the round shape when there is one, otherwise from the smaller supporting feature
+         * (a vertex pressing into a face marks the contact, the face's centroid does not) */
+        int ca, cb;
+        v3 fa = support_feature(A, vneg(n), &ca), fb = support_feature(B, n, &cb);
+        if (is_round(B) && !is_round(A)) *bpa = vsub(fb, vscale(n, depth));
+        else if (is_round(A)) *bpa = fa;
+        else *bpa = (ca <= cb) ? fa : vsub(fb, vscale(n, depth));
     }
 }
 static void shape_axes(const WShape* S, const WShape* O, double sign, const WShape* A, const WShape* B, double* best, v3* bn, v3* bpa) {

@@ -151,8 +151,10 @@ def test_oracle_closest_distance_and_reward_against_numpy(bb_data, bb_oracles):
         assert obs[23] == info[2]
 
 
-def _place_wiper_on_target(o, rec, t, depth=0.002):
-    """Move the wiper (free body) so that its cloth pad presses on wiping target t of the static arm."""
+def _place_wiper_on_target(o, rec, t, depth=0.002, tilt=(0.06, -0.04)):
+    """Move the wiper (free body) so that its cloth pad presses on wiping target t of the static arm.  The pad is tilted a
+    few degrees off the limb's tangent plane: a face lying exactly along the capsule axis has a whole segment of closest
+    points and the contact position would be arbitrary."""
     from helpers import quat_rot
     h = o.model["header"]; sh = o.model["shapes"]; bodies = o.model["bodies"]
     n_up = int(h["n_target_upper"])
@@ -167,7 +169,7 @@ def _place_wiper_on_target(o, rec, t, depth=0.002):
     zc = nrm; xc = axis - zc * np.dot(axis, zc); xc /= np.linalg.norm(xc); yc = np.cross(zc, xc)
     R = np.stack([xc, yc, zc], axis=1)
     from assistive_vr_gym_b200.compiler import xform as X
-    q_cloth = X.mat_to_quat(R)
+    q_cloth = X.quat_mul(X.mat_to_quat(R), X.quat_from_euler([tilt[0], tilt[1], 0.0]))
     p_cloth = tw + nrm * (float(S["half"][2]) - depth)
     # body pose = cloth pose * inverse(shape offset in the body frame)
     ip, iq = X.tf_inv(S["pos"].astype(float), S["quat"].astype(float))
@@ -236,7 +238,7 @@ def test_gpu_settle_reproduces_committed_pose(torch_cuda):
     for v, g in enumerate(("male", "female")):
         q = st[v, z[f"arm_qidx_{v}"]]
         assert np.abs(q - np.asarray(d[g]["arm_q"])).max() < 1e-5, (g, q)
-    assert np.abs(st[0, z["arm_qidx_0"]][:6] - REF_SETTLED_ARM[:6]).max() < 0.06
+    assert np.abs(st[0, z["arm_qidx_0"]][:5] - REF_SETTLED_ARM[:5]).max() < 0.05      # shoulder (3), elbow, forearm roll
     sim.close()
 
 
@@ -304,7 +306,8 @@ def test_gpu_wiping_matches_oracle_bit_exactly(torch_cuda, bb_data):
         o = oracles[int(variant[e])]
         rec = env_to_f64(env0[e]).copy()
         t = int(rng.randint(int(o.model["header"]["n_target"])))
-        _place_wiper_on_target(o, rec, t, depth=float(rng.uniform(-0.004, 0.004)))
+        _place_wiper_on_target(o, rec, t, depth=float(rng.uniform(-0.004, 0.004)),
+                               tilt=tuple(rng.choice([-1, 1], 2) * rng.uniform(0.03, 0.1, 2)))
         recs.append(rec)
     start = np.stack([env_to_f32(r) for r in recs])
     sim = capi.Sim(n, 0)
