@@ -123,7 +123,7 @@ def run_reference(args, rank: int, world: int):
         return
     # bounded sample: ~steps*envs sized so that each measured step lasts a few seconds in total
     cores = os.cpu_count() or 1
-    per_core, steps = 16, 200                      # one bench "step" = 16 full 200-step episodes per core
+    per_core, steps = 64, 200                      # one bench "step" = 64 full 200-step episodes per core (a few seconds)
     vals = []
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_throughput(1, 20, cores)
@@ -283,6 +283,37 @@ def main():
                   "note": "synthetic-policy rollout: orthogonal-init 30-64-64-7 tanh actor on VecNormalize'd observations, inference fused on "
                           "the device (avg_policy_act), steps 3-52 after reset"}
 
+    # ---- BedBathingJaco-v0 (extra; BASELINE.json configs[2] names BedBathingPR2-v0 with a pretrained policy at 8192 envs:
+    #      the PR2 model is not compiled yet and no checkpoint ships, so this is the Jaco variant with the synthetic
+    #      policy): whole 200-step episodes from a device reset, at the named batch size and at a GPU-filling one ----------
+    bed = None
+    if not args.no_episode:
+        from assistive_vr_gym_b200.policy import synthetic_policy
+        bed = []
+        for nb in (8192, 65536):
+            benv = make("BedBathingJaco-v0", num_envs=nb, device=local_rank, seed=1001 + rank)
+            pblob, _ = synthetic_policy(benv.obs_robot_len, benv.action_robot_len, seed=0)
+            benv.set_policy(pblob)
+            benv.reset_device(seed=1001 + rank)
+            benv.rollout(3); benv.elapsed = 0
+            benv.reset_device(seed=1001 + rank)
+            barrier()
+            b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            for k in range(200):
+                bo, br, bd, bi = benv.step(benv.act()); benv.elapsed = 0
+            b1.record(stream)
+            barrier()
+            tb = torch.tensor([b0.elapsed_time(b1)], device=dev)
+            bstat = torch.stack([bi["task_success"].float().sum(), benv.reward.sum()])
+            if distributed:
+                dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+                dist.all_reduce(bstat, op=dist.ReduceOp.SUM)
+            bed.append({"env_id": "BedBathingJaco-v0", "envs_per_gpu": nb, "value": nb * world * 200 / (float(tb.item()) * 1e-3), "unit": UNIT,
+                        "steps": 200, "task_success_rate": float(bstat[0]) / (nb * world), "mean_reward_last_step": float(bstat[1]) / (nb * world),
+                        "note": "synthetic-policy rollout (24-64-64-7 tanh actor, fused inference), full episode from a device reset"})
+            benv.close()
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpe = env.sim.bytes_per_env_step
@@ -319,8 +350,10 @@ def main():
             line["episode"] = episode
         if policy is not None:
             line["policy_rollout"] = policy
+        if bed is not None:
+            line["other_workloads"] = bed
         if not args.no_cpu_baseline and world == 1:
-            v, c, sample = cpu_oracle_throughput(16, 200)
+            v, c, sample = cpu_oracle_throughput(192, 200)         # ~10-20 s of CPU work on the box's cores
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if distributed:
