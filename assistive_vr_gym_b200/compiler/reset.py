@@ -396,7 +396,7 @@ def build_reset_data_bed_bathing(scene: CompiledScene, q_start: np.ndarray) -> d
     ee_p, ee_q = robot.com_frames(qrob)[8]
     base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
     bp, bq = X.tf_mul(base_p, base_q, ip, iq)
-    arm_qidx, arm_dof, fin_qidx, fin_dof = [], [], [], []
+    arm_qidx, arm_dof, fin_qidx, fin_dof, hum_qidx, hum_dof, hum_joint = [], [], [], [], [], [], []
     tool_qidx = -1
     for b in scene.bodies:
         if b.art == 0 and b.jtype != 2:
@@ -404,13 +404,19 @@ def build_reset_data_bed_bathing(scene: CompiledScene, q_start: np.ndarray) -> d
                 arm_qidx.append(b.qidx); arm_dof.append(b.dof)
             else:
                 fin_qidx.append(b.qidx); fin_dof.append(b.dof)
+        elif b.art == 1:                                   # human-active ids: the right arm stays dynamic, starts at the settled pose
+            hum_qidx.append(b.qidx); hum_dof.append(b.dof); hum_joint.append(b.ref_joint)
         elif b.art == 2:
             tool_qidx = b.qidx
-    zi = np.zeros(0, dtype=np.int64); zf = np.zeros(0)
+    human = scene.multibodies[1]
+    ii = lambda a: np.asarray(a, dtype=np.int64)
     return dict(pool_q=np.asarray([q_start]), pool_tool=np.asarray([np.concatenate([bp, bq])]), arm_qidx=np.asarray(arm_qidx),
                 arm_dof=np.asarray(arm_dof), fin_qidx=np.asarray(fin_qidx), fin_dof=np.asarray(fin_dof),
-                hum_qidx=zi, hum_dof=zi, hum_joint=zi, hum_lower=zf, hum_upper=zf, hum_reset=zf,
-                tool_qidx=np.asarray(tool_qidx), limb_dims=np.zeros((2, 2)), human_control=np.asarray(0),
+                hum_qidx=ii(hum_qidx), hum_dof=ii(hum_dof), hum_joint=ii(hum_joint),
+                hum_lower=np.array([human.links[j].lower for j in hum_joint], dtype=np.float64),
+                hum_upper=np.array([human.links[j].upper for j in hum_joint], dtype=np.float64),
+                hum_reset=np.array([scene.q_human_reset.get(j, 0.0) for j in hum_joint], dtype=np.float64),
+                tool_qidx=np.asarray(tool_qidx), limb_dims=np.zeros((2, 2)), human_control=np.asarray(int(scene.human_control)),
                 task=np.asarray(1), n_target=np.asarray(scene.info["n_target"]), fin_open=np.asarray(float(scene.finger_open)))
 
 

@@ -440,14 +440,15 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     velocity motor of 0.1 N m (world_creation.py:164-167), bed parts with friction 5; the robot parked where
     `init_jaco` puts it (world_creation.py:288).
     stage 'play': the world the episode steps in -- the whole human static at the settled pose `arm_q`
-    (human_controllable_joint_indices == [] makes every joint static, bed_bathing.py:294-295 + world_creation.py:157-161),
+    (human_controllable_joint_indices == [] makes every joint static, bed_bathing.py:294-295 + world_creation.py:157-161;
+    with `human_control` joints 4..13 stay controllable, i.e. the right arm remains dynamic, starts at `arm_q` and is driven
+    by the human half of the action exactly as in ScratchItch: position motors with human_gains 0.05, hard and realistic
+    joint limits, env.py:307-337,343-349),
     robot base at the pose chosen by `position_robot_toc` (random_pos x, y and yaw = `base_xy_yaw`, env.py:511-513,
     bed_bathing.py:325), nightstand under it (bed_bathing.py:330-338), gravity off for robot / human / tool (:341-344).
     """
     if robot_type != "jaco":
         raise NotImplementedError("round 1 compiles the Jaco recipe only")
-    if human_control:
-        raise NotImplementedError("BedBathingJacoHuman-v0 (dynamic arm during play) is next")
     cfg = CONFIG["bed_bathing"]
     deg = np.deg2rad
     play = stage == "play"
@@ -498,7 +499,8 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     for l in human.links:
         if l.jtype == "revolute":
             q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))       # world_creation.py:169
-    frozen_h = {l.ref_index for l in human.links if play or l.ref_index not in range(4, 14)}             # :285 non_static_joints / :294
+    controllable = list(range(4, 14))                                                                     # bed_bathing.py:294
+    frozen_h = {l.ref_index for l in human.links if (play and not human_control) or l.ref_index not in controllable}   # :285 / :294-295
     robot_arm = [1, 2, 3, 4, 5, 6, 7]
     fingers = [9, 11, 13]
     finger_open = 1.1                                                                                     # bed_bathing.py:327
@@ -511,6 +513,10 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
             elif b.ref_joint in fingers:
                 d.update(kp=0.05, max_force=500.0, init_target=finger_open)                               # world_creation.py:328
                 d["flags"] |= 2
+        elif b.art == 1 and play:                                 # human-active ids: take_step's position motors, env.py:337
+            slot = controllable.index(b.ref_joint)
+            d.update(kp=0.05, max_force=1.0, human_slot=slot, action=7 + slot)
+            d["flags"] |= 2 | 4 | 8
         elif b.art == 1:
             d.update(kp=0.0, kd=1.0, max_force=0.1)               # VELOCITY_CONTROL, target 0, force 0.1 (world_creation.py:164-167)
             d["flags"] |= 2
@@ -561,16 +567,20 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     task_f[16:19] = [-0.4, 0.0, 0.9]        # reference point of the device spatial algebra (float32 conditioning)
     header = dict(task=1, n_body=n_body, n_ebody=0, n_dof=n_dof, n_jdof=n_jdof, n_free=n_free,
                   substeps=5, solver_iters=50,                             # env.py:16, bed_bathing.py:340
-                  n_action_robot=7, n_action_human=0, n_obs_robot=24, n_obs_human=0, human_control=0,
+                  n_action_robot=7, n_action_human=10 if human_control else 0, n_obs_robot=24,
+                  n_obs_human=28 if human_control else 0, human_control=int(human_control),        # bed_bathing.py:19
                   dt=0.02, erp=0.2, lin_damp=0.04, ang_damp=0.04, residual_thr=1e-7, max_vel=100.0,
                   action_scale=0.05, weld_max_force=500.0,
                   weld_body_a=weld_parent[0], weld_body_b=frames[1][0], task_f=task_f)
     scene = CompiledScene(task="bed_bathing", robot_type=robot_type, gender=gender, human_control=human_control,
                           multibodies=mbs, bodies=bodies, attach=attach, shapes=shapes, n_mshape=n_mshape, pairs=pairs,
                           frames=frames, dofs=dofs, header=header, robot_arm_joints=robot_arm,
-                          human_joints=[] if play else arm, q_human_reset=q_human,
+                          human_joints=arm if (human_control or not play) else [], q_human_reset=q_human,
                           tool_offset=(tool_pos_offset, tool_orient_offset))
     scene.mlp_layers = None
+    if human_control and play:     # enforce_realistic_human_joint_limits, env.py:343-344,353-387
+        from .h5lite import load_keras_dense_stack
+        scene.mlp_layers = load_keras_dense_stack(os.path.join(assets_dir, 'realistic_arm_limits_model.h5'))
     scene.targets = (up, fo)
     scene.finger_open = finger_open
     scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape, n_target=n_target)

@@ -1748,9 +1748,9 @@ avg_epilogue_kernel(AvgStepArgs a) {
 // human_preferences, reward, observation, info
 // =================================================================================================================
 namespace {
-// bed_bathing.py:129-147 (robot half of the observation)
+// bed_bathing.py:129-153
 template <class SM>
-__device__ void fill_obs_bb(const KM& m, SM& s, float tool_force) {
+__device__ void fill_obs_bb(const KM& m, SM& s, float tool_force, float total_force_on_human, float tool_force_on_human) {
     const AvgModelHeader* h = m.h;
     const int nj = h->n_jdof;
     V3 torso, tool, sh, el, wr; Q4 tq, dq;
@@ -1768,6 +1768,18 @@ __device__ void fill_obs_bb(const KM& m, SM& s, float tool_force) {
     t = el - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
     t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
     o[k++] = tool_force;
+    if (h->human_control) {                                  // :136-139,149: positions relative to human link 3
+        V3 chest; frame_pose(m, s, AVG_F_CHEST, chest, dq);
+        t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+        const int hq0 = k;
+        for (int i = 0; i < 10; ++i) o[k++] = 0.0f;
+        for (int i = 0; i < nj; ++i) if (m.dof[i].human_slot >= 0) o[hq0 + m.dof[i].human_slot] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+        t = sh - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = el - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        t = wr - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = total_force_on_human; o[k++] = tool_force_on_human;
+    }
 }
 
 // world pose of any shape from the body poses of an epilogue's forward kinematics
@@ -1972,7 +1984,7 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
     }
     if (lane < 5) reinterpret_cast<uint32_t*>(grec)[AVG_E_TARGET_MASK + lane] = mask_w;
     if (lane == 0) {
-        fill_obs_bb(m, s, tool_force);
+        fill_obs_bb(m, s, tool_force, total_force_on_human, tool_force_on_human);
         V3 tool; Q4 tq; frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
         const int tb = m.frame[AVG_F_TOOL_TIP].body;
         const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
@@ -2018,7 +2030,7 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     const int* env_i = reinterpret_cast<const int*>(s.env);
     fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
     if (lane == 0) {
-        if (h->task == AVG_TASK_BED_BATHING) fill_obs_bb(m, s, 0.0f);                        // bed_bathing.py:350
+        if (h->task == AVG_TASK_BED_BATHING) fill_obs_bb(m, s, 0.0f, 0.0f, 0.0f);                        // bed_bathing.py:350
         else {
             V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
             const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));

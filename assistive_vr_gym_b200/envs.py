@@ -26,6 +26,7 @@ REGISTRY: Dict[str, dict] = {
     "ScratchItchJacoHuman-v0": dict(task="scratch_itch", robot="jaco", human_control=True, data="ScratchItchJacoHuman.npz"),
     # reference __init__.py:103-108; observation 24 wide (bed_bathing.py:19,147)
     "BedBathingJaco-v0": dict(task="bed_bathing", robot="jaco", human_control=False, data="BedBathingJaco.npz"),
+    "BedBathingJacoHuman-v0": dict(task="bed_bathing", robot="jaco", human_control=True, data="BedBathingJacoHuman.npz"),
 }
 _OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19
 _ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")

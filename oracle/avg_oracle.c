@@ -974,8 +974,9 @@ static double bb_closest_tool_human(const Model* m, const Kin* k) {
     }
     return best;
 }
-/* bed_bathing.py:129-153 (robot half; the human half belongs to the human-active ids) */
-static void bb_get_obs(const Model* m, const double* env, double tool_force, double* obs) {
+/* bed_bathing.py:129-153 */
+static void bb_get_obs(const Model* m, const double* env, double tool_force, double total_force_on_human,
+                       double tool_force_on_human, double* obs) {
     const AvgModelHeader* h = m->h;
     Kin k; fk(m, env, &k);
     v3 torso, tool, sh, el, wr; quat tq, dummy;
@@ -993,6 +994,18 @@ static void bb_get_obs(const Model* m, const double* env, double tool_force, dou
     t = vsub(el, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
     t = vsub(wr, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
     obs[o++] = tool_force;
+    if (h->human_control) {                                   /* :136-139,149: positions relative to human link 3 */
+        v3 chest; frame_pose(m, &k, AVG_F_CHEST, &chest, &dummy);
+        t = vsub(tool, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+        double hq[10]; memset(hq, 0, sizeof(hq));
+        for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].human_slot >= 0) hq[m->dof[i].human_slot] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+        for (int i = 0; i < 10; ++i) obs[o++] = hq[i];
+        t = vsub(sh, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        t = vsub(el, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        t = vsub(wr, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        obs[o++] = total_force_on_human; obs[o++] = tool_force_on_human;
+    }
 }
 /* The part of BedBathingEnv.step after take_step (bed_bathing.py:53-75) with get_total_force (:77-127).
  * out_info: [0] total_force_on_human, [1] task_success flag, [2] tool_force, [3] tool_force_on_human,
@@ -1038,7 +1051,7 @@ static void bb_finish_step(const Model* m, double* env, const Contact* contacts,
     int tb = m->frame[AVG_F_TOOL_TIP].body;
     const double* tv = env + AVG_E_QD + m->body[tb].dof;
     double ee_vel = vnorm(vadd(V(tv[0], tv[1], tv[2]), vcross(V(tv[3], tv[4], tv[5]), vsub(tip, k.p[tb]))));   /* :54 */
-    bb_get_obs(m, env, tool_force, obs);
+    bb_get_obs(m, env, tool_force, total_force_on_human, tool_force_on_human, obs);
     double pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-(total_force_on_human - tool_force_on_human))
                 + tf[AVG_TF_C_HF] * (tool_force_on_human < tf[AVG_TF_FORCE_CAP] ? 0.0 : -tool_force_on_human);   /* env.py:412-448 */
     double reward_distance = -bb_closest_tool_human(m, &k);                               /* :61 */
@@ -1063,7 +1076,7 @@ int avg_oracle_sizes(int* sizes) {
 /* initial observation, scratch_itch.py:268  (_get_obs([0],[0,0]) after generate_target) */
 int avg_oracle_reset_obs(const void* blob, double* env, double* obs) {
     Model m; if (model_open(blob, &m)) return -1;
-    if (m.h->task == AVG_TASK_BED_BATHING) { bb_get_obs(&m, env, 0, obs); return 0; }     /* bed_bathing.py:350 */
+    if (m.h->task == AVG_TASK_BED_BATHING) { bb_get_obs(&m, env, 0, 0, 0, obs); return 0; }     /* bed_bathing.py:350 */
     update_target(&m, env);
     get_obs(&m, env, 0, 0, 0, obs);
     return 0;

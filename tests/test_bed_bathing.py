@@ -206,6 +206,39 @@ def test_oracle_wipes_targets_once(bb_data, bb_oracles):
     assert info2[6] == 0 and rec[153] == info[6]
 
 
+def test_oracle_human_active_observation_layout():
+    """BedBathingJacoHuman-v0: obs = robot 24 + human 28 (bed_bathing.py:147-149): tool pose relative to human link 3,
+    joints 4..13 (4-6 are fixed joints, always 0), shoulder / elbow / wrist relative to link 3, the two force sums; the
+    human half of the action moves the arm (take_step, env.py:307-337)."""
+    from assistive_vr_gym_b200.envs import load_env_data
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from oracle.oracle import Oracle, env_to_f64
+    if not os.path.exists(os.path.join(DATA, "BedBathingJacoHuman.npz")):
+        pytest.skip("BedBathingJacoHuman.npz not compiled yet")
+    blobs, resets = load_env_data("BedBathingJacoHuman.npz")
+    env, variant = sample_states(resets, 2, np.random.RandomState(1))
+    for e in range(2):
+        o = Oracle(blobs[int(variant[e])])
+        assert o.n_obs == 52 and o.n_act == 17
+        rec = env_to_f64(env[e]).copy()
+        q0 = rec[:32].copy()
+        a = np.zeros(17, np.float32); a[7 + 3] = 1.0; a[7 + 6] = -1.0          # human joints 7 and 10
+        for _ in range(3):
+            obs, rew, info, cont = o.step(rec, a)
+        chest = o.frame(rec, 4)[:3]; tool = o.frame(rec, 0)
+        assert np.allclose(obs[24:27], tool[:3] - chest) and np.allclose(obs[27:31], tool[3:])
+        assert np.all(obs[31:34] == 0.0)                                        # joints 4, 5, 6
+        hq = {int(d["human_slot"]): rec[int(o.model["bodies"][int(d["body"])]["qidx"])] for d in o.model["dofs"] if d["human_slot"] >= 0}
+        assert sorted(hq) == [3, 4, 5, 6, 7, 8, 9]
+        assert np.allclose(obs[31:41], [hq.get(k, 0.0) for k in range(10)])
+        for k, f in enumerate((5, 6, 7)):
+            assert np.allclose(obs[41 + 3 * k:44 + 3 * k], o.frame(rec, f)[:3] - chest)
+        assert obs[50] == info[0] and obs[51] == info[3]
+        # the commanded joints moved the commanded way (0.05 rad per frame at most, position motor gain 0.05)
+        qi = {int(d["human_slot"]): int(o.model["bodies"][int(d["body"])]["qidx"]) for d in o.model["dofs"] if d["human_slot"] >= 0}
+        assert rec[qi[3]] > q0[qi[3]] + 1e-3 and rec[qi[6]] < q0[qi[6]] - 1e-3
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------------------------------------
@@ -242,23 +275,27 @@ def test_gpu_settle_reproduces_committed_pose(torch_cuda):
     sim.close()
 
 
-def _bb_env(n, seed=3):
+def _bb_env(n, seed=3, env_id="BedBathingJaco-v0"):
     from assistive_vr_gym_b200 import make
-    env = make("BedBathingJaco-v0", num_envs=n, device=0, seed=seed)
+    env = make(env_id, num_envs=n, device=0, seed=seed)
     env.sim.enable_debug(True)
     return env
 
 
 @pytest.mark.gpu
-def test_gpu_reset_observation_and_trajectories_match_oracle(torch_cuda, bb_oracles):
+@pytest.mark.parametrize("env_id,n_act,n_obs", [("BedBathingJaco-v0", 7, 24), ("BedBathingJacoHuman-v0", 17, 52)])
+def test_gpu_reset_observation_and_trajectories_match_oracle(torch_cuda, env_id, n_act, n_obs):
     """Reset observation (1e-5) and 10 env-steps of random actions: contact-free environments agree within
-    |dq| <= 1e-4, |dqd| <= 1e-3, |dreward| <= 1e-3 (the reward includes the closest tool-human distance), obs 1e-3."""
+    |dq| <= 1e-4, |dqd| <= 1e-3, |dreward| <= 1e-3 (the reward includes the closest tool-human distance), obs 1e-3.
+    The human-active id (17 actions, 24 + 28 observations, bed_bathing.py:19) keeps the right arm dynamic."""
     torch = torch_cuda
-    from oracle.oracle import env_to_f64
+    from assistive_vr_gym_b200.envs import load_env_data
+    from oracle.oracle import Oracle, env_to_f64
+    bb_oracles = [Oracle(b) for b in load_env_data(env_id[:-3] + ".npz")[0]]
     n, T = 64, 10
-    env = _bb_env(n, seed=5)
+    env = _bb_env(n, seed=5, env_id=env_id)
     obs = env.reset().cpu().numpy()
-    assert obs.shape == (n, 24)
+    assert obs.shape == (n, n_obs)
     st0 = env.get_state()
     assert len(set(env.variants.tolist())) > 4                        # genders x robot base poses
     recs = [env_to_f64(st0[e]).copy() for e in range(n)]
@@ -267,8 +304,9 @@ def test_gpu_reset_observation_and_trajectories_match_oracle(torch_cuda, bb_orac
     clean = np.ones(n, dtype=bool)
     rng = np.random.RandomState(0)
     worst = np.zeros(4)
+    dq_all = np.zeros(n); same = []
     for t in range(T):
-        a = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        a = rng.uniform(-1, 1, (n, n_act)).astype(np.float32)
         obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
         st = env.get_state(); cont, ncont = env.sim.get_contacts(); terms = env.sim.get_reward_terms()
         rew = rew.cpu().numpy(); obs = obs.cpu().numpy()
@@ -276,12 +314,20 @@ def test_gpu_reset_observation_and_trajectories_match_oracle(torch_cuda, bb_orac
             oobs, orew, oinfo, oc = bb_oracles[int(env.variants[e])].step(recs[e], a[e])
             if len(oc) or ncont[e]:
                 clean[e] = False
+            same.append([(int(c[0]), int(c[1])) for c in oc] == [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :ncont[e]]])
+            dq_all[e] = np.abs(recs[e][:32] - st[e, :32]).max()
             if clean[e]:
                 worst = np.maximum(worst, [np.abs(recs[e][:32] - st[e, :32]).max(), np.abs(recs[e][32:64] - st[e, 32:64]).max(),
                                            abs(orew - rew[e]), abs(oinfo[4] - terms[e, 4])])
                 assert np.abs(oobs - obs[e]).max() < 1e-3
-    assert clean.sum() >= n // 3, "too few contact-free environments to be meaningful"
-    assert worst[0] <= 1e-4 and worst[1] <= 1e-3 and worst[2] <= 1e-3 and worst[3] <= 1e-4, worst
+    if n_act == 7:
+        assert clean.sum() >= n // 3, "too few contact-free environments to be meaningful"
+        assert worst[0] <= 1e-4 and worst[1] <= 1e-3 and worst[2] <= 1e-3 and worst[3] <= 1e-4, worst
+    else:
+        # the dynamic arm rests on the mattress from the first sub-step on (contact in every environment), so this id is
+        # characterised over ALL environments after 10 env-steps: measured median 2e-6, 90th percentile 4e-4, max 7e-3 rad
+        assert np.median(dq_all) <= 2e-5 and np.percentile(dq_all, 90) <= 2e-3 and dq_all.max() <= 5e-2, (np.median(dq_all), dq_all.max())
+        assert np.mean(same) >= 0.95
     assert int(st.view(np.int32)[:, 166].max()) == 0
     env.close()
 

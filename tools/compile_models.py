@@ -39,7 +39,7 @@ def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
     if settled["male"] is None or settled["female"] is None:
         print("no data/bed_bathing_settle.json yet: run tools/settle_bed_bathing.py on a GPU box, then re-run this tool")
         return
-    payload = {}
+    payloads = {False: {}, True: {}}
     rng = np.random.RandomState(1001)
     robot = urdf_to_multibody(os.path.join(assets, "jaco", "j2s7s300_gym.urdf"), 0, "jaco")
     v = 0
@@ -51,18 +51,20 @@ def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
             xy, yaw, q_start, reached = toc_search_jaco(robot, [1, 2, 3, 4, 5, 6, 7], np.array([-0.5, -0.1, 1.0]),
                                                         X.quat_from_euler([0, np.pi / 2.0, 0]), goals, rng, [0.1, 0.55, 0.6],
                                                         attempts=attempts)
-            scene = build_bed_bathing(assets, "jaco", gender, stage="play", arm_q=settled[gender],
-                                      base_xy_yaw=(float(xy[0]), float(xy[1]), float(yaw)))
-            blob = scene_to_blob(scene)
-            payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
-            rd = build_reset_data_bed_bathing(scene, q_start)
-            for key, a in rd.items():
-                payload[f"reset_{v}_{key}"] = a
-            print("play", gender, k, "base", np.round(xy, 3), "yaw", round(float(yaw), 3), "goals reached", reached,
-                  scene.info["n_pairs"], "pairs", len(blob), "bytes")
+            for human_control in (False, True):                               # BedBathingJaco-v0 / BedBathingJacoHuman-v0 share the base poses
+                scene = build_bed_bathing(assets, "jaco", gender, human_control=human_control, stage="play", arm_q=settled[gender],
+                                          base_xy_yaw=(float(xy[0]), float(xy[1]), float(yaw)))
+                blob = scene_to_blob(scene)
+                payloads[human_control][f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+                rd = build_reset_data_bed_bathing(scene, q_start)
+                for key, a in rd.items():
+                    payloads[human_control][f"reset_{v}_{key}"] = a
+                print("play", gender, k, "human_control" if human_control else "", "base", np.round(xy, 3), "yaw", round(float(yaw), 3),
+                      "goals reached", reached, scene.info["n_pairs"], "pairs", len(blob), "bytes")
             v += 1
-    np.savez_compressed(os.path.join(out_dir, "BedBathingJaco.npz"), **payload)
-    print("wrote BedBathingJaco.npz")
+    np.savez_compressed(os.path.join(out_dir, "BedBathingJaco.npz"), **payloads[False])
+    np.savez_compressed(os.path.join(out_dir, "BedBathingJacoHuman.npz"), **payloads[True])
+    print("wrote BedBathingJaco.npz, BedBathingJacoHuman.npz")
 
 
 if __name__ == "__main__":

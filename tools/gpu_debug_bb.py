@@ -1,37 +1,30 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 np.set_printoptions(linewidth=220, precision=6, suppress=True)
-from assistive_vr_gym_b200 import capi
+from assistive_vr_gym_b200 import make
 from assistive_vr_gym_b200.envs import load_env_data
-from assistive_vr_gym_b200.compiler.reset import sample_states
 from oracle.oracle import Oracle, env_to_f64
-from helpers import patch_blob
-blobs, resets = load_env_data("BedBathingJaco.npz")
+env_id = "BedBathingJacoHuman-v0"
+oracles = [Oracle(b) for b in load_env_data(env_id[:-3] + ".npz")[0]]
 n = 64
-env0, variant = sample_states(resets, n, np.random.RandomState(5))
-a = np.random.RandomState(0).uniform(-1, 1, (n, 7)).astype(np.float32)
-hdr = {"substeps": 1, "residual_thr": 0.0}
-cases = {"base": dict(header=hdr), "no friction": dict(header=hdr, friction=0.0), "no limits": dict(header=hdr, dof_flags_clear=1),
-         "weak weld": dict(header=dict(hdr, weld_max_force=0.0)), "zero action": dict(header=hdr), "iters 1": dict(header=dict(hdr, solver_iters=1)),
-         "iters 2": dict(header=dict(hdr, solver_iters=2)), "iters 5": dict(header=dict(hdr, solver_iters=5))}
-for name, kw in cases.items():
-    pb = [patch_blob(b, **kw) for b in blobs]
-    oracles = [Oracle(b) for b in pb]
-    sim = capi.Sim(n, 0)
-    for v, b in enumerate(pb): sim.upload_model(v, b)
-    sim.enable_debug(True)
-    sim.set_state(env0, variant)
-    obs = torch.zeros((n, 24), device="cuda"); rew = torch.zeros(n, device="cuda"); info = torch.zeros((n, 2), device="cuda")
-    aa = a * 0 if name == "zero action" else a
-    act = torch.as_tensor(aa, device="cuda")
-    sim.step(act.data_ptr(), obs.data_ptr(), rew.data_ptr(), 0, info.data_ptr(), 0)
-    torch.cuda.synchronize()
-    st = sim.get_state(); cont, nc = sim.get_contacts()
-    e = 29
-    rec = env_to_f64(env0[e]).copy()
-    oobs, orew, oinfo, oc = oracles[int(variant[e])].step(rec, aa[e])
-    print(name, "force oracle", [round(c[12], 3) for c in oc], "gpu", [round(float(c["force"]), 3) for c in cont[e, :nc[e]]], "dqd %.3e" % np.abs(rec[32:64] - st[e, 32:64]).max())
-    print("    qd oracle", rec[32:48]); print("    qd gpu   ", st[e, 32:48])
-    sim.close()
+env = make(env_id, num_envs=n, device=0, seed=5); env.sim.enable_debug(True)
+env.reset(); st0 = env.get_state()
+recs = [env_to_f64(st0[e]).copy() for e in range(n)]
+rng = np.random.RandomState(0)
+sh = oracles[0].model["shapes"]
+for t in range(10):
+    a = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
+    obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
+    st = env.get_state(); cont, nc = env.sim.get_contacts(); rew = rew.cpu().numpy()
+    dq = np.zeros(n); dqd = np.zeros(n); dr = np.zeros(n); same = np.zeros(n, bool); kinds = []
+    for e in range(n):
+        o = oracles[int(env.variants[e])]
+        oobs, orew, oinfo, oc = o.step(recs[e], a[e])
+        dq[e] = np.abs(recs[e][:32] - st[e, :32]).max(); dqd[e] = np.abs(recs[e][32:64] - st[e, 32:64]).max(); dr[e] = abs(orew - rew[e])
+        op = [(int(c[0]), int(c[1])) for c in oc]; gp = [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :nc[e]]]
+        same[e] = op == gp
+        if e == 0 and t < 2:
+            print("  env0 contacts", [(x, int(o.model["shapes"][x[0]]["ref_body"]), int(o.model["shapes"][x[1]]["ref_body"]), round(c[11], 5), round(c[12], 4)) for x, c in zip(op, oc)])
+    print("step", t, "dq med %.2e p90 %.2e max %.2e | dqd med %.2e max %.2e | drew max %.2e | sets equal %.2f | ncont mean %.1f" % (
+        np.median(dq), np.percentile(dq, 90), dq.max(), np.median(dqd), dqd.max(), dr.max(), same.mean(), nc.mean()))
