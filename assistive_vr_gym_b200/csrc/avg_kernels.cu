@@ -39,7 +39,10 @@
 #define AVG_OCC_COLLIDE 5
 #endif
 #ifndef AVG_OCC_DYN
-#define AVG_OCC_DYN 5
+#define AVG_OCC_DYN 6
+#endif
+#ifndef AVG_OCC_SOLVE
+#define AVG_OCC_SOLVE 32
 #endif
 
 namespace {
@@ -1420,7 +1423,7 @@ __device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, 
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
 template <int MAXBLK>
-__global__ void __launch_bounds__(32, 32)
+__global__ void __launch_bounds__(32, AVG_OCC_SOLVE)
 avg_solve_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmSolve)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;

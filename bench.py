@@ -314,6 +314,42 @@ def main():
                         "note": "synthetic-policy rollout (24-64-64-7 tanh actor, fused inference), full episode from a device reset"})
             benv.close()
 
+    # ---- BASELINE.json configs[4] (ScratchItchJacoHuman-v0, 4096 envs per GPU, both halves of the action driven) and
+    #      configs[0] (one ScratchItchJaco-v0 environment through the reference-typed NumPy API, 200 steps) as extras --------
+    if not args.no_episode:
+        henv = make("ScratchItchJacoHuman-v0", num_envs=4096, device=local_rank, seed=1001 + rank)
+        henv.reset_device(seed=1001 + rank)
+        ha = torch.empty((4096, 17), device=dev)
+        for k in range(3):
+            ha.uniform_(-1, 1, generator=gen); henv.step(ha); henv.elapsed = 0
+        henv.reset_device(seed=1001 + rank)
+        barrier()
+        h0 = torch.cuda.Event(enable_timing=True); h1 = torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for k in range(200):
+            ha.uniform_(-1, 1, generator=gen); henv.step(ha); henv.elapsed = 0
+        h1.record(stream)
+        barrier()
+        th = torch.tensor([h0.elapsed_time(h1)], device=dev)
+        if distributed:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        bed.append({"env_id": "ScratchItchJacoHuman-v0", "envs_per_gpu": 4096, "value": 4096 * world * 200 / (float(th.item()) * 1e-3), "unit": UNIT,
+                    "steps": 200, "note": "random robot + human actions (17), arm-limit MLP after every sub-step, full episode from a device reset"})
+        henv.close()
+        if rank == 0:
+            senv = make("ScratchItchJaco-v0", device=local_rank, seed=1001)       # num_envs=None: float64 obs, python scalars, like gym.make
+            senv.reset()
+            sact = np.random.RandomState(0).uniform(-1, 1, (200, 7)).astype(np.float32)
+            for k in range(5):
+                senv.step(sact[k])
+            senv.reset()
+            t0 = time.perf_counter()
+            for k in range(200):
+                senv.step(sact[k])
+            bed.append({"env_id": "ScratchItchJaco-v0", "envs_per_gpu": 1, "value": 200 / (time.perf_counter() - t0), "unit": UNIT, "steps": 200,
+                        "note": "ONE environment through the reference-typed NumPy API (examples/random_actions.py loop): launch-latency bound"})
+            senv.close()
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpe = env.sim.bytes_per_env_step
