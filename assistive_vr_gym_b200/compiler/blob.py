@@ -20,7 +20,7 @@ BODY_DT = np.dtype([
 DOF_DT = np.dtype([
     ("body", "<i4"), ("flags", "<u4"), ("lower", "<f4"), ("upper", "<f4"), ("rep_lower", "<f4"), ("rep_upper", "<f4"),
     ("kp", "<f4"), ("kd", "<f4"), ("max_force", "<f4"), ("action", "<i4"), ("human_slot", "<i4"), ("init_target", "<f4"),
-    ("pad", "<i4", 4),
+    ("damping", "<f4"), ("pad", "<i4", 3),
 ])
 SHAPE_DT = np.dtype([
     ("type", "<i4"), ("body", "<i4"), ("ref_body", "<i4"), ("ref_link", "<i4"),
@@ -105,6 +105,7 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
         for k in ("body", "flags", "lower", "upper", "rep_lower", "rep_upper", "kp", "kd", "max_force", "action",
                   "human_slot", "init_target"):
             dofs[i][k] = d[k]
+        dofs[i]["damping"] = d.get("damping", 0.0)
     verts = []
     planes = []
     shapes = np.zeros(len(scene.shapes), dtype=SHAPE_DT)

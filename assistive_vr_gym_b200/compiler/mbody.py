@@ -75,6 +75,7 @@ class LinkDesc:
     limit_enforced: bool = False    # Bullet adds a joint-limit constraint (revolute/prismatic with lower <= upper)
     inertia_diag: Optional[np.ndarray] = None   # None -> from collision AABB (Bullet default)
     name: str = ""
+    damping: float = 0.0            # URDF <dynamics damping>: btMultibodyLink::m_jointDamping
 
 
 @dataclass
@@ -177,6 +178,7 @@ class DynBody:
     root_link: int = -1             # PyBullet link index of the composite's root link
     init_pos: Optional[np.ndarray] = None   # free bodies: world pose of the body frame at reset
     init_quat: Optional[np.ndarray] = None
+    damping: float = 0.0            # joint damping torque -damping * qd (URDF <dynamics damping>)
 
 
 @dataclass
@@ -305,7 +307,7 @@ def reduce_bodies(mb: MultiBodyDesc, art: int, q_reset: Dict[int, float], frozen
                               ta_pos=ta_p, ta_quat=ta_q, axis=l.axis / np.linalg.norm(l.axis),
                               tb_pos=bf_p, tb_quat=bf_q, mass=body_mass[r], inertia=body_inertia[r],
                               gravity=mb.gravity.copy(), ref_joint=r, lower=l.lower, upper=l.upper,
-                              limit_enforced=l.limit_enforced, root_link=r))
+                              limit_enforced=l.limit_enforced, root_link=r, damping=l.damping))
 
     # 5. attachment of every PyBullet LINK frame
     attach: Dict[int, Attached] = {}

@@ -41,10 +41,21 @@ def _chain_to(mb: MultiBodyDesc, link: int) -> List[int]:
 
 
 def ee_pose_and_jacobian(mb: MultiBodyDesc, q: Dict[int, float], ee_link: int, joints: List[int]):
-    frames = mb.link_frames(q)
+    # link frames along the chain base -> ee_link only (MultiBodyDesc.link_frames walks every link: 87 on the PR2)
+    frames = {}
+    pp, pq = np.asarray(mb.base_pos, float), np.asarray(mb.base_quat, float)
+    for i in _chain_to(mb, ee_link):
+        lk = mb.links[i]
+        pp, pq = X.tf_mul(pp, pq, lk.pos, lk.quat)
+        v = q.get(i, 0.0)
+        if lk.jtype == "revolute":
+            pq = X.quat_normalize(X.quat_mul(pq, X.quat_from_axis_angle(lk.axis, v)))
+        elif lk.jtype == "prismatic":
+            pp = pp + X.quat_rotate(pq, lk.axis * v)
+        frames[i] = (pp, pq)
     l = mb.links[ee_link]
     p_ee, q_ee = X.tf_mul(*frames[ee_link], l.inertial_pos, l.inertial_quat)
-    chain = set(_chain_to(mb, ee_link))
+    chain = set(frames)
     J = np.zeros((6, len(joints)))
     for k, j in enumerate(joints):
         if j not in chain:
@@ -341,7 +352,7 @@ def joint_limited_weighting(q, lower, upper) -> np.ndarray:
     return np.diag(w)
 
 
-def toc_search_jaco(robot: MultiBodyDesc, joints: List[int], start_pos, start_quat, goal_points, rng: np.random.RandomState,
+def toc_search(robot: MultiBodyDesc, joints: List[int], start_pos, start_quat, goal_points, rng: np.random.RandomState,
                     pos_offset, attempts: int = 100, random_rotation: float = 30.0, random_position: float = 0.1,
                     max_ik_iterations: int = 200, ee_link: int = 8):
     """`position_robot_toc` for a single-arm robot (env.py:486-585 as called at bed_bathing.py:325): `attempts` random
@@ -352,6 +363,7 @@ def toc_search_jaco(robot: MultiBodyDesc, joints: List[int], start_pos, start_qu
     -> (random_pos xy, yaw, start joint angles)"""
     lower = np.array([robot.links[j].lower for j in joints]); upper = np.array([robot.links[j].upper for j in joints])
     ik_lo = np.where(lower > upper, -2 * np.pi, lower); ik_hi = np.where(lower > upper, 2 * np.pi, upper)     # util.py:86-88
+    lower, upper = np.where(lower > upper, -1e10, lower), np.where(lower > upper, 1e10, upper)                # world_creation.py:122-124
     best = None
     it = 0
     while it < attempts or best is None:
@@ -382,20 +394,30 @@ def toc_search_jaco(robot: MultiBodyDesc, joints: List[int], start_pos, start_qu
     return best[2], best[3], best[4], best[0]
 
 
+toc_search_jaco = toc_search      # first user: BedBathingJaco-v0 (bed_bathing.py:325)
+
+
 def build_reset_data_bed_bathing(scene: CompiledScene, q_start: np.ndarray) -> dict:
-    """Reset table input of one BedBathing play variant (= one robot base pose): arm at the IK start pose
-    (env.py:571-572), fingers at 1.1 (bed_bathing.py:327), wiper in the gripper (world_creation.py:331-337), every
-    wiping target alive (bed_bathing.py:369-379)."""
+    """Reset table input of one play variant of a TOC-placed robot (= one robot base pose; BedBathing on both robots,
+    ScratchItch on the PR2): arm at the IK start pose(s) (env.py:571-572; `q_start` = one pose or a pool [k, 7]),
+    fingers at the task's open position (bed_bathing.py:320,327, scratch_itch.py:247), tool in the gripper
+    (world_creation.py:331-337); BedBathing: every wiping target alive (bed_bathing.py:369-379)."""
     robot = scene.multibodies[0]
     joints = scene.robot_arm_joints
+    spec = getattr(scene, "robot_spec", None) or dict(fingers=[9, 11, 13], ee_link=8, q_preset={})
     at = scene.attach[2][-1]
     ip, iq = X.tf_inv(at.pos, at.quat)
-    qrob = {j: float(q_start[k]) for k, j in enumerate(joints)}
-    for j in (9, 11, 13):
-        qrob[j] = float(scene.finger_open)
-    ee_p, ee_q = robot.com_frames(qrob)[8]
-    base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
-    bp, bq = X.tf_mul(base_p, base_q, ip, iq)
+    pool_q = np.atleast_2d(np.asarray(q_start, dtype=np.float64))
+    pool_tool = []
+    for qs in pool_q:
+        qrob = dict(spec["q_preset"])
+        qrob.update({j: float(qs[k]) for k, j in enumerate(joints)})
+        for j in spec["fingers"]:
+            qrob[j] = float(scene.finger_open)
+        ee_p, ee_q = robot.com_frames(qrob)[spec["ee_link"]]
+        base_p, base_q = X.tf_mul(ee_p, ee_q, *scene.tool_offset)
+        bp, bq = X.tf_mul(base_p, base_q, ip, iq)
+        pool_tool.append(np.concatenate([bp, bq]))
     arm_qidx, arm_dof, fin_qidx, fin_dof, hum_qidx, hum_dof, hum_joint = [], [], [], [], [], [], []
     tool_qidx = -1
     for b in scene.bodies:
@@ -410,7 +432,19 @@ def build_reset_data_bed_bathing(scene: CompiledScene, q_start: np.ndarray) -> d
             tool_qidx = b.qidx
     human = scene.multibodies[1]
     ii = lambda a: np.asarray(a, dtype=np.int64)
-    return dict(pool_q=np.asarray([q_start]), pool_tool=np.asarray([np.concatenate([bp, bq])]), arm_qidx=np.asarray(arm_qidx),
+    task = int(scene.header["task"])
+    if task == 0:                                          # ScratchItch: limb capsules for the target draw (scratch_itch.py:277-280)
+        limb = human.dims["limb_dims"]
+        return dict(pool_q=pool_q, pool_tool=np.asarray(pool_tool), arm_qidx=np.asarray(arm_qidx),
+                    arm_dof=np.asarray(arm_dof), fin_qidx=np.asarray(fin_qidx), fin_dof=np.asarray(fin_dof),
+                    hum_qidx=ii(hum_qidx), hum_dof=ii(hum_dof), hum_joint=ii(hum_joint),
+                    hum_lower=np.array([human.links[j].lower for j in hum_joint], dtype=np.float64),
+                    hum_upper=np.array([human.links[j].upper for j in hum_joint], dtype=np.float64),
+                    hum_reset=np.array([scene.q_human_reset.get(j, 0.0) for j in hum_joint], dtype=np.float64),
+                    tool_qidx=np.asarray(tool_qidx), limb_dims=np.array([limb[9], limb[11]]),
+                    human_control=np.asarray(int(scene.human_control)), task=np.asarray(0), n_target=np.asarray(0),
+                    fin_open=np.asarray(float(scene.finger_open)))
+    return dict(pool_q=pool_q, pool_tool=np.asarray(pool_tool), arm_qidx=np.asarray(arm_qidx),
                 arm_dof=np.asarray(arm_dof), fin_qidx=np.asarray(fin_qidx), fin_dof=np.asarray(fin_dof),
                 hum_qidx=ii(hum_qidx), hum_dof=ii(hum_dof), hum_joint=ii(hum_joint),
                 hum_lower=np.array([human.links[j].lower for j in hum_joint], dtype=np.float64),

@@ -37,9 +37,24 @@ _hull_cache: Dict[Tuple[str, Tuple[float, float, float]], list] = {}
 hull_errors: Dict[str, float] = {}
 
 
-def urdf_to_multibody(path: str, ref_body: int, name: str) -> MultiBodyDesc:
-    """`p.loadURDF` without `URDF_USE_INERTIA_FROM_FILE`: masses and inertial frames from the file, inertia from the
-    collision AABB (mbody.link_aabb_inertia), one hull per mesh piece."""
+def _file_inertia(link):
+    """`URDF_USE_INERTIA_FROM_FILE` (world_creation.py:187): the <inertia> tensor of the file; a tensor with products of
+    inertia is diagonalised and the inertial frame turned onto its principal axes, as Bullet's URDF importer does
+    [UPSTREAM-BULLET].  -> (inertial_quat, principal moments)"""
+    T = np.asarray(link.inertia_file, float)
+    off = np.abs(T - np.diag(np.diag(T))).max()
+    if off <= 1e-12 * max(np.abs(T).max(), 1e-30):
+        return link.inertial_quat, np.diag(T).copy()
+    w, V = np.linalg.eigh(T)
+    if np.linalg.det(V) < 0:
+        V[:, 2] = -V[:, 2]
+    return X.quat_normalize(X.quat_mul(link.inertial_quat, X.mat_to_quat(V))), w
+
+
+def urdf_to_multibody(path: str, ref_body: int, name: str, inertia_from_file: bool = False) -> MultiBodyDesc:
+    """`p.loadURDF`: masses and inertial frames from the file, one hull per mesh piece; inertia from the collision AABB
+    (mbody.link_aabb_inertia) unless `inertia_from_file` (the reference loads the PR2 with URDF_USE_INERTIA_FROM_FILE,
+    world_creation.py:187); joint damping from <dynamics damping> (btMultibodyLink::m_jointDamping)."""
     u = parse_urdf(path)
 
     def shapes_of(link, ref_index) -> List[ShapeDesc]:
@@ -71,19 +86,69 @@ def urdf_to_multibody(path: str, ref_body: int, name: str) -> MultiBodyDesc:
                     out.append(ShapeDesc(SHAPE_HULL, c.pos, c.quat, verts=v, planes=pl, friction=link.lateral_friction, ref_link=ref_index))
         return out
 
+    def inertial(l):
+        if inertia_from_file and l.mass > 0:
+            q, d = _file_inertia(l)
+            return q, d
+        return l.inertial_quat, None
+
     bl = u.links[u.base]
+    bq, bd = inertial(bl)
     base = LinkDesc(ref_index=-1, parent=-1, jtype="base", pos=np.zeros(3), quat=I4.copy(), axis=np.zeros(3),
-                    mass=bl.mass, inertial_pos=bl.inertial_pos, inertial_quat=bl.inertial_quat,
+                    mass=bl.mass, inertial_pos=bl.inertial_pos, inertial_quat=bq, inertia_diag=bd,
                     shapes=shapes_of(bl, -1), name=bl.name)
     links = []
     for i, j in enumerate(u.order):
         l = u.links[j.child]
         jt = {"fixed": "fixed", "revolute": "revolute", "continuous": "revolute", "prismatic": "prismatic"}[j.jtype]
         enforced = j.jtype in ("revolute", "prismatic") and j.lower <= j.upper
+        lq, ld = inertial(l)
         links.append(LinkDesc(ref_index=i, parent=u.parent_index(i), jtype=jt, pos=j.pos, quat=j.quat, axis=j.axis,
-                              mass=l.mass, inertial_pos=l.inertial_pos, inertial_quat=l.inertial_quat,
-                              shapes=shapes_of(l, i), lower=j.lower, upper=j.upper, limit_enforced=enforced, name=l.name))
+                              mass=l.mass, inertial_pos=l.inertial_pos, inertial_quat=lq, inertia_diag=ld,
+                              shapes=shapes_of(l, i), lower=j.lower, upper=j.upper, limit_enforced=enforced, name=l.name,
+                              damping=j.damping))
     return MultiBodyDesc(name=name, ref_body=ref_body, base=base, links=links)
+
+
+def load_robot(assets_dir: str, robot_type: str):
+    """The robot as `WorldCreation.init_<robot>` loads it (world_creation.py:181-217, 274-293) plus the indices the task
+    files hard-code for it.  -> (MultiBodyDesc, spec) with spec = arm joints driven by the action (the LEFT arm on the
+    PR2: robot_arm='left' at scratch_itch.py:45 / bed_bathing.py:44), gripper joints of `set_gripper_open_position`
+    (world_creation.py:309-328), tool link (`init_tool`, :332), robot links whose collisions with the tool are switched
+    off (:352-354), torso link of the observation (scratch_itch.py:105), joints kept out of the dynamics, presets."""
+    if robot_type == "jaco":
+        robot = urdf_to_multibody(os.path.join(assets_dir, "jaco", "j2s7s300_gym.urdf"), REF_ROBOT, "jaco")
+        robot.self_collision = True                                        # URDF_USE_SELF_COLLISION, world_creation.py:282
+        return robot, dict(arm=[1, 2, 3, 4, 5, 6, 7], fingers=[9, 11, 13], ee_link=8, tool_filtered=set(range(7, 15)),
+                           torso_link=0, frozen=set(), q_preset={})
+    if robot_type == "pr2":
+        robot = urdf_to_multibody(os.path.join(assets_dir, "PR2", "pr2_no_torso_lift_tall.urdf"), REF_ROBOT, "pr2",
+                                  inertia_from_file=True)                  # URDF_USE_INERTIA_FROM_FILE, world_creation.py:187
+        robot.self_collision = False                                       # loaded without URDF_USE_SELF_COLLISION
+        left = [64, 65, 66, 68, 69, 71, 72]; right = [42, 43, 44, 46, 47, 49, 50]       # world_creation.py:188-189
+        fingers = [79, 80, 81, 82]                                         # world_creation.py:311 (left gripper)
+        # Joints integrated on the device: the left arm and its four finger joints.  Everything else is baked into the
+        # static world at its reset pose: the base is fixed and the torso lift is a fixed joint, so the other branches
+        # (casters, head, right arm, lasers) are dynamically decoupled from the left arm, carry no gravity
+        # (scratch_itch.py:259, bed_bathing.py:342) and are held at zero velocity by PyBullet's default joint motors --
+        # they only move if something pushes them.  Also frozen: l_gripper_motor_slider / _screw (77, 78) and
+        # l_gripper_joint (83): 10 g / 10 g / 1 g links without collision geometry (documented deviation, DESIGN.md).
+        moving = set(left) | set(fingers)
+        frozen = {l.ref_index for l in robot.links if l.jtype in ("revolute", "prismatic") and l.ref_index not in moving}
+        q_preset = dict(zip(right, [-1.75, 1.25, -1.5, -0.5, -1.0, 0.0, -1.0]))          # env.py:455-459 reset_robot_joints
+        return robot, dict(arm=left, fingers=fingers, ee_link=76, tool_filtered=set(range(71, 86)), torso_link=15,
+                           frozen=frozen, q_preset=q_preset)
+    raise NotImplementedError(f"robot {robot_type!r}: the reference registers PR2 and Jaco ids only (SURVEY.md F4)")
+
+
+TOOL_SETUP = {   # (task, robot) -> gripper open position, tool pos_offset, tool orient_offset (euler)
+    ("scratch_itch", "jaco"): (1.0, [0.0, 0.0, 0.02], [0, -np.pi / 2.0, 0]),        # scratch_itch.py:254-255
+    ("scratch_itch", "pr2"): (0.25, [0.0, 0.0, 0.0], [0, 0, 0]),                    # scratch_itch.py:247-248
+    ("bed_bathing", "jaco"): (1.1, [-0.01, 0.0, 0.03], [0, -np.pi / 2.0, 0]),       # bed_bathing.py:327-328
+    ("bed_bathing", "pr2"): (0.2, [0.0, 0.0, 0.0], [0, 0, 0]),                      # bed_bathing.py:320-321
+}
+TOC_POS_OFFSET = {("scratch_itch", "pr2"): [0.1, 0.0, 0.0], ("bed_bathing", "pr2"): [0.0, 0.0, 0.0],
+                  ("bed_bathing", "jaco"): [0.1, 0.55, 0.6]}                         # scratch_itch.py:245, bed_bathing.py:318,325
 
 
 @dataclass
@@ -171,7 +236,7 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
             continue
         b.dof = len(dofs); b.qidx = qidx; qidx += 1
         d = dict(body=bi, flags=0, lower=b.lower, upper=b.upper, rep_lower=b.lower, rep_upper=b.upper,
-                 kp=0.0, kd=1.0, max_force=0.0, action=-1, human_slot=-1, init_target=0.0)
+                 kp=0.0, kd=1.0, max_force=0.0, action=-1, human_slot=-1, init_target=0.0, damping=float(b.damping))
         if b.limit_enforced:
             d["flags"] |= 1
         setup_dof(b, d)
@@ -224,7 +289,9 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
                 if link_parent(mb, a.ref_link) == b.ref_link or link_parent(mb, b.ref_link) == a.ref_link:
                     continue                                  # Bullet never collides a link with its parent
                 if mb is robot:
-                    pass                                      # URDF_USE_SELF_COLLISION, world_creation.py:282
+                    if not getattr(mb, "self_collision", True):
+                        continue                              # PR2: loaded without URDF_USE_SELF_COLLISION (world_creation.py:187)
+                    # Jaco: URDF_USE_SELF_COLLISION, world_creation.py:282
                 elif mb is human:
                     if not human_self_collision_enabled(a.ref_link, b.ref_link):
                         continue
@@ -238,14 +305,19 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
 
 
 def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,
-                       verbose: bool = False) -> CompiledScene:
-    if robot_type != "jaco":
-        raise NotImplementedError("round 1 compiles the Jaco recipe only (SURVEY.md §7 step 8 lists the others as next)")
+                       base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False) -> CompiledScene:
+    """ScratchItch<Robot>[Human]-v0.  PR2: `base_xy_yaw` = the random_pos / yaw chosen by `position_robot_toc`
+    (env.py:511-513 as called at scratch_itch.py:245)."""
     cfg = CONFIG["scratch_itch"]
     # -- bodies as the reference creates them ---------------------------------------------------------------
-    robot = urdf_to_multibody(os.path.join(assets_dir, "jaco", "j2s7s300_gym.urdf"), REF_ROBOT, "jaco")
-    robot.base_pos = np.array([-0.35, -0.3, 0.36])                       # scratch_itch.py:168
-    robot.base_quat = np.array([0.0, 0.0, -0.7071067811865475, 0.7071067811865476])
+    robot, rs = load_robot(assets_dir, robot_type)
+    if robot_type == "jaco":
+        robot.base_pos = np.array([-0.35, -0.3, 0.36])                   # scratch_itch.py:168
+        robot.base_quat = np.array([0.0, 0.0, -0.7071067811865475, 0.7071067811865476])
+    else:
+        robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.asarray(TOC_POS_OFFSET[("scratch_itch", robot_type)]) \
+            + np.array([base_xy_yaw[0], base_xy_yaw[1], 0.0])            # env.py:513
+        robot.base_quat = X.quat_from_euler([0, 0, base_xy_yaw[2]])
     robot.fixed_base = True
     h2m = 0.6 if gender == "male" else 0.54                              # scratch_itch.py:161
     human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
@@ -271,8 +343,9 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
             q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))
     controllable = list(range(4, 14))                                     # scratch_itch.py:197
     frozen_h = {l.ref_index for l in human.links if l.ref_index not in controllable}   # world_creation.py:157-161
-    robot_arm = [1, 2, 3, 4, 5, 6, 7]                                     # world_creation.py:283
-    fingers = [9, 11, 13]                                                 # world_creation.py:320
+    robot_arm = rs["arm"]                                                 # world_creation.py:283 / :189
+    fingers = rs["fingers"]                                               # world_creation.py:311-320
+    finger_open, tool_pos_offset, tool_euler = TOOL_SETUP[("scratch_itch", robot_type)]
 
     def setup_dof(b: DynBody, d: dict) -> None:
         if b.art == 0:
@@ -280,7 +353,7 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
                 d.update(kp=cfg["robot_gains"], max_force=cfg["robot_forces"], action=robot_arm.index(b.ref_joint))
                 d["flags"] |= 2
             elif b.ref_joint in fingers:
-                d.update(kp=0.05, max_force=500.0, init_target=1.0)      # world_creation.py:328, scratch_itch.py:254
+                d.update(kp=0.05, max_force=500.0, init_target=finger_open)   # world_creation.py:328, scratch_itch.py:254 / :247
                 d["flags"] |= 2
         elif b.art == 1:
             slot = controllable.index(b.ref_joint)
@@ -289,14 +362,14 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
             if human_control:
                 d["action"] = 7 + slot
 
-    tool_filtered_robot_links = set(range(7, 15))             # world_creation.py:352-354 (jaco)
+    tool_filtered_robot_links = rs["tool_filtered"]           # world_creation.py:352-354
 
     def cross_pair_ok(a: CompiledShape, b: CompiledShape) -> bool:
         ms = {a.mb_index: a, b.mb_index: b}
         return not (0 in ms and 2 in ms and ms[0].ref_link in tool_filtered_robot_links)
 
     bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs = _assemble(
-        mbs, {1: q_human}, {1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
+        mbs, {0: rs["q_preset"], 1: q_human}, {0: rs["frozen"], 1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
     n_body = len(bodies); n_dof = len(dofs)
 
     # -- frames of interest ----------------------------------------------------------------------------------
@@ -306,15 +379,15 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
         p, q = X.tf_mul(at.pos, at.quat, link.inertial_pos, link.inertial_quat)
         return (at.body, p, q)
 
-    tool_pos_offset = np.array([0.0, 0.0, 0.02])              # scratch_itch.py:255
-    tool_orient_offset = X.quat_from_euler([0, -np.pi / 2.0, 0])
-    ee = com_frame(0, 8)
+    tool_pos_offset = np.asarray(tool_pos_offset, float)      # scratch_itch.py:255 / :248
+    tool_orient_offset = X.quat_from_euler(tool_euler)
+    ee = com_frame(0, rs["ee_link"])
     weld_parent = (ee[0],) + X.tf_mul(ee[1], ee[2], tool_pos_offset, tool_orient_offset)
     frames = [
         com_frame(2, 1),            # AVG_F_TOOL_TIP
         com_frame(2, -1),           # AVG_F_TOOL_BASE
         weld_parent,                # AVG_F_WELD_PARENT
-        com_frame(0, 0),            # AVG_F_TORSO (robot link 0 COM, static)
+        com_frame(0, rs["torso_link"]),   # AVG_F_TORSO (robot link 0, PR2: link 15; COM frame, static; scratch_itch.py:105)
         com_frame(1, 3),            # AVG_F_CHEST
         com_frame(1, 9), com_frame(1, 11), com_frame(1, 13),
     ]
@@ -338,6 +411,7 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
                           frames=frames, dofs=dofs, header=header, robot_arm_joints=robot_arm,
                           human_joints=list(range(7, 14)), q_human_reset=q_human,
                           tool_offset=(tool_pos_offset, tool_orient_offset))
+    scene.finger_open = finger_open; scene.robot_spec = rs
     scene.mlp_layers = None
     if human_control:      # env.py:67: realistic_arm_limits_model.h5, used by enforce_realistic_human_joint_limits (env.py:353-387)
         from .h5lite import load_keras_dense_stack
@@ -447,19 +521,20 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     robot base at the pose chosen by `position_robot_toc` (random_pos x, y and yaw = `base_xy_yaw`, env.py:511-513,
     bed_bathing.py:325), nightstand under it (bed_bathing.py:330-338), gravity off for robot / human / tool (:341-344).
     """
-    if robot_type != "jaco":
-        raise NotImplementedError("round 1 compiles the Jaco recipe only")
     cfg = CONFIG["bed_bathing"]
     deg = np.deg2rad
     play = stage == "play"
-    robot = urdf_to_multibody(os.path.join(assets_dir, "jaco", "j2s7s300_gym.urdf"), REF_ROBOT, "jaco")
+    robot, rs = load_robot(assets_dir, robot_type)
     robot.fixed_base = True
     if play:
         rx, ry, yaw = base_xy_yaw
-        robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.array([0.1, 0.55, 0.6]) + np.array([rx, ry, 0.0])   # env.py:513, bed_bathing.py:325
+        robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.asarray(TOC_POS_OFFSET[("bed_bathing", robot_type)]) \
+            + np.array([rx, ry, 0.0])                                                                     # env.py:513, bed_bathing.py:318,325
         robot.base_quat = X.quat_from_euler([0, 0, yaw])
-    else:
+    elif robot_type == "jaco":
         robot.base_pos = np.array([-2.0, -2.0, 0.975]); robot.base_quat = I4.copy()                      # world_creation.py:288
+    else:
+        robot.base_pos = np.array([-2.0, -2.0, 0.0]); robot.base_quat = I4.copy()                        # world_creation.py:194
     h2m = 0.6 if gender == "male" else 0.54                                                               # bed_bathing.py:196
     human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
     human.base_pos = np.array([0.0, 0.0, 0.7]); human.base_quat = X.quat_from_euler([deg(-30), 0, 0])     # bed_bathing.py:203
@@ -477,7 +552,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
                          [0, y_offset + 0.45, 0.42], X.quat_from_euler([np.pi / 2.0, 0, -np.pi / 2.0]))   # :223-227
     plane = _static_body("plane", [ShapeDesc(SHAPE_PLANE, np.zeros(3), I4.copy(), friction=1.0, ref_link=-1)], [0, 0, 0], I4, REF_PLANE)
     mbs = [robot, human, tool, m0, m1, frame]
-    if play:
+    if play and robot_type == "jaco":                                                                     # "a nightstand ... for the jaco arm"
         ns = 0.275                                                                                        # :331-338
         nightstand = _static_body("nightstand", _mesh_shapes(os.path.join(assets_dir, "nightstand", "nightstand.obj"), [ns] * 3, 0.5,
                                                              single_hull=True),
@@ -501,9 +576,9 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
             q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))       # world_creation.py:169
     controllable = list(range(4, 14))                                                                     # bed_bathing.py:294
     frozen_h = {l.ref_index for l in human.links if (play and not human_control) or l.ref_index not in controllable}   # :285 / :294-295
-    robot_arm = [1, 2, 3, 4, 5, 6, 7]
-    fingers = [9, 11, 13]
-    finger_open = 1.1                                                                                     # bed_bathing.py:327
+    robot_arm = rs["arm"]
+    fingers = rs["fingers"]
+    finger_open, tool_pos_offset, tool_euler = TOOL_SETUP[("bed_bathing", robot_type)]                    # bed_bathing.py:320-321,327-328
 
     def setup_dof(b: DynBody, d: dict) -> None:
         if b.art == 0:
@@ -521,7 +596,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
             d.update(kp=0.0, kd=1.0, max_force=0.1)               # VELOCITY_CONTROL, target 0, force 0.1 (world_creation.py:164-167)
             d["flags"] |= 2
 
-    tool_filtered_robot_links = set(range(7, 15))                                                         # world_creation.py:352-354
+    tool_filtered_robot_links = rs["tool_filtered"]                                                       # world_creation.py:352-354
     bed_filtered_human_links = set(range(28, 42)) | {0, 1, 2, 3}                                          # bed_bathing.py:231-234
     bed_mbs = {3, 4, 5}
 
@@ -534,7 +609,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
         return True
 
     bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs = _assemble(
-        mbs, {1: q_human}, {1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
+        mbs, {0: rs["q_preset"], 1: q_human}, {0: rs["frozen"], 1: frozen_h}, setup_dof, cross_pair_ok, robot, human)
     n_body = len(bodies); n_dof = len(dofs)
 
     def com_frame(k: int, li: int):
@@ -543,15 +618,15 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
         p, q = X.tf_mul(at.pos, at.quat, link.inertial_pos, link.inertial_quat)
         return (at.body, p, q)
 
-    tool_pos_offset = np.array([-0.01, 0.0, 0.03])                                                        # bed_bathing.py:328
-    tool_orient_offset = X.quat_from_euler([0, -np.pi / 2.0, 0])
-    ee = com_frame(0, 8)
+    tool_pos_offset = np.asarray(tool_pos_offset, float)
+    tool_orient_offset = X.quat_from_euler(tool_euler)
+    ee = com_frame(0, rs["ee_link"])
     weld_parent = (ee[0],) + X.tf_mul(ee[1], ee[2], tool_pos_offset, tool_orient_offset)
     frames = [
         com_frame(2, 1),            # AVG_F_TOOL_TIP: wiper link 1 (cloth) COM, bed_bathing.py:54,131
         com_frame(2, -1),           # AVG_F_TOOL_BASE
         weld_parent,                # AVG_F_WELD_PARENT
-        com_frame(0, 0),            # AVG_F_TORSO: robot link 0 COM, bed_bathing.py:130
+        com_frame(0, rs["torso_link"]),   # AVG_F_TORSO: robot link 0 (PR2: 15) COM, bed_bathing.py:130
         com_frame(1, 3),            # AVG_F_CHEST: human link 3, bed_bathing.py:137
         com_frame(1, 9), com_frame(1, 11), com_frame(1, 13),       # :143-145
     ]
@@ -582,7 +657,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
         from .h5lite import load_keras_dense_stack
         scene.mlp_layers = load_keras_dense_stack(os.path.join(assets_dir, 'realistic_arm_limits_model.h5'))
     scene.targets = (up, fo)
-    scene.finger_open = finger_open
+    scene.finger_open = finger_open; scene.robot_spec = rs
     scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape, n_target=n_target)
     if verbose:
         print(scene.info)

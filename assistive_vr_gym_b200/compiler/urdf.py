@@ -41,6 +41,7 @@ class Link:
     inertial_pos: np.ndarray = field(default_factory=lambda: np.zeros(3))
     inertial_quat: np.ndarray = field(default_factory=lambda: np.array([0.0, 0, 0, 1]))
     inertia_diag_file: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    inertia_file: np.ndarray = field(default_factory=lambda: np.zeros((3, 3)))   # full <inertia> tensor, inertial frame
     collisions: List[Collision] = field(default_factory=list)
     lateral_friction: float = 0.5  # Bullet default
 
@@ -101,6 +102,9 @@ def parse_urdf(path: str) -> UrdfModel:
             ie = inert.find("inertia")
             if ie is not None:
                 link.inertia_diag_file = np.array([float(ie.get("ixx", 0)), float(ie.get("iyy", 0)), float(ie.get("izz", 0))])
+                ixy, ixz, iyz = float(ie.get("ixy", 0)), float(ie.get("ixz", 0)), float(ie.get("iyz", 0))
+                d = link.inertia_diag_file
+                link.inertia_file = np.array([[d[0], ixy, ixz], [ixy, d[1], iyz], [ixz, iyz, d[2]]])
         contact = le.find("contact")
         if contact is not None:
             lf = contact.find("lateral_friction")

@@ -44,6 +44,12 @@
 #ifndef AVG_OCC_SOLVE
 #define AVG_OCC_SOLVE 32
 #endif
+#ifndef AVG_GJK_SHRINK
+#define AVG_GJK_SHRINK 1e-6f      /* float32 GJK stops when |v|^2 fails to shrink by this relative amount */
+#endif
+#ifndef AVG_GJK_ITERS
+#define AVG_GJK_ITERS 32
+#endif
 
 namespace {
 
@@ -338,26 +344,30 @@ __device__ bool simplex_closest(Simplex& s, V3& v) {
         float l3[3]; closest_tri(s.w[0], s.w[1], s.w[2], l3, mask);
         lam[0] = l3[0]; lam[1] = l3[1]; lam[2] = l3[2];
     } else {
+        // Enclosed only when the origin is strictly inside all four faces of a non-degenerate tetrahedron; otherwise the
+        // best closest point over ALL four faces.  Hull-minus-capsule-core differences contain parallelograms, so four
+        // simplex points are routinely coplanar and culling faces by the apex side is decided by rounding noise.
         const int F[4][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 3, 1}, {1, 2, 3, 0}};
-        float best = 3.0e38f; bool any = false;
+        float best = 3.0e38f; bool inside = true, degenerate = false;
+#pragma unroll 1
         for (int f = 0; f < 4; ++f) {
             V3 a = s.w[F[f][0]], b = s.w[F[f][1]], c = s.w[F[f][2]], d = s.w[F[f][3]];
             V3 n = cross(b - a, c - a);
             float so = -dot(a, n), sd = dot(d - a, n);
-            if (sd == 0 || so * sd <= 0) {
-                float l3[3]; int km;
-                closest_tri(a, b, c, l3, km);
-                V3 p = a * l3[0] + b * l3[1] + c * l3[2];
-                float dd = dot(p, p);
-                if (dd < best) {
-                    best = dd; any = true;
-                    lam[0] = lam[1] = lam[2] = lam[3] = 0;
-                    lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
-                    mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
-                }
+            if (sd * sd <= 1e-10f * dot(n, n) * dot(d - a, d - a)) degenerate = true;
+            if (!(so * sd > 0.0f)) inside = false;
+            float l3[3]; int km;
+            closest_tri(a, b, c, l3, km);
+            V3 p = a * l3[0] + b * l3[1] + c * l3[2];
+            float dd = dot(p, p);
+            if (dd < best) {
+                best = dd;
+                lam[0] = lam[1] = lam[2] = lam[3] = 0;
+                lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
+                mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
             }
         }
-        if (!any) return true;
+        if (inside && !degenerate) return true;
     }
     int n = 0; V3 p = mk3(0, 0, 0);
     for (int i = 0; i < s.n; ++i) if (mask & (1 << i)) {
@@ -421,7 +431,7 @@ __device__ __noinline__ int gjk_lockstep(const WShape& A, const WShape& B, bool 
     if (dot(v, v) < 1e-12f) v = mk3(1, 0, 0);
     bool run = active;
 #pragma unroll 1
-    for (int it = 0; it < 32; ++it) {
+    for (int it = 0; it < AVG_GJK_ITERS; ++it) {
         if (!__any_sync(AVG_FULL, run)) break;
         const V3 sa = support_any(A, -v, run, lane) - org, sb = support_any(B, v, run, lane) - org;
         if (run) {
@@ -443,7 +453,7 @@ __device__ __noinline__ int gjk_lockstep(const WShape& A, const WShape& B, bool 
                     // float32 termination: |v| must shrink from one simplex to the next; once rounding stops it (near-touching
                     // cores, where the relative test above drowns in the noise of the support points) further
                     // iterations only cycle through the same vertices until the cap
-                    else if (!first && dot(v, v) >= vv * (1.0f - 1e-6f)) { result = 0; run = false; }
+                    else if (!first && dot(v, v) >= vv * (1.0f - AVG_GJK_SHRINK)) { result = 0; run = false; }
                 }
             }
         }
@@ -1179,6 +1189,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
     Sv F = inertia_mul(Ic_sub, L.S);          // composite inertia times own motion subspace
     float Cb = dot(L.S, f_sub);               // generalized bias force of this lane's joint
+    if (lane < nj) Cb = fmaf(m.dof[lane].damping, qd, Cb);   // joint damping torque -damping * qd (URDF <dynamics damping>, PR2)
     // ---- joint-space mass matrix in registers: lane c keeps column c of its articulation's diagonal block,
     //      mc[t] = M[bs+t][c] = S_row . (Ic_deeper S_deeper) (symmetric), one block per articulation -----------------
     int bs = lane, be = lane;

@@ -27,6 +27,11 @@ REGISTRY: Dict[str, dict] = {
     # reference __init__.py:103-108; observation 24 wide (bed_bathing.py:19,147)
     "BedBathingJaco-v0": dict(task="bed_bathing", robot="jaco", human_control=False, data="BedBathingJaco.npz"),
     "BedBathingJacoHuman-v0": dict(task="bed_bathing", robot="jaco", human_control=True, data="BedBathingJacoHuman.npz"),
+    # PR2 ids (reference __init__.py:4-14, 91-101): left arm + gripper integrated, the other branches baked static per base pose
+    "ScratchItchPR2-v0": dict(task="scratch_itch", robot="pr2", human_control=False, data="ScratchItchPR2.npz"),
+    "ScratchItchPR2Human-v0": dict(task="scratch_itch", robot="pr2", human_control=True, data="ScratchItchPR2Human.npz"),
+    "BedBathingPR2-v0": dict(task="bed_bathing", robot="pr2", human_control=False, data="BedBathingPR2.npz"),
+    "BedBathingPR2Human-v0": dict(task="bed_bathing", robot="pr2", human_control=True, data="BedBathingPR2Human.npz"),
 }
 _OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19
 _ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")

@@ -62,7 +62,9 @@ typedef struct AvgDof {           /* 16 x 4 bytes, one per velocity dof */
     int32_t  action;              /* index into the action vector, -1 = none                                */
     int32_t  human_slot;          /* index 0..9 into the reference's controllable-joint list, -1 = none     */
     float    init_target;
-    int32_t  pad[4];
+    float    damping;             /* joint damping torque -damping * qd (URDF <dynamics damping>, btMultibodyLink::m_jointDamping);
+                                     0 in blobs written before the PR2 was compiled (the slot was padding)              */
+    int32_t  pad[3];
 } AvgDof;
 
 typedef struct AvgShape {         /* 32 x 4 bytes */

@@ -317,27 +317,33 @@ static int simplex_closest(Simplex* s, v3* v) {
     else if (s->n == 2) { closest_seg(s, 0, 1, &lam[0], &lam[1], &mask); }
     else if (s->n == 3) { closest_tri(s, 0, 1, 2, lam, &mask); }
     else {
-        /* tetrahedron: test the four faces whose outside half-space contains the origin */
+        /* tetrahedron.  The origin is enclosed only when it lies strictly on the inner side of all four faces of a
+         * non-degenerate tetrahedron; otherwise the closest point is the best over ALL four faces (the closest point of a
+         * tetrahedron to an outside point lies on its boundary, so looking at a face that turns out to face away costs
+         * time, never correctness).  Culling faces by the sign of the apex side alone is not robust: the difference of a
+         * hull and a capsule core contains parallelograms (h_i - c_j with two hull vertices and the two segment ends), so
+         * four simplex points are routinely coplanar, the apex side is rounding noise, and a culled face could be the
+         * closest one (found with the PR2 forearm hull against the human forearm capsule: 1.2 cm of distance error). */
         static const int F[4][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 3, 1}, {1, 2, 3, 0}};
-        double best = 1e300; int any = 0;
+        double best = 1e300; int inside = 1, degenerate = 0;
         for (int f = 0; f < 4; ++f) {
             v3 a = s->w[F[f][0]], b = s->w[F[f][1]], c = s->w[F[f][2]], d = s->w[F[f][3]];
             v3 n = vcross(vsub(b, a), vsub(c, a));
             double so = -vdot(a, n), sd = vdot(vsub(d, a), n);
-            if (sd == 0 || so * sd <= 0) {      /* origin not strictly on the inner side of this face */
-                double l3[3]; int km;
-                closest_tri(s, F[f][0], F[f][1], F[f][2], l3, &km);
-                v3 p = vadd(vadd(vscale(a, l3[0]), vscale(b, l3[1])), vscale(c, l3[2]));
-                double dd = vdot(p, p);
-                if (dd < best) {
-                    best = dd; any = 1;
-                    lam[0] = lam[1] = lam[2] = lam[3] = 0;
-                    lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
-                    mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
-                }
+            if (fabs(sd) <= 1e-9 * vnorm(n) * vnorm(vsub(d, a))) degenerate = 1;
+            if (!(so * sd > 0)) inside = 0;
+            double l3[3]; int km;
+            closest_tri(s, F[f][0], F[f][1], F[f][2], l3, &km);
+            v3 p = vadd(vadd(vscale(a, l3[0]), vscale(b, l3[1])), vscale(c, l3[2]));
+            double dd = vdot(p, p);
+            if (dd < best) {
+                best = dd;
+                lam[0] = lam[1] = lam[2] = lam[3] = 0;
+                lam[F[f][0]] = l3[0]; lam[F[f][1]] = l3[1]; lam[F[f][2]] = l3[2];
+                mask = ((km & 1) ? (1 << F[f][0]) : 0) | ((km & 2) ? (1 << F[f][1]) : 0) | ((km & 4) ? (1 << F[f][2]) : 0);
             }
         }
-        if (!any) return 1;   /* origin inside */
+        if (inside && !degenerate) return 1;   /* origin inside */
     }
     /* compact */
     Simplex r; r.n = 0;
@@ -590,7 +596,9 @@ static void aba(const Model* m, const Kin* k, const double* env, Dyn* d, double*
         d->U[b] = sm_mul(&d->IA[b], &d->S[b]);
         d->D[b] = sv_dot(&d->S[b], &d->U[b]);
         d->invD[b] = (d->D[b] >= 2.2e-16) ? 1.0 / d->D[b] : 0.0;       /* [UPSTREAM-BULLET] D < eps => joint frozen */
-        u[b] = 0.0 - sv_dot(&d->S[b], &pA[b]);
+        /* joint torque: none applied (motors are constraint rows) except Bullet's explicit joint damping
+         * -m_jointDamping * qd (URDF <dynamics damping>; nonzero on the PR2 only) [UPSTREAM-BULLET] */
+        u[b] = -(double)m->dof[B->dof].damping * env[AVG_E_QD + B->dof] - sv_dot(&d->S[b], &pA[b]);
         if (B->parent >= 0) {
             sm Ia = d->IA[b];
             for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Ia.m[i][j] -= d->U[b].v[i] * d->invD[b] * d->U[b].v[j];

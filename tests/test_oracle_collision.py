@@ -142,3 +142,50 @@ def test_scene_contacts_are_symmetric_in_sign(oracles, env_data):
             assert row[11] < min(float(sa["thr"]), float(sb["thr"]))
             assert np.abs((row[2:5] - row[5:8]) - row[8:11] * row[11]).max() < 1e-7
     assert n_found > 0
+
+
+def test_gjk_coplanar_simplex_hull_vs_capsule(oracles):
+    """A hull against a capsule core (a segment): the Minkowski difference contains parallelograms (two hull vertices x
+    the two segment ends), so GJK's 4-point simplices are routinely coplanar.  The closest distance must not depend on
+    the rounding noise of the apex-side test (regression: 1.2 cm error between the PR2 forearm hull and the human forearm).
+    Checked against a brute-force minimisation over hull samples x the segment for many relative poses."""
+    o = oracles[0]
+    sh = o.model["shapes"]
+    hulls = [i for i in range(len(sh)) if sh[i]["type"] == 4 and sh[i]["vert_cnt"] >= 8]
+    caps = [i for i in range(len(sh)) if sh[i]["type"] == 1]
+    assert hulls and caps
+    rng = np.random.RandomState(11)
+    checked = 0
+    for trial in range(60):
+        ia = hulls[trial % len(hulls)]; ib = caps[trial % len(caps)]
+        va = o.model["verts"][int(sh[ia]["vert_off"]):int(sh[ia]["vert_off"]) + int(sh[ia]["vert_cnt"])].astype(np.float64)
+        hl = float(sh[ib]["half"][2])
+        size = np.linalg.norm(va.max(0) - va.min(0))
+        ctr = va.mean(0)
+        # capsule axis (its local z) parallel to a random hull edge direction makes coplanar simplices likely
+        e = va[rng.randint(len(va))] - va[rng.randint(len(va))]
+        if np.linalg.norm(e) < 1e-6:
+            continue
+        z = e / np.linalg.norm(e)
+        x = np.cross(z, rng.normal(size=3)); x /= np.linalg.norm(x); y = np.cross(z, x)
+        R = np.stack([x, y, z], axis=1)
+        w = 1.0 + np.trace(R); q = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1], w]); q /= np.linalg.norm(q)
+        off = rng.normal(size=3); off /= np.linalg.norm(off)
+        pb = ctr + off * (0.75 * size + 0.1)
+        hit, out = o.shape_pair(ia, [0, 0, 0, 0, 0, 0, 1], ib, list(pb) + list(q))
+        if not hit:
+            continue
+        core = out[9] + float(sh[ia]["margin"]) + float(sh[ib]["margin"])
+        if core <= 1e-6:
+            continue
+        # brute force: distance from the segment to the convex hull = min over hull surface samples; use the hull's
+        # vertices, edge and face samples via random convex combinations of vertex triples
+        t = np.linspace(-hl, hl, 201)
+        seg = pb[None, :] + t[:, None] * z[None, :]
+        lam = rng.dirichlet([0.3, 0.3, 0.3], size=4000)
+        idx = rng.randint(len(va), size=(4000, 3))
+        pts = np.concatenate([va, (va[idx] * lam[:, :, None]).sum(1)], axis=0)
+        d = np.sqrt(((pts[:, None, :] - seg[None, :, :]) ** 2).sum(-1)).min()
+        assert core <= d + 1e-9, (trial, core, d)            # GJK's distance is the global minimum: no sample may beat it
+        checked += 1
+    assert checked >= 30

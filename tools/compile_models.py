@@ -15,9 +15,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from assistive_vr_gym_b200.compiler.blob import scene_to_blob          # noqa: E402
 from assistive_vr_gym_b200.compiler import xform as X                  # noqa: E402
 from assistive_vr_gym_b200.compiler.reset import (build_reset_data, build_reset_data_bed_bathing, bed_bathing_settle_record,  # noqa: E402
-                                                  toc_search_jaco)
+                                                  toc_search_jaco, toc_search, ik_dls)
 from assistive_vr_gym_b200.compiler.scene import (build_scratch_itch, build_bed_bathing, load_settled_arm_q,  # noqa: E402
-                                                  urdf_to_multibody)
+                                                  urdf_to_multibody, load_robot)
 
 
 def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
@@ -67,11 +67,69 @@ def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
     print("wrote BedBathingJaco.npz, BedBathingJacoHuman.npz")
 
 
+def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int, pool: int):
+    """<Task>PR2-v0 / <Task>PR2Human-v0 for ScratchItch and BedBathing: per gender `n_base` base poses from the
+    task-oriented-configuration search (env.py:486-585 as called at scratch_itch.py:245 / bed_bathing.py:318: left arm,
+    tool link 76, random_position 0.5 m, +-30 deg), one model variant each (the PR2's static branches are baked into the
+    world at that pose).  ScratchItch draws its start target per episode (scratch_itch.py:243): each variant carries a
+    pool of IK start poses for `pool` target draws reached from its base."""
+    settled = load_settled_arm_q()
+    rng = np.random.RandomState(1001)
+    robot, rs = load_robot(assets, "pr2")
+    joints = rs["arm"]
+    lower = np.array([robot.links[j].lower for j in joints]); upper = np.array([robot.links[j].upper for j in joints])
+    ik_lo = np.where(lower > upper, -2 * np.pi, lower); ik_hi = np.where(lower > upper, 2 * np.pi, upper)
+    start_quat = X.quat_from_euler([0, 0, 0])
+    payloads = {False: {}, True: {}}
+    name = {"scratch_itch": "ScratchItchPR2", "bed_bathing": "BedBathingPR2"}[task]
+
+    def build(gender, human_control, base):
+        if task == "scratch_itch":
+            return build_scratch_itch(assets, "pr2", gender, human_control=human_control, base_xy_yaw=base)
+        return build_bed_bathing(assets, "pr2", gender, human_control=human_control, stage="play", arm_q=settled[gender], base_xy_yaw=base)
+
+    v = 0
+    for gender in ("male", "female"):
+        probe = build(gender, False, (0.0, 0.0, 0.0))
+        cf = probe.multibodies[1].com_frames(probe.q_human_reset)
+        goals = [cf[9][0], cf[11][0], cf[13][0]]                              # shoulder, elbow, wrist
+        pos_offset = [0.1, 0.0, 0.0] if task == "scratch_itch" else [0.0, 0.0, 0.0]
+        for k in range(n_base):
+            if task == "scratch_itch":
+                start_pos = np.array([-0.55, 0, 0.8]) + rng.uniform(-0.05, 0.05, size=3)   # scratch_itch.py:243
+            else:
+                start_pos = np.array([-0.5, -0.1, 1.0])                                   # bed_bathing.py:315
+            xy, yaw, q_start, reached = toc_search(robot, joints, start_pos, start_quat, goals, rng, pos_offset, attempts=attempts,
+                                                   random_position=0.5, ee_link=rs["ee_link"])
+            starts = [q_start]
+            tries = 0
+            while task == "scratch_itch" and len(starts) < pool and tries < 20 * pool:    # further episodes from the same base
+                tries += 1
+                tp = np.array([-0.55, 0, 0.8]) + rng.uniform(-0.05, 0.05, size=3)
+                q, ep, eq = ik_dls(robot, rs["ee_link"], joints, ik_lo, ik_hi, tp, start_quat, rng.uniform(ik_lo, ik_hi), iters=200)
+                if ep < 0.03 and eq < 0.03:
+                    starts.append(q)
+            for human_control in (False, True):
+                scene = build(gender, human_control, (float(xy[0]), float(xy[1]), float(yaw)))
+                blob = scene_to_blob(scene)
+                payloads[human_control][f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+                rd = build_reset_data_bed_bathing(scene, np.asarray(starts))
+                for key, a in rd.items():
+                    payloads[human_control][f"reset_{v}_{key}"] = a
+                print(name, gender, k, "human_control" if human_control else "", "base", np.round(xy, 3), "yaw", round(float(yaw), 3),
+                      "goals reached", reached, "start poses", len(starts), scene.info["n_pairs"], "pairs", scene.info["n_mshape"],
+                      "moving shapes", len(blob), "bytes")
+            v += 1
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **payloads[False])
+    np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
+    print("wrote", name + ".npz,", name + "Human.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--assets", default="/root/reference/assistive_gym/envs/assets")
     ap.add_argument("--pool", type=int, default=64)
-    ap.add_argument("--only", default="", help="scratch_itch | bed_bathing (default: both)")
+    ap.add_argument("--only", default="", help="scratch_itch | bed_bathing | pr2 | scratch_itch_pr2 | bed_bathing_pr2 (default: all)")
     ap.add_argument("--bases", type=int, default=8, help="BedBathing: robot base poses (model variants) per gender")
     ap.add_argument("--attempts", type=int, default=100, help="BedBathing: base poses tried per TOC search (env.py:486)")
     args = ap.parse_args()
@@ -79,6 +137,10 @@ if __name__ == "__main__":
     os.makedirs(out_dir, exist_ok=True)
     if args.only in ("", "bed_bathing"):
         compile_bed_bathing(args.assets, out_dir, args.bases, args.attempts)
+    if args.only in ("", "pr2", "scratch_itch_pr2"):
+        compile_pr2(args.assets, out_dir, "scratch_itch", args.bases, args.attempts, min(args.pool, 16))
+    if args.only in ("", "pr2", "bed_bathing_pr2"):
+        compile_pr2(args.assets, out_dir, "bed_bathing", args.bases, args.attempts, 1)
     for human_control in ((False, True) if args.only in ("", "scratch_itch") else ()):
         payload = {}
         rng = np.random.RandomState(1001)              # env.py:53 default seed
