@@ -41,6 +41,8 @@ struct AvgHandle {
     // narrowphase work queues: set 0 for avg_step and even chunks of avg_step_host, set 1 for odd chunks (second stream)
     AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0;
     cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // avg_step on two streams: fork from / join into the caller's stream
+    int step_chunks = 1;
     unsigned long long* d_cnt = nullptr;               // AVG_DBG & 32 (development aid)
     std::string err;
 };
@@ -102,6 +104,12 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     }
     cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    /* avg_step splits large batches into two halves on two streams: the kernels of one half fill the tails (and the
+       sparsely populated narrowphase kernel) of the other.  AVG_STEP_CHUNKS=1 restores the single-stream sequence. */
+    h->step_chunks = n_env >= 32768 ? 2 : 1;
+    { const char* c = getenv("AVG_STEP_CHUNKS"); if (c && atoi(c) > 0) h->step_chunks = atoi(c) > 1 ? 2 : 1; }
     *out = h;
     return 0;
 }
@@ -117,6 +125,8 @@ int avg_destroy(AvgHandle* h) {
     }
     for (int k = 0; k < 2; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) { cudaFree(h->d_model[v]); cudaFree(h->d_rtab[v]); }
     cudaFree(h->d_episode); cudaFree(h->d_policy);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
@@ -296,8 +306,24 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     AvgStepArgs a; memset(&a, 0, sizeof(a));
     int rc = fill_args(h, a, 0); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
+    if (h->step_chunks < 2 || h->debug) {
+        AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
+        h->launches += avg_kernels_per_step(h->substeps);
+        return 0;
+    }
+    /* two halves, two streams (still asynchronous and capturable: event fork / join around the second stream) */
+    const int half = ((h->n_env / 2) + 3) & ~3;
+    AvgStepArgs b; memset(&b, 0, sizeof(b));
+    rc = fill_args(h, b, 1); if (rc) return rc;
+    b.actions = actions; b.obs = obs; b.reward = reward; b.done = done; b.info = info;
+    a.env_begin = 0; a.env_end = half; b.env_begin = half; b.env_end = h->n_env;
+    AVG_CHECK(h, cudaEventRecord(h->ev_fork, (cudaStream_t)stream));
+    AVG_CHECK(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-    h->launches += avg_kernels_per_step(h->substeps);
+    AVG_CHECK(h, avg_launch_step(b, h->substeps, h->stream2));
+    AVG_CHECK(h, cudaEventRecord(h->ev_join, h->stream2));
+    AVG_CHECK(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
+    h->launches += 2 * avg_kernels_per_step(h->substeps);
     return 0;
 }
 

@@ -325,7 +325,23 @@ __device__ void closest_tri(const V3& a, const V3& b, const V3& c, float lam[3],
     if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
         float w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); lam[0] = 0; lam[1] = 1 - w; lam[2] = w; mask = 6; return;
     }
-    float den = 1.0f / (va + vb + vc);
+    const float sum = va + vb + vc;
+    if (!(sum > 0.0f)) {
+        // zero-area triangle whose vertex / edge tests all fell through (collinear points in float32): closest point of
+        // its longest edge, so that no 0/0 reaches the search direction
+        const V3 bc = c - b;
+        const float lab = dot(ab, ab), lac = dot(ac, ac), lbc = dot(bc, bc);
+        const V3 p0 = (lab >= lac && lab >= lbc) ? a : (lac >= lbc ? a : b);
+        const V3 e = (lab >= lac && lab >= lbc) ? ab : (lac >= lbc ? ac : bc);
+        const int i0 = (lab >= lac && lab >= lbc) ? 0 : (lac >= lbc ? 0 : 1), i1 = (lab >= lac && lab >= lbc) ? 1 : 2;
+        const float ee = dot(e, e);
+        const float t = ee > 0.0f ? fminf(fmaxf(-dot(p0, e) / ee, 0.0f), 1.0f) : 0.0f;
+        lam[0] = lam[1] = lam[2] = 0.0f; lam[i0] = 1.0f - t; lam[i1] += t;
+        mask = (1 << i0) | (t > 0.0f ? (1 << i1) : 0);
+        if (t >= 1.0f) mask = 1 << i1;
+        return;
+    }
+    float den = 1.0f / sum;
     lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2]; mask = 7;
 }
 
@@ -402,7 +418,7 @@ __device__ __noinline__ V3 support_any(const WShape& w, V3 d, bool active, int l
         const float4* v = reinterpret_cast<const float4*>(__shfl_sync(AVG_FULL, vp, src));
         const int n = __shfl_sync(AVG_FULL, nv, src);
         const float lx = __shfl_sync(AVG_FULL, l.x, src), ly = __shfl_sync(AVG_FULL, l.y, src), lz = __shfl_sync(AVG_FULL, l.z, src);
-        float bd = -3.0e38f; int bi = 0x7fffffff;
+        float bd = -3.0e38f; int bi = 0x7fffffff;                  // a lane without a vertex (or a NaN direction) keeps the sentinel
         for (int i = lane; i < n; i += 32) {
             const float4 p = __ldg(v + i);
             const float dd = fmaf(lx, p.x, fmaf(ly, p.y, lz * p.z));
@@ -413,7 +429,7 @@ __device__ __noinline__ V3 support_any(const WShape& w, V3 d, bool active, int l
             const float od = __shfl_xor_sync(AVG_FULL, bd, o); const int oi = __shfl_xor_sync(AVG_FULL, bi, o);
             if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
         }
-        if (lane == src) { const float4 bv = __ldg(v + bi); res = w.p + mmul(w.R, mk3(bv.x, bv.y, bv.z)); }
+        if (lane == src) { const float4 bv = __ldg(v + (bi < n ? bi : 0)); res = w.p + mmul(w.R, mk3(bv.x, bv.y, bv.z)); }   // bi >= n only for a NaN direction
     }
     return res;
 }
@@ -449,7 +465,7 @@ __device__ __noinline__ int gjk_lockstep(const WShape& A, const WShape& B, bool 
                     fresh = false;
                     const bool first = s.n == 0;
                     s.w[s.n] = w; s.a[s.n] = sa; s.b[s.n] = sb; s.n++;
-                    if (simplex_closest(s, v) || dot(v, v) < 1e-12f) { result = 1; run = false; }
+                    if (simplex_closest(s, v) || !(dot(v, v) >= 1e-12f)) { result = 1; run = false; }     // also catches a non-finite v
                     // float32 termination: |v| must shrink from one simplex to the next; once rounding stops it (near-touching
                     // cores, where the relative test above drowns in the noise of the support points) further
                     // iterations only cycle through the same vertices until the cap
@@ -953,7 +969,11 @@ avg_narrow_kernel(AvgStepArgs a) {
         const int variant = (valid && a.variant) ? a.variant[it.env] : 0;
         const KM m = c_models[a.slot][variant];
         float* scr = a.scratch + (size_t)it.env * AVG_S_STRIDE;
-        const int sa = it.pair & 0xffff, sb = it.pair >> 16;
+        int sa = it.pair & 0xffff, sb = it.pair >> 16;
+        if (valid && (sa >= m.h->n_mshape || sb >= m.h->n_shape || it.slot < 0 || it.slot >= AVG_S_NQMAX || it.cert >= AVG_S_NSEPMAX || it.env < 0 || it.env >= a.n_env)) {
+            if (a.dbg & 64) printf("[avg_narrow] bad work item %d of %d: env %d pair %08x slot %d cert %d\n", i, count, it.env, it.pair, it.slot, it.cert);
+            sa = 0; sb = m.h->n_mshape; it.slot = 0; it.cert = -1; it.env = a.env_begin;     // never dereference a corrupt item
+        }
         WShape A, B; Q4 qa, qb;
         np_load_shape(m, scr, sa, A, qa); np_load_shape(m, scr, sb, B, qb);
         const float thr = fminf(A.s->thr, B.s->thr), ma = A.s->margin, mb = B.s->margin;
@@ -2245,7 +2265,16 @@ cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t str
     const bool kt_on = g_kt.on && a.env_begin == 0 && a.env_end == a.n_env;     // whole-batch launches only
     int nev = 0;
     if (kt_on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
-    auto mark = [&]() { if (kt_on) cudaEventRecord(g_kt.ev[nev++], stream); };
+    static const bool sync_each = getenv("AVG_SYNC_EACH") != nullptr;        // development aid: name the kernel that faults
+    int kseq = 0;
+    auto mark = [&]() {
+        if (kt_on) cudaEventRecord(g_kt.ev[nev++], stream);
+        if (sync_each) {
+            const cudaError_t e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) fprintf(stderr, "[avg] launch #%d of the step (0 = before prologue, 1 = prologue, then collide/narrow/dynamics/solve per sub-step) failed: %s\n", kseq, cudaGetErrorString(e));
+            kseq++;
+        }
+    };
     const int n_range = a.env_end - a.env_begin;
     if (n_range <= 0) return cudaSuccess;
     auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };

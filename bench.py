@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--envs-per-gpu", type=int, default=196608)
+    ap.add_argument("--envs-per-gpu", type=int, default=393216)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-episode", action="store_true", help="skip the extra whole-episode (200-step) throughput measurement")
@@ -283,15 +283,40 @@ def main():
                   "note": "synthetic-policy rollout: orthogonal-init 30-64-64-7 tanh actor on VecNormalize'd observations, inference fused on "
                           "the device (avg_policy_act), steps 3-52 after reset"}
 
-    # ---- BedBathingJaco-v0 (extra; BASELINE.json configs[2] names BedBathingPR2-v0 with a pretrained policy at 8192 envs:
-    #      the PR2 model is not compiled yet and no checkpoint ships, so this is the Jaco variant with the synthetic
-    #      policy): whole 200-step episodes from a device reset, at the named batch size and at a GPU-filling one ----------
+    # ---- batch-size sweep (extra): the same random-action steps at smaller batches; 4096 envs is less than one wave of
+    #      warps on 148 SMs, so small batches are latency-bound by the 44-kernel launch sequence ------------------------------
+    sweep = None
+    if not args.no_episode:
+        sweep = []
+        for nb in (4096, 16384, 65536, 196608):
+            senv_b = make(ENV_ID, num_envs=nb, device=local_rank, seed=1001 + rank)
+            senv_b.reset_device(seed=1001 + rank)
+            sa = torch.empty((nb, 7), device=dev)
+            for k in range(3):
+                sa.uniform_(-1, 1, generator=gen); senv_b.step(sa); senv_b.elapsed = 0
+            barrier()
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for k in range(20):
+                sa.uniform_(-1, 1, generator=gen); senv_b.step(sa); senv_b.elapsed = 0
+            s1.record(stream)
+            barrier()
+            ts = torch.tensor([s0.elapsed_time(s1)], device=dev)
+            if distributed:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            sweep.append({"envs_per_gpu": nb, "value": nb * world * 20 / (float(ts.item()) * 1e-3), "unit": UNIT, "steps": 20})
+            senv_b.close()
+
+    # ---- BedBathing (extra; BASELINE.json configs[2] names BedBathingPR2-v0 with a pretrained policy at 8192 envs: no
+    #      checkpoint ships, so the policy is the synthetic one): whole 200-step episodes from a device reset, on the PR2
+    #      at the named batch size, on the Jaco at the named and at a GPU-filling batch size ------------------------------
     bed = None
     if not args.no_episode:
         from assistive_vr_gym_b200.policy import synthetic_policy
         bed = []
-        for nb in (8192, 65536):
-            benv = make("BedBathingJaco-v0", num_envs=nb, device=local_rank, seed=1001 + rank)
+        for bid, nb in (("BedBathingPR2-v0", 8192), ("BedBathingPR2-v0", 65536), ("BedBathingJaco-v0", 8192), ("BedBathingJaco-v0", 65536),
+                        ("ScratchItchPR2-v0", 65536)):
+            benv = make(bid, num_envs=nb, device=local_rank, seed=1001 + rank)
             pblob, _ = synthetic_policy(benv.obs_robot_len, benv.action_robot_len, seed=0)
             benv.set_policy(pblob)
             benv.reset_device(seed=1001 + rank)
@@ -309,9 +334,9 @@ def main():
             if distributed:
                 dist.all_reduce(tb, op=dist.ReduceOp.MAX)
                 dist.all_reduce(bstat, op=dist.ReduceOp.SUM)
-            bed.append({"env_id": "BedBathingJaco-v0", "envs_per_gpu": nb, "value": nb * world * 200 / (float(tb.item()) * 1e-3), "unit": UNIT,
+            bed.append({"env_id": bid, "envs_per_gpu": nb, "value": nb * world * 200 / (float(tb.item()) * 1e-3), "unit": UNIT,
                         "steps": 200, "task_success_rate": float(bstat[0]) / (nb * world), "mean_reward_last_step": float(bstat[1]) / (nb * world),
-                        "note": "synthetic-policy rollout (24-64-64-7 tanh actor, fused inference), full episode from a device reset"})
+                        "note": "synthetic-policy rollout (%d-64-64-7 tanh actor, fused inference), full episode from a device reset" % benv.obs_robot_len})
             benv.close()
 
     # ---- BASELINE.json configs[4] (ScratchItchJacoHuman-v0, 4096 envs per GPU, both halves of the action driven) and
@@ -375,7 +400,7 @@ def main():
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernels of one env-step" % (launches // max(1, args.steps)),
+                             "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (22 kernels x 2 half-batches on 2 streams)" % (launches // max(1, args.steps)),
                              "issue_slots": prof.get("issue_slots"),
                              "note": "issue/latency bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks; "
                                      "issue_slots (from the committed ncu launch list) is the roof that binds"},
@@ -386,6 +411,8 @@ def main():
             line["episode"] = episode
         if policy is not None:
             line["policy_rollout"] = policy
+        if sweep is not None:
+            line["batch_sweep"] = sweep
         if bed is not None:
             line["other_workloads"] = bed
         if not args.no_cpu_baseline and world == 1:

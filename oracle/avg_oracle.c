@@ -306,7 +306,23 @@ static void closest_tri(const Simplex* s, int i0, int i1, int i2, double lam[3],
     if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
         double w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); lam[0] = 0; lam[1] = 1 - w; lam[2] = w; *keep_mask = 6; return;
     }
-    double den = 1.0 / (va + vb + vc);
+    double sum = va + vb + vc;
+    if (!(sum > 0.0)) {
+        /* zero-area triangle whose vertex / edge tests all fell through (collinear points): closest point of its longest
+         * edge, so that no 0/0 reaches the search direction */
+        v3 bc = vsub(c, b);
+        double lab = vdot(ab, ab), lac = vdot(ac, ac), lbc = vdot(bc, bc);
+        int first = (lab >= lac && lab >= lbc) ? 0 : (lac >= lbc ? 1 : 2);      /* ab, ac, bc */
+        v3 p0 = first == 2 ? b : a, e = first == 0 ? ab : (first == 1 ? ac : bc);
+        int i0 = first == 2 ? 1 : 0, i1 = first == 0 ? 1 : 2;
+        double ee = vdot(e, e);
+        double t = ee > 0.0 ? fmin(fmax(-vdot(p0, e) / ee, 0.0), 1.0) : 0.0;
+        lam[0] = lam[1] = lam[2] = 0.0; lam[i0] = 1.0 - t; lam[i1] += t;
+        *keep_mask = (1 << i0) | (t > 0.0 ? (1 << i1) : 0);
+        if (t >= 1.0) *keep_mask = 1 << i1;
+        return;
+    }
+    double den = 1.0 / sum;
     lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2]; *keep_mask = 7;
 }
 

@@ -178,3 +178,23 @@ def test_human_active_variant_matches_oracle(torch_cuda):
                 assert np.abs(oobs - obs[e]).max() < 1e-3
     assert clean.sum() >= n // 4
     env.close()
+
+
+def test_degenerate_simplex_regression(torch_cuda, oracles):
+    """tests/golden/scratch_itch_fault_env.npz: a state found in a 393 216-environment policy rollout in which GJK meets a
+    zero-area triangle (collinear support points); the 0/0 of the barycentric formula used to reach the hull support scan
+    as a NaN direction and index out of bounds.  The step must run and agree with the oracle."""
+    torch = torch_cuda
+    from oracle.oracle import env_to_f64
+    z = np.load(os.path.join(GOLD, "scratch_itch_fault_env.npz"))
+    env = make_env(1)
+    env.set_state(z["state"], z["variants"])
+    obs, rew, done, info = env.step(torch.as_tensor(z["actions"], device="cuda"))
+    torch.cuda.synchronize()
+    st = env.get_state(); cont, nc = env.sim.get_contacts()
+    rec = env_to_f64(z["state"][0]).copy()
+    oobs, orew, oinfo, oc = oracles[int(z["variants"][0])].step(rec, z["actions"][0])
+    assert np.isfinite(st[0, :64]).all()
+    assert [(int(c[0]), int(c[1])) for c in oc] == [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[0, :nc[0]]]
+    assert np.abs(rec[:32] - st[0, :32]).max() < 1e-3 and abs(orew - float(rew[0])) < 1e-3
+    env.close()
