@@ -214,6 +214,15 @@ float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset);
 
+int avg_get_variants(AvgHandle* h, int env_begin, int env_count, int32_t* variants) {
+    if (!h || !variants) return -1;
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_variants: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(variants, h->d_variant + env_begin, sizeof(int32_t) * (size_t)env_count, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int avg_upload_policy(AvgHandle* h, const void* blob, size_t nbytes) {
     if (!h || !blob) return -1;
     if (h->task < 0) return fail(h, -1, "avg_upload_policy: upload a model first");

@@ -1468,6 +1468,8 @@ avg_solve_kernel(AvgStepArgs a) {
     {
         const float4* g_rd = reinterpret_cast<const float4*>(scr + AVG_S_ROWS_D);
         for (int i = lane; i < 2 * ndense; i += 32) s.rd[i >> 1][i & 1] = g_rd[i];
+        __syncwarp();
+        if (lane < 6) s.rd[lane][0].z = s.rd[lane][1].x;             // weld rows: lo = -hi, so the slot carries the row's diagonal instead (one load per row and sweep)
     }
     const float qd = lane < nd ? scr[AVG_S_QD + lane] : 0.0f;
     // block of this lane's dof, and this lane's column of the block of M^-1 (registers).  Unit rows are staged per
@@ -1537,13 +1539,13 @@ avg_solve_kernel(AvgStepArgs a) {
         }
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
-            const float4 ra = s.rd[d][0];                            // {target, 1/diag, -max, +max}
+            const float4 ra = s.rd[d][0];                            // {target, 1/diag, diag, max}: the weld clamp is symmetric (+-max)
             const float jdv = warp_sum(jw[d] * dv);
-            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lamW[d]), ra.z), ra.w);
+            const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lamW[d]), -ra.w), ra.w);
             const float delta = sum - lamW[d];
             lamW[d] = sum;
             dv = fmaf(s.W[d][lane], delta, dv);
-            resid = fmaxf(resid, fabsf(delta) * s.rd[d][1].x);
+            resid = fmaxf(resid, fabsf(delta) * ra.z);
         }
 #pragma unroll 1
         for (int d = 6; d < nfr; ++d) {

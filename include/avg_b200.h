@@ -39,6 +39,9 @@ int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_r
 /* Replaces getJointStates / getBasePositionAndOrientation / getBaseVelocity bulk reads: copies env records to HOST
  * memory.  Synchronous (waits for the stream work issued so far on the default stream of the handle). */
 int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records);
+/* Model variant of each environment (gender x robot base pose; chosen by avg_set_state or drawn by avg_reset) to HOST
+ * memory: what the reference stores as `gender` in setup.pkl (scratch_itch.py:269-272).  Synchronous. */
+int avg_get_variants(AvgHandle* h, int env_begin, int env_count, int32_t* variants);
 /* Device pointer of the state arena ([n_env][AVG_ENV_STRIDE] floats) for zero-copy inspection. */
 float* avg_state_device_ptr(AvgHandle* h);
 

@@ -17,6 +17,10 @@ for r in rows[1:]:
 agg = collections.defaultdict(lambda: collections.defaultdict(list))
 for (i, k), m in d.items():
     for mm, v in m.items(): agg[k][mm].append(v)
+# launches of each of our kernels in one env-step of one (half-)batch: a list cut at an arbitrary launch is normalised by these
+PER_STEP = {"avg_solve": 5, "avg_dynamics": 5, "avg_collide": 5, "avg_narrow": 5, "avg_epilogue": 1, "avg_prologue": 1}
+def per_step(k):
+    return next((c for n, c in PER_STEP.items() if n in k), 0)
 tot = sum(sum(v['gpu__time_duration.sum']) for v in agg.values())
 tot_inst = tot_dram = 0.0
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]['gpu__time_duration.sum'])):
@@ -33,6 +37,11 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]['gpu__time_duration.su
     if 'smsp__thread_inst_executed_per_inst_executed.ratio' in v:
         extra += f" lanes/inst {sum(v['smsp__thread_inst_executed_per_inst_executed.ratio'])/len(t):4.1f}"
     print(f"{k:40s} n={len(t):3d} mean {sum(t)/len(t)/1e6:8.3f} ms share {sum(t)/tot*100:5.1f}%{extra}")
+step_inst = sum(per_step(k) * sum(v['smsp__inst_executed.sum']) / len(v['smsp__inst_executed.sum']) for k, v in agg.items() if 'smsp__inst_executed.sum' in v)
+step_dram = sum(per_step(k) * (sum(v['dram__bytes_read.sum']) + sum(v['dram__bytes_write.sum'])) / len(v['dram__bytes_read.sum']) for k, v in agg.items() if 'dram__bytes_read.sum' in v)
+step_time = sum(per_step(k) * sum(v['gpu__time_duration.sum']) / len(v['gpu__time_duration.sum']) for k, v in agg.items())
+print(f"one env-step (per-kernel means x launches per step): {step_inst/n_env:.0f} warp instructions / env, {step_dram/n_env:.0f} DRAM bytes / env, serialised kernel time {step_time/1e6:.3f} ms for {n_env} envs")
+tot_inst, tot_dram, n_steps, tot = step_inst, step_dram, 1.0, step_time
 print(f"per env-step: {tot_inst/n_steps/n_env:.0f} warp instructions, {tot_dram/n_steps/n_env:.0f} DRAM bytes (read+write), serialised kernel time {tot/n_steps/1e6:.3f} ms")
 if len(sys.argv) > 4:
     json.dump({"source": sys.argv[1], "n_env": n_env, "dram_bytes_per_step_per_env": tot_dram / n_steps / n_env,
