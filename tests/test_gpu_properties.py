@@ -150,14 +150,19 @@ def test_separating_axis_cache_only_skips_work(torch_cuda):
     assert np.array_equal(out[0][1], out[1][1])
 
 
-def test_step_is_cuda_graph_capturable(torch_cuda):
-    """the step is a fixed launch sequence on one stream with no hidden synchronisation, so it can be
-    captured once and replayed; replays are bit-identical to eager steps."""
+@pytest.mark.parametrize("chunks", [1, 2])
+def test_step_is_cuda_graph_capturable(torch_cuda, chunks, monkeypatch):
+    """the step is a fixed launch sequence with no hidden synchronisation, so it can be captured once and
+    replayed; replays are bit-identical to eager steps.  chunks = 2: the two-stream form large batches use (half batches on
+    the caller's stream and on the handle's second stream, joined by events) is captured as a forked graph and equals the
+    single-stream sequence bit for bit."""
     torch = torch_cuda
     from assistive_vr_gym_b200 import make
     n = 4096
     acts = torch.rand((6, n, 7), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 2 - 1
+    monkeypatch.setenv("AVG_STEP_CHUNKS", "1")
     ref = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=31); ref.reset()
+    monkeypatch.setenv("AVG_STEP_CHUNKS", str(chunks))               # read when the handle is created
     env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=31); env.reset()
     for t in range(2):                                         # warm-up outside the capture (function attributes, lazy state)
         ref.step(acts[t]); env.step(acts[t])
