@@ -235,7 +235,8 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
         if b.jtype == JOINT_FREE:
             continue
         b.dof = len(dofs); b.qidx = qidx; qidx += 1
-        d = dict(body=bi, flags=0, lower=b.lower, upper=b.upper, rep_lower=b.lower, rep_upper=b.upper,
+        unlimited = b.lower == 0.0 and b.upper == -1.0        # getJointInfo of a continuous joint; the action mask sees +-1e10 (world_creation.py:122-124)
+        d = dict(body=bi, flags=0, lower=b.lower, upper=b.upper, rep_lower=-1e10 if unlimited else b.lower, rep_upper=1e10 if unlimited else b.upper,
                  kp=0.0, kd=1.0, max_force=0.0, action=-1, human_slot=-1, init_target=0.0, damping=float(b.damping))
         if b.limit_enforced:
             d["flags"] |= 1

@@ -65,6 +65,9 @@ def test_pr2_scene_layout(task):
     fin = [i for i in range(int(m["header"]["n_jdof"])) if d[i]["max_force"] == 500.0]
     assert len(fin) == 4 and np.allclose(d["init_target"][fin], 0.25 if task == "scratch_itch" else 0.2)
     assert np.allclose(d["damping"][arm], [10.0, 10.0, 0.1, 1.0, 0.1, 0.1, 0.1])
+    # continuous joints (forearm roll, wrist roll) report (0, -1) and are unlimited for the action mask: +-1e10, world_creation.py:122-124
+    assert np.all(d["rep_lower"][[arm[4], arm[6]]] == np.float32(-1e10)) and np.all(d["rep_upper"][[arm[4], arm[6]]] == np.float32(1e10))
+    assert np.all(d["rep_lower"][[arm[0], arm[3]]] > -3) and not (d["flags"][arm[4]] & 1)
     # no robot self collision (world_creation.py:187), tool vs links 71..85 filtered (world_creation.py:352)
     sh = m["shapes"]
     for pr in m["pairs"]:
@@ -125,6 +128,21 @@ def test_oracle_joint_damping_term():
     expect = -minv @ (damping * rec[32:32 + len(damping)])
     assert np.abs((qdd1 - qdd0) - expect).max() < 1e-9 * max(1.0, np.abs(expect).max())
     assert np.abs(expect).max() > 1e-2
+
+
+def test_oracle_pr2_action_moves_every_arm_joint():
+    """env.py:323-326: the limit mask zeroes an action component only when the joint would cross its limit; the PR2's two
+    continuous joints have none (+-1e10), so a +1 action moves all seven motor targets by 5 x 0.05 rad unless a limit is near."""
+    o, rec, _ = _first_env("BedBathingPR2.npz", seed=1)
+    d = o.model["dofs"]
+    arm = [i for i in range(len(d)) if 0 <= d[i]["action"] < 7]
+    before = rec[64 + np.asarray(arm)].copy()
+    o.step(rec, np.ones(7, dtype=np.float32))
+    moved = rec[64 + np.asarray(arm)] - before
+    assert abs(moved[4] - 0.25) < 1e-6 and abs(moved[6] - 0.25) < 1e-6          # forearm roll, wrist roll
+    for k in range(7):
+        room = d[arm[k]]["rep_upper"] - before[k]
+        assert moved[k] >= min(0.25, 0.05 * np.floor(room / 0.05 + 1e-9)) - 1e-6
 
 
 @pytest.mark.parametrize("name", ["ScratchItchPR2.npz", "BedBathingPR2.npz", "ScratchItchPR2Human.npz", "BedBathingPR2Human.npz"])
