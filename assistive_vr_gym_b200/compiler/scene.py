@@ -138,7 +138,27 @@ def load_robot(assets_dir: str, robot_type: str):
         q_preset = dict(zip(right, [-1.75, 1.25, -1.5, -0.5, -1.0, 0.0, -1.0]))          # env.py:455-459 reset_robot_joints
         return robot, dict(arm=left, fingers=fingers, ee_link=76, tool_filtered=set(range(71, 86)), torso_link=15,
                            frozen=frozen, q_preset=q_preset)
-    raise NotImplementedError(f"robot {robot_type!r}: the reference registers PR2 and Jaco ids only (SURVEY.md F4)")
+    if robot_type == "sawyer":
+        # world_creation.py:219-245.  No reference environment instantiates it (the task files have no Sawyer branch);
+        # the loader is compiled so that the build-defined Feeding / Drinking ids of BASELINE.json can use it.
+        robot = urdf_to_multibody(os.path.join(assets_dir, "sawyer", "sawyer.urdf"), REF_ROBOT, "sawyer")
+        robot.self_collision = True                                        # URDF_USE_SELF_COLLISION, world_creation.py:227
+        # setCollisionFilterPair(..., 0) for links 3..23 x 3..23 and 0..2 x 0..8 (world_creation.py:229-234)
+        robot.self_filter = lambda a, b: (3 <= a <= 23 and 3 <= b <= 23) or (0 <= a <= 2 and 0 <= b <= 8) or (0 <= b <= 2 and 0 <= a <= 8)
+        return robot, dict(arm=[3, 8, 9, 10, 11, 13, 16], fingers=[20, 22], finger_signs=[1.0, -1.0], ee_link=18,
+                           tool_filtered={18, 20, 21, 22, 23}, torso_link=0, frozen={4}, q_preset={})          # :235,317,332,352; joint 4 = head pan (idle, held by its default motor)
+    if robot_type == "baxter":
+        # world_creation.py:247-272 (right arm drives the tool; `useFixedBase` only: inertia from the collision shapes, no self collision)
+        robot = urdf_to_multibody(os.path.join(assets_dir, "baxter", "baxter_custom.urdf"), REF_ROBOT, "baxter")
+        robot.self_collision = False
+        right = [12, 13, 14, 15, 16, 18, 19]; left = [34, 35, 36, 37, 38, 40, 41]
+        fingers = [27, 29]                                                 # world_creation.py:313-315 (right gripper)
+        moving = set(right) | set(fingers)
+        frozen = {l.ref_index for l in robot.links if l.jtype in ("revolute", "prismatic") and l.ref_index not in moving}
+        q_preset = dict(zip(left, [0.75, 1.0, 0.5, 0.5, 1.0, -0.5, 0.0]))   # env.py:460-462 reset_robot_joints (idle left arm)
+        return robot, dict(arm=right, fingers=fingers, finger_signs=[1.0, -1.0], ee_link=25, tool_filtered={25, 27, 28, 29, 30},
+                           torso_link=0, frozen=frozen, q_preset=q_preset)                                     # :334,360
+    raise NotImplementedError(f"robot {robot_type!r}: the reference loads PR2, Jaco, Sawyer and Baxter (world_creation.py:181-293)")
 
 
 TOOL_SETUP = {   # (task, robot) -> gripper open position, tool pos_offset, tool orient_offset (euler)
@@ -292,6 +312,8 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
                 if mb is robot:
                     if not getattr(mb, "self_collision", True):
                         continue                              # PR2: loaded without URDF_USE_SELF_COLLISION (world_creation.py:187)
+                    if getattr(mb, "self_filter", None) is not None and mb.self_filter(a.ref_link, b.ref_link):
+                        continue                              # Sawyer: setCollisionFilterPair(robot, robot, i, j, 0), world_creation.py:229-234
                     # Jaco: URDF_USE_SELF_COLLISION, world_creation.py:282
                 elif mb is human:
                     if not human_self_collision_enabled(a.ref_link, b.ref_link):

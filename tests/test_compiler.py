@@ -109,3 +109,33 @@ def test_oracle_fk_matches_numpy_fk(scene):
                 l = mb.links[link]
                 p = bp[:3] + quat_rot(bp[3:], at.pos + quat_rot(at.quat, l.inertial_pos))
                 assert np.abs(p - com[link][0]).max() < 5e-7, (mb.name, link)      # blob transforms are float32
+
+
+@pytest.mark.assets
+@pytest.mark.parametrize("robot_type", ["sawyer", "baxter"])
+def test_sawyer_baxter_loaders_match_reference_constants(robot_type):
+    """`init_sawyer` / `init_baxter` (world_creation.py:219-272): PyBullet numbering re-derived from the URDFs reproduces the
+    hard-coded arm / gripper / tool-link indices (:235,254-255,313-318,332-334); the multibody reduces to <= 32 one-lane dofs
+    with a 6-dof tool (no reference environment uses these robots, SURVEY.md F4 -- they are compiled for the build-defined
+    Feeding / Drinking ids)."""
+    from assistive_vr_gym_b200.compiler.scene import load_robot
+    from assistive_vr_gym_b200.compiler.mbody import reduce_bodies
+    robot, rs = load_robot(ASSETS, robot_type)
+    names = {l.ref_index: l.name for l in robot.links}
+    movable = [l.ref_index for l in robot.links if l.jtype in ("revolute", "prismatic")]
+    if robot_type == "sawyer":
+        assert len(robot.links) == 24 and len(movable) == 10          # SURVEY.md 2.1: 8 revolute + 2 prismatic
+        assert rs["arm"] == [3, 8, 9, 10, 11, 13, 16] and [names[j] for j in rs["arm"]] == [f"right_l{k}" for k in range(7)]
+        assert names[18] == "right_gripper_base" and [names[j] for j in rs["fingers"]] == ["r_gripper_l_finger", "r_gripper_r_finger"]
+        assert robot.self_filter(5, 12) and robot.self_filter(1, 7) and not robot.self_filter(1, 12)
+    else:
+        assert len(robot.links) == 56 and len(movable) == 19          # 15 revolute + 4 prismatic
+        assert rs["arm"] == [12, 13, 14, 15, 16, 18, 19] and names[12] == "right_upper_shoulder" and names[19] == "right_wrist"
+        assert names[25] == "right_gripper_base" and names[47] == "left_gripper_base" and names[34] == "left_upper_shoulder"
+        assert [names[j] for j in rs["fingers"]] == ["r_gripper_l_finger", "r_gripper_r_finger"]
+    bodies, attach = reduce_bodies(robot, 0, rs["q_preset"], rs["frozen"], 0)
+    assert [b.ref_joint for b in bodies] == sorted(rs["arm"] + rs["fingers"])
+    assert len(bodies) + 6 + 4 <= 32                                  # + tool + head joints of Feeding / Drinking
+    assert all(b.mass > 0 and np.all(np.asarray(b.inertia) > 0) for b in bodies)
+    for b in bodies:
+        assert b.limit_enforced and b.lower < b.upper
