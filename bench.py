@@ -403,6 +403,12 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (22 kernels x 2 half-batches on 2 streams)" % (launches // max(1, args.steps)),
                              "issue_slots": prof.get("issue_slots"),
+                             "fp32": (lambda fp: None if not fp else {"flop_per_env_step": fp["flop_per_env_step_substep_kernels"],
+                                                                       "achieved_tflops": fp["flop_per_env_step_substep_kernels"] * value / world / 1e12,
+                                                                       "peak_tflops": 148 * 128 * 2 * 1.965e-3,
+                                                                       "frac": fp["flop_per_env_step_substep_kernels"] * value / world / 1e12 / (148 * 128 * 2 * 1.965e-3),
+                                                                       "note": "FADD + FMUL + 2 FFMA thread instructions per env-step from the committed ncu full-set capture "
+                                                                               "(profiles/traffic.json) x measured env-steps/s; FMA-pipe utilisation per kernel is in profiles/ncu_full_r1o.txt"})(prof.get("fp32")),
                              "note": "issue/latency bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks; "
                                      "issue_slots (from the committed ncu launch list) is the roof that binds"},
                 "clocks": sampler.summary(),
