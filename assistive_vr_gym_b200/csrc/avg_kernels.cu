@@ -138,11 +138,13 @@ struct __align__(16) SmEpi {
     float env[AVG_ENV_STRIDE];
     float bp[32][3]; float bq[32][4];
     float obs[64];
+    float fr[AVG_F_COUNT][8];              // world poses of the frames of interest (pos, quat), one lane each (frames_warp)
 };
 struct __align__(16) SmEpiBB {             // BedBathing epilogue: + the tool / human shape lists of the closest-point query
     float env[AVG_ENV_STRIDE];
     float bp[32][3]; float bq[32][4];
     float obs[64];
+    float fr[AVG_F_COUNT][8];
     float4 tcap[8][2];                     // bounding capsules of the tool shapes, world frame
     uint8_t tool_idx[8];
     uint8_t hum_idx[120];
@@ -160,6 +162,24 @@ __device__ __noinline__ void frame_pose(const KM& m, const SM& s, int f, V3& p, 
     body_pose(s, F->body, bp, bq);
     p = bp + qrot(bq, ld3(F->pos));
     q = qnormalize(qmul(bq, ldq(F->quat)));
+}
+
+// The frames of interest of the observation / reward code, all at once: lane f evaluates frame f into s.fr (the
+// epilogues used to walk them one after the other on lane 0).
+template <class SM>
+__device__ __forceinline__ void frames_warp(const KM& m, SM& s, int lane) {
+    if (lane < AVG_F_COUNT) {
+        V3 p; Q4 q;
+        frame_pose(m, s, lane, p, q);
+        float* f = s.fr[lane];
+        f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = q.x; f[4] = q.y; f[5] = q.z; f[6] = q.w;
+    }
+    __syncwarp();
+}
+template <class SM>
+__device__ __forceinline__ void frame_cached(const SM& s, int f, V3& p, Q4& q) {
+    const float* v = s.fr[f];
+    p = mk3(v[0], v[1], v[2]); q = mkq(v[3], v[4], v[5], v[6]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1705,12 +1725,12 @@ __device__ void fill_obs(const KM& m, SM& s, V3 tgt, float tool_force, float tot
     const AvgModelHeader* h = m.h;
     const int nj = h->n_jdof;
     V3 torso, tool, sh, el, wr, chest; Q4 tq, dq;
-    frame_pose(m, s, AVG_F_TORSO, torso, dq);
-    frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
-    frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
-    frame_pose(m, s, AVG_F_ELBOW, el, dq);
-    frame_pose(m, s, AVG_F_WRIST, wr, dq);
-    frame_pose(m, s, AVG_F_CHEST, chest, dq);
+    frame_cached(s, AVG_F_TORSO, torso, dq);
+    frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
+    frame_cached(s, AVG_F_SHOULDER, sh, dq);
+    frame_cached(s, AVG_F_ELBOW, el, dq);
+    frame_cached(s, AVG_F_WRIST, wr, dq);
+    frame_cached(s, AVG_F_CHEST, chest, dq);
     float* o = s.obs; int k = 0;
     V3 t;
     t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
@@ -1753,7 +1773,8 @@ avg_epilogue_kernel(AvgStepArgs a) {
         raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, scratch_itch.py:64
     }
     fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
-    V3 tgt; { V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
+    frames_warp(m, s, lane);
+    V3 tgt; { V3 lp; Q4 lq; frame_cached(s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
     const float dt = h->dt;
     const float* tf = h->task_f;
     const int ncontact = scr_i[AVG_S_NCS];
@@ -1780,7 +1801,7 @@ avg_epilogue_kernel(AvgStepArgs a) {
     }
     if (lane == 0) {
         fill_obs(m, s, tgt, tool_force, total_force_on_human, tool_force_at_target);
-        V3 tool; Q4 tq; frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+        V3 tool; Q4 tq; frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
         const int tb = m.frame[AVG_F_TOOL_TIP].body;
         const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
         const float ee_vel = norm(ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb])));       // scratch_itch.py:54
@@ -1849,11 +1870,11 @@ __device__ void fill_obs_bb(const KM& m, SM& s, float tool_force, float total_fo
     const AvgModelHeader* h = m.h;
     const int nj = h->n_jdof;
     V3 torso, tool, sh, el, wr; Q4 tq, dq;
-    frame_pose(m, s, AVG_F_TORSO, torso, dq);
-    frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
-    frame_pose(m, s, AVG_F_SHOULDER, sh, dq);
-    frame_pose(m, s, AVG_F_ELBOW, el, dq);
-    frame_pose(m, s, AVG_F_WRIST, wr, dq);
+    frame_cached(s, AVG_F_TORSO, torso, dq);
+    frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
+    frame_cached(s, AVG_F_SHOULDER, sh, dq);
+    frame_cached(s, AVG_F_ELBOW, el, dq);
+    frame_cached(s, AVG_F_WRIST, wr, dq);
     float* o = s.obs; int k = 0;
     V3 t;
     t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
@@ -1864,7 +1885,7 @@ __device__ void fill_obs_bb(const KM& m, SM& s, float tool_force, float total_fo
     t = wr - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
     o[k++] = tool_force;
     if (h->human_control) {                                  // :136-139,149: positions relative to human link 3
-        V3 chest; frame_pose(m, s, AVG_F_CHEST, chest, dq);
+        V3 chest; frame_cached(s, AVG_F_CHEST, chest, dq);
         t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
         o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
         const int hq0 = k;
@@ -1983,6 +2004,7 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
         raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, bed_bathing.py:62
     }
     fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    frames_warp(m, s, lane);
     const float dt = h->dt;
     const float* tf = h->task_f;
     const int ncontact = scr_i[AVG_S_NCS];
@@ -1990,8 +2012,8 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
     //      sweep over the targets lane l looks at target 32 r + l, i.e. bit l of word r.
     uint32_t mask_w = lane < 5 ? (uint32_t)env_i[AVG_E_TARGET_MASK + lane] : 0u;
     V3 up_p, fo_p; Q4 up_q, fo_q;
-    frame_pose(m, s, AVG_F_SHOULDER, up_p, up_q);            // human link 9 / 11 COM frames, bed_bathing.py:383,389
-    frame_pose(m, s, AVG_F_ELBOW, fo_p, fo_q);
+    frame_cached(s, AVG_F_SHOULDER, up_p, up_q);             // human link 9 / 11 COM frames, bed_bathing.py:383,389
+    frame_cached(s, AVG_F_ELBOW, fo_p, fo_q);
     const int n_target = h->n_target, n_upper = h->n_target_upper;
     const float radius = tf[AVG_TF_TARGET_RADIUS];
     float tool_force = 0, tool_force_on_human = 0, total_force_on_human = 0;
@@ -2080,7 +2102,7 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
     if (lane < 5) reinterpret_cast<uint32_t*>(grec)[AVG_E_TARGET_MASK + lane] = mask_w;
     if (lane == 0) {
         fill_obs_bb(m, s, tool_force, total_force_on_human, tool_force_on_human);
-        V3 tool; Q4 tq; frame_pose(m, s, AVG_F_TOOL_TIP, tool, tq);
+        V3 tool; Q4 tq; frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
         const int tb = m.frame[AVG_F_TOOL_TIP].body;
         const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
         const float ee_vel = norm(ld3(tv) + cross(ld3(tv + 3), tool - ld3(s.bp[tb])));       // bed_bathing.py:54
@@ -2124,10 +2146,11 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     __syncwarp();
     const int* env_i = reinterpret_cast<const int*>(s.env);
     fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    frames_warp(m, s, lane);
     if (lane == 0) {
         if (h->task == AVG_TASK_BED_BATHING) fill_obs_bb(m, s, 0.0f, 0.0f, 0.0f);                        // bed_bathing.py:350
         else {
-            V3 lp; Q4 lq; frame_pose(m, s, env_i[AVG_E_LIMB_FRAME], lp, lq);
+            V3 lp; Q4 lq; frame_cached(s, env_i[AVG_E_LIMB_FRAME], lp, lq);
             const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
             fill_obs(m, s, tgt, 0.0f, 0.0f, 0.0f);
             st3(grec + AVG_E_TARGET_POS, tgt);
