@@ -230,6 +230,28 @@ def target_mask_words(n_target: int) -> np.ndarray:
     return w.view(np.int32)
 
 
+# Start pose by inverse kinematics, per (task, robot): EE link target of the reference's reset() -- centre of the +-0.05 box and
+# orientation (scratch_itch.py:243-244 PR2, :251-252 Jaco).  BedBathing's start target is fixed, so its pool entry is exact.
+IK_START_TARGET = {("scratch_itch", "jaco"): ([-0.5, 0.0, 0.8], [0.0, np.pi / 2.0, 0.0]),
+                   ("scratch_itch", "pr2"): ([-0.55, 0.0, 0.8], [0.0, 0.0, 0.0])}
+
+
+def device_ik_setup(blob: bytes, task: str, robot: str) -> dict | None:
+    """What the device IK needs beyond the model: the EE link COM frame relative to its dynamic body, recovered from the
+    blob's weld-parent frame (= EE COM frame o tool offset, world_creation.py:331-337,356) and the task's tool offset."""
+    if (task, robot) not in IK_START_TARGET:
+        return None
+    from .blob import read_blob
+    from .scene import TOOL_SETUP
+    fr = read_blob(blob)["frames"][2]                                   # AVG_F_WELD_PARENT
+    _, tool_pos, tool_euler = TOOL_SETUP[(task, robot)]
+    ip, iq = X.tf_inv(np.asarray(tool_pos, float), X.quat_from_euler(tool_euler))
+    ee_p, ee_q = X.tf_mul(np.asarray(fr["pos"], float), np.asarray(fr["quat"], float), ip, iq)
+    pos, euler = IK_START_TARGET[(task, robot)]
+    return dict(ee_body=int(fr["body"]), ee_pos=ee_p, ee_quat=ee_q, target_pos=np.asarray(pos, float),
+                target_quat=X.quat_from_euler(euler), range=0.05)
+
+
 # ---- device reset (include/avg_model.h AvgResetTable, csrc avg_reset_kernel) ------------------------------------------
 RESET_POOL = 64
 RESET_TABLE_DT = np.dtype([
@@ -238,13 +260,19 @@ RESET_TABLE_DT = np.dtype([
     ("arm_qidx", "<i4", 8), ("arm_dof", "<i4", 8), ("fin_qidx", "<i4", 8), ("fin_dof", "<i4", 8),
     ("hum_qidx", "<i4", 8), ("hum_dof", "<i4", 8), ("hum_joint", "<i4", 8),
     ("hum_lower", "<f4", 8), ("hum_upper", "<f4", 8), ("hum_reset", "<f4", 8), ("limb_dims", "<f4", (2, 2)),
-    ("fin_open", "<f4"), ("pad_f", "<f4", 3),
+    ("fin_open", "<f4"), ("ik_enabled", "<i4"), ("ik_ee_body", "<i4"), ("ik_range", "<f4"),
+    ("ik_target", "<f4", 8), ("ik_ee_frame", "<f4", 8),
 ])
 
 
-def reset_table_bytes(rd: dict) -> bytes:
-    """One variant's `build_reset_data` as the AvgResetTable the device sampler reads."""
+def reset_table_bytes(rd: dict, ik: dict | None = None) -> bytes:
+    """One variant's `build_reset_data` as the AvgResetTable the device sampler reads.  `ik` (device_ik_setup) switches the
+    start pose from the pool to the on-device IK."""
     t = np.zeros(1, dtype=RESET_TABLE_DT)[0]
+    if ik is not None:
+        t["ik_enabled"] = 1; t["ik_ee_body"] = int(ik["ee_body"]); t["ik_range"] = float(ik["range"])
+        t["ik_target"][:3] = ik["target_pos"]; t["ik_target"][3:7] = ik["target_quat"]
+        t["ik_ee_frame"][:3] = ik["ee_pos"]; t["ik_ee_frame"][3:7] = ik["ee_quat"]
     n_pool = min(len(rd["pool_q"]), RESET_POOL)
     t["n_pool"] = n_pool; t["n_arm"] = len(rd["arm_qidx"]); t["n_fin"] = len(rd["fin_qidx"]); t["n_hum"] = len(rd["hum_qidx"])
     t["tool_qidx"] = int(rd["tool_qidx"]); t["human_control"] = int(rd["human_control"])

@@ -41,6 +41,7 @@ struct AvgHandle {
     // narrowphase work queues: set 0 for avg_step and even chunks of avg_step_host, set 1 for odd chunks (second stream)
     AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0;
     cudaStream_t stream2 = nullptr;
+    bool rtab_ik[AVG_K_MAX_VARIANTS] = {}; bool any_ik = false;     // reset tables that ask for the on-device IK start pose
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // avg_step on two streams: fork from / join into the caller's stream
     int step_chunks = 1;
     unsigned long long* d_cnt = nullptr;               // AVG_DBG & 32 (development aid)
@@ -258,6 +259,9 @@ int avg_upload_reset_table(AvgHandle* h, int variant, const void* table, size_t 
     cudaSetDevice(h->device);
     if (!h->d_rtab[variant]) AVG_CHECK(h, cudaMalloc(&h->d_rtab[variant], sizeof(AvgResetTable)));
     AVG_CHECK(h, cudaMemcpy(h->d_rtab[variant], table, sizeof(AvgResetTable), cudaMemcpyHostToDevice));
+    h->rtab_ik[variant] = t->ik_enabled != 0;
+    h->any_ik = false;
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) h->any_ik = h->any_ik || h->rtab_ik[v];
     return 0;
 }
 
@@ -270,8 +274,10 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
     if (nv == 0) return fail(h, -1, "avg_reset: no reset table uploaded (avg_upload_reset_table)");
     r.n_variants = nv; r.n_per_gender = nv >= 2 ? nv / 2 : 1; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
     r.mask = mask; r.n_env = h->n_env; r.seed = seed;
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) r.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
+    r.any_ik = h->any_ik ? 1 : 0;
     AVG_CHECK(h, avg_launch_reset(r, (cudaStream_t)stream));
-    h->launches++;
+    h->launches += 1 + r.any_ik;
     if (obs) {
         AvgStepArgs a; memset(&a, 0, sizeof(a));
         int rc = fill_args(h, a, 0); if (rc) return rc;

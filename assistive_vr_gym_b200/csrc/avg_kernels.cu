@@ -2233,8 +2233,137 @@ avg_reset_kernel(AvgResetArgs r) {
     scr_i[AVG_S_NSEP] = 0; scr_i[AVG_S_NC] = 0; scr_i[AVG_S_NCS] = 0; scr_i[AVG_S_NQ] = 0;    // no certificates / contacts carried over
 }
 
+// Start pose by inverse kinematics on the device (reference scratch_itch.py:243-253 -> util.ik_random_restarts, util.py:34-105:
+// PyBullet's calculateInverseKinematics with random rest poses, accepted when the end effector is within 0.03 of the target in
+// position and in quaternion distance, up to 40 restarts).  Restated as damped least squares over the 7 arm joints, one
+// thread per environment: dq = J^T (J J^T + lambda^2 I)^-1 e with the step clamped to 0.3 rad and the joints to their limits.
+// Runs after avg_reset_kernel for the environments it has just reset; the pool pose written there stays as the fallback.
+namespace {
+struct IkChain {
+    int n;
+    int body[8], qidx[8], dof[8];
+    float lo[8], hi[8];
+};
+__device__ void ik_fk(const KM& m, const IkChain& c, const float* q, const AvgResetTable* T, V3* jp, V3* ja, V3& pe, Q4& qe, V3& pb, Q4& qb) {
+    V3 p = mk3(0, 0, 0); Q4 r = mkq(0, 0, 0, 1);
+    for (int j = 0; j < c.n; ++j) {
+        const AvgBody* B = &m.body[c.body[j]];
+        const Q4 jq0 = qmul(r, ldq(B->ta_quat));
+        jp[j] = p + qrot(r, ld3(B->ta_pos));
+        const V3 ax = ld3(B->axis);
+        ja[j] = qrot(jq0, ax);
+        const Q4 jq = qmul(jq0, qaxis(ax, q[j]));
+        p = jp[j] + qrot(jq, ld3(B->tb_pos));
+        r = qnormalize(qmul(jq, ldq(B->tb_quat)));
+    }
+    pb = p; qb = r;                                              // pose of the last arm body (carries the end effector)
+    pe = p + qrot(r, ld3(T->ik_ee_frame));
+    qe = qnormalize(qmul(r, ldq(T->ik_ee_frame + 3)));
+}
+__device__ __forceinline__ V3 ik_rot_err(Q4 target, Q4 cur) {
+    Q4 d = qmul(target, qconj(cur));
+    if (d.w < 0) d = mkq(-d.x, -d.y, -d.z, -d.w);
+    const float sn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    if (sn < 1e-9f) return mk3(0, 0, 0);
+    const float ang = 2.0f * atan2f(sn, d.w) / sn;
+    return mk3(d.x * ang, d.y * ang, d.z * ang);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(64)
+avg_reset_ik_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env) return;
+    if (r.mask && !r.mask[e]) return;
+    const int v = r.variant[e];
+    const AvgResetTable* T = r.tables[v];
+    if (!T->ik_enabled || T->n_arm <= 0 || T->n_arm > 8) return;
+    const KM m = open_model(r.models[v]);
+    const uint32_t sd = r.seed, ue = (uint32_t)e, ep = (uint32_t)r.episode[e];
+    float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    IkChain c; c.n = T->n_arm;
+    for (int j = 0; j < c.n; ++j) {
+        c.dof[j] = T->arm_dof[j]; c.qidx[j] = T->arm_qidx[j];
+        const AvgDof* D = &m.dof[c.dof[j]];
+        c.body[j] = D->body;
+        const bool unlimited = D->lower > D->upper;                                  // continuous joint: +-2 pi for the IK, util.py:86-88
+        c.lo[j] = unlimited ? -6.283185307f : D->lower; c.hi[j] = unlimited ? 6.283185307f : D->upper;
+    }
+    // start target: centre + U(-range, range)^3 (scratch_itch.py:243,251), fixed orientation
+    V3 tp = ld3(T->ik_target);
+    tp.x += (2.0f * reset_u01(sd, ue, ep, 20) - 1.0f) * T->ik_range;
+    tp.y += (2.0f * reset_u01(sd, ue, ep, 21) - 1.0f) * T->ik_range;
+    tp.z += (2.0f * reset_u01(sd, ue, ep, 22) - 1.0f) * T->ik_range;
+    const Q4 tq = ldq(T->ik_target + 3);
+    float q[8], qbest[8]; float best_err = 3.0e38f;
+    V3 jp[8], ja[8], pe, pb; Q4 qe, qb;
+    const float lambda2 = 0.05f * 0.05f;
+    for (int restart = 0; restart < 40; ++restart) {                                  // max_ik_random_restarts
+        for (int j = 0; j < c.n; ++j) {                                               // random rest pose, util.py:100
+            const float a = fmaxf(c.lo[j], -3.14159265f), b = fminf(c.hi[j], 3.14159265f);
+            q[j] = a + (b - a) * reset_u01(sd, ue, ep, 32 + 8 * restart + j);
+        }
+        for (int it = 0; it < 200; ++it) {
+            ik_fk(m, c, q, T, jp, ja, pe, qe, pb, qb);
+            const V3 ev = tp - pe, ew = ik_rot_err(tq, qe);
+            if (dot(ev, ev) < 1e-8f && dot(ew, ew) < 1e-6f) break;
+            float J[6][8], A[6][6], y[6];
+            const float err[6] = {ev.x, ev.y, ev.z, ew.x, ew.y, ew.z};
+            for (int j = 0; j < c.n; ++j) {
+                const V3 jl = cross(ja[j], pe - jp[j]);
+                J[0][j] = jl.x; J[1][j] = jl.y; J[2][j] = jl.z; J[3][j] = ja[j].x; J[4][j] = ja[j].y; J[5][j] = ja[j].z;
+            }
+            for (int a = 0; a < 6; ++a) for (int b = 0; b <= a; ++b) {
+                float sacc = a == b ? lambda2 : 0.0f;
+                for (int j = 0; j < c.n; ++j) sacc = fmaf(J[a][j], J[b][j], sacc);
+                A[a][b] = sacc;
+            }
+            // Cholesky A = L L^T in place (lower), then forward / backward substitution
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b <= a; ++b) {
+                    float sacc = A[a][b];
+                    for (int k = 0; k < b; ++k) sacc -= A[a][k] * A[b][k];
+                    A[a][b] = a == b ? sqrtf(fmaxf(sacc, 1e-12f)) : sacc / A[b][b];
+                }
+            }
+            for (int a = 0; a < 6; ++a) { float sacc = err[a]; for (int k = 0; k < a; ++k) sacc -= A[a][k] * y[k]; y[a] = sacc / A[a][a]; }
+            for (int a = 5; a >= 0; --a) { float sacc = y[a]; for (int k = a + 1; k < 6; ++k) sacc -= A[k][a] * y[k]; y[a] = sacc / A[a][a]; }
+            float dq[8], mx = 0.0f;
+            for (int j = 0; j < c.n; ++j) {
+                float sacc = 0.0f;
+                for (int a = 0; a < 6; ++a) sacc = fmaf(J[a][j], y[a], sacc);
+                dq[j] = sacc; mx = fmaxf(mx, fabsf(sacc));
+            }
+            const float sc = mx > 0.3f ? 0.3f / mx : 1.0f;
+            for (int j = 0; j < c.n; ++j) q[j] = fminf(fmaxf(q[j] + sc * dq[j], c.lo[j]), c.hi[j]);
+        }
+        ik_fk(m, c, q, T, jp, ja, pe, qe, pb, qb);
+        const float epos = norm(tp - pe);
+        const float dm = sqrtf((tq.x - qe.x) * (tq.x - qe.x) + (tq.y - qe.y) * (tq.y - qe.y) + (tq.z - qe.z) * (tq.z - qe.z) + (tq.w - qe.w) * (tq.w - qe.w));
+        const float dp = sqrtf((tq.x + qe.x) * (tq.x + qe.x) + (tq.y + qe.y) * (tq.y + qe.y) + (tq.z + qe.z) * (tq.z + qe.z) + (tq.w + qe.w) * (tq.w + qe.w));
+        const float eq = fminf(dm, dp);
+        const bool ok = epos < 0.03f && eq < 0.03f;                                   // random_restart_threshold, util.py:51
+        if (ok || epos < best_err) { best_err = epos; for (int j = 0; j < c.n; ++j) qbest[j] = q[j]; }   // util.py:53-55: else the closest attempt
+        if (ok) break;
+    }
+    ik_fk(m, c, qbest, T, jp, ja, pe, qe, pb, qb);
+    for (int j = 0; j < c.n; ++j) { rec[AVG_E_Q + c.qidx[j]] = qbest[j]; rec[AVG_E_MTARGET + c.dof[j]] = qbest[j]; }
+    // the tool goes where init_tool puts it (world_creation.py:331-337): weld-parent frame o inverse of the tool's base frame
+    {
+        const AvgFrame* FW = &m.frame[AVG_F_WELD_PARENT]; const AvgFrame* FT = &m.frame[AVG_F_TOOL_BASE];
+        const V3 wp = pb + qrot(qb, ld3(FW->pos)); const Q4 wq = qnormalize(qmul(qb, ldq(FW->quat)));
+        const Q4 tbq = qnormalize(qmul(wq, qconj(ldq(FT->quat))));
+        const V3 tbp = wp - qrot(tbq, ld3(FT->pos));
+        float* tq7 = rec + AVG_E_Q + T->tool_qidx;
+        tq7[0] = tbp.x; tq7[1] = tbp.y; tq7[2] = tbp.z; tq7[3] = tbq.x; tq7[4] = tbq.y; tq7[5] = tbq.z; tq7[6] = tbq.w;
+    }
+    // inspection slots (the env-static pose block is unused by these tasks): drawn start target and the position error reached
+    rec[AVG_E_EBODY + 0] = tp.x; rec[AVG_E_EBODY + 1] = tp.y; rec[AVG_E_EBODY + 2] = tp.z; rec[AVG_E_EBODY + 3] = norm(tp - pe);
+}
+
 cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream) {
     avg_reset_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    if (r.any_ik) avg_reset_ik_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
     return cudaGetLastError();
 }
 

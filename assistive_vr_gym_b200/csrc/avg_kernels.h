@@ -84,6 +84,8 @@ cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blo
  * the per-variant reset tables, bumps their episode counters, empties their scratch state. */
 struct AvgResetArgs {
     const AvgResetTable* tables[AVG_K_MAX_VARIANTS];
+    const unsigned char* models[AVG_K_MAX_VARIANTS];   // device ModelBlobs (the on-device IK walks the arm chain)
+    int any_ik;                                        // some table has ik_enabled: launch avg_reset_ik_kernel after the draws
     int n_variants;
     int n_per_gender;                                  // variants per gender (1 ScratchItch; BedBathing: one per robot base pose)
     float* env; float* scratch; int32_t* variant; int32_t* episode;

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import capi
-from .compiler.reset import reset_table_bytes, sample_states
+from .compiler.reset import device_ik_setup, reset_table_bytes, sample_states
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 MAX_EPISODE_STEPS = 200      # reference __init__.py:21
@@ -73,7 +73,8 @@ def load_env_data(name: str):
 class BatchedAssistiveEnv:
     """N copies of one reference environment stepping in lock-step on one GPU."""
 
-    def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False):
+    def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False,
+                 device_ik: bool = False):
         if env_id not in REGISTRY:
             if env_id in _ALL_REFERENCE_IDS:
                 raise NotImplementedError(f"{env_id}: registered by the reference but not compiled yet "
@@ -89,9 +90,14 @@ class BatchedAssistiveEnv:
         self.device = torch.device("cuda", device)
         self.blobs, self.reset_data = load_env_data(self.spec["data"])
         self.sim = capi.Sim(self.num_envs, device)
+        # device_ik: `reset_device` solves every episode's start pose on the GPU for a freshly drawn start target
+        # (scratch_itch.py:243-253) instead of picking one of the pool's precomputed IK solutions; BedBathing's start target
+        # is fixed (bed_bathing.py:315), so its pool entry already is the solution and the option changes nothing there.
+        self.device_ik = bool(device_ik)
         for v, b in enumerate(self.blobs):
             self.sim.upload_model(v, b)
-            self.sim.upload_reset_table(v, reset_table_bytes(self.reset_data[v]))
+            ik = device_ik_setup(b, self.spec["task"], self.spec["robot"]) if self.device_ik else None
+            self.sim.upload_reset_table(v, reset_table_bytes(self.reset_data[v], ik))
         self.action_robot_len = 7
         self.action_human_len = 10 if self.spec["human_control"] else 0
         self.obs_robot_len = _OBS_LEN[self.spec["task"]][0]

@@ -48,7 +48,9 @@ float* avg_state_device_ptr(AvgHandle* h);
 /* Episode reset on the device: replaces ScratchItchEnv.reset (scratch_itch.py:130-273) for the environments whose byte
  * in `mask` (DEVICE, [n_env], NULL = all) is non-zero, without a host round trip: gender, impairment and its
  * parameters (world_creation.py:66-72), tremor amplitudes (:141), a start pose from the variant's pool of IK solutions
- * (scratch_itch.py:251-253), limb and the target point on it (scratch_itch.py:278, util.py:118,129), with
+ * (scratch_itch.py:251-253) -- or, when the variant's table sets ik_enabled, a freshly drawn start target and an arm
+ * pose solved for it on the device (util.ik_random_restarts, util.py:34-57) --, limb and the target point on it
+ * (scratch_itch.py:278, util.py:118,129), with
  * counter-based random numbers keyed by (seed, environment, episode count).  Needs avg_upload_reset_table for every
  * variant (HOST pointer to an AvgResetTable, include/avg_model.h).  obs (DEVICE, may be NULL) receives the initial
  * observation of the reset environments; other rows are left alone.  Asynchronous on `stream`. */

@@ -206,13 +206,21 @@ typedef struct AvgResetTable {
     float   hum_lower[8], hum_upper[8], hum_reset[8];
     float   limb_dims[2][2];              /* (length, radius) of upper arm and forearm (scratch_itch.py:277-280)                     */
     float   fin_open;                     /* gripper open position: 1.0 ScratchItch (scratch_itch.py:254), 1.1 BedBathing (bed_bathing.py:327) */
-    float   pad_f[3];
+    /* On-device IK for the start pose (scratch_itch.py:243-253 + util.py:34-105): when ik_enabled, the pool entry is only the
+     * fallback; each episode draws its own start target in the +-ik_range box around ik_target and solves the arm for it with
+     * damped least squares and up to 40 random restarts (same acceptance test as util.py:51: position and quaternion
+     * distance < 0.03).  ik_ee_frame = COM frame of the end-effector link (getLinkState of link 8 / 76) in the frame of
+     * dynamic body ik_ee_body. */
+    int32_t ik_enabled, ik_ee_body;
+    float   ik_range;
+    float   ik_target[8];                 /* pos(3) of the box centre, quat(4) target orientation, pad */
+    float   ik_ee_frame[8];               /* pos(3), quat(4), pad */
 } AvgResetTable;
 
 /* Counter-based random numbers of the device reset: draw k of episode `episode` of environment `env` under `seed`.
  * A 32-bit mix (murmur3 finaliser over a running hash); the numpy mirror in compiler/reset.py computes the same bits.
  * Draw indices: 0 gender, 1 impairment, 2 limit scale, 3 strength, 4..13 tremor, 14 limb, 15 point along the limb,
- * 16 angle around the limb, 17 start pose. */
+ * 16 angle around the limb, 17 start pose; on-device IK: 20..22 start target, 32 + 8 r + j rest pose of joint j in restart r. */
 #define AVG_RNG_MIX(h) do { (h) ^= (h) >> 16; (h) *= 0x85ebca6bu; (h) ^= (h) >> 13; (h) *= 0xc2b2ae35u; (h) ^= (h) >> 16; } while (0)
 
 /* ---- policy for on-device rollouts (reference enjoy_vr.py:77-117: actor_critic.act on VecNormalize'd observations) ----

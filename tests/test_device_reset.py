@@ -61,3 +61,59 @@ def test_device_reset_matches_host_mirror():
         o, r, d, info = env.step(torch.rand((n, 7), device="cuda") * 2 - 1)
     assert torch.isfinite(o).all() and torch.isfinite(r).all()
     env.close(); env_b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,ee_tol", [("ScratchItchJaco-v0", 0.03), ("ScratchItchPR2-v0", 0.03)])
+def test_device_ik_start_poses(env_id, ee_tol):
+    """device_ik=True: every reset environment gets its own start target (centre +- 0.05, scratch_itch.py:243,251) and an arm
+    pose solved for it on the GPU.  Checked with the oracle's forward kinematics: the end-effector link reaches the drawn
+    target within the reference's acceptance test (util.py:51: 0.03 in position and in quaternion distance) in >= 97 % of
+    the environments (the reference, too, falls back to its closest attempt after 40 restarts), joints inside their limits,
+    the tool exactly in the gripper, start poses all different, and the episode steps normally afterwards."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from assistive_vr_gym_b200 import make
+    from assistive_vr_gym_b200.compiler import xform as X
+    from assistive_vr_gym_b200.compiler.reset import device_ik_setup
+    from oracle.oracle import Oracle, env_to_f64
+    n = 2048
+    env = make(env_id, num_envs=n, device=0, seed=3, device_ik=True)
+    env.reset_device(seed=99)
+    torch.cuda.synchronize()
+    st = env.get_state(); variants = env.sim.get_variants()
+    oracles = {}
+    ok = 0; poses = set()
+    for e in range(0, n, 8):
+        v = int(variants[e])
+        if v not in oracles:
+            oracles[v] = (Oracle(env.blobs[v]), device_ik_setup(env.blobs[v], env.spec["task"], env.spec["robot"]))
+        o, ik = oracles[v]
+        rec = env_to_f64(st[e]).copy()
+        target = rec[124:127]
+        assert np.all(np.abs(target - ik["target_pos"]) <= 0.05 + 1e-6)
+        bp = o.body_pose(rec, ik["ee_body"])
+        ee_p, ee_q = X.tf_mul(bp[:3], bp[3:], ik["ee_pos"], ik["ee_quat"])
+        epos = np.linalg.norm(ee_p - target)
+        eq = min(np.linalg.norm(ee_q - ik["target_quat"]), np.linalg.norm(ee_q + ik["target_quat"]))
+        ok += int(epos < ee_tol and eq < 0.03)
+        assert abs(epos - rec[127]) < 1e-4                                 # the error the kernel reports is the real one
+        d = o.model["dofs"]
+        for i in range(int(o.model["header"]["n_jdof"])):
+            if 0 <= d[i]["action"] < 7:
+                q = rec[int(o.model["bodies"][int(d[i]["body"])]["qidx"])]
+                if d[i]["lower"] <= d[i]["upper"]:
+                    assert d[i]["lower"] - 1e-5 <= q <= d[i]["upper"] + 1e-5
+                assert rec[64 + i] == q                                    # motor target = start pose
+        wp, tb = o.frame(rec, 2), o.frame(rec, 1)
+        assert np.linalg.norm(wp[:3] - tb[:3]) < 1e-5                      # tool welded where init_tool puts it
+        poses.add(tuple(np.round(rec[:7], 4)))
+    total = len(range(0, n, 8))
+    assert ok >= 0.97 * total, (ok, total)
+    assert len(poses) >= 0.95 * total
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(5):
+        obs, rew, done, info = env.step(torch.rand((n, 7), device="cuda", generator=g) * 2 - 1)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    env.close()
