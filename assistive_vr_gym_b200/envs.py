@@ -133,7 +133,9 @@ class BatchedAssistiveEnv:
     def reset_device(self, mask=None, seed: Optional[int] = None):
         """Reset on the GPU (avg_reset): `mask` = CUDA bool/uint8 tensor [N] of environments to restart (None = all).
         No host round trip, so it can follow a step directly (per-environment auto-reset for training loops); the
-        draws are those of `reset()` but from the counter-based generator of the device sampler."""
+        draws are those of `reset()` but from the counter-based generator of the device sampler.  The TimeLimit(200)
+        bookkeeping of `step()` is one counter for the lock-stepped batch: it restarts only with mask=None; a caller that
+        restarts subsets tracks their episode lengths itself (AVG_E_ITERATION in the state record counts them per env)."""
         torch = self.torch
         if seed is None:
             seed = int(self.np_random.randint(1 << 31)) if not hasattr(self, "_device_seed") else self._device_seed
