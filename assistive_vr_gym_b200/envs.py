@@ -128,6 +128,7 @@ class BatchedAssistiveEnv:
         """scratch_itch.py:130-273, batched: samples every env's post-reset state on the host and uploads it."""
         env, variant = sample_states(self.reset_data, self.num_envs, self.np_random, genders)
         self.set_state(env, variant)
+        self._last_reset = "host"
         return self.obs
 
     def reset_device(self, mask=None, seed: Optional[int] = None):
@@ -147,6 +148,7 @@ class BatchedAssistiveEnv:
         self.sim.reset_device(mptr, seed, self.obs.data_ptr(), self._stream())
         if mask is None:
             self.elapsed = 0
+            self._last_reset = "device"
         self.variants = None          # now lives on the device only
         self._needs_reset = False
         return self.obs
@@ -205,9 +207,12 @@ class BatchedAssistiveEnv:
                 "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len,
                 "TimeLimit.truncated": timeout}
         if timeout:
-            if self.auto_reset:
+            if self.auto_reset:                # gym vector-env convention: the returned observation starts the next episode
                 info["terminal_observation"] = self.obs.clone()
-                self.reset()
+                if getattr(self, "_last_reset", "host") == "device":
+                    self.reset_device()        # no host round trip (counter-based draws, next episode index)
+                else:
+                    self.reset()
             else:
                 self._needs_reset = False      # like gym, stepping past the limit is the caller's business
         return self.obs, self.reward, done, info

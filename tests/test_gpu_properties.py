@@ -185,3 +185,26 @@ def test_step_is_cuda_graph_capturable(torch_cuda, chunks, monkeypatch):
     assert torch.equal(env.obs, ref.obs) and torch.equal(env.reward, ref.reward)
     assert np.array_equal(env.get_state()[:, :64], ref.get_state()[:, :64])
     env.close(); ref.close()
+
+
+def test_auto_reset_on_the_device(torch_cuda):
+    """auto_reset=True after a device reset: step 200 reports done (TimeLimit), hands back the terminal observation in info
+    and the first observation of the next episode as `obs`, restarted on the GPU (next episode index: different draws),
+    and the batch keeps stepping."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 256
+    env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4, auto_reset=True, device_ik=True)
+    first = env.reset_device(seed=11).clone()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    for t in range(200):
+        obs, rew, done, info = env.step(torch.rand((n, 7), device="cuda", generator=g) * 2 - 1)
+        assert bool(done.all()) == (t == 199)
+    assert "terminal_observation" in info and info["terminal_observation"].shape == obs.shape
+    assert env.elapsed == 0
+    st = env.get_state()
+    assert np.all(st.view(np.int32)[:, 152] == 0)                 # AVG_E_ITERATION: a fresh episode in every environment
+    assert not torch.equal(obs, first) and not torch.equal(obs, info["terminal_observation"])
+    obs2, rew2, done2, info2 = env.step(torch.zeros((n, 7), device="cuda"))
+    assert not bool(done2.any()) and torch.isfinite(obs2).all()
+    env.close()
