@@ -74,13 +74,15 @@ def test_state_invariants_at_scale(torch_cuda):
     assert np.percentile(np.linalg.norm(obs[:, 0:3], axis=1), 99) < 1.2
 
 
-def test_step_host_equals_device_step(torch_cuda):
+@pytest.mark.parametrize("env_id,n", [("ScratchItchJaco-v0", 257), ("BedBathingPR2-v0", 130), ("ScratchItchPR2Human-v0", 66), ("ScratchItchJaco-v0", 40000)])
+def test_step_host_equals_device_step(torch_cuda, env_id, n):
+    """The host-buffer entry point (pinned staging, two chunks on two streams from 16384 envs up) returns bit for bit what the
+    device-resident step returns (itself two half batches on two streams from 32768 envs up)."""
     torch = torch_cuda
     from assistive_vr_gym_b200 import make
-    n = 257
-    a = np.random.RandomState(0).uniform(-1, 1, (3, n, 7)).astype(np.float32)
-    e1 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e1.reset()
-    e2 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e2.reset()
+    e1 = make(env_id, num_envs=n, device=0, seed=4); e1.reset()
+    e2 = make(env_id, num_envs=n, device=0, seed=4); e2.reset()
+    a = np.random.RandomState(0).uniform(-1, 1, (3, n, e1.sim.n_actions)).astype(np.float32)
     for t in range(3):
         o1, r1, d1, i1 = e1.step(torch.as_tensor(a[t], device="cuda"))
         o2, r2, d2, i2 = e2.step_host(a[t])
