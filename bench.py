@@ -340,6 +340,33 @@ def main():
                         "note": "synthetic-policy rollout (%d-64-64-7 tanh actor, fused inference), full episode from a device reset" % benv.obs_robot_len})
             benv.close()
 
+    # ---- mixed-task batch (extra; BASELINE.json configs[3] "mixed-task batch (all robots)"): one homogeneous sub-batch per
+    #      registered id, each its own handle, stepped concurrently on separate streams (assistive_vr_gym_b200/mixed.py) ----
+    if not args.no_episode:
+        from assistive_vr_gym_b200.mixed import MixedBatch
+        per_id = 8192
+        mb = MixedBatch(envs_per_id=per_id, device=local_rank, seed=1001 + 100 * rank)
+        mb.reset_device(seed=1001 + rank)
+        for k in range(3):
+            mb.step(mb.sample_actions(gen))
+            for e_ in mb.envs.values():
+                e_.elapsed = 0
+        barrier()
+        m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for k in range(50):
+            mb.step(mb.sample_actions(gen))
+            for e_ in mb.envs.values():
+                e_.elapsed = 0
+        m1.record(stream)
+        barrier()
+        tm = torch.tensor([m0.elapsed_time(m1)], device=dev)
+        if distributed:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        bed.append({"env_id": "mixed: " + ", ".join(mb.env_ids), "envs_per_gpu": mb.num_envs, "value": mb.num_envs * world * 50 / (float(tm.item()) * 1e-3),
+                    "unit": UNIT, "steps": 50, "note": "%d ids x %d envs, one handle and one stream per id, random actions, steps 3-52 after a device reset" % (len(mb.env_ids), per_id)})
+        mb.close()
+
     # ---- BASELINE.json configs[4] (ScratchItchJacoHuman-v0, 4096 envs per GPU, both halves of the action driven) and
     #      configs[0] (one ScratchItchJaco-v0 environment through the reference-typed NumPy API, 200 steps) as extras --------
     if not args.no_episode:

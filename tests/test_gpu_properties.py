@@ -210,3 +210,29 @@ def test_auto_reset_on_the_device(torch_cuda):
     obs2, rew2, done2, info2 = env.step(torch.zeros((n, 7), device="cuda"))
     assert not bool(done2.any()) and torch.isfinite(obs2).all()
     env.close()
+
+
+def test_mixed_task_batch(torch_cuda):
+    """One sub-batch per id on separate streams (mixed.py): every sub-batch returns exactly what the same id returns when
+    stepped alone (handles are independent), with the right shapes per id."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    from assistive_vr_gym_b200.mixed import MixedBatch
+    ids = ["ScratchItchJaco-v0", "BedBathingPR2-v0", "ScratchItchPR2Human-v0", "BedBathingJacoHuman-v0"]
+    n = 96
+    mb = MixedBatch(ids, envs_per_id=n, device=0, seed=50)
+    mb.reset_device(seed=8)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    acts = [mb.sample_actions(g) for _ in range(4)]
+    for a in acts:
+        out = mb.step(a)
+    torch.cuda.synchronize()
+    for k, i in enumerate(ids):
+        solo = make(i, num_envs=n, device=0, seed=50 + k)
+        solo.reset_device(seed=8)
+        for a in acts:
+            o, r, d, info = solo.step(a[i])
+        assert out[i][0].shape == (n, solo.sim.n_obs) and acts[0][i].shape == (n, solo.sim.n_actions)
+        assert torch.equal(out[i][0], o) and torch.equal(out[i][1], r)
+        solo.close()
+    mb.close()
