@@ -140,10 +140,33 @@ def run_reference(args, rank: int, world: int):
             "config": {"workload": f"{ENV_ID}, random actions, CPU oracle port of the path (PyBullet itself is not installable here)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f", median of {reps}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything libraries write to fd 1 from here on (NCCL prints its version banner there) goes to stderr; the JSON line
+    is written to the saved descriptor, so stdout carries exactly ONE line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -452,7 +475,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, c, sample = cpu_oracle_throughput(192, 200)         # ~10-20 s of CPU work on the box's cores
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if distributed:
         dist.destroy_process_group()
 
