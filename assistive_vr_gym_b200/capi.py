@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AVG_B200_LIB") or os.path.join(_HERE, "libavg_b200.so")   # override: A/B builds during tuning
 
 EXPORTS = [
-    "avg_create", "avg_destroy", "avg_last_error", "avg_upload_model", "avg_set_state", "avg_get_state", "avg_get_variants",
+    "avg_create", "avg_destroy", "avg_last_error", "avg_upload_model", "avg_set_state", "avg_get_state", "avg_get_variants", "avg_set_time_limit",
     "avg_state_device_ptr", "avg_reset_obs", "avg_step", "avg_step_host", "avg_enable_debug", "avg_get_contacts",
     "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
     "avg_bytes_per_env_step", "avg_arm_limit_logits", "avg_alloc_host", "avg_free_host", "avg_upload_reset_table", "avg_reset",
@@ -52,6 +52,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_set_state.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.avg_get_state.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.avg_get_variants.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_set_time_limit.argtypes = [vp, ctypes.c_int]
     lib.avg_state_device_ptr.argtypes = [vp]; lib.avg_state_device_ptr.restype = vp
     lib.avg_reset_obs.argtypes = [vp, vp, vp]
     lib.avg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -138,6 +139,9 @@ class Sim:
         out = np.zeros((count, self.lib.avg_env_stride()), dtype=np.float32)
         self._check(self.lib.avg_get_state(self.h, begin, count, out.ctypes.data), "avg_get_state")
         return out
+
+    def set_time_limit(self, max_episode_steps: int):
+        self._check(self.lib.avg_set_time_limit(self.h, int(max_episode_steps)), "avg_set_time_limit")
 
     def get_variants(self, begin: int = 0, count: int | None = None) -> np.ndarray:
         count = self.n_env - begin if count is None else count

@@ -44,6 +44,7 @@ struct AvgHandle {
     bool rtab_ik[AVG_K_MAX_VARIANTS] = {}; bool any_ik = false;     // reset tables that ask for the on-device IK start pose
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // avg_step on two streams: fork from / join into the caller's stream
     int step_chunks = 1;
+    int time_limit = 0;                                // avg_set_time_limit
     unsigned long long* d_cnt = nullptr;               // AVG_DBG & 32 (development aid)
     std::string err;
 };
@@ -215,6 +216,12 @@ float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset);
 
+int avg_set_time_limit(AvgHandle* h, int max_episode_steps) {
+    if (!h || max_episode_steps < 0) return -1;
+    h->time_limit = max_episode_steps;
+    return 0;
+}
+
 int avg_get_variants(AvgHandle* h, int env_begin, int env_count, int32_t* variants) {
     if (!h || !variants) return -1;
     if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_variants: range");
@@ -291,7 +298,7 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset) {
     if (!h->have[0]) return fail(h, -1, "no model uploaded for variant 0");
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) a.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
-    a.slot = h->slot; a.task = h->task;
+    a.slot = h->slot; a.task = h->task; a.time_limit = h->time_limit;
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
     a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity;

@@ -1832,7 +1832,9 @@ avg_epilogue_kernel(AvgStepArgs a) {
         const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;
         a.info[2 * e] = total_force_on_human;
         a.info[2 * e + 1] = success;
-        if (a.done) a.done[e] = 0;                            // the env itself never terminates, scratch_itch.py:78
+        // the env itself never terminates (scratch_itch.py:78); with a time limit set, `done` is gym's TimeLimit wrapper
+        // (__init__.py:21) evaluated per environment on its own step counter, so staggered episodes need no host bookkeeping
+        if (a.done) a.done[e] = (a.time_limit > 0 && env_i[AVG_E_ITERATION] + 1 >= a.time_limit) ? 1 : 0;
         if (a.terms) {
             float* tr = a.terms + 8 * (size_t)e;
             tr[0] = total_force_on_human; tr[1] = success; tr[2] = tool_force; tr[3] = tool_force_at_target;
@@ -2124,7 +2126,7 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
         const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;          // bed_bathing.py:72
         a.info[2 * e] = total_force_on_human;
         a.info[2 * e + 1] = success;
-        if (a.done) a.done[e] = 0;
+        if (a.done) a.done[e] = (a.time_limit > 0 && env_i[AVG_E_ITERATION] + 1 >= a.time_limit) ? 1 : 0;     // TimeLimit per environment, see avg_epilogue_kernel
         if (a.terms) {
             float* tr = a.terms + 8 * (size_t)e;
             tr[0] = total_force_on_human; tr[1] = success; tr[2] = tool_force; tr[3] = tool_force_on_human;

@@ -67,6 +67,7 @@ struct AvgStepArgs {
     int maxblk;                                        // largest articulation block (dofs) over the uploaded variants
     int dbg;                                           // development switches (AVG_DBG), 0 in production
     int task;                                          // AVG_TASK_* of the uploaded models: selects the epilogue / reset-observation kernel
+    int time_limit;                                    // > 0: done[e] = (env-steps of the episode >= time_limit), gym TimeLimit per environment; 0: done = 0
     AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
     int* np_count;                                     // item counter: filled by the collide kernel, read by the narrowphase kernel, zeroed by the dynamics kernel
     int np_capacity;

@@ -106,7 +106,12 @@ class BatchedAssistiveEnv:
         assert self.sim.n_obs == self.obs_robot_len + self.obs_human_len
         self.action_space = Box(self.sim.n_actions)
         self.observation_space = Box(self.sim.n_obs)
+        # auto_reset: False | True (lock-stepped episodes: the whole batch restarts when the shared TimeLimit counter hits 200)
+        # | "device" (staggered episodes: TimeLimit per environment on the device, the environments whose `done` byte is
+        # set restart inside step() through avg_reset with that byte array as the mask -- no host round trip)
         self.auto_reset = auto_reset
+        if auto_reset == "device":
+            self.sim.set_time_limit(MAX_EPISODE_STEPS)
         self.seed(seed)
         n = self.num_envs
         with torch.cuda.device(self.device):
@@ -199,6 +204,19 @@ class BatchedAssistiveEnv:
             raise ValueError(f"expected actions of shape {(self.num_envs, self.sim.n_actions)}, got {tuple(actions.shape)}")
         self.sim.step(actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done_dev.data_ptr(),
                       self.info_dev.data_ptr(), self._stream())
+        if self.auto_reset == "device":
+            if not hasattr(self, "terminal_obs"):
+                self.terminal_obs = torch.empty_like(self.obs)
+            self.terminal_obs.copy_(self.obs)                       # last observation of the episodes that end at this step
+            if not hasattr(self, "_device_seed"):
+                self._device_seed = int(self.np_random.randint(1 << 31))
+            self.sim.reset_device(self.done_dev.data_ptr(), self._device_seed, self.obs.data_ptr(), self._stream())
+            done = self.done_dev.bool()
+            return self.obs, self.reward, done, {
+                "total_force_on_human": self.info_dev[:, 0], "task_success": self.info_dev[:, 1].to(torch.int32),
+                "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
+                "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len,
+                "TimeLimit.truncated": done, "terminal_observation": self.terminal_obs}
         self.elapsed += 1
         timeout = self.elapsed >= MAX_EPISODE_STEPS                 # gym TimeLimit, __init__.py:21
         done = self.done_dev.bool() | timeout

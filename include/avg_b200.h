@@ -39,6 +39,11 @@ int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_r
 /* Replaces getJointStates / getBasePositionAndOrientation / getBaseVelocity bulk reads: copies env records to HOST
  * memory.  Synchronous (waits for the stream work issued so far on the default stream of the handle). */
 int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records);
+/* gym's TimeLimit wrapper (`max_episode_steps=200`, assistive_gym/__init__.py:21) evaluated on the device: with a limit > 0
+ * avg_step writes done[e] = 1 when environment e has taken that many env-steps since its last reset (the environments
+ * themselves never terminate, scratch_itch.py:78); that byte array is a valid `mask` for avg_reset, so staggered episodes
+ * restart without a host round trip.  0 (default) switches it off: done = 0. */
+int avg_set_time_limit(AvgHandle* h, int max_episode_steps);
 /* Model variant of each environment (gender x robot base pose; chosen by avg_set_state or drawn by avg_reset) to HOST
  * memory: what the reference stores as `gender` in setup.pkl (scratch_itch.py:269-272).  Synchronous. */
 int avg_get_variants(AvgHandle* h, int env_begin, int env_count, int32_t* variants);

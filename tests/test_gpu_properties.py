@@ -236,3 +236,33 @@ def test_mixed_task_batch(torch_cuda):
         assert torch.equal(out[i][0], o) and torch.equal(out[i][1], r)
         solo.close()
     mb.close()
+
+
+def test_staggered_episodes_with_device_time_limit(torch_cuda):
+    """auto_reset="device": gym's TimeLimit(200) is evaluated per environment on the device (avg_set_time_limit), and the
+    environments whose done byte is set restart inside step() with that byte array as avg_reset's mask.  Half of the batch
+    is restarted by hand after 50 steps, so the halves end their episodes 50 steps apart."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 64
+    env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=6, auto_reset="device", device_ik=True)
+    env.reset_device(seed=21)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    first_half = torch.zeros(n, dtype=torch.uint8, device="cuda"); first_half[: n // 2] = 1
+    ends = []
+    for t in range(1, 261):
+        obs, rew, done, info = env.step(torch.rand((n, 7), device="cuda", generator=g) * 2 - 1)
+        d = done.cpu().numpy()
+        if d.any():
+            ends.append((t, d.copy()))
+            to = info["terminal_observation"]
+            assert not torch.equal(to[done], obs[done])                       # restarted rows carry the next episode's first observation
+            assert torch.equal(to[~done], obs[~done])
+            it = env.get_state().view(np.int32)[:, 152]
+            assert np.all(it[d] == 0) and np.all(it[~d] > 0)                  # AVG_E_ITERATION: fresh episodes exactly where done was set
+        if t == 50:
+            env.reset_device(mask=first_half)
+    assert [e[0] for e in ends] == [200, 250]
+    assert ends[0][1][n // 2:].all() and not ends[0][1][: n // 2].any()       # second half: 200 steps since the common reset
+    assert ends[1][1][: n // 2].all() and not ends[1][1][n // 2:].any()       # first half: 200 steps since its own restart
+    env.close()
