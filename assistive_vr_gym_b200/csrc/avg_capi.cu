@@ -39,7 +39,9 @@ struct AvgHandle {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     // narrowphase work queues: set 0 for avg_step and even chunks of avg_step_host, set 1 for odd chunks (second stream)
-    AvgNpItem* d_npq[2] = {nullptr, nullptr}; int* d_npc[2] = {nullptr, nullptr}; int np_capacity = 0;
+    AvgNpItem* d_npq[4] = {nullptr, nullptr, nullptr, nullptr}; int* d_npc[4] = {nullptr, nullptr, nullptr, nullptr}; int np_capacity = 0;
+    cudaStream_t xstream[2] = {nullptr, nullptr};      // third / fourth stream of avg_step (AVG_STEP_CHUNKS=3|4)
+    cudaEvent_t ev_xjoin[2] = {nullptr, nullptr};
     cudaStream_t stream2 = nullptr;
     bool rtab_ik[AVG_K_MAX_VARIANTS] = {}; bool any_ik = false;     // reset tables that ask for the on-device IK start pose
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // avg_step on two streams: fork from / join into the caller's stream
@@ -97,7 +99,7 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
     h->np_capacity = n_env * 12 + 4096;                /* 1-6 candidates per environment and sub-step survive the culls (more late in
                                                           random-action episodes); overflow is flagged, never silent */
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (cudaMalloc(&h->d_npq[k], sizeof(AvgNpItem) * (size_t)h->np_capacity) != cudaSuccess || cudaMalloc(&h->d_npc[k], 2 * sizeof(int)) != cudaSuccess) {
             g_slot_used[slot] = false; delete h;
             return fail(nullptr, -2, "avg_create: cudaMalloc of the narrowphase queue failed");
@@ -111,7 +113,8 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     /* avg_step splits large batches into two halves on two streams: the kernels of one half fill the tails (and the
        sparsely populated narrowphase kernel) of the other.  AVG_STEP_CHUNKS=1 restores the single-stream sequence. */
     h->step_chunks = n_env >= 32768 ? 2 : 1;
-    { const char* c = getenv("AVG_STEP_CHUNKS"); if (c && atoi(c) > 0) h->step_chunks = atoi(c) > 1 ? 2 : 1; }
+    { const char* c = getenv("AVG_STEP_CHUNKS"); if (c && atoi(c) > 0) h->step_chunks = atoi(c) > 4 ? 4 : atoi(c); }
+    for (int k = 0; k < 2; ++k) { cudaStreamCreateWithFlags(&h->xstream[k], cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_xjoin[k], cudaEventDisableTiming); }
     *out = h;
     return 0;
 }
@@ -125,7 +128,8 @@ int avg_destroy(AvgHandle* h) {
         fprintf(stderr, "[avg narrowphase counters] items %llu, rejected by the plane test %llu, GJK calls %llu, GJK iterations %llu, SAT fallbacks %llu, contacts %llu, cycles/item mean %llu max %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[0] ? c[6] / c[0] : 0ull, c[7]);
         cudaFree(h->d_cnt);
     }
-    for (int k = 0; k < 2; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
+    for (int k = 0; k < 4; ++k) { cudaFree(h->d_npq[k]); cudaFree(h->d_npc[k]); }
+    for (int k = 0; k < 2; ++k) { if (h->xstream[k]) cudaStreamDestroy(h->xstream[k]); if (h->ev_xjoin[k]) cudaEventDestroy(h->ev_xjoin[k]); }
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -333,19 +337,26 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
         h->launches += avg_kernels_per_step(h->substeps);
         return 0;
     }
-    /* two halves, two streams (still asynchronous and capturable: event fork / join around the second stream) */
-    const int half = ((h->n_env / 2) + 3) & ~3;
-    AvgStepArgs b; memset(&b, 0, sizeof(b));
-    rc = fill_args(h, b, 1); if (rc) return rc;
-    b.actions = actions; b.obs = obs; b.reward = reward; b.done = done; b.info = info;
-    a.env_begin = 0; a.env_end = half; b.env_begin = half; b.env_end = h->n_env;
+    /* k equal parts on k streams (k = 2 by default; still asynchronous and capturable: event fork / join around the extra streams) */
+    const int k = h->step_chunks;
+    const int part = ((h->n_env + k - 1) / k + 3) & ~3;
     AVG_CHECK(h, cudaEventRecord(h->ev_fork, (cudaStream_t)stream));
-    AVG_CHECK(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-    AVG_CHECK(h, avg_launch_step(b, h->substeps, h->stream2));
-    AVG_CHECK(h, cudaEventRecord(h->ev_join, h->stream2));
-    AVG_CHECK(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
-    h->launches += 2 * avg_kernels_per_step(h->substeps);
+    for (int c = 0; c < k; ++c) {
+        AvgStepArgs b; memset(&b, 0, sizeof(b));
+        rc = fill_args(h, b, c); if (rc) return rc;
+        b.actions = actions; b.obs = obs; b.reward = reward; b.done = done; b.info = info;
+        b.env_begin = c * part; b.env_end = (c + 1) * part < h->n_env ? (c + 1) * part : h->n_env;
+        if (b.env_begin >= b.env_end) break;
+        cudaStream_t st = c == 0 ? (cudaStream_t)stream : (c == 1 ? h->stream2 : h->xstream[c - 2]);
+        if (c > 0) AVG_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
+        AVG_CHECK(h, avg_launch_step(b, h->substeps, st));
+        if (c > 0) {
+            cudaEvent_t ej = c == 1 ? h->ev_join : h->ev_xjoin[c - 2];
+            AVG_CHECK(h, cudaEventRecord(ej, st));
+            AVG_CHECK(h, cudaStreamWaitEvent((cudaStream_t)stream, ej, 0));
+        }
+        h->launches += avg_kernels_per_step(h->substeps);
+    }
     return 0;
 }
 

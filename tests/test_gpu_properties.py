@@ -152,7 +152,7 @@ def test_separating_axis_cache_only_skips_work(torch_cuda):
     assert np.array_equal(out[0][1], out[1][1])
 
 
-@pytest.mark.parametrize("chunks", [1, 2])
+@pytest.mark.parametrize("chunks", [1, 2, 4])
 def test_step_is_cuda_graph_capturable(torch_cuda, chunks, monkeypatch):
     """the step is a fixed launch sequence with no hidden synchronisation, so it can be captured once and
     replayed; replays are bit-identical to eager steps.  chunks = 2: the two-stream form large batches use (half batches on
