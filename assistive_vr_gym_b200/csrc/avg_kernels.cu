@@ -44,6 +44,9 @@
 #ifndef AVG_OCC_SOLVE
 #define AVG_OCC_SOLVE 32
 #endif
+#ifndef AVG_REDUX
+#define AVG_REDUX 2               /* solver: J.dv of dense rows by an integer redux.sync (1: fixed point 2^-22 m/s, 2: scaled to the largest product) instead of a 5-stage float butterfly (0) */
+#endif
 #ifndef AVG_WELD_BATCH
 #define AVG_WELD_BATCH 1          /* dynamics kernel: the six weld rows built together with one packed reduction (0: row by row) */
 #endif
@@ -1532,6 +1535,30 @@ __device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, 
 // =================================================================================================================
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
+// J.dv over the warp, the inner operation of every dense Gauss-Seidel row.  A float butterfly costs five DEPENDENT shuffle +
+// add stages (~150 cycles on the row-to-row dependency chain that bounds this kernel, profiles/ncu_full_r1p.txt).
+// AVG_REDUX = 2 (default): two redux.sync.  The first takes the largest |product| of the warp (max over the float bit
+//   patterns, monotonic for non-negative floats), which fixes a power-of-two scale such that every lane's product rounds
+//   to an integer below 2^25 -- the 24-25 significant bits a float sum keeps, at any magnitude -- and the 32-lane sum stays
+//   below 2^30; the second adds the integers, exactly and order-independently (bit-deterministic by construction).
+// AVG_REDUX = 1: one redux.sync at a fixed scale of 2^-22 m/s.  3 % faster, but the PR2's finger tips (1.5e-5 kg m^2 under a
+//   500 N m motor) reach intermediate J.dv of tens of m/s inside a sweep, so a fixed range is not safe for every model.
+// AVG_REDUX = 0: the float butterfly.
+__device__ __forceinline__ float dense_dot(float j, float dv) {
+#if AVG_REDUX == 1
+    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(j * dv * 4194304.0f)) * (1.0f / 4194304.0f);
+#elif AVG_REDUX == 2
+    const float x = j * dv;
+    const unsigned m = __reduce_max_sync(AVG_FULL, __float_as_uint(x) & 0x7fffffffu);
+    const int e = max((int)(m >> 23), 40);                                   // biased exponent of the largest |x|: |x| < 2^(e - 126) in every lane
+    const float scale = __uint_as_float((unsigned)(278 - e) << 23);          // 2^(151 - e)
+    const float inv = __uint_as_float((unsigned)(e - 24) << 23);             // 2^(e - 151)
+    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(x * scale)) * inv;
+#else
+    return warp_sum(j * dv);
+#endif
+}
+
 template <int MAXBLK>
 __global__ void __launch_bounds__(32, AVG_OCC_SOLVE)
 avg_solve_kernel(AvgStepArgs a) {
@@ -1619,7 +1646,7 @@ avg_solve_kernel(AvgStepArgs a) {
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
             const float4 ra = s.rd[d][0];                            // {target, 1/diag, diag, max}: the weld clamp is symmetric (+-max)
-            const float jdv = warp_sum(jw[d] * dv);
+            const float jdv = dense_dot(jw[d], dv);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lamW[d]), -ra.w), ra.w);
             const float delta = sum - lamW[d];
             lamW[d] = sum;
@@ -1631,7 +1658,7 @@ avg_solve_kernel(AvgStepArgs a) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
-            const float jdv = warp_sum(*jp * dv);
+            const float jdv = dense_dot(*jp, dv);
             const float lam = __shfl_sync(AVG_FULL, lamD, d);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), ra.z), ra.w);
             const float delta = sum - lam;
@@ -1645,7 +1672,7 @@ avg_solve_kernel(AvgStepArgs a) {
             const int par = __float_as_int(rb.w);
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
-            const float jdv = warp_sum(*jp * dv);
+            const float jdv = dense_dot(*jp, dv);
             const float lam = __shfl_sync(AVG_FULL, lamD, d);
             const float lim = rb.y * __shfl_sync(AVG_FULL, lamD, par);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -lim), lim);
