@@ -621,10 +621,11 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
         const float c[3] = {b0.x, b0.y, b0.z}, hh[3] = {b0.w + b1.z, b1.x + b1.z, b1.y + b1.z};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            float lo = v ? c[k] - hh[k] : 3.0e38f, hi = v ? c[k] + hh[k] : -3.0e38f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(AVG_FULL, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(AVG_FULL, hi, o)); }
-            ulo[k] = lo; uhi[k] = hi;
+            const float lo = v ? c[k] - hh[k] : 3.0e38f, hi = v ? c[k] + hh[k] : -3.0e38f;
+            // min / max over the warp with one redux.sync each, on the order-preserving integer image of the floats
+            auto key = [](float f) { const unsigned b = __float_as_uint(f); return b ^ ((unsigned)((int)b >> 31) | 0x80000000u); };
+            auto unkey = [](unsigned q) { return __uint_as_float(q ^ ((q >> 31) ? 0x80000000u : 0xffffffffu)); };
+            ulo[k] = unkey(__reduce_min_sync(AVG_FULL, key(lo))); uhi[k] = unkey(__reduce_max_sync(AVG_FULL, key(hi)));
         }
     }
     int nnear = 0;
@@ -1075,6 +1076,30 @@ avg_narrow_kernel(AvgStepArgs a) {
     }
 }
 
+// J.dv over the warp, the inner operation of every dense Gauss-Seidel row.  A float butterfly costs five DEPENDENT shuffle +
+// add stages (~150 cycles on the row-to-row dependency chain that bounds this kernel, profiles/ncu_full_r1p.txt).
+// AVG_REDUX = 2 (default): two redux.sync.  The first takes the largest |product| of the warp (max over the float bit
+//   patterns, monotonic for non-negative floats), which fixes a power-of-two scale such that every lane's product rounds
+//   to an integer below 2^25 -- the 24-25 significant bits a float sum keeps, at any magnitude -- and the 32-lane sum stays
+//   below 2^30; the second adds the integers, exactly and order-independently (bit-deterministic by construction).
+// AVG_REDUX = 1: one redux.sync at a fixed scale of 2^-22 m/s.  3 % faster, but the PR2's finger tips (1.5e-5 kg m^2 under a
+//   500 N m motor) reach intermediate J.dv of tens of m/s inside a sweep, so a fixed range is not safe for every model.
+// AVG_REDUX = 0: the float butterfly.
+__device__ __forceinline__ float dense_dot(float j, float dv) {
+#if AVG_REDUX == 1
+    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(j * dv * 4194304.0f)) * (1.0f / 4194304.0f);
+#elif AVG_REDUX == 2
+    const float x = j * dv;
+    const unsigned m = __reduce_max_sync(AVG_FULL, __float_as_uint(x) & 0x7fffffffu);
+    const unsigned ee = max(m & 0x7f800000u, 40u << 23);                     // e << 23, e = biased exponent of the largest |x| (|x| < 2^(e - 126) in every lane)
+    const float scale = __uint_as_float((278u << 23) - ee);                  // 2^(151 - e)
+    const float inv = __uint_as_float(ee - (24u << 23));                     // 2^(e - 151)
+    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(x * scale)) * inv;
+#else
+    return warp_sum(j * dv);
+#endif
+}
+
 // =================================================================================================================
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
@@ -1455,7 +1480,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
                 tgt = dist > 0 ? -dist / dt : -dist * h->erp / dt;       // speculative margin / ERP push
                 lo = 0.0f; hi = 1e30f;
             } else {
-                const V3 vrel = mk3(warp_sum(cc.x * qd), warp_sum(cc.y * qd), warp_sum(cc.z * qd));
+                const V3 vrel = mk3(dense_dot(cc.x, qd), dense_dot(cc.y, qd), dense_dot(cc.z, qd));
                 const V3 lat = vrel - n * dot(vrel, n);
                 const float ll = norm(lat);
                 V3 t;
@@ -1481,8 +1506,8 @@ avg_dynamics_kernel(AvgStepArgs a) {
             }
         }
         gJ[d * 32 + lane] = jl; gW[d * 32 + lane] = w;
-        const float diag = warp_sum(jl * w);
-        const float u0 = warp_sum(jl * qd);
+        const float diag = dense_dot(jl, w);
+        const float u0 = dense_dot(jl, qd);
         if (lane == 0) {
             g_rows[2 * d] = make_float4(tgt - u0, diag > 1e-12f ? 1.0f / diag : 0.0f, lo, hi);
             g_rows[2 * d + 1] = make_float4(diag, mu, __int_as_float(d), __int_as_float(par));
@@ -1535,30 +1560,6 @@ __device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, 
 // =================================================================================================================
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
-// J.dv over the warp, the inner operation of every dense Gauss-Seidel row.  A float butterfly costs five DEPENDENT shuffle +
-// add stages (~150 cycles on the row-to-row dependency chain that bounds this kernel, profiles/ncu_full_r1p.txt).
-// AVG_REDUX = 2 (default): two redux.sync.  The first takes the largest |product| of the warp (max over the float bit
-//   patterns, monotonic for non-negative floats), which fixes a power-of-two scale such that every lane's product rounds
-//   to an integer below 2^25 -- the 24-25 significant bits a float sum keeps, at any magnitude -- and the 32-lane sum stays
-//   below 2^30; the second adds the integers, exactly and order-independently (bit-deterministic by construction).
-// AVG_REDUX = 1: one redux.sync at a fixed scale of 2^-22 m/s.  3 % faster, but the PR2's finger tips (1.5e-5 kg m^2 under a
-//   500 N m motor) reach intermediate J.dv of tens of m/s inside a sweep, so a fixed range is not safe for every model.
-// AVG_REDUX = 0: the float butterfly.
-__device__ __forceinline__ float dense_dot(float j, float dv) {
-#if AVG_REDUX == 1
-    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(j * dv * 4194304.0f)) * (1.0f / 4194304.0f);
-#elif AVG_REDUX == 2
-    const float x = j * dv;
-    const unsigned m = __reduce_max_sync(AVG_FULL, __float_as_uint(x) & 0x7fffffffu);
-    const int e = max((int)(m >> 23), 40);                                   // biased exponent of the largest |x|: |x| < 2^(e - 126) in every lane
-    const float scale = __uint_as_float((unsigned)(278 - e) << 23);          // 2^(151 - e)
-    const float inv = __uint_as_float((unsigned)(e - 24) << 23);             // 2^(e - 151)
-    return (float)__reduce_add_sync(AVG_FULL, __float2int_rn(x * scale)) * inv;
-#else
-    return warp_sum(j * dv);
-#endif
-}
-
 template <int MAXBLK>
 __global__ void __launch_bounds__(32, AVG_OCC_SOLVE)
 avg_solve_kernel(AvgStepArgs a) {
