@@ -881,6 +881,21 @@ struct LaneDyn {
     float* scr = a.scratch + (size_t)e * AVG_S_STRIDE;                                           \
     (void)lane; (void)s; (void)h; (void)grec; (void)scr;
 
+// L2 prefetch of what the warp that will run `ahead` environments later is going to read first (its blocks are dispatched
+// as the resident ones retire, so by then the lines sit in L2 instead of HBM): lane l touches 128-byte line l of the record
+// / of the given scratch sections.  A hint only: no register, no scoreboard, dropped if the address is out of range.
+#ifndef AVG_PREFETCH
+#define AVG_PREFETCH 1
+#endif
+#ifndef AVG_PF_PCT
+#define AVG_PF_PCT 50             /* prefetch distance in percent of the resident environments of the kernel */
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if AVG_PREFETCH
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // =================================================================================================================
 // action -> motor targets, env.py:274-337 (one lane per dof; no shared memory)
 // =================================================================================================================
@@ -943,6 +958,14 @@ __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     s.q[lane] = grec[AVG_E_Q + lane];
+    {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (12)
+        const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
+        if (ea < a.env_end) {
+            const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
+            const float* p = lane < 1 ? r2 : (lane < 2 ? s2 : (lane < 14 ? s2 + AVG_S_SEP + 32 * (lane - 2) : nullptr));
+            if (p) prefetch_l2(p);
+        }
+    }
     __syncwarp();
     fk_warp(m, s, s.q, lane, h->n_body);
     if (lane < h->n_body) {                  // the dynamics kernel of this sub-step reuses the poses
@@ -1112,6 +1135,15 @@ avg_dynamics_kernel(AvgStepArgs a) {
     const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
     int* scr_i = reinterpret_cast<int*>(scr);
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
+    {   // what this kernel reads first, for the environment whose warp takes this slot next: record (4 lines), counters (1),
+        // body poses (8), narrowphase results (16)
+        const int ea = e + 148 * AVG_OCC_DYN * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
+        if (ea < a.env_end) {
+            const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
+            const float* p = lane < 4 ? r2 + 32 * lane : (lane < 5 ? s2 : (lane < 13 ? s2 + AVG_S_POSE + 32 * (lane - 5) : (lane < 29 ? s2 + AVG_S_NPRES + 32 * (lane - 13) : nullptr)));
+            if (p) prefetch_l2(p);
+        }
+    }
     int overflow = 0;
     // the narrowphase queue has been drained by the kernel before this one; empty it for the next sub-step's collide kernel
     if (e == a.env_begin && lane == 0) a.np_count[0] = 0;
@@ -1570,6 +1602,16 @@ avg_solve_kernel(AvgStepArgs a) {
     const int ndense = scr_i[AVG_S_NR], nlim = scr_i[AVG_S_NS], nfr = scr_i[AVG_S_NFR], first_contact_row = scr_i[AVG_S_FCR];
     const int nc = scr_i[AVG_S_NCS];
     const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
+    {   // L2 prefetch for the environment whose warp takes this slot next: counters + velocities (1 line), motor / limit rows (4),
+        // weld rows (2), M^-1 columns (10), J and W of the weld rows (6 + 6)
+        const int ea = e + 148 * AVG_OCC_SOLVE * AVG_PF_PCT / 100;
+        if (ea < a.env_end) {
+            const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
+            const float* p = lane < 1 ? s2 : (lane < 5 ? s2 + AVG_S_ROWS_M + 32 * (lane - 1) : (lane < 7 ? s2 + AVG_S_ROWS_D + 32 * (lane - 5)
+                           : (lane < 17 ? s2 + AVG_S_MINV + 32 * (lane - 7) : (lane < 23 ? s2 + AVG_S_J + 32 * (lane - 17) : (lane < 29 ? s2 + AVG_S_W + 32 * (lane - 23) : nullptr)))));
+            if (p) prefetch_l2(p);
+        }
+    }
     // stage rows: coalesced loads from the arena
     for (int d = 0; d < min(ndense, kSmDense); ++d) { if (d >= 6) s.J[d][lane] = gJ[d * 32 + lane]; s.W[d][lane] = gW[d * 32 + lane]; }
     {
