@@ -958,11 +958,11 @@ __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     s.q[lane] = grec[AVG_E_Q + lane];
-    {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (12)
+    {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (3)
         const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
         if (ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
-            const float* p = lane < 1 ? r2 : (lane < 2 ? s2 : (lane < 14 ? s2 + AVG_S_SEP + 32 * (lane - 2) : nullptr));
+            const float* p = lane < 1 ? r2 : (lane < 2 ? s2 : (lane < 5 ? s2 + AVG_S_SEP + 4 * AVG_S_NSEPMAX * (lane - 2) : nullptr));   // first 8 certificates of each of the 3 planes
             if (p) prefetch_l2(p);
         }
     }
@@ -1136,11 +1136,11 @@ avg_dynamics_kernel(AvgStepArgs a) {
     int* scr_i = reinterpret_cast<int*>(scr);
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
     {   // what this kernel reads first, for the environment whose warp takes this slot next: record (4 lines), counters (1),
-        // body poses (8), narrowphase results (16)
+        // body poses (6), narrowphase results (4)
         const int ea = e + 148 * AVG_OCC_DYN * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
         if (ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
-            const float* p = lane < 4 ? r2 + 32 * lane : (lane < 5 ? s2 : (lane < 13 ? s2 + AVG_S_POSE + 32 * (lane - 5) : (lane < 29 ? s2 + AVG_S_NPRES + 32 * (lane - 13) : nullptr)));
+            const float* p = lane < 4 ? r2 + 32 * lane : (lane < 5 ? s2 : (lane < 11 ? s2 + AVG_S_POSE + 32 * (lane - 5) : (lane < 15 ? s2 + AVG_S_NPRES + 32 * (lane - 11) : nullptr)));   // 24 bodies, 8 results: what is usually there
             if (p) prefetch_l2(p);
         }
     }
