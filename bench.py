@@ -452,7 +452,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (22 kernels x 2 half-batches on 2 streams)" % (launches // max(1, args.steps)),
-                             "issue_slots": prof.get("issue_slots"),
+                             "issue_slots": (lambda s: None if not s else dict(s, achieved_warp_inst_per_s=s["warp_inst_per_env_step"] * value / world,
+                                                                                  frac=s["warp_inst_per_env_step"] * value / world / s["peak_warp_inst_per_s"]))(prof.get("issue_slots")),
                              "fp32": (lambda fp: None if not fp else {"flop_per_env_step": fp["flop_per_env_step_substep_kernels"],
                                                                        "achieved_tflops": fp["flop_per_env_step_substep_kernels"] * value / world / 1e12,
                                                                        "peak_tflops": 148 * 128 * 2 * 1.965e-3,
