@@ -74,7 +74,7 @@ class BatchedAssistiveEnv:
     """N copies of one reference environment stepping in lock-step on one GPU."""
 
     def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False,
-                 device_ik: bool = False):
+                 device_ik: bool = False, cuda_graph: bool = False):
         if env_id not in REGISTRY:
             if env_id in _ALL_REFERENCE_IDS:
                 raise NotImplementedError(f"{env_id}: registered by the reference but not compiled yet "
@@ -122,6 +122,44 @@ class BatchedAssistiveEnv:
         self.elapsed = 0
         self.variants: Optional[np.ndarray] = None
         self._needs_reset = True
+        # cuda_graph: the launch sequence of one step (44 kernels at two half batches, plus the device auto-reset and, in
+        # rollout(), the policy kernel) is captured once into a CUDA graph and replayed -- one driver call per step instead
+        # of one per kernel.  Pays where the step is launch-bound (small batches); results are bit-identical to eager steps.
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self._eager_steps = 0
+
+    # -- CUDA graph of the step ---------------------------------------------------------------------------------------
+    def _enqueue_step(self, act_ptr: int):
+        """The device work of one step on the current stream: avg_step and, with auto_reset="device", the masked restart."""
+        torch = self.torch
+        self.sim.step(act_ptr, self.obs.data_ptr(), self.reward.data_ptr(), self.done_dev.data_ptr(),
+                      self.info_dev.data_ptr(), self._stream())
+        if self.auto_reset == "device":
+            self.terminal_obs.copy_(self.obs)                       # last observation of the episodes that end at this step
+            self.sim.reset_device(self.done_dev.data_ptr(), self._device_seed, self.obs.data_ptr(), self._stream())
+
+    def _replay(self, key: str, with_policy: bool):
+        """Replay (capturing on first use) the graph `key`: [policy ->] step, reading the static action buffer."""
+        torch = self.torch
+        g = self._graphs.get(key)
+        if g is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                side.synchronize()
+                g.capture_begin()
+                try:
+                    if with_policy:
+                        self.sim.policy_act(self.obs.data_ptr(), self.actions_dev.data_ptr(), self._stream())
+                    self._enqueue_step(self.actions_dev.data_ptr())
+                finally:
+                    g.capture_end()
+            cur.wait_stream(side)
+            self._graphs[key] = g
+        g.replay()
 
     # -- reference API ------------------------------------------------------------------------------------------
     def seed(self, seed=None):
@@ -161,6 +199,7 @@ class BatchedAssistiveEnv:
     def set_policy(self, blob: bytes):
         """Upload a policy (assistive_vr_gym_b200.policy) for `act()` / `rollout()`."""
         self.sim.upload_policy(blob)
+        self._graphs.pop("rollout", None)        # the captured policy launch holds the old blob's arguments
         if not hasattr(self, "actions_dev"):
             self.actions_dev = self.torch.zeros((self.num_envs, self.sim.n_actions), dtype=self.torch.float32, device=self.device)
 
@@ -173,7 +212,10 @@ class BatchedAssistiveEnv:
         """`n_steps` of act -> step without leaving the GPU (the loop of enjoy_vr.py:105-117)."""
         out = None
         for _ in range(n_steps):
-            out = self.step(self.act())
+            if self._needs_reset:
+                raise RuntimeError("call reset() before step()")
+            self._advance(None)
+            out = self._step_result()
         return out
 
     def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None):
@@ -202,15 +244,35 @@ class BatchedAssistiveEnv:
             actions = actions.unsqueeze(0)
         if tuple(actions.shape) != (self.num_envs, self.sim.n_actions):
             raise ValueError(f"expected actions of shape {(self.num_envs, self.sim.n_actions)}, got {tuple(actions.shape)}")
-        self.sim.step(actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done_dev.data_ptr(),
-                      self.info_dev.data_ptr(), self._stream())
+        self._advance(actions)
+        return self._step_result()
+
+    def _advance(self, actions=None):
+        """Device side of step(): eager launches, or one graph replay (actions=None: the policy acts inside the graph)."""
+        torch = self.torch
         if self.auto_reset == "device":
             if not hasattr(self, "terminal_obs"):
                 self.terminal_obs = torch.empty_like(self.obs)
-            self.terminal_obs.copy_(self.obs)                       # last observation of the episodes that end at this step
             if not hasattr(self, "_device_seed"):
                 self._device_seed = int(self.np_random.randint(1 << 31))
-            self.sim.reset_device(self.done_dev.data_ptr(), self._device_seed, self.obs.data_ptr(), self._stream())
+        if self.cuda_graph and not hasattr(self, "actions_dev"):
+            self.actions_dev = torch.zeros((self.num_envs, self.sim.n_actions), dtype=torch.float32, device=self.device)
+        if self.cuda_graph and self._eager_steps >= 1:              # first step eager: lazy state (function attributes) settles
+            if actions is None:
+                self._replay("rollout", True)
+            else:
+                if actions.data_ptr() != self.actions_dev.data_ptr():
+                    self.actions_dev.copy_(actions)
+                self._replay("step", False)
+            return
+        self._eager_steps += 1
+        if actions is None:
+            actions = self.act()
+        self._enqueue_step(actions.data_ptr())
+
+    def _step_result(self):
+        torch = self.torch
+        if self.auto_reset == "device":
             done = self.done_dev.bool()
             return self.obs, self.reward, done, {
                 "total_force_on_human": self.info_dev[:, 0], "task_success": self.info_dev[:, 1].to(torch.int32),

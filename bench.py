@@ -312,23 +312,26 @@ def main():
     sweep = None
     if not args.no_episode:
         sweep = []
-        for nb in (4096, 16384, 65536, 196608):
-            senv_b = make(ENV_ID, num_envs=nb, device=local_rank, seed=1001 + rank)
+        for nb, graphed in ((1024, False), (1024, True), (4096, False), (4096, True), (16384, False), (16384, True),
+                            (65536, False), (196608, False)):
+            # cuda_graph=True: the step's launch sequence replayed as one CUDA graph (envs.py) -- where launches bind
+            senv_b = make(ENV_ID, num_envs=nb, device=local_rank, seed=1001 + rank, cuda_graph=graphed)
             senv_b.reset_device(seed=1001 + rank)
             sa = torch.empty((nb, 7), device=dev)
+            nsw = 20 if nb > 16384 else 100
             for k in range(3):
                 sa.uniform_(-1, 1, generator=gen); senv_b.step(sa); senv_b.elapsed = 0
             barrier()
             s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
             s0.record(stream)
-            for k in range(20):
+            for k in range(nsw):
                 sa.uniform_(-1, 1, generator=gen); senv_b.step(sa); senv_b.elapsed = 0
             s1.record(stream)
             barrier()
             ts = torch.tensor([s0.elapsed_time(s1)], device=dev)
             if distributed:
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-            sweep.append({"envs_per_gpu": nb, "value": nb * world * 20 / (float(ts.item()) * 1e-3), "unit": UNIT, "steps": 20})
+            sweep.append({"envs_per_gpu": nb, "cuda_graph": graphed, "value": nb * world * nsw / (float(ts.item()) * 1e-3), "unit": UNIT, "steps": nsw})
             senv_b.close()
 
     # ---- BedBathing (extra; BASELINE.json configs[2] names BedBathingPR2-v0 with a pretrained policy at 8192 envs: no
