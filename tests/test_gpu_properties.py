@@ -266,3 +266,54 @@ def test_staggered_episodes_with_device_time_limit(torch_cuda):
     assert ends[0][1][n // 2:].all() and not ends[0][1][: n // 2].any()       # second half: 200 steps since the common reset
     assert ends[1][1][: n // 2].all() and not ends[1][1][n // 2:].any()       # first half: 200 steps since its own restart
     env.close()
+
+
+@pytest.mark.parametrize("env_id", ["ScratchItchJaco-v0", "BedBathingPR2-v0"])
+def test_cuda_graph_mode_equals_eager_steps(torch_cuda, env_id):
+    """make(..., cuda_graph=True): step() replays one captured graph of the launch sequence; observations, rewards, done bytes
+    and the state records equal those of eager steps bit for bit, for caller-owned action tensors that change every step."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 1024
+    ref = make(env_id, num_envs=n, device=0, seed=41); ref.reset()
+    env = make(env_id, num_envs=n, device=0, seed=41, cuda_graph=True); env.set_state(ref.get_state(), ref.variants)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for t in range(7):
+        a = torch.rand((n, env.sim.n_actions), device="cuda", generator=g) * 2 - 1
+        o0, r0, d0, i0 = ref.step(a)
+        o1, r1, d1, i1 = env.step(a.clone())
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+        assert torch.equal(i0["total_force_on_human"], i1["total_force_on_human"])
+    assert "step" in env._graphs and env._eager_steps == 1            # one eager step, then replays
+    # bit patterns, not float values: the record holds integer words too (the alive-target bitmap of BedBathing reads as NaN)
+    assert np.array_equal(env.get_state().view(np.uint32), ref.get_state().view(np.uint32))
+    env.close(); ref.close()
+
+
+def test_cuda_graph_rollout_with_device_auto_reset(torch_cuda):
+    """The graph of rollout() holds policy -> step -> masked device restart (auto_reset="device"); with a 5-step time limit the
+    restarts happen inside the replays and the run equals the eager one bit for bit."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    from assistive_vr_gym_b200.policy import pack_policy, synthetic_policy
+    n = 512
+    _, arrs = synthetic_policy(30, 7, seed=3)
+    envs = []
+    for graphed in (False, True):
+        e = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=8, auto_reset="device", device_ik=True, cuda_graph=graphed)
+        e.sim.set_time_limit(5)
+        e.set_policy(pack_policy(**arrs))
+        e.reset_device(seed=33)
+        envs.append(e)
+    ends = []
+    for t in range(1, 13):
+        o0, r0, d0, i0 = envs[0].rollout(1)
+        o1, r1, d1, i1 = envs[1].rollout(1)
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+        assert torch.equal(i0["terminal_observation"], i1["terminal_observation"])
+        if bool(d1.all()):
+            ends.append(t)
+    assert ends == [5, 10] and "rollout" in envs[1]._graphs
+    assert np.array_equal(envs[0].get_state().view(np.uint32), envs[1].get_state().view(np.uint32))
+    for e in envs:
+        e.close()
