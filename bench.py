@@ -343,7 +343,7 @@ def main():
         bed = []
         for bid, nb in (("BedBathingPR2-v0", 8192), ("BedBathingPR2-v0", 65536), ("BedBathingJaco-v0", 8192), ("BedBathingJaco-v0", 65536),
                         ("ScratchItchPR2-v0", 65536)):
-            benv = make(bid, num_envs=nb, device=local_rank, seed=1001 + rank)
+            benv = make(bid, num_envs=nb, device=local_rank, seed=1001 + rank, cuda_graph=nb <= 16384)   # graph replay where launches matter
             pblob, _ = synthetic_policy(benv.obs_robot_len, benv.action_robot_len, seed=0)
             benv.set_policy(pblob)
             benv.reset_device(seed=1001 + rank)
@@ -361,7 +361,7 @@ def main():
             if distributed:
                 dist.all_reduce(tb, op=dist.ReduceOp.MAX)
                 dist.all_reduce(bstat, op=dist.ReduceOp.SUM)
-            bed.append({"env_id": bid, "envs_per_gpu": nb, "value": nb * world * 200 / (float(tb.item()) * 1e-3), "unit": UNIT,
+            bed.append({"env_id": bid, "envs_per_gpu": nb, "cuda_graph": benv.cuda_graph, "value": nb * world * 200 / (float(tb.item()) * 1e-3), "unit": UNIT,
                         "steps": 200, "task_success_rate": float(bstat[0]) / (nb * world), "mean_reward_last_step": float(bstat[1]) / (nb * world),
                         "note": "synthetic-policy rollout (%d-64-64-7 tanh actor, fused inference), full episode from a device reset" % benv.obs_robot_len})
             benv.close()
