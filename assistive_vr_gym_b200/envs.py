@@ -150,7 +150,8 @@ class BatchedAssistiveEnv:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
                 side.synchronize()
-                g.capture_begin()
+                # thread-local capture mode: other threads (NCCL's watchdog under torchrun) keep making CUDA calls meanwhile
+                g.capture_begin(capture_error_mode="thread_local")
                 try:
                     if with_policy:
                         self.sim.policy_act(self.obs.data_ptr(), self.actions_dev.data_ptr(), self._stream())
