@@ -19,12 +19,13 @@ EXPORTS = [
     "avg_get_reward_terms", "avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_env_stride", "avg_launch_count",
     "avg_bytes_per_env_step", "avg_arm_limit_logits", "avg_alloc_host", "avg_free_host", "avg_upload_reset_table", "avg_reset",
     "avg_upload_policy", "avg_policy_act",
+    "avg_set_particles", "avg_get_particles", "avg_particles_device_ptr", "avg_particle_stride", "avg_num_particles", "avg_settle",
 ]
 
 CONTACT_DT = np.dtype([("shape_a", "<i4"), ("shape_b", "<i4"), ("pos_a", "<f4", 3), ("pos_b", "<f4", 3),
                        ("normal", "<f4", 3), ("dist", "<f4"), ("force", "<f4"), ("pad", "<i4", 3)])
 assert CONTACT_DT.itemsize == 64
-MAX_CONTACT = 12
+MAX_CONTACT = 32       # AVG_MAX_CONTACT (include/avg_model.h)
 
 
 class AvgError(RuntimeError):
@@ -67,6 +68,12 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.avg_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.avg_free_host.argtypes = [vp]
     lib.avg_arm_limit_logits.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
+    lib.avg_set_particles.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_get_particles.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.avg_particles_device_ptr.argtypes = [vp]; lib.avg_particles_device_ptr.restype = vp
+    lib.avg_particle_stride.argtypes = []
+    lib.avg_num_particles.argtypes = [vp]
+    lib.avg_settle.argtypes = [vp, vp, ctypes.c_int, vp]
     for f in ("avg_num_envs", "avg_num_actions", "avg_num_obs", "avg_bytes_per_env_step"):
         getattr(lib, f).argtypes = [vp]
     lib.avg_env_stride.argtypes = []
@@ -142,6 +149,39 @@ class Sim:
 
     def set_time_limit(self, max_episode_steps: int):
         self._check(self.lib.avg_set_time_limit(self.h, int(max_episode_steps)), "avg_set_time_limit")
+
+    def set_particles(self, part: np.ndarray, begin: int = 0):
+        part = np.ascontiguousarray(part, dtype=np.float32)
+        assert part.shape[1] == self.lib.avg_particle_stride()
+        self._check(self.lib.avg_set_particles(self.h, begin, part.shape[0], part.ctypes.data), "avg_set_particles")
+
+    def get_particles(self, begin: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_env - begin if count is None else count
+        out = np.zeros((count, self.lib.avg_particle_stride()), dtype=np.float32)
+        self._check(self.lib.avg_get_particles(self.h, begin, count, out.ctypes.data), "avg_get_particles")
+        return out
+
+    def settle(self, n_steps: int, mask_ptr: int = 0, stream: int = 0):
+        """n_steps x p.stepSimulation() without actions (the settle loop of reset(), feeding.py:318-320)."""
+        self._check(self.lib.avg_settle(self.h, mask_ptr or None, int(n_steps), stream), "avg_settle")
+
+    @property
+    def n_particles(self) -> int:
+        return self.lib.avg_num_particles(self.h)
+
+    @property
+    def state_ptr(self) -> int:
+        return int(self.lib.avg_state_device_ptr(self.h) or 0)
+
+    def get_state_tensor(self, torch, device):
+        """Zero-copy [n_env, AVG_ENV_STRIDE] float32 CUDA tensor over the state arena (avg_state_device_ptr)."""
+        if getattr(self, "_state_tensor", None) is None:
+            stride = self.lib.avg_env_stride()
+
+            class _Arena:
+                __cuda_array_interface__ = {"shape": (self.n_env, stride), "typestr": "<f4", "data": (self.state_ptr, False), "version": 2}
+            self._state_tensor = torch.as_tensor(_Arena(), device=device)
+        return self._state_tensor
 
     def get_variants(self, begin: int = 0, count: int | None = None) -> np.ndarray:
         count = self.n_env - begin if count is None else count

@@ -4,11 +4,11 @@ from __future__ import annotations
 import numpy as np
 
 from . import xform as X
-from .mbody import JOINT_FREE, SHAPE_HULL
+from .mbody import JOINT_FREE, SHAPE_HULL, SHAPE_COMPOUND
 from .scene import CompiledScene, _world_aabb
 
 AVG_MAGIC = 0x4D475641
-AVG_VERSION = 9
+AVG_VERSION = 10
 ENV_STRIDE = 192
 
 BODY_DT = np.dtype([
@@ -44,7 +44,9 @@ HEADER_DT = np.dtype([
     ("off_pair", "<u4"), ("off_frame", "<u4"), ("off_bps", "<u4"), ("off_bpm", "<u4"),
     ("n_block", "<i4"), ("block_start", "<i4", 4), ("off_bcap", "<u4"),
     ("off_mlp", "<u4"), ("n_mlp", "<i4"), ("mlp_dof", "<i4", 4),
-    ("off_target", "<u4"), ("n_target", "<i4"), ("n_target_upper", "<i4"), ("pad2", "<u4", 3),
+    ("off_target", "<u4"), ("n_target", "<i4"), ("n_target_upper", "<i4"),
+    ("n_cshape", "<i4"), ("off_caabb", "<u4"), ("n_internal", "<i4"), ("n_particle", "<i4"), ("pshape", "<i4"),
+    ("p_mass", "<f4"), ("p_gravity", "<f4", 3), ("tool_body", "<i4"), ("head_frozen_mask", "<i4"), ("pad2", "<u4", 5),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
 
@@ -64,8 +66,11 @@ def bounding_capsule(d) -> tuple:
         a = np.zeros(3); a[k] = d.half[k]
         others = [d.half[i] for i in range(3) if i != k]
         return -a, a, float(np.hypot(*others))
-    if d.kind == SHAPE_HULL:
-        v = np.asarray(d.verts, dtype=np.float64)
+    if d.kind in (SHAPE_HULL, SHAPE_COMPOUND):
+        if d.kind == SHAPE_COMPOUND:
+            v = np.concatenate([np.asarray(c.verts, dtype=np.float64) @ X.quat_to_mat(c.quat).T + c.pos for c in d.children], axis=0)
+        else:
+            v = np.asarray(d.verts, dtype=np.float64)
         c = v.mean(0)
         w, V = np.linalg.eigh(np.cov((v - c).T))
         a = V[:, -1]
@@ -108,9 +113,16 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
         dofs[i]["damping"] = d.get("damping", 0.0)
     verts = []
     planes = []
-    shapes = np.zeros(len(scene.shapes), dtype=SHAPE_DT)
+    cshapes = list(getattr(scene, "cshapes", None) or [])
+    particle = getattr(scene, "particle", None)
+    all_shapes = list(scene.shapes) + cshapes
+    n_top = len(scene.shapes)
+    shapes = np.zeros(len(all_shapes) + (1 if particle is not None else 0), dtype=SHAPE_DT)
     hull_index = {}
-    for i, s in enumerate(scene.shapes):
+    first_child = {}
+    for k, c in enumerate(cshapes):
+        first_child.setdefault(c.parent, n_top + k)
+    for i, s in enumerate(all_shapes):
         r = shapes[i]
         d = s.desc
         r["type"] = d.kind; r["body"] = s.body; r["ref_body"] = s.ref_body; r["ref_link"] = s.ref_link
@@ -122,17 +134,33 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
                 verts.append(np.asarray(d.verts, dtype=np.float32))
                 planes.append(np.asarray(d.planes, dtype=np.float32))
             r["vert_off"], r["vert_cnt"], r["plane_off"], r["plane_cnt"] = hull_index[key]
+        if d.kind == SHAPE_COMPOUND:
+            r["vert_off"] = first_child[i]; r["vert_cnt"] = len(s.children)
         r["friction"] = d.friction; r["thr"] = s.thr
+        r["pad"][0] = s.parent if i >= n_top else -1          # children: their compound
         if s.body >= 0:
             lo, hi = d.local_aabb()
             r["aabb_c"] = 0.5 * (lo + hi); r["aabb_h"] = 0.5 * (hi - lo)
         else:
             c, h = _world_aabb(d, s.pos, s.quat)
             r["aabb_c"] = c; r["aabb_h"] = h
+    if particle is not None:                                  # template of the food / water spheres (pose from the particle record)
+        r = shapes[len(all_shapes)]
+        r["type"] = particle.kind; r["body"] = -1; r["ref_body"] = 7; r["ref_link"] = -1; r["quat"] = [0, 0, 0, 1]
+        r["radius"] = particle.radius; r["margin"] = particle.radius; r["friction"] = particle.friction; r["thr"] = scene.particle_thr
+        r["aabb_h"] = [particle.radius] * 3; r["pad"][0] = -1
+    # child AABBs in the frame of the owning body (the device tests them against points / boxes brought into that frame)
+    caabb = np.zeros((len(cshapes), 8), dtype="<f4")
+    for k, c in enumerate(cshapes):
+        R = X.quat_to_mat(c.quat)
+        lo, hi = c.desc.local_aabb()
+        caabb[k, 0:3] = R @ (0.5 * (lo + hi)) + c.pos; caabb[k, 4:7] = np.abs(R) @ (0.5 * (hi - lo))
     verts = np.concatenate(verts, axis=0).astype("<f4") if verts else np.zeros((0, 3), "<f4")
     verts = np.concatenate([verts, np.zeros((len(verts), 1), "<f4")], axis=1)          # padded to float4 for 16-byte loads
     planes = np.concatenate(planes, axis=0).astype("<f4") if planes else np.zeros((0, 4), "<f4")
-    pairs = (scene.pairs[:, 0].astype("<u4") | (scene.pairs[:, 1].astype("<u4") << 16)).astype("<u4")
+    opairs = scene.opairs if getattr(scene, "opairs", None) is not None else scene.pairs
+    assert len(shapes) < 32768
+    pairs = (opairs[:, 0].astype("<u4") | (opairs[:, 1].astype("<u4") << 16)).astype("<u4")
     frames = np.zeros(len(scene.frames), dtype=FRAME_DT)
     for i, (b, p, q) in enumerate(scene.frames):
         frames[i]["body"] = b; frames[i]["pos"] = p; frames[i]["quat"] = q
@@ -150,8 +178,8 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
             assert b > a
             bpm[a] |= np.uint32(1 << b)
     # bounding capsules: shape frame for moving shapes, world frame for static ones
-    bcap = np.zeros((len(scene.shapes), 8), dtype="<f4")
-    for i, sh in enumerate(scene.shapes):
+    bcap = np.zeros((len(shapes), 8), dtype="<f4")
+    for i, sh in enumerate(all_shapes):
         p0, p1, r = bounding_capsule(sh.desc)
         if sh.body < 0:
             R = X.quat_to_mat(sh.quat)
@@ -198,9 +226,11 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     vals = dict(scene.header)
     if overrides:
         vals.update(overrides)
+    h["n_internal"] = 1; h["tool_body"] = -1
     for k, v in vals.items():
         h[k] = v
-    h["n_shape"] = len(shapes); h["n_mshape"] = scene.n_mshape; h["n_vert"] = len(verts); h["n_plane"] = len(planes)
+    h["n_shape"] = n_top; h["n_cshape"] = len(cshapes); h["pshape"] = len(all_shapes) if particle is not None else -1
+    h["n_mshape"] = scene.n_mshape; h["n_vert"] = len(verts); h["n_plane"] = len(planes)
     h["n_pair"] = len(pairs); h["n_frame"] = len(frames)
     h["n_block"] = n_block; h["block_start"] = starts
     h["n_mlp"] = mlp.size; h["mlp_dof"] = mlp_dof
@@ -209,7 +239,7 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     sections = []
     for name, arr in (("off_body", bodies), ("off_dof", dofs), ("off_shape", shapes), ("off_vert", verts),
                       ("off_plane", planes), ("off_pair", pairs), ("off_frame", frames), ("off_bps", bps), ("off_bpm", bpm),
-                      ("off_bcap", bcap), ("off_mlp", mlp), ("off_target", tgt)):
+                      ("off_bcap", bcap), ("off_mlp", mlp), ("off_target", tgt), ("off_caabb", caabb)):
         h[name] = off
         sections.append((off, arr.tobytes()))
         off = _align(off + arr.nbytes)
@@ -227,7 +257,9 @@ def read_blob(blob: bytes) -> dict:
     out = {"header": h}
     out["bodies"] = np.frombuffer(blob, dtype=BODY_DT, count=int(h["n_body"]), offset=int(h["off_body"]))
     out["dofs"] = np.frombuffer(blob, dtype=DOF_DT, count=int(h["n_dof"]), offset=int(h["off_dof"]))
-    out["shapes"] = np.frombuffer(blob, dtype=SHAPE_DT, count=int(h["n_shape"]), offset=int(h["off_shape"]))
+    n_all = int(h["n_shape"]) + int(h["n_cshape"]) + (1 if int(h["n_particle"]) > 0 else 0)
+    out["shapes"] = np.frombuffer(blob, dtype=SHAPE_DT, count=n_all, offset=int(h["off_shape"]))
+    out["caabb"] = np.frombuffer(blob, dtype="<f4", count=8 * int(h["n_cshape"]), offset=int(h["off_caabb"])).reshape(-1, 8)
     out["verts"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_vert"]), offset=int(h["off_vert"])).reshape(-1, 4)[:, :3]
     out["planes"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_plane"]), offset=int(h["off_plane"])).reshape(-1, 4)
     out["pairs"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_pair"]), offset=int(h["off_pair"]))

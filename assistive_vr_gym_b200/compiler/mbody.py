@@ -24,7 +24,7 @@ import numpy as np
 
 from . import xform as X
 
-SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_CYLINDER, SHAPE_HULL, SHAPE_PLANE = 0, 1, 2, 3, 4, 5
+SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_CYLINDER, SHAPE_HULL, SHAPE_PLANE, SHAPE_COMPOUND = 0, 1, 2, 3, 4, 5, 6
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_FREE = 0, 1, 2
 
 
@@ -39,6 +39,7 @@ class ShapeDesc:
     planes: Optional[np.ndarray] = None     # hull planes (n, d)
     friction: float = 0.5
     ref_link: int = -1              # PyBullet link index this shape reports as
+    children: Optional[list] = None # SHAPE_COMPOUND: the convex pieces (ShapeDesc, poses in the same frame as this shape's pos/quat = identity)
 
     def local_aabb(self, margin_in_aabb: bool = True) -> Tuple[np.ndarray, np.ndarray]:
         """AABB (min, max) in the shape's own frame."""
@@ -53,6 +54,14 @@ class ShapeDesc:
         elif self.kind == SHAPE_HULL:
             m = 0.001 if margin_in_aabb else 0.0
             return self.verts.min(0) - m, self.verts.max(0) + m
+        elif self.kind == SHAPE_COMPOUND:
+            lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
+            for c in self.children:
+                R = X.quat_to_mat(c.quat)
+                clo, chi = c.local_aabb(margin_in_aabb)
+                cc = R @ (0.5 * (clo + chi)) + c.pos; ch = np.abs(R) @ (0.5 * (chi - clo))
+                lo = np.minimum(lo, cc - ch); hi = np.maximum(hi, cc + ch)
+            return lo, hi
         else:                       # ground plane = the reference's 30 x 30 x 10 box centred at z = -5 (plane.urdf)
             return np.array([-15.0, -15.0, -10.0]), np.array([15.0, 15.0, 0.0])
         return -h, h

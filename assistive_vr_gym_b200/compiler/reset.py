@@ -262,6 +262,8 @@ RESET_TABLE_DT = np.dtype([
     ("hum_lower", "<f4", 8), ("hum_upper", "<f4", 8), ("hum_reset", "<f4", 8), ("limb_dims", "<f4", (2, 2)),
     ("fin_open", "<f4"), ("ik_enabled", "<i4"), ("ik_ee_body", "<i4"), ("ik_range", "<f4"),
     ("ik_target", "<f4", 8), ("ik_ee_frame", "<f4", 8),
+    ("hum_slot", "<i4", 8), ("fin_q", "<f4", 8), ("n_particle", "<i4"), ("has_bowl", "<i4"), ("head_mask", "<u4"), ("ik_tol", "<f4"),
+    ("bowl_center", "<f4", 4), ("bowl_quat", "<f4", 4), ("grid", "<f4", (64, 4)),
 ])
 
 
@@ -282,6 +284,20 @@ def reset_table_bytes(rd: dict, ik: dict | None = None) -> bytes:
         t[k][:len(rd[k])] = rd[k]
     t["limb_dims"] = rd["limb_dims"]
     t["task"] = int(rd.get("task", 0)); t["n_target"] = int(rd.get("n_target", 0)); t["fin_open"] = float(rd.get("fin_open", 1.0))
+    fd = int(t["task"]) >= 2
+    hj = np.asarray(rd["hum_joint"], dtype=np.int64)
+    t["hum_slot"][:len(hj)] = hj - (24 if fd else 4)
+    t["fin_q"][:len(rd["fin_qidx"])] = rd["fin_q"] if "fin_q" in rd else float(rd.get("fin_open", 1.0))
+    t["ik_tol"] = float(rd.get("ik_tol", 0.03))
+    if fd:                                                     # Feeding / Drinking (compiler/reset_fd.py build_reset_data_fd)
+        npart = int(rd["n_particle"])
+        t["n_particle"] = npart; t["has_bowl"] = int(rd["has_bowl"]); t["head_mask"] = int(rd["head_mask"])
+        t["bowl_center"][:3] = rd["bowl_center"]; t["bowl_quat"] = rd["bowl_quat"]
+        t["grid"][:npart, :3] = rd["grid"]
+        if ik is None:                                         # these tasks always solve the start pose on the device
+            t["ik_enabled"] = 1; t["ik_ee_body"] = int(rd["ik_ee_body"]); t["ik_range"] = 0.05
+            t["ik_target"][:3] = rd["ik_center"]; t["ik_target"][3:7] = rd["ik_quat"]
+            t["ik_ee_frame"][:3] = rd["ik_ee_pos"]; t["ik_ee_frame"][3:7] = rd["ik_ee_quat"]
     return t.tobytes()
 
 

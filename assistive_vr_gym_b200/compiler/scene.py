@@ -16,13 +16,13 @@ import numpy as np
 from . import xform as X
 from .human import create_human, human_self_collision_enabled
 from .mbody import (Attached, DynBody, LinkDesc, MultiBodyDesc, ShapeDesc, reduce_bodies, link_contact_threshold,
-                    SHAPE_BOX, SHAPE_CAPSULE, SHAPE_CYLINDER, SHAPE_HULL, SHAPE_PLANE, SHAPE_SPHERE,
+                    SHAPE_BOX, SHAPE_CAPSULE, SHAPE_CYLINDER, SHAPE_HULL, SHAPE_PLANE, SHAPE_SPHERE, SHAPE_COMPOUND,
                     JOINT_FREE, JOINT_PRISMATIC, JOINT_REVOLUTE)
 from .meshes import load_mesh_hulls, prepare_hull
 from .urdf import parse_urdf
 
 I4 = np.array([0.0, 0, 0, 1])
-REF_ROBOT, REF_HUMAN, REF_TOOL, REF_FURNITURE, REF_PLANE = 0, 1, 2, 3, 4
+REF_ROBOT, REF_HUMAN, REF_TOOL, REF_FURNITURE, REF_PLANE, REF_TABLE, REF_BOWL = 0, 1, 2, 3, 4, 5, 6
 
 # reference config.ini
 CONFIG = {
@@ -110,7 +110,7 @@ def urdf_to_multibody(path: str, ref_body: int, name: str, inertia_from_file: bo
     return MultiBodyDesc(name=name, ref_body=ref_body, base=base, links=links)
 
 
-def load_robot(assets_dir: str, robot_type: str):
+def load_robot(assets_dir: str, robot_type: str, arm: str = "left"):
     """The robot as `WorldCreation.init_<robot>` loads it (world_creation.py:181-217, 274-293) plus the indices the task
     files hard-code for it.  -> (MultiBodyDesc, spec) with spec = arm joints driven by the action (the LEFT arm on the
     PR2: robot_arm='left' at scratch_itch.py:45 / bed_bathing.py:44), gripper joints of `set_gripper_open_position`
@@ -133,6 +133,13 @@ def load_robot(assets_dir: str, robot_type: str):
         # (scratch_itch.py:259, bed_bathing.py:342) and are held at zero velocity by PyBullet's default joint motors --
         # they only move if something pushes them.  Also frozen: l_gripper_motor_slider / _screw (77, 78) and
         # l_gripper_joint (83): 10 g / 10 g / 1 g links without collision geometry (documented deviation).
+        if arm == "right":                                                 # Feeding / Drinking: robot_arm='right' (feeding.py:48), tool on link 54
+            fingers = [57, 58, 59, 60]                                     # world_creation.py:311 (right gripper)
+            moving = set(right) | set(fingers)
+            frozen = {l.ref_index for l in robot.links if l.jtype in ("revolute", "prismatic") and l.ref_index not in moving}
+            q_preset = dict(zip(left, [1.75, 1.25, 1.5, -0.5, 1.0, 0.0, 1.0]))           # env.py:455-457 (idle left arm)
+            return robot, dict(arm=right, fingers=fingers, ee_link=54, tool_filtered=set(range(49, 64)), torso_link=15,
+                               frozen=frozen, q_preset=q_preset)                           # world_creation.py:335,359
         moving = set(left) | set(fingers)
         frozen = {l.ref_index for l in robot.links if l.jtype in ("revolute", "prismatic") and l.ref_index not in moving}
         q_preset = dict(zip(right, [-1.75, 1.25, -1.5, -0.5, -1.0, 0.0, -1.0]))          # env.py:455-459 reset_robot_joints
@@ -182,6 +189,8 @@ class CompiledShape:
     thr: float
     margin: float
     mb_index: int              # which MultiBodyDesc it came from (for the filter rules)
+    children: Optional[list] = None   # SHAPE_COMPOUND: CompiledShape per convex piece (poses in the owning body's frame)
+    parent: int = -1                  # children: index of their compound in the top-level shape list
 
 
 @dataclass
@@ -204,6 +213,8 @@ class CompiledScene:
     q_human_reset: Dict[int, float]
     tool_offset: Tuple[np.ndarray, np.ndarray]
     info: dict = field(default_factory=dict)
+    cshapes: List[CompiledShape] = field(default_factory=list)   # compound children, shape table indices len(shapes) + k
+    opairs: Optional[np.ndarray] = None    # pair table with the compounds expanded into their children (what the oracle walks)
 
 
 def _safe_margin(half_min: float) -> float:
@@ -275,18 +286,34 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
     assert n_dof <= 32 and qidx <= 32
 
     # -- shapes ---------------------------------------------------------------------------------------------
+    # A multibody with `env_static = e` (the Feeding bowl) is a static body whose pose comes from the environment record
+    # (AVG_E_EBODY[e]): its shapes hang on "body" n_body + e, relative to the base frame.  Links listed in `compound_links`
+    # (VHACD meshes: spoon, cup, bowl, head) become ONE top-level compound shape with their hulls as children.
     shapes: List[CompiledShape] = []
     for k, mb in enumerate(mbs):
+        estatic = getattr(mb, "env_static", None)
         for li in [-1] + list(range(len(mb.links))):
             link = mb.link(li)
             if not link.shapes:
                 continue
             thr = link_contact_threshold(link)
             at = attach[k][li]
+            if estatic is not None:
+                assert at.body < 0 and not mb.links, "env-static bodies are single fixed links"
+                at = Attached(n_body + int(estatic), np.zeros(3), I4.copy())
+            made = []
             for s in link.shapes:
                 p, q = X.tf_mul(at.pos, at.quat, s.pos, s.quat)
-                shapes.append(CompiledShape(desc=s, body=at.body, pos=p, quat=q, ref_body=mb.ref_body, ref_link=li,
-                                            thr=thr, margin=_shape_margin(s), mb_index=k))
+                made.append(CompiledShape(desc=s, body=at.body, pos=p, quat=q, ref_body=mb.ref_body, ref_link=li,
+                                          thr=thr, margin=_shape_margin(s), mb_index=k))
+            if li in getattr(mb, "compound_links", ()) and len(made) > 1 and at.body >= 0:
+                assert all(c.desc.kind == SHAPE_HULL for c in made) and len(made) <= 72
+                cd = ShapeDesc(SHAPE_COMPOUND, np.zeros(3), I4.copy(), friction=made[0].desc.friction, ref_link=li,
+                               children=[ShapeDesc(SHAPE_HULL, c.pos, c.quat, verts=c.desc.verts, planes=c.desc.planes) for c in made])
+                shapes.append(CompiledShape(desc=cd, body=at.body, pos=np.zeros(3), quat=I4.copy(), ref_body=mb.ref_body, ref_link=li,
+                                            thr=thr, margin=0.0, mb_index=k, children=made))
+            else:
+                shapes.extend(made)
     shapes.sort(key=lambda s: 0 if s.body >= 0 else 1)       # moving shapes first (stable)
     n_mshape = sum(1 for s in shapes if s.body >= 0)
 
@@ -303,6 +330,8 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
                 continue                                      # unordered pairs once; moving A first
             if a.body == b.body:
                 continue
+            if a.body >= n_body and (b.body < 0 or b.body >= n_body):
+                continue                                      # env-static against static: nothing moves
             if a.mb_index == b.mb_index:
                 mb = mbs[a.mb_index]
                 if a.ref_link == b.ref_link:
@@ -325,6 +354,28 @@ def _assemble(mbs: List[MultiBodyDesc], q_presets: Dict[int, Dict[int, float]], 
             pairs.append((ia, ib))
     pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
     return bodies, attach, dofs, n_jdof, n_free, shapes, n_mshape, pairs
+
+
+def expand_compounds(shapes: List[CompiledShape], pairs: np.ndarray):
+    """Children of the compound shapes as a flat list (shape table indices len(shapes) + k, `parent` set) and the pair
+    table with every compound replaced by its children -- the explicit pair list the oracle walks; the device expands
+    compound candidates itself (csrc collide kernel)."""
+    cshapes: List[CompiledShape] = []
+    first = {}
+    for i, s in enumerate(shapes):
+        if s.desc.kind == SHAPE_COMPOUND:
+            first[i] = len(shapes) + len(cshapes)
+            for c in s.children:
+                c.parent = i
+                cshapes.append(c)
+    if not first:
+        return cshapes, pairs
+
+    def members(i):
+        return range(first[i], first[i] + len(shapes[i].children)) if i in first else (i,)
+
+    out = [(ca, cb) for a, b in pairs for ca in members(int(a)) for cb in members(int(b))]
+    return cshapes, np.asarray(out, dtype=np.int32).reshape(-1, 2)
 
 
 def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,

@@ -20,11 +20,15 @@ struct AvgHandle {
     bool have[AVG_K_MAX_VARIANTS] = {false, false, false, false};
     float* d_env = nullptr;
     float* d_scratch = nullptr;
+    float* d_part = nullptr;                           // particle records (Feeding / Drinking), allocated with the first such model
+    float* d_pscratch = nullptr;
+    int n_particle = 0, n_internal = 1;
     int substeps = 5;
     int maxblk = 0;
     int32_t* d_variant = nullptr;
     unsigned char* d_policy = nullptr;                 // uploaded policy blob (avg_upload_policy)
     int32_t* d_episode = nullptr;                      // episodes started per environment (device reset counter)
+    uint8_t* d_retry = nullptr;                        // start poses rejected by the self-contact test of the device reset
     AvgResetTable* d_rtab[AVG_K_MAX_VARIANTS] = {nullptr, nullptr, nullptr, nullptr};
     // debug taps
     bool debug = false;
@@ -95,7 +99,11 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     }
     cudaMemset(h->d_env, 0, sizeof(float) * AVG_ENV_STRIDE * (size_t)n_env);
     cudaMemset(h->d_variant, 0, sizeof(int32_t) * (size_t)n_env);
-    if (cudaMalloc(&h->d_episode, sizeof(int32_t) * (size_t)n_env) == cudaSuccess) cudaMemset(h->d_episode, 0, sizeof(int32_t) * (size_t)n_env);
+    if (cudaMalloc(&h->d_episode, sizeof(int32_t) * (size_t)n_env) != cudaSuccess) {
+        g_slot_used[slot] = false; cudaFree(h->d_env); cudaFree(h->d_variant); cudaFree(h->d_scratch); delete h;
+        return fail(nullptr, -2, "avg_create: cudaMalloc of the episode counters failed");
+    }
+    cudaMemset(h->d_episode, 0, sizeof(int32_t) * (size_t)n_env);
     cudaMemset(h->d_scratch, 0, sizeof(float) * AVG_S_STRIDE * (size_t)n_env);
     h->np_capacity = n_env * 12 + 4096;                /* 1-6 candidates per environment and sub-step survive the culls (more late in
                                                           random-action episodes); overflow is flagged, never silent */
@@ -134,7 +142,7 @@ int avg_destroy(AvgHandle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) { cudaFree(h->d_model[v]); cudaFree(h->d_rtab[v]); }
-    cudaFree(h->d_episode); cudaFree(h->d_policy);
+    cudaFree(h->d_episode); cudaFree(h->d_policy); cudaFree(h->d_retry); cudaFree(h->d_part); cudaFree(h->d_pscratch);
     cudaFree(h->d_env); cudaFree(h->d_scratch); cudaFree(h->d_variant); cudaFree(h->d_contacts); cudaFree(h->d_ncontacts); cudaFree(h->d_terms);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_info); cudaFree(h->d_done);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_info); cudaFreeHost(h->h_done);
@@ -151,11 +159,24 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     const AvgModelHeader* mh = (const AvgModelHeader*)blob;
     if (mh->magic != AVG_MAGIC || mh->version != AVG_VERSION) return fail(h, -1, "avg_upload_model: bad magic/version");
     if (mh->total_bytes != nbytes) return fail(h, -1, "avg_upload_model: size mismatch");
-    if (mh->n_body > AVG_MAX_BODY || mh->n_dof > AVG_MAX_DOF || mh->n_jdof > AVG_K_MAXJ || mh->n_mshape > AVG_K_MAXMS ||
-        mh->n_free > 2 || mh->n_shape - mh->n_mshape > 256 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32)
+    if (mh->n_body + mh->n_ebody > AVG_MAX_BODY || mh->n_ebody > AVG_MAX_EBODY || mh->n_dof > AVG_MAX_DOF || mh->n_jdof > AVG_K_MAXJ || mh->n_mshape > AVG_K_MAXMS ||
+        mh->n_free > 2 || mh->n_shape - mh->n_mshape > 256 || mh->n_obs_robot + mh->n_obs_human > 64 || mh->n_action_robot + mh->n_action_human > 32 ||
+        mh->n_shape + mh->n_cshape + 1 >= 32768 || mh->n_particle < 0 || mh->n_particle > AVG_MAX_PARTICLE || mh->n_internal < 1 || mh->n_internal > 4)
         return fail(h, -4, "avg_upload_model: model exceeds the warp-per-environment kernel limits");
-    if (mh->task != AVG_TASK_SCRATCH_ITCH && mh->task != AVG_TASK_BED_BATHING)
-        return fail(h, -4, "avg_upload_model: only the ScratchItch and BedBathing epilogues are built (round 1)");
+    if (mh->task < AVG_TASK_SCRATCH_ITCH || mh->task > AVG_TASK_DRINKING)
+        return fail(h, -4, "avg_upload_model: unknown task");
+    if ((mh->task == AVG_TASK_FEEDING || mh->task == AVG_TASK_DRINKING) && (mh->n_particle <= 0 || mh->pshape != mh->n_shape + mh->n_cshape || mh->tool_body < 0 || mh->n_frame <= AVG_F_HEAD))
+        return fail(h, -4, "avg_upload_model: Feeding / Drinking models need particles, a free tool body and the head frame");
+    {   /* compound shapes: children in range, at most AVG_MAX_CCHILD each */
+        const AvgShape* sh = (const AvgShape*)((const char*)blob + mh->off_shape);
+        int ncomp = 0;
+        for (int i = 0; i < mh->n_shape; ++i) if (sh[i].type == AVG_SHAPE_COMPOUND) {
+            ncomp++;
+            if (i >= mh->n_mshape || sh[i].vert_off < mh->n_shape || sh[i].vert_cnt < 1 || sh[i].vert_cnt > AVG_MAX_CCHILD || sh[i].vert_off + sh[i].vert_cnt > mh->n_shape + mh->n_cshape)
+                return fail(h, -4, "avg_upload_model: bad compound shape");
+        }
+        if (ncomp > AVG_MAX_COMPOUND) return fail(h, -4, "avg_upload_model: too many compound shapes");
+    }
     if (mh->n_target < 0 || mh->n_target > AVG_MAX_TARGET) return fail(h, -4, "avg_upload_model: too many wiping targets");
     const AvgBody* bodies = (const AvgBody*)((const char*)blob + mh->off_body);
     for (int b = 0; b < mh->n_body; ++b) {
@@ -168,9 +189,21 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
         if (!contiguous || cnt != bodies[b].sub_end - b) return fail(h, -4, "avg_upload_model: bodies must be in depth-first order (sub_end)");
     }
     int na = mh->n_action_robot + mh->n_action_human, no = mh->n_obs_robot + mh->n_obs_human;
-    if (h->task >= 0 && (h->n_act != na || h->n_obs != no || h->task != mh->task))
+    if (h->task >= 0 && (h->n_act != na || h->n_obs != no || h->task != mh->task || h->n_particle != mh->n_particle || h->n_internal != mh->n_internal))
         return fail(h, -4, "avg_upload_model: variants of one handle must share task / action / observation widths");
     cudaSetDevice(h->device);
+    if (mh->n_particle > 0 && !h->d_part) {            /* particle arenas + a narrowphase queue sized for the particle candidates */
+        AVG_CHECK(h, cudaMalloc(&h->d_part, sizeof(float) * AVG_P_STRIDE * (size_t)h->n_env));
+        AVG_CHECK(h, cudaMalloc(&h->d_pscratch, sizeof(float) * AVG_PS_STRIDE * (size_t)h->n_env));
+        AVG_CHECK(h, cudaMemset(h->d_part, 0, sizeof(float) * AVG_P_STRIDE * (size_t)h->n_env));
+        AVG_CHECK(h, cudaMemset(h->d_pscratch, 0, sizeof(float) * AVG_PS_STRIDE * (size_t)h->n_env));
+        const long long cap = (long long)h->n_env * (12 + 6 * mh->n_particle) + 4096;
+        h->np_capacity = cap > 0x3fffffff ? 0x3fffffff : (int)cap;
+        for (int k = 0; k < 4; ++k) {
+            cudaFree(h->d_npq[k]); h->d_npq[k] = nullptr;
+            AVG_CHECK(h, cudaMalloc(&h->d_npq[k], sizeof(AvgNpItem) * (size_t)h->np_capacity));
+        }
+    }
     cudaFree(h->d_model[variant]); h->d_model[variant] = nullptr;
     AVG_CHECK(h, cudaMalloc(&h->d_model[variant], nbytes));
     AVG_CHECK(h, cudaMemcpy(h->d_model[variant], blob, nbytes, cudaMemcpyHostToDevice));
@@ -181,6 +214,7 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
     if (h->task >= 0 && h->substeps != mh->substeps && variant != 0)
         return fail(h, -4, "avg_upload_model: variants of one handle must share frame_skip");
     h->task = mh->task; h->n_act = na; h->n_obs = no; h->substeps = mh->substeps;
+    h->n_particle = mh->n_particle; h->n_internal = mh->n_internal;
     for (int b = 0; b < mh->n_block; ++b) {
         int sz = mh->block_start[b + 1] - mh->block_start[b];
         if (sz > 16) return fail(h, -4, "avg_upload_model: articulation with more than 16 dofs (solver register block)");
@@ -193,6 +227,8 @@ int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_r
     if (!h || !env_records) return -1;
     if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_set_state: range");
     cudaSetDevice(h->device);
+    /* steps run on the caller's / the handle's non-blocking streams, which do not order against the copies below */
+    AVG_CHECK(h, cudaDeviceSynchronize());
     AVG_CHECK(h, cudaMemcpy(h->d_env + (size_t)env_begin * AVG_ENV_STRIDE, env_records,
                             sizeof(float) * AVG_ENV_STRIDE * (size_t)env_count, cudaMemcpyHostToDevice));
     /* a new state starts with an empty separating-axis cache (and clean hand-off slots) */
@@ -203,8 +239,33 @@ int avg_set_state(AvgHandle* h, int env_begin, int env_count, const float* env_r
                 return fail(h, -1, "avg_set_state: variant without an uploaded model");
         AVG_CHECK(h, cudaMemcpy(h->d_variant + env_begin, variants, sizeof(int32_t) * (size_t)env_count, cudaMemcpyHostToDevice));
     }
+    AVG_CHECK(h, cudaDeviceSynchronize());              /* the memset is asynchronous: a step on another stream must not start under it */
     return 0;
 }
+
+int avg_set_particles(AvgHandle* h, int env_begin, int env_count, const float* records) {
+    if (!h || !records) return -1;
+    if (!h->d_part) return fail(h, -1, "avg_set_particles: this handle's task has no particles (Feeding / Drinking only)");
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_set_particles: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(h->d_part + (size_t)env_begin * AVG_P_STRIDE, records, sizeof(float) * AVG_P_STRIDE * (size_t)env_count, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int avg_get_particles(AvgHandle* h, int env_begin, int env_count, float* records) {
+    if (!h || !records) return -1;
+    if (!h->d_part) return fail(h, -1, "avg_get_particles: this handle's task has no particles (Feeding / Drinking only)");
+    if (env_begin < 0 || env_count < 0 || env_begin + env_count > h->n_env) return fail(h, -1, "avg_get_particles: range");
+    cudaSetDevice(h->device);
+    AVG_CHECK(h, cudaDeviceSynchronize());
+    AVG_CHECK(h, cudaMemcpy(records, h->d_part + (size_t)env_begin * AVG_P_STRIDE, sizeof(float) * AVG_P_STRIDE * (size_t)env_count, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+float* avg_particles_device_ptr(AvgHandle* h) { return h ? h->d_part : nullptr; }
+int avg_particle_stride(void) { return AVG_P_STRIDE; }
+int avg_num_particles(const AvgHandle* h) { return h ? h->n_particle : 0; }
 
 int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records) {
     if (!h || !env_records) return -1;
@@ -219,6 +280,17 @@ int avg_get_state(AvgHandle* h, int env_begin, int env_count, float* env_records
 float* avg_state_device_ptr(AvgHandle* h) { return h ? h->d_env : nullptr; }
 
 static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset);
+
+int avg_settle(AvgHandle* h, const uint8_t* mask, int n_steps, void* stream) {
+    if (!h || n_steps < 0) return -1;
+    cudaSetDevice(h->device);
+    AvgStepArgs a; memset(&a, 0, sizeof(a));
+    int rc = fill_args(h, a, 0); if (rc) return rc;
+    a.mask = mask;
+    AVG_CHECK(h, avg_launch_settle(a, n_steps, (cudaStream_t)stream));
+    h->launches += (long long)n_steps * h->n_internal * (h->d_part ? 5 : 4);
+    return 0;
+}
 
 int avg_set_time_limit(AvgHandle* h, int max_episode_steps) {
     if (!h || max_episode_steps < 0) return -1;
@@ -284,11 +356,26 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
     while (nv < AVG_K_MAX_VARIANTS && h->d_rtab[nv]) { r.tables[nv] = h->d_rtab[nv]; nv++; }
     if (nv == 0) return fail(h, -1, "avg_reset: no reset table uploaded (avg_upload_reset_table)");
     r.n_variants = nv; r.n_per_gender = nv >= 2 ? nv / 2 : 1; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
-    r.mask = mask; r.n_env = h->n_env; r.seed = seed;
+    r.mask = mask; r.n_env = h->n_env; r.seed = seed; r.part = h->d_part;
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) r.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
     r.any_ik = h->any_ik ? 1 : 0;
     AVG_CHECK(h, avg_launch_reset(r, (cudaStream_t)stream));
-    h->launches += 1 + r.any_ik;
+    h->launches += 1 + r.any_ik + (h->d_part ? 1 : 0);
+    if (r.any_ik) {
+        /* util.ik_random_restarts(step_sim=True) (util.py:41-46): 5 x stepSimulation from the solved pose, poses whose robot
+           touches itself (or that were pushed away) are solved again from new random restarts, up to 5 times */
+        static const int rounds = getenv("AVG_IK_RETRY") ? atoi(getenv("AVG_IK_RETRY")) : 5;
+        if (rounds > 0 && !h->d_retry) { AVG_CHECK(h, cudaMalloc(&h->d_retry, (size_t)h->n_env)); AVG_CHECK(h, cudaMemset(h->d_retry, 0, (size_t)h->n_env)); }
+        for (int k = 1; k <= rounds; ++k) {
+            int rc = avg_settle(h, mask, 5, stream); if (rc) return rc;
+            r.retry = h->d_retry; r.round = k;
+            AVG_CHECK(h, avg_launch_reset_check(r, (cudaStream_t)stream));
+            h->launches += 2 + (h->d_part ? 1 : 0);
+        }
+    }
+    if (h->d_part) {                                   /* "Drop food in the spoon": 100 x stepSimulation (feeding.py:318-320, drinking.py:320-322) */
+        int rc = avg_settle(h, mask, 100, stream); if (rc) return rc;
+    }
     if (obs) {
         AvgStepArgs a; memset(&a, 0, sizeof(a));
         int rc = fill_args(h, a, 0); if (rc) return rc;
@@ -306,6 +393,7 @@ static int fill_args(AvgHandle* h, AvgStepArgs& a, int qset) {
     a.variant = h->d_variant; a.env = h->d_env; a.scratch = h->d_scratch; a.n_env = h->n_env; a.maxblk = h->maxblk;
     { const char* d = getenv("AVG_DBG"); a.dbg = d ? atoi(d) : 0; }
     a.np_queue = h->d_npq[qset]; a.np_count = h->d_npc[qset]; a.np_capacity = h->np_capacity;
+    a.part = h->d_part; a.pscratch = h->d_pscratch; a.n_internal = h->n_internal; a.post = 1;
     a.env_begin = 0; a.env_end = h->n_env;
     if ((a.dbg & 32) && !h->d_cnt) { cudaMalloc(&h->d_cnt, 64); cudaMemset(h->d_cnt, 0, 64); }
     a.dbg_counters = (a.dbg & 32) ? h->d_cnt : nullptr;
@@ -334,7 +422,7 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     if (h->step_chunks < 2 || h->debug) {
         AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-        h->launches += avg_kernels_per_step(h->substeps);
+        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
         return 0;
     }
     /* k equal parts on k streams (k = 2 by default; still asynchronous and capturable: event fork / join around the extra streams) */
@@ -355,7 +443,7 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
             AVG_CHECK(h, cudaEventRecord(ej, st));
             AVG_CHECK(h, cudaStreamWaitEvent((cudaStream_t)stream, ej, 0));
         }
-        h->launches += avg_kernels_per_step(h->substeps);
+        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
     }
     return 0;
 }
@@ -417,7 +505,7 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
         a.actions = h->d_act; a.obs = h->d_obs; a.reward = h->d_rew; a.done = h->d_done; a.info = h->d_info;
         a.env_begin = b0; a.env_end = b1;
         AVG_CHECK(h, avg_launch_step(a, h->substeps, st));
-        h->launches += avg_kernels_per_step(h->substeps);
+        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
         AVG_CHECK(h, cudaMemcpyAsync(dst_obs + (size_t)b0 * h->n_obs, h->d_obs + (size_t)b0 * h->n_obs, sizeof(float) * cnt * h->n_obs, cudaMemcpyDeviceToHost, st));
         AVG_CHECK(h, cudaMemcpyAsync(dst_rew + b0, h->d_rew + b0, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
         AVG_CHECK(h, cudaMemcpyAsync(dst_info + 2 * (size_t)b0, h->d_info + 2 * (size_t)b0, sizeof(float) * cnt * 2, cudaMemcpyDeviceToHost, st));
@@ -493,7 +581,9 @@ int avg_bytes_per_env_step(const AvgHandle* h) {
     int read_state = AVG_ENV_STRIDE * 4;
     int write_state = (AVG_E_STRENGTH + (AVG_E_TARGET_ON_ARM - AVG_E_TARGET_H) + (AVG_E_LAST - AVG_E_ITERATION)) * 4;
     int io = h->n_act * 4 + h->n_obs * 4 + 4 + 8 + 1 + 4 /* variant id */;
-    return read_state + write_state + io;
+    /* particles: position / velocity / angular velocity of each sphere read and written once, plus the mask words */
+    int particles = h->n_particle > 0 ? 2 * (9 * 4 * h->n_particle) + 2 * 16 * 4 : 0;
+    return read_state + write_state + io + particles;
 }
 
 }  // extern "C"

@@ -31,6 +31,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "../../include/avg_model.h"
 #include "avg_math.cuh"
 #include "avg_kernels.h"
@@ -84,6 +85,7 @@ struct KM {                                // device view of a ModelBlob
     const float4* bcap;
     const float* mlp;
     const float4* target;                  // BedBathing wiping targets (bed_bathing.py:360-379)
+    const float4* caabb;                   // compound children: AABB centre | half extents in the owning body's frame
 };
 
 // Section pointers per (handle slot, variant), resolved on the host when a model is uploaded: a warp reads its model
@@ -105,6 +107,7 @@ __device__ __forceinline__ KM open_model(const unsigned char* blob) {
     m.bcap = reinterpret_cast<const float4*>(blob + m.h->off_bcap);
     m.mlp = m.h->n_mlp > 0 ? reinterpret_cast<const float*>(blob + m.h->off_mlp) : nullptr;
     m.target = m.h->n_target > 0 ? reinterpret_cast<const float4*>(blob + m.h->off_target) : nullptr;
+    m.caabb = m.h->n_cshape > 0 ? reinterpret_cast<const float4*>(blob + m.h->off_caabb) : nullptr;
     return m;
 }
 
@@ -171,7 +174,7 @@ __device__ __noinline__ void frame_pose(const KM& m, const SM& s, int f, V3& p, 
 // epilogues used to walk them one after the other on lane 0).
 template <class SM>
 __device__ __forceinline__ void frames_warp(const KM& m, SM& s, int lane) {
-    if (lane < AVG_F_COUNT) {
+    if (lane < AVG_F_COUNT && lane < m.h->n_frame) {
         V3 p; Q4 q;
         frame_pose(m, s, lane, p, q);
         float* f = s.fr[lane];
@@ -190,10 +193,14 @@ __device__ __forceinline__ void frame_cached(const SM& s, int f, V3& p, Q4& q) {
 // are formed by pointer jumping over the parent array (log2(depth) shuffle rounds instead of a serial walk).
 // qpos = position coordinates (AVG_E_Q block of the env record).
 // ---------------------------------------------------------------------------------------------------------------
+// Env-static bodies (the Feeding bowl: pose drawn per episode, feeding.py:184) take the slots nb .. nb + n_ebody - 1 with
+// their pose straight from the record (`ebody` = its AVG_E_EBODY block).
 template <class SM>
-__device__ void fk_warp(const KM& m, SM& s, const float* qpos, int lane, int nb) {
+__device__ void fk_warp(const KM& m, SM& s, const float* qpos, int lane, int nb, const float* ebody = nullptr) {
     V3 p = mk3(0, 0, 0); Q4 q = mkq(0, 0, 0, 1);
     int anc = -1;
+    const int ne = ebody ? m.h->n_ebody : 0;
+    if (lane >= nb && lane < nb + ne) { const float* e7 = ebody + 7 * (lane - nb); p = ld3(e7); q = ldq(e7 + 3); }
     if (lane < nb) {
         const AvgBody* B = &m.body[lane];
         if (B->jtype == AVG_JOINT_FREE) {
@@ -217,7 +224,7 @@ __device__ void fk_warp(const KM& m, SM& s, const float* qpos, int lane, int nb)
         int aa = __shfl_sync(AVG_FULL, anc, src);
         if (anc >= 0) { p = ap + qrot(aq, p); q = qmul(aq, q); anc = aa; }
     }
-    if (lane < nb) {
+    if (lane < nb + ne) {
         q = qnormalize(q);
         st3(s.bp[lane], p);
         s.bq[lane][0] = q.x; s.bq[lane][1] = q.y; s.bq[lane][2] = q.z; s.bq[lane][3] = q.w;
@@ -436,6 +443,11 @@ __device__ __noinline__ V3 support_any(const WShape& w, V3 d, bool active, int l
     if (active && !hull) res = support(w, d);
     unsigned req = __ballot_sync(AVG_FULL, hull);
     if (req == 0) return res;
+    // Serving pays when a few lanes of the warp hold hulls (mixed shape types: the others would idle through a divergent
+    // scan).  When most lanes need a scan (particle-vs-hull items of Feeding / Drinking: every lane a different small hull),
+    // 32 served scans cost more than one divergent scan of every lane over its own hull; the vertex picked is the same
+    // (first maximum in index order).
+    if (__popc(req) >= 8) { if (hull) res = support(w, d); return res; }
     const V3 l = hull ? mtmul(w.R, d) : mk3(0, 0, 0);
     const unsigned long long vp = hull ? reinterpret_cast<unsigned long long>(w.verts) : 0ull;
     const int nv = hull ? w.s->vert_cnt : 0;
@@ -578,6 +590,37 @@ __device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool n
             }
             else { best_out = 3.0e38f; bn_out = mk3(0, 0, 1); bpa_out = A.p; }
         }
+    }
+}
+
+// World pose of any shape of the table from the body poses in shared memory: top-level moving shapes are cached (s.sp / s.sq),
+// children of compound shapes hang on their body (dynamic or env-static), everything else is static.
+template <class SM>
+__device__ __forceinline__ void any_shape_pose(const KM& m, const SM& s, int si, V3& p, Q4& q) {
+    const AvgShape* S = &m.shape[si];
+    if (si < m.h->n_mshape) { p = ld3(s.sp[si]); q = ldq(s.sq[si]); }
+    else if (S->body >= 0) { const Q4 bq = ldq(s.bq[S->body]); p = ld3(s.bp[S->body]) + qrot(bq, ld3(S->pos)); q = qnormalize(qmul(bq, ldq(S->quat))); }
+    else { p = ld3(S->pos); q = ldq(S->quat); }
+}
+// World AABB (centre, half extents) of shape si for the expansion of compound candidates: children from their body-frame box
+// (m.caabb), top-level moving shapes from the cache, static shapes from their broadphase record.
+template <class SM>
+__device__ __forceinline__ void any_shape_aabb(const KM& m, const SM& s, int si, V3& c, V3& hh) {
+    const int nms = m.h->n_mshape, ns = m.h->n_shape;
+    if (si >= ns) {
+        const float4 c4 = __ldg(&m.caabb[2 * (si - ns)]), h4 = __ldg(&m.caabb[2 * (si - ns) + 1]);
+        const int b = m.shape[si].body;
+        const M3 R = qmat(ldq(s.bq[b]));
+        c = ld3(s.bp[b]) + mmul(R.m, mk3(c4.x, c4.y, c4.z));
+        hh = mk3(fabsf(R.m[0]) * h4.x + fabsf(R.m[1]) * h4.y + fabsf(R.m[2]) * h4.z, fabsf(R.m[3]) * h4.x + fabsf(R.m[4]) * h4.y + fabsf(R.m[5]) * h4.z,
+                 fabsf(R.m[6]) * h4.x + fabsf(R.m[7]) * h4.y + fabsf(R.m[8]) * h4.z);
+    } else if (si < nms) {
+        const float4 a0 = s.saabb[si][0], a1 = s.saabb[si][1];
+        c = mk3(a0.x, a0.y, a0.z); hh = mk3(a0.w, a1.x, a1.y);
+    } else {
+        const float4* rp = reinterpret_cast<const float4*>(&m.bps[si - nms]);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        c = mk3(r0.x, r0.y, r0.z); hh = mk3(r0.w, r1.x, r1.y);
     }
 }
 
@@ -750,6 +793,51 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
         }
         ncand = nk;
     }
+    // Compound shapes (VHACD tool / bowl / head): a surviving candidate that involves one is replaced by the pairs of its
+    // convex children whose boxes overlap (children x other shape, or children x children), the lanes sharing the products.
+    if (h->n_cshape > 0) {
+        __syncwarp();
+        int nx = 0;
+#pragma unroll 1
+        for (int base = 0; base < ncand; base += 32) {
+            const int ci = base + lane;
+            const uint32_t pr = ci < ncand ? s.cand[ci] : 0u;
+            const bool comp = ci < ncand && (m.shape[pr & 0xffff].type == AVG_SHAPE_COMPOUND || m.shape[pr >> 16].type == AVG_SHAPE_COMPOUND);
+            const unsigned bplain = __ballot_sync(AVG_FULL, ci < ncand && !comp);
+            unsigned bcomp = __ballot_sync(AVG_FULL, comp);
+            if (ci < ncand && !comp) { const int k = nx + __popc(bplain & ((1u << lane) - 1)); if (k < kMaxCand) s.cand2[k] = pr; }
+            nx += __popc(bplain);
+            while (bcomp) {
+                const int src = __ffs(bcomp) - 1; bcomp &= bcomp - 1;
+                const uint32_t q = __shfl_sync(AVG_FULL, pr, src);
+                const int a = q & 0xffff, b = q >> 16;
+                const AvgShape* SA = &m.shape[a]; const AvgShape* SB = &m.shape[b];
+                const int fa = SA->type == AVG_SHAPE_COMPOUND ? SA->vert_off : a, na = SA->type == AVG_SHAPE_COMPOUND ? SA->vert_cnt : 1;
+                const int fb = SB->type == AVG_SHAPE_COMPOUND ? SB->vert_off : b, nbb = SB->type == AVG_SHAPE_COMPOUND ? SB->vert_cnt : 1;
+                const float thr = fminf(SA->thr, SB->thr);
+                const int total = na * nbb;
+#pragma unroll 1
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    bool hit = false; int ca = 0, cb = 0;
+                    if (t < total) {
+                        ca = fa + t / nbb; cb = fb + t % nbb;
+                        V3 c1, h1, c2, h2;
+                        any_shape_aabb(m, s, ca, c1, h1); any_shape_aabb(m, s, cb, c2, h2);
+                        hit = fabsf(c1.x - c2.x) <= h1.x + h2.x + thr && fabsf(c1.y - c2.y) <= h1.y + h2.y + thr && fabsf(c1.z - c2.z) <= h1.z + h2.z + thr;
+                    }
+                    const unsigned bh = __ballot_sync(AVG_FULL, hit);
+                    if (hit) { const int k = nx + __popc(bh & ((1u << lane) - 1)); if (k < kMaxCand) s.cand2[k] = (uint32_t)ca | ((uint32_t)cb << 16); }
+                    nx += __popc(bh);
+                }
+            }
+        }
+        if (nx > kMaxCand) { overflow |= 4; nx = kMaxCand; }
+        __syncwarp();
+        for (int i = lane; i < nx; i += 32) s.cand[i] = s.cand2[i];
+        ncand = nx;
+        __syncwarp();
+    }
     // canonical order = pair-table order: ascending (moving shape a, other shape b); rank by counting (the list is short)
 #pragma unroll 1
     for (int base = 0; base < ncand; base += 32) {
@@ -797,10 +885,9 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
                 if (f >= 0) {
                     const float4 e0 = s.sep[0][f], e1 = s.sep[1][f], e2 = s.sep[2][f];
                     if (e1.w > 0.0f) {
-                        const Q4 qa = ldq(s.sq[a]);
-                        const Q4 qb = b < nms ? ldq(s.sq[b]) : ldq(SB->quat);
-                        const V3 pbw = b < nms ? ld3(s.sp[b]) : ld3(SB->pos);
-                        const V3 prel = qrot_inv(qa, pbw - ld3(s.sp[a]));
+                        V3 paw, pbw; Q4 qa, qb;
+                        any_shape_pose(m, s, a, paw, qa); any_shape_pose(m, s, b, pbw, qb);
+                        const V3 prel = qrot_inv(qa, pbw - paw);
                         const Q4 qrel = qmul(qconj(qa), qb);
                         const float md = fminf(SA->thr, SB->thr) + SA->margin + SB->margin;
                         const V3 dp = prel - mk3(e1.x, e1.y, e1.z);
@@ -808,7 +895,7 @@ __device__ void collide_warp(const KM& m, SM& s, int lane, int env_index, int& n
                         const float dx = qrel.x - sg * e2.x, dy = qrel.y - sg * e2.y, dz = qrel.z - sg * e2.z, dw = qrel.w - sg * e2.w;
                         const float chord = 2.0f * sqrtf(dx * dx + dy * dy + dz * dz + dw * dw);     // >= 2 sin(angle / 2)
                         const float4 c0 = __ldg(&m.bcap[2 * b]), c1 = __ldg(&m.bcap[2 * b + 1]);
-                        const V3 o = b < nms ? mk3(0, 0, 0) : ld3(SB->pos);
+                        const V3 o = SB->body >= 0 ? mk3(0, 0, 0) : ld3(SB->pos);
                         const float rb = fmaxf(norm(mk3(c0.x, c0.y, c0.z) - o), norm(mk3(c1.x, c1.y, c1.z) - o)) + c0.w;
                         if (e1.w - (norm(dp) + chord * rb) > md + 1e-5f) { carried = true; queued = false; k0 = e0; k1 = e1; k2 = e2; }
                     }
@@ -880,6 +967,8 @@ struct LaneDyn {
     float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;                                            \
     float* scr = a.scratch + (size_t)e * AVG_S_STRIDE;                                           \
     (void)lane; (void)s; (void)h; (void)grec; (void)scr;
+/* settle / reset paths step only the environments whose mask byte is set */
+#define AVG_MASK_CHECK if (a.mask && !a.mask[e]) return;
 
 // L2 prefetch of what the warp that will run `ahead` environments later is going to read first (its blocks are dispatched
 // as the resident ones retire, so by then the lines sit in L2 instead of HBM): lane l touches 128-byte line l of the record
@@ -957,6 +1046,7 @@ avg_prologue_kernel(AvgStepArgs a) {
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
+    AVG_MASK_CHECK
     s.q[lane] = grec[AVG_E_Q + lane];
     {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (3)
         const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
@@ -967,8 +1057,8 @@ avg_collide_kernel(AvgStepArgs a) {
         }
     }
     __syncwarp();
-    fk_warp(m, s, s.q, lane, h->n_body);
-    if (lane < h->n_body) {                  // the dynamics kernel of this sub-step reuses the poses
+    fk_warp(m, s, s.q, lane, h->n_body, grec + AVG_E_EBODY);
+    if (lane < h->n_body + h->n_ebody) {     // the dynamics / narrowphase / particle kernels of this sub-step reuse the poses
         float4* gp = reinterpret_cast<float4*>(scr + AVG_S_POSE) + 2 * lane;
         gp[0] = make_float4(s.bp[lane][0], s.bp[lane][1], s.bp[lane][2], 0.0f);
         gp[1] = make_float4(s.bq[lane][0], s.bq[lane][1], s.bq[lane][2], s.bq[lane][3]);
@@ -990,7 +1080,7 @@ namespace {
 __device__ __forceinline__ void np_load_shape(const KM& m, const float* scr, int si, WShape& w, Q4& q) {
     const AvgShape* S = &m.shape[si];
     w.s = S; w.verts = m.vert + 4 * S->vert_off; w.planes = m.plane + 4 * S->plane_off;
-    if (si < m.h->n_mshape) {
+    if (S->body >= 0) {                     // top-level moving shapes and children of compounds: on a dynamic or env-static body
         const float4* gp = reinterpret_cast<const float4*>(scr + AVG_S_POSE) + 2 * S->body;
         const float4 p4 = gp[0], q4 = gp[1];
         const Q4 bq = mkq(q4.x, q4.y, q4.z, q4.w);
@@ -1020,12 +1110,26 @@ avg_narrow_kernel(AvgStepArgs a) {
         const KM m = c_models[a.slot][variant];
         float* scr = a.scratch + (size_t)it.env * AVG_S_STRIDE;
         int sa = it.pair & 0xffff, sb = it.pair >> 16;
-        if (valid && (sa >= m.h->n_mshape || sb >= m.h->n_shape || it.slot < 0 || it.slot >= AVG_S_NQMAX || it.cert >= AVG_S_NSEPMAX || it.env < 0 || it.env >= a.n_env)) {
+        // particle items (Feeding / Drinking): shape a = the sphere template at the particle's position, result into the
+        // particle scratch arena
+        const bool is_part = valid && (sa & AVG_NP_PARTICLE) != 0;
+        const int pidx = sa & 0x7f;
+        const int n_all = m.h->n_shape + m.h->n_cshape;
+        if (valid && ((!is_part && (sa >= n_all || m.shape[sa].body < 0)) || (is_part && (!a.part || m.h->pshape < 0 || pidx >= m.h->n_particle)) || sb >= n_all ||
+                      it.slot < 0 || it.slot >= (is_part ? AVG_MAX_PCAND : AVG_S_NQMAX) || it.cert >= AVG_S_NSEPMAX || it.env < 0 || it.env >= a.n_env)) {
             if (a.dbg & 64) printf("[avg_narrow] bad work item %d of %d: env %d pair %08x slot %d cert %d\n", i, count, it.env, it.pair, it.slot, it.cert);
             sa = 0; sb = m.h->n_mshape; it.slot = 0; it.cert = -1; it.env = a.env_begin;     // never dereference a corrupt item
         }
         WShape A, B; Q4 qa, qb;
-        np_load_shape(m, scr, sa, A, qa); np_load_shape(m, scr, sb, B, qb);
+        if (is_part) {
+            const float* pr = a.part + (size_t)it.env * AVG_P_STRIDE;
+            A.s = &m.shape[m.h->pshape]; A.verts = m.vert; A.planes = m.plane;
+            A.p = mk3(pr[AVG_P_POS + pidx], pr[AVG_P_POS + 64 + pidx], pr[AVG_P_POS + 128 + pidx]);
+            qa = mkq(0, 0, 0, 1);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) A.R[k] = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f;
+        } else np_load_shape(m, scr, sa, A, qa);
+        np_load_shape(m, scr, sb, B, qb);
         const float thr = fminf(A.s->thr, B.s->thr), ma = A.s->margin, mb = B.s->margin;
         const bool plane = B.s->type == AVG_SHAPE_PLANE;
         float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
@@ -1089,11 +1193,17 @@ avg_narrow_kernel(AvgStepArgs a) {
                 gsep[AVG_S_NSEPMAX + it.cert] = make_float4(prel.x, prel.y, prel.z, sepgap);
                 gsep[2 * AVG_S_NSEPMAX + it.cert] = make_float4(qrel.x, qrel.y, qrel.z, qrel.w);
             }                                                        // else the slot keeps the "no certificate" seed of the collide kernel
-            float4* r = reinterpret_cast<float4*>(scr + AVG_S_NPRES) + 4 * it.slot;
-            r[0] = make_float4(pa.x, pa.y, pa.z, pb.x);
-            r[1] = make_float4(pb.y, pb.z, n.x, n.y);
-            r[2] = make_float4(n.z, d, __int_as_float(sa), __int_as_float(sb));
-            r[3] = make_float4(hit ? 1.0f : 0.0f, 0, 0, 0);
+            if (is_part) {
+                float4* r = reinterpret_cast<float4*>(a.pscratch + (size_t)it.env * AVG_PS_STRIDE + AVG_PS_CAND) + 2 * it.slot;
+                r[0] = make_float4(n.x, n.y, n.z, d);
+                r[1] = make_float4(__int_as_float(pidx), __int_as_float(sb), hit ? 1.0f : 0.0f, 0.0f);
+            } else {
+                float4* r = reinterpret_cast<float4*>(scr + AVG_S_NPRES) + 4 * it.slot;
+                r[0] = make_float4(pa.x, pa.y, pa.z, pb.x);
+                r[1] = make_float4(pb.y, pb.z, n.x, n.y);
+                r[2] = make_float4(n.z, d, __int_as_float(sa), __int_as_float(sb));
+                r[3] = make_float4(hit ? 1.0f : 0.0f, 0, 0, 0);
+            }
         }
         __syncwarp();
     }
@@ -1147,32 +1257,37 @@ avg_dynamics_kernel(AvgStepArgs a) {
     int overflow = 0;
     // the narrowphase queue has been drained by the kernel before this one; empty it for the next sub-step's collide kernel
     if (e == a.env_begin && lane == 0) a.np_count[0] = 0;
+    AVG_MASK_CHECK
     // contacts: the hits among the narrowphase results, compacted in pair order; the list is also written to the arena
     // for the solver (impulses) and the epilogue
     int ncontact;
     {
         const int nq = scr_i[AVG_S_NQ];
-        const float4* r = reinterpret_cast<const float4*>(scr + AVG_S_NPRES) + 4 * lane;
-        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
-        bool hit = false;
-        if (lane < nq) { hit = r[3].x != 0.0f; if (hit) { r0 = r[0]; r1 = r[1]; r2 = r[2]; } }
-        const unsigned bal = __ballot_sync(AVG_FULL, hit);
-        ncontact = __popc(bal);
-        if (ncontact > kMaxC) { overflow |= 1; ncontact = kMaxC; }
-        const int slot = __popc(bal & ((1u << lane) - 1));
-        if (hit && slot < kMaxC) {
-            s.c_pa[slot][0] = r0.x; s.c_pa[slot][1] = r0.y; s.c_pa[slot][2] = r0.z;
-            s.c_pb[slot][0] = r0.w; s.c_pb[slot][1] = r1.x; s.c_pb[slot][2] = r1.y;
-            s.c_n[slot][0] = r1.z; s.c_n[slot][1] = r1.w; s.c_n[slot][2] = r2.x;
-            s.c_dist[slot] = r2.y; s.c_sa[slot] = __float_as_int(r2.z); s.c_sb[slot] = __float_as_int(r2.w);
-            float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * slot;
-            c[0] = r0.x; c[1] = r0.y; c[2] = r0.z; c[3] = r0.w; c[4] = r1.x; c[5] = r1.y; c[6] = r1.z; c[7] = r1.w; c[8] = r2.x;
-            c[9] = r2.y; c[10] = r2.z; c[11] = r2.w; c[12] = 0.0f;
+        ncontact = 0;
+#pragma unroll 1
+        for (int base = 0; base < nq; base += 32) {
+            const float4* r = reinterpret_cast<const float4*>(scr + AVG_S_NPRES) + 4 * (base + lane);
+            float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
+            bool hit = false;
+            if (base + lane < nq) { hit = r[3].x != 0.0f; if (hit) { r0 = r[0]; r1 = r[1]; r2 = r[2]; } }
+            const unsigned bal = __ballot_sync(AVG_FULL, hit);
+            const int slot = ncontact + __popc(bal & ((1u << lane) - 1));
+            if (hit && slot < kMaxC) {
+                s.c_pa[slot][0] = r0.x; s.c_pa[slot][1] = r0.y; s.c_pa[slot][2] = r0.z;
+                s.c_pb[slot][0] = r0.w; s.c_pb[slot][1] = r1.x; s.c_pb[slot][2] = r1.y;
+                s.c_n[slot][0] = r1.z; s.c_n[slot][1] = r1.w; s.c_n[slot][2] = r2.x;
+                s.c_dist[slot] = r2.y; s.c_sa[slot] = __float_as_int(r2.z); s.c_sb[slot] = __float_as_int(r2.w);
+                float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * slot;
+                c[0] = r0.x; c[1] = r0.y; c[2] = r0.z; c[3] = r0.w; c[4] = r1.x; c[5] = r1.y; c[6] = r1.z; c[7] = r1.w; c[8] = r2.x;
+                c[9] = r2.y; c[10] = r2.z; c[11] = r2.w; c[12] = 0.0f;
+            }
+            ncontact += __popc(bal);
         }
+        if (ncontact > kMaxC) { overflow |= 1; ncontact = kMaxC; }        // flagged (AVG_E_OVERFLOW, info), never silent
         if (lane == 0) scr_i[AVG_S_NC] = ncontact;
     }
     __syncwarp();
-    if (lane < nb) {                         // body poses: forward kinematics was done by the collide kernel
+    if (lane < nb + h->n_ebody) {            // body poses: forward kinematics was done by the collide kernel
         const float4* gp = reinterpret_cast<const float4*>(scr + AVG_S_POSE) + 2 * lane;
         const float4 p4 = gp[0], q4 = gp[1];
         s.bp[lane][0] = p4.x; s.bp[lane][1] = p4.y; s.bp[lane][2] = p4.z;
@@ -1196,6 +1311,9 @@ avg_dynamics_kernel(AvgStepArgs a) {
         V3 p = ld3(s.bp[lane]); Q4 q = ldq(s.bq[lane]);
         M3 R = qmat(q);
         float i0 = B->inertia[0], i1 = B->inertia[1], i2 = B->inertia[2];
+        // changeDynamics(mass=0) per episode (world_creation.py:157-161: the head chain of Feeding / Drinking unless the episode
+        // drew a tremor): a massless subtree gives M_kk = 0, which the inverse below turns into a frozen dof
+        if ((__float_as_uint(grec[AVG_E_FROZEN]) >> lane) & 1u) { mass = 0.0f; i0 = i1 = i2 = 0.0f; }
         Ic[0] = R.m[0] * R.m[0] * i0 + R.m[1] * R.m[1] * i1 + R.m[2] * R.m[2] * i2;
         Ic[1] = R.m[3] * R.m[3] * i0 + R.m[4] * R.m[4] * i1 + R.m[5] * R.m[5] * i2;
         Ic[2] = R.m[6] * R.m[6] * i0 + R.m[7] * R.m[7] * i1 + R.m[8] * R.m[8] * i2;
@@ -1245,6 +1363,10 @@ avg_dynamics_kernel(AvgStepArgs a) {
             int aa = __shfl_sync(AVG_FULL, anc, src);
             if (anc >= 0) { V = V + av; anc = aa; }
         }
+    }
+    if (h->n_particle > 0) {                 // start-of-step body twists for the one-way particle-vs-link contacts (solve kernel)
+        float4* tw = reinterpret_cast<float4*>(scr + AVG_S_TWIST) + 2 * lane;
+        tw[0] = make_float4(V.a.x, V.a.y, V.a.z, 0.0f); tw[1] = make_float4(V.l.x, V.l.y, V.l.z, 0.0f);
     }
     Sv Ab = crm(V, vj);
     {
@@ -1416,7 +1538,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     // (normal + friction) two more.
     auto jcol = [&](int body, V3 r, V3& cl, V3& cw) {
         cl = mk3(0, 0, 0); cw = mk3(0, 0, 0);
-        if (body < 0) return;
+        if (body < 0 || body >= nb) return;              // static world / env-static body
         const AvgBody* B = &m.body[body];
         if (B->jtype == AVG_JOINT_FREE) {
             const int k = lane - B->dof;
@@ -1547,6 +1669,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
 
     // ---- hand-off to the solver -----------------------------------------------------------------------------------
+    if (h->n_particle > 0 && lane < 24) scr[AVG_S_FREEINV + lane] = (&s.freeInv[0][0])[lane];
     if (lane < nd) scr[AVG_S_QD + lane] = qd;
 #pragma unroll
     for (int t = 0; t < MAXBLK; ++t) scr[AVG_S_MINV + t * 32 + lane] = mc[t];       // [t][lane]: row bs(lane)+t, column lane
@@ -1590,12 +1713,318 @@ __device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, 
 }
 
 // =================================================================================================================
+// Food / water particles (feeding.py:291-320, drinking.py:291-322) inside the solver kernel.
+//
+// 8 or 64 free spheres of 5 mm / 1 g.  Their contact rows belong to the same projected Gauss-Seidel sweep as the rows of the
+// articulation (a particle on the spoon loads the spoon, the spoon is welded to the gripper), in Bullet's order: ... contact
+// normals (articulation, then particles), friction (articulation, then particles).  A particle row touches one particle and,
+// on its other side, another particle, the tool (free body, two-way) or something kinematic (static shape, or a robot / human
+// link with its start-of-step velocity: one-way).  Rows that share no body commute, so the strictly ordered
+// sweep of the oracle is executed here in ROUNDS: a greedy schedule puts every row in the first round after the rows before it
+// (canonical contact order) that use one of its bodies, <= 32 rows per round, one lane per row -- the same numbers as the
+// sequential sweep, up to 32 rows at a time.  Particle velocities and the tool's six velocity components live in shared
+// memory during these phases; the per-contact records (20 floats) stay in the particle scratch arena (L1 / L2).
+// =================================================================================================================
+// NP / NPC: particles / particle contacts the instance holds (Feeding: 8 / 64, Drinking: 64 / AVG_MAX_PCONTACT): the small
+// instance keeps the solver kernel's shared memory per warp low enough for the register-limited occupancy.
+template <int NP, int NPC>
+struct __align__(16) SmPartT {
+    static constexpr int kNP = NP, kNPC = NPC;
+    float pv[6][NP];                       // unconstrained velocities after gravity / damping (v*, w*), component-major
+    float pdv[6][NP];                      // velocity changes accumulated by the solver
+    float px[3][NP];                       // centres
+    float tdv[8];                          // the tool's six velocity changes while particle rows run
+    float tinv[12];                        // tool: 1 / m, world inverse inertia (row-major 3 x 3 from [1])
+    float tpos[4];                         // tool body frame origin (its COM)
+    float tqd[8];                          // tool velocity after the unconstrained update
+    uint32_t touch[4];                     // particles with a contact point on the human [0..1] / on the table or the bowl [2..3]
+    float lam[2][NPC];                     // accumulated normal / friction impulses, indexed like the sorted records
+    uint16_t order[NPC];                   // contact indices sorted by round
+    uint16_t round_of[NPC];
+    uint16_t rstart[NPC + 2];              // first entry of each round in `order`
+    uint16_t last[66];                     // greedy schedule: first round a new row of particle p / the tool (slot 64) may use
+    uint8_t fill[NPC + 2];
+};
+using SmPartSmall = SmPartT<8, 64>;
+using SmPartLarge = SmPartT<64, AVG_MAX_PCONTACT>;
+
+namespace {
+__device__ __forceinline__ V3 plane_space1(V3 n) {       // btPlaneSpace1
+    if (fabsf(n.z) > 0.70710678f) { const float k = rsqrtf(n.y * n.y + n.z * n.z); return mk3(0, -n.z * k, n.y * k); }
+    const float k = rsqrtf(n.x * n.x + n.y * n.y); return mk3(-n.y * k, n.x * k, 0);
+}
+template <int NP>
+__device__ __forceinline__ V3 sm3(const float (*a)[NP], int base, int p) { return mk3(a[base][p], a[base + 1][p], a[base + 2][p]); }
+__device__ __forceinline__ V3 tinv_mul(const float* ti, V3 v) {
+    return mk3(ti[1] * v.x + ti[2] * v.y + ti[3] * v.z, ti[4] * v.x + ti[5] * v.y + ti[6] * v.z, ti[7] * v.x + ti[8] * v.y + ti[9] * v.z);
+}
+
+// One contact record: row data of the normal and the friction row of a particle contact (see the header comment).
+// [0..2] n  [3] target_n  [4] 1/diag_n  [5] lambda_n  [6..8] t  [9] target_t  [10] 1/diag_t  [11] lambda_t  [12] mu
+// [13] p | q << 8 | kind << 16  [14..16] lever arm on the tool  [17] diag_n  [18] diag_t
+template <class SP>
+__device__ void particle_record(const KM& m, const SP& sp, const float* scr, float* rec, V3 n, float dist, int p, int q, int shape_b,
+                                float dt, uint32_t* touch) {
+    const AvgModelHeader* h = m.h;
+    const AvgShape* PS = &m.shape[h->pshape];
+    const float r = PS->radius, inv_m = 1.0f / h->p_mass, inv_i = 1.0f / (0.4f * h->p_mass * r * r);
+    const V3 xa = sm3(sp.px, 0, p), va = sm3(sp.pv, 0, p), wa = sm3(sp.pv, 3, p);
+    const V3 ra = n * (-r);
+    V3 vrel = va + cross(wa, ra);
+    int kind = 0;
+    float mu_b = PS->friction;
+    V3 rb = mk3(0, 0, 0);
+    float dn = inv_m, dtg = inv_m + r * r * inv_i;                       // (ra x t)^2 = r^2 for a unit tangent
+    if (q >= 0) {
+        kind = 1;
+        vrel = vrel - (sm3(sp.pv, 0, q) + cross(sm3(sp.pv, 3, q), n * r));
+        dn += inv_m; dtg += inv_m + r * r * inv_i;
+    } else {
+        const AvgShape* SB = &m.shape[shape_b];
+        mu_b = SB->friction;
+        const int body = SB->body;
+        const V3 pb = xa - n * (r + dist);
+        if (body >= 0 && body == h->tool_body) {
+            kind = 2;
+            rb = pb - mk3(sp.tpos[0], sp.tpos[1], sp.tpos[2]);
+            vrel = vrel - (mk3(sp.tqd[0], sp.tqd[1], sp.tqd[2]) + cross(mk3(sp.tqd[3], sp.tqd[4], sp.tqd[5]), rb));
+        } else if (body >= 0 && body < h->n_body) {
+            kind = 3;
+            const float4* tw = reinterpret_cast<const float4*>(scr + AVG_S_TWIST) + 2 * body;
+            const float4 wa4 = tw[0], vl4 = tw[1];
+            const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
+            vrel = vrel - (mk3(vl4.x, vl4.y, vl4.z) + cross(mk3(wa4.x, wa4.y, wa4.z), pb - ref));
+        }
+        const int rbd = SB->ref_body;
+        if (rbd == AVG_REF_HUMAN) atomicOr(&touch[p >> 5], 1u << (p & 31));
+        if (rbd == AVG_REF_TABLE || rbd == AVG_REF_BOWL) atomicOr(&touch[2 + (p >> 5)], 1u << (p & 31));
+    }
+    const float vn = dot(vrel, n);
+    const V3 lat = vrel - n * vn;
+    const float ll = norm(lat);
+    const V3 t = ll > 1e-6f ? lat * (1.0f / ll) : plane_space1(n);
+    if (kind == 2) {
+        const V3 jn = cross(rb, n), jt = cross(rb, t);
+        dn += sp.tinv[0] + dot(jn, tinv_mul(sp.tinv, jn));
+        dtg += sp.tinv[0] + dot(jt, tinv_mul(sp.tinv, jt));
+    }
+    rec[0] = n.x; rec[1] = n.y; rec[2] = n.z;
+    rec[3] = (dist > 0.0f ? -dist / dt : -dist * h->erp / dt) - vn;
+    rec[4] = dn > 1e-12f ? 1.0f / dn : 0.0f; rec[5] = 0.0f;
+    rec[6] = t.x; rec[7] = t.y; rec[8] = t.z;
+    rec[9] = -dot(vrel, t);
+    rec[10] = dtg > 1e-12f ? 1.0f / dtg : 0.0f; rec[11] = 0.0f;
+    rec[12] = PS->friction * mu_b;
+    rec[13] = __int_as_float(p | ((q >= 0 ? q : 0xff) << 8) | (kind << 16));
+    rec[14] = rb.x; rec[15] = rb.y; rec[16] = rb.z; rec[17] = dn; rec[18] = dtg; rec[19] = 0.0f;
+}
+
+// Prologue of the particle part of one internal step: unconstrained particle velocities, contact records, touch masks and
+// the round schedule.  Returns the number of contacts; nrounds through the reference.
+template <class SP>
+__device__ int particles_prepare(const KM& m, SP& sp, const AvgStepArgs& a, int e, const float* scr, int lane, float dt, int& nrounds, int& overflow) {
+    const AvgModelHeader* h = m.h;
+    const int np = h->n_particle;
+    float* ps = a.pscratch + (size_t)e * AVG_PS_STRIDE;
+    const int* ps_i = reinterpret_cast<const int*>(ps);
+    const float* prec = a.part + (size_t)e * AVG_P_STRIDE;
+    const uint32_t alive0 = __float_as_uint(prec[AVG_P_ALIVE]), alive1 = __float_as_uint(prec[AVG_P_ALIVE + 1]);
+    const V3 g = mk3(h->p_gravity[0], h->p_gravity[1], h->p_gravity[2]);
+    for (int p = lane; p < SP::kNP; p += 32) {
+        const bool live = p < np && (((p < 32 ? alive0 : alive1) >> (p & 31)) & 1u);
+        V3 x = mk3(0, 0, 0), v = x, w = x;
+        if (live) {
+            x = mk3(prec[AVG_P_POS + p], prec[AVG_P_POS + 64 + p], prec[AVG_P_POS + 128 + p]);
+            v = mk3(prec[AVG_P_VEL + p], prec[AVG_P_VEL + 64 + p], prec[AVG_P_VEL + 128 + p]);
+            w = mk3(prec[AVG_P_ANG + p], prec[AVG_P_ANG + 64 + p], prec[AVG_P_ANG + 128 + p]);
+            // gravity and the multibody base damping (0.04, as for every other body of the step)
+            v = v + (g - v * (h->lin_damp + h->lin_damp * norm(v))) * dt;
+            w = w - w * ((h->ang_damp + h->ang_damp * norm(w)) * dt);
+        }
+        sp.px[0][p] = x.x; sp.px[1][p] = x.y; sp.px[2][p] = x.z;
+        sp.pv[0][p] = v.x; sp.pv[1][p] = v.y; sp.pv[2][p] = v.z; sp.pv[3][p] = w.x; sp.pv[4][p] = w.y; sp.pv[5][p] = w.z;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sp.pdv[k][p] = 0.0f;
+    }
+    const int tb = h->tool_body;
+    if (tb >= 0) {
+        const int td = m.body[tb].dof, fbi = (td - h->n_jdof) / 6;
+        if (lane < 12) sp.tinv[lane] = scr[AVG_S_FREEINV + 12 * fbi + lane];
+        if (lane < 6) sp.tqd[lane] = scr[AVG_S_QD + td + lane];
+        if (lane < 3) sp.tpos[lane] = scr[AVG_S_POSE + 8 * tb + lane];
+    }
+    if (lane < 4) sp.touch[lane] = 0u;
+    if (lane < 6) sp.tdv[lane] = 0.0f;
+    __syncwarp();
+    // contact records in canonical order: hits among the particle-vs-shape candidates (particle-major, shape index ascending),
+    // then the particle-particle contacts
+    float* rec = ps + AVG_PS_REC;
+    const int ncand = min(ps_i[AVG_PS_NCAND], AVG_MAX_PCAND), npp = min(ps_i[AVG_PS_NPP], AVG_PS_MAXPP);
+    int nc = 0;
+    const float4* cand = reinterpret_cast<const float4*>(ps + AVG_PS_CAND);
+#pragma unroll 1
+    for (int base = 0; base < ncand; base += 32) {
+        const int i = base + lane;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+        bool hit = false;
+        if (i < ncand) { r1 = cand[2 * i + 1]; hit = r1.z != 0.0f; if (hit) r0 = cand[2 * i]; }
+        const unsigned bal = __ballot_sync(AVG_FULL, hit);
+        const int slot = nc + __popc(bal & ((1u << lane) - 1));
+        if (hit && slot < SP::kNPC)
+            particle_record(m, sp, scr, rec + AVG_PS_REC_STRIDE * slot, mk3(r0.x, r0.y, r0.z), r0.w, __float_as_int(r1.x), -1, __float_as_int(r1.y), dt, sp.touch);
+        nc += __popc(bal);
+    }
+    const float4* pp = reinterpret_cast<const float4*>(ps + AVG_PS_PP);
+#pragma unroll 1
+    for (int base = 0; base < npp; base += 32) {
+        const int i = base + lane, slot = nc + i;
+        if (i < npp && slot < SP::kNPC) {
+            const float4 r0 = pp[2 * i], r1 = pp[2 * i + 1];
+            particle_record(m, sp, scr, rec + AVG_PS_REC_STRIDE * slot, mk3(r0.x, r0.y, r0.z), r0.w, __float_as_int(r1.x), __float_as_int(r1.y), -1, dt, sp.touch);
+        }
+    }
+    nc += npp;
+    if (nc > SP::kNPC) { overflow |= 8; nc = SP::kNPC; }
+    if (ps_i[AVG_PS_OVERFLOW]) overflow |= ps_i[AVG_PS_OVERFLOW];
+    __syncwarp();
+    // greedy round schedule (serial: ~20 instructions per contact, once per internal step)
+    for (int i = lane; i < 66; i += 32) sp.last[i] = 0;
+    for (int i = lane; i < nc + 2; i += 32) sp.fill[i] = 0;
+    __syncwarp();
+    int nr = 0;
+    if (lane == 0) {
+        for (int c = 0; c < nc; ++c) {
+            const int pk = __float_as_int(rec[AVG_PS_REC_STRIDE * c + 13]);
+            const int p = pk & 0xff, q = (pk >> 8) & 0xff, kind = pk >> 16;
+            int r = sp.last[p];
+            if (kind == 1) r = max(r, (int)sp.last[q]);
+            if (kind == 2) r = max(r, (int)sp.last[64]);
+            while (sp.fill[r] >= 32) ++r;
+            sp.round_of[c] = (uint16_t)r; sp.fill[r]++;
+            sp.last[p] = (uint16_t)(r + 1);
+            if (kind == 1) sp.last[q] = (uint16_t)(r + 1);
+            if (kind == 2) sp.last[64] = (uint16_t)(r + 1);
+            nr = max(nr, r + 1);
+        }
+        int acc = 0;
+        for (int r = 0; r < nr; ++r) { sp.rstart[r] = (uint16_t)acc; acc += sp.fill[r]; sp.fill[r] = 0; }
+        sp.rstart[nr] = (uint16_t)acc;
+        for (int c = 0; c < nc; ++c) { const int r = sp.round_of[c]; sp.order[sp.rstart[r] + sp.fill[r]] = (uint16_t)c; sp.fill[r]++; }
+    }
+    nrounds = __shfl_sync(AVG_FULL, nr, 0);
+    __syncwarp();
+    // the records in round order, so that the rows of a round are adjacent (one vector load per lane and float4)
+    {
+        const float4* src = reinterpret_cast<const float4*>(rec);
+        float4* dst = reinterpret_cast<float4*>(ps + AVG_PS_SORTED);
+        for (int i = lane; i < 5 * nc; i += 32) { const int row = i / 5, k = i - 5 * row; dst[i] = src[5 * sp.order[row] + k]; }
+        for (int i = lane; i < nc; i += 32) { sp.lam[0][i] = 0.0f; sp.lam[1][i] = 0.0f; }
+    }
+    __syncwarp();
+    return nc;
+}
+
+// One sweep over the particle rows (normal rows, or friction rows), round by round; `srec` = records in round order.  The
+// records of the next round are fetched while the current one is computed (they do not depend on it; only the impulses and
+// velocities in shared memory do).  Returns the largest |delta| * diag.
+template <bool FRICTION, class SP>
+__device__ __forceinline__ float particles_sweep(const KM& m, SP& sp, const float* srec, int nrounds, int lane) {
+    const AvgModelHeader* h = m.h;
+    const float r = m.shape[h->pshape].radius, inv_m = 1.0f / h->p_mass, inv_i = 1.0f / (0.4f * h->p_mass * r * r);
+    const float4* R4 = reinterpret_cast<const float4*>(srec);
+    float resid = 0.0f;
+    float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0, n4 = n0;
+    {
+        const int cnt = nrounds > 0 ? sp.rstart[1] - sp.rstart[0] : 0;
+        if (lane < cnt) { const float4* q = R4 + 5 * lane; n0 = q[0]; n1 = q[1]; if (FRICTION) n2 = q[2]; n3 = q[3]; n4 = q[4]; }
+    }
+#pragma unroll 1
+    for (int rd = 0; rd < nrounds; ++rd) {
+        const int s0 = sp.rstart[rd], s1 = sp.rstart[rd + 1], cnt = s1 - s0;
+        const float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3, c4 = n4;
+        if (rd + 1 < nrounds) {
+            const int cn = sp.rstart[rd + 2] - s1;
+            if (lane < cn) { const float4* q = R4 + 5 * (s1 + lane); n0 = q[0]; n1 = q[1]; if (FRICTION) n2 = q[2]; n3 = q[3]; n4 = q[4]; }
+        }
+        if (lane < cnt) {
+            const int idx = s0 + lane;
+            // c0 = n, target_n | c1 = 1/diag_n, lambda_n (unused), t.x, t.y | c2 = t.z, target_t, 1/diag_t, lambda_t (unused)
+            // c3 = mu, packed, rb.x, rb.y | c4 = rb.z, diag_n, diag_t, pad
+            const int pk = __float_as_int(c3.y);
+            const int p = pk & 0xff, q = (pk >> 8) & 0xff, kind = pk >> 16;
+            const V3 n = mk3(c0.x, c0.y, c0.z);
+            const V3 d = FRICTION ? mk3(c1.z, c1.w, c2.x) : n;
+            const V3 ja = FRICTION ? cross(n, d) * (-r) : mk3(0, 0, 0);        // A's angular Jacobian: lever -r n (zero for the normal row)
+            float jdv = dot(d, sm3(sp.pdv, 0, p));
+            if (FRICTION) jdv += dot(ja, sm3(sp.pdv, 3, p));
+            V3 jb = mk3(0, 0, 0);
+            if (kind == 1) {
+                jdv -= dot(d, sm3(sp.pdv, 0, q));
+                if (FRICTION) { jb = cross(n, d) * r; jdv -= dot(jb, sm3(sp.pdv, 3, q)); }
+            } else if (kind == 2) {
+                jb = cross(mk3(c3.z, c3.w, c4.x), d);
+                jdv -= dot(d, mk3(sp.tdv[0], sp.tdv[1], sp.tdv[2])) + dot(jb, mk3(sp.tdv[3], sp.tdv[4], sp.tdv[5]));
+            }
+            const float lam = sp.lam[FRICTION ? 1 : 0][idx];
+            float sum = fmaf((FRICTION ? c2.y : c0.w) - jdv, FRICTION ? c2.z : c1.x, lam);
+            if (FRICTION) { const float lim = c3.x * sp.lam[0][idx]; sum = fminf(fmaxf(sum, -lim), lim); }
+            else sum = fmaxf(sum, 0.0f);
+            const float delta = sum - lam;
+            sp.lam[FRICTION ? 1 : 0][idx] = sum;
+            const float dm = delta * inv_m;
+            sp.pdv[0][p] += d.x * dm; sp.pdv[1][p] += d.y * dm; sp.pdv[2][p] += d.z * dm;
+            if (FRICTION) { const float di = delta * inv_i; sp.pdv[3][p] += ja.x * di; sp.pdv[4][p] += ja.y * di; sp.pdv[5][p] += ja.z * di; }
+            if (kind == 1) {
+                sp.pdv[0][q] -= d.x * dm; sp.pdv[1][q] -= d.y * dm; sp.pdv[2][q] -= d.z * dm;
+                if (FRICTION) { const float di = delta * inv_i; sp.pdv[3][q] -= jb.x * di; sp.pdv[4][q] -= jb.y * di; sp.pdv[5][q] -= jb.z * di; }
+            } else if (kind == 2) {
+                const float dmt = delta * sp.tinv[0];
+                const V3 wj = tinv_mul(sp.tinv, jb) * delta;
+                sp.tdv[0] -= d.x * dmt; sp.tdv[1] -= d.y * dmt; sp.tdv[2] -= d.z * dmt;
+                sp.tdv[3] -= wj.x; sp.tdv[4] -= wj.y; sp.tdv[5] -= wj.z;
+            }
+            resid = fmaxf(resid, fabsf(delta) * (FRICTION ? c4.z : c4.y));
+        }
+        __syncwarp();
+    }
+    return resid;
+}
+
+// End of the internal step: integrate the live particles and publish the touch masks (feeding.py:111,116 read them).
+template <class SP>
+__device__ void particles_finish(const KM& m, const SP& sp, const AvgStepArgs& a, int e, int lane, float dt, int nc, int overflow) {
+    const AvgModelHeader* h = m.h;
+    const int np = h->n_particle;
+    float* prec = a.part + (size_t)e * AVG_P_STRIDE;
+    const uint32_t alive0 = __float_as_uint(prec[AVG_P_ALIVE]), alive1 = __float_as_uint(prec[AVG_P_ALIVE + 1]);
+    for (int p = lane; p < np; p += 32) {
+        if (!(((p < 32 ? alive0 : alive1) >> (p & 31)) & 1u)) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = sp.pv[k][p] + sp.pdv[k][p];
+            prec[AVG_P_VEL + 64 * k + p] = v;
+            prec[AVG_P_ANG + 64 * k + p] = sp.pv[3 + k][p] + sp.pdv[3 + k][p];
+            prec[AVG_P_POS + 64 * k + p] = sp.px[k][p] + dt * v;
+        }
+    }
+    if (lane < 2) prec[AVG_P_TOUCH_HUMAN + lane] = __uint_as_float(sp.touch[lane]);
+    else if (lane < 4) prec[AVG_P_TOUCH_SPILL + lane - 2] = __uint_as_float(sp.touch[lane]);
+    if (lane == 0) {
+        reinterpret_cast<int*>(prec)[AVG_P_NCONTACT] = nc;
+        if (overflow) reinterpret_cast<int*>(prec)[AVG_P_NCONTACT + 1] |= overflow;
+    }
+}
+}  // namespace
+
+// =================================================================================================================
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
-template <int MAXBLK>
-__global__ void __launch_bounds__(32, AVG_OCC_SOLVE)
+// PART: 0 no particles, 1 Feeding (8 particles), 2 Drinking (64 particles)
+template <int MAXBLK, int PART>
+__global__ void __launch_bounds__(32, PART ? 20 : AVG_OCC_SOLVE)
 avg_solve_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmSolve)
+    AVG_MASK_CHECK
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
     int* scr_i = reinterpret_cast<int*>(scr);
@@ -1652,7 +2081,17 @@ avg_solve_kernel(AvgStepArgs a) {
     //      block hold all-zero rows (1/diag = 0), which makes their delta exactly 0.
     //      Dense rows follow in strict order: the six weld rows unrolled with J, W and impulses in registers, then
     //      the contact rows (rare) from shared memory / the arena with the impulse of row d in lane d.
-    float dv = 0.0f, lamL = 0.0f, lamD = 0.0f;
+    float dv = 0.0f, lamL = 0.0f, lamD0 = 0.0f, lamD1 = 0.0f, lamD2 = 0.0f;      // impulse of dense row d: lane d & 31, register d >> 5
+    // particles (Feeding / Drinking): records, schedule and unconstrained velocities for this internal step
+    using SP = typename std::conditional<PART == 2, SmPartLarge, SmPartSmall>::type;
+    SP* spp = PART ? reinterpret_cast<SP*>(smem_raw + sizeof(SmSolve)) : nullptr;
+    int npc = 0, nrounds = 0, p_overflow = 0, tool_dof = -1;
+    float* prec_rows = nullptr;
+    if (PART) {
+        npc = particles_prepare(m, *spp, a, e, scr, lane, dt, nrounds, p_overflow);
+        prec_rows = a.pscratch + (size_t)e * AVG_PS_STRIDE + AVG_PS_SORTED;
+        tool_dof = h->tool_body >= 0 ? m.body[h->tool_body].dof : -1;
+    }
     float lamM[MAXBLK], lamW[6], jw[6];
 #pragma unroll
     for (int t = 0; t < MAXBLK; ++t) lamM[t] = 0.0f;
@@ -1696,18 +2135,26 @@ avg_solve_kernel(AvgStepArgs a) {
             dv = fmaf(s.W[d][lane], delta, dv);
             resid = fmaxf(resid, fabsf(delta) * ra.z);
         }
+        auto lam_get = [&](int d) { return __shfl_sync(AVG_FULL, d < 32 ? lamD0 : (d < 64 ? lamD1 : lamD2), d & 31); };
+        auto lam_set = [&](int d, float v) { if (lane == (d & 31)) { if (d < 32) lamD0 = v; else if (d < 64) lamD1 = v; else lamD2 = v; } };
 #pragma unroll 1
         for (int d = 6; d < nfr; ++d) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
             const float jdv = dense_dot(*jp, dv);
-            const float lam = __shfl_sync(AVG_FULL, lamD, d);
+            const float lam = lam_get(d);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), ra.z), ra.w);
             const float delta = sum - lam;
-            if (lane == d) lamD = sum;
+            lam_set(d, sum);
             dv = fmaf(*wp, delta, dv);
             resid = fmaxf(resid, fabsf(delta) * rb.x);
+        }
+        if (PART && npc > 0) {                                       // particle contact normals (after the articulation's, Bullet's order)
+            if (tool_dof >= 0 && lane >= tool_dof && lane < tool_dof + 6) spp->tdv[lane - tool_dof] = dv;
+            __syncwarp();
+            resid = fmaxf(resid, particles_sweep<false, SP>(m, *spp, prec_rows, nrounds, lane));
+            if (tool_dof >= 0 && lane >= tool_dof && lane < tool_dof + 6) dv = spp->tdv[lane - tool_dof];
         }
 #pragma unroll 1
         for (int d = nfr; d < ndense; ++d) {
@@ -1716,22 +2163,31 @@ avg_solve_kernel(AvgStepArgs a) {
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
             const float jdv = dense_dot(*jp, dv);
-            const float lam = __shfl_sync(AVG_FULL, lamD, d);
-            const float lim = rb.y * __shfl_sync(AVG_FULL, lamD, par);
+            const float lam = lam_get(d);
+            const float lim = rb.y * lam_get(par);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -lim), lim);
             const float delta = sum - lam;
-            if (lane == d) lamD = sum;
+            lam_set(d, sum);
             dv = fmaf(*wp, delta, dv);
             resid = fmaxf(resid, fabsf(delta) * rb.x);
+        }
+        if (PART && npc > 0) {                                       // particle friction rows
+            if (tool_dof >= 0 && lane >= tool_dof && lane < tool_dof + 6) spp->tdv[lane - tool_dof] = dv;
+            __syncwarp();
+            resid = fmaxf(resid, particles_sweep<true, SP>(m, *spp, prec_rows, nrounds, lane));
+            if (tool_dof >= 0 && lane >= tool_dof && lane < tool_dof + 6) dv = spp->tdv[lane - tool_dof];
         }
         iters++;
         if (!__any_sync(AVG_FULL, resid > thr)) break;              // blocks ran in different lanes
     }
 
     // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
-    if (lane >= first_contact_row && lane < first_contact_row + nc)
-        scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * (lane - first_contact_row) + 12] = lamD;
+    for (int c = 0; c < nc; ++c) {
+        const int d = first_contact_row + c;
+        if (lane == (d & 31)) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c + 12] = d < 32 ? lamD0 : (d < 64 ? lamD1 : lamD2);
+    }
     if (lane == 0) scr_i[AVG_S_ITERS] += iters;
+    if (PART) particles_finish(m, *spp, a, e, lane, dt, npc, p_overflow);
 
     // ---- integrate (semi-implicit Euler), enforce_realistic_human_joint_limits (env.py:353-371, human-active ids),
     //      enforce_hard_human_joint_limits (env.py:389-410) -----------------------------------------------------------
@@ -1740,7 +2196,9 @@ avg_solve_kernel(AvgStepArgs a) {
     const bool is_jlane = lane < nb && m.body[lane].jtype != AVG_JOINT_FREE;
     float qn = 0.0f;
     if (is_jlane) qn = grec[AVG_E_Q + m.body[lane].qidx] + dt * v;
-    if (h->human_control && m.mlp && h->mlp_dof[0] >= 0) {
+    // the reference's per-frame hooks run after every p.stepSimulation call (env.py:343-349), i.e. after the LAST internal
+    // step of a frame when numSubSteps > 1
+    if (a.post && h->human_control && m.mlp && h->mlp_dof[0] >= 0) {
         float q4[4], x[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) q4[k] = __shfl_sync(AVG_FULL, qn, h->mlp_dof[k]);
@@ -1757,7 +2215,7 @@ avg_solve_kernel(AvgStepArgs a) {
     }
     if (is_jlane) {
         const AvgDof* D = &m.dof[lane];
-        if (D->flags & AVG_DOF_HARD_LIMIT) {
+        if (a.post && (D->flags & AVG_DOF_HARD_LIMIT)) {
             const float sc = grec[AVG_E_LIMIT_SCALE];
             const float lo = D->lower * sc, hi = D->upper * sc;
             if (qn < lo) { qn = lo; v = 0.0f; }
@@ -1842,7 +2300,7 @@ avg_epilogue_kernel(AvgStepArgs a) {
         const float av = lane < na ? act[lane] : 0.0f;
         raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, scratch_itch.py:64
     }
-    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body, s.env + AVG_E_EBODY);
     frames_warp(m, s, lane);
     V3 tgt; { V3 lp; Q4 lq; frame_cached(s, env_i[AVG_E_LIMB_FRAME], lp, lq); tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM)); }
     const float dt = h->dt;
@@ -2075,7 +2533,7 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
         const float av = lane < na ? act[lane] : 0.0f;
         raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, bed_bathing.py:62
     }
-    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body, s.env + AVG_E_EBODY);
     frames_warp(m, s, lane);
     const float dt = h->dt;
     const float* tf = h->task_f;
@@ -2209,6 +2667,378 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
     if (a.contacts) dump_contacts(a, e, scr, ncontact, dt, lane);
 }
 
+// =================================================================================================================
+// Feeding / Drinking epilogue (feeding.py:56-142, drinking.py:57-157): get_total_force, get_food_rewards /
+// get_water_rewards with one lane per particle, human_preferences (env.py:412-448, feeding branch), reward, observation, info
+// =================================================================================================================
+namespace {
+// feeding.py:123-142 / drinking.py:138-157 (lane 0 fills s.obs)
+template <class SM>
+__device__ void fill_obs_fd(const KM& m, SM& s, V3 mouth, float tool_force_on_human, float robot_force_on_human) {
+    const AvgModelHeader* h = m.h;
+    const int nj = h->n_jdof;
+    V3 torso, tool, head, chest; Q4 tq, hq, dq;
+    frame_cached(s, AVG_F_TORSO, torso, dq);
+    frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
+    frame_cached(s, AVG_F_HEAD, head, hq);
+    frame_cached(s, AVG_F_CHEST, chest, dq);
+    float* o = s.obs; int k = 0;
+    V3 t;
+    t = tool - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+    t = tool - mouth; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    for (int i = 0; i < nj; ++i) if (m.dof[i].action >= 0 && m.dof[i].action < h->n_action_robot) o[k++] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx];
+    t = head - torso; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+    o[k++] = hq.x; o[k++] = hq.y; o[k++] = hq.z; o[k++] = hq.w;
+    o[k++] = tool_force_on_human;
+    if (h->human_control) {
+        t = tool - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = tq.x; o[k++] = tq.y; o[k++] = tq.z; o[k++] = tq.w;
+        t = tool - mouth; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        const int hq0 = k;
+        for (int i = 0; i < 4; ++i) o[k++] = 0.0f;
+        for (int i = 0; i < nj; ++i) { const int sl = m.dof[i].human_slot; if (sl >= 0 && sl < 4) o[hq0 + sl] = s.env[AVG_E_Q + m.body[m.dof[i].body].qidx]; }
+        t = head - chest; o[k++] = t.x; o[k++] = t.y; o[k++] = t.z;
+        o[k++] = hq.x; o[k++] = hq.y; o[k++] = hq.z; o[k++] = hq.w;
+        o[k++] = robot_force_on_human; o[k++] = tool_force_on_human;
+    }
+}
+// btQuaternion::getEulerZYX roll, what p.getEulerFromQuaternion(q)[0] returns (drinking.py:71)
+__device__ __forceinline__ float quat_roll(Q4 q) {
+    const float sqx = q.x * q.x, sqy = q.y * q.y, sqz = q.z * q.z, sqw = q.w * q.w;
+    const float sarg = -2.0f * (q.x * q.z - q.w * q.y) / (sqx + sqy + sqz + sqw);
+    if (sarg <= -0.99999f || sarg >= 0.99999f) return 0.0f;
+    return atan2f(2.0f * (q.y * q.z + q.w * q.x), sqw - sqx - sqy + sqz);
+}
+template <class SM>
+__device__ __forceinline__ V3 fd_mouth(const KM& m, const SM& s) {
+    V3 hp; Q4 hq; frame_cached(s, AVG_F_HEAD, hp, hq);
+    const float* tf = m.h->task_f;
+    return hp + qrot(hq, mk3(tf[AVG_TF_MOUTH], tf[AVG_TF_MOUTH + 1], tf[AVG_TF_MOUTH + 2]));
+}
+}  // namespace
+
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_epilogue_fd_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmEpi)
+    for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
+    __syncwarp();
+    int* env_i = reinterpret_cast<int*>(s.env);
+    const int* scr_i = reinterpret_cast<const int*>(scr);
+    const int na = h->n_action_robot + h->n_action_human;
+    const float* act = a.actions + (size_t)e * na;
+    float raw_sq;
+    {
+        const float av = lane < na ? act[lane] : 0.0f;
+        raw_sq = warp_sum(av * av);                          // reward_action uses the raw action, feeding.py:69
+    }
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body, s.env + AVG_E_EBODY);
+    frames_warp(m, s, lane);
+    const float dt = h->dt;
+    const float* tf = h->task_f;
+    const bool drinking = h->task == AVG_TASK_DRINKING;
+    const int ncontact = scr_i[AVG_S_NCS];
+    // get_total_force, feeding.py:83-90
+    float robot_force_on_human = 0, tool_force_on_human = 0;
+    for (int ci = 0; ci < ncontact; ++ci) {
+        const float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * ci;
+        const AvgShape* sa = &m.shape[__float_as_int(c[10])]; const AvgShape* sb = &m.shape[__float_as_int(c[11])];
+        const float force = c[12] / dt;
+        const bool a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        const bool a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        const bool a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if ((a_rob && b_hum) || (b_rob && a_hum)) robot_force_on_human += force;
+        if ((a_tool && b_hum) || (b_tool && a_hum)) tool_force_on_human += force;
+    }
+    const V3 mouth = fd_mouth(m, s);
+    V3 tool; Q4 tq; frame_cached(s, AVG_F_TOOL_TIP, tool, tq);
+    // the cup's frame and the ends of its cylinder, drinking.py:97-102
+    V3 top = tool, bottom = tool; Q4 cup_q = tq;
+    if (drinking) {
+        const V3 cup_p = tool + qrot(tq, mk3(0.0f, 0.06f, 0.0f));
+        cup_q = qnormalize(qmul(tq, qaxis(mk3(1, 0, 0), 1.57079632679f)));
+        top = cup_p + qrot(cup_q, mk3(0, 0, tf[AVG_TF_CUP_TOP])); bottom = cup_p + qrot(cup_q, mk3(0, 0, tf[AVG_TF_CUP_BOTTOM]));
+    }
+    // get_food_rewards / get_water_rewards: lane l looks at particles l and l + 32
+    float* prec = a.part + (size_t)e * AVG_P_STRIDE;
+    uint32_t* prec_u = reinterpret_cast<uint32_t*>(prec);
+    uint32_t alive[2] = {prec_u[AVG_P_ALIVE], prec_u[AVG_P_ALIVE + 1]}, hitm[2] = {prec_u[AVG_P_HIT], prec_u[AVG_P_HIT + 1]};
+    const uint32_t th[2] = {prec_u[AVG_P_TOUCH_HUMAN], prec_u[AVG_P_TOUCH_HUMAN + 1]}, tsp[2] = {prec_u[AVG_P_TOUCH_SPILL], prec_u[AVG_P_TOUCH_SPILL + 1]};
+    int n_eat = 0, n_spill = 0, n_hit = 0;
+    float vel_sum = 0.0f;
+    uint32_t ev_eat[2], ev_spill[2], ev_hit[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int p = lane + 32 * k;
+        bool eat = false, spill = false, hit = false, hit_remove = false;
+        float speed = 0.0f;
+        if (p < h->n_particle && ((alive[k] >> lane) & 1u)) {
+            const V3 x = mk3(prec[AVG_P_POS + p], prec[AVG_P_POS + 64 + p], prec[AVG_P_POS + 128 + p]);
+            bool inside = false;
+            if (drinking) {                                   // util.points_in_cylinder(top, bottom, 0.05, x), util.py:107-110
+                const V3 vec = bottom - top;
+                inside = dot(x - top, vec) >= 0.0f && dot(x - bottom, vec) <= 0.0f && norm(cross(x - top, vec)) <= tf[AVG_TF_CUP_RADIUS] * norm(vec);
+            }
+            if (!inside) {
+                if (norm(mouth - x) < tf[AVG_TF_EAT_RADIUS]) {                                                    // feeding.py:102, drinking.py:114
+                    eat = true;
+                    if (!drinking) speed = norm(mk3(prec[AVG_P_VEL + p], prec[AVG_P_VEL + 64 + p], prec[AVG_P_VEL + 128 + p]));   // Drinking reads it after the teleport zeroed it
+                } else if (x.z < tf[AVG_TF_Z_MIN] || (!drinking && ((tsp[k] >> lane) & 1u))) spill = true;      // feeding.py:111, drinking.py:124
+                else if ((th[k] >> lane) & 1u) {
+                    if (drinking) { hit = true; hit_remove = true; }                                             // drinking.py:131-134
+                    else if (!((hitm[k] >> lane) & 1u)) hit = true;                                              // feeding.py:116-119
+                }
+            }
+        }
+        ev_eat[k] = __ballot_sync(AVG_FULL, eat); ev_spill[k] = __ballot_sync(AVG_FULL, spill); ev_hit[k] = __ballot_sync(AVG_FULL, hit);
+        const uint32_t rem = ev_eat[k] | ev_spill[k] | __ballot_sync(AVG_FULL, hit_remove);
+        alive[k] &= ~rem;
+        if (!drinking) hitm[k] |= ev_hit[k];
+        n_eat += __popc(ev_eat[k]); n_spill += __popc(ev_spill[k]); n_hit += __popc(ev_hit[k]);
+        vel_sum += warp_sum(speed);
+    }
+    if (lane < 2) {
+        prec_u[AVG_P_ALIVE + lane] = alive[lane]; prec_u[AVG_P_HIT + lane] = hitm[lane];
+        prec_u[AVG_P_EV_EAT + lane] = ev_eat[lane]; prec_u[AVG_P_EV_SPILL + lane] = ev_spill[lane]; prec_u[AVG_P_EV_HIT + lane] = ev_hit[lane];
+    }
+    if (lane == 0) {
+        fill_obs_fd(m, s, mouth, tool_force_on_human, robot_force_on_human);
+        const int tb = m.frame[AVG_F_TOOL_TIP].body;
+        const float* tv = s.env + AVG_E_QD + m.body[tb].dof;
+        const float ee_vel = norm(ld3(tv));                                                   // getBaseVelocity(spoon)[0], feeding.py:59
+        const float food_reward = tf[AVG_TF_EAT_REWARD] * (float)n_eat + tf[AVG_TF_SPILL_REWARD] * (float)n_spill;
+        const float hit_reward = -(float)n_hit;
+        // human_preferences, env.py:412-448: total_force_on_human = robot force, tool_force_at_target = tool force (feeding.py:63)
+        const float pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-robot_force_on_human)
+                         + tf[AVG_TF_C_HF] * (tool_force_on_human < tf[AVG_TF_FORCE_CAP] ? 0.0f : -tool_force_on_human)
+                         + tf[AVG_TF_C_FD] * hit_reward + tf[AVG_TF_C_FDV] * (-vel_sum);
+        float reward_distance, reward_tilt = 0.0f;
+        if (drinking) {
+            reward_distance = -norm(mouth - top);                                             // drinking.py:68
+            const float roll = quat_roll(cup_q);
+            reward_tilt = tf[AVG_TF_TILT_SIGN] > 0.0f ? -fabsf(roll + 1.57079632679f) : -fabsf(roll - 1.57079632679f);   // :72
+        } else reward_distance = -norm(mouth - tool);                                         // feeding.py:68
+        const float reward_action = -raw_sq;
+        const float task_success = s.env[AVG_E_TASK_SUCCESS] + (float)n_eat;
+        grec[AVG_E_TASK_SUCCESS] = task_success;
+        const float reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action + tf[AVG_TF_TILT_W] * reward_tilt
+                           + tf[AVG_TF_FOOD_W] * food_reward + pref;                          // feeding.py:71, drinking.py:74
+        int* grec_i = reinterpret_cast<int*>(grec);
+        grec[AVG_E_EPISODE_RETURN] = s.env[AVG_E_EPISODE_RETURN] + reward;
+        st3(grec + AVG_E_TARGET_POS, mouth);
+        grec_i[AVG_E_ITERATION] = env_i[AVG_E_ITERATION] + 1;                                // env.py:351
+        grec_i[AVG_E_OVERFLOW] = env_i[AVG_E_OVERFLOW] | scr_i[AVG_S_OVERFLOW] | reinterpret_cast<const int*>(prec)[AVG_P_NCONTACT + 1];
+        grec_i[AVG_E_SOLVER_ITERS] = scr_i[AVG_S_ITERS];
+        grec_i[AVG_E_NCAND] = scr_i[AVG_S_NCAND];
+        a.reward[e] = reward;
+        const float success = task_success >= tf[AVG_TF_SUCCESS_THR] ? 1.0f : 0.0f;           // feeding.py:76
+        a.info[2 * e] = robot_force_on_human + tool_force_on_human;
+        a.info[2 * e + 1] = success;
+        if (a.done) a.done[e] = (a.time_limit > 0 && env_i[AVG_E_ITERATION] + 1 >= a.time_limit) ? 1 : 0;
+        if (a.terms) {
+            float* tr = a.terms + 8 * (size_t)e;
+            tr[0] = robot_force_on_human + tool_force_on_human; tr[1] = success; tr[2] = robot_force_on_human; tr[3] = tool_force_on_human;
+            tr[4] = reward_distance; tr[5] = reward_action; tr[6] = food_reward + tf[AVG_TF_TILT_W] * reward_tilt; tr[7] = pref;
+        }
+    }
+    __syncwarp();
+    const int nobs = h->n_obs_robot + h->n_obs_human;
+    for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
+    if (a.contacts) dump_contacts(a, e, scr, ncontact, dt, lane);
+}
+
+// =================================================================================================================
+// particle broadphase (Feeding / Drinking): one warp per environment, one lane per particle (two when there are 64).
+// Particle-vs-shape candidates go to the narrowphase queue (the sphere template against the shape: GJK like any other pair);
+// particle-vs-particle contacts are closed form and are written directly.  Canonical order of both lists: particle index,
+// then shape-table index / second particle index.
+// =================================================================================================================
+namespace {
+constexpr int kPCandPerParticle = 16;      // particle-vs-shape candidates kept per particle after the box and face-plane culls (more: flagged)
+struct __align__(16) SmPCol {
+    float bp[32][3]; float bq[32][4];
+    float4 saabb[kMaxMS][2];
+    float px[64][3];
+    uint16_t cand[64][kPCandPerParticle];  // candidate shapes of each particle, ascending shape index (one enumeration, then the prefix sum)
+    uint8_t near_idx[256];
+};
+}  // namespace
+
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_pcollide_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmPCol)
+    AVG_MASK_CHECK
+    const int np = h->n_particle;
+    if (np <= 0 || !a.part || !a.pscratch) return;
+    const int nb = h->n_body, nms = h->n_mshape, nstat = h->n_shape - nms;
+    float* ps = a.pscratch + (size_t)e * AVG_PS_STRIDE;
+    int* ps_i = reinterpret_cast<int*>(ps);
+    const float* prec = a.part + (size_t)e * AVG_P_STRIDE;
+    const AvgShape* PS = &m.shape[h->pshape];
+    const float r = PS->radius, pthr = PS->thr, infl = r + pthr;
+    if (lane < nb + h->n_ebody) {
+        const float4* gp = reinterpret_cast<const float4*>(scr + AVG_S_POSE) + 2 * lane;
+        const float4 p4 = gp[0], q4 = gp[1];
+        s.bp[lane][0] = p4.x; s.bp[lane][1] = p4.y; s.bp[lane][2] = p4.z;
+        s.bq[lane][0] = q4.x; s.bq[lane][1] = q4.y; s.bq[lane][2] = q4.z; s.bq[lane][3] = q4.w;
+    }
+    const uint32_t alive0 = __float_as_uint(prec[AVG_P_ALIVE]), alive1 = __float_as_uint(prec[AVG_P_ALIVE + 1]);
+    bool live[2]; V3 x[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int p = lane + 32 * k;
+        live[k] = p < np && (((k ? alive1 : alive0) >> lane) & 1u);
+        x[k] = live[k] ? mk3(prec[AVG_P_POS + p], prec[AVG_P_POS + 64 + p], prec[AVG_P_POS + 128 + p]) : mk3(0, 0, 0);
+        s.px[p][0] = x[k].x; s.px[p][1] = x[k].y; s.px[p][2] = x[k].z;
+    }
+    __syncwarp();
+    if (lane < nms) {                        // world AABBs of the top-level moving shapes (compounds: of the whole compound)
+        const AvgShape* S = &m.shape[lane];
+        const Q4 bq = ldq(s.bq[S->body]);
+        const V3 p = ld3(s.bp[S->body]) + qrot(bq, ld3(S->pos));
+        const M3 R = qmat(qnormalize(qmul(bq, ldq(S->quat))));
+        const V3 lc = ld3(S->aabb_c), lh = ld3(S->aabb_h);
+        const V3 c = p + mmul(R.m, lc);
+        s.saabb[lane][0] = make_float4(c.x, c.y, c.z, fabsf(R.m[0]) * lh.x + fabsf(R.m[1]) * lh.y + fabsf(R.m[2]) * lh.z);
+        s.saabb[lane][1] = make_float4(fabsf(R.m[3]) * lh.x + fabsf(R.m[4]) * lh.y + fabsf(R.m[5]) * lh.z,
+                                       fabsf(R.m[6]) * lh.x + fabsf(R.m[7]) * lh.y + fabsf(R.m[8]) * lh.z, 0.0f, 0.0f);
+    }
+    // union box of the live particles -> static shapes near any of them
+    float ulo[3], uhi[3];
+    {
+        auto key = [](float f) { const unsigned b = __float_as_uint(f); return b ^ ((unsigned)((int)b >> 31) | 0x80000000u); };
+        auto unkey = [](unsigned q) { return __uint_as_float(q ^ ((q >> 31) ? 0x80000000u : 0xffffffffu)); };
+        const float xs[2][3] = {{x[0].x, x[0].y, x[0].z}, {x[1].x, x[1].y, x[1].z}};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float lo = 3.0e38f, hi = -3.0e38f;
+            if (live[0]) { lo = xs[0][k]; hi = xs[0][k]; }
+            if (live[1]) { lo = fminf(lo, xs[1][k]); hi = fmaxf(hi, xs[1][k]); }
+            ulo[k] = unkey(__reduce_min_sync(AVG_FULL, key(lo))) - infl; uhi[k] = unkey(__reduce_max_sync(AVG_FULL, key(hi))) + infl;
+        }
+    }
+    int nnear = 0;
+    for (int base = 0; base < nstat; base += 32) {
+        const int si = base + lane;
+        bool near = false;
+        if (si < nstat) {
+            const float4* rp = reinterpret_cast<const float4*>(&m.bps[si]);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            near = r0.x + r0.w >= ulo[0] && r0.x - r0.w <= uhi[0] && r0.y + r1.x >= ulo[1] && r0.y - r1.x <= uhi[1] &&
+                   r0.z + r1.y >= ulo[2] && r0.z - r1.y <= uhi[2];
+        }
+        const unsigned bal = __ballot_sync(AVG_FULL, near);
+        if (near) s.near_idx[nnear + __popc(bal & ((1u << lane) - 1))] = (uint8_t)si;
+        nnear += __popc(bal);
+    }
+    __syncwarp();
+    // candidate enumeration of one particle in ascending shape-table order; f(shape index) is called for every candidate
+    auto enumerate = [&](V3 xp, auto&& f) {
+        for (int sa = 0; sa < nms; ++sa) {
+            if (m.shape[sa].type == AVG_SHAPE_COMPOUND) continue;
+            const float4 a0 = s.saabb[sa][0], a1 = s.saabb[sa][1];
+            if (fabsf(xp.x - a0.x) <= a0.w + infl && fabsf(xp.y - a0.y) <= a1.x + infl && fabsf(xp.z - a0.z) <= a1.y + infl) f(sa);
+        }
+        for (int k = 0; k < nnear; ++k) {
+            const int si = s.near_idx[k];
+            const float4* rp = reinterpret_cast<const float4*>(&m.bps[si]);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            if (fabsf(xp.x - r0.x) <= r0.w + infl && fabsf(xp.y - r0.y) <= r1.x + infl && fabsf(xp.z - r0.z) <= r1.y + infl) f(nms + si);
+        }
+        for (int sa = 0; sa < nms; ++sa) {
+            const AvgShape* S = &m.shape[sa];
+            if (S->type != AVG_SHAPE_COMPOUND) continue;
+            const float4 a0 = s.saabb[sa][0], a1 = s.saabb[sa][1];
+            if (!(fabsf(xp.x - a0.x) <= a0.w + infl && fabsf(xp.y - a0.y) <= a1.x + infl && fabsf(xp.z - a0.z) <= a1.y + infl)) continue;
+            const V3 pl = qrot_inv(ldq(s.bq[S->body]), xp - ld3(s.bp[S->body]));          // the particle in the compound's body frame
+            const int first = S->vert_off, cnt = S->vert_cnt;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 c4 = __ldg(&m.caabb[2 * (first - h->n_shape + k)]), h4 = __ldg(&m.caabb[2 * (first - h->n_shape + k) + 1]);
+                if (!(fabsf(pl.x - c4.x) <= h4.x + infl && fabsf(pl.y - c4.y) <= h4.y + infl && fabsf(pl.z - c4.z) <= h4.z + infl)) continue;
+                // face-plane bound: a point outside a hull is at least max_i (n_i . x - d_i) away from it, so children whose planes
+                // already put the particle beyond the contact distance never reach GJK (thin VHACD pieces have loose boxes)
+                const AvgShape* C = &m.shape[first + k];
+                const V3 xs = qrot_inv(ldq(C->quat), pl - ld3(C->pos));
+                const float4* pln = reinterpret_cast<const float4*>(m.plane) + C->plane_off;
+                float lb = -3.0e38f;
+                for (int i = 0; i < C->plane_cnt; ++i) { const float4 q4 = __ldg(pln + i); lb = fmaxf(lb, fmaf(q4.x, xs.x, fmaf(q4.y, xs.y, q4.z * xs.z)) - q4.w); }
+                if (lb < infl + C->margin + 1e-6f) f(first + k);
+            }
+        }
+    };
+    int cnt[2] = {0, 0};
+    int cand_over = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) if (live[k]) {
+        const int p = lane + 32 * k;
+        enumerate(x[k], [&](int sb) { if (cnt[k] < kPCandPerParticle) s.cand[p][cnt[k]++] = (uint16_t)sb; else cand_over = 16; });
+    }
+    // particle-major offsets: particles 0..31 first, then 32..63
+    int inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v0 = __shfl_up_sync(AVG_FULL, inc0, o), v1 = __shfl_up_sync(AVG_FULL, inc1, o);
+        if (lane >= o) { inc0 += v0; inc1 += v1; }
+    }
+    const int tot0 = __shfl_sync(AVG_FULL, inc0, 31), tot1 = __shfl_sync(AVG_FULL, inc1, 31);
+    int off[2] = {inc0 - cnt[0], tot0 + inc1 - cnt[1]};
+    int total = tot0 + tot1, overflow = __any_sync(AVG_FULL, cand_over != 0) ? 16 : 0;
+    if (total > AVG_MAX_PCAND) { overflow |= 16; total = AVG_MAX_PCAND; }
+    int qbase = 0;
+    if (lane == 0 && total > 0) qbase = atomicAdd(a.np_count, total);
+    qbase = __shfl_sync(AVG_FULL, qbase, 0);
+    if (qbase + total > a.np_capacity) { overflow |= 1; total = max(0, min(total, a.np_capacity - qbase)); }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) if (live[k]) {
+        const int p = lane + 32 * k;
+        int o = off[k];
+        for (int c = 0; c < cnt[k]; ++c, ++o)
+            if (o < total) { AvgNpItem it; it.env = e; it.pair = (AVG_NP_PARTICLE | (uint32_t)p) | ((uint32_t)s.cand[p][c] << 16); it.slot = o; it.cert = -1; a.np_queue[qbase + o] = it; }
+    }
+    // particle-particle contacts: spheres of equal radius, closed form
+    const float reach = 2.0f * r + pthr;
+    int pc[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) if (live[k]) {
+        const int p = lane + 32 * k;
+        for (int q = p + 1; q < np; ++q) {
+            if (!(((q < 32 ? alive0 : alive1) >> (q & 31)) & 1u)) continue;
+            const V3 d = x[k] - ld3(s.px[q]);
+            pc[k] += dot(d, d) < reach * reach ? 1 : 0;
+        }
+    }
+    int pi0 = pc[0], pi1 = pc[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v0 = __shfl_up_sync(AVG_FULL, pi0, o), v1 = __shfl_up_sync(AVG_FULL, pi1, o);
+        if (lane >= o) { pi0 += v0; pi1 += v1; }
+    }
+    const int pt0 = __shfl_sync(AVG_FULL, pi0, 31), pt1 = __shfl_sync(AVG_FULL, pi1, 31);
+    int poff[2] = {pi0 - pc[0], pt0 + pi1 - pc[1]};
+    int npp = pt0 + pt1;
+    if (npp > AVG_PS_MAXPP) { overflow |= 8; npp = AVG_PS_MAXPP; }
+    float4* pp = reinterpret_cast<float4*>(ps + AVG_PS_PP);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) if (live[k]) {
+        const int p = lane + 32 * k;
+        int o = poff[k];
+        for (int q = p + 1; q < np; ++q) {
+            if (!(((q < 32 ? alive0 : alive1) >> (q & 31)) & 1u)) continue;
+            const V3 d = x[k] - ld3(s.px[q]);
+            const float dd = dot(d, d);
+            if (!(dd < reach * reach)) continue;
+            if (o < npp) {
+                const float dn = sqrtf(dd);
+                const V3 n = dn > 1e-9f ? d * (1.0f / dn) : mk3(0, 0, 1);
+                pp[2 * o] = make_float4(n.x, n.y, n.z, dn - 2.0f * r);
+                pp[2 * o + 1] = make_float4(__int_as_float(p), __int_as_float(q), 0.0f, 0.0f);
+            }
+            ++o;
+        }
+    }
+    if (lane == 0) { ps_i[AVG_PS_NCAND] = total; ps_i[AVG_PS_NPP] = npp; ps_i[AVG_PS_OVERFLOW] = overflow; }
+}
+
 // initial observation after reset (scratch_itch.py:268): FK + target + _get_obs([0],[0,0])
 __global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
 avg_reset_obs_kernel(AvgStepArgs a) {
@@ -2217,10 +3047,15 @@ avg_reset_obs_kernel(AvgStepArgs a) {
     for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
     __syncwarp();
     const int* env_i = reinterpret_cast<const int*>(s.env);
-    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body);
+    fk_warp(m, s, s.env + AVG_E_Q, lane, h->n_body, s.env + AVG_E_EBODY);
     frames_warp(m, s, lane);
     if (lane == 0) {
         if (h->task == AVG_TASK_BED_BATHING) fill_obs_bb(m, s, 0.0f, 0.0f, 0.0f);                        // bed_bathing.py:350
+        else if (h->task == AVG_TASK_FEEDING || h->task == AVG_TASK_DRINKING) {                           // feeding.py:325
+            const V3 mouth = fd_mouth(m, s);
+            fill_obs_fd(m, s, mouth, 0.0f, 0.0f);
+            st3(grec + AVG_E_TARGET_POS, mouth);
+        }
         else {
             V3 lp; Q4 lq; frame_cached(s, env_i[AVG_E_LIMB_FRAME], lp, lq);
             const V3 tgt = lp + qrot(lq, ld3(s.env + AVG_E_TARGET_ON_ARM));
@@ -2332,6 +3167,17 @@ __device__ void ik_fk(const KM& m, const IkChain& c, const float* q, const AvgRe
     pe = p + qrot(r, ld3(T->ik_ee_frame));
     qe = qnormalize(qmul(r, ldq(T->ik_ee_frame + 3)));
 }
+// start target: centre + U(-range, range)^3 (scratch_itch.py:243,251), fixed orientation
+__device__ __forceinline__ V3 ik_start_target(const AvgResetTable* T, uint32_t sd, uint32_t ue, uint32_t ep) {
+    V3 tp = ld3(T->ik_target);
+    tp.x += (2.0f * reset_u01(sd, ue, ep, 20) - 1.0f) * T->ik_range;
+    tp.y += (2.0f * reset_u01(sd, ue, ep, 21) - 1.0f) * T->ik_range;
+    tp.z += (2.0f * reset_u01(sd, ue, ep, 22) - 1.0f) * T->ik_range;
+    if (T->has_bowl) {                                                               // Feeding: the target sits above the bowl drawn for this episode (feeding.py:276)
+        tp.x += (2.0f * reset_u01(sd, ue, ep, 11) - 1.0f) * 0.05f; tp.y += (2.0f * reset_u01(sd, ue, ep, 12) - 1.0f) * 0.05f;
+    }
+    return tp;
+}
 __device__ __forceinline__ V3 ik_rot_err(Q4 target, Q4 cur) {
     Q4 d = qmul(target, qconj(cur));
     if (d.w < 0) d = mkq(-d.x, -d.y, -d.z, -d.w);
@@ -2353,6 +3199,7 @@ avg_reset_ik_kernel(AvgResetArgs r) {
     const KM m = open_model(r.models[v]);
     const uint32_t sd = r.seed, ue = (uint32_t)e, ep = (uint32_t)r.episode[e];
     float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    const bool resolve = r.round == 0 || (r.retry && r.retry[e]);                    // else: back onto the accepted pose after the 5 test steps
     IkChain c; c.n = T->n_arm;
     for (int j = 0; j < c.n; ++j) {
         c.dof[j] = T->arm_dof[j]; c.qidx[j] = T->arm_qidx[j];
@@ -2361,19 +3208,17 @@ avg_reset_ik_kernel(AvgResetArgs r) {
         const bool unlimited = D->lower > D->upper;                                  // continuous joint: +-2 pi for the IK, util.py:86-88
         c.lo[j] = unlimited ? -6.283185307f : D->lower; c.hi[j] = unlimited ? 6.283185307f : D->upper;
     }
-    // start target: centre + U(-range, range)^3 (scratch_itch.py:243,251), fixed orientation
-    V3 tp = ld3(T->ik_target);
-    tp.x += (2.0f * reset_u01(sd, ue, ep, 20) - 1.0f) * T->ik_range;
-    tp.y += (2.0f * reset_u01(sd, ue, ep, 21) - 1.0f) * T->ik_range;
-    tp.z += (2.0f * reset_u01(sd, ue, ep, 22) - 1.0f) * T->ik_range;
+    const V3 tp = ik_start_target(T, sd, ue, ep);
+    const float tol = T->ik_tol > 0.0f ? T->ik_tol : 0.03f;
     const Q4 tq = ldq(T->ik_target + 3);
     float q[8], qbest[8]; float best_err = 3.0e38f;
     V3 jp[8], ja[8], pe, pb; Q4 qe, qb;
     const float lambda2 = 0.05f * 0.05f;
-    for (int restart = 0; restart < 40; ++restart) {                                  // max_ik_random_restarts
+    if (!resolve) for (int j = 0; j < c.n; ++j) qbest[j] = rec[AVG_E_MTARGET + c.dof[j]];
+    for (int restart = 0; resolve && restart < 40; ++restart) {                       // max_ik_random_restarts
         for (int j = 0; j < c.n; ++j) {                                               // random rest pose, util.py:100
             const float a = fmaxf(c.lo[j], -3.14159265f), b = fminf(c.hi[j], 3.14159265f);
-            q[j] = a + (b - a) * reset_u01(sd, ue, ep, 32 + 8 * restart + j);
+            q[j] = a + (b - a) * reset_u01(sd, ue, ep, 32 + 8 * (restart + 40 * r.round) + j);
         }
         for (int it = 0; it < 200; ++it) {
             ik_fk(m, c, q, T, jp, ja, pe, qe, pb, qb);
@@ -2414,11 +3259,15 @@ avg_reset_ik_kernel(AvgResetArgs r) {
         const float dm = sqrtf((tq.x - qe.x) * (tq.x - qe.x) + (tq.y - qe.y) * (tq.y - qe.y) + (tq.z - qe.z) * (tq.z - qe.z) + (tq.w - qe.w) * (tq.w - qe.w));
         const float dp = sqrtf((tq.x + qe.x) * (tq.x + qe.x) + (tq.y + qe.y) * (tq.y + qe.y) + (tq.z + qe.z) * (tq.z + qe.z) + (tq.w + qe.w) * (tq.w + qe.w));
         const float eq = fminf(dm, dp);
-        const bool ok = epos < 0.03f && eq < 0.03f;                                   // random_restart_threshold, util.py:51
+        const bool ok = epos < tol && eq < tol;                                       // random_restart_threshold, util.py:51
         if (ok || epos < best_err) { best_err = epos; for (int j = 0; j < c.n; ++j) qbest[j] = q[j]; }   // util.py:53-55: else the closest attempt
         if (ok) break;
     }
     ik_fk(m, c, qbest, T, jp, ja, pe, qe, pb, qb);
+    if (r.round > 0) {                                                                // after test steps: every joint back on its reset pose, at rest
+        for (int d = 0; d < m.h->n_jdof; ++d) rec[AVG_E_Q + m.body[m.dof[d].body].qidx] = rec[AVG_E_MTARGET + d];
+        for (int d = 0; d < 32; ++d) rec[AVG_E_QD + d] = 0.0f;
+    }
     for (int j = 0; j < c.n; ++j) { rec[AVG_E_Q + c.qidx[j]] = qbest[j]; rec[AVG_E_MTARGET + c.dof[j]] = qbest[j]; }
     // the tool goes where init_tool puts it (world_creation.py:331-337): weld-parent frame o inverse of the tool's base frame
     {
@@ -2429,13 +3278,130 @@ avg_reset_ik_kernel(AvgResetArgs r) {
         float* tq7 = rec + AVG_E_Q + T->tool_qidx;
         tq7[0] = tbp.x; tq7[1] = tbp.y; tq7[2] = tbp.z; tq7[3] = tbq.x; tq7[4] = tbq.y; tq7[5] = tbq.z; tq7[6] = tbq.w;
     }
-    // inspection slots (the env-static pose block is unused by these tasks): drawn start target and the position error reached
-    rec[AVG_E_EBODY + 0] = tp.x; rec[AVG_E_EBODY + 1] = tp.y; rec[AVG_E_EBODY + 2] = tp.z; rec[AVG_E_EBODY + 3] = norm(tp - pe);
+    // inspection slots (last env-static pose slot, unused by every task): drawn start target and the position error reached
+    rec[AVG_E_EBODY + 21] = tp.x; rec[AVG_E_EBODY + 22] = tp.y; rec[AVG_E_EBODY + 23] = tp.z; rec[AVG_E_EBODY + 24] = norm(tp - pe);
+}
+
+// Episode reset of Feeding / Drinking on the device: the random draws of FeedingEnv.reset / DrinkingEnv.reset (feeding.py:171-185,
+// 242-245, drinking.py:185-201, 241-243) restated as in compiler/reset_fd.py sample_states_fd(), one thread per environment.
+// The start pose comes from avg_reset_ik_kernel (fresh target above the bowl, feeding.py:276-278), the particles are placed by
+// avg_reset_particles_kernel once the tool sits in the gripper (feeding.py:291-307), and the caller then runs the reference's
+// 100 settle steps (feeding.py:318-320) with avg_launch_settle.
+__global__ void __launch_bounds__(128)
+avg_reset_fd_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env) return;
+    if (r.mask && !r.mask[e]) return;
+    const uint32_t ep = (uint32_t)(r.episode[e] + 1);
+    r.episode[e] = (int32_t)ep;
+    const uint32_t sd = r.seed, ue = (uint32_t)e;
+    const uint32_t pick = reset_u32(sd, ue, ep, 17);
+    const int npg = r.n_per_gender;
+    const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)min(r.n_variants, 2)) * npg + (int)(pick % (uint32_t)npg);   // gender, feeding.py:172
+    const AvgResetTable* T = r.tables[v];
+    const int impairment = (int)(reset_u32(sd, ue, ep, 1) & 3u);                                   // none, limits, weakness, tremor (world_creation.py:67)
+    const float limit_scale = impairment == 1 ? 0.5f + 0.5f * reset_u01(sd, ue, ep, 2) : 1.0f;
+    const float strength = impairment == 2 ? 0.25f + 0.75f * reset_u01(sd, ue, ep, 3) : 1.0f;
+    float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    for (int i = 0; i < AVG_ENV_STRIDE; ++i) rec[i] = 0.0f;
+    const int k = (int)((pick / (uint32_t)npg) % (uint32_t)T->n_pool);
+    for (int j = 0; j < T->n_arm; ++j) { rec[AVG_E_Q + T->arm_qidx[j]] = T->pool_q[k][j]; rec[AVG_E_MTARGET + T->arm_dof[j]] = T->pool_q[k][j]; }
+    for (int j = 0; j < T->n_fin; ++j) { rec[AVG_E_Q + T->fin_qidx[j]] = T->fin_q[j]; rec[AVG_E_MTARGET + T->fin_dof[j]] = T->fin_q[j]; }
+    const float deg30 = 0.5235987755982988f, deg20 = 0.3490658503988659f;
+    for (int j = 0; j < T->n_hum; ++j) {
+        float q = T->hum_reset[j];
+        const int joint = T->hum_joint[j];
+        if (joint >= 25 && joint <= 27) q = (2.0f * reset_u01(sd, ue, ep, 8 + joint - 25) - 1.0f) * deg30;              // feeding.py:243
+        q = fminf(fmaxf(q, T->hum_lower[j] * limit_scale), T->hum_upper[j] * limit_scale);                              // world_creation.py:172
+        rec[AVG_E_Q + T->hum_qidx[j]] = q; rec[AVG_E_MTARGET + T->hum_dof[j]] = q;
+        rec[AVG_E_TARGET_H + T->hum_slot[j]] = q;                                                                       // feeding.py:248
+    }
+    for (int j = 0; j < 7; ++j) rec[AVG_E_Q + T->tool_qidx + j] = T->pool_tool[k][j];
+    for (int j = 0; j < 4; ++j) rec[AVG_E_TREMOR + j] = impairment == 3 ? (2.0f * reset_u01(sd, ue, ep, 4 + j) - 1.0f) * deg20 : 0.0f;   // world_creation.py:138-139
+    if (T->has_bowl) {                                                                                                  // feeding.py:184-185
+        rec[AVG_E_EBODY + 0] = T->bowl_center[0] + (2.0f * reset_u01(sd, ue, ep, 11) - 1.0f) * 0.05f;
+        rec[AVG_E_EBODY + 1] = T->bowl_center[1] + (2.0f * reset_u01(sd, ue, ep, 12) - 1.0f) * 0.05f;
+        rec[AVG_E_EBODY + 2] = T->bowl_center[2];
+        for (int j = 0; j < 4; ++j) rec[AVG_E_EBODY + 3 + j] = T->bowl_quat[j];
+    }
+    rec[AVG_E_STRENGTH] = strength; rec[AVG_E_LIMIT_SCALE] = limit_scale;
+    rec[AVG_E_TREMOR_ON] = impairment == 3 ? 1.0f : 0.0f;
+    rec[AVG_E_HUMAN_KP] = 0.005f;                                                                  // human_gains, feeding.py:48
+    reinterpret_cast<uint32_t*>(rec)[AVG_E_FROZEN] = (T->human_control || impairment == 3) ? 0u : T->head_mask;   // feeding.py:244
+    r.variant[e] = v;
+    int* scr_i = reinterpret_cast<int*>(r.scratch + (size_t)e * AVG_S_STRIDE);
+    scr_i[AVG_S_NSEP] = 0; scr_i[AVG_S_NC] = 0; scr_i[AVG_S_NCS] = 0; scr_i[AVG_S_NQ] = 0;
+}
+
+// feeding.py:291-307 / drinking.py:291-312: the particle grid above the tool, at rest; every particle alive
+__global__ void __launch_bounds__(128)
+avg_reset_particles_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env || !r.part) return;
+    if (r.mask && !r.mask[e]) return;
+    const AvgResetTable* T = r.tables[r.variant[e]];
+    const float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    float* pr = r.part + (size_t)e * AVG_P_STRIDE;
+    for (int i = 0; i < AVG_P_STRIDE; ++i) pr[i] = 0.0f;
+    const float* tp = rec + AVG_E_Q + T->tool_qidx;
+    const int np = T->n_particle;
+    for (int p = 0; p < np; ++p) for (int c = 0; c < 3; ++c) pr[AVG_P_POS + 64 * c + p] = tp[c] + T->grid[p][c];
+    uint32_t* pu = reinterpret_cast<uint32_t*>(pr);
+    pu[AVG_P_ALIVE] = np >= 32 ? 0xffffffffu : ((1u << np) - 1u);
+    pu[AVG_P_ALIVE + 1] = np > 32 ? (np >= 64 ? 0xffffffffu : ((1u << (np - 32)) - 1u)) : 0u;
+}
+
+// util.ik_random_restarts(step_sim=True), util.py:41-46,51: after 5 stepSimulation calls from the solved pose, the pose is kept only
+// if the robot does not touch itself (getContactPoints(body, body)) and the arm is still where the IK put it (the reference measures
+// the end effector after the steps against random_restart_threshold; a pose in contact with the table or the chair is pushed away).
+__global__ void __launch_bounds__(128)
+avg_reset_check_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env || !r.retry) return;
+    if (r.mask && !r.mask[e]) { r.retry[e] = 0; return; }
+    const int v = r.variant[e];
+    const AvgResetTable* T = r.tables[v];
+    if (!T->ik_enabled) { r.retry[e] = 0; return; }
+    const KM m = open_model(r.models[v]);
+    const float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    const float* scr = r.scratch + (size_t)e * AVG_S_STRIDE;
+    const int nc = reinterpret_cast<const int*>(scr)[AVG_S_NCS];
+    bool bad = false;
+    for (int c = 0; c < nc && c < AVG_MAX_CONTACT; ++c) {
+        const float* g = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c;
+        const int sa = __float_as_int(g[10]), sb = __float_as_int(g[11]);
+        if (m.shape[sa].ref_body == AVG_REF_ROBOT && m.shape[sb].ref_body == AVG_REF_ROBOT) bad = true;
+    }
+    // the reference's acceptance test runs AFTER the 5 steps (util.py:50-52): end effector within random_restart_threshold of the
+    // target in position and in quaternion distance -- a pose that something (the table, the chair) pushed away fails it
+    if (T->n_arm > 0 && T->n_arm <= 8) {
+        IkChain c; c.n = T->n_arm;
+        float q[8];
+        for (int j = 0; j < c.n; ++j) { c.dof[j] = T->arm_dof[j]; c.qidx[j] = T->arm_qidx[j]; c.body[j] = m.dof[c.dof[j]].body; q[j] = rec[AVG_E_Q + c.qidx[j]]; }
+        V3 jp[8], ja[8], pe, pb; Q4 qe, qb;
+        ik_fk(m, c, q, T, jp, ja, pe, qe, pb, qb);
+        const V3 tp = ik_start_target(T, r.seed, (uint32_t)e, (uint32_t)r.episode[e]);
+        const Q4 tq = ldq(T->ik_target + 3);
+        const float tol = T->ik_tol > 0.0f ? T->ik_tol : 0.03f;
+        const float dm = sqrtf((tq.x - qe.x) * (tq.x - qe.x) + (tq.y - qe.y) * (tq.y - qe.y) + (tq.z - qe.z) * (tq.z - qe.z) + (tq.w - qe.w) * (tq.w - qe.w));
+        const float dp = sqrtf((tq.x + qe.x) * (tq.x + qe.x) + (tq.y + qe.y) * (tq.y + qe.y) + (tq.z + qe.z) * (tq.z + qe.z) + (tq.w + qe.w) * (tq.w + qe.w));
+        if (!(norm(tp - pe) < tol && fminf(dm, dp) < tol)) bad = true;
+    }
+    r.retry[e] = bad ? 1 : 0;
+}
+
+cudaError_t avg_launch_reset_check(const AvgResetArgs& r, cudaStream_t stream) {
+    avg_reset_check_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    avg_reset_ik_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
+    if (r.part) avg_reset_particles_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    return cudaGetLastError();
 }
 
 cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream) {
-    avg_reset_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    if (r.part) avg_reset_fd_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
+    else avg_reset_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     if (r.any_ik) avg_reset_ik_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
+    if (r.part) avg_reset_particles_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     return cudaGetLastError();
 }
 
@@ -2506,7 +3472,7 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-int avg_kernels_per_step(int substeps) { return 2 + 4 * substeps; }
+int avg_kernels_per_step(int substeps, int n_internal, int particles) { return 2 + (particles ? 5 : 4) * substeps * (n_internal > 0 ? n_internal : 1); }
 
 // warps (= environments) per block, per kernel.  The solver uses one warp per block: its iteration count varies per
 // environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
@@ -2518,87 +3484,143 @@ constexpr int kWpbCollide = 4, kWpbDyn = 4, kWpbSolve = 1, kWpbEpi = 4, kWpbPro 
 namespace {
 struct KernelTimes {
     bool on = false, init = false;
-    cudaEvent_t ev[64];
-    double ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[128];
+    double ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int steps = 0;
 };
 KernelTimes g_kt;
-}  // namespace
+bool g_configured[64];                        // per device ordinal: the shared-memory opt-ins are per device / context
 
-cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream) {
-    static bool configured = false;
+cudaError_t configure_kernels() {
+    int dev = 0;
+    cudaError_t e1 = cudaGetDevice(&dev);
+    if (e1 != cudaSuccess) return e1;
+    if (dev >= 0 && dev < 64 && g_configured[dev]) return cudaSuccess;
     const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
     const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
-    if (!configured) {
-        cudaError_t e1;
-        if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_dynamics_kernel<8>, sm_dyn)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_dynamics_kernel<12>, sm_dyn)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_dynamics_kernel<16>, sm_dyn)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_solve_kernel<8>, sm_sol)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_solve_kernel<10>, sm_sol)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_solve_kernel<12>, sm_sol)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_solve_kernel<16>, sm_sol)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_epilogue_bb_kernel, sizeof(SmEpiBB) * kWpbEpi)) != cudaSuccess) return e1;
-        if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
-        configured = true;
-        const char* kt = getenv("AVG_KERNEL_TIMES");
-        g_kt.on = kt && kt[0] == '1' && 4 * substeps + 3 <= 64;
+    const size_t sm_sol1 = sizeof(SmSolve) + sizeof(SmPartSmall), sm_sol2 = sizeof(SmSolve) + sizeof(SmPartLarge);
+    if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_pcollide_kernel, sizeof(SmPCol) * kWpbCollide)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynamics_kernel<8>, sm_dyn)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynamics_kernel<12>, sm_dyn)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynamics_kernel<16>, sm_dyn)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<8, 0>, sm_sol)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<10, 0>, sm_sol)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<12, 0>, sm_sol)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<16, 0>, sm_sol)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<10, 1>, sm_sol1)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<12, 1>, sm_sol1)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<16, 1>, sm_sol1)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<10, 2>, sm_sol2)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<12, 2>, sm_sol2)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_solve_kernel<16, 2>, sm_sol2)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_epilogue_kernel, sm_epi)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_epilogue_bb_kernel, sizeof(SmEpiBB) * kWpbEpi)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_epilogue_fd_kernel, sm_epi)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_reset_obs_kernel, sm_epi)) != cudaSuccess) return e1;
+    if (dev >= 0 && dev < 64) g_configured[dev] = true;
+    return cudaSuccess;
+}
+
+// the kernels of ONE internal physics step (collide [, particle broadphase], narrowphase, dynamics, solve)
+template <class MARK>
+void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark) {
+    const size_t sm_col = sizeof(SmCollide) * kWpbCollide, sm_dyn = sizeof(SmDyn) * kWpbDyn;
+    const size_t sm_sol = sizeof(SmSolve) * kWpbSolve;
+    const size_t sm_sol1 = sizeof(SmSolve) + sizeof(SmPartSmall), sm_sol2 = sizeof(SmSolve) + sizeof(SmPartLarge);
+    const int n_range = a.env_end - a.env_begin;
+    auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
+    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 16);     // grid-stride over the queue, one thread per work item
+    const bool part = a.part != nullptr;
+    avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+    mark(1);
+    if (part) { avg_pcollide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sizeof(SmPCol) * kWpbCollide, stream>>>(a); mark(6); }
+    avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
+    mark(5);
+    if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+    else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+    else if (a.maxblk <= 12) avg_dynamics_kernel<12><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+    else avg_dynamics_kernel<16><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
+    mark(2);
+    if (part && a.task == AVG_TASK_FEEDING) {
+        if (a.maxblk <= 10) avg_solve_kernel<10, 1><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol1, stream>>>(a);
+        else if (a.maxblk <= 12) avg_solve_kernel<12, 1><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol1, stream>>>(a);
+        else avg_solve_kernel<16, 1><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol1, stream>>>(a);
+    } else if (part) {
+        if (a.maxblk <= 10) avg_solve_kernel<10, 2><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol2, stream>>>(a);
+        else if (a.maxblk <= 12) avg_solve_kernel<12, 2><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol2, stream>>>(a);
+        else avg_solve_kernel<16, 2><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol2, stream>>>(a);
     }
+    else if (a.maxblk <= 8) avg_solve_kernel<8, 0><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+    else if (a.maxblk <= 10) avg_solve_kernel<10, 0><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+    else if (a.maxblk <= 12) avg_solve_kernel<12, 0><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+    else avg_solve_kernel<16, 0><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
+    mark(3);
+}
+}  // namespace
+
+cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t stream) {
+    cudaError_t ec = configure_kernels();
+    if (ec != cudaSuccess) return ec;
+    static bool env_read = false;
+    const int n_internal = a_in.n_internal > 0 ? a_in.n_internal : 1;
+    if (!env_read) {
+        const char* kt = getenv("AVG_KERNEL_TIMES");
+        g_kt.on = kt && kt[0] == '1' && 5 * substeps * n_internal + 3 <= 128;
+        env_read = true;
+    }
+    AvgStepArgs a = a_in;
+    const size_t sm_epi = sizeof(SmEpi) * kWpbEpi;
     const bool kt_on = g_kt.on && a.env_begin == 0 && a.env_end == a.n_env;     // whole-batch launches only
-    int nev = 0;
-    if (kt_on && !g_kt.init) { for (int i = 0; i < 64; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
+    int nev = 0; int kinds[128];
+    if (kt_on && !g_kt.init) { for (int i = 0; i < 128; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
     static const bool sync_each = getenv("AVG_SYNC_EACH") != nullptr;        // development aid: name the kernel that faults
     int kseq = 0;
-    auto mark = [&]() {
-        if (kt_on) cudaEventRecord(g_kt.ev[nev++], stream);
+    auto mark = [&](int kind) {
+        if (kt_on && nev < 128) { kinds[nev] = kind; cudaEventRecord(g_kt.ev[nev++], stream); }
         if (sync_each) {
             const cudaError_t e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) fprintf(stderr, "[avg] launch #%d of the step (0 = before prologue, 1 = prologue, then collide/narrow/dynamics/solve per sub-step) failed: %s\n", kseq, cudaGetErrorString(e));
+            if (e != cudaSuccess) fprintf(stderr, "[avg] launch #%d of the step (kind %d: 0 prologue, 1 collide, 6 particle broadphase, 5 narrowphase, 2 dynamics, 3 solve, 4 epilogue) failed: %s\n", kseq, kind, cudaGetErrorString(e));
             kseq++;
         }
     };
     const int n_range = a.env_end - a.env_begin;
     if (n_range <= 0) return cudaSuccess;
     auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
-    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 16);     // grid-stride over the queue, one thread per work item
-    mark();
+    mark(-1);
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
-    mark();
-    for (int f = 0; f < substeps; ++f) {
-        avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
-        mark();
-        avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
-        mark();
-        if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
-        else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
-        else if (a.maxblk <= 12) avg_dynamics_kernel<12><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
-        else avg_dynamics_kernel<16><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
-        mark();
-        if (a.maxblk <= 8) avg_solve_kernel<8><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
-        else if (a.maxblk <= 10) avg_solve_kernel<10><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
-        else if (a.maxblk <= 12) avg_solve_kernel<12><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
-        else avg_solve_kernel<16><<<grid(kWpbSolve), 32 * kWpbSolve, sm_sol, stream>>>(a);
-        mark();
-    }
+    mark(0);
+    for (int f = 0; f < substeps; ++f)
+        for (int i = 0; i < n_internal; ++i) {
+            a.post = (i == n_internal - 1) ? 1 : 0;
+            launch_internal_step(a, stream, mark);
+        }
     if (a.task == AVG_TASK_BED_BATHING) avg_epilogue_bb_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sizeof(SmEpiBB) * kWpbEpi, stream>>>(a);
+    else if (a.task == AVG_TASK_FEEDING || a.task == AVG_TASK_DRINKING) avg_epilogue_fd_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     else avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
-    mark();
+    mark(4);
     if (kt_on) {
         cudaEventSynchronize(g_kt.ev[nev - 1]);
-        auto el = [&](int i) { float t = 0; cudaEventElapsedTime(&t, g_kt.ev[i], g_kt.ev[i + 1]); return (double)t; };
-        g_kt.ms[0] += el(0);
-        for (int f = 0; f < substeps; ++f) { g_kt.ms[1] += el(1 + 4 * f); g_kt.ms[5] += el(2 + 4 * f); g_kt.ms[2] += el(3 + 4 * f); g_kt.ms[3] += el(4 + 4 * f); }
-        g_kt.ms[4] += el(1 + 4 * substeps);
+        for (int i = 1; i < nev; ++i) { float t = 0; cudaEventElapsedTime(&t, g_kt.ev[i - 1], g_kt.ev[i]); g_kt.ms[kinds[i]] += (double)t; }
         if (++g_kt.steps % 8 == 0) {                 // mean over the last 8 steps
-            const double tot = g_kt.ms[0] + g_kt.ms[1] + g_kt.ms[2] + g_kt.ms[3] + g_kt.ms[4] + g_kt.ms[5];
-            fprintf(stderr, "[avg kernel times, steps %d-%d, %d envs] prologue %.3f collide %.3f narrow %.3f dynamics %.3f solve %.3f epilogue %.3f ms/step (total %.3f)\n",
-                    g_kt.steps - 8, g_kt.steps - 1, a.n_env, g_kt.ms[0] / 8, g_kt.ms[1] / 8, g_kt.ms[5] / 8, g_kt.ms[2] / 8, g_kt.ms[3] / 8, g_kt.ms[4] / 8, tot / 8);
-            for (int i = 0; i < 6; ++i) g_kt.ms[i] = 0;
+            double tot = 0; for (int i = 0; i < 7; ++i) tot += g_kt.ms[i];
+            fprintf(stderr, "[avg kernel times, steps %d-%d, %d envs] prologue %.3f collide %.3f pcollide %.3f narrow %.3f dynamics %.3f solve %.3f epilogue %.3f ms/step (total %.3f)\n",
+                    g_kt.steps - 8, g_kt.steps - 1, a.n_env, g_kt.ms[0] / 8, g_kt.ms[1] / 8, g_kt.ms[6] / 8, g_kt.ms[5] / 8, g_kt.ms[2] / 8, g_kt.ms[3] / 8, g_kt.ms[4] / 8, tot / 8);
+            for (int i = 0; i < 7; ++i) g_kt.ms[i] = 0;
         }
     }
+    return cudaGetLastError();
+}
+
+cudaError_t avg_launch_settle(const AvgStepArgs& a_in, int n, cudaStream_t stream) {
+    cudaError_t ec = configure_kernels();
+    if (ec != cudaSuccess) return ec;
+    AvgStepArgs a = a_in;
+    a.post = 0;                                      // reset() calls p.stepSimulation only: no per-frame hooks (feeding.py:318-320)
+    if (a.env_end - a.env_begin <= 0) return cudaSuccess;
+    const int n_internal = a.n_internal > 0 ? a.n_internal : 1;
+    for (int i = 0; i < n * n_internal; ++i) launch_internal_step(a, stream, [](int) {});
     return cudaGetLastError();
 }
 
@@ -2618,6 +3640,7 @@ cudaError_t avg_register_model(int slot, int variant, const unsigned char* d_blo
     m.bcap = reinterpret_cast<const float4*>(d_blob + hh->off_bcap);
     m.mlp = hh->n_mlp > 0 ? reinterpret_cast<const float*>(d_blob + hh->off_mlp) : nullptr;
     m.target = hh->n_target > 0 ? reinterpret_cast<const float4*>(d_blob + hh->off_target) : nullptr;
+    m.caabb = hh->n_cshape > 0 ? reinterpret_cast<const float4*>(d_blob + hh->off_caabb) : nullptr;
     return cudaMemcpyToSymbol(c_models, &m, sizeof(KM), sizeof(KM) * ((size_t)slot * AVG_K_MAX_VARIANTS + variant));
 }
 
@@ -2628,7 +3651,7 @@ cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, flo
 
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream) {
     const size_t sm_epi = sizeof(SmEpi) * kWpbEpi;
-    cudaError_t e1 = set_smem(avg_reset_obs_kernel, sm_epi);
+    cudaError_t e1 = configure_kernels();
     if (e1 != cudaSuccess) return e1;
     const int blocks = (a.env_end - a.env_begin + kWpbEpi - 1) / kWpbEpi;
     avg_reset_obs_kernel<<<blocks, 32 * kWpbEpi, sm_epi, stream>>>(a);

@@ -35,8 +35,24 @@
 #define AVG_S_NSEPMAX 32
 #define AVG_S_POSE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)   /* [32][8] body poses (pos, pad, quat) from the collide kernel's forward kinematics */
 #define AVG_S_NPRES (AVG_S_POSE + 8 * 32)             /* [AVG_S_NQMAX][16] narrowphase results of the queued candidates: pa, pb, n, dist, shape a, shape b, hit */
-#define AVG_S_NQMAX 32
-#define AVG_S_STRIDE (AVG_S_NPRES + 16 * AVG_S_NQMAX)
+#define AVG_S_NQMAX 64
+#define AVG_S_TWIST (AVG_S_NPRES + 16 * AVG_S_NQMAX)  /* [32][8] start-of-step body twists about the model's reference point (ang, pad, lin, pad); particle tasks only */
+#define AVG_S_FREEINV (AVG_S_TWIST + 8 * 32)          /* [2][12] inverse mass / world inverse inertia of the free bodies (tool); particle tasks only */
+#define AVG_S_STRIDE (AVG_S_FREEINV + 24)
+
+/* Particle scratch arena (Feeding / Drinking only): per-environment hand-off between the particle broadphase, the narrowphase
+   and the solver of one internal step (floats; ints bit-cast). */
+#define AVG_PS_NCAND 0        /* particle-vs-shape candidates queued for the narrowphase (result slots used)   */
+#define AVG_PS_NPP 1          /* particle-particle contacts found by the particle broadphase                   */
+#define AVG_PS_OVERFLOW 2
+#define AVG_PS_CAND 16        /* [AVG_MAX_PCAND][8]: n(3), dist, particle, shape b, hit, pad                     */
+#define AVG_PS_PP (AVG_PS_CAND + 8 * AVG_MAX_PCAND)           /* [AVG_PS_MAXPP][8]: n(3), dist, p, q, pad, pad */
+#define AVG_PS_MAXPP 256
+#define AVG_PS_REC (AVG_PS_PP + 8 * AVG_PS_MAXPP)             /* [AVG_MAX_PCONTACT][AVG_PS_REC_STRIDE] solver records  */
+#define AVG_PS_REC_STRIDE 20
+#define AVG_PS_SORTED (AVG_PS_REC + AVG_PS_REC_STRIDE * AVG_MAX_PCONTACT)   /* the same records in round order (what the sweeps read) */
+#define AVG_PS_STRIDE (AVG_PS_SORTED + AVG_PS_REC_STRIDE * AVG_MAX_PCONTACT)
+#define AVG_NP_PARTICLE 0x8000u   /* AvgNpItem.pair: shape-a field = AVG_NP_PARTICLE | particle index */
 
 #define AVG_K_MAX_HANDLES 16   /* handles per process that can hold models at the same time (constant-memory table slots) */
 
@@ -71,12 +87,19 @@ struct AvgStepArgs {
     AvgNpItem* np_queue;                               // [np_capacity] narrowphase work items of the current sub-step
     int* np_count;                                     // item counter: filled by the collide kernel, read by the narrowphase kernel, zeroed by the dynamics kernel
     int np_capacity;
-    const uint8_t* mask;                               // reset paths: environments to touch (null = all)
+    const uint8_t* mask;                               // reset / settle paths: environments to touch (null = all)
+    float* part;                                       // [n_env][AVG_P_STRIDE] particle records (Feeding / Drinking), else null
+    float* pscratch;                                   // [n_env][AVG_PS_STRIDE] particle scratch arena, else null
+    int post;                                          // this internal step ends a p.stepSimulation call: run the per-frame hooks (env.py:343-349)
+    int n_internal;                                    // internal steps per stepSimulation (numSubSteps, feeding.py:289)
     unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)
 };
 
-int avg_kernels_per_step(int substeps);
+int avg_kernels_per_step(int substeps, int n_internal, int particles);
 cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
+/* `n` calls of p.stepSimulation without actions, hooks or epilogue for the environments of a.mask: the settle loop of
+ * FeedingEnv.reset / DrinkingEnv.reset (feeding.py:318-320). */
+cudaError_t avg_launch_settle(const AvgStepArgs& a, int n, cudaStream_t stream);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
 /* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */
@@ -90,10 +113,18 @@ struct AvgResetArgs {
     int n_variants;
     int n_per_gender;                                  // variants per gender (1 ScratchItch; BedBathing: one per robot base pose)
     float* env; float* scratch; int32_t* variant; int32_t* episode;
+    float* part;                                       // particle records (Feeding / Drinking), else null
+    uint8_t* retry;                                    // [n_env] start poses rejected by the self-contact test (util.py:41-46), written by avg_launch_reset_check
+    int round;                                         // 0: first solve; k > 0: k-th re-solve of the rejected environments with fresh random restarts
     const uint8_t* mask;
     int n_env;
     uint32_t seed;
 };
 cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream);
+/* util.ik_random_restarts(step_sim=True), util.py:41-46: after the caller has run 5 stepSimulation calls from the solved start
+ * pose, reject the poses whose robot touches itself (or that were pushed off their pose), re-solve those with new random
+ * restarts (r.round), put every other masked environment back on its solved pose with zero velocities, and re-place the
+ * particles. */
+cudaError_t avg_launch_reset_check(const AvgResetArgs& r, cudaStream_t stream);
 /* Policy inference for on-device rollouts: obs [n_env][n_obs] -> actions [n_env][n_act] (enjoy_vr.py:106-113). */
 cudaError_t avg_launch_policy(const unsigned char* policy_blob, const float* obs, float* actions, int n_env, int n_obs, int n_act, cudaStream_t stream);

@@ -16,6 +16,7 @@ import numpy as np
 
 from . import capi
 from .compiler.reset import device_ik_setup, reset_table_bytes, sample_states
+from .compiler.reset_fd import sample_states_fd
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 MAX_EPISODE_STEPS = 200      # reference __init__.py:21
@@ -33,7 +34,16 @@ REGISTRY: Dict[str, dict] = {
     "BedBathingPR2-v0": dict(task="bed_bathing", robot="pr2", human_control=False, data="BedBathingPR2.npz"),
     "BedBathingPR2Human-v0": dict(task="bed_bathing", robot="pr2", human_control=True, data="BedBathingPR2Human.npz"),
 }
-_OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19
+# Feeding / Drinking (reference __init__.py:175-260, 259-344): Jaco and PR2 are the reference's ids; the Sawyer and Baxter ids
+# are named by BASELINE.json but have no reference environment: their recipes are defined by
+# compiler/scene_fd.py ROBOT_FD.
+for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
+    for _r, _robot in (("Jaco", "jaco"), ("PR2", "pr2"), ("Sawyer", "sawyer"), ("Baxter", "baxter")):
+        REGISTRY[f"{_t}{_r}-v0"] = dict(task=_task, robot=_robot, human_control=False, data=f"{_t}{_r}.npz")
+        REGISTRY[f"{_t}{_r}Human-v0"] = dict(task=_task, robot=_robot, human_control=True, data=f"{_t}{_r}Human.npz")
+_OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28), "feeding": (25, 23), "drinking": (25, 23)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19, feeding.py:18
+_ACT_HUMAN = {"scratch_itch": 10, "bed_bathing": 10, "feeding": 4, "drinking": 4}                              # scratch_itch.py:19, feeding.py:18
+SETTLE_STEPS = 100           # feeding.py:318-320
 _ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")
                       for r in ("PR2", "Jaco") for v in ("", "Human", "New")]
 
@@ -74,7 +84,7 @@ class BatchedAssistiveEnv:
     """N copies of one reference environment stepping in lock-step on one GPU."""
 
     def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False,
-                 device_ik: bool = False, cuda_graph: bool = False):
+                 device_ik: bool = True, cuda_graph: bool = False):
         if env_id not in REGISTRY:
             if env_id in _ALL_REFERENCE_IDS:
                 raise NotImplementedError(f"{env_id}: registered by the reference but not compiled yet "
@@ -90,16 +100,18 @@ class BatchedAssistiveEnv:
         self.device = torch.device("cuda", device)
         self.blobs, self.reset_data = load_env_data(self.spec["data"])
         self.sim = capi.Sim(self.num_envs, device)
-        # device_ik: `reset_device` solves every episode's start pose on the GPU for a freshly drawn start target
-        # (scratch_itch.py:243-253) instead of picking one of the pool's precomputed IK solutions; BedBathing's start target
-        # is fixed (bed_bathing.py:315), so its pool entry already is the solution and the option changes nothing there.
+        # device_ik (default): `reset_device` / `reset()` solve every episode's start pose on the GPU for a freshly drawn start
+        # target (scratch_itch.py:243-253), as the reference does; False picks one of the pool's <= 64 precomputed IK solutions.
+        # BedBathing's start target is fixed (bed_bathing.py:315), so its pool entry already is the solution and the option
+        # changes nothing there; Feeding / Drinking always solve on the device.
         self.device_ik = bool(device_ik)
         for v, b in enumerate(self.blobs):
             self.sim.upload_model(v, b)
             ik = device_ik_setup(b, self.spec["task"], self.spec["robot"]) if self.device_ik else None
             self.sim.upload_reset_table(v, reset_table_bytes(self.reset_data[v], ik))
         self.action_robot_len = 7
-        self.action_human_len = 10 if self.spec["human_control"] else 0
+        self.action_human_len = _ACT_HUMAN[self.spec["task"]] if self.spec["human_control"] else 0
+        self.has_particles = self.spec["task"] in ("feeding", "drinking")
         self.obs_robot_len = _OBS_LEN[self.spec["task"]][0]
         self.obs_human_len = _OBS_LEN[self.spec["task"]][1] if self.spec["human_control"] else 0
         assert self.sim.n_actions == self.action_robot_len + self.action_human_len
@@ -168,10 +180,24 @@ class BatchedAssistiveEnv:
         self.np_random = np.random.RandomState(seed)
         return [seed]
 
-    def reset(self, genders: Optional[np.ndarray] = None):
-        """scratch_itch.py:130-273, batched: samples every env's post-reset state on the host and uploads it."""
-        env, variant = sample_states(self.reset_data, self.num_envs, self.np_random, genders)
-        self.set_state(env, variant)
+    def reset(self, genders: Optional[np.ndarray] = None, host: Optional[bool] = None):
+        """scratch_itch.py:130-273, batched.  Default: the device sampler (`reset_device`: every draw of the reference's reset,
+        a fresh start target per episode with the IK solved on the GPU).  host=True (implied by explicit `genders`): the numpy
+        sampler of compiler/reset.py, whose start poses come from the variant's pool of precomputed IK solutions."""
+        if host is None:
+            host = genders is not None
+        if not host:
+            obs = self.reset_device()
+            self.variants = self.sim.get_variants()
+            return obs
+        if self.has_particles:
+            # Feeding / Drinking: a complete draw (bowl, start target, arm pose) from the host pool, the particle grid above the
+            # tool, then the reference's 100 settle steps on the device (feeding.py:318-320)
+            env, part, variant = sample_states_fd(self.reset_data, self.num_envs, self.np_random, genders)
+            self.set_state(env, variant, part, settle=SETTLE_STEPS)
+        else:
+            env, variant = sample_states(self.reset_data, self.num_envs, self.np_random, genders)
+            self.set_state(env, variant)
         self._last_reset = "host"
         return self.obs
 
@@ -219,16 +245,33 @@ class BatchedAssistiveEnv:
             out = self._step_result()
         return out
 
-    def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None):
-        """Import explicit env records ("identical initial states" for parity runs)."""
+    def set_state(self, env: np.ndarray, variant: Optional[np.ndarray] = None, part: Optional[np.ndarray] = None, settle: int = 0):
+        """Import explicit env records ("identical initial states" for parity runs); Feeding / Drinking also
+        take the particle records (`part`), and `settle` > 0 runs that many stepSimulation calls before the observation."""
         self.variants = variant
         self.sim.set_state(env, variant)
+        if part is not None:
+            self.sim.set_particles(part)
+        if settle > 0:
+            self.sim.settle(settle, 0, self._stream())
         self.sim.reset_obs(self.obs.data_ptr(), self._stream())
         self.elapsed = 0
         self._needs_reset = False
 
     def get_state(self) -> np.ndarray:
         return self.sim.get_state()
+
+    def get_particles(self) -> np.ndarray:
+        """Particle records of Feeding / Drinking (AVG_P_* layout of include/avg_model.h)."""
+        return self.sim.get_particles()
+
+    def contact_overflow(self):
+        """Per-environment overflow flags accumulated over the episode (AVG_E_OVERFLOW: bit 0 contact points beyond
+        AVG_MAX_CONTACT, bit 1 rows, bit 2 broadphase candidates, bit 3 particle contacts, bit 4 particle candidates) as a
+        CUDA int32 tensor: a contact the simulator could not keep is flagged, never silently dropped."""
+        torch = self.torch
+        state = self.sim.get_state_tensor(torch, self.device)
+        return state[:, 166].view(torch.int32)
 
     def _stream(self) -> int:
         return int(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -286,7 +329,7 @@ class BatchedAssistiveEnv:
         info = {"total_force_on_human": self.info_dev[:, 0], "task_success": self.info_dev[:, 1].to(torch.int32),
                 "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
                 "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len,
-                "TimeLimit.truncated": timeout}
+                "TimeLimit.truncated": timeout, "contact_overflow": self.contact_overflow()}
         if timeout:
             if self.auto_reset:                # gym vector-env convention: the returned observation starts the next episode
                 info["terminal_observation"] = self.obs.clone()

@@ -50,6 +50,21 @@ int avg_get_variants(AvgHandle* h, int env_begin, int env_count, int32_t* varian
 /* Device pointer of the state arena ([n_env][AVG_ENV_STRIDE] floats) for zero-copy inspection. */
 float* avg_state_device_ptr(AvgHandle* h);
 
+/* Feeding / Drinking: the food / water spheres the reference creates with createMultiBody(batchPositions=...) and reads with
+ * getBasePositionAndOrientation / getBaseVelocity (feeding.py:291-307,99-108; drinking.py:291-312,110-122).  One particle record
+ * per environment (AVG_P_* in include/avg_model.h: positions, velocities, alive / hit / event masks), HOST buffers of
+ * env_count x avg_particle_stride() floats.  Synchronous. */
+int avg_set_particles(AvgHandle* h, int env_begin, int env_count, const float* records);
+int avg_get_particles(AvgHandle* h, int env_begin, int env_count, float* records);
+float* avg_particles_device_ptr(AvgHandle* h);
+int avg_particle_stride(void);
+int avg_num_particles(const AvgHandle* h);
+/* Replaces the `for _ in range(100): p.stepSimulation()` settle loop of reset() (feeding.py:318-320, drinking.py:320-322,
+ * bed_bathing.py:286-292): n_steps calls of stepSimulation (each numSubSteps internal steps) without actions or per-frame
+ * hooks, for the environments whose byte in `mask` (DEVICE, NULL = all) is non-zero.  avg_reset runs it itself for
+ * Feeding / Drinking.  Asynchronous on `stream`. */
+int avg_settle(AvgHandle* h, const uint8_t* mask, int n_steps, void* stream);
+
 /* Episode reset on the device: replaces ScratchItchEnv.reset (scratch_itch.py:130-273) for the environments whose byte
  * in `mask` (DEVICE, [n_env], NULL = all) is non-zero, without a host round trip: gender, impairment and its
  * parameters (world_creation.py:66-72), tremor amplitudes (:141), a start pose from the variant's pool of IK solutions

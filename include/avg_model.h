@@ -12,21 +12,30 @@
 #include <stdint.h>
 
 #define AVG_MAGIC   0x4D475641u  /* "AVGM" */
-#define AVG_VERSION 9u
+#define AVG_VERSION 10u
 
 #define AVG_MAX_BODY   32   /* dynamic bodies per environment (one lane each)            */
 #define AVG_MAX_DOF    32   /* velocity DoF per environment (one lane each)               */
-#define AVG_MAX_EBODY   8   /* env-static bodies (pose given per environment)             */
-#define AVG_MAX_CONTACT 12  /* contact points kept per sub-step                           */
-#define AVG_MAX_ROWS   64   /* constraint rows per sub-step (2 per lane)                  */
+#define AVG_MAX_EBODY   4   /* env-static bodies (pose given per environment, AVG_E_EBODY) */
+#define AVG_MAX_CONTACT 32  /* articulation contact points kept per sub-step (SURVEY.md App. E budget) */
+#define AVG_MAX_ROWS   160  /* oracle: constraint rows per sub-step (motors, limits, weld, 2 per contact) */
 #define AVG_MAX_HULL_VERTS 48
+#define AVG_MAX_PARTICLE 64 /* food / water spheres per environment (feeding.py:300, drinking.py:301) */
+#define AVG_MAX_PCONTACT 320 /* particle contact points kept per internal step                */
+#define AVG_MAX_PCAND   384 /* particle-vs-shape narrowphase candidates per internal step     */
+#define AVG_MAX_COMPOUND 4  /* compound shapes (VHACD tool / bowl / head) per model           */
+#define AVG_MAX_CCHILD  72  /* convex children of one compound                                */
 
 enum { AVG_JOINT_REVOLUTE = 0, AVG_JOINT_PRISMATIC = 1, AVG_JOINT_FREE = 2 };
 enum { AVG_SHAPE_SPHERE = 0, AVG_SHAPE_CAPSULE = 1, AVG_SHAPE_BOX = 2, AVG_SHAPE_CYLINDER = 3,
-       AVG_SHAPE_HULL = 4, AVG_SHAPE_PLANE = 5 };
+       AVG_SHAPE_HULL = 4, AVG_SHAPE_PLANE = 5,
+       AVG_SHAPE_COMPOUND = 6 /* a link whose collision mesh is a VHACD set of convex hulls (spoon 64, cup 68, bowl 70, head 8-9):
+                                 one broadphase entry; vert_off / vert_cnt = first child / number of children in the child section
+                                 of the shape table (indices n_shape ..), which hold the hulls with body-frame AABBs */ };
 enum { AVG_TASK_SCRATCH_ITCH = 0, AVG_TASK_BED_BATHING = 1, AVG_TASK_FEEDING = 2, AVG_TASK_DRINKING = 3 };
 /* contact-report body ids (what the reference compares getContactPoints bodies against) */
-enum { AVG_REF_ROBOT = 0, AVG_REF_HUMAN = 1, AVG_REF_TOOL = 2, AVG_REF_FURNITURE = 3, AVG_REF_PLANE = 4 };
+enum { AVG_REF_ROBOT = 0, AVG_REF_HUMAN = 1, AVG_REF_TOOL = 2, AVG_REF_FURNITURE = 3, AVG_REF_PLANE = 4,
+       AVG_REF_TABLE = 5, AVG_REF_BOWL = 6 /* feeding.py:111: food touching the table or the bowl is spilled */ };
 
 /* dof flags */
 #define AVG_DOF_LIMIT        1u   /* Bullet joint-limit constraint exists (revolute/prismatic with lower<=upper) */
@@ -108,6 +117,7 @@ enum {
     AVG_F_SHOULDER,       /* human link 9  COM frame (upper arm), scratch_itch.py:118                        */
     AVG_F_ELBOW,          /* human link 11 COM frame (forearm)                                               */
     AVG_F_WRIST,          /* human link 13 COM frame (hand)                                                  */
+    AVG_F_HEAD,           /* human link 27 COM frame (head), feeding.py:134,346 / drinking.py:149                     */
     AVG_F_COUNT
 };
 
@@ -144,7 +154,19 @@ typedef struct AvgModelHeader {
                                      human link 9 (entries [0, n_target_upper), frame AVG_F_SHOULDER) or link 11 (the rest, AVG_F_ELBOW) */
     int32_t  n_target;            /* total_target_count (129 male / 91 female), 0 for other tasks; <= AVG_MAX_TARGET                     */
     int32_t  n_target_upper;
-    uint32_t pad2[3];
+    /* ---- version 10: compound shapes, env-static bodies, internal sub-steps, particles (Feeding / Drinking) ---- */
+    int32_t  n_cshape;            /* convex children of the compound shapes: shape table entries [n_shape, n_shape + n_cshape)               */
+    uint32_t off_caabb;           /* float4[n_cshape][2]: child AABB centre | half extents in the frame of the owning body                   */
+    int32_t  n_internal;          /* setPhysicsEngineParameter(numSubSteps) (feeding.py:289, drinking.py:287): internal steps per
+                                     p.stepSimulation, 1 when the reference passes 0; `dt` is the INTERNAL step (time_step / n_internal)     */
+    int32_t  n_particle;          /* food (8, feeding.py:300) / water (64, drinking.py:301) spheres; 0 for the other tasks                   */
+    int32_t  pshape;              /* shape table index of the particle template (a sphere), n_shape + n_cshape when n_particle > 0           */
+    float    p_mass;              /* 0.001 (feeding.py:299)                                                                                   */
+    float    p_gravity[3];        /* world gravity (0, 0, -9.81) (feeding.py:284); robot / human / tool are exempt through AvgBody.gravity    */
+    int32_t  tool_body;           /* dynamic body of the spoon / cup (free body), -1 when the tool is not a single free body                  */
+    int32_t  head_frozen_mask;    /* bodies of human joints 24..27: their masses are zeroed per environment (AVG_E_FROZEN) unless the
+                                     episode drew a tremor or the id is human-active (feeding.py:244 + world_creation.py:157-161)             */
+    uint32_t pad2[5];
 } AvgModelHeader;
 #define AVG_MAX_TARGET 160
 
@@ -157,8 +179,21 @@ enum {
     AVG_TF_FORCE_CAP,            /* 10,    scratch_itch.py:66 */
     AVG_TF_HUMAN_KP_ACTIVE,      /* human_gains passed to take_step (0.05), scratch_itch.py:45 */
     AVG_TF_HUMAN_FORCE,          /* human_forces (1.0) */
-    AVG_TF_CLOSEST_RANGE         /* BedBathing: getClosestPoints query distance (4.0), bed_bathing.py:61 */
+    AVG_TF_CLOSEST_RANGE,        /* BedBathing: getClosestPoints query distance (4.0), bed_bathing.py:61 */
+    /* 16..18: reference point of the device spatial algebra */
+    AVG_TF_MOUTH = 19,           /* [3] mouth_pos in the head frame: (0, -0.11 | -0.10, 0.03), feeding.py:253 / drinking.py:252 */
+    AVG_TF_EAT_RADIUS = 22,      /* 0.02 feeding.py:102, 0.03 drinking.py:114 */
+    AVG_TF_EAT_REWARD = 23,      /* +20 feeding.py:104, +10 drinking.py:117 */
+    AVG_TF_SPILL_REWARD = 24,    /* -5 feeding.py:113, -1 drinking.py:126 */
+    AVG_TF_Z_MIN = 25,           /* 0.5 feeding.py:111 / drinking.py:124 */
+    AVG_TF_FOOD_W = 26,          /* food_reward_weight / drinking_reward_weight (config.ini:25,34) */
+    AVG_TF_TILT_W = 27,          /* cup_tilt_weight 0.1 (config.ini:33); 0 for Feeding */
+    AVG_TF_TILT_SIGN = 28,       /* +1: -|roll + pi/2| (Jaco), -1: -|roll - pi/2| (other robots), drinking.py:72 */
+    AVG_TF_CUP_RADIUS = 29,      /* 0.05, drinking.py:112 */
+    AVG_TF_CUP_TOP = 30,         /* cup_top_center_offset z = -0.055, drinking.py:278 */
+    AVG_TF_CUP_BOTTOM = 31       /* cup_bottom_center_offset z = 0.07, drinking.py:279 */
 };
+/* Feeding / Drinking reuse AVG_TF_SUCCESS_THR for total count * task_success_threshold (feeding.py:76). */
 /* BedBathing reuses AVG_TF_SCRATCH_W for wiping_reward_weight (config.ini:17) and AVG_TF_SUCCESS_THR for
  * total_target_count * task_success_threshold (bed_bathing.py:72). */
 
@@ -187,7 +222,25 @@ enum {
     AVG_E_SOLVER_ITERS = 167, /* int: PGS iterations executed in the last env-step (diagnostic) */
     AVG_E_NCAND = 168,       /* int: narrowphase candidate pairs examined in the last env-step (diagnostic) */
     AVG_E_TARGET_MASK = 170, /* [5] uint32: BedBathing targets not yet wiped, bit t of word t/32 (bed_bathing.py:111-125 shrink the lists) */
-    AVG_E_LAST = 175
+    AVG_E_FROZEN = 175,      /* uint32: bodies whose mass / inertia count as zero in this episode (changeDynamics(mass=0), world_creation.py:157-161) */
+    AVG_E_LAST = 176
+};
+
+/* ---- per-environment particle record (Feeding / Drinking): AVG_P_STRIDE floats, structure of arrays so that lane p reads
+ *      particle p (and p + 32) with coalesced loads.  Spheres need no orientation.  Bit p of word p / 32 in the masks. ---- */
+enum {
+    AVG_P_POS = 0,           /* [3][64] centre, world */
+    AVG_P_VEL = 192,         /* [3][64] linear velocity */
+    AVG_P_ANG = 384,         /* [3][64] angular velocity */
+    AVG_P_ALIVE = 576,       /* uint32[2]: still in self.foods / self.waters (feeding.py:120, drinking.py:135); removed particles leave the simulation */
+    AVG_P_HIT = 578,         /* uint32[2]: foods_hit_person (feeding.py:116-119) */
+    AVG_P_TOUCH_HUMAN = 580, /* uint32[2]: has a contact point with the human in the last internal step (getContactPoints(f, human)) */
+    AVG_P_TOUCH_SPILL = 582, /* uint32[2]: ... with the table or the bowl (feeding.py:111) */
+    AVG_P_EV_EAT = 584,      /* uint32[2]: events of the last env-step, for parity tests: reached the mouth */
+    AVG_P_EV_SPILL = 586,    /*            spilled */
+    AVG_P_EV_HIT = 588,      /*            hit the person */
+    AVG_P_NCONTACT = 590,    /* int: particle contact points of the last internal step; [591] int: overflow flags */
+    AVG_P_STRIDE = 592
 };
 
 /* ---- episode reset on the device (reference ScratchItchEnv.reset random draws) ----
@@ -215,12 +268,21 @@ typedef struct AvgResetTable {
     float   ik_range;
     float   ik_target[8];                 /* pos(3) of the box centre, quat(4) target orientation, pad */
     float   ik_ee_frame[8];               /* pos(3), quat(4), pad */
+    /* ---- version 10: Feeding / Drinking (feeding.py:171-185,242-245,276-280,291-310) ---- */
+    int32_t hum_slot[8];                  /* slot of each dynamic human joint in the controllable list: joint - 4 (ScratchItch / BedBathing), joint - 24 (head) */
+    float   fin_q[8];                     /* open position per finger joint (Sawyer / Baxter: +position, -position, world_creation.py:313-320) */
+    int32_t n_particle, has_bowl;
+    uint32_t head_mask;                   /* bodies frozen unless the episode has a tremor or the id is human-active (AVG_E_FROZEN) */
+    float   ik_tol;                       /* random_restart_threshold: 0.03 ScratchItch, 0.01 Feeding / Drinking on the Jaco (feeding.py:278) */
+    float   bowl_center[4], bowl_quat[4]; /* feeding.py:184-185: centre of the +-0.05 square the bowl is drawn from, its orientation */
+    float   grid[AVG_MAX_PARTICLE][4];    /* particle offsets from the tool's base position, world axes (feeding.py:301-305) */
 } AvgResetTable;
 
 /* Counter-based random numbers of the device reset: draw k of episode `episode` of environment `env` under `seed`.
  * A 32-bit mix (murmur3 finaliser over a running hash); the numpy mirror in compiler/reset.py computes the same bits.
  * Draw indices: 0 gender, 1 impairment, 2 limit scale, 3 strength, 4..13 tremor, 14 limb, 15 point along the limb,
- * 16 angle around the limb, 17 start pose; on-device IK: 20..22 start target, 32 + 8 r + j rest pose of joint j in restart r. */
+ * 16 angle around the limb, 17 start pose; on-device IK: 20..22 start target, 32 + 8 r + j rest pose of joint j in restart r.
+ * Feeding / Drinking: 4..7 tremor of the head joints, 8..10 head angles (joints 25..27), 11..12 bowl offset. */
 #define AVG_RNG_MIX(h) do { (h) ^= (h) >> 16; (h) *= 0x85ebca6bu; (h) ^= (h) >> 13; (h) *= 0xc2b2ae35u; (h) ^= (h) >> 16; } while (0)
 
 /* ---- policy for on-device rollouts (reference enjoy_vr.py:77-117: actor_critic.act on VecNormalize'd observations) ----

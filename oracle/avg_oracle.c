@@ -97,7 +97,7 @@ typedef struct {
 static int model_open(const void* blob, Model* m) {
     const AvgModelHeader* h = (const AvgModelHeader*)blob;
     if (h->magic != AVG_MAGIC || h->version != AVG_VERSION) return -1;
-    if (h->n_body > MAXB || h->n_dof > MAXD) return -2;
+    if (h->n_body + h->n_ebody > MAXB || h->n_dof > MAXD || h->n_ebody > AVG_MAX_EBODY || h->n_particle > AVG_MAX_PARTICLE) return -2;
     const char* b = (const char*)blob;
     m->h = h;
     m->body = (const AvgBody*)(b + h->off_body);
@@ -128,6 +128,15 @@ static void body_pose(const Kin* k, int body, v3* p, quat* q) {
 
 /* forward kinematics: C_body = C_parent ∘ Ta ∘ joint(q) ∘ Tb  (include/avg_model.h AvgBody) */
 static void fk(const Model* m, const double* env, Kin* k) {
+    /* env-static bodies (the Feeding bowl, feeding.py:184-185): pose straight from the record, slots n_body + e */
+    for (int e = 0; e < m->h->n_ebody; ++e) {
+        int b = m->h->n_body + e;
+        const double* q = env + AVG_E_EBODY + 7 * e;
+        k->p[b] = V(q[0], q[1], q[2]);
+        quat r = {q[3], q[4], q[5], q[6]};
+        k->q[b] = qnormalize(r); k->R[b] = qmat(k->q[b]);
+        k->axis[b] = V(0, 0, 0); k->org[b] = k->p[b];
+    }
     for (int b = 0; b < m->h->n_body; ++b) {
         const AvgBody* B = &m->body[b];
         if (B->jtype == AVG_JOINT_FREE) {
@@ -481,8 +490,11 @@ static int narrowphase(const WShape* A, const WShape* B, double thr, Contact* c)
     return 1;
 }
 
+static int n_shapes_all(const Model* m) { return m->h->n_shape + m->h->n_cshape + (m->h->n_particle > 0 ? 1 : 0); }
+
 static int collide(const Model* m, const Kin* k, Contact* out, int* overflow) {
-    int ns = m->h->n_shape, nc = 0;
+    /* the pair table lists the convex children of compound shapes explicitly (compiler/scene.py expand_compounds) */
+    int ns = n_shapes_all(m), nc = 0;
     WShape* ws = (WShape*)malloc(sizeof(WShape) * ns);
     v3* ac = (v3*)malloc(sizeof(v3) * ns); v3* ah = (v3*)malloc(sizeof(v3) * ns);
     for (int i = 0; i < ns; ++i) { shape_world(m, k, i, &ws[i]); shape_aabb(&ws[i], &ac[i], &ah[i]); }
@@ -557,14 +569,19 @@ typedef struct {
     double IwInv[MAXB][3][3];
 } Dyn;
 
-static void world_inertia(const Model* m, const Kin* k, Dyn* d) {
+/* changeDynamics(mass=0) per episode (world_creation.py:157-161): bodies in the record's AVG_E_FROZEN mask count as massless */
+static int body_frozen(const double* env, int b) { return (((uint32_t)env[AVG_E_FROZEN]) >> b) & 1u; }
+
+static void world_inertia(const Model* m, const Kin* k, const double* env, Dyn* d) {
     for (int b = 0; b < m->h->n_body; ++b) {
         const AvgBody* B = &m->body[b];
+        double ine[3] = {B->inertia[0], B->inertia[1], B->inertia[2]};
+        if (body_frozen(env, b)) ine[0] = ine[1] = ine[2] = 0.0;
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
             double s = 0, si = 0;
             for (int a = 0; a < 3; ++a) {
-                s += k->R[b].m[i][a] * B->inertia[a] * k->R[b].m[j][a];
-                si += (B->inertia[a] > 0) ? k->R[b].m[i][a] / B->inertia[a] * k->R[b].m[j][a] : 0.0;
+                s += k->R[b].m[i][a] * ine[a] * k->R[b].m[j][a];
+                si += (ine[a] > 0) ? k->R[b].m[i][a] / ine[a] * k->R[b].m[j][a] : 0.0;
             }
             d->Iw[b][i][j] = s; d->IwInv[b][i][j] = si;
         }
@@ -576,11 +593,12 @@ static void aba(const Model* m, const Kin* k, const double* env, Dyn* d, double*
     const AvgModelHeader* h = m->h;
     int nb = h->n_body;
     sv pA[MAXB];
-    world_inertia(m, k, d);
+    world_inertia(m, k, env, d);
     /* pass 1 */
     for (int b = 0; b < nb; ++b) {
         const AvgBody* B = &m->body[b];
         if (B->jtype == AVG_JOINT_FREE) continue;
+        const double bmass = body_frozen(env, b) ? 0.0 : B->mass;
         double qd = env[AVG_E_QD + B->dof];
         if (B->jtype == AVG_JOINT_REVOLUTE) d->S[b] = sv_make(k->axis[b], vcross(k->org[b], k->axis[b]));
         else d->S[b] = sv_make(V(0, 0, 0), k->axis[b]);
@@ -588,14 +606,14 @@ static void aba(const Model* m, const Kin* k, const double* env, Dyn* d, double*
         if (B->parent >= 0) { for (int i = 0; i < 6; ++i) d->vel[b].v[i] = d->vel[B->parent].v[i] + vj.v[i]; }
         else d->vel[b] = vj;
         d->cb[b] = crm(&d->vel[b], &vj);
-        spatial_inertia(B->mass, k->p[b], d->Iw[b], &d->IA[b]);
+        spatial_inertia(bmass, k->p[b], d->Iw[b], &d->IA[b]);
         sv Iv = sm_mul(&d->IA[b], &d->vel[b]);
         pA[b] = crf(&d->vel[b], &Iv);
         /* external force at the COM: gravity and Bullet's velocity damping */
         v3 w = sv_ang(&d->vel[b]);
         v3 vc = vadd(sv_lin(&d->vel[b]), vcross(w, k->p[b]));
-        v3 f = vscale(f3(B->gravity), B->mass);
-        f = vsub(f, vscale(vc, B->mass * (h->lin_damp + h->lin_damp * vnorm(vc))));
+        v3 f = vscale(f3(B->gravity), bmass);
+        f = vsub(f, vscale(vc, bmass * (h->lin_damp + h->lin_damp * vnorm(vc))));
         v3 Iw_w = V(d->Iw[b][0][0] * w.x + d->Iw[b][0][1] * w.y + d->Iw[b][0][2] * w.z,
                     d->Iw[b][1][0] * w.x + d->Iw[b][1][1] * w.y + d->Iw[b][1][2] * w.z,
                     d->Iw[b][2][0] * w.x + d->Iw[b][2][1] * w.y + d->Iw[b][2][2] * w.z);
@@ -687,7 +705,7 @@ static void aba_delta(const Model* m, const Dyn* d, const double* tau, double* o
 
 /* Jacobian row of "velocity of the point r on `body` along n" (body < 0: static, contributes nothing) */
 static void jac_point(const Model* m, const Kin* k, const Dyn* d, int body, v3 r, v3 n, double sign, double* J) {
-    if (body < 0) return;
+    if (body < 0 || body >= m->h->n_body) return;             /* static world / env-static body */
     const AvgBody* B = &m->body[body];
     if (B->jtype == AVG_JOINT_FREE) {
         v3 rn = vcross(vsub(r, k->p[body]), n);
@@ -699,7 +717,7 @@ static void jac_point(const Model* m, const Kin* k, const Dyn* d, int body, v3 r
     for (int b = body; b >= 0; b = m->body[b].parent) J[m->body[b].dof] += sign * sv_dot(&d->S[b], &f);
 }
 static void jac_ang(const Model* m, const Dyn* d, int body, v3 n, double sign, double* J) {
-    if (body < 0) return;
+    if (body < 0 || body >= m->h->n_body) return;
     const AvgBody* B = &m->body[body];
     if (B->jtype == AVG_JOINT_FREE) { J[B->dof + 3] += sign * n.x; J[B->dof + 4] += sign * n.y; J[B->dof + 5] += sign * n.z; return; }
     sv f = sv_make(n, V(0, 0, 0));
@@ -713,6 +731,10 @@ typedef struct {
     double diag, lambda;
     int friction_of;     /* row index of the normal row for friction rows, else -1 */
     double mu;
+    /* particle part of the row (Feeding / Drinking): particle pa (and pb for particle-particle contacts), -1 = none.
+     * Linear / angular Jacobian blocks and their M^-1 images (spheres: v += jl / m, w += ja / I). */
+    int pa, pb;
+    v3 jl_a, ja_a, jl_b, ja_b;
 } Row;
 
 static double limit_lo(const AvgDof* D, const double* env) { return (D->flags & AVG_DOF_HUMAN) ? D->lower * env[AVG_E_LIMIT_SCALE] : D->lower; }
@@ -724,10 +746,96 @@ static void finish_row(const Model* m, const Dyn* d, const double* qd, Row* r) {
     for (int i = 0; i < m->h->n_dof; ++i) { diag += r->J[i] * r->W[i]; u0 += r->J[i] * qd[i]; }
     r->diag = diag; r->lambda = 0;
     r->target -= u0;
+    r->pa = r->pb = -1;
 }
 
-/* one physics sub-step = p.stepSimulation() with numSubSteps=0 (scratch_itch.py:258) */
-static void substep(const Model* m, double* env, Contact* contacts, int* ncontact) {
+/* ---- food / water particles (feeding.py:291-307, drinking.py:291-312): free spheres, r = 5 mm, 1 g ------------------------
+ * [UPSTREAM-BULLET] createMultiBody(baseMass, sphere, useMaximalCoordinates=False) makes each one a btMultiBody with a free
+ * base and no links: gravity, the multibody velocity damping (0.04), sphere inertia 2/5 m r^2, contacts against everything.
+ * Restated with these documented simplifications: a particle exchanges momentum with other particles and with the
+ * tool (two-way, the tool is a free body); against links of the robot / human articulations the contact is one-way (the link
+ * counts as kinematic with its start-of-step velocity: a 1 g sphere does not push a robot arm); particles removed from
+ * self.foods / self.waters leave the simulation (the reference leaves spilled ones rolling on the floor). */
+typedef struct {
+    int p;               /* particle A */
+    int q;               /* particle B or -1 */
+    int shape_b;         /* shape index of B (-1 for particle-particle) */
+    v3 n;                /* from B to A */
+    double dist;
+    v3 pb;               /* contact point on B */
+} PContact;
+
+#define P_X(part, p, c) ((part)[AVG_P_POS + 64 * (c) + (p)])
+#define P_V(part, p, c) ((part)[AVG_P_VEL + 64 * (c) + (p)])
+#define P_W(part, p, c) ((part)[AVG_P_ANG + 64 * (c) + (p)])
+static int p_alive(const double* part, int p) { return (((uint32_t)part[AVG_P_ALIVE + (p >> 5)]) >> (p & 31)) & 1u; }
+static void p_setbit(double* part, int slot, int p) { part[slot + (p >> 5)] = (double)(((uint32_t)part[slot + (p >> 5)]) | (1u << (p & 31))); }
+static void p_clrbit(double* part, int slot, int p) { part[slot + (p >> 5)] = (double)(((uint32_t)part[slot + (p >> 5)]) & ~(1u << (p & 31))); }
+static int p_getbit(const double* part, int slot, int p) { return (((uint32_t)part[slot + (p >> 5)]) >> (p & 31)) & 1u; }
+
+/* Particle contacts of one internal step, in canonical order: for p ascending, the shapes in ascending shape-table index
+ * (moving, static, compound children); then the particle-particle pairs (p, q > p) in lexicographic order. */
+static int particle_collide(const Model* m, const Kin* k, const double* part, PContact* out, int* overflow) {
+    const AvgModelHeader* h = m->h;
+    int np = h->n_particle, nc = 0;
+    if (np <= 0) return 0;
+    const AvgShape* PS = &m->shape[h->pshape];
+    const double r = PS->radius, pthr = PS->thr;
+    int nall = h->n_shape + h->n_cshape;
+    WShape* ws = (WShape*)malloc(sizeof(WShape) * nall);
+    v3* ac = (v3*)malloc(sizeof(v3) * nall); v3* ah = (v3*)malloc(sizeof(v3) * nall);
+    for (int i = 0; i < nall; ++i) { shape_world(m, k, i, &ws[i]); if (ws[i].s->type != AVG_SHAPE_COMPOUND) shape_aabb(&ws[i], &ac[i], &ah[i]); }
+    for (int p = 0; p < np; ++p) {
+        if (!p_alive(part, p)) continue;
+        WShape A; A.s = PS; A.verts = 0; A.planes = 0;
+        A.p = V(P_X(part, p, 0), P_X(part, p, 1), P_X(part, p, 2));
+        quat id = {0, 0, 0, 1}; A.R = qmat(id);
+        for (int b = 0; b < nall; ++b) {
+            const AvgShape* S = ws[b].s;
+            if (S->type == AVG_SHAPE_COMPOUND) continue;
+            double thr = fmin(pthr, (double)S->thr);
+            if (S->type != AVG_SHAPE_PLANE) {
+                if (fabs(A.p.x - ac[b].x) > ah[b].x + r + thr) continue;
+                if (fabs(A.p.y - ac[b].y) > ah[b].y + r + thr) continue;
+                if (fabs(A.p.z - ac[b].z) > ah[b].z + r + thr) continue;
+            } else if (A.p.z - r > thr) continue;
+            Contact c;
+            if (narrowphase(&A, &ws[b], thr, &c)) {
+                if (nc >= AVG_MAX_PCONTACT) { *overflow |= 8; goto done; }
+                out[nc].p = p; out[nc].q = -1; out[nc].shape_b = b; out[nc].n = c.n; out[nc].dist = c.dist; out[nc].pb = c.pb;
+                nc++;
+            }
+        }
+    }
+    for (int p = 0; p < np; ++p) {
+        if (!p_alive(part, p)) continue;
+        v3 xp = V(P_X(part, p, 0), P_X(part, p, 1), P_X(part, p, 2));
+        for (int q = p + 1; q < np; ++q) {
+            if (!p_alive(part, q)) continue;
+            v3 xq = V(P_X(part, q, 0), P_X(part, q, 1), P_X(part, q, 2));
+            v3 dlt = vsub(xp, xq);
+            double dd = vnorm(dlt), dist = dd - 2.0 * r;
+            if (dist >= pthr) continue;
+            if (nc >= AVG_MAX_PCONTACT) { *overflow |= 8; goto done; }
+            out[nc].p = p; out[nc].q = q; out[nc].shape_b = -1; out[nc].dist = dist;
+            out[nc].n = dd > 1e-12 ? vscale(dlt, 1.0 / dd) : V(0, 0, 1);
+            out[nc].pb = vadd(xq, vscale(out[nc].n, r));
+            nc++;
+        }
+    }
+done:
+    free(ws); free(ac); free(ah);
+    return nc;
+}
+
+static v3 plane_space1(v3 n) {                       /* btPlaneSpace1 */
+    if (fabs(n.z) > 0.7071067811865476) { double a = n.y * n.y + n.z * n.z, kk = 1.0 / sqrt(a); return V(0, -n.z * kk, n.y * kk); }
+    double a = n.x * n.x + n.y * n.y, kk = 1.0 / sqrt(a); return V(-n.y * kk, n.x * kk, 0);
+}
+
+/* one internal physics step: p.stepSimulation() with numSubSteps = 0 (scratch_itch.py:258), or one of the numSubSteps = 2
+ * internal steps of Feeding / Drinking (feeding.py:289).  `part` = particle record (float64 image, ints as numbers) or NULL. */
+static void substep(const Model* m, double* env, double* part, Contact* contacts, int* ncontact) {
     const AvgModelHeader* h = m->h;
     int nd = h->n_dof, nb = h->n_body;
     double dt = h->dt;
@@ -735,14 +843,29 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
     fk(m, env, &k);
     int overflow = 0;
     int nc = collide(m, &k, contacts, &overflow);
+    const int np = part ? h->n_particle : 0;
+    PContact* pcs = np > 0 ? (PContact*)malloc(sizeof(PContact) * AVG_MAX_PCONTACT) : 0;
+    int npc = np > 0 ? particle_collide(m, &k, part, pcs, &overflow) : 0;
     /* unconstrained velocity update */
     double qdd[MAXD], qd[MAXD];
     aba(m, &k, env, d, qdd);
     for (int i = 0; i < nd; ++i) {
         qd[i] = env[AVG_E_QD + i] + dt * qdd[i];
     }
+    /* particles: gravity and the multibody base damping, v* = v + dt (g - v (k + k |v|)), w* = w - dt w (k + k |w|) */
+    double pv[AVG_MAX_PARTICLE][6];
+    const double pm = h->p_mass, prad = np > 0 ? m->shape[h->pshape].radius : 0.0;
+    const double pinv_m = pm > 0 ? 1.0 / pm : 0.0, pinv_i = pm > 0 ? 1.0 / (0.4 * pm * prad * prad) : 0.0;
+    for (int p = 0; p < np; ++p) {
+        v3 v = V(P_V(part, p, 0), P_V(part, p, 1), P_V(part, p, 2)), w = V(P_W(part, p, 0), P_W(part, p, 1), P_W(part, p, 2));
+        v3 a = vsub(f3(h->p_gravity), vscale(v, h->lin_damp + h->lin_damp * vnorm(v)));
+        v3 al = vneg(vscale(w, h->ang_damp + h->ang_damp * vnorm(w)));
+        pv[p][0] = v.x + dt * a.x; pv[p][1] = v.y + dt * a.y; pv[p][2] = v.z + dt * a.z;
+        pv[p][3] = w.x + dt * al.x; pv[p][4] = w.y + dt * al.y; pv[p][5] = w.z + dt * al.z;
+    }
     /* constraint rows, Bullet order: non-contact (motors, limits, fixed constraint), contact normals, friction */
-    Row* rows = (Row*)calloc(MAXR, sizeof(Row));
+    const int maxr = MAXR + 2 * AVG_MAX_PCONTACT;
+    Row* rows = (Row*)calloc(maxr, sizeof(Row));
     int nr = 0;
     for (int i = 0; i < h->n_jdof; ++i) {          /* position motors, btMultiBodyJointMotor [UPSTREAM-BULLET] */
         const AvgDof* D = &m->dof[i];
@@ -808,6 +931,38 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
         r->lo = 0; r->hi = 1e30; r->friction_of = -1;
         finish_row(m, d, qd, r);
     }
+    /* particle contact normals.  Body B is another particle, the tool (free body: two-way), or kinematic (static shape, or a
+     * link of an articulation with its start-of-step point velocity).  A sphere's normal impulse passes through its centre. */
+    int first_pcontact_row = nr;
+    v3* pc_vb = npc > 0 ? (v3*)malloc(sizeof(v3) * npc) : 0;      /* velocity of B's contact point when B is kinematic */
+    for (int c = 0; c < npc; ++c) {
+        PContact* C = &pcs[c];
+        Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+        r->pa = C->p; r->pb = C->q; r->jl_a = C->n; r->ja_a = V(0, 0, 0);
+        double diag = pinv_m, u0 = C->n.x * pv[C->p][0] + C->n.y * pv[C->p][1] + C->n.z * pv[C->p][2];
+        pc_vb[c] = V(0, 0, 0);
+        if (C->q >= 0) {
+            r->jl_b = vneg(C->n); r->ja_b = V(0, 0, 0);
+            diag += pinv_m; u0 -= C->n.x * pv[C->q][0] + C->n.y * pv[C->q][1] + C->n.z * pv[C->q][2];
+        } else {
+            int body = m->shape[C->shape_b].body;
+            if (body >= 0 && body < nb && body == h->tool_body) {
+                jac_point(m, &k, d, body, C->pb, C->n, -1.0, r->J);
+                aba_delta(m, d, r->J, r->W);
+                for (int i = 0; i < nd; ++i) { diag += r->J[i] * r->W[i]; u0 += r->J[i] * qd[i]; }
+            } else if (body >= 0 && body < nb) {
+                double Jx[3][MAXD]; memset(Jx, 0, sizeof(Jx));
+                for (int ax = 0; ax < 3; ++ax) jac_point(m, &k, d, body, C->pb, V(ax == 0, ax == 1, ax == 2), 1.0, Jx[ax]);
+                double vb[3] = {0, 0, 0};
+                for (int ax = 0; ax < 3; ++ax) for (int i = 0; i < nd; ++i) vb[ax] += Jx[ax][i] * env[AVG_E_QD + i];
+                pc_vb[c] = V(vb[0], vb[1], vb[2]);
+                u0 -= vdot(C->n, pc_vb[c]);
+            }
+        }
+        r->diag = diag; r->lambda = 0;
+        r->target = ((C->dist > 0) ? -C->dist / dt : -C->dist * h->erp / dt) - u0;
+        r->lo = 0; r->hi = 1e30; r->friction_of = -1;
+    }
     for (int c = 0; c < nc; ++c) {                  /* one friction direction per contact [UPSTREAM-BULLET default] */
         Contact* C = &contacts[c];
         Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
@@ -826,17 +981,60 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
         double ll = vnorm(lat);
         v3 t;
         if (ll > 1e-6) t = vscale(lat, 1.0 / ll);
-        else {                                      /* btPlaneSpace1 */
-            if (fabs(C->n.z) > 0.7071067811865476) { double a = C->n.y * C->n.y + C->n.z * C->n.z, kk = 1.0 / sqrt(a); t = V(0, -C->n.z * kk, C->n.y * kk); }
-            else { double a = C->n.x * C->n.x + C->n.y * C->n.y, kk = 1.0 / sqrt(a); t = V(-C->n.y * kk, C->n.x * kk, 0); }
-        }
+        else t = plane_space1(C->n);
         for (int i = 0; i < nd; ++i) r->J[i] = t.x * Jx[0][i] + t.y * Jx[1][i] + t.z * Jx[2][i];
         r->target = 0; r->lo = 0; r->hi = 0; r->friction_of = first_contact_row + c;
         r->mu = (double)m->shape[C->sa].friction * (double)m->shape[C->sb].friction;
         finish_row(m, d, qd, r);
     }
+    for (int c = 0; c < npc; ++c) {                 /* particle friction rows: the sphere's lever arm is -r n */
+        PContact* C = &pcs[c];
+        Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
+        r->pa = C->p; r->pb = C->q;
+        const double* va = pv[C->p];
+        v3 ra = vscale(C->n, -prad);
+        v3 vrel = vadd(V(va[0], va[1], va[2]), vcross(V(va[3], va[4], va[5]), ra));
+        double Jx[3][MAXD]; memset(Jx, 0, sizeof(Jx));
+        int body = -1, twoway = 0;
+        double mu_b = 0.5;
+        if (C->q >= 0) {
+            const double* vb = pv[C->q];
+            v3 rb = vscale(C->n, prad);
+            vrel = vsub(vrel, vadd(V(vb[0], vb[1], vb[2]), vcross(V(vb[3], vb[4], vb[5]), rb)));
+            mu_b = m->shape[h->pshape].friction;
+        } else {
+            body = m->shape[C->shape_b].body;
+            mu_b = m->shape[C->shape_b].friction;
+            if (body >= 0 && body < nb && body == h->tool_body) {
+                twoway = 1;
+                for (int ax = 0; ax < 3; ++ax) jac_point(m, &k, d, body, C->pb, V(ax == 0, ax == 1, ax == 2), -1.0, Jx[ax]);
+                double vr[3] = {0, 0, 0};
+                for (int ax = 0; ax < 3; ++ax) for (int i = 0; i < nd; ++i) vr[ax] += Jx[ax][i] * qd[i];
+                vrel = vadd(vrel, V(vr[0], vr[1], vr[2]));
+            } else vrel = vsub(vrel, pc_vb[c]);
+        }
+        v3 lat = vsub(vrel, vscale(C->n, vdot(vrel, C->n)));
+        double ll = vnorm(lat);
+        v3 t = ll > 1e-6 ? vscale(lat, 1.0 / ll) : plane_space1(C->n);
+        r->jl_a = t; r->ja_a = vcross(ra, t);
+        double diag = pinv_m + pinv_i * vdot(r->ja_a, r->ja_a);
+        if (C->q >= 0) {
+            v3 rb = vscale(C->n, prad);
+            r->jl_b = vneg(t); r->ja_b = vneg(vcross(rb, t));
+            diag += pinv_m + pinv_i * vdot(r->ja_b, r->ja_b);
+        } else if (twoway) {
+            for (int i = 0; i < nd; ++i) r->J[i] = t.x * Jx[0][i] + t.y * Jx[1][i] + t.z * Jx[2][i];
+            aba_delta(m, d, r->J, r->W);
+            for (int i = 0; i < nd; ++i) diag += r->J[i] * r->W[i];
+        }
+        r->diag = diag; r->lambda = 0;
+        r->target = -vdot(vrel, t);                 /* target change of J.v: cancel the lateral velocity (clamped by mu * normal impulse) */
+        r->lo = 0; r->hi = 0; r->friction_of = first_pcontact_row + c;
+        r->mu = (double)m->shape[h->pshape].friction * mu_b;
+    }
     /* projected Gauss-Seidel in velocity space, as btMultiBodyConstraintSolver */
     double dv[MAXD]; memset(dv, 0, sizeof(dv));
+    double dpv[AVG_MAX_PARTICLE][6]; memset(dpv, 0, sizeof(dpv));
     for (int it = 0; it < h->solver_iters; ++it) {
         double resid = 0;
         for (int ri = 0; ri < nr; ++ri) {
@@ -845,11 +1043,17 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
             double lo = r->lo, hi = r->hi;
             if (r->friction_of >= 0) { double lim = r->mu * rows[r->friction_of].lambda; lo = -lim; hi = lim; }
             double jdv = 0; for (int i = 0; i < nd; ++i) jdv += r->J[i] * dv[i];
+            if (r->pa >= 0) { const double* a = dpv[r->pa]; jdv += r->jl_a.x * a[0] + r->jl_a.y * a[1] + r->jl_a.z * a[2] + r->ja_a.x * a[3] + r->ja_a.y * a[4] + r->ja_a.z * a[5]; }
+            if (r->pb >= 0) { const double* b = dpv[r->pb]; jdv += r->jl_b.x * b[0] + r->jl_b.y * b[1] + r->jl_b.z * b[2] + r->ja_b.x * b[3] + r->ja_b.y * b[4] + r->ja_b.z * b[5]; }
             double delta = (r->target - jdv) / r->diag;
             double sum = r->lambda + delta;
             if (sum < lo) sum = lo; if (sum > hi) sum = hi;
             delta = sum - r->lambda; r->lambda = sum;
             for (int i = 0; i < nd; ++i) dv[i] += r->W[i] * delta;
+            if (r->pa >= 0) { double* a = dpv[r->pa]; a[0] += pinv_m * r->jl_a.x * delta; a[1] += pinv_m * r->jl_a.y * delta; a[2] += pinv_m * r->jl_a.z * delta;
+                              a[3] += pinv_i * r->ja_a.x * delta; a[4] += pinv_i * r->ja_a.y * delta; a[5] += pinv_i * r->ja_a.z * delta; }
+            if (r->pb >= 0) { double* b = dpv[r->pb]; b[0] += pinv_m * r->jl_b.x * delta; b[1] += pinv_m * r->jl_b.y * delta; b[2] += pinv_m * r->jl_b.z * delta;
+                              b[3] += pinv_i * r->ja_b.x * delta; b[4] += pinv_i * r->ja_b.y * delta; b[5] += pinv_i * r->ja_b.z * delta; }
             double rv = delta * r->diag; if (rv * rv > resid) resid = rv * rv;
         }
         if (resid <= h->residual_thr) break;
@@ -874,8 +1078,28 @@ static void substep(const Model* m, double* env, Contact* contacts, int* ncontac
             q[3] = cur.x; q[4] = cur.y; q[5] = cur.z; q[6] = cur.w;
         } else env[AVG_E_Q + B->qidx] += dt * env[AVG_E_QD + B->dof];
     }
+    if (np > 0) {
+        /* which live particles have a contact point with the human / the table or the bowl (feeding.py:111,116: existence of
+         * getContactPoints entries, i.e. of manifold points of this step's collision pass) */
+        part[AVG_P_TOUCH_HUMAN] = part[AVG_P_TOUCH_HUMAN + 1] = 0; part[AVG_P_TOUCH_SPILL] = part[AVG_P_TOUCH_SPILL + 1] = 0;
+        for (int c = 0; c < npc; ++c) {
+            if (pcs[c].q >= 0) continue;
+            int rb = m->shape[pcs[c].shape_b].ref_body;
+            if (rb == AVG_REF_HUMAN) p_setbit(part, AVG_P_TOUCH_HUMAN, pcs[c].p);
+            if (rb == AVG_REF_TABLE || rb == AVG_REF_BOWL) p_setbit(part, AVG_P_TOUCH_SPILL, pcs[c].p);
+        }
+        for (int p = 0; p < np; ++p) {
+            if (!p_alive(part, p)) continue;
+            for (int c = 0; c < 3; ++c) {
+                P_V(part, p, c) = pv[p][c] + dpv[p][c]; P_W(part, p, c) = pv[p][3 + c] + dpv[p][3 + c];
+                P_X(part, p, c) += dt * P_V(part, p, c);
+            }
+        }
+        part[AVG_P_NCONTACT] = npc;
+        if (overflow) part[AVG_P_NCONTACT + 1] = (double)((int)part[AVG_P_NCONTACT + 1] | overflow);
+    }
     if (overflow) env[AVG_E_OVERFLOW] = (double)((int)env[AVG_E_OVERFLOW] | overflow);
-    free(rows); free(d);
+    free(rows); free(d); free(pcs); free(pc_vb);
 }
 
 /* env.py:353-371: Keras Sequential Dense 4 -> 64 tanh -> 64 tanh -> 64 tanh -> 1 sigmoid on the remapped right-arm
@@ -1090,17 +1314,181 @@ static void bb_finish_step(const Model* m, double* env, const Contact* contacts,
     }
 }
 
+
+/* ---- Feeding / Drinking (feeding.py, drinking.py) ------------------------------------------------------------- */
+/* update_targets, feeding.py:345-349: the mouth = head link 27 frame o mouth_pos */
+static v3 fd_mouth(const Model* m, const Kin* k) {
+    v3 p; quat q; frame_pose(m, k, AVG_F_HEAD, &p, &q);
+    const float* tf = m->h->task_f;
+    return vadd(p, qrot(q, V(tf[AVG_TF_MOUTH], tf[AVG_TF_MOUTH + 1], tf[AVG_TF_MOUTH + 2])));
+}
+/* feeding.py:123-142, drinking.py:138-157: robot obs[25] (+ human obs[23]) */
+static void fd_get_obs(const Model* m, const double* env, double tool_force_on_human, double robot_force_on_human, double* obs) {
+    const AvgModelHeader* h = m->h;
+    Kin k; fk(m, env, &k);
+    v3 torso, tool, head, chest; quat tq, hq, dummy;
+    frame_pose(m, &k, AVG_F_TORSO, &torso, &dummy);
+    frame_pose(m, &k, AVG_F_TOOL_TIP, &tool, &tq);
+    frame_pose(m, &k, AVG_F_HEAD, &head, &hq);
+    frame_pose(m, &k, AVG_F_CHEST, &chest, &dummy);
+    v3 tgt = fd_mouth(m, &k);
+    int o = 0; v3 t;
+    t = vsub(tool, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+    t = vsub(tool, tgt); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].action >= 0 && m->dof[i].action < h->n_action_robot) obs[o++] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+    t = vsub(head, torso); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+    obs[o++] = hq.x; obs[o++] = hq.y; obs[o++] = hq.z; obs[o++] = hq.w;
+    obs[o++] = tool_force_on_human;
+    if (h->human_control) {                                   /* positions relative to human link 3, head joints 24..27 */
+        t = vsub(tool, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        obs[o++] = tq.x; obs[o++] = tq.y; obs[o++] = tq.z; obs[o++] = tq.w;
+        t = vsub(tool, tgt); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        double hq4[4] = {0, 0, 0, 0};
+        for (int i = 0; i < h->n_jdof; ++i) if (m->dof[i].human_slot >= 0 && m->dof[i].human_slot < 4) hq4[m->dof[i].human_slot] = env[AVG_E_Q + m->body[m->dof[i].body].qidx];
+        for (int i = 0; i < 4; ++i) obs[o++] = hq4[i];
+        t = vsub(head, chest); obs[o++] = t.x; obs[o++] = t.y; obs[o++] = t.z;
+        obs[o++] = hq.x; obs[o++] = hq.y; obs[o++] = hq.z; obs[o++] = hq.w;
+        obs[o++] = robot_force_on_human; obs[o++] = tool_force_on_human;
+    }
+}
+/* btQuaternion::getEulerZYX roll (p.getEulerFromQuaternion(q)[0]) [UPSTREAM-BULLET] */
+static double quat_roll(quat q) {
+    double sqx = q.x * q.x, sqy = q.y * q.y, sqz = q.z * q.z, sqw = q.w * q.w;
+    double sarg = -2.0 * (q.x * q.z - q.w * q.y) / (sqx + sqy + sqz + sqw);
+    if (sarg <= -0.99999 || sarg >= 0.99999) return 0.0;
+    return atan2(2.0 * (q.y * q.z + q.w * q.x), sqw - sqx - sqy + sqz);
+}
+/* The part of FeedingEnv.step / DrinkingEnv.step after take_step (feeding.py:56-80, drinking.py:57-83) with get_total_force
+ * (feeding.py:83-90) and get_food_rewards / get_water_rewards (feeding.py:92-121, drinking.py:95-136).
+ * out_info: [0] total_force_on_human, [1] task_success flag, [2] robot_force_on_human, [3] tool_force_on_human,
+ *           [4] reward_distance, [5] reward_action, [6] reward_food (+ tilt term for Drinking in [8] of the CUDA taps), [7] preferences_score */
+static void fd_finish_step(const Model* m, double* env, double* part, const Contact* contacts, int nc, double raw_sq, double* obs,
+                           double* reward, double* out_info) {
+    const AvgModelHeader* h = m->h;
+    const float* tf = h->task_f;
+    const double dt = h->dt;
+    const int drinking = h->task == AVG_TASK_DRINKING;
+    Kin k; fk(m, env, &k);
+    double robot_force_on_human = 0, tool_force_on_human = 0;
+    for (int c = 0; c < nc; ++c) {
+        const AvgShape* sa = &m->shape[contacts[c].sa]; const AvgShape* sb = &m->shape[contacts[c].sb];
+        double force = contacts[c].lambda_n / dt;
+        int a_tool = sa->ref_body == AVG_REF_TOOL, b_tool = sb->ref_body == AVG_REF_TOOL;
+        int a_hum = sa->ref_body == AVG_REF_HUMAN, b_hum = sb->ref_body == AVG_REF_HUMAN;
+        int a_rob = sa->ref_body == AVG_REF_ROBOT, b_rob = sb->ref_body == AVG_REF_ROBOT;
+        if ((a_rob && b_hum) || (b_rob && a_hum)) robot_force_on_human += force;           /* feeding.py:86-87 */
+        if ((a_tool && b_hum) || (b_tool && a_hum)) tool_force_on_human += force;          /* :88-89 */
+    }
+    const v3 mouth = fd_mouth(m, &k);
+    v3 tool; quat tq; frame_pose(m, &k, AVG_F_TOOL_TIP, &tool, &tq);
+    /* particles */
+    double food_reward = 0, hit_reward = 0, mouth_vel_sum = 0;
+    part[AVG_P_EV_EAT] = part[AVG_P_EV_EAT + 1] = part[AVG_P_EV_SPILL] = part[AVG_P_EV_SPILL + 1] = part[AVG_P_EV_HIT] = part[AVG_P_EV_HIT + 1] = 0;
+    v3 top = V(0, 0, 0), bottom = V(0, 0, 0), cup_p = tool; quat cup_q = tq;
+    if (drinking) {                                           /* drinking.py:97-100: cup frame = base o ([0, 0.06, 0], rotX 90 deg) */
+        quat rx = qaxis(V(1, 0, 0), 1.5707963267948966);
+        cup_p = vadd(tool, qrot(tq, V(0, 0.06, 0))); cup_q = qnormalize(qmul(tq, rx));
+        top = vadd(cup_p, qrot(cup_q, V(0, 0, tf[AVG_TF_CUP_TOP])));
+        bottom = vadd(cup_p, qrot(cup_q, V(0, 0, tf[AVG_TF_CUP_BOTTOM])));
+    }
+    for (int p = 0; p < h->n_particle; ++p) {
+        if (!p_alive(part, p)) continue;
+        v3 x = V(P_X(part, p, 0), P_X(part, p, 1), P_X(part, p, 2));
+        if (drinking) {                                       /* util.points_in_cylinder(top, bottom, 0.05, x), util.py:107-110 */
+            v3 vec = vsub(bottom, top);
+            double cst = tf[AVG_TF_CUP_RADIUS] * vnorm(vec);
+            int inside = vdot(vsub(x, top), vec) >= 0 && vdot(vsub(x, bottom), vec) <= 0 && vnorm(vcross(vsub(x, top), vec)) <= cst;
+            if (inside) continue;
+        }
+        double dist = vnorm(vsub(mouth, x));
+        if (dist < tf[AVG_TF_EAT_RADIUS]) {                   /* feeding.py:102-110, drinking.py:114-122 */
+            food_reward += tf[AVG_TF_EAT_REWARD];
+            env[AVG_E_TASK_SUCCESS] += 1;
+            /* Feeding reads the velocity before the teleport; Drinking after resetBasePositionAndOrientation, which zeroes it
+             * (drinking.py:118-119) [UPSTREAM-BULLET] */
+            if (!drinking) mouth_vel_sum += vnorm(V(P_V(part, p, 0), P_V(part, p, 1), P_V(part, p, 2)));
+            p_clrbit(part, AVG_P_ALIVE, p); p_setbit(part, AVG_P_EV_EAT, p);
+            continue;
+        }
+        int spill = x.z < tf[AVG_TF_Z_MIN] || (!drinking && p_getbit(part, AVG_P_TOUCH_SPILL, p));   /* feeding.py:111, drinking.py:124 */
+        if (spill) {
+            food_reward += tf[AVG_TF_SPILL_REWARD];
+            p_clrbit(part, AVG_P_ALIVE, p); p_setbit(part, AVG_P_EV_SPILL, p);
+            continue;
+        }
+        if (p_getbit(part, AVG_P_TOUCH_HUMAN, p)) {
+            if (drinking) {                                   /* drinking.py:131-134: removed on the first touch */
+                hit_reward -= 1; p_clrbit(part, AVG_P_ALIVE, p); p_setbit(part, AVG_P_EV_HIT, p);
+            } else if (!p_getbit(part, AVG_P_HIT, p)) {       /* feeding.py:116-119: penalised once, stays in play */
+                hit_reward -= 1; p_setbit(part, AVG_P_HIT, p); p_setbit(part, AVG_P_EV_HIT, p);
+            }
+        }
+    }
+    int tb = m->frame[AVG_F_TOOL_TIP].body;
+    const double* tv = env + AVG_E_QD + m->body[tb].dof;
+    double ee_vel = vnorm(V(tv[0], tv[1], tv[2]));                                         /* getBaseVelocity(spoon)[0], feeding.py:59 */
+    fd_get_obs(m, env, tool_force_on_human, robot_force_on_human, obs);
+    /* human_preferences, env.py:412-448 with total_force_on_human = robot force, tool_force_at_target = tool force (feeding.py:63) */
+    double pref = tf[AVG_TF_C_V] * (-ee_vel) + tf[AVG_TF_C_F] * (-robot_force_on_human)
+                + tf[AVG_TF_C_HF] * (tool_force_on_human < tf[AVG_TF_FORCE_CAP] ? 0.0 : -tool_force_on_human)
+                + tf[AVG_TF_C_FD] * hit_reward + tf[AVG_TF_C_FDV] * (-mouth_vel_sum);
+    double reward_distance, reward_tilt = 0;
+    if (drinking) {
+        reward_distance = -vnorm(vsub(mouth, top));                                        /* drinking.py:68 */
+        double roll = quat_roll(cup_q);
+        reward_tilt = tf[AVG_TF_TILT_SIGN] > 0 ? -fabs(roll + 1.5707963267948966) : -fabs(roll - 1.5707963267948966);   /* :72 */
+    } else reward_distance = -vnorm(vsub(mouth, tool));                                    /* feeding.py:68 */
+    double reward_action = -raw_sq;
+    *reward = tf[AVG_TF_DISTANCE_W] * reward_distance + tf[AVG_TF_ACTION_W] * reward_action + tf[AVG_TF_TILT_W] * reward_tilt
+            + tf[AVG_TF_FOOD_W] * food_reward + pref;                                      /* feeding.py:71, drinking.py:74 */
+    env[AVG_E_EPISODE_RETURN] += *reward;
+    env[AVG_E_TARGET_POS] = mouth.x; env[AVG_E_TARGET_POS + 1] = mouth.y; env[AVG_E_TARGET_POS + 2] = mouth.z;
+    if (out_info) {
+        out_info[0] = robot_force_on_human + tool_force_on_human;
+        out_info[1] = env[AVG_E_TASK_SUCCESS] >= tf[AVG_TF_SUCCESS_THR] ? 1.0 : 0.0;
+        out_info[2] = robot_force_on_human; out_info[3] = tool_force_on_human; out_info[4] = reward_distance;
+        out_info[5] = reward_action; out_info[6] = food_reward + tf[AVG_TF_TILT_W] * reward_tilt; out_info[7] = pref;
+    }
+}
+
+/* `n` calls of p.stepSimulation() without actions or per-step hooks: the settle loop of reset() (feeding.py:318-320,
+ * drinking.py:320-322: "Drop food in the spoon"). */
+int avg_oracle_settle(const void* blob, double* env, double* part, int n) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Contact contacts[MAXC]; int nc = 0;
+    const int n_internal = m.h->n_internal > 0 ? m.h->n_internal : 1;
+    for (int s = 0; s < n * n_internal; ++s) substep(&m, env, part, contacts, &nc);
+    return 0;
+}
+/* particle contacts at the current state (no stepping): rows of 8 doubles (p, q, shape_b, n(3), dist, 0) */
+int avg_oracle_particle_collide(const void* blob, const double* env, const double* part, double* out, int* n_out) {
+    Model m; if (model_open(blob, &m)) return -1;
+    Kin k; fk(&m, env, &k);
+    PContact* pcs = (PContact*)malloc(sizeof(PContact) * AVG_MAX_PCONTACT);
+    int overflow = 0;
+    int n = particle_collide(&m, &k, part, pcs, &overflow);
+    for (int c = 0; c < n; ++c) {
+        double* o = out + 8 * c;
+        o[0] = pcs[c].p; o[1] = pcs[c].q; o[2] = pcs[c].shape_b; o[3] = pcs[c].n.x; o[4] = pcs[c].n.y; o[5] = pcs[c].n.z; o[6] = pcs[c].dist; o[7] = 0;
+    }
+    *n_out = n; free(pcs);
+    return overflow;
+}
+
 /* exported ---------------------------------------------------------------------------------------------------- */
 int avg_oracle_sizes(int* sizes) {
     sizes[0] = (int)sizeof(AvgModelHeader); sizes[1] = (int)sizeof(AvgBody); sizes[2] = (int)sizeof(AvgDof);
     sizes[3] = (int)sizeof(AvgShape); sizes[4] = (int)sizeof(AvgFrame); sizes[5] = (int)sizeof(AvgContact);
-    return 6;
+    sizes[6] = (int)sizeof(AvgResetTable);
+    return 7;
 }
 
 /* initial observation, scratch_itch.py:268  (_get_obs([0],[0,0]) after generate_target) */
 int avg_oracle_reset_obs(const void* blob, double* env, double* obs) {
     Model m; if (model_open(blob, &m)) return -1;
     if (m.h->task == AVG_TASK_BED_BATHING) { bb_get_obs(&m, env, 0, 0, 0, obs); return 0; }     /* bed_bathing.py:350 */
+    if (m.h->task == AVG_TASK_FEEDING || m.h->task == AVG_TASK_DRINKING) { fd_get_obs(&m, env, 0, 0, obs); return 0; }   /* feeding.py:325 */
     update_target(&m, env);
     get_obs(&m, env, 0, 0, 0, obs);
     return 0;
@@ -1111,9 +1499,21 @@ int avg_oracle_reset_obs(const void* blob, double* env, double* obs) {
  *           [4] reward_distance, [5] reward_action, [6] reward_force_scratch, [7] preferences_score
  * contacts_out: AvgContactD records of the last sub-step (10 doubles each + 2 ints packed as doubles):
  *           [sa, sb, pa(3), pb(3), n(3), dist, force] = 13 doubles */
+static void fd_finish_step(const Model* m, double* env, double* part, const Contact* contacts, int nc, double raw_sq, double* obs,
+                           double* reward, double* out_info);
+static void fd_get_obs(const Model* m, const double* env, double tool_force_on_human, double robot_force_on_human, double* obs);
+
+int avg_oracle_step_fd(const void* blob, double* env, double* part, const float* action, double* obs, double* reward, double* out_info,
+                       double* contacts_out, int* ncontacts_out);
 int avg_oracle_step(const void* blob, double* env, const float* action, double* obs, double* reward, double* out_info,
                     double* contacts_out, int* ncontacts_out) {
+    return avg_oracle_step_fd(blob, env, 0, action, obs, reward, out_info, contacts_out, ncontacts_out);
+}
+/* `part`: the particle record of Feeding / Drinking (AVG_P_STRIDE doubles, masks as numbers), NULL for the other tasks */
+int avg_oracle_step_fd(const void* blob, double* env, double* part, const float* action, double* obs, double* reward, double* out_info,
+                       double* contacts_out, int* ncontacts_out) {
     Model m; if (model_open(blob, &m)) return -1;
+    if (m.h->n_particle > 0 && !part) return -3;
     const AvgModelHeader* h = m.h;
     int na = h->n_action_robot + h->n_action_human;
     float act[64];
@@ -1139,7 +1539,7 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
             hpos[s] = env[AVG_E_Q + m.body[m.dof[i].body].qidx];
             hlo[s] = limit_lo(&m.dof[i], env); hhi[s] = limit_hi(&m.dof[i], env);
         }
-        if (h->human_control) for (int s = 0; s < 10; ++s) ah[s] = act[h->n_action_robot + s];
+        if (h->human_control) for (int s = 0; s < 10 && s < h->n_action_human; ++s) ah[s] = act[h->n_action_robot + s];
     }
     for (int f = 0; f < h->substeps; ++f) {
         for (int j = 0; j < nrob; ++j) {
@@ -1170,8 +1570,9 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
     }
     Contact contacts[MAXC]; int nc = 0;
     const double dt = h->dt;
+    const int n_internal = h->n_internal > 0 ? h->n_internal : 1;
     for (int f = 0; f < h->substeps; ++f) {                    /* env.py:341-349 */
-        substep(&m, env, contacts, &nc);
+        for (int i = 0; i < n_internal; ++i) substep(&m, env, part, contacts, &nc);     /* p.stepSimulation = numSubSteps internal steps */
         enforce_realistic_limits(&m, env);                     /* env.py:343-344, human_control only */
         enforce_hard_limits(&m, env);
         if (h->task == AVG_TASK_SCRATCH_ITCH) update_target(&m, env);
@@ -1179,6 +1580,10 @@ int avg_oracle_step(const void* blob, double* env, const float* action, double* 
     env[AVG_E_ITERATION] += 1;                                 /* env.py:351 */
     if (h->task == AVG_TASK_BED_BATHING) {
         bb_finish_step(&m, env, contacts, nc, raw_sq, obs, reward, out_info);
+        goto report_contacts;
+    }
+    if (h->task == AVG_TASK_FEEDING || h->task == AVG_TASK_DRINKING) {
+        fd_finish_step(&m, env, part, contacts, nc, raw_sq, obs, reward, out_info);
         goto report_contacts;
     }
 

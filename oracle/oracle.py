@@ -15,7 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libavg_oracle.so")
 ENV_STRIDE = 192
 INT_SLOTS = (123, 152, 161, 166, 167, 168)    # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
-UINT_SLOTS = (170, 171, 172, 173, 174)        # AVG_E_TARGET_MASK words (BedBathing)
+UINT_SLOTS = (170, 171, 172, 173, 174, 175)   # AVG_E_TARGET_MASK words (BedBathing), AVG_E_FROZEN
+P_STRIDE = 592                                # AVG_P_STRIDE (include/avg_model.h)
+P_UINT_SLOTS = tuple(range(576, 590))         # AVG_P_ALIVE .. AVG_P_EV_HIT mask words
+P_INT_SLOTS = (590, 591)                      # AVG_P_NCONTACT, overflow flags
+MAX_CONTACT = 32                              # AVG_MAX_CONTACT
 _DP = ctypes.POINTER(ctypes.c_double)
 _FP = ctypes.POINTER(ctypes.c_float)
 _IP = ctypes.POINTER(ctypes.c_int)
@@ -52,6 +56,23 @@ def env_to_f32(env_f64: np.ndarray) -> np.ndarray:
     return out
 
 
+def part_to_f64(part_f32: np.ndarray) -> np.ndarray:
+    """float32 device particle record (masks bit-cast) -> float64 oracle record (masks as numbers)."""
+    part_f32 = np.ascontiguousarray(part_f32, dtype=np.float32)
+    out = part_f32.astype(np.float64)
+    uv = part_f32.view(np.uint32); iv = part_f32.view(np.int32)
+    for s in P_UINT_SLOTS:
+        out[..., s] = uv[..., s]
+    for s in P_INT_SLOTS:
+        out[..., s] = iv[..., s]
+    return out
+
+
+def part_masks(part_f64: np.ndarray, slot: int) -> int:
+    """64-bit mask stored in two words at `slot` of a float64 particle record."""
+    return int(part_f64[slot]) | (int(part_f64[slot + 1]) << 32)
+
+
 class Oracle:
     def __init__(self, blob: bytes):
         self.lib = ctypes.CDLL(build())
@@ -73,6 +94,11 @@ class Oracle:
         L.avg_oracle_shape_pair.argtypes = [ctypes.c_void_p, ctypes.c_int, _DP, ctypes.c_int, _DP, ctypes.c_double, _DP]
         L.avg_oracle_sizes.argtypes = [_IP]
         L.avg_oracle_arm_limit.argtypes = [ctypes.c_void_p, _DP, _DP]
+        L.avg_oracle_step_fd.restype = ctypes.c_int
+        L.avg_oracle_step_fd.argtypes = [ctypes.c_void_p, _DP, _DP, _FP, _DP, _DP, _DP, _DP, _IP]
+        L.avg_oracle_settle.argtypes = [ctypes.c_void_p, _DP, _DP, ctypes.c_int]
+        L.avg_oracle_particle_collide.argtypes = [ctypes.c_void_p, _DP, _DP, _DP, _IP]
+        self.n_particle = int(h["n_particle"])
 
     def sizes(self):
         a = (ctypes.c_int * 8)()
@@ -88,19 +114,32 @@ class Oracle:
         assert self.lib.avg_oracle_reset_obs(self.blob, self._dp(env), self._dp(obs)) == 0
         return obs
 
-    def step(self, env: np.ndarray, action: np.ndarray):
-        """env: float64 [ENV_STRIDE] (modified in place). -> obs, reward, info[8], contacts[n,13]"""
+    def step(self, env: np.ndarray, action: np.ndarray, part: np.ndarray | None = None):
+        """env: float64 [ENV_STRIDE] (modified in place); part: float64 [P_STRIDE] particle record of Feeding / Drinking
+        (modified in place). -> obs, reward, info[8], contacts[n,13]"""
         assert env.dtype == np.float64 and env.flags.c_contiguous
         act = np.ascontiguousarray(action, dtype=np.float32)
         obs = np.zeros(self.n_obs)
         rew = np.zeros(1)
         info = np.zeros(8)
-        cont = np.zeros((12, 13))
+        cont = np.zeros((MAX_CONTACT, 13))
         nc = ctypes.c_int(0)
-        rc = self.lib.avg_oracle_step(self.blob, self._dp(env), act.ctypes.data_as(_FP), self._dp(obs), self._dp(rew),
-                                      self._dp(info), self._dp(cont), ctypes.byref(nc))
-        assert rc == 0
+        if part is not None:
+            assert part.dtype == np.float64 and part.flags.c_contiguous and part.shape == (P_STRIDE,)
+        rc = self.lib.avg_oracle_step_fd(self.blob, self._dp(env), self._dp(part) if part is not None else None,
+                                         act.ctypes.data_as(_FP), self._dp(obs), self._dp(rew),
+                                         self._dp(info), self._dp(cont), ctypes.byref(nc))
+        assert rc == 0, rc
         return obs, float(rew[0]), info, cont[:nc.value].copy()
+
+    def settle(self, env: np.ndarray, part: np.ndarray | None, n: int):
+        """n x p.stepSimulation() without actions (the reset() settle loop, feeding.py:318-320)."""
+        assert self.lib.avg_oracle_settle(self.blob, self._dp(env), self._dp(part) if part is not None else None, int(n)) == 0
+
+    def particle_collide(self, env: np.ndarray, part: np.ndarray):
+        out = np.zeros((320, 8)); n = ctypes.c_int(0)
+        self.lib.avg_oracle_particle_collide(self.blob, self._dp(env), self._dp(part), self._dp(out), ctypes.byref(n))
+        return out[:n.value].copy()
 
     def frame(self, env, f):
         out = np.zeros(7)
@@ -119,7 +158,7 @@ class Oracle:
         return qdd[:self.n_dof], minv
 
     def collide(self, env):
-        cont = np.zeros((12, 13))
+        cont = np.zeros((MAX_CONTACT, 13))
         nc = ctypes.c_int(0)
         self.lib.avg_oracle_collide(self.blob, self._dp(env), self._dp(cont), ctypes.byref(nc))
         return cont[:nc.value].copy()

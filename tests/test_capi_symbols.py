@@ -61,5 +61,6 @@ def test_struct_sizes_agree_between_c_and_numpy(oracles):
     from assistive_vr_gym_b200.compiler import blob
     from assistive_vr_gym_b200.capi import CONTACT_DT
     sizes = oracles[0].sizes()
+    from assistive_vr_gym_b200.compiler.reset import RESET_TABLE_DT
     assert sizes == [blob.HEADER_DT.itemsize, blob.BODY_DT.itemsize, blob.DOF_DT.itemsize, blob.SHAPE_DT.itemsize,
-                     blob.FRAME_DT.itemsize, CONTACT_DT.itemsize]
+                     blob.FRAME_DT.itemsize, CONTACT_DT.itemsize, RESET_TABLE_DT.itemsize]

@@ -125,6 +125,48 @@ def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int
     print("wrote", name + ".npz,", name + "Human.npz")
 
 
+def compile_feeding_drinking(assets: str, out_dir: str, task: str, robot: str, n_base: int, attempts: int, pool: int):
+    """Feeding<Robot>[Human]-v0 / Drinking<Robot>[Human]-v0 (feeding.py:144-331, drinking.py:159-335).  Jaco: fixed base, one
+    variant per gender.  PR2 (feeding.py:266-270) and the build-defined Sawyer / Baxter ids: per gender `n_base` base poses from
+    the task-oriented-configuration search with the start target and the mouth as goals, one variant each."""
+    from assistive_vr_gym_b200.compiler.scene_fd import build_feeding_drinking, ROBOT_FD, start_target
+    from assistive_vr_gym_b200.compiler.reset_fd import build_reset_data_fd
+    rng = np.random.RandomState(1001)
+    rec = ROBOT_FD[(task, robot)]
+    name = {"feeding": "Feeding", "drinking": "Drinking"}[task] + {"jaco": "Jaco", "pr2": "PR2", "sawyer": "Sawyer", "baxter": "Baxter"}[robot]
+    payloads = {False: {}, True: {}}
+    v = 0
+    for gender in ("male", "female"):
+        bases = [(0.0, 0.0, 0.0)]
+        if rec["toc"] is not None:
+            probe = build_feeding_drinking(assets, task, robot, gender)
+            hp, hq = probe.multibodies[1].com_frames(probe.q_human_reset)[27]
+            mouth = hp + X.quat_rotate(hq, np.asarray(probe.header["task_f"][19:22], float))     # feeding.py:253-256
+            robot_mb, rs = load_robot(assets, robot, arm="right")
+            centre, quat = start_target(task, robot)
+            bases = []
+            for k in range(n_base):
+                sp = centre + rng.uniform(-0.05, 0.05, size=3)
+                xy, yaw, q_start, reached = toc_search(robot_mb, rs["arm"], sp, quat, [mouth, mouth], rng, rec["toc"], attempts=attempts,
+                                                       random_position=0.5, ee_link=rs["ee_link"])
+                bases.append((float(xy[0]), float(xy[1]), float(yaw)))
+                print(name, gender, "base", k, np.round(xy, 3), "yaw", round(float(yaw), 3), "goals reached", reached)
+        for base in bases:
+            for human_control in (False, True):
+                scene = build_feeding_drinking(assets, task, robot, gender, human_control=human_control, base_xy_yaw=base)
+                blob = scene_to_blob(scene)
+                payloads[human_control][f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+                rd = build_reset_data_fd(scene, np.random.RandomState(1001 + v), ik_pool=pool)
+                for key, a in rd.items():
+                    payloads[human_control][f"reset_{v}_{key}"] = a
+                print(name, gender, "human_control" if human_control else "", scene.info["n_body"], "bodies", scene.info["n_dof"], "dof",
+                      scene.info["n_mshape"], "moving shapes", scene.info["n_cshape"], "compound children", scene.info["n_pairs"], "pairs", len(blob), "bytes")
+            v += 1
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **payloads[False])
+    np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
+    print("wrote", name + ".npz,", name + "Human.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--assets", default="/root/reference/assistive_gym/envs/assets")
@@ -132,6 +174,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="", help="scratch_itch | bed_bathing | pr2 | scratch_itch_pr2 | bed_bathing_pr2 (default: all)")
     ap.add_argument("--bases", type=int, default=8, help="BedBathing: robot base poses (model variants) per gender")
     ap.add_argument("--attempts", type=int, default=100, help="BedBathing: base poses tried per TOC search (env.py:486)")
+    ap.add_argument("--fd-bases", type=int, default=4, help="Feeding / Drinking on PR2 / Sawyer / Baxter: robot base poses (model variants) per gender")
     args = ap.parse_args()
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data")
     os.makedirs(out_dir, exist_ok=True)
@@ -141,6 +184,10 @@ if __name__ == "__main__":
         compile_pr2(args.assets, out_dir, "scratch_itch", args.bases, args.attempts, min(args.pool, 16))
     if args.only in ("", "pr2", "bed_bathing_pr2"):
         compile_pr2(args.assets, out_dir, "bed_bathing", args.bases, args.attempts, 1)
+    for task in ("feeding", "drinking"):
+        for robot in ("jaco", "pr2", "sawyer", "baxter"):
+            if args.only in ("", "fd", task, f"{task}_{robot}"):
+                compile_feeding_drinking(args.assets, out_dir, task, robot, args.fd_bases, args.attempts, min(args.pool, 8))
     for human_control in ((False, True) if args.only in ("", "scratch_itch") else ()):
         payload = {}
         rng = np.random.RandomState(1001)              # env.py:53 default seed
