@@ -197,7 +197,7 @@ int avg_upload_model(AvgHandle* h, int variant, const void* blob, size_t nbytes)
         AVG_CHECK(h, cudaMalloc(&h->d_pscratch, sizeof(float) * AVG_PS_STRIDE * (size_t)h->n_env));
         AVG_CHECK(h, cudaMemset(h->d_part, 0, sizeof(float) * AVG_P_STRIDE * (size_t)h->n_env));
         AVG_CHECK(h, cudaMemset(h->d_pscratch, 0, sizeof(float) * AVG_PS_STRIDE * (size_t)h->n_env));
-        const long long cap = (long long)h->n_env * (12 + 6 * mh->n_particle) + 4096;
+        const long long cap = (long long)h->n_env * (16 + 12 * mh->n_particle) + 4096;     /* worst case 16 candidates per particle; typical 3-5 */
         h->np_capacity = cap > 0x3fffffff ? 0x3fffffff : (int)cap;
         for (int k = 0; k < 4; ++k) {
             cudaFree(h->d_npq[k]); h->d_npq[k] = nullptr;

@@ -137,7 +137,8 @@ def test_oracle_food_rewards():
     obs, rew0, info0, _ = o.step(env, a, part)                                  # a quiet step: no events
     assert part_masks(part, P_ALIVE) == 0xff and info0[6] == 0.0
     mouth = env[E_TARGET_POS:E_TARGET_POS + 3].copy()
-    _set_particle(part, 2, mouth, v=(0.0, 0.0, 0.5396))                         # thrown up so that it is back at the mouth after 10 x 0.01 s of gravity
+    head = o.frame(env, F_HEAD)
+    _set_particle(part, 2, mouth + 0.014 * quat_rot(head[3:], [0, -1, 0]), v=(0.0, 0.0, 0.5396))   # just in front of the lips, thrown up so that it is back there after 10 x 0.01 s of gravity
     _set_particle(part, 5, np.array([0.3, -0.3, 0.45]))                         # below z = 0.5
     success0 = env[E_TASK_SUCCESS]
     obs, rew, info, _ = o.step(env, a, part)
@@ -186,7 +187,8 @@ def test_oracle_water_rewards_and_cylinder():
     inside = ((x - top) @ vec >= 0) & ((x - bottom) @ vec <= 0) & (np.linalg.norm(np.cross(x - top, vec), axis=1) <= 0.05 * np.linalg.norm(vec))
     assert inside.all()
     mouth = env[E_TARGET_POS:E_TARGET_POS + 3].copy()
-    _set_particle(part, 40, mouth, v=(0.0, 0.0, 0.5396))                        # back at the mouth after 10 x 0.01 s of gravity
+    head = o.frame(env, F_HEAD)
+    _set_particle(part, 40, mouth + 0.014 * quat_rot(head[3:], [0, -1, 0]), v=(0.0, 0.0, 0.5396))  # in front of the lips, back there after 10 x 0.01 s of gravity
     _set_particle(part, 41, np.array([0.4, -0.4, 0.3]))
     s0 = env[E_TASK_SUCCESS]
     obs, rew, info, _ = o.step(env, a, part)
@@ -288,7 +290,8 @@ def test_gpu_particle_events_bit_exact(env_id):
     env.step(torch.as_tensor(a, device="cuda:0"))                                              # publishes the mouth position
     state = env.get_state(); part = env.get_particles()
     for e in range(n):
-        mouth = state[e, E_TARGET_POS:E_TARGET_POS + 3]
+        head = oracles[int(env.variants[e])].frame(env_to_f64(state[e]), F_HEAD)
+        mouth = state[e, E_TARGET_POS:E_TARGET_POS + 3] + (0.014 * quat_rot(head[3:], [0, -1, 0])).astype(np.float32)   # just in front of the lips
         for p, x, vz in ((1, mouth, 0.5396), (3, np.array([0.5, 0.5, 0.2], dtype=np.float32), 0.0),     # back at the mouth after the step / on the floor
                          (6, np.array([0.1, -0.05, 0.62 + 0.08], dtype=np.float32), 0.0)):          # above the right thigh: falls onto the lap
             for c in range(3):
@@ -368,5 +371,6 @@ def test_gpu_episode_invariants(env_id, n):
     st = env.get_state()
     assert np.isfinite(st[:, :64]).all()
     assert np.array_equal(st[:, E_TASK_SUCCESS].astype(np.int64), eaten)
-    assert np.array_equal(st[0], st[1]) and np.array_equal(env.get_particles()[0], env.get_particles()[1])
+    pf = env.get_particles().view(np.uint32)                                   # bit patterns: mask words are not numbers
+    assert np.array_equal(st.view(np.uint32)[0], st.view(np.uint32)[1]) and np.array_equal(pf[0], pf[1])
     env.close()

@@ -363,8 +363,8 @@ def test_gpu_pr2_device_reset_and_episode_invariants(torch_cuda, env_id):
     from assistive_vr_gym_b200.envs import load_env_data, REGISTRY
     from assistive_vr_gym_b200.compiler.reset import sample_states_hashed
     n = 4096
-    env = _env(env_id, n)
-    env.sim.enable_debug(False)
+    from assistive_vr_gym_b200 import make
+    env = make(env_id, num_envs=n, device=0, seed=7, device_ik=False)     # the mirror draws start poses from the pool
     env.reset_device(seed=77)
     torch.cuda.synchronize()
     st = env.get_state()
