@@ -4,7 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
 
 A "step" is one env.step() of every environment of the batch (take_step + 5 physics sub-steps + reward/obs), with
-synthetic uniform random actions (seed 0) and random-reset initial states (seed 1001).  `value` is measured with the
+synthetic uniform random actions (seed 0).  The batch is at STAGGERED EPISODE PHASES: before the timed region it is rolled
+forward (untimed) with one tenth of the environments restarted every 20 steps, so that the K timed steps see episode steps
+0..199 uniformly -- the mean of whole 200-step random-action episodes, which is also what the reference arm runs (steps right
+after a reset have fewer contacts and would flatter the simulator; that window is reported as `post_reset_window`).
+`value` is measured with the
 state, actions and outputs resident in HBM (CUDA events on the launch stream, max over ranks); `e2e` is the same
 metric through the reference-facing host-buffer call (avg_step_host: NumPy actions in, NumPy obs/reward/done/info out,
 host<->device copies inside the timed region).  Environments are sharded over ranks with no data-path collective
@@ -40,6 +44,18 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash() -> str:
+    """sha256/16 of the kernel sources: profiles/traffic.json records the hash it was captured at; a stale capture is not
+    reported as this build's traffic."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("assistive_vr_gym_b200/csrc/avg_kernels.cu", "assistive_vr_gym_b200/csrc/avg_kernels.h", "assistive_vr_gym_b200/csrc/avg_math.cuh",
+              "assistive_vr_gym_b200/csrc/avg_capi.cu", "include/avg_model.h"):
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -119,26 +135,31 @@ def cpu_oracle_throughput(envs_per_core: int, steps: int, cores: int | None = No
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference arm: the CPU restatement of the path (kind "port": PyBullet is not installable here) on every host core.
+    One bench "step" = one bounded sample: 16 whole 200-step random-action episodes per core (about a second), so that the
+    K timed repetitions it reports as `steps` are the ones it ran and K x ms_per_step is the run's wall time."""
     if rank != 0:
         return
-    # bounded sample: ~steps*envs sized so that each measured step lasts a few seconds in total
+    import ctypes
+    from oracle.oracle import build as build_oracle
+    ctypes.CDLL(build_oracle())                  # mapped in this process too (the workers are forked from it)
     cores = os.cpu_count() or 1
-    per_core, steps = 64, 200                      # one bench "step" = 64 full 200-step episodes per core (a few seconds)
-    vals = []
-    for _ in range(min(args.warmup, 1)):
+    per_core, ep_steps = 16, 200
+    for _ in range(max(args.warmup, 1)):
         cpu_oracle_throughput(1, 20, cores)
-    reps = max(1, min(args.steps, 5))
+    vals = []
     t0 = time.perf_counter()
-    for _ in range(reps):
-        v, c, sample = cpu_oracle_throughput(per_core, steps, cores)
+    for _ in range(args.steps):
+        v, c, sample = cpu_oracle_throughput(per_core, ep_steps, cores)
         vals.append(v)
-    ms_per = (time.perf_counter() - t0) * 1e3 / reps
+    ms_per = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
     value = float(np.median(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{ENV_ID}, random actions, CPU oracle port of the path (PyBullet itself is not installable here)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f", median of {reps}"},
+            "config": {"workload": f"{ENV_ID}, whole 200-step random-action episodes, CPU oracle port of the path (PyBullet itself is not installable here)",
+                       "step": f"one step = {cores} processes x {per_core} episodes x {ep_steps} env-steps"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f", median of {args.steps}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
@@ -195,8 +216,11 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
+    from assistive_vr_gym_b200.sharding import make_shard, reduce_episode_stats, reduce_max
     E = args.envs_per_gpu
-    env = make(ENV_ID, num_envs=E, device=local_rank, seed=1001 + rank)
+    # weak scaling: every rank owns E environments of the global batch [rank * E, (rank + 1) * E) (sharding.make_shard)
+    env = make_shard(ENV_ID, E * world, rank, world, device=local_rank, seed=1001)
+    assert env.num_envs == E
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     # fresh i.i.d. actions for every step (reference examples/random_actions.py samples anew each step; a short ring
@@ -213,9 +237,30 @@ def main():
         torch.cuda.synchronize(dev)
 
     W = max(args.warmup, 3)
+    # ---- post-reset window (extra): the K steps right after a reset, few contacts yet -----------------------------
     for w in range(W):
         env.step(ring[w % len(ring)])
     env.elapsed = 0
+    barrier()
+    q0 = torch.cuda.Event(enable_timing=True); q1 = torch.cuda.Event(enable_timing=True)
+    q0.record(stream)
+    for k in range(args.steps):
+        env.step(ring[(W + k) % len(ring)]); env.elapsed = 0
+    q1.record(stream)
+    barrier()
+    post_reset_ms = reduce_max(torch.tensor([q0.elapsed_time(q1)], device=dev))
+    # ---- staggered episode phases: group g (a tenth of the batch) restarts at step 20 g of a 200-step untimed roll, so the
+    #      timed window holds environments at episode steps 0..199 in equal shares (the whole-episode mean) --------------
+    env.reset()
+    groups = 10
+    gid = torch.arange(E, device=dev) % groups
+    for k in range(200 - W):
+        if k % 20 == 0 and k > 0:
+            env.reset_device(mask=(gid == (k // 20)))
+        act_ep.uniform_(-1, 1, generator=gen)
+        env.step(act_ep); env.elapsed = 0
+    for w in range(W):
+        env.step(ring[w % len(ring)]); env.elapsed = 0
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
     launches0 = env.sim.launch_count
@@ -232,24 +277,21 @@ def main():
     sampler.stop_flag = True; sampler.join(timeout=2)
     # episode statistics: the only collective of the path (NCCL all-reduce of a 4-float vector)
     stats[0] = rew.sum(); stats[1] = info["task_success"].sum(); stats[2] = info["total_force_on_human"].sum(); stats[3] = float(E)
-    t = torch.tensor([ms], device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    ms = float(t.item())
+    overflow_envs = float((info["contact_overflow"] != 0).sum())
+    ms = reduce_max(torch.tensor([ms], device=dev))
+    reduce_episode_stats(stats)
     value = E * world * args.steps / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer API: the same steps of the episode as the device-resident measurement
     #      (fresh reset with the same seed, W warm-up steps, then the timed steps), so the two numbers differ only by the
-    #      host<->device traffic.  Actions sit in page-locked arrays (a caller writes its policy output there); results
+    #      host<->device traffic (same staggered batch, a few steps later).  Actions sit in page-locked arrays (a caller writes its policy output there); results
     #      come back in the env's own pinned arrays.
     from assistive_vr_gym_b200 import capi
     e2e_steps = max(3, min(args.steps, 20))
     a_pin = [capi.PinnedArray((E, 7), np.float32) for _ in range(min(W + e2e_steps, 32))]
     for i, p in enumerate(a_pin):
         p.array[...] = ring[i % len(ring)].cpu().numpy()
-    env.seed(1001 + rank); env.reset()
-    for w in range(W):
+    for w in range(W):                               # continues on the staggered batch of the device-resident measurement
         env.step_host(a_pin[w % len(a_pin)].array); env.elapsed = 0
     barrier()
     t0 = time.perf_counter()
@@ -257,10 +299,7 @@ def main():
         o, r, d, i = env.step_host(a_pin[(W + k) % len(a_pin)].array); env.elapsed = 0
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    te = torch.tensor([e2e_ms], device=dev)
-    if distributed:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = E * world * e2e_steps / (float(te.item()) * 1e-3)
+    e2e_value = E * world * e2e_steps / (reduce_max(torch.tensor([e2e_ms], device=dev)) * 1e-3)
     h2d = E * 7 * 4
     d2h = E * (env.sim.n_obs * 4 + 4 + 8 + 1)
 
@@ -366,12 +405,44 @@ def main():
                         "note": "synthetic-policy rollout (%d-64-64-7 tanh actor, fused inference), full episode from a device reset" % benv.obs_robot_len})
             benv.close()
 
+    # ---- BASELINE.json configs[1] (FeedingSawyer-v0, 4096 envs on one B200, random actions) and configs[3] (DrinkingBaxter-v0,
+    #      4096 envs per GPU, env-sharded: under torchrun every rank owns 4096): whole episodes (Feeding) / the first 50 steps
+    #      (Drinking: 64 water particles, ~250 particle contacts per internal step) from a device reset.  Both ids are
+    #      build-defined (the reference's task files have no Sawyer / Baxter branch) ----------------------------
+    if not args.no_episode:
+        for fid, nb, nst in (("FeedingSawyer-v0", 4096, 200), ("FeedingJaco-v0", 4096, 200), ("DrinkingBaxter-v0", 4096, 50), ("DrinkingJaco-v0", 4096, 50)):
+            fenv = make_shard(fid, nb * world, rank, world, device=local_rank, seed=1001)
+            fenv.reset()
+            fa = torch.empty((nb, fenv.sim.n_actions), device=dev)
+            for k in range(3):
+                fa.uniform_(-1, 1, generator=gen); fenv.step(fa); fenv.elapsed = 0
+            fenv.reset()
+            barrier()
+            f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for k in range(nst):
+                fa.uniform_(-1, 1, generator=gen); fo, fr, fd_, fi = fenv.step(fa); fenv.elapsed = 0
+            f1.record(stream)
+            barrier()
+            tf_ = reduce_max(torch.tensor([f0.elapsed_time(f1)], device=dev))
+            fstat = torch.stack([fi["task_success"].float().sum(), fr.sum(), (fi["contact_overflow"] != 0).float().sum(), torch.tensor(float(nb), device=dev)])
+            reduce_episode_stats(fstat)
+            bed.append({"env_id": fid, "envs_per_gpu": nb, "value": nb * world * nst / (tf_ * 1e-3), "unit": UNIT, "steps": nst,
+                        "task_success_rate": float(fstat[0] / fstat[3]), "mean_reward_last_step": float(fstat[1] / fstat[3]),
+                        "envs_with_contact_overflow": int(fstat[2]),
+                        "note": "random actions, 5 frames x 2 internal steps x 10 PGS iterations per env-step, %d particles, from a device reset "
+                                "(fresh IK start pose + 100 settle steps per episode)" % fenv.sim.n_particles})
+            fenv.close()
+
     # ---- mixed-task batch (extra; BASELINE.json configs[3] "mixed-task batch (all robots)"): one homogeneous sub-batch per
-    #      registered id, each its own handle, stepped concurrently on separate streams (assistive_vr_gym_b200/mixed.py) ----
+    #      (task, robot) id, each its own handle, stepped concurrently on separate streams (assistive_vr_gym_b200/mixed.py) ----
     if not args.no_episode:
         from assistive_vr_gym_b200.mixed import MixedBatch
-        per_id = 8192
-        mb = MixedBatch(envs_per_id=per_id, device=local_rank, seed=1001 + 100 * rank)
+        per_id = 2048
+        mixed_ids = [t + r + "-v0" for t, robots in (("ScratchItch", ("Jaco", "PR2")), ("BedBathing", ("Jaco", "PR2")),
+                                                     ("Feeding", ("Jaco", "PR2", "Sawyer", "Baxter")), ("Drinking", ("Jaco", "PR2", "Sawyer", "Baxter")))
+                     for r in robots]
+        mb = MixedBatch(env_ids=mixed_ids, envs_per_id=per_id, device=local_rank, seed=1001 + 100 * rank)
         mb.reset_device(seed=1001 + rank)
         for k in range(3):
             mb.step(mb.sample_actions(gen))
@@ -386,9 +457,7 @@ def main():
                 e_.elapsed = 0
         m1.record(stream)
         barrier()
-        tm = torch.tensor([m0.elapsed_time(m1)], device=dev)
-        if distributed:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        tm = torch.tensor([reduce_max(torch.tensor([m0.elapsed_time(m1)], device=dev))])
         bed.append({"env_id": "mixed: " + ", ".join(mb.env_ids), "envs_per_gpu": mb.num_envs, "value": mb.num_envs * world * 50 / (float(tm.item()) * 1e-3),
                     "unit": UNIT, "steps": 50, "note": "%d ids x %d envs, one handle and one stream per id, random actions, steps 3-52 after a device reset" % (len(mb.env_ids), per_id)})
         mb.close()
@@ -435,25 +504,37 @@ def main():
         # one "launch" of the path = the kernel sequence of one env-step (prologue, 5 x {collide, narrowphase, dynamics,
         # solve}, epilogue); its algorithmic bytes are per env-step, its duration the step time
         achieved = bpe * E / (ms / args.steps * 1e-3) / 1e9
-        traffic = None; prof = {}
+        traffic = None; prof = {}; traffic_note = "no committed ncu capture"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 prof = json.load(open(tp))
-                traffic = prof.get("dram_bytes_per_step_per_env", None)
-                traffic = traffic * E if traffic is not None else None
+                if prof.get("kernel_hash") != kernel_source_hash():
+                    # a capture of other kernels says nothing about this build: refuse it
+                    traffic_note = "profiles/traffic.json was captured at kernel hash %s, this build is %s: not reported" % (prof.get("kernel_hash"), kernel_source_hash())
+                    prof = {}
+                else:
+                    traffic = prof.get("dram_bytes_per_step_per_env", None)
+                    traffic = traffic * E if traffic is not None else None
+                    traffic_note = "ncu dram__bytes of the step's kernels (%s, %d envs) x this batch" % (prof.get("source"), prof.get("n_env", 0))
             except Exception:
-                traffic = None
+                traffic = None; prof = {}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{ENV_ID}, {E} envs/GPU, uniform random actions (seed 0), random-reset states (seed 1001), "
+                "config": {"workload": f"{ENV_ID}, {E} envs/GPU, uniform random actions (seed 0), staggered episode phases (a tenth of the batch "
+                                       f"restarted every 20 steps: the timed steps cover episode steps 0..199 uniformly = whole-episode mean), "
                                        f"5 sub-steps x 50 PGS iterations per env-step",
+                           "reset": "device sampler: every episode draws its own start target and solves the IK on the GPU (util.py:34-57 incl. the "
+                                    "5-step self-contact test)",
                            "envs_per_gpu": E, "l2": "state + I/O per GPU = %.0f MB > 126 MB L2 (inputs larger than L2)" % ((E * (768 + 37 * 4 + 13)) / 1e6),
                            "parallelism": f"env-sharded x{world}, no step-path collective"},
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "post_reset_window": {"value": E * world * args.steps / (post_reset_ms * 1e-3), "unit": UNIT, "steps": args.steps,
+                                      "note": "the same K steps taken right after a reset (few contacts yet): NOT the headline"},
+                "envs_with_contact_overflow": int(overflow_envs),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                              "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (22 kernels x 2 half-batches on 2 streams)" % (launches // max(1, args.steps)),
                              "issue_slots": (lambda s: None if not s else dict(s, achieved_warp_inst_per_s=s["warp_inst_per_env_step"] * value / world,
                                                                                   frac=s["warp_inst_per_env_step"] * value / world / s["peak_warp_inst_per_s"]))(prof.get("issue_slots")),
@@ -477,7 +558,7 @@ def main():
         if bed is not None:
             line["other_workloads"] = bed
         if not args.no_cpu_baseline and world == 1:
-            v, c, sample = cpu_oracle_throughput(192, 200)         # ~10-20 s of CPU work on the box's cores
+            v, c, sample = cpu_oracle_throughput(192, 200)         # ~10-20 s of CPU work on the box's cores: whole 200-step episodes
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample}
         _emit(line)
     if distributed:

@@ -44,7 +44,10 @@ print(f"one env-step (per-kernel means x launches per step): {step_inst/n_env:.0
 tot_inst, tot_dram, n_steps, tot = step_inst, step_dram, 1.0, step_time
 print(f"per env-step: {tot_inst/n_steps/n_env:.0f} warp instructions, {tot_dram/n_steps/n_env:.0f} DRAM bytes (read+write), serialised kernel time {tot/n_steps/1e6:.3f} ms")
 if len(sys.argv) > 4:
-    json.dump({"source": sys.argv[1], "n_env": n_env, "dram_bytes_per_step_per_env": tot_dram / n_steps / n_env,
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import kernel_source_hash
+    json.dump({"source": sys.argv[1], "n_env": n_env, "kernel_hash": kernel_source_hash(), "dram_bytes_per_step_per_env": tot_dram / n_steps / n_env,
                "warp_inst_per_env_step": tot_inst / n_steps / n_env,
                "issue_slots": {"warp_inst_per_env_step": tot_inst / n_steps / n_env, "peak_warp_inst_per_s": 148 * 4 * 1.965e9,
                                "note": "issue-slot roof = 148 SMs x 4 schedulers x 1.965 GHz; frac = env-steps/s x warp_inst_per_env_step / peak"}},
