@@ -36,17 +36,26 @@
 #include "avg_math.cuh"
 #include "avg_kernels.h"
 
+#ifndef AVG_WPB_COLLIDE
+#define AVG_WPB_COLLIDE 4         /* warps (= environments) per block of the collide kernel */
+#endif
+#ifndef AVG_WPB_DYN
+#define AVG_WPB_DYN 4             /* warps per block of the dynamics kernel */
+#endif
 #ifndef AVG_OCC_COLLIDE
-#define AVG_OCC_COLLIDE 5
+#define AVG_OCC_COLLIDE (20 / AVG_WPB_COLLIDE)
 #endif
 #ifndef AVG_OCC_DYN
-#define AVG_OCC_DYN 6
+#define AVG_OCC_DYN (24 / AVG_WPB_DYN)
 #endif
 #ifndef AVG_OCC_SOLVE
 #define AVG_OCC_SOLVE 32
 #endif
 #ifndef AVG_REDUX
 #define AVG_REDUX 2               /* solver: J.dv of dense rows by an integer redux.sync (1: fixed point 2^-22 m/s, 2: scaled to the largest product) instead of a 5-stage float butterfly (0) */
+#endif
+#ifndef AVG_LIM_SKIP
+#define AVG_LIM_SKIP 1            /* solver: sweep only the block slots in which some articulation has an active limit row */
 #endif
 #ifndef AVG_WELD_BATCH
 #define AVG_WELD_BATCH 1          /* dynamics kernel: the six weld rows built together with one packed reduction (0: row by row) */
@@ -1043,13 +1052,13 @@ avg_prologue_kernel(AvgStepArgs a) {
 // =================================================================================================================
 // forward kinematics + collision -> contact list in the scratch arena
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_COLLIDE)
+__global__ void __launch_bounds__(32 * AVG_WPB_COLLIDE, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     AVG_MASK_CHECK
     s.q[lane] = grec[AVG_E_Q + lane];
     {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (3)
-        const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
+        const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_WPB_COLLIDE * AVG_PF_PCT / 100;
         if (ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
             const float* p = lane < 1 ? r2 : (lane < 2 ? s2 : (lane < 5 ? s2 + AVG_S_SEP + 4 * AVG_S_NSEPMAX * (lane - 2) : nullptr));   // first 8 certificates of each of the 3 planes
@@ -1237,7 +1246,7 @@ __device__ __forceinline__ float dense_dot(float j, float dv) {
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
 template <int MAXBLK>
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK, AVG_OCC_DYN)
+__global__ void __launch_bounds__(32 * AVG_WPB_DYN, AVG_OCC_DYN)
 avg_dynamics_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmDyn)
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
@@ -1247,7 +1256,7 @@ avg_dynamics_kernel(AvgStepArgs a) {
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
     {   // what this kernel reads first, for the environment whose warp takes this slot next: record (4 lines), counters (1),
         // body poses (6), narrowphase results (4)
-        const int ea = e + 148 * AVG_OCC_DYN * AVG_K_WARPS_PER_BLOCK * AVG_PF_PCT / 100;
+        const int ea = e + 148 * AVG_OCC_DYN * AVG_WPB_DYN * AVG_PF_PCT / 100;
         if (ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
             const float* p = lane < 4 ? r2 + 32 * lane : (lane < 5 ? s2 : (lane < 11 ? s2 + AVG_S_POSE + 32 * (lane - 5) : (lane < 15 ? s2 + AVG_S_NPRES + 32 * (lane - 11) : nullptr)));   // 24 bodies, 8 results: what is usually there
@@ -2069,6 +2078,13 @@ avg_solve_kernel(AvgStepArgs a) {
     }
     const float4* umg = s.um[grp]; const float4* ulg = s.ul[grp];
     const int lt = lane - bs;
+    // block slots that hold a limit row in ANY articulation: the sweep skips the others (a uniform branch per slot)
+    unsigned limslots = 0;
+#if AVG_LIM_SKIP
+    if (nlim) limslots = __reduce_or_sync(AVG_FULL, (lane < nj && s.ul[grp][lt].y != 0.0f) ? 1u << lt : 0u);
+#else
+    limslots = 0xffffffffu;
+#endif
     float mcol[MAXBLK];
 #pragma unroll
     for (int t = 0; t < MAXBLK; ++t) mcol[t] = scr[AVG_S_MINV + t * 32 + lane];
@@ -2114,6 +2130,7 @@ avg_solve_kernel(AvgStepArgs a) {
         if (nlim) {
 #pragma unroll
             for (int t = 0; t < MAXBLK; ++t) {
+                if (!((limslots >> t) & 1u)) continue;
                 const float4 ra = ulg[t];
                 const float sg = ra.w;
                 const float jdv = sg * __shfl_sync(AVG_FULL, dv, bs + t);
@@ -3476,7 +3493,7 @@ int avg_kernels_per_step(int substeps, int n_internal, int particles) { return 2
 
 // warps (= environments) per block, per kernel.  The solver uses one warp per block: its iteration count varies per
 // environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
-constexpr int kWpbCollide = 4, kWpbDyn = 4, kWpbSolve = 1, kWpbEpi = 4, kWpbPro = 4;
+constexpr int kWpbCollide = AVG_WPB_COLLIDE, kWpbDyn = AVG_WPB_DYN, kWpbSolve = 1, kWpbEpi = 4, kWpbPro = 4, kWpbPCol = 4;
 
 // AVG_KERNEL_TIMES=1 in the environment: every launch of the step is bracketed by CUDA events and the per-kernel totals
 // are printed to stderr every 8 steps (a development aid; it serialises the host with the stream, so never set it for
@@ -3500,7 +3517,7 @@ cudaError_t configure_kernels() {
     const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
     const size_t sm_sol1 = sizeof(SmSolve) + sizeof(SmPartSmall), sm_sol2 = sizeof(SmSolve) + sizeof(SmPartLarge);
     if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
-    if ((e1 = set_smem(avg_pcollide_kernel, sizeof(SmPCol) * kWpbCollide)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_pcollide_kernel, sizeof(SmPCol) * kWpbPCol)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<8>, sm_dyn)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<12>, sm_dyn)) != cudaSuccess) return e1;
@@ -3535,7 +3552,7 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
     const bool part = a.part != nullptr;
     avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
     mark(1);
-    if (part) { avg_pcollide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sizeof(SmPCol) * kWpbCollide, stream>>>(a); mark(6); }
+    if (part) { avg_pcollide_kernel<<<grid(kWpbPCol), 32 * kWpbPCol, sizeof(SmPCol) * kWpbPCol, stream>>>(a); mark(6); }
     avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
     mark(5);
     if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);

@@ -198,3 +198,71 @@ def test_degenerate_simplex_regression(torch_cuda, oracles):
     assert [(int(c[0]), int(c[1])) for c in oc] == [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[0, :nc[0]]]
     assert np.abs(rec[:32] - st[0, :32]).max() < 1e-3 and abs(orew - float(rew[0])) < 1e-3
     env.close()
+
+
+def _pairs_g(cont, nc, e):
+    return [(int(c["shape_a"]), int(c["shape_b"])) for c in cont[e, :nc[e]]]
+
+
+def test_with_contact_trajectories_match_oracle(torch_cuda, oracles):
+    """10 env-steps (50 sub-steps) on environments that ARE in contact.  The batch is first walked with
+    drifting actions until arms, tool and people touch; then both sides continue from the same float32 states with the same
+    actions.  What is asserted, with the tolerances written here:
+      * contact-pair sets of every env-step: identical (pair-table order) in >= 97 % of the (environment, step) samples that
+        have a contact on either side; a differing sample must be explained by a pair within 1e-4 m of its threshold or by a
+        trajectory that had already separated by > 1e-4 rad;
+      * first step (identical start states): |dq| <= 1e-4 rad for >= 90 % and <= 1e-2 rad for >= 99 % of the environments in contact;
+      * after 10 steps: median |dq| over the environments that had a contact <= 1e-4 rad.
+    The tail is not a tolerance but a property of the restated algorithm: tools/oracle_sensitivity.py shows the float64 oracle
+    itself moving by up to 2e-3 rad in ONE env-step when its start state is perturbed by 1e-7 rad (limit rows that exist only
+    while violated, closest-feature switches), for ~1 % of the environments in contact."""
+    torch = torch_cuda
+    from oracle.oracle import env_to_f64
+    n, T = 384, 10
+    env = make_env(n, seed=17)
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    drift = torch.rand((n, 7), device="cuda", generator=g) * 1.4 - 0.7
+    for k in range(18):
+        env.step((drift + torch.rand((n, 7), device="cuda", generator=g) - 0.5).clamp(-1, 1)); env.elapsed = 0
+    st0 = env.get_state()
+    recs = [env_to_f64(st0[e]).copy() for e in range(n)]
+    rng = np.random.RandomState(4)
+    drift_np = drift.cpu().numpy()
+    had = np.zeros(n, dtype=bool)
+    samples = same = explained = 0
+    dq_first = None
+    for t in range(T):
+        a = np.clip(drift_np + rng.uniform(-0.5, 0.5, (n, 7)), -1, 1).astype(np.float32)
+        env.step(torch.as_tensor(a, device="cuda")); env.elapsed = 0
+        st = env.get_state(); cont, nc = env.sim.get_contacts()
+        dq = np.zeros(n); now = np.zeros(n, dtype=bool)
+        for e in range(n):
+            o = oracles[int(env.variants[e])]
+            _, _, _, oc = o.step(recs[e], a[e])
+            dq[e] = np.abs(recs[e][:17] - st[e, :17]).max()
+            gp = _pairs_g(cont, nc, e); op = [(int(c[0]), int(c[1])) for c in oc]
+            if gp or op:
+                now[e] = True; samples += 1
+                if gp == op:
+                    same += 1
+                else:
+                    thr = lambda sa, sb: min(float(o.model["shapes"][sa]["thr"]), float(o.model["shapes"][sb]["thr"]))
+                    sym = set(gp) ^ set(op)
+                    near = all(abs(c[11] - thr(int(c[0]), int(c[1]))) < 1e-4 for c in oc if (int(c[0]), int(c[1])) in sym) and \
+                        all(abs(float(c["dist"]) - thr(int(c["shape_a"]), int(c["shape_b"]))) < 1e-4 for c in cont[e, :nc[e]] if (int(c["shape_a"]), int(c["shape_b"])) in sym)
+                    explained += int(near or dq[e] > 1e-4)
+        had |= now
+        if t == 0:
+            dq_first = dq[now].copy()
+    dq_last = dq[had]
+    print(f"with-contact parity: {had.sum()} of {n} environments had a contact; (env, step) samples with contact {samples}, identical pair sets {same}, "
+          f"explained differences {explained}; first step |dq| p50 {np.median(dq_first):.1e} p90 {np.percentile(dq_first, 90):.1e} p99 {np.percentile(dq_first, 99):.1e} "
+          f"max {dq_first.max():.1e}; after {T} steps p50 {np.median(dq_last):.1e} p90 {np.percentile(dq_last, 90):.1e} max {dq_last.max():.1e}")
+    assert had.sum() >= 40, "too few environments in contact to be meaningful"
+    assert same >= 0.97 * samples, (same, samples)
+    assert same + explained == samples, (same, explained, samples)
+    assert (dq_first <= 1e-4).mean() >= 0.90 and (dq_first <= 1e-2).mean() >= 0.99, np.sort(dq_first)[-10:]
+    assert np.median(dq_last) <= 1e-4
+    assert int(st.view(np.int32)[:, 166].max()) == 0          # no overflow flags
+    env.close()
