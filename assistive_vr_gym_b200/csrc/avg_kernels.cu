@@ -57,6 +57,9 @@
 #ifndef AVG_LIM_SKIP
 #define AVG_LIM_SKIP 1            /* solver: sweep only the block slots in which some articulation has an active limit row */
 #endif
+#ifndef AVG_NARROW_WARPS
+#define AVG_NARROW_WARPS (148 * 12 * 2)   /* narrowphase: warps a short work queue is spread over (two waves at 12 warps per SM) */
+#endif
 #ifndef AVG_WELD_BATCH
 #define AVG_WELD_BATCH 1          /* dynamics kernel: the six weld rows built together with one packed reduction (0: row by row) */
 #endif
@@ -1109,9 +1112,14 @@ avg_narrow_kernel(AvgStepArgs a) {
     const int count = min(a.np_count[0], a.np_capacity);
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int base = wid * 32; base < count; base += nwarps * 32) {
+    // Items per warp.  A full queue gives every warp 32 items (throughput: the lockstep iterations are shared by 32 pairs).  A
+    // short queue (small batches: ~1 item per environment and sub-step) is spread over the warps the GPU can hold at once
+    // instead -- a warp with few items finishes its lockstep GJK in a fraction of the time (fewer iterations to wait for, every
+    // hull scan served by the whole warp), and at a small batch the step waits for the slowest warp of this kernel.
+    const int ipw = count >= 16 * AVG_NARROW_WARPS ? 32 : min(32, max(1, (count + AVG_NARROW_WARPS - 1) / AVG_NARROW_WARPS));
+    for (int base = wid * ipw; base < count; base += nwarps * ipw) {
         const int i = base + lane;
-        const bool valid = i < count;
+        const bool valid = lane < ipw && i < count;
         const long long t_begin = a.dbg_counters ? clock64() : 0;
         AvgNpItem it; it.env = 0; it.pair = 0; it.slot = 0; it.cert = -1;
         if (valid) it = a.np_queue[i];
@@ -1728,10 +1736,12 @@ __device__ __noinline__ float arm_limit_logit_warp(const float* __restrict__ w, 
 // articulation (a particle on the spoon loads the spoon, the spoon is welded to the gripper), in Bullet's order: ... contact
 // normals (articulation, then particles), friction (articulation, then particles).  A particle row touches one particle and,
 // on its other side, another particle, the tool (free body, two-way) or something kinematic (static shape, or a robot / human
-// link with its start-of-step velocity: one-way).  Rows that share no body commute, so the strictly ordered
-// sweep of the oracle is executed here in ROUNDS: a greedy schedule puts every row in the first round after the rows before it
-// (canonical contact order) that use one of its bodies, <= 32 rows per round, one lane per row -- the same numbers as the
-// sequential sweep, up to 32 rows at a time.  Particle velocities and the tool's six velocity components live in shared
+// link with its start-of-step velocity: one-way).  Inside one block of particle rows (normals / friction) every
+// row sees the tool's velocity change as the block began and the block's reactions reach the tool at once (the oracle does the
+// same): what a block orders are the rows that share a PARTICLE.  Rows that share no particle commute, so the
+// ordered sweep of the oracle is executed here in ROUNDS: a greedy schedule puts every row in the first round after the rows
+// before it (canonical contact order) that use one of its particles, <= 32 rows per round, one lane per row -- the same numbers
+// as the sequential sweep, up to 32 rows at a time.  Particle velocities and the tool's six velocity components live in shared
 // memory during these phases; the per-contact records (20 floats) stay in the particle scratch arena (L1 / L2).
 // =================================================================================================================
 // NP / NPC: particles / particle contacts the instance holds (Feeding: 8 / 64, Drinking: 64 / AVG_MAX_PCONTACT): the small
@@ -1907,12 +1917,10 @@ __device__ int particles_prepare(const KM& m, SP& sp, const AvgStepArgs& a, int 
             const int p = pk & 0xff, q = (pk >> 8) & 0xff, kind = pk >> 16;
             int r = sp.last[p];
             if (kind == 1) r = max(r, (int)sp.last[q]);
-            if (kind == 2) r = max(r, (int)sp.last[64]);
             while (sp.fill[r] >= 32) ++r;
             sp.round_of[c] = (uint16_t)r; sp.fill[r]++;
             sp.last[p] = (uint16_t)(r + 1);
             if (kind == 1) sp.last[q] = (uint16_t)(r + 1);
-            if (kind == 2) sp.last[64] = (uint16_t)(r + 1);
             nr = max(nr, r + 1);
         }
         int acc = 0;
@@ -1942,6 +1950,10 @@ __device__ __forceinline__ float particles_sweep(const KM& m, SP& sp, const floa
     const float r = m.shape[h->pshape].radius, inv_m = 1.0f / h->p_mass, inv_i = 1.0f / (0.4f * h->p_mass * r * r);
     const float4* R4 = reinterpret_cast<const float4*>(srec);
     float resid = 0.0f;
+    // the tool's velocity change as the block began (read by every row of the block) and this lane's share of the block's
+    // reactions on the tool (summed over the warp after the last round: a fixed order, so the result is bit-deterministic)
+    const V3 tdl = mk3(sp.tdv[0], sp.tdv[1], sp.tdv[2]), tda = mk3(sp.tdv[3], sp.tdv[4], sp.tdv[5]);
+    V3 accl = mk3(0, 0, 0), acca = mk3(0, 0, 0);
     float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0, n4 = n0;
     {
         const int cnt = nrounds > 0 ? sp.rstart[1] - sp.rstart[0] : 0;
@@ -1972,7 +1984,7 @@ __device__ __forceinline__ float particles_sweep(const KM& m, SP& sp, const floa
                 if (FRICTION) { jb = cross(n, d) * r; jdv -= dot(jb, sm3(sp.pdv, 3, q)); }
             } else if (kind == 2) {
                 jb = cross(mk3(c3.z, c3.w, c4.x), d);
-                jdv -= dot(d, mk3(sp.tdv[0], sp.tdv[1], sp.tdv[2])) + dot(jb, mk3(sp.tdv[3], sp.tdv[4], sp.tdv[5]));
+                jdv -= dot(d, tdl) + dot(jb, tda);
             }
             const float lam = sp.lam[FRICTION ? 1 : 0][idx];
             float sum = fmaf((FRICTION ? c2.y : c0.w) - jdv, FRICTION ? c2.z : c1.x, lam);
@@ -1987,15 +1999,26 @@ __device__ __forceinline__ float particles_sweep(const KM& m, SP& sp, const floa
                 sp.pdv[0][q] -= d.x * dm; sp.pdv[1][q] -= d.y * dm; sp.pdv[2][q] -= d.z * dm;
                 if (FRICTION) { const float di = delta * inv_i; sp.pdv[3][q] -= jb.x * di; sp.pdv[4][q] -= jb.y * di; sp.pdv[5][q] -= jb.z * di; }
             } else if (kind == 2) {
-                const float dmt = delta * sp.tinv[0];
-                const V3 wj = tinv_mul(sp.tinv, jb) * delta;
-                sp.tdv[0] -= d.x * dmt; sp.tdv[1] -= d.y * dmt; sp.tdv[2] -= d.z * dmt;
-                sp.tdv[3] -= wj.x; sp.tdv[4] -= wj.y; sp.tdv[5] -= wj.z;
+                accl = accl - d * delta; acca = acca - jb * delta;          // impulse and angular impulse on the tool
             }
             resid = fmaxf(resid, fabsf(delta) * (FRICTION ? c4.z : c4.y));
         }
         __syncwarp();
     }
+    // the block's reactions reach the tool at once: dv_tool += M_tool^-1 (sum of the impulses)
+    if (__any_sync(AVG_FULL, accl.x != 0.0f || accl.y != 0.0f || accl.z != 0.0f || acca.x != 0.0f || acca.y != 0.0f || acca.z != 0.0f)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            accl.x += __shfl_xor_sync(AVG_FULL, accl.x, o); accl.y += __shfl_xor_sync(AVG_FULL, accl.y, o); accl.z += __shfl_xor_sync(AVG_FULL, accl.z, o);
+            acca.x += __shfl_xor_sync(AVG_FULL, acca.x, o); acca.y += __shfl_xor_sync(AVG_FULL, acca.y, o); acca.z += __shfl_xor_sync(AVG_FULL, acca.z, o);
+        }
+        if (lane == 0) {
+            const V3 wj = tinv_mul(sp.tinv, acca);
+            sp.tdv[0] += accl.x * sp.tinv[0]; sp.tdv[1] += accl.y * sp.tinv[0]; sp.tdv[2] += accl.z * sp.tinv[0];
+            sp.tdv[3] += wj.x; sp.tdv[4] += wj.y; sp.tdv[5] += wj.z;
+        }
+    }
+    __syncwarp();
     return resid;
 }
 
@@ -3548,7 +3571,7 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
     const size_t sm_sol1 = sizeof(SmSolve) + sizeof(SmPartSmall), sm_sol2 = sizeof(SmSolve) + sizeof(SmPartLarge);
     const int n_range = a.env_end - a.env_begin;
     auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
-    const int np_grid = min((a.np_capacity + 127) / 128, 148 * 16);     // grid-stride over the queue, one thread per work item
+    const int np_grid = 148 * 16;                                       // grid-stride over the queue; a short queue is spread over all of these warps (ipw)
     const bool part = a.part != nullptr;
     avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
     mark(1);

@@ -987,6 +987,7 @@ static void substep(const Model* m, double* env, double* part, Contact* contacts
         r->mu = (double)m->shape[C->sa].friction * (double)m->shape[C->sb].friction;
         finish_row(m, d, qd, r);
     }
+    const int first_pfriction_row = nr;
     for (int c = 0; c < npc; ++c) {                 /* particle friction rows: the sphere's lever arm is -r n */
         PContact* C = &pcs[c];
         Row* r = &rows[nr++]; memset(r, 0, sizeof(Row));
@@ -1033,16 +1034,24 @@ static void substep(const Model* m, double* env, double* part, Contact* contacts
         r->mu = (double)m->shape[h->pshape].friction * mu_b;
     }
     /* projected Gauss-Seidel in velocity space, as btMultiBodyConstraintSolver */
+    /* Particle rows and the tool (documented deviation from Bullet's strict row order): inside one block of particle
+     * rows (the normal block, the friction block) every row sees the tool's velocity change as it was when the block began; the
+     * reactions of the block reach the tool -- and the rows after the block -- at once.  A block then only orders the rows that
+     * share a PARTICLE, which is what lets the device sweep a block in a few parallel rounds instead of one row at a time; the
+     * coupling that is lagged by one block is of the order particle mass / tool mass (1 g against the spoon / cup). */
     double dv[MAXD]; memset(dv, 0, sizeof(dv));
+    double dv_block[MAXD]; memset(dv_block, 0, sizeof(dv_block));
     double dpv[AVG_MAX_PARTICLE][6]; memset(dpv, 0, sizeof(dpv));
     for (int it = 0; it < h->solver_iters; ++it) {
         double resid = 0;
         for (int ri = 0; ri < nr; ++ri) {
             Row* r = &rows[ri];
+            if (npc > 0 && (ri == first_pcontact_row || ri == first_pfriction_row)) memcpy(dv_block, dv, sizeof(dv));
             if (r->diag < 1e-12) continue;
             double lo = r->lo, hi = r->hi;
             if (r->friction_of >= 0) { double lim = r->mu * rows[r->friction_of].lambda; lo = -lim; hi = lim; }
-            double jdv = 0; for (int i = 0; i < nd; ++i) jdv += r->J[i] * dv[i];
+            const double* dvr = r->pa >= 0 ? dv_block : dv;
+            double jdv = 0; for (int i = 0; i < nd; ++i) jdv += r->J[i] * dvr[i];
             if (r->pa >= 0) { const double* a = dpv[r->pa]; jdv += r->jl_a.x * a[0] + r->jl_a.y * a[1] + r->jl_a.z * a[2] + r->ja_a.x * a[3] + r->ja_a.y * a[4] + r->ja_a.z * a[5]; }
             if (r->pb >= 0) { const double* b = dpv[r->pb]; jdv += r->jl_b.x * b[0] + r->jl_b.y * b[1] + r->jl_b.z * b[2] + r->ja_b.x * b[3] + r->ja_b.y * b[4] + r->ja_b.z * b[5]; }
             double delta = (r->target - jdv) / r->diag;

@@ -3,10 +3,11 @@
 Anchors that come from the reference tree itself:
   * total_target_count = 129 (male) / 91 (female): `util.capsule_points` with the limb dimensions of
     `bed_bathing.py:361-368` (SURVEY.md §8c "constants");
-  * the settled right-arm pose: `bed_bathing.py:245` hard-codes `joint_angles = [0.397, 0.279, -0.009, -0.673, -0.006,
-    0.060, 0.010]` for the VR branch -- the pose PyBullet produced for the authors after the same drop onto the same
-    mattress.  It is the only number in the tree that came out of the reference's physics engine; our restated
-    `stepSimulation` must land the arm there (shoulder / elbow joints within a few hundredths of a radian).
+  * a PLAUSIBILITY check only, not a pin: `bed_bathing.py:232` hard-codes `joint_angles = [0.397, 0.279, -0.009, -0.673,
+    -0.006, 0.060, 0.010]` in the VR / replay branch and applies them to joints 0..6 of the VR human (`:233`; the legend in
+    `human_creation_vr.py:5-9` names those waist / chest / shoulder joints).  Reading them as the right-arm pose the non-VR
+    branch reaches after its 100-step drop onto the mattress is this build's inference; under it the restated drop lands the
+    shoulder / elbow joints within a few hundredths of a radian and the wrist 0.3 rad away.
 """
 import json
 import os
@@ -17,7 +18,7 @@ import pytest
 from conftest import ASSETS
 
 DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data")
-REF_SETTLED_ARM = np.array([0.39717707, 0.27890519, -0.00883447, -0.67345593, -0.00568484, 0.05987911, 0.00957937])  # bed_bathing.py:245
+REF_SETTLED_ARM = np.array([0.39717707, 0.27890519, -0.00883447, -0.67345593, -0.00568484, 0.05987911, 0.00957937])  # bed_bathing.py:232 (joint mapping inferred, see above)
 
 
 def _settle_with_oracle(v):
