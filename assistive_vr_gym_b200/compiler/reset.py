@@ -264,6 +264,7 @@ RESET_TABLE_DT = np.dtype([
     ("ik_target", "<f4", 8), ("ik_ee_frame", "<f4", 8),
     ("hum_slot", "<i4", 8), ("fin_q", "<f4", 8), ("n_particle", "<i4"), ("has_bowl", "<i4"), ("head_mask", "<u4"), ("ik_tol", "<f4"),
     ("bowl_center", "<f4", 4), ("bowl_quat", "<f4", 4), ("grid", "<f4", (64, 4)),
+    ("new_mode", "<i4"), ("hum_jitter", "<f4"), ("new_min_dist", "<f4"), ("pad_new", "<i4"),
 ])
 
 
@@ -289,6 +290,8 @@ def reset_table_bytes(rd: dict, ik: dict | None = None) -> bytes:
     t["hum_slot"][:len(hj)] = hj - (24 if fd else 4)
     t["fin_q"][:len(rd["fin_qidx"])] = rd["fin_q"] if "fin_q" in rd else float(rd.get("fin_open", 1.0))
     t["ik_tol"] = float(rd.get("ik_tol", 0.03))
+    if int(rd.get("new_mode", 0)):                             # <Task><Robot>New-v0
+        t["new_mode"] = 1; t["hum_jitter"] = float(rd.get("hum_jitter", 0.0)); t["new_min_dist"] = float(rd.get("new_min_dist", 0.01))
     if fd:                                                     # Feeding / Drinking (compiler/reset_fd.py build_reset_data_fd)
         npart = int(rd["n_particle"])
         t["n_particle"] = npart; t["has_bowl"] = int(rd["has_bowl"]); t["head_mask"] = int(rd["head_mask"])

@@ -379,9 +379,14 @@ def expand_compounds(shapes: List[CompiledShape], pairs: np.ndarray):
 
 
 def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,
-                       base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False) -> CompiledScene:
+                       base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False,
+                       new: bool = False, hipbone_to_mouth_height: Optional[float] = None,
+                       waist: Tuple[float, float, float] = (0.0, 0.0, 0.0)) -> CompiledScene:
     """ScratchItch<Robot>[Human]-v0.  PR2: `base_xy_yaw` = the random_pos / yaw chosen by `position_robot_toc`
-    (env.py:511-513 as called at scratch_itch.py:245)."""
+    (env.py:511-513 as called at scratch_itch.py:245).
+    `new` = ScratchItch<Robot>New-v0 (`__init__.py:38-50`): the human is built with revolute waist joints
+    (`human_creation.py:185-189`) held at the drawn `waist` angles (`scratch_itch.py:211`, frozen like every other
+    non-controllable joint) and with every link length scaled by `hipbone_to_mouth_height` (`:158`, `human_creation.py:60-63`)."""
     cfg = CONFIG["scratch_itch"]
     # -- bodies as the reference creates them ---------------------------------------------------------------
     robot, rs = load_robot(assets_dir, robot_type)
@@ -394,7 +399,9 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
         robot.base_quat = X.quat_from_euler([0, 0, base_xy_yaw[2]])
     robot.fixed_base = True
     h2m = 0.6 if gender == "male" else 0.54                              # scratch_itch.py:161
-    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
+    if new and hipbone_to_mouth_height is not None:
+        h2m = float(hipbone_to_mouth_height)                             # scratch_itch.py:158: uniform(h2m - 0.1, h2m + 0.1)
+    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=new)
     human.base_pos = np.array([0, 0.03, 0.89 - 0.23725 if gender == "male" else 0.86 - 0.225])   # scratch_itch.py:232
     human.gravity = np.array([0.0, 0.0, -1.0])                           # scratch_itch.py:260
     tool = urdf_to_multibody(os.path.join(assets_dir, "scratcher", "tool_scratch.urdf"), REF_TOOL, "scratcher")
@@ -411,6 +418,8 @@ def build_scratch_itch(assets_dir: str, robot_type: str = "jaco", gender: str = 
     # -- reset-time joint presets and frozen joints ----------------------------------------------------------
     deg = np.deg2rad
     q_human = {7: deg(30), 10: deg(-90), 20: deg(-90), 28: deg(-90), 31: deg(80), 35: deg(-90), 38: deg(80)}  # :230
+    if new:                                                              # scratch_itch.py:211: waist joints 0..2, U(-10, 10) degrees
+        q_human.update({0: float(waist[0]), 1: float(waist[1]), 2: float(waist[2])})
     # enforce_joint_limits after the preset (world_creation.py:172, limit_scale = 1 for the baked static pose)
     for l in human.links:
         if l.jtype == "revolute":

@@ -87,9 +87,12 @@ def particle_grid(task: str) -> np.ndarray:
 
 def build_feeding_drinking(assets_dir: str, task: str = "feeding", robot_type: str = "jaco", gender: str = "male",
                            human_control: bool = False, base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0),
-                           verbose: bool = False) -> CompiledScene:
+                           verbose: bool = False, new: bool = False, hipbone_to_mouth_height: float | None = None,
+                           waist: Tuple[float, float, float] = (0.0, 0.0, 0.0)) -> CompiledScene:
     """Feeding<Robot>[Human]-v0 / Drinking<Robot>[Human]-v0.  `base_xy_yaw` = random_pos x, y and yaw of the robot base chosen by
-    `position_robot_toc` (env.py:511-513; PR2, and the build-defined Sawyer / Baxter placements)."""
+    `position_robot_toc` (env.py:511-513; PR2, and the build-defined Sawyer / Baxter placements).
+    `new` = <Task><Robot>New-v0 (`__init__.py:206-218,290-302`): person of height `hipbone_to_mouth_height` (feeding.py:171) with
+    revolute waist joints held at the drawn `waist` angles (feeding.py:233); the whole person is static in these ids (:235)."""
     assert task in ("feeding", "drinking")
     cfg = CONFIG[task]
     rec = ROBOT_FD[(task, robot_type)]
@@ -103,7 +106,9 @@ def build_feeding_drinking(assets_dir: str, task: str = "feeding", robot_type: s
         robot.base_pos = np.array([-0.85, -0.4, 0.0]) + np.asarray(rec["toc"], float) + np.array([base_xy_yaw[0], base_xy_yaw[1], 0.0])   # env.py:513
         robot.base_quat = X.quat_from_euler([0, 0, base_xy_yaw[2]])
     h2m = 0.6 if gender == "male" else 0.54                                                       # feeding.py:174
-    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
+    if new and hipbone_to_mouth_height is not None:
+        h2m = float(hipbone_to_mouth_height)                                                      # feeding.py:171
+    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=new)
     human.base_pos = np.array([0, 0.03, 0.89 - 0.23725 if gender == "male" else 0.86 - 0.225])    # feeding.py:245
     human.compound_links = {27}                                                                   # head: 8 / 9 VHACD hulls
     tool = urdf_to_multibody(os.path.join(assets_dir, "dinnerware", "spoon.urdf" if task == "feeding" else "cup.urdf"), REF_TOOL,
@@ -129,6 +134,8 @@ def build_feeding_drinking(assets_dir: str, task: str = "feeding", robot_type: s
 
     # -- joint presets and frozen joints (feeding.py:242-244) ---------------------------------------------------
     q_human = {10: deg(-90), 20: deg(-90), 28: deg(-90), 31: deg(80), 35: deg(-90), 38: deg(80)}
+    if new:
+        q_human.update({0: float(waist[0]), 1: float(waist[1]), 2: float(waist[2])})              # feeding.py:233
     for l in human.links:
         if l.jtype == "revolute":
             q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))      # world_creation.py:172

@@ -48,6 +48,7 @@ struct AvgHandle {
     cudaEvent_t ev_xjoin[2] = {nullptr, nullptr};
     cudaStream_t stream2 = nullptr;
     bool rtab_ik[AVG_K_MAX_VARIANTS] = {}; bool any_ik = false;     // reset tables that ask for the on-device IK start pose
+    bool rtab_new[AVG_K_MAX_VARIANTS] = {}; bool any_new = false;   // reset tables of `New` ids with a per-episode arm pose draw
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // avg_step on two streams: fork from / join into the caller's stream
     int step_chunks = 1;
     int time_limit = 0;                                // avg_set_time_limit
@@ -349,6 +350,9 @@ int avg_upload_reset_table(AvgHandle* h, int variant, const void* table, size_t 
     h->rtab_ik[variant] = t->ik_enabled != 0;
     h->any_ik = false;
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) h->any_ik = h->any_ik || h->rtab_ik[v];
+    h->rtab_new[variant] = t->new_mode != 0 && t->hum_jitter > 0.0f;
+    h->any_new = false;
+    for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) h->any_new = h->any_new || h->rtab_new[v];
     return 0;
 }
 
@@ -362,9 +366,9 @@ int avg_reset(AvgHandle* h, const uint8_t* mask, uint32_t seed, float* obs, void
     r.n_variants = nv; r.n_per_gender = nv >= 2 ? nv / 2 : 1; r.env = h->d_env; r.scratch = h->d_scratch; r.variant = h->d_variant; r.episode = h->d_episode;
     r.mask = mask; r.n_env = h->n_env; r.seed = seed; r.part = h->d_part;
     for (int v = 0; v < AVG_K_MAX_VARIANTS; ++v) r.models[v] = h->d_model[v] ? h->d_model[v] : h->d_model[0];
-    r.any_ik = h->any_ik ? 1 : 0;
+    r.any_ik = h->any_ik ? 1 : 0; r.any_new = h->any_new ? 1 : 0;
     AVG_CHECK(h, avg_launch_reset(r, (cudaStream_t)stream));
-    h->launches += 1 + r.any_ik + (h->d_part ? 1 : 0);
+    h->launches += 1 + r.any_ik + r.any_new + (h->d_part ? 1 : 0);
     if (r.any_ik) {
         /* util.ik_random_restarts(step_sim=True) (util.py:41-46): 5 x stepSimulation from the solved pose, poses whose robot
            touches itself (or that were pushed away) are solved again from new random restarts, up to 5 times */

@@ -3142,7 +3142,7 @@ avg_reset_kernel(AvgResetArgs r) {
     const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)min(r.n_variants, 2)) * npg + (int)(pick % (uint32_t)npg);
     const AvgResetTable* T = r.tables[v];
     const bool bb = T->task == AVG_TASK_BED_BATHING;                                              // human_impairment='none', bed_bathing.py:198
-    const int impairment = bb ? 0 : (int)(reset_u32(sd, ue, ep, 1) & 3u);                         // none, limits, weakness, tremor
+    const int impairment = (bb || T->new_mode) ? 0 : (int)(reset_u32(sd, ue, ep, 1) & 3u);        // none, limits, weakness, tremor; `New`: 'none' (scratch_itch.py:159)
     const float limit_scale = impairment == 1 ? 0.5f + 0.5f * reset_u01(sd, ue, ep, 2) : 1.0f;    // world_creation.py:70
     const float strength = impairment == 2 ? 0.25f + 0.75f * reset_u01(sd, ue, ep, 3) : 1.0f;     // world_creation.py:71
     float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
@@ -3341,7 +3341,7 @@ avg_reset_fd_kernel(AvgResetArgs r) {
     const int npg = r.n_per_gender;
     const int v = (int)(reset_u32(sd, ue, ep, 0) % (uint32_t)min(r.n_variants, 2)) * npg + (int)(pick % (uint32_t)npg);   // gender, feeding.py:172
     const AvgResetTable* T = r.tables[v];
-    const int impairment = (int)(reset_u32(sd, ue, ep, 1) & 3u);                                   // none, limits, weakness, tremor (world_creation.py:67)
+    const int impairment = T->new_mode ? 0 : (int)(reset_u32(sd, ue, ep, 1) & 3u);                 // none, limits, weakness, tremor (world_creation.py:67); `New`: 'none' (feeding.py:172)
     const float limit_scale = impairment == 1 ? 0.5f + 0.5f * reset_u01(sd, ue, ep, 2) : 1.0f;
     const float strength = impairment == 2 ? 0.25f + 0.75f * reset_u01(sd, ue, ep, 3) : 1.0f;
     float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
@@ -3432,6 +3432,95 @@ avg_reset_check_kernel(AvgResetArgs r) {
     r.retry[e] = bad ? 1 : 0;
 }
 
+// `New` ids of ScratchItch / BedBathing (scratch_itch.py:198-228, bed_bathing.py:256-279): the dynamic arm joints start at their
+// preset plus U(-10, 10) degrees, redrawn until the arm keeps new_min_dist (0.01) from the rest of the person (links other than
+// the arm itself, the chest 3 and the shoulder 6), from the robot and from the furniture.  The reference measures those
+// distances with getClosestPoints; here every shape is represented by its bounding capsule (exact for the capsules and spheres
+// the person is made of, conservative for hulls: a pose may be redrawn that the reference would have kept, never the reverse).
+// One thread per environment, after the start pose of the robot is known (avg_reset_ik_kernel); at most 20 draws, the last kept.
+namespace {
+__device__ __forceinline__ float capsule_gap(V3 a0, V3 a1, float ra, V3 b0, V3 b1, float rb) {
+    return seg_seg_distance(a0, a1 - a0, b0, b1 - b0) - ra - rb;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(64)
+avg_reset_new_kernel(AvgResetArgs r) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n_env) return;
+    if (r.mask && !r.mask[e]) return;
+    const int v = r.variant[e];
+    const AvgResetTable* T = r.tables[v];
+    if (!T->new_mode || !(T->hum_jitter > 0.0f) || T->n_hum <= 0 || T->n_hum > 8) return;
+    const KM m = open_model(r.models[v]);
+    const AvgModelHeader* h = m.h;
+    const uint32_t sd = r.seed, ue = (uint32_t)e, ep = (uint32_t)r.episode[e];
+    float* rec = r.env + (size_t)e * AVG_ENV_STRIDE;
+    const int nb = h->n_body, nms = h->n_mshape, ns = h->n_shape;
+    // world poses of the dynamic bodies (serial: parents precede children)
+    V3 bp[AVG_MAX_BODY]; Q4 bq[AVG_MAX_BODY];
+    auto fk_body = [&](int b) {
+        const AvgBody* B = &m.body[b];
+        if (B->jtype == AVG_JOINT_FREE) { const float* qq = rec + AVG_E_Q + B->qidx; bp[b] = ld3(qq); bq[b] = qnormalize(ldq(qq + 3)); return; }
+        V3 pp = mk3(0, 0, 0); Q4 pq = mkq(0, 0, 0, 1);
+        if (B->parent >= 0) { pp = bp[B->parent]; pq = bq[B->parent]; }
+        const V3 ax = ld3(B->axis);
+        const float qv = rec[AVG_E_Q + B->qidx];
+        Q4 jq = ldq(B->ta_quat); V3 jp = ld3(B->ta_pos);
+        if (B->jtype == AVG_JOINT_REVOLUTE) jq = qmul(jq, qaxis(ax, qv)); else jp = jp + qrot(jq, ax * qv);
+        bp[b] = pp + qrot(pq, jp + qrot(jq, ld3(B->tb_pos)));
+        bq[b] = qnormalize(qmul(pq, qmul(jq, ldq(B->tb_quat))));
+    };
+    for (int b = 0; b < nb; ++b) fk_body(b);
+    auto world_capsule = [&](int si, V3& c0, V3& c1, float& rad) {
+        const float4 k0 = __ldg(&m.bcap[2 * si]), k1 = __ldg(&m.bcap[2 * si + 1]);
+        rad = k0.w;
+        if (si < nms) {
+            const AvgShape* S = &m.shape[si];
+            const Q4 sq = qnormalize(qmul(bq[S->body], ldq(S->quat)));
+            const V3 sp = bp[S->body] + qrot(bq[S->body], ld3(S->pos));
+            c0 = sp + qrot(sq, mk3(k0.x, k0.y, k0.z)); c1 = sp + qrot(sq, mk3(k1.x, k1.y, k1.z));
+        } else { c0 = mk3(k0.x, k0.y, k0.z); c1 = mk3(k1.x, k1.y, k1.z); }
+    };
+    // the arm's shapes: the moving shapes of the person
+    int arm[4], narm = 0;
+    for (int si = 0; si < nms && narm < 4; ++si) if (m.shape[si].ref_body == AVG_REF_HUMAN && m.shape[si].body < nb) arm[narm++] = si;
+    float qbest[8]; float gap_best = -3.0e38f; int attempts = 0;
+    for (int at = 0; at < 20; ++at) {
+        attempts = at + 1;
+        float q[8];
+        for (int j = 0; j < T->n_hum; ++j) {
+            const float u = 2.0f * reset_u01(sd, ue, ep, 2048u + 8u * (uint32_t)at + (uint32_t)j) - 1.0f;
+            q[j] = fminf(fmaxf(T->hum_reset[j] + u * T->hum_jitter, T->hum_lower[j]), T->hum_upper[j]);      // add_joint_positions + enforce_joint_limits
+            rec[AVG_E_Q + T->hum_qidx[j]] = q[j];
+        }
+        for (int j = 0; j < T->n_hum; ++j) fk_body(m.dof[T->hum_dof[j]].body);       // the arm chain is listed root first
+        float gap = 3.0e38f;
+        for (int k = 0; k < narm; ++k) {
+            V3 a0, a1; float ra; world_capsule(arm[k], a0, a1, ra);
+            for (int sj = 0; sj < ns; ++sj) {
+                const AvgShape* S = &m.shape[sj];
+                if (S->type == AVG_SHAPE_PLANE) continue;
+                const int rb_ = S->ref_body;
+                bool other = false;
+                if (rb_ == AVG_REF_HUMAN) other = sj >= nms && S->ref_link != 3 && S->ref_link != 6;       // scratch_itch.py:219
+                else if (rb_ == AVG_REF_ROBOT || rb_ == AVG_REF_FURNITURE) other = true;                    // :221-223
+                if (!other) continue;
+                V3 b0, b1; float rbb; world_capsule(sj, b0, b1, rbb);
+                gap = fminf(gap, capsule_gap(a0, a1, ra, b0, b1, rbb));
+            }
+        }
+        if (gap > gap_best) { gap_best = gap; for (int j = 0; j < T->n_hum; ++j) qbest[j] = q[j]; }
+        if (gap >= T->new_min_dist) break;
+    }
+    for (int j = 0; j < T->n_hum; ++j) {
+        rec[AVG_E_Q + T->hum_qidx[j]] = qbest[j]; rec[AVG_E_MTARGET + T->hum_dof[j]] = qbest[j];
+        rec[AVG_E_TARGET_H + T->hum_slot[j]] = qbest[j];                                                      // scratch_itch.py:235
+    }
+    // inspection slots (third env-static pose slot, unused by these tasks): bounding-capsule clearance of the kept pose, draws used
+    rec[AVG_E_EBODY + 14] = gap_best; rec[AVG_E_EBODY + 15] = (float)attempts;
+}
+
 cudaError_t avg_launch_reset_check(const AvgResetArgs& r, cudaStream_t stream) {
     avg_reset_check_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     avg_reset_ik_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
@@ -3443,6 +3532,7 @@ cudaError_t avg_launch_reset(const AvgResetArgs& r, cudaStream_t stream) {
     if (r.part) avg_reset_fd_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     else avg_reset_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     if (r.any_ik) avg_reset_ik_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
+    if (r.any_new) avg_reset_new_kernel<<<(r.n_env + 63) / 64, 64, 0, stream>>>(r);
     if (r.part) avg_reset_particles_kernel<<<(r.n_env + 127) / 128, 128, 0, stream>>>(r);
     return cudaGetLastError();
 }

@@ -110,6 +110,7 @@ struct AvgResetArgs {
     const AvgResetTable* tables[AVG_K_MAX_VARIANTS];
     const unsigned char* models[AVG_K_MAX_VARIANTS];   // device ModelBlobs (the on-device IK walks the arm chain)
     int any_ik;                                        // some table has ik_enabled: launch avg_reset_ik_kernel after the draws
+    int any_new;                                       // some table is a `New` id with an arm pose draw: launch avg_reset_new_kernel after the IK
     int n_variants;
     int n_per_gender;                                  // variants per gender (1 ScratchItch; BedBathing: one per robot base pose)
     float* env; float* scratch; int32_t* variant; int32_t* episode;

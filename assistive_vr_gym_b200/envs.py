@@ -41,6 +41,15 @@ for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
     for _r, _robot in (("Jaco", "jaco"), ("PR2", "pr2"), ("Sawyer", "sawyer"), ("Baxter", "baxter")):
         REGISTRY[f"{_t}{_r}-v0"] = dict(task=_task, robot=_robot, human_control=False, data=f"{_t}{_r}.npz")
         REGISTRY[f"{_t}{_r}Human-v0"] = dict(task=_task, robot=_robot, human_control=True, data=f"{_t}{_r}Human.npz")
+# `New` ids (reference __init__.py:38-50): a person of random height with a random waist pose (both per model variant here: 8
+# per gender), no impairment, the arm pose drawn per episode on the device until it is collision-free (avg_reset_new_kernel)
+REGISTRY["ScratchItchJacoNew-v0"] = dict(task="scratch_itch", robot="jaco", human_control=False, data="ScratchItchJacoNew.npz", new=True)
+REGISTRY["ScratchItchPR2New-v0"] = dict(task="scratch_itch", robot="pr2", human_control=False, data="ScratchItchPR2New.npz", new=True)
+# Feeding / Drinking `New` ids (__init__.py:206-218,290-302): the whole person is static in these (feeding.py:235), so height and
+# waist pose per variant are all there is to them besides human_impairment = 'none'
+for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
+    for _r, _robot in (("Jaco", "jaco"), ("PR2", "pr2")):
+        REGISTRY[f"{_t}{_r}New-v0"] = dict(task=_task, robot=_robot, human_control=False, data=f"{_t}{_r}New.npz", new=True)
 _OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28), "feeding": (25, 23), "drinking": (25, 23)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19, feeding.py:18
 _ACT_HUMAN = {"scratch_itch": 10, "bed_bathing": 10, "feeding": 4, "drinking": 4}                              # scratch_itch.py:19, feeding.py:18
 SETTLE_STEPS = 100           # feeding.py:318-320
@@ -186,6 +195,8 @@ class BatchedAssistiveEnv:
         sampler of compiler/reset.py, whose start poses come from the variant's pool of precomputed IK solutions."""
         if host is None:
             host = genders is not None
+        if host and self.spec.get("new"):
+            raise NotImplementedError(f"{self.env_id}: the `New` ids draw their collision-free arm pose on the device; use reset() / reset_device()")
         if not host:
             obs = self.reset_device()
             self.variants = self.sim.get_variants()

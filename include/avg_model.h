@@ -276,6 +276,15 @@ typedef struct AvgResetTable {
     float   ik_tol;                       /* random_restart_threshold: 0.03 ScratchItch, 0.01 Feeding / Drinking on the Jaco (feeding.py:278) */
     float   bowl_center[4], bowl_quat[4]; /* feeding.py:184-185: centre of the +-0.05 square the bowl is drawn from, its orientation */
     float   grid[AVG_MAX_PARTICLE][4];    /* particle offsets from the tool's base position, world axes (feeding.py:301-305) */
+    /* ---- `New` ids (<Task><Robot>New-v0, reference __init__.py:38-50,122-134,206-218,290-302) ----
+     * new_mode: human_impairment = 'none' (scratch_itch.py:159); ScratchItch / BedBathing: every dynamic arm joint starts at
+     * hum_reset + U(-hum_jitter, hum_jitter) (scratch_itch.py:216-217), redrawn while the arm is closer than new_min_dist to the
+     * rest of the person, the robot or the furniture (:198,219-223; bounding-capsule distances on the device, see
+     * avg_reset_new_kernel).  Waist angles and hipbone_to_mouth_height are properties of the model variant. */
+    int32_t new_mode;
+    float   hum_jitter;                   /* 10 degrees */
+    float   new_min_dist;                 /* 0.01 */
+    int32_t pad_new;
 } AvgResetTable;
 
 /* Counter-based random numbers of the device reset: draw k of episode `episode` of environment `env` under `seed`.

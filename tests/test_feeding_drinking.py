@@ -234,7 +234,8 @@ def _gpu_env(env_id, n, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env_id", ["FeedingJaco-v0", "DrinkingJaco-v0", "FeedingPR2Human-v0", "FeedingSawyer-v0", "DrinkingBaxter-v0"])
+@pytest.mark.parametrize("env_id", ["FeedingJaco-v0", "DrinkingJaco-v0", "FeedingPR2Human-v0", "FeedingSawyer-v0", "DrinkingBaxter-v0",
+                                    "FeedingJacoNew-v0", "DrinkingPR2New-v0"])
 def test_gpu_reset_and_trajectory_vs_oracle(env_id):
     """Device reset (draws, IK, particle grid, 100 settle steps) leaves the food in the tool; from that state the CUDA step and the
     oracle agree over 3 env-steps (= 30 internal steps with ~30 / ~250 particle contacts each): reset observation 1e-5, joint

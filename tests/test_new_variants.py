@@ -1,0 +1,169 @@
+"""`New` ids (reference `__init__.py:38-50`, `scratch_itch.py:157-159,198-228`, `human_creation.py:185-194`).
+
+What the reference draws per episode and where this build puts it:
+  * hipbone_to_mouth_height +-0.1 and the three waist angles: per MODEL VARIANT (8 per gender, compiled offline);
+  * human_impairment = 'none': the device reset (AvgResetTable.new_mode);
+  * the arm pose preset + U(-10, 10) degrees per joint, redrawn until the arm is >= 0.01 from the rest of the person, the robot
+    and the wheelchair: the device reset (avg_reset_new_kernel), with bounding-capsule distances (conservative for hulls).
+CPU tests need the reference assets (model compiler); GPU tests run on the committed data.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS
+
+DEG10 = np.deg2rad(10.0)
+
+
+@pytest.mark.assets
+def test_new_human_has_revolute_waist_and_scaled_links():
+    """human_creation.py:185-189 (waist joints revolute with limits -30..75 / +-30 / +-30 degrees) and :60-63 (height scale)."""
+    from assistive_vr_gym_b200.compiler.human import create_human
+    base = create_human(ASSETS, "male", 0.6, new=False)
+    new = create_human(ASSETS, "male", 0.69, new=True)
+    for j, (lo, hi) in enumerate([(-30, 75), (-30, 30), (-30, 30)]):
+        assert base.links[j].jtype == "fixed" and new.links[j].jtype == "revolute"
+        assert abs(new.links[j].lower - np.deg2rad(lo)) < 1e-9 and abs(new.links[j].upper - np.deg2rad(hi)) < 1e-9
+    # every length along the body scales with hipbone_to_mouth_height / 0.6; radii do not
+    k = 0.69 / 0.6
+    up_b, up_n = base.links[9].shapes[0], new.links[9].shapes[0]
+    assert abs(up_n.half[2] / up_b.half[2] - k) < 1e-9 and abs(up_n.radius - up_b.radius) < 1e-12
+    assert abs(new.links[10].pos[2] / base.links[10].pos[2] - k) < 1e-9          # elbow joint below the shoulder (forearm_p)
+
+
+@pytest.mark.assets
+def test_new_scene_bakes_the_waist_pose():
+    """The waist joints are not controllable (scratch_itch.py:197), so they are frozen like every other such joint
+    (world_creation.py:157-161) at the drawn angles: same bodies / dofs as the stock id, the static upper body moved."""
+    from assistive_vr_gym_b200.compiler.scene import build_scratch_itch
+    s0 = build_scratch_itch(ASSETS, "jaco", "female")
+    s1 = build_scratch_itch(ASSETS, "jaco", "female", new=True, hipbone_to_mouth_height=0.6, waist=(0.15, -0.1, 0.12))
+    assert len(s0.bodies) == len(s1.bodies) and len(s0.dofs) == len(s1.dofs) and s0.n_mshape == s1.n_mshape
+    chest0 = [s for s in s0.shapes if s.ref_body == 1 and s.ref_link == 3][0]
+    chest1 = [s for s in s1.shapes if s.ref_body == 1 and s.ref_link == 3][0]
+    assert np.linalg.norm(np.asarray(chest0.pos) - np.asarray(chest1.pos)) > 0.02
+    hips0 = [s for s in s0.shapes if s.ref_body == 1 and s.ref_link == -1][0]
+    hips1 = [s for s in s1.shapes if s.ref_body == 1 and s.ref_link == -1][0]
+    assert abs(hips0.pos[0] - hips1.pos[0]) < 1e-9 and abs(hips0.pos[1] - hips1.pos[1]) < 1e-9      # below the waist: not rotated
+
+
+def test_new_ids_are_registered_with_variant_draws():
+    from assistive_vr_gym_b200.envs import REGISTRY, load_env_data
+    for env_id, base in (("ScratchItchJacoNew-v0", 0), ("ScratchItchPR2New-v0", 0), ("FeedingJacoNew-v0", 0), ("FeedingPR2New-v0", 0),
+                         ("DrinkingJacoNew-v0", 0), ("DrinkingPR2New-v0", 0)):
+        assert REGISTRY[env_id]["new"]
+        path_ok = os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data", REGISTRY[env_id]["data"]))
+        if not path_ok:
+            pytest.skip(f"{REGISTRY[env_id]['data']} not compiled yet")
+        blobs, resets = load_env_data(REGISTRY[env_id]["data"])
+        assert len(blobs) == 16
+        h2m = np.array([float(r["new_h2m"]) for r in resets]); waist = np.array([r["new_waist"] for r in resets])
+        assert (np.abs(h2m[:8] - 0.6) <= 0.1).all() and (np.abs(h2m[8:] - 0.54) <= 0.1).all() and h2m.std() > 0.02
+        assert (np.abs(waist) <= DEG10 + 1e-9).all() and np.abs(waist).max() > 0.5 * DEG10
+        assert all(int(r["new_mode"]) == 1 for r in resets)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ["ScratchItchJacoNew-v0", "ScratchItchPR2New-v0"])
+def test_gpu_new_reset_draws_and_parity(env_id):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from assistive_vr_gym_b200 import make
+    from assistive_vr_gym_b200.compiler.reset import reset_table_bytes, RESET_TABLE_DT
+    from oracle.oracle import Oracle, env_to_f64
+    n = 1024
+    env = make(env_id, num_envs=n, device=0, seed=5)
+    env.sim.enable_debug(True)
+    obs0 = env.reset().cpu().numpy()
+    st = env.get_state(); variants = np.asarray(env.variants)
+    assert len(set(variants.tolist())) == 16                                  # every height / waist variant is in use
+    # human_impairment = 'none' (scratch_itch.py:159)
+    assert (st[:, 96] == 1.0).all() and (st[:, 97] == 1.0).all() and (st[:, 99] == 0.0).all() and (st[:, 100:110] == 0.0).all()
+    tabs = [np.frombuffer(reset_table_bytes(r), dtype=RESET_TABLE_DT)[0] for r in env.reset_data]
+    gaps = st[:, 124 + 14]; attempts = st[:, 124 + 15]
+    for v in range(16):
+        t = tabs[v]; sel = variants == v
+        nh = int(t["n_hum"])
+        q = st[sel][:, t["hum_qidx"][:nh]]
+        lo = np.maximum(t["hum_reset"][:nh] - DEG10, t["hum_lower"][:nh]); hi = np.minimum(t["hum_reset"][:nh] + DEG10, t["hum_upper"][:nh])
+        assert (q >= lo - 1e-6).all() and (q <= hi + 1e-6).all()              # preset + U(-10, 10) degrees, clipped to the limits
+        assert q.std(axis=0).min() > 0.02                                     # ... and actually drawn per episode
+    # collision-free resampling: nearly every environment keeps the 0.01 clearance; the few that exhaust 20 draws keep their best
+    ok = gaps >= 0.01 - 1e-6
+    print(f"{env_id}: clearance kept in {ok.mean() * 100:.1f} % of the resets, draws per reset mean {attempts.mean():.2f} max {attempts.max():.0f}, "
+          f"smallest clearance {gaps.min():.4f}")
+    assert ok.mean() >= 0.95 and attempts.min() >= 1
+    # the bounding-capsule clearance is conservative: the exact distance between the arm's shapes and the shapes the reference
+    # tests (getClosestPoints, scratch_itch.py:219-223) is never smaller
+    oracles = [Oracle(b) for b in env.blobs]
+    rng = np.random.RandomState(0)
+    for e in rng.choice(np.nonzero(ok)[0], 24, replace=False):
+        o = oracles[int(variants[e])]; m = o.model; h = m["header"]
+        rec = env_to_f64(st[e]).copy()
+        nms, ns, nb = int(h["n_mshape"]), int(h["n_shape"]), int(h["n_body"])
+
+        def pose(si):
+            s = m["shapes"][si]
+            if int(s["body"]) < 0:
+                return np.concatenate([s["pos"], s["quat"]]).astype(np.float64)
+            bp = o.body_pose(rec, int(s["body"]))
+            from assistive_vr_gym_b200.compiler import xform as X
+            p, q = X.tf_mul(bp[:3], bp[3:], np.asarray(s["pos"], float), np.asarray(s["quat"], float))
+            return np.concatenate([p, q])
+        arm = [si for si in range(nms) if int(m["shapes"][si]["ref_body"]) == 1]
+        exact = 1e9
+        for sa in arm:
+            for sb in range(ns):
+                s = m["shapes"][sb]
+                rb = int(s["ref_body"])
+                if int(s["type"]) == 5 or not ((rb == 1 and sb >= nms and int(s["ref_link"]) not in (3, 6)) or rb in (0, 3)):
+                    continue
+                hit, out = o.shape_pair(sa, pose(sa), sb, pose(sb), thr=0.05)
+                if hit:
+                    exact = min(exact, float(out[9]))
+        assert exact >= float(gaps[e]) - 1e-4, (e, exact, gaps[e])
+    # the reset observation and a few contact-free steps against the oracle
+    recs = [env_to_f64(st[e]).copy() for e in range(64)]
+    for e in range(64):
+        assert np.abs(oracles[int(variants[e])].reset_obs(recs[e].copy()) - obs0[e]).max() < 1e-5
+    clean = np.ones(64, dtype=bool)
+    for t in range(5):
+        a = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.as_tensor(a, device="cuda"))
+        s2 = env.get_state(); cont, nc = env.sim.get_contacts(); rew = rew.cpu().numpy()
+        for e in range(64):
+            oobs, orew, oinfo, oc = oracles[int(variants[e])].step(recs[e], a[e])
+            if len(oc) or nc[e]:
+                clean[e] = False
+            if clean[e]:
+                assert np.abs(recs[e][:32] - s2[e, :32]).max() < 3e-4 and abs(orew - rew[e]) < 1e-3
+    assert clean.sum() >= 16
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ["FeedingJacoNew-v0", "DrinkingJacoNew-v0", "FeedingPR2New-v0", "DrinkingPR2New-v0"])
+def test_gpu_feeding_drinking_new_reset(env_id):
+    """feeding.py:170-172,235: no impairment, the whole person static (head chain frozen in every environment), every height /
+    waist variant in use; 10 random steps run clean."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from assistive_vr_gym_b200 import make
+    n = 512
+    env = make(env_id, num_envs=n, device=0, seed=9)
+    obs = env.reset()
+    st = env.get_state(); variants = np.asarray(env.variants)
+    assert len(set(variants.tolist())) == 16
+    assert (st[:, 96] == 1.0).all() and (st[:, 97] == 1.0).all() and (st[:, 99] == 0.0).all()
+    frozen = st.view(np.uint32)[:, 175]
+    assert (frozen != 0).all()                                                # head chain frozen everywhere (no tremor, not human-active)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for _ in range(10):
+        obs, rew, done, info = env.step(torch.rand((n, 7), device="cuda", generator=g) * 2 - 1)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert int((info["contact_overflow"] != 0).sum()) == 0
+    env.close()

@@ -67,7 +67,38 @@ def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
     print("wrote BedBathingJaco.npz, BedBathingJacoHuman.npz")
 
 
-def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int, pool: int):
+def draw_new_human(rng: np.random.RandomState, gender: str):
+    """Per-episode draws of the `New` ids that this build bakes per model variant: hipbone_to_mouth_height
+    (scratch_itch.py:158) and the three waist angles (scratch_itch.py:211)."""
+    h2m = rng.uniform(0.6 - 0.1, 0.6 + 0.1) if gender == "male" else rng.uniform(0.54 - 0.1, 0.54 + 0.1)
+    waist = rng.uniform(np.deg2rad(-10), np.deg2rad(10), size=3)
+    return float(h2m), tuple(float(w) for w in waist)
+
+
+def compile_scratch_itch_jaco_new(assets: str, out_dir: str, n_var: int, pool: int):
+    """ScratchItchJacoNew-v0 (__init__.py:45-50): `n_var` model variants per gender, each with its own drawn height and waist
+    pose (the reference draws both per episode); the arm pose is drawn per episode on the device (AvgResetTable.new_mode)."""
+    payload = {}
+    rng = np.random.RandomState(2001)
+    v = 0
+    for gender in ("male", "female"):
+        for k in range(n_var):
+            h2m, waist = draw_new_human(rng, gender)
+            scene = build_scratch_itch(assets, "jaco", gender, new=True, hipbone_to_mouth_height=h2m, waist=waist)
+            blob = scene_to_blob(scene)
+            payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+            rd = build_reset_data(scene, rng, ik_pool=pool)
+            rd.update(new_mode=np.asarray(1), hum_jitter=np.asarray(np.deg2rad(10.0)), new_min_dist=np.asarray(0.01),
+                      new_h2m=np.asarray(h2m), new_waist=np.asarray(waist))
+            for key, a in rd.items():
+                payload[f"reset_{v}_{key}"] = a
+            print("ScratchItchJacoNew", gender, k, "h2m", round(h2m, 3), "waist", np.round(np.rad2deg(waist), 1), scene.info["n_pairs"], "pairs", len(blob), "bytes")
+            v += 1
+    np.savez_compressed(os.path.join(out_dir, "ScratchItchJacoNew.npz"), **payload)
+    print("wrote ScratchItchJacoNew.npz")
+
+
+def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int, pool: int, new: bool = False):
     """<Task>PR2-v0 / <Task>PR2Human-v0 for ScratchItch and BedBathing: per gender `n_base` base poses from the
     task-oriented-configuration search (env.py:486-585 as called at scratch_itch.py:245 / bed_bathing.py:318: left arm,
     tool link 76, random_position 0.5 m, +-30 deg), one model variant each (the PR2's static branches are baked into the
@@ -81,20 +112,25 @@ def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int
     ik_lo = np.where(lower > upper, -2 * np.pi, lower); ik_hi = np.where(lower > upper, 2 * np.pi, upper)
     start_quat = X.quat_from_euler([0, 0, 0])
     payloads = {False: {}, True: {}}
-    name = {"scratch_itch": "ScratchItchPR2", "bed_bathing": "BedBathingPR2"}[task]
+    name = {"scratch_itch": "ScratchItchPR2", "bed_bathing": "BedBathingPR2"}[task] + ("New" if new else "")
+    assert not new or task == "scratch_itch"
+    new_kw = {}
 
     def build(gender, human_control, base):
         if task == "scratch_itch":
-            return build_scratch_itch(assets, "pr2", gender, human_control=human_control, base_xy_yaw=base)
+            return build_scratch_itch(assets, "pr2", gender, human_control=human_control, base_xy_yaw=base, **new_kw)
         return build_bed_bathing(assets, "pr2", gender, human_control=human_control, stage="play", arm_q=settled[gender], base_xy_yaw=base)
 
     v = 0
     for gender in ("male", "female"):
-        probe = build(gender, False, (0.0, 0.0, 0.0))
-        cf = probe.multibodies[1].com_frames(probe.q_human_reset)
-        goals = [cf[9][0], cf[11][0], cf[13][0]]                              # shoulder, elbow, wrist
         pos_offset = [0.1, 0.0, 0.0] if task == "scratch_itch" else [0.0, 0.0, 0.0]
         for k in range(n_base):
+            if new:                                                            # ScratchItchPR2New-v0: the variant's own height and waist pose
+                h2m, waist = draw_new_human(rng, gender)
+                new_kw = dict(new=True, hipbone_to_mouth_height=h2m, waist=waist)
+            probe = build(gender, False, (0.0, 0.0, 0.0))
+            cf = probe.multibodies[1].com_frames(probe.q_human_reset)
+            goals = [cf[9][0], cf[11][0], cf[13][0]]                              # shoulder, elbow, wrist
             if task == "scratch_itch":
                 start_pos = np.array([-0.55, 0, 0.8]) + rng.uniform(-0.05, 0.05, size=3)   # scratch_itch.py:243
             else:
@@ -109,11 +145,14 @@ def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int
                 q, ep, eq = ik_dls(robot, rs["ee_link"], joints, ik_lo, ik_hi, tp, start_quat, rng.uniform(ik_lo, ik_hi), iters=200)
                 if ep < 0.03 and eq < 0.03:
                     starts.append(q)
-            for human_control in (False, True):
+            for human_control in ((False,) if new else (False, True)):
                 scene = build(gender, human_control, (float(xy[0]), float(xy[1]), float(yaw)))
                 blob = scene_to_blob(scene)
                 payloads[human_control][f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
                 rd = build_reset_data_bed_bathing(scene, np.asarray(starts))
+                if new:
+                    rd.update(new_mode=np.asarray(1), hum_jitter=np.asarray(np.deg2rad(10.0)), new_min_dist=np.asarray(0.01),
+                              new_h2m=np.asarray(h2m), new_waist=np.asarray(waist))
                 for key, a in rd.items():
                     payloads[human_control][f"reset_{v}_{key}"] = a
                 print(name, gender, k, "human_control" if human_control else "", "base", np.round(xy, 3), "yaw", round(float(yaw), 3),
@@ -121,50 +160,61 @@ def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int
                       "moving shapes", len(blob), "bytes")
             v += 1
     np.savez_compressed(os.path.join(out_dir, name + ".npz"), **payloads[False])
-    np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
-    print("wrote", name + ".npz,", name + "Human.npz")
+    if not new:
+        np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
+    print("wrote", name + ".npz" + ("" if new else ", " + name + "Human.npz"))
 
 
-def compile_feeding_drinking(assets: str, out_dir: str, task: str, robot: str, n_base: int, attempts: int, pool: int):
+def compile_feeding_drinking(assets: str, out_dir: str, task: str, robot: str, n_base: int, attempts: int, pool: int, new: bool = False):
     """Feeding<Robot>[Human]-v0 / Drinking<Robot>[Human]-v0 (feeding.py:144-331, drinking.py:159-335).  Jaco: fixed base, one
     variant per gender.  PR2 (feeding.py:266-270) and the build-defined Sawyer / Baxter ids: per gender `n_base` base poses from
-    the task-oriented-configuration search with the start target and the mouth as goals, one variant each."""
+    the task-oriented-configuration search with the start target and the mouth as goals, one variant each.
+    `new` = <Task><Robot>New-v0 (__init__.py:206-218,290-302; Jaco and PR2): `n_base` variants per gender, each with its own
+    person (height and waist pose, drawn per episode in the reference: feeding.py:171,233) and, on the PR2, its own base pose."""
     from assistive_vr_gym_b200.compiler.scene_fd import build_feeding_drinking, ROBOT_FD, start_target
     from assistive_vr_gym_b200.compiler.reset_fd import build_reset_data_fd
-    rng = np.random.RandomState(1001)
+    rng = np.random.RandomState(1001 if not new else 3001)
     rec = ROBOT_FD[(task, robot)]
-    name = {"feeding": "Feeding", "drinking": "Drinking"}[task] + {"jaco": "Jaco", "pr2": "PR2", "sawyer": "Sawyer", "baxter": "Baxter"}[robot]
+    name = ({"feeding": "Feeding", "drinking": "Drinking"}[task] + {"jaco": "Jaco", "pr2": "PR2", "sawyer": "Sawyer", "baxter": "Baxter"}[robot]
+            + ("New" if new else ""))
     payloads = {False: {}, True: {}}
     v = 0
     for gender in ("male", "female"):
-        bases = [(0.0, 0.0, 0.0)]
-        if rec["toc"] is not None:
-            probe = build_feeding_drinking(assets, task, robot, gender)
-            hp, hq = probe.multibodies[1].com_frames(probe.q_human_reset)[27]
-            mouth = hp + X.quat_rotate(hq, np.asarray(probe.header["task_f"][19:22], float))     # feeding.py:253-256
-            robot_mb, rs = load_robot(assets, robot, arm="right")
-            centre, quat = start_target(task, robot)
-            bases = []
-            for k in range(n_base):
+        n_var = n_base if (new or rec["toc"] is not None) else 1
+        for k in range(n_var):
+            pkw = {}
+            if new:
+                h2m, waist = draw_new_human(rng, gender)
+                pkw = dict(new=True, hipbone_to_mouth_height=h2m, waist=waist)
+            base = (0.0, 0.0, 0.0)
+            if rec["toc"] is not None:
+                probe = build_feeding_drinking(assets, task, robot, gender, **pkw)
+                hp, hq = probe.multibodies[1].com_frames(probe.q_human_reset)[27]
+                mouth = hp + X.quat_rotate(hq, np.asarray(probe.header["task_f"][19:22], float))     # feeding.py:253-256
+                robot_mb, rs = load_robot(assets, robot, arm="right")
+                centre, quat = start_target(task, robot)
                 sp = centre + rng.uniform(-0.05, 0.05, size=3)
                 xy, yaw, q_start, reached = toc_search(robot_mb, rs["arm"], sp, quat, [mouth, mouth], rng, rec["toc"], attempts=attempts,
                                                        random_position=0.5, ee_link=rs["ee_link"])
-                bases.append((float(xy[0]), float(xy[1]), float(yaw)))
+                base = (float(xy[0]), float(xy[1]), float(yaw))
                 print(name, gender, "base", k, np.round(xy, 3), "yaw", round(float(yaw), 3), "goals reached", reached)
-        for base in bases:
-            for human_control in (False, True):
-                scene = build_feeding_drinking(assets, task, robot, gender, human_control=human_control, base_xy_yaw=base)
+            for human_control in ((False,) if new else (False, True)):
+                scene = build_feeding_drinking(assets, task, robot, gender, human_control=human_control, base_xy_yaw=base, **pkw)
                 blob = scene_to_blob(scene)
                 payloads[human_control][f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
                 rd = build_reset_data_fd(scene, np.random.RandomState(1001 + v), ik_pool=pool)
+                if new:
+                    rd.update(new_mode=np.asarray(1), hum_jitter=np.asarray(0.0), new_min_dist=np.asarray(0.01),
+                              new_h2m=np.asarray(h2m), new_waist=np.asarray(waist))
                 for key, a in rd.items():
                     payloads[human_control][f"reset_{v}_{key}"] = a
                 print(name, gender, "human_control" if human_control else "", scene.info["n_body"], "bodies", scene.info["n_dof"], "dof",
                       scene.info["n_mshape"], "moving shapes", scene.info["n_cshape"], "compound children", scene.info["n_pairs"], "pairs", len(blob), "bytes")
             v += 1
     np.savez_compressed(os.path.join(out_dir, name + ".npz"), **payloads[False])
-    np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
-    print("wrote", name + ".npz,", name + "Human.npz")
+    if not new:
+        np.savez_compressed(os.path.join(out_dir, name + "Human.npz"), **payloads[True])
+    print("wrote", name + ".npz" + ("" if new else ", " + name + "Human.npz"))
 
 
 if __name__ == "__main__":
@@ -182,12 +232,18 @@ if __name__ == "__main__":
         compile_bed_bathing(args.assets, out_dir, args.bases, args.attempts)
     if args.only in ("", "pr2", "scratch_itch_pr2"):
         compile_pr2(args.assets, out_dir, "scratch_itch", args.bases, args.attempts, min(args.pool, 16))
+    if args.only in ("", "new", "scratch_itch_jaco_new"):
+        compile_scratch_itch_jaco_new(args.assets, out_dir, args.bases, min(args.pool, 8))
+    if args.only in ("", "new", "scratch_itch_pr2_new"):
+        compile_pr2(args.assets, out_dir, "scratch_itch", args.bases, args.attempts, 4, new=True)
     if args.only in ("", "pr2", "bed_bathing_pr2"):
         compile_pr2(args.assets, out_dir, "bed_bathing", args.bases, args.attempts, 1)
     for task in ("feeding", "drinking"):
         for robot in ("jaco", "pr2", "sawyer", "baxter"):
             if args.only in ("", "fd", task, f"{task}_{robot}"):
                 compile_feeding_drinking(args.assets, out_dir, task, robot, args.fd_bases, args.attempts, min(args.pool, 8))
+            if robot in ("jaco", "pr2") and args.only in ("", "new", "fd_new", f"{task}_{robot}_new"):
+                compile_feeding_drinking(args.assets, out_dir, task, robot, args.bases, args.attempts, min(args.pool, 8), new=True)
     for human_control in ((False, True) if args.only in ("", "scratch_itch") else ()):
         payload = {}
         rng = np.random.RandomState(1001)              # env.py:53 default seed
