@@ -266,6 +266,7 @@ def read_blob(blob: bytes) -> dict:
     out["frames"] = np.frombuffer(blob, dtype=FRAME_DT, count=int(h["n_frame"]), offset=int(h["off_frame"]))
     out["bps"] = np.frombuffer(blob, dtype=BPS_DT, count=int(h["n_shape"] - h["n_mshape"]), offset=int(h["off_bps"]))
     out["bpm"] = np.frombuffer(blob, dtype="<u4", count=int(h["n_mshape"]), offset=int(h["off_bpm"]))
+    out["bcap"] = np.frombuffer(blob, dtype="<f4", count=8 * int(h["n_shape"]), offset=int(h["off_bcap"])).reshape(-1, 8)
     out["mlp"] = np.frombuffer(blob, dtype="<f4", count=int(h["n_mlp"]), offset=int(h["off_mlp"]))
     out["targets"] = np.frombuffer(blob, dtype="<f4", count=4 * int(h["n_target"]), offset=int(h["off_target"])).reshape(-1, 4)[:, :3]
     return out

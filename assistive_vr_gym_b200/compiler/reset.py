@@ -292,6 +292,8 @@ def reset_table_bytes(rd: dict, ik: dict | None = None) -> bytes:
     t["ik_tol"] = float(rd.get("ik_tol", 0.03))
     if int(rd.get("new_mode", 0)):                             # <Task><Robot>New-v0
         t["new_mode"] = 1; t["hum_jitter"] = float(rd.get("hum_jitter", 0.0)); t["new_min_dist"] = float(rd.get("new_min_dist", 0.01))
+        if "frozen_mask" in rd:                                # BedBathing New: the arm is static during play (bed_bathing.py:271)
+            t["head_mask"] = int(rd["frozen_mask"])
     if fd:                                                     # Feeding / Drinking (compiler/reset_fd.py build_reset_data_fd)
         npart = int(rd["n_particle"])
         t["n_particle"] = npart; t["has_bowl"] = int(rd["has_bowl"]); t["head_mask"] = int(rd["head_mask"])
@@ -530,3 +532,103 @@ def bed_bathing_settle_record(scene: CompiledScene) -> np.ndarray:
     env[E_STRENGTH] = 1.0; env[E_LIMIT_SCALE] = 1.0; env[E_HUMAN_KP] = 0.0
     env.view(np.int32)[E_LIMB_FRAME] = F_SHOULDER
     return env
+
+
+# =====================================================================================================================
+# `New` ids: numpy mirror of the clearance test of avg_reset_new_kernel (bounding capsules; static boxes by their face axes)
+# =====================================================================================================================
+def _seg_seg(p1, q1, p2, q2) -> float:
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f = d1 @ d1, d2 @ d2, d2 @ r
+    if a <= 1e-12 and e <= 1e-12:
+        return float(np.linalg.norm(r))
+    if a <= 1e-12:
+        sc, tc = 0.0, float(np.clip(f / e, 0, 1))
+    else:
+        c = d1 @ r
+        if e <= 1e-12:
+            tc, sc = 0.0, float(np.clip(-c / a, 0, 1))
+        else:
+            b = d1 @ d2
+            den = a * e - b * b
+            sc = float(np.clip((b * f - c * e) / den, 0, 1)) if den > 1e-12 else 0.0
+            tc = (b * sc + f) / e
+            if tc < 0:
+                tc, sc = 0.0, float(np.clip(-c / a, 0, 1))
+            elif tc > 1:
+                tc, sc = 1.0, float(np.clip((b - c) / a, 0, 1))
+    return float(np.linalg.norm((p1 + d1 * sc) - (p2 + d2 * tc)))
+
+
+def body_poses(model: dict, rec: np.ndarray):
+    """World poses of the dynamic bodies of a ModelBlob for the positions in an env record (parents precede children)."""
+    poses = []
+    for B in model["bodies"]:
+        if int(B["jtype"]) == 2:
+            q = rec[E_Q + int(B["qidx"]):E_Q + int(B["qidx"]) + 7].astype(np.float64)
+            poses.append((q[:3], X.quat_normalize(q[3:7]))); continue
+        pp, pq = (np.zeros(3), np.array([0.0, 0, 0, 1])) if int(B["parent"]) < 0 else poses[int(B["parent"])]
+        ax = np.asarray(B["axis"], float); qv = float(rec[E_Q + int(B["qidx"])])
+        jp, jq = np.asarray(B["ta_pos"], float), np.asarray(B["ta_quat"], float)
+        if int(B["jtype"]) == 0:
+            jq = X.quat_mul(jq, X.quat_from_axis_angle(ax, qv))
+        else:
+            jp = jp + X.quat_rotate(jq, ax * qv)
+        p1, q1 = X.tf_mul(jp, jq, np.asarray(B["tb_pos"], float), np.asarray(B["tb_quat"], float))
+        p, q = X.tf_mul(pp, pq, p1, q1)
+        poses.append((p, X.quat_normalize(q)))
+    return poses
+
+
+def new_arm_clearance(model: dict, rec: np.ndarray) -> float:
+    """Smallest bounding-capsule gap between the person's moving (arm) shapes and the shapes the reference tests in the `New`
+    resampling loop (scratch_itch.py:219-223, bed_bathing.py:274-276): the rest of the person except links 3 and 6, the robot,
+    the furniture.  Same rule as avg_reset_new_kernel."""
+    h = model["header"]; sh = model["shapes"]; bc = model["bcap"]
+    nms, ns, nb = int(h["n_mshape"]), int(h["n_shape"]), int(h["n_body"])
+    poses = body_poses(model, rec)
+
+    def capsule(si):
+        k = bc[si].astype(np.float64)
+        if si < nms:
+            S = sh[si]; bp, bq = poses[int(S["body"])]
+            sp, sq = X.tf_mul(bp, bq, np.asarray(S["pos"], float), np.asarray(S["quat"], float))
+            return sp + X.quat_rotate(sq, k[0:3]), sp + X.quat_rotate(sq, k[4:7]), k[3]
+        return k[0:3], k[4:7], k[3]
+    gap = 1e9
+    for sa in range(nms):
+        if int(sh[sa]["ref_body"]) != 1 or int(sh[sa]["body"]) >= nb:
+            continue
+        a0, a1, ra = capsule(sa)
+        for sb in range(ns):
+            S = sh[sb]; rb = int(S["ref_body"])
+            if int(S["type"]) == 5:
+                continue
+            if not ((rb == 1 and sb >= nms and int(S["ref_link"]) not in (3, 6)) or rb in (0, 3)):
+                continue
+            if int(S["type"]) == 2 and sb >= nms:
+                R = X.quat_to_mat(np.asarray(S["quat"], float))
+                l0, l1 = R.T @ (a0 - S["pos"]), R.T @ (a1 - S["pos"])
+                sep = max((min(abs(l0[k]), abs(l1[k])) - float(S["half"][k])) if (l0[k] > 0) == (l1[k] > 0) else -float(S["half"][k]) for k in range(3))
+                gap = min(gap, sep - ra); continue
+            b0, b1, rbb = capsule(sb)
+            gap = min(gap, _seg_seg(a0, a1, b0, b1) - ra - rbb)
+    return gap
+
+
+def new_variant_acceptance(blob: bytes, rd: dict, rng: np.random.RandomState, draws: int = 24) -> float:
+    """Fraction of arm-pose draws (preset + U(-jitter, jitter) per joint, clipped to the limits) that keep the 0.01 clearance for
+    the person of this model variant with the robot at its first start pose: the compile tool drops persons for whom the
+    reference's resampling loop (which redraws the waist pose too, scratch_itch.py:211) would rarely terminate."""
+    from .blob import read_blob
+    model = read_blob(blob)
+    rec = np.zeros(ENV_STRIDE, dtype=np.float64)
+    rec[E_Q + np.asarray(rd["arm_qidx"])] = np.asarray(rd["pool_q"])[0][:len(rd["arm_qidx"])]
+    rec[E_Q + np.asarray(rd["fin_qidx"])] = float(rd.get("fin_open", 1.0))
+    tq = int(rd["tool_qidx"]); rec[E_Q + tq:E_Q + tq + 7] = np.asarray(rd["pool_tool"])[0][:7]
+    ok = 0
+    for _ in range(draws):
+        q = np.clip(np.asarray(rd["hum_reset"]) + rng.uniform(-1, 1, len(rd["hum_reset"])) * float(rd["hum_jitter"]), rd["hum_lower"], rd["hum_upper"])
+        rec[E_Q + np.asarray(rd["hum_qidx"])] = q
+        ok += new_arm_clearance(model, rec) >= float(rd.get("new_min_dist", 0.01))
+    return ok / draws

@@ -589,8 +589,16 @@ def bed_bathing_targets(gender: str, hipbone_to_mouth_height: float):
 
 def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "male", human_control: bool = False,
                       stage: str = "play", arm_q: Optional[List[float]] = None,
-                      base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False) -> CompiledScene:
+                      base_xy_yaw: Tuple[float, float, float] = (0.0, 0.0, 0.0), verbose: bool = False,
+                      new: bool = False, hipbone_to_mouth_height: Optional[float] = None,
+                      waist: Tuple[float, float, float] = (0.0, 0.0, 0.0)) -> CompiledScene:
     """BedBathing<Robot>-v0 (bed_bathing.py:155-358).
+
+    `new` = BedBathing<Robot>New-v0 (`__init__.py:122-134`, bed_bathing.py:183-185,256-279): person of height
+    `hipbone_to_mouth_height` with revolute waist joints at the drawn `waist` angles, the arm at its preset (:269) plus a per-episode
+    draw instead of the settled pose (no 100-step drop in this branch), the whole person static during play.  The arm joints
+    stay in the articulation so that the per-episode pose can be written into the record; they are frozen per environment
+    through AVG_E_FROZEN (mass 0, world_creation.py:157-161) and carry neither motor nor action.
 
     stage 'settle': the world as it is during `for _ in range(100): p.stepSimulation()` (bed_bathing.py:286-292) -- human
     base fixed over the bed, right arm (joints 7..13) dynamic under gravity (0, 0, -1), every human joint with a
@@ -619,7 +627,10 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     else:
         robot.base_pos = np.array([-2.0, -2.0, 0.0]); robot.base_quat = I4.copy()                        # world_creation.py:194
     h2m = 0.6 if gender == "male" else 0.54                                                               # bed_bathing.py:196
-    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=False)
+    if new and hipbone_to_mouth_height is not None:
+        h2m = float(hipbone_to_mouth_height)                                                              # bed_bathing.py:184
+    assert not (new and (human_control or not play))
+    human = create_human(assets_dir, gender, h2m, limit_scale=1.0, static_base=True, new=new)
     human.base_pos = np.array([0.0, 0.0, 0.7]); human.base_quat = X.quat_from_euler([deg(-30), 0, 0])     # bed_bathing.py:203
     human.gravity = np.array([0.0, 0.0, 0.0 if play else -1.0])                                           # :289 / :343
     tool = urdf_to_multibody(os.path.join(assets_dir, "bed_bathing", "wiper.urdf"), REF_TOOL, "wiper")
@@ -647,7 +658,10 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     # -- joint presets and frozen joints ----------------------------------------------------------------------
     q_human = {7: deg(50), 8: deg(-50), 17: deg(-30), 28: deg(-60), 35: deg(-60)}                         # bed_bathing.py:284
     arm = list(range(7, 14))
-    if play:
+    if new:                                                                                               # bed_bathing.py:269-271
+        q_human = {7: deg(20), 8: deg(-20), 10: deg(-45), 20: deg(-45), 28: deg(-60), 35: deg(-60),
+                   0: float(waist[0]), 1: float(waist[1]), 2: float(waist[2])}
+    elif play:
         if arm_q is None:
             arm_q = load_settled_arm_q()[gender]
         if arm_q is None:
@@ -659,6 +673,8 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
             q_human[l.ref_index] = float(np.clip(q_human.get(l.ref_index, 0.0), l.lower, l.upper))       # world_creation.py:169
     controllable = list(range(4, 14))                                                                     # bed_bathing.py:294
     frozen_h = {l.ref_index for l in human.links if (play and not human_control) or l.ref_index not in controllable}   # :285 / :294-295
+    if new:
+        frozen_h = {l.ref_index for l in human.links if l.ref_index not in arm}   # the arm is frozen per environment (AVG_E_FROZEN), not baked
     robot_arm = rs["arm"]
     fingers = rs["fingers"]
     finger_open, tool_pos_offset, tool_euler = TOOL_SETUP[("bed_bathing", robot_type)]                    # bed_bathing.py:320-321,327-328
@@ -671,6 +687,8 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
             elif b.ref_joint in fingers:
                 d.update(kp=0.05, max_force=500.0, init_target=finger_open)                               # world_creation.py:328
                 d["flags"] |= 2
+        elif b.art == 1 and new:
+            pass                                                  # static during play: no motor, no action (frozen through AVG_E_FROZEN)
         elif b.art == 1 and play:                                 # human-active ids: take_step's position motors, env.py:337
             slot = controllable.index(b.ref_joint)
             d.update(kp=0.05, max_force=1.0, human_slot=slot, action=7 + slot)
@@ -733,7 +751,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
     scene = CompiledScene(task="bed_bathing", robot_type=robot_type, gender=gender, human_control=human_control,
                           multibodies=mbs, bodies=bodies, attach=attach, shapes=shapes, n_mshape=n_mshape, pairs=pairs,
                           frames=frames, dofs=dofs, header=header, robot_arm_joints=robot_arm,
-                          human_joints=arm if (human_control or not play) else [], q_human_reset=q_human,
+                          human_joints=arm if (human_control or not play or new) else [], q_human_reset=q_human,
                           tool_offset=(tool_pos_offset, tool_orient_offset))
     scene.mlp_layers = None
     if human_control and play:     # enforce_realistic_human_joint_limits, env.py:343-344,353-387
@@ -741,6 +759,7 @@ def build_bed_bathing(assets_dir: str, robot_type: str = "jaco", gender: str = "
         scene.mlp_layers = load_keras_dense_stack(os.path.join(assets_dir, 'realistic_arm_limits_model.h5'))
     scene.targets = (up, fo)
     scene.finger_open = finger_open; scene.robot_spec = rs
+    scene.frozen_mask = sum(1 << i for i, b in enumerate(bodies) if b.art == 1) if new else 0
     scene.info = dict(hull_errors=dict(hull_errors), n_pairs=len(pairs), n_shapes=len(shapes), n_mshape=n_mshape, n_target=n_target)
     if verbose:
         print(scene.info)

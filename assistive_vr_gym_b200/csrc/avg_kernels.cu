@@ -3177,6 +3177,7 @@ avg_reset_kernel(AvgResetArgs r) {
     rec[AVG_E_STRENGTH] = strength; rec[AVG_E_LIMIT_SCALE] = limit_scale;
     rec[AVG_E_TREMOR_ON] = impairment == 3 ? 1.0f : 0.0f;
     rec[AVG_E_HUMAN_KP] = (T->human_control || impairment == 3) ? 0.05f : 0.01f;                 // scratch_itch.py:45 / :231
+    if (T->new_mode && T->head_mask) reinterpret_cast<uint32_t*>(rec)[AVG_E_FROZEN] = T->head_mask;   // BedBathing New: the arm is static during play (bed_bathing.py:271)
     r.variant[e] = v;
     int* scr_i = reinterpret_cast<int*>(r.scratch + (size_t)e * AVG_S_STRIDE);
     scr_i[AVG_S_NSEP] = 0; scr_i[AVG_S_NC] = 0; scr_i[AVG_S_NCS] = 0; scr_i[AVG_S_NQ] = 0;    // no certificates / contacts carried over
@@ -3436,7 +3437,8 @@ avg_reset_check_kernel(AvgResetArgs r) {
 // preset plus U(-10, 10) degrees, redrawn until the arm keeps new_min_dist (0.01) from the rest of the person (links other than
 // the arm itself, the chest 3 and the shoulder 6), from the robot and from the furniture.  The reference measures those
 // distances with getClosestPoints; here every shape is represented by its bounding capsule (exact for the capsules and spheres
-// the person is made of, conservative for hulls: a pose may be redrawn that the reference would have kept, never the reverse).
+// the person is made of, conservative for hulls; static boxes use their face axes: a pose may be redrawn that the reference would
+// have kept, never the reverse).
 // One thread per environment, after the start pose of the robot is known (avg_reset_ik_kernel); at most 20 draws, the last kept.
 namespace {
 __device__ __forceinline__ float capsule_gap(V3 a0, V3 a1, float ra, V3 b0, V3 b1, float rb) {
@@ -3506,6 +3508,20 @@ avg_reset_new_kernel(AvgResetArgs r) {
                 if (rb_ == AVG_REF_HUMAN) other = sj >= nms && S->ref_link != 3 && S->ref_link != 6;       // scratch_itch.py:219
                 else if (rb_ == AVG_REF_ROBOT || rb_ == AVG_REF_FURNITURE) other = true;                    // :221-223
                 if (!other) continue;
+                if (S->type == AVG_SHAPE_BOX && sj >= nms) {
+                    // a flat box (the mattress) has a hopeless bounding capsule: lower bound from its face axes instead -- the
+                    // largest separation of the arm's segment from a pair of faces (exact when the closest point lies on a face)
+                    const Q4 bq_ = ldq(S->quat); const V3 bc = ld3(S->pos);
+                    const V3 l0 = qrot_inv(bq_, a0 - bc), l1 = qrot_inv(bq_, a1 - bc);
+                    const float p0[3] = {l0.x, l0.y, l0.z}, p1[3] = {l1.x, l1.y, l1.z};
+                    float sep = -3.0e38f;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const float sk = (p0[ax] > 0.0f) == (p1[ax] > 0.0f) ? fminf(fabsf(p0[ax]), fabsf(p1[ax])) - S->half[ax] : -S->half[ax];
+                        sep = fmaxf(sep, sk);
+                    }
+                    gap = fminf(gap, sep - ra);
+                    continue;
+                }
                 V3 b0, b1; float rbb; world_capsule(sj, b0, b1, rbb);
                 gap = fminf(gap, capsule_gap(a0, a1, ra, b0, b1, rbb));
             }

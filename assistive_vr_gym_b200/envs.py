@@ -45,6 +45,8 @@ for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
 # per gender), no impairment, the arm pose drawn per episode on the device until it is collision-free (avg_reset_new_kernel)
 REGISTRY["ScratchItchJacoNew-v0"] = dict(task="scratch_itch", robot="jaco", human_control=False, data="ScratchItchJacoNew.npz", new=True)
 REGISTRY["ScratchItchPR2New-v0"] = dict(task="scratch_itch", robot="pr2", human_control=False, data="ScratchItchPR2New.npz", new=True)
+REGISTRY["BedBathingJacoNew-v0"] = dict(task="bed_bathing", robot="jaco", human_control=False, data="BedBathingJacoNew.npz", new=True)
+REGISTRY["BedBathingPR2New-v0"] = dict(task="bed_bathing", robot="pr2", human_control=False, data="BedBathingPR2New.npz", new=True)
 # Feeding / Drinking `New` ids (__init__.py:206-218,290-302): the whole person is static in these (feeding.py:235), so height and
 # waist pose per variant are all there is to them besides human_impairment = 'none'
 for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):

@@ -51,7 +51,7 @@ def test_new_scene_bakes_the_waist_pose():
 
 def test_new_ids_are_registered_with_variant_draws():
     from assistive_vr_gym_b200.envs import REGISTRY, load_env_data
-    for env_id, base in (("ScratchItchJacoNew-v0", 0), ("ScratchItchPR2New-v0", 0), ("FeedingJacoNew-v0", 0), ("FeedingPR2New-v0", 0),
+    for env_id, base in (("ScratchItchJacoNew-v0", 0), ("ScratchItchPR2New-v0", 0), ("FeedingJacoNew-v0", 0), ("FeedingPR2New-v0", 0), ("BedBathingJacoNew-v0", 0), ("BedBathingPR2New-v0", 0),
                          ("DrinkingJacoNew-v0", 0), ("DrinkingPR2New-v0", 0)):
         assert REGISTRY[env_id]["new"]
         path_ok = os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assistive_vr_gym_b200", "data", REGISTRY[env_id]["data"]))
@@ -66,7 +66,7 @@ def test_new_ids_are_registered_with_variant_draws():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env_id", ["ScratchItchJacoNew-v0", "ScratchItchPR2New-v0"])
+@pytest.mark.parametrize("env_id", ["ScratchItchJacoNew-v0", "ScratchItchPR2New-v0", "BedBathingJacoNew-v0", "BedBathingPR2New-v0"])
 def test_gpu_new_reset_draws_and_parity(env_id):
     import torch
     if not torch.cuda.is_available():
@@ -90,7 +90,7 @@ def test_gpu_new_reset_draws_and_parity(env_id):
         q = st[sel][:, t["hum_qidx"][:nh]]
         lo = np.maximum(t["hum_reset"][:nh] - DEG10, t["hum_lower"][:nh]); hi = np.minimum(t["hum_reset"][:nh] + DEG10, t["hum_upper"][:nh])
         assert (q >= lo - 1e-6).all() and (q <= hi + 1e-6).all()              # preset + U(-10, 10) degrees, clipped to the limits
-        assert q.std(axis=0).min() > 0.02                                     # ... and actually drawn per episode
+        assert q.std(axis=0).min() > 0.005 and q.std(axis=0).max() > 0.05     # ... and actually drawn per episode (the rejection narrows some joints)
     # collision-free resampling: nearly every environment keeps the 0.01 clearance; the few that exhaust 20 draws keep their best
     ok = gaps >= 0.01 - 1e-6
     print(f"{env_id}: clearance kept in {ok.mean() * 100:.1f} % of the resets, draws per reset mean {attempts.mean():.2f} max {attempts.max():.0f}, "

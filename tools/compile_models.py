@@ -20,6 +20,47 @@ from assistive_vr_gym_b200.compiler.scene import (build_scratch_itch, build_bed_
                                                   urdf_to_multibody, load_robot)
 
 
+def compile_bed_bathing_new(assets: str, out_dir: str, robot_type: str, n_var: int, attempts: int):
+    """BedBathing<Robot>New-v0 (__init__.py:122-134): `n_var` variants per gender, each with its own person (height, waist pose)
+    and robot base pose (task-oriented-configuration search against that person's shoulder / elbow / wrist at the preset arm
+    pose, bed_bathing.py:303-318).  No settle stage: the New branch starts from the preset arm pose (bed_bathing.py:269)."""
+    rng = np.random.RandomState(4001)
+    payload = {}
+    name = "BedBathing" + {"jaco": "Jaco", "pr2": "PR2"}[robot_type] + "New"
+    if robot_type == "jaco":
+        robot = urdf_to_multibody(os.path.join(assets, "jaco", "j2s7s300_gym.urdf"), 0, "jaco")
+    else:
+        robot, rs = load_robot(assets, "pr2")
+    v = 0
+    for gender in ("male", "female"):
+        for k in range(n_var):
+            h2m, waist, pkw, acc = draw_feasible_person(rng, gender, lambda kw: build_bed_bathing(assets, robot_type, gender, stage="play", **kw),
+                                                        lambda sc: build_reset_data_bed_bathing(sc, np.zeros(7)))
+            probe = build_bed_bathing(assets, robot_type, gender, stage="play", **pkw)
+            cf = probe.multibodies[1].com_frames(probe.q_human_reset)
+            goals = [cf[9][0], cf[11][0], cf[13][0]]
+            if robot_type == "jaco":
+                xy, yaw, q_start, reached = toc_search_jaco(robot, [1, 2, 3, 4, 5, 6, 7], np.array([-0.5, -0.1, 1.0]),
+                                                            X.quat_from_euler([0, np.pi / 2.0, 0]), goals, rng, [0.1, 0.55, 0.6], attempts=attempts)
+            else:
+                xy, yaw, q_start, reached = toc_search(robot, rs["arm"], np.array([-0.5, -0.1, 1.0]), X.quat_from_euler([0, 0, 0]), goals, rng,
+                                                       [0.0, 0.0, 0.0], attempts=attempts, random_position=0.5, ee_link=rs["ee_link"])
+            scene = build_bed_bathing(assets, robot_type, gender, stage="play", base_xy_yaw=(float(xy[0]), float(xy[1]), float(yaw)), **pkw)
+            blob = scene_to_blob(scene)
+            payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
+            rd = build_reset_data_bed_bathing(scene, q_start)
+            rd.update(new_mode=np.asarray(1), hum_jitter=np.asarray(np.deg2rad(10.0)), new_min_dist=np.asarray(0.01),
+                      new_h2m=np.asarray(h2m), new_waist=np.asarray(waist), frozen_mask=np.asarray(scene.frozen_mask))
+            for key, a in rd.items():
+                payload[f"reset_{v}_{key}"] = a
+            print(name, gender, k, "h2m", round(h2m, 3), "waist", np.round(np.rad2deg(waist), 1), "arm draws accepted", round(acc, 2),
+                  "base", np.round(xy, 3), "yaw", round(float(yaw), 3), "goals reached", reached,
+                  scene.info["n_pairs"], "pairs", scene.info["n_target"], "targets", len(blob), "bytes")
+            v += 1
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **payload)
+    print("wrote", name + ".npz")
+
+
 def compile_bed_bathing(assets: str, out_dir: str, n_base: int, attempts: int):
     """BedBathingJaco-v0 in two stages.  Stage 1 (always): the 'settle' worlds of both genders + their start records ->
     BedBathingJacoSettle.npz; tools/settle_bed_bathing.py runs them for 100 sub-steps on a GPU and writes the settled
@@ -75,6 +116,23 @@ def draw_new_human(rng: np.random.RandomState, gender: str):
     return float(h2m), tuple(float(w) for w in waist)
 
 
+def draw_feasible_person(rng, gender, build_probe, reset_data_of, min_accept: float = 0.25):
+    """Draw (height, waist pose) until the per-episode arm resampling has a fair chance for that person: the reference redraws the
+    waist together with the arm until the pose is collision-free (scratch_itch.py:198-223), so persons whose arm cannot be placed
+    never appear in its episodes.  build_probe(pkw) -> scene, reset_data_of(scene) -> reset data with the robot at a start pose."""
+    from assistive_vr_gym_b200.compiler.reset import new_variant_acceptance
+    for attempt in range(40):
+        h2m, waist = draw_new_human(rng, gender)
+        pkw = dict(new=True, hipbone_to_mouth_height=h2m, waist=waist)
+        scene = build_probe(pkw)
+        rd = reset_data_of(scene)
+        rd.update(hum_jitter=np.deg2rad(10.0), new_min_dist=0.01)
+        acc = new_variant_acceptance(scene_to_blob(scene), rd, np.random.RandomState(attempt))
+        if acc >= min_accept:
+            return h2m, waist, pkw, acc
+    raise RuntimeError("no feasible person drawn")
+
+
 def compile_scratch_itch_jaco_new(assets: str, out_dir: str, n_var: int, pool: int):
     """ScratchItchJacoNew-v0 (__init__.py:45-50): `n_var` model variants per gender, each with its own drawn height and waist
     pose (the reference draws both per episode); the arm pose is drawn per episode on the device (AvgResetTable.new_mode)."""
@@ -83,8 +141,9 @@ def compile_scratch_itch_jaco_new(assets: str, out_dir: str, n_var: int, pool: i
     v = 0
     for gender in ("male", "female"):
         for k in range(n_var):
-            h2m, waist = draw_new_human(rng, gender)
-            scene = build_scratch_itch(assets, "jaco", gender, new=True, hipbone_to_mouth_height=h2m, waist=waist)
+            h2m, waist, pkw, acc = draw_feasible_person(rng, gender, lambda kw: build_scratch_itch(assets, "jaco", gender, **kw),
+                                                        lambda sc: build_reset_data(sc, np.random.RandomState(7), ik_pool=1))
+            scene = build_scratch_itch(assets, "jaco", gender, **pkw)
             blob = scene_to_blob(scene)
             payload[f"blob_{v}"] = np.frombuffer(blob, dtype=np.uint8)
             rd = build_reset_data(scene, rng, ik_pool=pool)
@@ -92,7 +151,8 @@ def compile_scratch_itch_jaco_new(assets: str, out_dir: str, n_var: int, pool: i
                       new_h2m=np.asarray(h2m), new_waist=np.asarray(waist))
             for key, a in rd.items():
                 payload[f"reset_{v}_{key}"] = a
-            print("ScratchItchJacoNew", gender, k, "h2m", round(h2m, 3), "waist", np.round(np.rad2deg(waist), 1), scene.info["n_pairs"], "pairs", len(blob), "bytes")
+            print("ScratchItchJacoNew", gender, k, "h2m", round(h2m, 3), "waist", np.round(np.rad2deg(waist), 1), "arm draws accepted", round(acc, 2),
+                  scene.info["n_pairs"], "pairs", len(blob), "bytes")
             v += 1
     np.savez_compressed(os.path.join(out_dir, "ScratchItchJacoNew.npz"), **payload)
     print("wrote ScratchItchJacoNew.npz")
@@ -126,8 +186,10 @@ def compile_pr2(assets: str, out_dir: str, task: str, n_base: int, attempts: int
         pos_offset = [0.1, 0.0, 0.0] if task == "scratch_itch" else [0.0, 0.0, 0.0]
         for k in range(n_base):
             if new:                                                            # ScratchItchPR2New-v0: the variant's own height and waist pose
-                h2m, waist = draw_new_human(rng, gender)
-                new_kw = dict(new=True, hipbone_to_mouth_height=h2m, waist=waist)
+                h2m, waist, new_kw, acc = draw_feasible_person(
+                    rng, gender, lambda kw: build_scratch_itch(assets, "pr2", gender, **kw),
+                    lambda sc: build_reset_data_bed_bathing(sc, np.zeros(7)))
+                print(name, gender, k, "h2m", round(h2m, 3), "waist", np.round(np.rad2deg(waist), 1), "arm draws accepted", round(acc, 2))
             probe = build(gender, False, (0.0, 0.0, 0.0))
             cf = probe.multibodies[1].com_frames(probe.q_human_reset)
             goals = [cf[9][0], cf[11][0], cf[13][0]]                              # shoulder, elbow, wrist
@@ -236,6 +298,9 @@ if __name__ == "__main__":
         compile_scratch_itch_jaco_new(args.assets, out_dir, args.bases, min(args.pool, 8))
     if args.only in ("", "new", "scratch_itch_pr2_new"):
         compile_pr2(args.assets, out_dir, "scratch_itch", args.bases, args.attempts, 4, new=True)
+    for robot in ("jaco", "pr2"):
+        if args.only in ("", "new", f"bed_bathing_{robot}_new"):
+            compile_bed_bathing_new(args.assets, out_dir, robot, args.bases, args.attempts)
     if args.only in ("", "pr2", "bed_bathing_pr2"):
         compile_pr2(args.assets, out_dir, "bed_bathing", args.bases, args.attempts, 1)
     for task in ("feeding", "drinking"):
