@@ -55,8 +55,10 @@ for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
 _OBS_LEN = {"scratch_itch": (30, 34), "bed_bathing": (24, 28), "feeding": (25, 23), "drinking": (25, 23)}      # (robot, human) widths: scratch_itch.py:19, bed_bathing.py:19, feeding.py:18
 _ACT_HUMAN = {"scratch_itch": 10, "bed_bathing": 10, "feeding": 4, "drinking": 4}                              # scratch_itch.py:19, feeding.py:18
 SETTLE_STEPS = 100           # feeding.py:318-320
-_ALL_REFERENCE_IDS = [f"{t}{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")
-                      for r in ("PR2", "Jaco") for v in ("", "Human", "New")]
+# every non-VR id of the reference is registered above; its VR ids (`<Task>VR<Robot>[Human|New]-v0`, __init__.py:52-89 etc.) drive a
+# headset and are out of scope (north_star)
+_VR_REFERENCE_IDS = [f"{t}VR{r}{v}-v0" for t in ("ScratchItch", "BedBathing", "Feeding", "Drinking")
+                     for r in ("PR2", "Jaco") for v in ("", "Human", "New")]
 
 
 class Box:
@@ -97,9 +99,9 @@ class BatchedAssistiveEnv:
     def __init__(self, env_id: str, num_envs: int = 1, device: int = 0, seed: int = 1001, auto_reset: bool = False,
                  device_ik: bool = True, cuda_graph: bool = False):
         if env_id not in REGISTRY:
-            if env_id in _ALL_REFERENCE_IDS:
-                raise NotImplementedError(f"{env_id}: registered by the reference but not compiled yet "
-                                          f"(built so far: {sorted(REGISTRY)})")
+            if env_id in _VR_REFERENCE_IDS:
+                raise NotImplementedError(f"{env_id}: the reference's VR / headset ids are out of scope of this simulator "
+                                          f"(built: {sorted(REGISTRY)})")
             raise KeyError(f"unknown environment id {env_id}")
         import torch
         if not torch.cuda.is_available():

@@ -119,7 +119,7 @@ def test_time_limit(torch_cuda):
 def test_unknown_ids():
     from assistive_vr_gym_b200 import make
     with pytest.raises(NotImplementedError):
-        make("FeedingPR2New-v0", num_envs=1)                              # registered by the reference, not compiled (the `New` ids)
+        make("ScratchItchVRJaco-v0", num_envs=1)                          # registered by the reference, out of scope (VR / headset ids)
     with pytest.raises(KeyError):
         make("NoSuchEnv-v0", num_envs=1)
 
