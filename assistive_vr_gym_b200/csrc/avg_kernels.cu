@@ -40,7 +40,7 @@
 #define AVG_WPB_COLLIDE 4         /* warps (= environments) per block of the collide kernel */
 #endif
 #ifndef AVG_WPB_DYN
-#define AVG_WPB_DYN 4             /* warps per block of the dynamics kernel */
+#define AVG_WPB_DYN 8             /* warps per block of the dynamics kernel */
 #endif
 #ifndef AVG_OCC_COLLIDE
 #define AVG_OCC_COLLIDE (20 / AVG_WPB_COLLIDE)
@@ -56,6 +56,9 @@
 #endif
 #ifndef AVG_LIM_SKIP
 #define AVG_LIM_SKIP 1            /* solver: sweep only the block slots in which some articulation has an active limit row */
+#endif
+#ifndef AVG_OCC_NARROW
+#define AVG_OCC_NARROW 6          /* blocks of 128 threads per SM the narrowphase kernel is compiled for */
 #endif
 #ifndef AVG_NARROW_WARPS
 #define AVG_NARROW_WARPS (148 * 12 * 2)   /* narrowphase: warps a short work queue is spread over (two waves at 12 warps per SM) */
@@ -151,6 +154,7 @@ struct __align__(16) SmSolve {
     float4 um[4][kMaxBlk];                 // motor row of dof block_start[g] + t: {target, 1/diag, hi (lo = -hi), diag}; zero when absent
     float4 ul[4][kMaxBlk];                 // limit row, same indexing: {target, 1/diag, diag, sign}; 1/diag = 0 when not violated
     float4 rd[kMaxDense][2];               // dense rows: {target, 1/diag, lo, hi}, {diag, mu, index, normal row}
+    float lam[kMaxDense];                  // accumulated impulse of the contact rows (every lane writes the same value and reads back its own write)
 };
 struct __align__(16) SmEpi {
     float env[AVG_ENV_STRIDE];
@@ -348,6 +352,33 @@ __device__ __noinline__ V3 support_feature(const WShape& w, V3 d, int& count) {
     }
     count = cnt;
     return w.p + mmul(w.R, r);
+}
+
+// The same for one shape held by EVERY lane of a converged warp (the broadcast copies of sat_served): hull vertices are spread
+// over the lanes, maximum / count / centroid by shuffles; every lane returns the result.  The centroid is summed lane by lane and
+// then over the lanes instead of in vertex order: the same feature, rounding differences of 1e-7 of a hull's size.
+__device__ __noinline__ V3 support_feature_warp(const WShape& w, V3 d, int& count, int lane) {
+    const AvgShape* S = w.s;
+    if (S->type != AVG_SHAPE_HULL) return support_feature(w, d, count);
+    const V3 l = mtmul(w.R, d);
+    const float4* v = reinterpret_cast<const float4*>(w.verts);
+    const int nv = S->vert_cnt;
+    float bd = -3.0e38f;
+    for (int i = lane; i < nv; i += 32) { const float4 p = __ldg(v + i); bd = fmaxf(bd, fmaf(l.x, p.x, fmaf(l.y, p.y, l.z * p.z))); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bd = fmaxf(bd, __shfl_xor_sync(AVG_FULL, bd, o));
+    V3 acc = mk3(0, 0, 0); int cnt = 0;
+    for (int i = lane; i < nv; i += 32) {
+        const float4 p = __ldg(v + i);
+        if (fmaf(l.x, p.x, fmaf(l.y, p.y, l.z * p.z)) >= bd - kFeatTol) { acc = acc + mk3(p.x, p.y, p.z); cnt++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(AVG_FULL, acc.x, o); acc.y += __shfl_xor_sync(AVG_FULL, acc.y, o); acc.z += __shfl_xor_sync(AVG_FULL, acc.z, o);
+        cnt += __shfl_xor_sync(AVG_FULL, cnt, o);
+    }
+    count = cnt;
+    return w.p + mmul(w.R, acc * (1.0f / (float)max(cnt, 1)));
 }
 
 struct Simplex { V3 w[4], a[4], b[4]; float lam[4]; int n; };
@@ -589,14 +620,15 @@ __device__ __noinline__ void sat_served(const WShape& A, const WShape& B, bool n
         const int win = __ffs(__ballot_sync(AVG_FULL, bk == wk && wk != 0x7fffffff)) - 1;
         const int w = win < 0 ? 0 : win;
         const V3 n = shfl3(bn, w);
+        int ca = 1, cb = 1;
+        V3 fa = mk3(0, 0, 0), fb = fa;
+        if (win >= 0) { fa = support_feature_warp(a, -n, ca, lane); fb = support_feature_warp(b, n, cb, lane); }   // a, b: the requester's shapes in every lane
         if (lane == src) {
             // witness on A's core: from the round shape when there is one, otherwise from the smaller supporting feature
             // (sat_axis() of the oracle)
             const bool ra = A.s->type == AVG_SHAPE_SPHERE || A.s->type == AVG_SHAPE_CAPSULE;
             const bool rb = B.s->type == AVG_SHAPE_SPHERE || B.s->type == AVG_SHAPE_CAPSULE;
             if (win >= 0) {
-                int ca, cb;
-                const V3 fa = support_feature(A, -n, ca), fb = support_feature(B, n, cb);
                 best_out = wbest; bn_out = n;
                 bpa_out = (rb && !ra) ? fb - n * wbest : (ra ? fa : (ca <= cb ? fa : fb - n * wbest));
             }
@@ -1105,7 +1137,11 @@ __device__ __forceinline__ void np_load_shape(const KM& m, const float* scr, int
 }
 }  // namespace
 
-__global__ void __launch_bounds__(128)
+// OCC = blocks per SM the instance is compiled for: 3 (151 registers, nothing spilled) for small batches, where the step waits
+// for the slowest warp of this kernel, AVG_OCC_NARROW (85 registers, a few spills) for large ones, where more resident warps
+// hide the latency of the lockstep GJK (+4 % on an in-contact policy rollout at 196608 environments).
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC)
 avg_narrow_kernel(AvgStepArgs a) {
     // one THREAD per work item; the 32 items of a warp advance through the certificate test and the GJK iterations in
     // lockstep so that hull support scans can be served by the whole warp (support_any)
@@ -1763,7 +1799,7 @@ struct __align__(16) SmPartT {
     uint16_t order[NPC];                   // contact indices sorted by round
     uint16_t round_of[NPC];
     uint16_t rstart[NPC + 2];              // first entry of each round in `order`
-    uint16_t last[66];                     // greedy schedule: first round a new row of particle p may use
+    unsigned long long used[64];           // greedy colouring: rounds already taken by a row of particle p
     uint8_t fill[NPC + 2];
 };
 using SmPartSmall = SmPartT<8, 64>;
@@ -1908,21 +1944,25 @@ __device__ int particles_prepare(const KM& m, SP& sp, const AvgStepArgs& a, int 
     if (nc > SP::kNPC) { overflow |= 8; nc = SP::kNPC; }
     if (ps_i[AVG_PS_OVERFLOW]) overflow |= ps_i[AVG_PS_OVERFLOW];
     __syncwarp();
-    // greedy round schedule (serial: ~20 instructions per contact, once per internal step)
-    for (int i = lane; i < 66; i += 32) sp.last[i] = 0;
+    // round schedule = greedy colouring of the contacts in canonical order (serial: ~15 instructions per contact, once per
+    // internal step): a contact takes the lowest round not yet used by a contact of its particle(s), at most 32 per round.
+    // Rows of one round share no particle, so they commute; the oracle sweeps in the same order (particle_row_order).
+    for (int i = lane; i < 64; i += 32) sp.used[i] = 0ull;
     for (int i = lane; i < nc + 2; i += 32) sp.fill[i] = 0;
     __syncwarp();
     int nr = 0;
     if (lane == 0) {
+        unsigned long long full = 0ull;
         for (int c = 0; c < nc; ++c) {
             const int pk = __float_as_int(rec[AVG_PS_REC_STRIDE * c + 13]);
             const int p = pk & 0xff, q = (pk >> 8) & 0xff, kind = pk >> 16;
-            int r = sp.last[p];
-            if (kind == 1) r = max(r, (int)sp.last[q]);
-            while (sp.fill[r] >= 32) ++r;
-            sp.round_of[c] = (uint16_t)r; sp.fill[r]++;
-            sp.last[p] = (uint16_t)(r + 1);
-            if (kind == 1) sp.last[q] = (uint16_t)(r + 1);
+            const unsigned long long mk = sp.used[p] | (kind == 1 ? sp.used[q] : 0ull) | full;
+            int r = 63;
+            if (mk != ~0ull) r = __ffsll((long long)~mk) - 1; else overflow |= 8;
+            sp.round_of[c] = (uint16_t)r;
+            sp.used[p] |= 1ull << r;
+            if (kind == 1) sp.used[q] |= 1ull << r;
+            if (++sp.fill[r] >= 32) full |= 1ull << r;
             nr = max(nr, r + 1);
         }
         int acc = 0;
@@ -2122,7 +2162,9 @@ avg_solve_kernel(AvgStepArgs a) {
     //      block hold all-zero rows (1/diag = 0), which makes their delta exactly 0.
     //      Dense rows follow in strict order: the six weld rows unrolled with J, W and impulses in registers, then
     //      the contact rows (rare) from shared memory / the arena with the impulse of row d in lane d.
-    float dv = 0.0f, lamL = 0.0f, lamD0 = 0.0f, lamD1 = 0.0f, lamD2 = 0.0f;      // impulse of dense row d: lane d & 31, register d >> 5
+    float dv = 0.0f, lamL = 0.0f;
+    for (int d = 6 + lane; d < ndense; d += 32) s.lam[d] = 0.0f;                 // impulses of the contact rows live in shared memory
+    __syncwarp();
     // particles (Feeding / Drinking): records, schedule and unconstrained velocities for this internal step
     using SP = typename std::conditional<PART == 2, SmPartLarge, SmPartSmall>::type;
     SP* spp = PART ? reinterpret_cast<SP*>(smem_raw + sizeof(SmSolve)) : nullptr;
@@ -2177,8 +2219,14 @@ avg_solve_kernel(AvgStepArgs a) {
             dv = fmaf(s.W[d][lane], delta, dv);
             resid = fmaxf(resid, fabsf(delta) * ra.z);
         }
-        auto lam_get = [&](int d) { return __shfl_sync(AVG_FULL, d < 32 ? lamD0 : (d < 64 ? lamD1 : lamD2), d & 31); };
-        auto lam_set = [&](int d, float v) { if (lane == (d & 31)) { if (d < 32) lamD0 = v; else if (d < 64) lamD1 = v; else lamD2 = v; } };
+        // every lane holds the same jdv (an exact integer sum) and the same row data, hence the same impulse: all lanes store it
+        // to the same word and each reads back what it wrote itself -- no owner lane, no shuffle, no barrier
+        auto lam_get = [&](int d) { return s.lam[d]; };
+#if AVG_REDUX == 0
+        auto lam_set = [&](int d, float v) { s.lam[d] = __shfl_sync(AVG_FULL, v, 0); };    // float butterflies may differ in the last bit between lanes
+#else
+        auto lam_set = [&](int d, float v) { s.lam[d] = v; };
+#endif
 #pragma unroll 1
         for (int d = 6; d < nfr; ++d) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
@@ -2224,10 +2272,7 @@ avg_solve_kernel(AvgStepArgs a) {
     }
 
     // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
-    for (int c = 0; c < nc; ++c) {
-        const int d = first_contact_row + c;
-        if (lane == (d & 31)) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c + 12] = d < 32 ? lamD0 : (d < 64 ? lamD1 : lamD2);
-    }
+    for (int c = lane; c < nc; c += 32) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c + 12] = s.lam[first_contact_row + c];
     if (lane == 0) scr_i[AVG_S_ITERS] += iters;
     if (PART) particles_finish(m, *spp, a, e, lane, dt, npc, p_overflow);
 
@@ -3684,7 +3729,8 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
     avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
     mark(1);
     if (part) { avg_pcollide_kernel<<<grid(kWpbPCol), 32 * kWpbPCol, sizeof(SmPCol) * kWpbPCol, stream>>>(a); mark(6); }
-    avg_narrow_kernel<<<np_grid, 128, 0, stream>>>(a);
+    if (n_range > 16384) avg_narrow_kernel<AVG_OCC_NARROW><<<np_grid, 128, 0, stream>>>(a);
+    else avg_narrow_kernel<3><<<np_grid, 128, 0, stream>>>(a);
     mark(5);
     if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
     else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);

@@ -828,6 +828,32 @@ done:
     return nc;
 }
 
+/* Order of the particle rows inside a block of the Gauss-Seidel sweep.  Bullet's order is the order of its overlapping-pair
+ * cache (hash order: not reproducible from the reference, and of no physical meaning), so the order is build-defined, and it
+ * is chosen so that the device can sweep many rows at once: the contacts, taken in canonical order (particle_collide), are
+ * coloured greedily -- each gets the lowest colour not yet used by a contact of its particle(s), at most 32 contacts per
+ * colour -- and the sweep runs colour by colour, canonical order inside a colour.  Contacts of one colour share no particle,
+ * so they commute.  The kernels compute the same colouring (particles_prepare in avg_kernels.cu). */
+static void particle_row_order(PContact* pcs, int npc, int* overflow) {
+    unsigned long long used[AVG_MAX_PARTICLE]; memset(used, 0, sizeof(used));
+    unsigned long long full = 0;
+    int fill[64]; memset(fill, 0, sizeof(fill));
+    int* colour = (int*)malloc(sizeof(int) * npc);
+    for (int c = 0; c < npc; ++c) {
+        unsigned long long mk = used[pcs[c].p] | (pcs[c].q >= 0 ? used[pcs[c].q] : 0ull) | full;
+        int r = 63;
+        if (mk != ~0ull) { r = 0; while ((mk >> r) & 1ull) ++r; } else *overflow |= 8;
+        colour[c] = r;
+        used[pcs[c].p] |= 1ull << r; if (pcs[c].q >= 0) used[pcs[c].q] |= 1ull << r;
+        if (++fill[r] >= 32) full |= 1ull << r;
+    }
+    PContact* tmp = (PContact*)malloc(sizeof(PContact) * npc);
+    int n = 0;
+    for (int r = 0; r < 64; ++r) for (int c = 0; c < npc; ++c) if (colour[c] == r) tmp[n++] = pcs[c];
+    memcpy(pcs, tmp, sizeof(PContact) * npc);
+    free(tmp); free(colour);
+}
+
 static v3 plane_space1(v3 n) {                       /* btPlaneSpace1 */
     if (fabs(n.z) > 0.7071067811865476) { double a = n.y * n.y + n.z * n.z, kk = 1.0 / sqrt(a); return V(0, -n.z * kk, n.y * kk); }
     double a = n.x * n.x + n.y * n.y, kk = 1.0 / sqrt(a); return V(-n.y * kk, n.x * kk, 0);
@@ -846,6 +872,7 @@ static void substep(const Model* m, double* env, double* part, Contact* contacts
     const int np = part ? h->n_particle : 0;
     PContact* pcs = np > 0 ? (PContact*)malloc(sizeof(PContact) * AVG_MAX_PCONTACT) : 0;
     int npc = np > 0 ? particle_collide(m, &k, part, pcs, &overflow) : 0;
+    if (npc > 1) particle_row_order(pcs, npc, &overflow);
     /* unconstrained velocity update */
     double qdd[MAXD], qd[MAXD];
     aba(m, &k, env, d, qdd);
