@@ -61,7 +61,7 @@
 #define AVG_OCC_NARROW 6          /* blocks of 128 threads per SM the narrowphase kernel is compiled for */
 #endif
 #ifndef AVG_NARROW_WARPS
-#define AVG_NARROW_WARPS (148 * 12 * 2)   /* narrowphase: warps a short work queue is spread over (two waves at 12 warps per SM) */
+#define AVG_NARROW_WARPS (148 * 6)        /* narrowphase: warps a short work queue is spread over (measured: 12 / 24 per SM cost 5-15 % on in-contact 8192-env rollouts) */
 #endif
 #ifndef AVG_WELD_BATCH
 #define AVG_WELD_BATCH 1          /* dynamics kernel: the six weld rows built together with one packed reduction (0: row by row) */

@@ -434,6 +434,28 @@ def main():
                                 "(fresh IK start pose + 100 settle steps per episode)" % fenv.sim.n_particles})
             fenv.close()
 
+    # ---- a `New` id (extra): ScratchItchJacoNew-v0, random-action episode from a device reset (16 persons of different height /
+    #      waist pose as model variants, the arm pose drawn per episode with the collision-free resampling on the device) ----------
+    if not args.no_episode:
+        nenv = make("ScratchItchJacoNew-v0", num_envs=65536, device=local_rank, seed=1001 + rank)
+        nenv.reset_device(seed=1001 + rank)
+        na_ = torch.empty((65536, 7), device=dev)
+        for k in range(3):
+            na_.uniform_(-1, 1, generator=gen); nenv.step(na_); nenv.elapsed = 0
+        nenv.reset_device(seed=1001 + rank)
+        barrier()
+        n0 = torch.cuda.Event(enable_timing=True); n1 = torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for k in range(200):
+            na_.uniform_(-1, 1, generator=gen); no_, nr_, nd_, ni_ = nenv.step(na_); nenv.elapsed = 0
+        n1.record(stream)
+        barrier()
+        tn = reduce_max(torch.tensor([n0.elapsed_time(n1)], device=dev))
+        bed.append({"env_id": "ScratchItchJacoNew-v0", "envs_per_gpu": 65536, "value": 65536 * world * 200 / (tn * 1e-3), "unit": UNIT, "steps": 200,
+                    "envs_with_contact_overflow": int((ni_["contact_overflow"] != 0).sum()),
+                    "note": "random actions, full episode from a device reset; 16 model variants (persons) per batch"})
+        nenv.close()
+
     # ---- mixed-task batch (extra; BASELINE.json configs[3] "mixed-task batch (all robots)"): one homogeneous sub-batch per
     #      (task, robot) id, each its own handle, stepped concurrently on separate streams (assistive_vr_gym_b200/mixed.py) ----
     if not args.no_episode:
