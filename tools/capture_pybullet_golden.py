@@ -20,6 +20,11 @@ What is recorded (everything the comparison needs, nothing from our own code):
             joint positions / velocities of every movable joint of robot and human, base pose + twist of the tool,
             getContactPoints() of the tool and of the robot: (bodyA, bodyB, linkA, linkB, posA, posB, normal, distance, force)
   per env-step: action, observation, reward, info['total_force_on_human'], info['task_success']
+  Feeding / Drinking (round 2): the bowl pose, and per sub-step the position and linear velocity of every food / water sphere
+            (NaN once the reference has removed it from self.foods / self.waters); per env-step how many are left and how many
+            have hit the person (feeding.py:92-121, drinking.py:95-136) -- what the particle-event parity needs
+  BedBathing: per env-step the number of wiping targets left on the upper arm / forearm (bed_bathing.py:111-125)
+  `New` ids:  hipbone_to_mouth_height and every human joint angle at reset (waist draw, arm draw: scratch_itch.py:158,211-217)
 """
 import argparse
 import json
@@ -70,6 +75,18 @@ def main():
     bodies = {"robot": u.robot, "human": u.human, "tool": tool}
     mov = {k: movable(p, b, cid) for k, b in bodies.items()}
 
+    particles0 = list(getattr(u, "foods", None) or getattr(u, "waters", None) or [])      # body ids in creation order (feeding.py:300-307)
+
+    def particle_state():
+        alive = set(getattr(u, "foods", None) or getattr(u, "waters", None) or [])
+        out = np.full((len(particles0), 6), np.nan)
+        for i, b in enumerate(particles0):
+            if b in alive:
+                pos, _ = p.getBasePositionAndOrientation(b, physicsClientId=cid)
+                lin, _ = p.getBaseVelocity(b, physicsClientId=cid)
+                out[i] = list(pos) + list(lin)
+        return out.tolist()
+
     substeps = []
     real_step = p.stepSimulation
 
@@ -87,6 +104,8 @@ def main():
             for c in p.getContactPoints(bodyA=body, physicsClientId=cid):
                 cps.append([c[1], c[2], c[3], c[4]] + list(c[5]) + list(c[6]) + list(c[7]) + [c[8], c[9]])
         rec["contacts"] = cps
+        if particles0:
+            rec["particles"] = particle_state()
         substeps.append(rec)
         return r
 
@@ -101,6 +120,11 @@ def main():
             "human_tremors": [float(x) for x in np.atleast_1d(getattr(u.world_creation, "human_tremors", []))],
             "target_on_arm": [float(x) for x in np.atleast_1d(getattr(u, "target_on_arm", []))],
             "limb": int(getattr(u, "limb", -1)),
+            "hipbone_to_mouth_height": float(getattr(u, "hipbone_to_mouth_height", 0.0) or 0.0), "new": bool(getattr(u, "new", False)),
+            "human_q_all": [s[0] for s in p.getJointStates(u.human, list(range(p.getNumJoints(u.human, physicsClientId=cid))), physicsClientId=cid)],
+            "bowl": ([list(x) for x in p.getBasePositionAndOrientation(u.bowl, physicsClientId=cid)] if hasattr(u, "bowl") else None),
+            "n_particles": len(particles0),
+            "total_target_count": int(getattr(u, "total_target_count", 0) or 0),
             "target_human_joint_positions": [float(x) for x in np.atleast_1d(getattr(u, "target_human_joint_positions", []))]}
     init = {}
     for k, b in bodies.items():
@@ -112,12 +136,15 @@ def main():
     p.stepSimulation = hooked
     n_act = env.action_space.shape[0]
     actions = np.random.RandomState(0).uniform(-1, 1, (args.steps, n_act)).astype(np.float32)
-    obs, rew, force, success, marks = [], [], [], [], []
+    obs, rew, force, success, marks, left, hit, targets_left = [], [], [], [], [], [], [], []
     for t in range(args.steps):
         o, r, d, info = env.step(actions[t])
         obs.append(np.asarray(o, dtype=np.float64)); rew.append(float(r))
         force.append(float(info["total_force_on_human"])); success.append(int(info["task_success"]))
         marks.append(len(substeps))
+        left.append(len(getattr(u, "foods", None) or getattr(u, "waters", None) or []))
+        hit.append(len(getattr(u, "foods_hit_person", []) or []))
+        targets_left.append([len(getattr(u, "targets_upperarm", []) or []), len(getattr(u, "targets_forearm", []) or [])])
     p.stepSimulation = real_step
 
     def stack(key):
@@ -131,7 +158,9 @@ def main():
     np.savez_compressed(args.out, meta=json.dumps(meta), init=json.dumps(init), actions=actions, obs0=np.asarray(obs0, dtype=np.float64),
                         obs=np.asarray(obs), reward=np.asarray(rew), total_force_on_human=np.asarray(force), task_success=np.asarray(success),
                         substep_marks=np.asarray(marks), robot_q=stack("robot_q"), robot_qd=stack("robot_qd"), human_q=stack("human_q"),
-                        human_qd=stack("human_qd"), tool_base=stack("tool_base"), contacts=contacts)
+                        human_qd=stack("human_qd"), tool_base=stack("tool_base"), contacts=contacts,
+                        particles=(stack("particles") if particles0 else np.zeros((0, 0, 6))), particles_left=np.asarray(left),
+                        particles_hit_person=np.asarray(hit), targets_left=np.asarray(targets_left))
     print("wrote", args.out, "substeps", len(substeps), "max contacts per sub-step", max_c)
 
 

@@ -1,5 +1,5 @@
 """Divergence-vs-horizon curve of the CUDA path against the CPU oracle (north_star: "with the divergence-vs-horizon
-curve reported because contact dynamics are chaotic").  Writes profiles/divergence_r1.json.
+curve reported because contact dynamics are chaotic").  Writes gpurun_out/divergence_r2[_<id>].json.
 usage: python tools/divergence_curve.py [n_env=256] [steps=100] [env_id=ScratchItchJaco-v0]"""
 import json, os, sys
 import numpy as np, torch
@@ -43,5 +43,5 @@ for t in range(T):
         print(rows[-1])
 out = {"env_id": env_id, "n_env": n, "steps": T, "note": "max |dq| over the %d joint coordinates, CUDA float32 vs oracle float64, random actions" % nq, "curve": rows}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-name = "divergence_r1.json" if env_id == "ScratchItchJaco-v0" else "divergence_r1_%s.json" % env_id[:-3]
+name = "divergence_r2.json" if env_id == "ScratchItchJaco-v0" else "divergence_r2_%s.json" % env_id[:-3]
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
