@@ -2948,6 +2948,7 @@ struct __align__(16) SmPCol {
     float px[64][3];
     uint16_t cand[64][kPCandPerParticle];  // candidate shapes of each particle, ascending shape index (one enumeration, then the prefix sum)
     uint8_t near_idx[256];
+    uint32_t cmask[16][AVG_MAX_COMPOUND][3];   // few particles (Feeding): children of compound c that pass the culls for particle p, found by the whole warp
 };
 }  // namespace
 
@@ -3019,8 +3020,47 @@ avg_pcollide_kernel(AvgStepArgs a) {
         nnear += __popc(bal);
     }
     __syncwarp();
+    // the culls of one (particle, compound child) pair: the child's body-frame box, then the face-plane bound -- a point outside
+    // a hull is at least max_i (n_i . x - d_i) away from it, so children whose planes already put the particle beyond the contact
+    // distance never reach GJK (thin VHACD pieces have loose boxes)
+    auto child_passes = [&](V3 pl, int first, int k) -> bool {
+        const float4 c4 = __ldg(&m.caabb[2 * (first - h->n_shape + k)]), h4 = __ldg(&m.caabb[2 * (first - h->n_shape + k) + 1]);
+        if (!(fabsf(pl.x - c4.x) <= h4.x + infl && fabsf(pl.y - c4.y) <= h4.y + infl && fabsf(pl.z - c4.z) <= h4.z + infl)) return false;
+        const AvgShape* C = &m.shape[first + k];
+        const V3 xs = qrot_inv(ldq(C->quat), pl - ld3(C->pos));
+        const float4* pln = reinterpret_cast<const float4*>(m.plane) + C->plane_off;
+        float lb = -3.0e38f;
+        for (int i = 0; i < C->plane_cnt; ++i) { const float4 q4 = __ldg(pln + i); lb = fmaxf(lb, fmaf(q4.x, xs.x, fmaf(q4.y, xs.y, q4.z * xs.z)) - q4.w); }
+        return lb < infl + C->margin + 1e-6f;
+    };
+    // Few particles (Feeding: 8 lanes would walk 134 children each while 24 idle): the whole warp tests the children of a
+    // compound for one particle at a time, one child per lane, and leaves the survivors as bit masks for the enumeration below.
+    const bool coop = np <= 16;
+    if (coop) {
+        int ncomp = 0;
+        for (int sa = 0; sa < nms && ncomp < AVG_MAX_COMPOUND; ++sa) {
+            const AvgShape* S = &m.shape[sa];
+            if (S->type != AVG_SHAPE_COMPOUND) continue;
+            const float4 a0 = s.saabb[sa][0], a1 = s.saabb[sa][1];
+            const Q4 cq = ldq(s.bq[S->body]); const V3 cp = ld3(s.bp[S->body]);
+            const int first = S->vert_off, cnt = min(S->vert_cnt, 96);
+            for (int p = 0; p < np; ++p) {
+                const bool alive_p = (alive0 >> p) & 1u;
+                const V3 xp = ld3(s.px[p]);
+                const bool inbox = alive_p && fabsf(xp.x - a0.x) <= a0.w + infl && fabsf(xp.y - a0.y) <= a1.x + infl && fabsf(xp.z - a0.z) <= a1.y + infl;
+                for (int r3 = 0; r3 < 3; ++r3) {
+                    const int k = 32 * r3 + lane;
+                    const bool pass = inbox && k < cnt && child_passes(qrot_inv(cq, xp - cp), first, k);
+                    const unsigned w = __ballot_sync(AVG_FULL, pass);
+                    if (lane == 0) s.cmask[p][ncomp][r3] = w;
+                }
+            }
+            ++ncomp;
+        }
+        __syncwarp();
+    }
     // candidate enumeration of one particle in ascending shape-table order; f(shape index) is called for every candidate
-    auto enumerate = [&](V3 xp, auto&& f) {
+    auto enumerate = [&](V3 xp, int pidx, auto&& f) {
         for (int sa = 0; sa < nms; ++sa) {
             if (m.shape[sa].type == AVG_SHAPE_COMPOUND) continue;
             const float4 a0 = s.saabb[sa][0], a1 = s.saabb[sa][1];
@@ -3032,25 +3072,24 @@ avg_pcollide_kernel(AvgStepArgs a) {
             const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
             if (fabsf(xp.x - r0.x) <= r0.w + infl && fabsf(xp.y - r0.y) <= r1.x + infl && fabsf(xp.z - r0.z) <= r1.y + infl) f(nms + si);
         }
+        int ncomp = 0;
         for (int sa = 0; sa < nms; ++sa) {
             const AvgShape* S = &m.shape[sa];
             if (S->type != AVG_SHAPE_COMPOUND) continue;
+            const int first = S->vert_off, cnt = S->vert_cnt;
+            if (coop && ncomp < AVG_MAX_COMPOUND && cnt <= 96) {               // survivors found by the whole warp above
+                for (int r3 = 0; r3 < 3; ++r3) {
+                    unsigned w = s.cmask[pidx][ncomp][r3];
+                    while (w) { const int k = __ffs(w) - 1; w &= w - 1; f(first + 32 * r3 + k); }
+                }
+                ++ncomp;
+                continue;
+            }
+            ++ncomp;
             const float4 a0 = s.saabb[sa][0], a1 = s.saabb[sa][1];
             if (!(fabsf(xp.x - a0.x) <= a0.w + infl && fabsf(xp.y - a0.y) <= a1.x + infl && fabsf(xp.z - a0.z) <= a1.y + infl)) continue;
             const V3 pl = qrot_inv(ldq(s.bq[S->body]), xp - ld3(s.bp[S->body]));          // the particle in the compound's body frame
-            const int first = S->vert_off, cnt = S->vert_cnt;
-            for (int k = 0; k < cnt; ++k) {
-                const float4 c4 = __ldg(&m.caabb[2 * (first - h->n_shape + k)]), h4 = __ldg(&m.caabb[2 * (first - h->n_shape + k) + 1]);
-                if (!(fabsf(pl.x - c4.x) <= h4.x + infl && fabsf(pl.y - c4.y) <= h4.y + infl && fabsf(pl.z - c4.z) <= h4.z + infl)) continue;
-                // face-plane bound: a point outside a hull is at least max_i (n_i . x - d_i) away from it, so children whose planes
-                // already put the particle beyond the contact distance never reach GJK (thin VHACD pieces have loose boxes)
-                const AvgShape* C = &m.shape[first + k];
-                const V3 xs = qrot_inv(ldq(C->quat), pl - ld3(C->pos));
-                const float4* pln = reinterpret_cast<const float4*>(m.plane) + C->plane_off;
-                float lb = -3.0e38f;
-                for (int i = 0; i < C->plane_cnt; ++i) { const float4 q4 = __ldg(pln + i); lb = fmaxf(lb, fmaf(q4.x, xs.x, fmaf(q4.y, xs.y, q4.z * xs.z)) - q4.w); }
-                if (lb < infl + C->margin + 1e-6f) f(first + k);
-            }
+            for (int k = 0; k < cnt; ++k) if (child_passes(pl, first, k)) f(first + k);
         }
     };
     int cnt[2] = {0, 0};
@@ -3058,7 +3097,7 @@ avg_pcollide_kernel(AvgStepArgs a) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) if (live[k]) {
         const int p = lane + 32 * k;
-        enumerate(x[k], [&](int sb) { if (cnt[k] < kPCandPerParticle) s.cand[p][cnt[k]++] = (uint16_t)sb; else cand_over = 16; });
+        enumerate(x[k], p, [&](int sb) { if (cnt[k] < kPCandPerParticle) s.cand[p][cnt[k]++] = (uint16_t)sb; else cand_over = 16; });
     }
     // particle-major offsets: particles 0..31 first, then 32..63
     int inc0 = cnt[0], inc1 = cnt[1];

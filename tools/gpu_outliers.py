@@ -1,7 +1,7 @@
 """Where do the largest one-env-step deviations between the CUDA path and the oracle come from?  Walks N environments for
 0..K policy / random steps, takes ONE env-step from identical float32 states on both sides and prints, for the worst
 environments, the contact lists of both sides (pair, distance, force) and the joints that differ.
-usage: python tools/gpu_outliers.py [env_id] [n_env] [top]"""
+usage: python tools/gpu_outliers.py [env_id] [n_env] [top] [walk max]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,6 +12,7 @@ from oracle.oracle import Oracle, env_to_f64
 env_id = sys.argv[1] if len(sys.argv) > 1 else "ScratchItchJaco-v0"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+wmax = int(sys.argv[4]) if len(sys.argv) > 4 else 25
 env = make(env_id, num_envs=n, device=0, seed=21)
 env.sim.enable_debug(True)
 env.reset()
@@ -20,8 +21,8 @@ oracles = [Oracle(b) for b in env.blobs]
 na = env.sim.n_actions
 rng = np.random.RandomState(3)
 g = torch.Generator(device="cuda"); g.manual_seed(4)
-walk = rng.randint(0, 25, size=n)
-for k in range(24):
+walk = rng.randint(0, wmax, size=n)
+for k in range(wmax - 1):
     a = (torch.rand((n, na), device="cuda", generator=g) * 2 - 1)
     before = env.get_state()
     env.step(a); env.elapsed = 0
