@@ -125,6 +125,13 @@ def test_gpu_new_reset_draws_and_parity(env_id):
                 if hit:
                     exact = min(exact, float(out[9]))
         assert exact >= float(gaps[e]) - 1e-4, (e, exact, gaps[e])
+    # ... and equals the numpy mirror of the device test (compiler/reset.py new_arm_clearance, what the model compiler uses to
+    # drop infeasible persons)
+    from assistive_vr_gym_b200.compiler.blob import read_blob
+    from assistive_vr_gym_b200.compiler.reset import new_arm_clearance
+    models = [read_blob(b) for b in env.blobs]
+    for e in rng.choice(n, 16, replace=False):
+        assert abs(new_arm_clearance(models[int(variants[e])], st[e].astype(np.float64)) - float(gaps[e])) < 2e-5, e
     # the reset observation and a few contact-free steps against the oracle
     recs = [env_to_f64(st[e]).copy() for e in range(64)]
     for e in range(64):
@@ -139,7 +146,9 @@ def test_gpu_new_reset_draws_and_parity(env_id):
             if len(oc) or nc[e]:
                 clean[e] = False
             if clean[e]:
-                assert np.abs(recs[e][:32] - s2[e, :32]).max() < 3e-4 and abs(orew - rew[e]) < 1e-3
+                # PR2: the residual early exit stops the float32 and the float64 solver one iteration apart on start poses that sit
+                # on a joint limit (tests/test_pr2.py): 1e-3 rad over 5 steps there, 3e-4 on the Jaco
+                assert np.abs(recs[e][:32] - s2[e, :32]).max() < (1e-3 if "PR2" in env_id else 3e-4) and abs(orew - rew[e]) < 1e-3
     assert clean.sum() >= 16
     env.close()
 
