@@ -40,7 +40,7 @@
 #define AVG_WPB_COLLIDE 4         /* warps (= environments) per block of the collide kernel */
 #endif
 #ifndef AVG_WPB_DYN
-#define AVG_WPB_DYN 8             /* warps per block of the dynamics kernel */
+#define AVG_WPB_DYN 12            /* warps per block of the dynamics kernel */
 #endif
 #ifndef AVG_OCC_COLLIDE
 #define AVG_OCC_COLLIDE (20 / AVG_WPB_COLLIDE)
@@ -2220,7 +2220,8 @@ avg_solve_kernel(AvgStepArgs a) {
             resid = fmaxf(resid, fabsf(delta) * ra.z);
         }
         // every lane holds the same jdv (an exact integer sum) and the same row data, hence the same impulse: all lanes store it
-        // to the same word and each reads back what it wrote itself -- no owner lane, no shuffle, no barrier
+        // to the same word -- no owner lane, no shuffle.  A row reads its words before its warp-wide reduction (redux.sync is a
+        // convergence point) and writes after it, so a write never overtakes another lane's read of the old value.
         auto lam_get = [&](int d) { return s.lam[d]; };
 #if AVG_REDUX == 0
         auto lam_set = [&](int d, float v) { s.lam[d] = __shfl_sync(AVG_FULL, v, 0); };    // float butterflies may differ in the last bit between lanes
@@ -2232,8 +2233,8 @@ avg_solve_kernel(AvgStepArgs a) {
             const float4 ra = s.rd[d][0]; const float4 rb = s.rd[d][1];
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
-            const float jdv = dense_dot(*jp, dv);
-            const float lam = lam_get(d);
+            const float lam = lam_get(d);                            // read BEFORE the warp-wide reduction, written after it: no lane can
+            const float jdv = dense_dot(*jp, dv);                    // overwrite the word while another still has to read the old value
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), ra.z), ra.w);
             const float delta = sum - lam;
             lam_set(d, sum);
@@ -2252,9 +2253,9 @@ avg_solve_kernel(AvgStepArgs a) {
             const int par = __float_as_int(rb.w);
             const float* jp = d < kSmDense ? &s.J[d][lane] : &gJ[d * 32 + lane];
             const float* wp = d < kSmDense ? &s.W[d][lane] : &gW[d * 32 + lane];
-            const float jdv = dense_dot(*jp, dv);
             const float lam = lam_get(d);
             const float lim = rb.y * lam_get(par);
+            const float jdv = dense_dot(*jp, dv);
             const float sum = fminf(fmaxf(fmaf(ra.x - jdv, ra.y, lam), -lim), lim);
             const float delta = sum - lam;
             lam_set(d, sum);
