@@ -46,7 +46,7 @@ HEADER_DT = np.dtype([
     ("off_mlp", "<u4"), ("n_mlp", "<i4"), ("mlp_dof", "<i4", 4),
     ("off_target", "<u4"), ("n_target", "<i4"), ("n_target_upper", "<i4"),
     ("n_cshape", "<i4"), ("off_caabb", "<u4"), ("n_internal", "<i4"), ("n_particle", "<i4"), ("pshape", "<i4"),
-    ("p_mass", "<f4"), ("p_gravity", "<f4", 3), ("tool_body", "<i4"), ("head_frozen_mask", "<i4"), ("pad2", "<u4", 5),
+    ("p_mass", "<f4"), ("p_gravity", "<f4", 3), ("tool_body", "<i4"), ("head_frozen_mask", "<i4"), ("warmstart", "<f4"), ("pad2", "<u4", 4),
 ])
 assert BODY_DT.itemsize == 128 and DOF_DT.itemsize == 64 and SHAPE_DT.itemsize == 128 and FRAME_DT.itemsize == 32
 
@@ -227,6 +227,7 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     if overrides:
         vals.update(overrides)
     h["n_internal"] = 1; h["tool_body"] = -1
+    h["warmstart"] = WARMSTART_FACTOR
     for k, v in vals.items():
         h[k] = v
     h["n_shape"] = n_top; h["n_cshape"] = len(cshapes); h["pshape"] = len(all_shapes) if particle is not None else -1
@@ -249,6 +250,11 @@ def scene_to_blob(scene: CompiledScene, overrides: dict | None = None) -> bytes:
     for o, b in sections:
         buf[o:o + len(b)] = b
     return bytes(buf)
+
+
+# Warm-starting factor of the contact normal rows [UPSTREAM-BULLET, from memory]: btContactSolverInfo defaults to 0.85, the PyBullet
+# physics server sets m_warmstartingFactor = 0.1 when it creates the world; the reference never touches it.
+WARMSTART_FACTOR = 0.1
 
 
 def read_blob(blob: bytes) -> dict:

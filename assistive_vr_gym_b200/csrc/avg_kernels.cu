@@ -1335,6 +1335,16 @@ avg_dynamics_kernel(AvgStepArgs a) {
                 float* c = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * slot;
                 c[0] = r0.x; c[1] = r0.y; c[2] = r0.z; c[3] = r0.w; c[4] = r1.x; c[5] = r1.y; c[6] = r1.z; c[7] = r1.w; c[8] = r2.x;
                 c[9] = r2.y; c[10] = r2.z; c[11] = r2.w; c[12] = 0.0f;
+                // warm start (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint): the impulse the same shape pair carried
+                // in the last internal step (AVG_E_WCACHE), times the warm-starting factor, initialises the normal row in the solver
+                float lam0 = 0.0f;
+                if (h->warmstart > 0.0f) {
+                    const uint32_t key = (uint32_t)__float_as_int(r2.z) | ((uint32_t)__float_as_int(r2.w) << 16);
+#pragma unroll
+                    for (int w = AVG_WCACHE_N - 1; w >= 0; --w)
+                        if (__float_as_uint(grec[AVG_E_WCACHE + 2 * w]) == key) lam0 = h->warmstart * grec[AVG_E_WCACHE + 2 * w + 1];
+                }
+                c[13] = lam0;
             }
             ncontact += __popc(bal);
         }
@@ -2175,6 +2185,19 @@ avg_solve_kernel(AvgStepArgs a) {
         prec_rows = a.pscratch + (size_t)e * AVG_PS_STRIDE + AVG_PS_SORTED;
         tool_dof = h->tool_body >= 0 ? m.body[h->tool_body].dof : -1;
     }
+    // warm-started contact normal rows: the row starts from its impulse and the velocities from that impulse's effect
+    if (h->warmstart > 0.0f) {
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+            const float lam0 = scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c + 13];
+            if (lam0 != 0.0f) {
+                const int d = first_contact_row + c;
+                s.lam[d] = lam0;
+                dv = fmaf(d < kSmDense ? s.W[d][lane] : gW[d * 32 + lane], lam0, dv);
+            }
+        }
+        __syncwarp();
+    }
     float lamM[MAXBLK], lamW[6], jw[6];
 #pragma unroll
     for (int t = 0; t < MAXBLK; ++t) lamM[t] = 0.0f;
@@ -2274,6 +2297,13 @@ avg_solve_kernel(AvgStepArgs a) {
 
     // contact impulses (getContactPoints()[9] = impulse / dt), read by the epilogue after the last sub-step
     for (int c = lane; c < nc; c += 32) scr[AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * c + 12] = s.lam[first_contact_row + c];
+    if (lane < AVG_WCACHE_N) {                                   // what the next internal step warm-starts from
+        const bool have = lane < nc;
+        const float* cc = scr + AVG_S_CONTACT + AVG_S_CONTACT_STRIDE * lane;
+        const uint32_t key = have ? ((uint32_t)__float_as_int(cc[10]) | ((uint32_t)__float_as_int(cc[11]) << 16)) : 0u;
+        grec[AVG_E_WCACHE + 2 * lane] = __uint_as_float(key);
+        grec[AVG_E_WCACHE + 2 * lane + 1] = have ? s.lam[first_contact_row + lane] : 0.0f;
+    }
     if (lane == 0) scr_i[AVG_S_ITERS] += iters;
     if (PART) particles_finish(m, *spp, a, e, lane, dt, npc, p_overflow);
 
@@ -3395,6 +3425,7 @@ avg_reset_ik_kernel(AvgResetArgs r) {
     if (r.round > 0) {                                                                // after test steps: every joint back on its reset pose, at rest
         for (int d = 0; d < m.h->n_jdof; ++d) rec[AVG_E_Q + m.body[m.dof[d].body].qidx] = rec[AVG_E_MTARGET + d];
         for (int d = 0; d < 32; ++d) rec[AVG_E_QD + d] = 0.0f;
+        for (int d = 0; d < 2 * AVG_WCACHE_N; ++d) rec[AVG_E_WCACHE + d] = 0.0f;      // no impulses carried over from the test steps
     }
     for (int j = 0; j < c.n; ++j) { rec[AVG_E_Q + c.qidx[j]] = qbest[j]; rec[AVG_E_MTARGET + c.dof[j]] = qbest[j]; }
     // the tool goes where init_tool puts it (world_creation.py:331-337): weld-parent frame o inverse of the tool's base frame

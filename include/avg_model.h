@@ -166,7 +166,10 @@ typedef struct AvgModelHeader {
     int32_t  tool_body;           /* dynamic body of the spoon / cup (free body), -1 when the tool is not a single free body                  */
     int32_t  head_frozen_mask;    /* bodies of human joints 24..27: their masses are zeroed per environment (AVG_E_FROZEN) unless the
                                      episode drew a tremor or the id is human-active (feeding.py:244 + world_creation.py:157-161)             */
-    uint32_t pad2[5];
+    float    warmstart;           /* warm-starting factor of the contact normal rows: the impulse a contact point carried in the last
+                                     internal step, times this, initialises its row ([UPSTREAM-BULLET] m_warmstartingFactor: 0.85 in
+                                     btContactSolverInfo, set to 0.1 by the PyBullet server -- from memory); 0 = off (blobs older than round 2) */
+    uint32_t pad2[4];
 } AvgModelHeader;
 #define AVG_MAX_TARGET 160
 
@@ -223,8 +226,12 @@ enum {
     AVG_E_NCAND = 168,       /* int: narrowphase candidate pairs examined in the last env-step (diagnostic) */
     AVG_E_TARGET_MASK = 170, /* [5] uint32: BedBathing targets not yet wiped, bit t of word t/32 (bed_bathing.py:111-125 shrink the lists) */
     AVG_E_FROZEN = 175,      /* uint32: bodies whose mass / inertia count as zero in this episode (changeDynamics(mass=0), world_creation.py:157-161) */
-    AVG_E_LAST = 176
+    AVG_E_WCACHE = 176,      /* [8][2] {uint32 key = shape a | shape b << 16 (0 = empty), float normal impulse}: the contact points of the
+                                last internal step that the next one warm-starts from (Bullet keeps the applied impulse in the
+                                persistent manifold point, btMultiBodyConstraintSolver::setupMultiBodyContactConstraint) */
+    AVG_E_LAST = 192
 };
+#define AVG_WCACHE_N 8
 
 /* ---- per-environment particle record (Feeding / Drinking): AVG_P_STRIDE floats, structure of arrays so that lane p reads
  *      particle p (and p + 32) with coalesced loads.  Spheres need no orientation.  Bit p of word p / 32 in the masks. ---- */

@@ -1060,13 +1060,30 @@ static void substep(const Model* m, double* env, double* part, Contact* contacts
         r->lo = 0; r->hi = 0; r->friction_of = first_pcontact_row + c;
         r->mu = (double)m->shape[h->pshape].friction * mu_b;
     }
+    /* Warm starting of the contact normal rows [UPSTREAM-BULLET: btMultiBodyConstraintSolver::setupMultiBodyContactConstraint,
+     * m_appliedImpulse = cp.m_appliedImpulse * m_warmstartingFactor for normal rows, 0 for friction rows; motors, limits and the
+     * fixed constraint are not warm-started ("disable warmstarting for btMultiBody ... gaining energy")].  Bullet finds the old
+     * impulse in the persistent manifold point; with one point per shape pair the match is by pair: the record keeps the
+     * (pair, impulse) of the first AVG_WCACHE_N contact points of the last internal step (AVG_E_WCACHE). */
+    double dv[MAXD]; memset(dv, 0, sizeof(dv));
+    if (h->warmstart > 0.0f) {
+        for (int c = 0; c < nc; ++c) {
+            const uint32_t key = (uint32_t)contacts[c].sa | ((uint32_t)contacts[c].sb << 16);
+            for (int w = 0; w < AVG_WCACHE_N; ++w) {
+                if ((uint32_t)env[AVG_E_WCACHE + 2 * w] != key) continue;
+                Row* r = &rows[first_contact_row + c];
+                r->lambda = (double)h->warmstart * env[AVG_E_WCACHE + 2 * w + 1];
+                for (int i = 0; i < nd; ++i) dv[i] += r->W[i] * r->lambda;
+                break;
+            }
+        }
+    }
     /* projected Gauss-Seidel in velocity space, as btMultiBodyConstraintSolver */
     /* Particle rows and the tool (documented deviation from Bullet's strict row order): inside one block of particle
      * rows (the normal block, the friction block) every row sees the tool's velocity change as it was when the block began; the
      * reactions of the block reach the tool -- and the rows after the block -- at once.  A block then only orders the rows that
      * share a PARTICLE, which is what lets the device sweep a block in a few parallel rounds instead of one row at a time; the
      * coupling that is lagged by one block is of the order particle mass / tool mass (1 g against the spoon / cup). */
-    double dv[MAXD]; memset(dv, 0, sizeof(dv));
     double dv_block[MAXD]; memset(dv_block, 0, sizeof(dv_block));
     double dpv[AVG_MAX_PARTICLE][6]; memset(dpv, 0, sizeof(dpv));
     for (int it = 0; it < h->solver_iters; ++it) {
@@ -1095,6 +1112,10 @@ static void substep(const Model* m, double* env, double* part, Contact* contacts
         if (resid <= h->residual_thr) break;
     }
     for (int c = 0; c < nc; ++c) contacts[c].lambda_n = rows[first_contact_row + c].lambda;
+    for (int w = 0; w < AVG_WCACHE_N; ++w) {          /* what the next internal step warm-starts from */
+        env[AVG_E_WCACHE + 2 * w] = w < nc ? (double)((uint32_t)contacts[w].sa | ((uint32_t)contacts[w].sb << 16)) : 0.0;
+        env[AVG_E_WCACHE + 2 * w + 1] = w < nc ? contacts[w].lambda_n : 0.0;
+    }
     *ncontact = nc;
     /* integrate (btMultiBody::stepPositionsMultiDof): semi-implicit Euler */
     for (int i = 0; i < nd; ++i) {

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libavg_oracle.so")
 ENV_STRIDE = 192
 INT_SLOTS = (123, 152, 161, 166, 167, 168)    # AVG_E_LIMB_FRAME, AVG_E_ITERATION, AVG_E_HAS_VALID, AVG_E_OVERFLOW
-UINT_SLOTS = (170, 171, 172, 173, 174, 175)   # AVG_E_TARGET_MASK words (BedBathing), AVG_E_FROZEN
+UINT_SLOTS = (170, 171, 172, 173, 174, 175,   # AVG_E_TARGET_MASK words (BedBathing), AVG_E_FROZEN
+              176, 178, 180, 182, 184, 186, 188, 190)   # keys of the warm-start contact cache (AVG_E_WCACHE)
 P_STRIDE = 592                                # AVG_P_STRIDE (include/avg_model.h)
 P_UINT_SLOTS = tuple(range(576, 590))         # AVG_P_ALIVE .. AVG_P_EV_HIT mask words
 P_INT_SLOTS = (590, 591)                      # AVG_P_NCONTACT, overflow flags

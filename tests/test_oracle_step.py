@@ -127,3 +127,45 @@ def test_forces_come_from_tool_and_robot_contacts_only(env_data, oracles):
                 seen += 1
         assert info[2] == pytest.approx(tool) and info[0] == pytest.approx(total)
     assert seen > 0
+
+
+def test_warm_start_cache_round_trip(env_data, oracles):
+    """AVG_E_WCACHE (round 2): after a step with contacts the record holds (pair key, normal impulse) of the first contact points;
+    the next internal step starts those rows from warmstart x impulse (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint).
+    Checked on the oracle: the keys are the contact pairs, the impulses the reported forces x dt, and switching the factor off
+    (header.warmstart = 0) changes the next step only through those rows."""
+    from assistive_vr_gym_b200.compiler.reset import sample_states
+    from oracle.oracle import Oracle, env_to_f64
+    from helpers import patch_blob
+    blobs, resets = env_data
+    env0, variant = sample_states(resets, 200, np.random.RandomState(11))
+    rng = np.random.RandomState(2)
+    found = 0
+    for e in range(200):
+        o = oracles[int(variant[e])]
+        rec = env_to_f64(env0[e]).copy()
+        drift = rng.uniform(-0.8, 0.8, 7)
+        for t in range(25):
+            _, _, _, oc = o.step(rec, np.clip(drift + rng.uniform(-0.4, 0.4, 7), -1, 1))
+            if len(oc):
+                break
+        if not len(oc):
+            continue
+        found += 1
+        dt = float(o.model["header"]["dt"])
+        keys = [int(rec[176 + 2 * w]) for w in range(8)]; imps = [rec[177 + 2 * w] for w in range(8)]
+        for w, c in enumerate(oc[:8]):
+            assert keys[w] == (int(c[0]) | (int(c[1]) << 16)) and abs(imps[w] - c[12] * dt) < 1e-12
+        assert all(k == 0 for k in keys[len(oc):])
+        # the same next step with and without the cache: identical unless a cached pair is in contact again
+        a = rng.uniform(-1, 1, 7)
+        warm1 = Oracle(patch_blob(blobs[int(variant[e])], header={"substeps": 1}))                      # one internal step per env-step
+        cold1 = Oracle(patch_blob(blobs[int(variant[e])], header={"substeps": 1, "warmstart": 0.0}))
+        r1 = rec.copy(); r2 = rec.copy(); r2[176:192] = 0.0; r3 = rec.copy()
+        _, _, _, c1 = warm1.step(r1, a); warm1.step(r2, a); cold1.step(r3, a)
+        assert np.array_equal(r2[:64], r3[:64])                      # empty cache == factor 0
+        if any((int(c[0]) | (int(c[1]) << 16)) in keys for c in c1):
+            assert not np.array_equal(r1[32:64], r2[32:64])          # a cached pair in contact again: its row started from 0.1 x impulse
+        if found >= 6:
+            break
+    assert found >= 3
