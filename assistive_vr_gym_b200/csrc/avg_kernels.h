@@ -35,7 +35,7 @@
 #define AVG_S_NSEPMAX 32
 #define AVG_S_POSE (AVG_S_SEP + 12 * AVG_S_NSEPMAX)   /* [32][8] body poses (pos, pad, quat) from the collide kernel's forward kinematics */
 #define AVG_S_NPRES (AVG_S_POSE + 8 * 32)             /* [AVG_S_NQMAX][16] narrowphase results of the queued candidates: pa, pb, n, dist, shape a, shape b, hit */
-#define AVG_S_NQMAX 64
+#define AVG_S_NQMAX 128          /* = the broadphase candidate capacity (kMaxCand): a cup near the head queues > 64 child pairs */
 #define AVG_S_TWIST (AVG_S_NPRES + 16 * AVG_S_NQMAX)  /* [32][8] start-of-step body twists about the model's reference point (ang, pad, lin, pad); particle tasks only */
 #define AVG_S_FREEINV (AVG_S_TWIST + 8 * 32)          /* [2][12] inverse mass / world inverse inertia of the free bodies (tool); particle tasks only */
 #define AVG_S_STRIDE (AVG_S_FREEINV + 24)

@@ -411,7 +411,7 @@ def main():
     #      build-defined (the reference's task files have no Sawyer / Baxter branch) ----------------------------
     if not args.no_episode:
         for fid, nb, nst in (("FeedingSawyer-v0", 4096, 200), ("FeedingJaco-v0", 4096, 200), ("DrinkingBaxter-v0", 4096, 50), ("DrinkingJaco-v0", 4096, 50)):
-            fenv = make_shard(fid, nb * world, rank, world, device=local_rank, seed=1001)
+            fenv = make_shard(fid, nb * world, rank, world, device=local_rank, seed=1001, cuda_graph=True)   # 52 launches per env-step: one graph replay
             fenv.reset()
             fa = torch.empty((nb, fenv.sim.n_actions), device=dev)
             for k in range(3):
@@ -430,6 +430,7 @@ def main():
             bed.append({"env_id": fid, "envs_per_gpu": nb, "value": nb * world * nst / (tf_ * 1e-3), "unit": UNIT, "steps": nst,
                         "task_success_rate": float(fstat[0] / fstat[3]), "mean_reward_last_step": float(fstat[1] / fstat[3]),
                         "envs_with_contact_overflow": int(fstat[2]),
+                        "cuda_graph": True,
                         "note": "random actions, 5 frames x 2 internal steps x 10 PGS iterations per env-step, %d particles, from a device reset "
                                 "(fresh IK start pose + 100 settle steps per episode)" % fenv.sim.n_particles})
             fenv.close()
