@@ -566,7 +566,7 @@ def main():
                                                                        "peak_tflops": 148 * 128 * 2 * 1.965e-3,
                                                                        "frac": fp["flop_per_env_step_substep_kernels"] * value / world / 1e12 / (148 * 128 * 2 * 1.965e-3),
                                                                        "note": "FADD + FMUL + 2 FFMA thread instructions per env-step from the committed ncu full-set capture "
-                                                                               "(profiles/traffic.json) x measured env-steps/s; FMA-pipe utilisation per kernel is in profiles/ncu_full_r1t.txt"})(prof.get("fp32")),
+                                                                               "(profiles/traffic.json) x measured env-steps/s; FMA-pipe utilisation per kernel is in profiles/ncu_full_r2e.txt"})(prof.get("fp32")),
                              "note": "issue/latency bound by design (SURVEY.md 8d): the HBM fraction is reported as north_star asks; "
                                      "issue_slots (from the committed ncu launch list) is the roof that binds"},
                 "clocks": sampler.summary(),
