@@ -3602,7 +3602,7 @@ avg_reset_new_kernel(AvgResetArgs r) {
     };
     // the arm's shapes: the moving shapes of the person
     int arm[4], narm = 0;
-    for (int si = 0; si < nms && narm < 4; ++si) if (m.shape[si].ref_body == AVG_REF_HUMAN && m.shape[si].body < nb) arm[narm++] = si;
+    for (int si = 0; si < nms && narm < 4; ++si) if (m.shape[si].ref_body == AVG_REF_HUMAN && m.shape[si].body >= 0 && m.shape[si].body < nb) arm[narm++] = si;
     float qbest[8]; float gap_best = -3.0e38f; int attempts = 0;
     for (int at = 0; at < 20; ++at) {
         attempts = at + 1;
@@ -3618,7 +3618,7 @@ avg_reset_new_kernel(AvgResetArgs r) {
             V3 a0, a1; float ra; world_capsule(arm[k], a0, a1, ra);
             for (int sj = 0; sj < ns; ++sj) {
                 const AvgShape* S = &m.shape[sj];
-                if (S->type == AVG_SHAPE_PLANE) continue;
+                if (S->type == AVG_SHAPE_PLANE || (sj < nms && (S->body < 0 || S->body >= nb))) continue;      // env-static bodies: none in these tasks
                 const int rb_ = S->ref_body;
                 bool other = false;
                 if (rb_ == AVG_REF_HUMAN) other = sj >= nms && S->ref_link != 3 && S->ref_link != 6;       // scratch_itch.py:219

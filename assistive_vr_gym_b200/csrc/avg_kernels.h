@@ -7,7 +7,8 @@
 #define AVG_K_WARPS_PER_BLOCK 4
 #define AVG_K_MAXJ 24      /* 1-DoF joints per environment supported by the warp-per-environment kernels */
 #define AVG_K_MAXMS 24     /* moving collision shapes per environment */
-#define AVG_K_MAX_VARIANTS 16  /* model variants per handle: gender (x robot base pose for BedBathing) */
+#define AVG_K_MAX_VARIANTS 32  /* model variants per handle: gender x (robot base pose | person of a `New` id); the section pointers of
+                                  16 handles x 32 variants fill 56 KB of the 64 KB constant bank */
 
 /* Scratch arena: per-environment hand-off between the kernels of one sub-step (floats; ints bit-cast). */
 #define AVG_S_MAXDENSE (6 + 2 * AVG_MAX_CONTACT)

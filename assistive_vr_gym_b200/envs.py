@@ -41,7 +41,7 @@ for _t, _task in (("Feeding", "feeding"), ("Drinking", "drinking")):
     for _r, _robot in (("Jaco", "jaco"), ("PR2", "pr2"), ("Sawyer", "sawyer"), ("Baxter", "baxter")):
         REGISTRY[f"{_t}{_r}-v0"] = dict(task=_task, robot=_robot, human_control=False, data=f"{_t}{_r}.npz")
         REGISTRY[f"{_t}{_r}Human-v0"] = dict(task=_task, robot=_robot, human_control=True, data=f"{_t}{_r}Human.npz")
-# `New` ids (reference __init__.py:38-50): a person of random height with a random waist pose (both per model variant here: 8
+# `New` ids (reference __init__.py:38-50): a person of random height with a random waist pose (both per model variant here: 16
 # per gender), no impairment, the arm pose drawn per episode on the device until it is collision-free (avg_reset_new_kernel)
 REGISTRY["ScratchItchJacoNew-v0"] = dict(task="scratch_itch", robot="jaco", human_control=False, data="ScratchItchJacoNew.npz", new=True)
 REGISTRY["ScratchItchPR2New-v0"] = dict(task="scratch_itch", robot="pr2", human_control=False, data="ScratchItchPR2New.npz", new=True)

@@ -435,7 +435,7 @@ def main():
                                 "(fresh IK start pose + 100 settle steps per episode)" % fenv.sim.n_particles})
             fenv.close()
 
-    # ---- a `New` id (extra): ScratchItchJacoNew-v0, random-action episode from a device reset (16 persons of different height /
+    # ---- a `New` id (extra): ScratchItchJacoNew-v0, random-action episode from a device reset (32 persons of different height /
     #      waist pose as model variants, the arm pose drawn per episode with the collision-free resampling on the device) ----------
     if not args.no_episode:
         nenv = make("ScratchItchJacoNew-v0", num_envs=65536, device=local_rank, seed=1001 + rank)
@@ -454,7 +454,7 @@ def main():
         tn = reduce_max(torch.tensor([n0.elapsed_time(n1)], device=dev))
         bed.append({"env_id": "ScratchItchJacoNew-v0", "envs_per_gpu": 65536, "value": 65536 * world * 200 / (tn * 1e-3), "unit": UNIT, "steps": 200,
                     "envs_with_contact_overflow": int((ni_["contact_overflow"] != 0).sum()),
-                    "note": "random actions, full episode from a device reset; 16 model variants (persons) per batch"})
+                    "note": "random actions, full episode from a device reset; 32 model variants (persons) per batch"})
         nenv.close()
 
     # ---- mixed-task batch (extra; BASELINE.json configs[3] "mixed-task batch (all robots)"): one homogeneous sub-batch per

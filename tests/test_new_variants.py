@@ -1,7 +1,7 @@
 """`New` ids (reference `__init__.py:38-50`, `scratch_itch.py:157-159,198-228`, `human_creation.py:185-194`).
 
 What the reference draws per episode and where this build puts it:
-  * hipbone_to_mouth_height +-0.1 and the three waist angles: per MODEL VARIANT (8 per gender, compiled offline);
+  * hipbone_to_mouth_height +-0.1 and the three waist angles: per MODEL VARIANT (16 per gender, compiled offline);
   * human_impairment = 'none': the device reset (AvgResetTable.new_mode);
   * the arm pose preset + U(-10, 10) degrees per joint, redrawn until the arm is >= 0.01 from the rest of the person, the robot
     and the wheelchair: the device reset (avg_reset_new_kernel), with bounding-capsule distances (conservative for hulls).
@@ -58,9 +58,10 @@ def test_new_ids_are_registered_with_variant_draws():
         if not path_ok:
             pytest.skip(f"{REGISTRY[env_id]['data']} not compiled yet")
         blobs, resets = load_env_data(REGISTRY[env_id]["data"])
-        assert len(blobs) == 16
+        assert len(blobs) == 32                                                   # 16 persons per gender
+        npg = len(blobs) // 2
         h2m = np.array([float(r["new_h2m"]) for r in resets]); waist = np.array([r["new_waist"] for r in resets])
-        assert (np.abs(h2m[:8] - 0.6) <= 0.1).all() and (np.abs(h2m[8:] - 0.54) <= 0.1).all() and h2m.std() > 0.02
+        assert (np.abs(h2m[:npg] - 0.6) <= 0.1).all() and (np.abs(h2m[npg:] - 0.54) <= 0.1).all() and h2m.std() > 0.02
         assert (np.abs(waist) <= DEG10 + 1e-9).all() and np.abs(waist).max() > 0.5 * DEG10
         assert all(int(r["new_mode"]) == 1 for r in resets)
 
@@ -79,12 +80,13 @@ def test_gpu_new_reset_draws_and_parity(env_id):
     env.sim.enable_debug(True)
     obs0 = env.reset().cpu().numpy()
     st = env.get_state(); variants = np.asarray(env.variants)
-    assert len(set(variants.tolist())) == 16                                  # every height / waist variant is in use
+    nv = len(env.blobs)
+    assert len(set(variants.tolist())) == nv == 32                            # every height / waist variant is in use
     # human_impairment = 'none' (scratch_itch.py:159)
     assert (st[:, 96] == 1.0).all() and (st[:, 97] == 1.0).all() and (st[:, 99] == 0.0).all() and (st[:, 100:110] == 0.0).all()
     tabs = [np.frombuffer(reset_table_bytes(r), dtype=RESET_TABLE_DT)[0] for r in env.reset_data]
     gaps = st[:, 124 + 14]; attempts = st[:, 124 + 15]
-    for v in range(16):
+    for v in range(nv):
         t = tabs[v]; sel = variants == v
         nh = int(t["n_hum"])
         q = st[sel][:, t["hum_qidx"][:nh]]
@@ -166,7 +168,7 @@ def test_gpu_feeding_drinking_new_reset(env_id):
     env = make(env_id, num_envs=n, device=0, seed=9)
     obs = env.reset()
     st = env.get_state(); variants = np.asarray(env.variants)
-    assert len(set(variants.tolist())) == 16
+    assert len(set(variants.tolist())) == len(env.blobs) == 32
     assert (st[:, 96] == 1.0).all() and (st[:, 97] == 1.0).all() and (st[:, 99] == 0.0).all()
     frozen = st.view(np.uint32)[:, 175]
     assert (frozen != 0).all()                                                # head chain frozen everywhere (no tremor, not human-active)
