@@ -292,8 +292,9 @@ int avg_settle(AvgHandle* h, const uint8_t* mask, int n_steps, void* stream) {
     AvgStepArgs a; memset(&a, 0, sizeof(a));
     int rc = fill_args(h, a, 0); if (rc) return rc;
     a.mask = mask;
-    AVG_CHECK(h, avg_launch_settle(a, n_steps, (cudaStream_t)stream));
-    h->launches += (long long)n_steps * h->n_internal * (h->d_part ? 5 : 4);
+    int nl = 0;
+    AVG_CHECK(h, avg_launch_settle(a, n_steps, (cudaStream_t)stream, &nl));
+    h->launches += nl;
     return 0;
 }
 
@@ -429,8 +430,9 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
     int rc = fill_args(h, a, 0); if (rc) return rc;
     a.actions = actions; a.obs = obs; a.reward = reward; a.done = done; a.info = info;
     if (h->step_chunks < 2 || h->debug) {
-        AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream));
-        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
+        int nl = 0;
+        AVG_CHECK(h, avg_launch_step(a, h->substeps, (cudaStream_t)stream, &nl));
+        h->launches += nl;
         return 0;
     }
     /* k equal parts on k streams (k = 2 by default; still asynchronous and capturable: event fork / join around the extra streams) */
@@ -445,13 +447,14 @@ int avg_step(AvgHandle* h, const float* actions, float* obs, float* reward, uint
         if (b.env_begin >= b.env_end) break;
         cudaStream_t st = c == 0 ? (cudaStream_t)stream : (c == 1 ? h->stream2 : h->xstream[c - 2]);
         if (c > 0) AVG_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
-        AVG_CHECK(h, avg_launch_step(b, h->substeps, st));
+        int nl = 0;
+        AVG_CHECK(h, avg_launch_step(b, h->substeps, st, &nl));
+        h->launches += nl;
         if (c > 0) {
             cudaEvent_t ej = c == 1 ? h->ev_join : h->ev_xjoin[c - 2];
             AVG_CHECK(h, cudaEventRecord(ej, st));
             AVG_CHECK(h, cudaStreamWaitEvent((cudaStream_t)stream, ej, 0));
         }
-        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
     }
     return 0;
 }
@@ -512,8 +515,9 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
         int rc = fill_args(h, a, qs); if (rc) return rc;
         a.actions = h->d_act; a.obs = h->d_obs; a.reward = h->d_rew; a.done = h->d_done; a.info = h->d_info;
         a.env_begin = b0; a.env_end = b1;
-        AVG_CHECK(h, avg_launch_step(a, h->substeps, st));
-        h->launches += avg_kernels_per_step(h->substeps, h->n_internal, h->d_part != nullptr);
+        int nl = 0;
+        AVG_CHECK(h, avg_launch_step(a, h->substeps, st, &nl));
+        h->launches += nl;
         AVG_CHECK(h, cudaMemcpyAsync(dst_obs + (size_t)b0 * h->n_obs, h->d_obs + (size_t)b0 * h->n_obs, sizeof(float) * cnt * h->n_obs, cudaMemcpyDeviceToHost, st));
         AVG_CHECK(h, cudaMemcpyAsync(dst_rew + b0, h->d_rew + b0, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
         AVG_CHECK(h, cudaMemcpyAsync(dst_info + 2 * (size_t)b0, h->d_info + 2 * (size_t)b0, sizeof(float) * cnt * 2, cudaMemcpyDeviceToHost, st));

@@ -69,6 +69,14 @@
 #ifndef AVG_GJK_SHRINK
 #define AVG_GJK_SHRINK 1e-6f      /* float32 GJK stops when |v|^2 fails to shrink by this relative amount */
 #endif
+#ifndef AVG_FUSE_DEFAULT
+#define AVG_FUSE_DEFAULT 2        /* dynamics + solve as one kernel: 0 never, 1 always, 2 for launches of <= AVG_FUSE_MAX environments (AVG_FUSE overrides) */
+#endif
+#ifndef AVG_FUSE_MAX
+#define AVG_FUSE_MAX 2048         /* measured on a B200 (staggered episodes): 64 / 1024 / 2048 / 4096 envs (= halves of <= 2048) +4..7 %, ScratchItchJacoHuman / BedBathingPR2
+                                     at 4096 envs +11 / +8 %; halves of 4096: -1 %, of 8192: -9 %, of 98304: -22 % (80 registers and no phase alignment
+                                     of the 116 KB dynamics code across the warps of an SM) */
+#endif
 #ifndef AVG_GJK_ITERS
 #define AVG_GJK_ITERS 32
 #endif
@@ -1032,16 +1040,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // =================================================================================================================
 // action -> motor targets, env.py:274-337 (one lane per dof; no shared memory)
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
-avg_prologue_kernel(AvgStepArgs a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = a.env_begin + blockIdx.x * (blockDim.x >> 5) + warp;
-    if (e >= a.env_end) return;
-    const int variant = a.variant ? a.variant[e] : 0;
-    const KM m = c_models[a.slot][variant];
+__device__ __forceinline__ void prologue_body(const AvgStepArgs& a, const int e, const int lane, const KM& m, float* grec, float* scr) {
     const AvgModelHeader* h = m.h;
-    float* grec = a.env + (size_t)e * AVG_ENV_STRIDE;
-    int* scr_i = reinterpret_cast<int*>(a.scratch + (size_t)e * AVG_S_STRIDE);
+    int* scr_i = reinterpret_cast<int*>(scr);
     const int nj = h->n_jdof;
     const int na = h->n_action_robot + h->n_action_human;
     const float* act = a.actions + (size_t)e * na;
@@ -1083,18 +1084,29 @@ avg_prologue_kernel(AvgStepArgs a) {
         scr_i[AVG_S_ITERS] = 0; scr_i[AVG_S_OVERFLOW] = 0; scr_i[AVG_S_NCAND] = 0;
     }
 }
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_prologue_kernel(AvgStepArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = a.env_begin + blockIdx.x * (blockDim.x >> 5) + warp;
+    if (e >= a.env_end) return;
+    const int variant = a.variant ? a.variant[e] : 0;
+    const KM m = c_models[a.slot][variant];
+    prologue_body(a, e, lane, m, a.env + (size_t)e * AVG_ENV_STRIDE, a.scratch + (size_t)e * AVG_S_STRIDE);
+}
 
 // =================================================================================================================
 // forward kinematics + collision -> contact list in the scratch arena
 // =================================================================================================================
-__global__ void __launch_bounds__(32 * AVG_WPB_COLLIDE, AVG_OCC_COLLIDE)
-avg_collide_kernel(AvgStepArgs a) {
-    AVG_KERNEL_PREAMBLE(SmCollide)
+// Body of the collide kernel for ONE environment.  The work items go to `np_queue` / `np_count` (the global narrowphase queue).
+template <int PF_AHEAD>
+__device__ __forceinline__ void collide_body(const AvgStepArgs& a, SmCollide& s, const int e, const int lane, const KM& m, float* grec, float* scr,
+                                             AvgNpItem* np_queue, int* np_count, int np_capacity) {
+    const AvgModelHeader* h = m.h;
     AVG_MASK_CHECK
     s.q[lane] = grec[AVG_E_Q + lane];
     {   // L2 prefetch for the environment whose warp takes this slot next: positions (1 line), counters (1), certificate cache (3)
-        const int ea = e + 148 * AVG_OCC_COLLIDE * AVG_WPB_COLLIDE * AVG_PF_PCT / 100;
-        if (ea < a.env_end) {
+        const int ea = e + PF_AHEAD;
+        if (PF_AHEAD > 0 && ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
             const float* p = lane < 1 ? r2 : (lane < 2 ? s2 : (lane < 5 ? s2 + AVG_S_SEP + 4 * AVG_S_NSEPMAX * (lane - 2) : nullptr));   // first 8 certificates of each of the 3 planes
             if (p) prefetch_l2(p);
@@ -1112,9 +1124,14 @@ avg_collide_kernel(AvgStepArgs a) {
     float4* gsep = reinterpret_cast<float4*>(scr + AVG_S_SEP);
     int nsep = (a.dbg & 16) ? 0 : min(max(scr_i[AVG_S_NSEP], 0), AVG_S_NSEPMAX);
     if (lane < nsep) { s.sep[0][lane] = gsep[lane]; s.sep[1][lane] = gsep[AVG_S_NSEPMAX + lane]; s.sep[2][lane] = gsep[2 * AVG_S_NSEPMAX + lane]; }
-    if (!(a.dbg & 4)) collide_warp(m, s, lane, e, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, a.np_queue, a.np_count,
-                                   a.np_capacity, a.dbg);
+    if (!(a.dbg & 4)) collide_warp(m, s, lane, e, nc, overflow, ncand, nsep, scr + AVG_S_SEP, nsep_out, np_queue, np_count,
+                                   np_capacity, a.dbg);
     if (lane == 0) { scr_i[AVG_S_NQ] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
+}
+__global__ void __launch_bounds__(32 * AVG_WPB_COLLIDE, AVG_OCC_COLLIDE)
+avg_collide_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmCollide)
+    collide_body<148 * AVG_OCC_COLLIDE * AVG_WPB_COLLIDE * AVG_PF_PCT / 100>(a, s, e, lane, m, grec, scr, a.np_queue, a.np_count, a.np_capacity);
 }
 
 // =================================================================================================================
@@ -1137,30 +1154,14 @@ __device__ __forceinline__ void np_load_shape(const KM& m, const float* scr, int
 }
 }  // namespace
 
-// OCC = blocks per SM the instance is compiled for: 3 (151 registers, nothing spilled) for small batches, where the step waits
-// for the slowest warp of this kernel, AVG_OCC_NARROW (85 registers, a few spills) for large ones, where more resident warps
-// hide the latency of the lockstep GJK (+4 % on an in-contact policy rollout at 196608 environments).
-template <int OCC>
-__global__ void __launch_bounds__(128, OCC)
-avg_narrow_kernel(AvgStepArgs a) {
-    // one THREAD per work item; the 32 items of a warp advance through the certificate test and the GJK iterations in
-    // lockstep so that hull support scans can be served by the whole warp (support_any)
-    const int count = min(a.np_count[0], a.np_capacity);
-    const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    // Items per warp.  A full queue gives every warp 32 items (throughput: the lockstep iterations are shared by 32 pairs).  A
-    // short queue (small batches: ~1 item per environment and sub-step) is spread over the warps the GPU can hold at once
-    // instead -- a warp with few items finishes its lockstep GJK in a fraction of the time (fewer iterations to wait for, every
-    // hull scan served by the whole warp), and at a small batch the step waits for the slowest warp of this kernel.
-    // (Only at small batches: spreading costs instructions -- fewer pairs share a lockstep iteration -- and at a large batch this
-    // kernel overlaps with the other half's kernels, so there its instruction count matters, not its latency: -3 % when spread.)
-    const int ipw = (a.env_end - a.env_begin) > 16384 ? 32 : min(32, max(1, (count + AVG_NARROW_WARPS - 1) / AVG_NARROW_WARPS));
-    for (int base = wid * ipw; base < count; base += nwarps * ipw) {
+// One slab of the narrowphase: lane l < ipw of a converged warp takes item base + l of `queue` (items [0, count)).
+__device__ __forceinline__ void narrow_slab(const AvgStepArgs& a, const AvgNpItem* queue, const int base, const int count, const int ipw, const int lane) {
+    {
         const int i = base + lane;
         const bool valid = lane < ipw && i < count;
         const long long t_begin = a.dbg_counters ? clock64() : 0;
         AvgNpItem it; it.env = 0; it.pair = 0; it.slot = 0; it.cert = -1;
-        if (valid) it = a.np_queue[i];
+        if (valid) it = queue[i];
         const int variant = (valid && a.variant) ? a.variant[it.env] : 0;
         const KM m = c_models[a.slot][variant];
         float* scr = a.scratch + (size_t)it.env * AVG_S_STRIDE;
@@ -1263,6 +1264,26 @@ avg_narrow_kernel(AvgStepArgs a) {
         __syncwarp();
     }
 }
+// OCC = blocks per SM the instance is compiled for: 3 (151 registers, nothing spilled) for small batches, where the step waits
+// for the slowest warp of this kernel, AVG_OCC_NARROW (85 registers, a few spills) for large ones, where more resident warps
+// hide the latency of the lockstep GJK (+4 % on an in-contact policy rollout at 196608 environments).
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC)
+avg_narrow_kernel(AvgStepArgs a) {
+    // one THREAD per work item; the 32 items of a warp advance through the certificate test and the GJK iterations in
+    // lockstep so that hull support scans can be served by the whole warp (support_any)
+    const int count = min(a.np_count[0], a.np_capacity);
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    // Items per warp.  A full queue gives every warp 32 items (throughput: the lockstep iterations are shared by 32 pairs).  A
+    // short queue (small batches: ~1 item per environment and sub-step) is spread over the warps the GPU can hold at once
+    // instead -- a warp with few items finishes its lockstep GJK in a fraction of the time (fewer iterations to wait for, every
+    // hull scan served by the whole warp), and at a small batch the step waits for the slowest warp of this kernel.
+    // (Only at small batches: spreading costs instructions -- fewer pairs share a lockstep iteration -- and at a large batch this
+    // kernel overlaps with the other half's kernels, so there its instruction count matters, not its latency: -3 % when spread.)
+    const int ipw = (a.env_end - a.env_begin) > 16384 ? 32 : min(32, max(1, (count + AVG_NARROW_WARPS - 1) / AVG_NARROW_WARPS));
+    for (int base = wid * ipw; base < count; base += nwarps * ipw) narrow_slab(a, a.np_queue, base, count, ipw, lane);
+}
 
 // J.dv over the warp, the inner operation of every dense Gauss-Seidel row.  A float butterfly costs five DEPENDENT shuffle +
 // add stages (~150 cycles on the row-to-row dependency chain that bounds this kernel, profiles/ncu_full_r1p.txt).
@@ -1291,10 +1312,10 @@ __device__ __forceinline__ float dense_dot(float j, float dv) {
 // =================================================================================================================
 // dynamics + constraint rows -> row arena
 // =================================================================================================================
-template <int MAXBLK>
-__global__ void __launch_bounds__(32 * AVG_WPB_DYN, AVG_OCC_DYN)
-avg_dynamics_kernel(AvgStepArgs a) {
-    AVG_KERNEL_PREAMBLE(SmDyn)
+// Body of the dynamics kernel for ONE environment (one warp).  PF_AHEAD: distance (in environments) of the L2 prefetch hints.
+template <int MAXBLK, int PF_AHEAD>
+__device__ __forceinline__ void dynamics_body(const AvgStepArgs& a, SmDyn& s, const int e, const int lane, const KM& m, float* grec, float* scr) {
+    const AvgModelHeader* h = m.h;
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
     const V3 ref = mk3(h->task_f[16], h->task_f[17], h->task_f[18]);
@@ -1302,8 +1323,8 @@ avg_dynamics_kernel(AvgStepArgs a) {
     for (int i = lane; i < AVG_E_EBODY; i += 32) s.env[i] = grec[i];
     {   // what this kernel reads first, for the environment whose warp takes this slot next: record (4 lines), counters (1),
         // body poses (6), narrowphase results (4)
-        const int ea = e + 148 * AVG_OCC_DYN * AVG_WPB_DYN * AVG_PF_PCT / 100;
-        if (ea < a.env_end) {
+        const int ea = e + PF_AHEAD;
+        if (PF_AHEAD > 0 && ea < a.env_end) {
             const float* r2 = a.env + (size_t)ea * AVG_ENV_STRIDE; const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
             const float* p = lane < 4 ? r2 + 32 * lane : (lane < 5 ? s2 : (lane < 11 ? s2 + AVG_S_POSE + 32 * (lane - 5) : (lane < 15 ? s2 + AVG_S_NPRES + 32 * (lane - 11) : nullptr)));   // 24 bodies, 8 results: what is usually there
             if (p) prefetch_l2(p);
@@ -1745,6 +1766,13 @@ avg_dynamics_kernel(AvgStepArgs a) {
     }
 }
 
+template <int MAXBLK>
+__global__ void __launch_bounds__(32 * AVG_WPB_DYN, AVG_OCC_DYN)
+avg_dynamics_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmDyn)
+    dynamics_body<MAXBLK, 148 * AVG_OCC_DYN * AVG_WPB_DYN * AVG_PF_PCT / 100>(a, s, e, lane, m, grec, scr);
+}
+
 // enforce_realistic_human_joint_limits, env.py:353-371: Dense 4 -> 64 tanh -> 64 tanh -> 64 tanh -> 1; lane u evaluates
 // hidden units u and u + 32, activations are exchanged by shuffles, weight rows are read coalesced (L1-resident).
 // Returns the logit (class 1 <=> logit > 0), identical in every lane.
@@ -2104,10 +2132,11 @@ __device__ void particles_finish(const KM& m, const SP& sp, const AvgStepArgs& a
 // projected Gauss-Seidel + integration + human hard limits
 // =================================================================================================================
 // PART: 0 no particles, 1 Feeding (8 particles), 2 Drinking (64 particles)
-template <int MAXBLK, int PART>
-__global__ void __launch_bounds__(32, PART ? 20 : AVG_OCC_SOLVE)
-avg_solve_kernel(AvgStepArgs a) {
-    AVG_KERNEL_PREAMBLE(SmSolve)
+// Body of the solve kernel for ONE environment (one warp).  PF_AHEAD: distance of the L2 prefetch hints (0: none -- the fused
+// dynamics + solve kernel reads rows its own warp has just written); part_smem: the particle block behind SmSolve (PART > 0).
+template <int MAXBLK, int PART, int PF_AHEAD>
+__device__ __forceinline__ void solve_body(const AvgStepArgs& a, SmSolve& s, unsigned char* part_smem, const int e, const int lane, const KM& m, float* grec, float* scr) {
+    const AvgModelHeader* h = m.h;
     AVG_MASK_CHECK
     const int nb = h->n_body, nj = h->n_jdof, nd = h->n_dof;
     const float dt = h->dt;
@@ -2117,8 +2146,8 @@ avg_solve_kernel(AvgStepArgs a) {
     const float* gJ = scr + AVG_S_J; const float* gW = scr + AVG_S_W;
     {   // L2 prefetch for the environment whose warp takes this slot next: counters + velocities (1 line), motor / limit rows (4),
         // weld rows (2), M^-1 columns (10), J and W of the weld rows (6 + 6)
-        const int ea = e + 148 * AVG_OCC_SOLVE * AVG_PF_PCT / 100;
-        if (ea < a.env_end) {
+        const int ea = e + PF_AHEAD;
+        if (PF_AHEAD > 0 && ea < a.env_end) {
             const float* s2 = a.scratch + (size_t)ea * AVG_S_STRIDE;
             const float* p = lane < 1 ? s2 : (lane < 5 ? s2 + AVG_S_ROWS_M + 32 * (lane - 1) : (lane < 7 ? s2 + AVG_S_ROWS_D + 32 * (lane - 5)
                            : (lane < 17 ? s2 + AVG_S_MINV + 32 * (lane - 7) : (lane < 23 ? s2 + AVG_S_J + 32 * (lane - 17) : (lane < 29 ? s2 + AVG_S_W + 32 * (lane - 23) : nullptr)))));
@@ -2177,7 +2206,7 @@ avg_solve_kernel(AvgStepArgs a) {
     __syncwarp();
     // particles (Feeding / Drinking): records, schedule and unconstrained velocities for this internal step
     using SP = typename std::conditional<PART == 2, SmPartLarge, SmPartSmall>::type;
-    SP* spp = PART ? reinterpret_cast<SP*>(smem_raw + sizeof(SmSolve)) : nullptr;
+    SP* spp = PART ? reinterpret_cast<SP*>(part_smem) : nullptr;
     int npc = 0, nrounds = 0, p_overflow = 0, tool_dof = -1;
     float* prec_rows = nullptr;
     if (PART) {
@@ -2361,6 +2390,32 @@ avg_solve_kernel(AvgStepArgs a) {
     }
 }
 
+template <int MAXBLK, int PART>
+__global__ void __launch_bounds__(32, PART ? 20 : AVG_OCC_SOLVE)
+avg_solve_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmSolve)
+    solve_body<MAXBLK, PART, 148 * AVG_OCC_SOLVE * AVG_PF_PCT / 100>(a, s, smem_raw + sizeof(SmSolve), e, lane, m, grec, scr);
+}
+
+// Dynamics + solve of one internal step in ONE kernel (no particles): the warp that built an environment's rows sweeps them,
+// reading them back from the arena lines it has just written (L2 hits instead of an HBM round trip across two kernels), and
+// the sub-step is one launch shorter.  Shared memory is the union of the two bodies' blocks.
+#ifndef AVG_WPB_FUSED
+#define AVG_WPB_FUSED 1
+#endif
+#ifndef AVG_OCC_FUSED
+#define AVG_OCC_FUSED (24 / AVG_WPB_FUSED)
+#endif
+union __align__(16) SmDynSolve { SmDyn d; SmSolve s; };
+template <int MAXBLK>
+__global__ void __launch_bounds__(32 * AVG_WPB_FUSED, AVG_OCC_FUSED)
+avg_dynsolve_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmDynSolve)
+    dynamics_body<MAXBLK, 148 * AVG_OCC_FUSED * AVG_WPB_FUSED * AVG_PF_PCT / 100>(a, s.d, e, lane, m, grec, scr);
+    __syncwarp();
+    solve_body<MAXBLK, 0, 0>(a, s.s, nullptr, e, lane, m, grec, scr);
+}
+
 // =================================================================================================================
 // forces, reward, observation, info (scratch_itch.py:53-128)
 // =================================================================================================================
@@ -2404,9 +2459,8 @@ __device__ void fill_obs(const KM& m, SM& s, V3 tgt, float tool_force, float tot
 }
 }  // namespace
 
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
-avg_epilogue_kernel(AvgStepArgs a) {
-    AVG_KERNEL_PREAMBLE(SmEpi)
+__device__ __forceinline__ void epilogue_body(const AvgStepArgs& a, SmEpi& s, const int e, const int lane, const KM& m, float* grec, float* scr) {
+    const AvgModelHeader* h = m.h;
     for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
     __syncwarp();
     int* env_i = reinterpret_cast<int*>(s.env);
@@ -2505,6 +2559,11 @@ avg_epilogue_kernel(AvgStepArgs a) {
         }
         if (lane == 0) a.ncontacts[e] = ncontact;
     }
+}
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_epilogue_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmEpi)
+    epilogue_body(a, s, e, lane, m, grec, scr);
 }
 
 // =================================================================================================================
@@ -2637,9 +2696,8 @@ __device__ void dump_contacts(const AvgStepArgs& a, int e, const float* scr, int
 }
 }  // namespace
 
-__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
-avg_epilogue_bb_kernel(AvgStepArgs a) {
-    AVG_KERNEL_PREAMBLE(SmEpiBB)
+__device__ __forceinline__ void epilogue_bb_body(const AvgStepArgs& a, SmEpiBB& s, const int e, const int lane, const KM& m, float* grec, float* scr) {
+    const AvgModelHeader* h = m.h;
     for (int i = lane; i < AVG_ENV_STRIDE; i += 32) s.env[i] = grec[i];
     __syncwarp();
     int* env_i = reinterpret_cast<int*>(s.env);
@@ -2783,6 +2841,11 @@ avg_epilogue_bb_kernel(AvgStepArgs a) {
     const int nobs = h->n_obs_robot + h->n_obs_human;
     for (int i = lane; i < nobs; i += 32) a.obs[(size_t)e * nobs + i] = s.obs[i];
     if (a.contacts) dump_contacts(a, e, scr, ncontact, dt, lane);
+}
+__global__ void __launch_bounds__(32 * AVG_K_WARPS_PER_BLOCK)
+avg_epilogue_bb_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmEpiBB)
+    epilogue_bb_body(a, s, e, lane, m, grec, scr);
 }
 
 // =================================================================================================================
@@ -3736,8 +3799,6 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-int avg_kernels_per_step(int substeps, int n_internal, int particles) { return 2 + (particles ? 5 : 4) * substeps * (n_internal > 0 ? n_internal : 1); }
-
 // warps (= environments) per block, per kernel.  The solver uses one warp per block: its iteration count varies per
 // environment (residual early exit), and a block holds its shared memory until its slowest warp is done.
 constexpr int kWpbCollide = AVG_WPB_COLLIDE, kWpbDyn = AVG_WPB_DYN, kWpbSolve = 1, kWpbEpi = 4, kWpbPro = 4, kWpbPCol = 4;
@@ -3769,6 +3830,11 @@ cudaError_t configure_kernels() {
     if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<12>, sm_dyn)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<16>, sm_dyn)) != cudaSuccess) return e1;
+    const size_t sm_fus = sizeof(SmDynSolve) * AVG_WPB_FUSED;
+    if ((e1 = set_smem(avg_dynsolve_kernel<8>, sm_fus)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynsolve_kernel<10>, sm_fus)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynsolve_kernel<12>, sm_fus)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_dynsolve_kernel<16>, sm_fus)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_solve_kernel<8, 0>, sm_sol)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_solve_kernel<10, 0>, sm_sol)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_solve_kernel<12, 0>, sm_sol)) != cudaSuccess) return e1;
@@ -3803,6 +3869,17 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
     if (n_range > 16384) avg_narrow_kernel<AVG_OCC_NARROW><<<np_grid, 128, 0, stream>>>(a);
     else avg_narrow_kernel<3><<<np_grid, 128, 0, stream>>>(a);
     mark(5);
+    static const int fuse_mode = [] { const char* c = getenv("AVG_FUSE"); return c ? atoi(c) : AVG_FUSE_DEFAULT; }();   // 0 never, 1 always, 2 small batches
+    if (!part && (fuse_mode == 1 || (fuse_mode == 2 && n_range <= AVG_FUSE_MAX))) {
+        const size_t sm_fus = sizeof(SmDynSolve) * AVG_WPB_FUSED;
+        const int g = grid(AVG_WPB_FUSED);
+        if (a.maxblk <= 8) avg_dynsolve_kernel<8><<<g, 32 * AVG_WPB_FUSED, sm_fus, stream>>>(a);
+        else if (a.maxblk <= 10) avg_dynsolve_kernel<10><<<g, 32 * AVG_WPB_FUSED, sm_fus, stream>>>(a);
+        else if (a.maxblk <= 12) avg_dynsolve_kernel<12><<<g, 32 * AVG_WPB_FUSED, sm_fus, stream>>>(a);
+        else avg_dynsolve_kernel<16><<<g, 32 * AVG_WPB_FUSED, sm_fus, stream>>>(a);
+        mark(3);
+        return;
+    }
     if (a.maxblk <= 8) avg_dynamics_kernel<8><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
     else if (a.maxblk <= 10) avg_dynamics_kernel<10><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
     else if (a.maxblk <= 12) avg_dynamics_kernel<12><<<grid(kWpbDyn), 32 * kWpbDyn, sm_dyn, stream>>>(a);
@@ -3825,7 +3902,7 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
 }
 }  // namespace
 
-cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t stream) {
+cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t stream, int* launched) {
     cudaError_t ec = configure_kernels();
     if (ec != cudaSuccess) return ec;
     static bool env_read = false;
@@ -3841,8 +3918,9 @@ cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t 
     int nev = 0; int kinds[128];
     if (kt_on && !g_kt.init) { for (int i = 0; i < 128; ++i) cudaEventCreate(&g_kt.ev[i]); g_kt.init = true; }
     static const bool sync_each = getenv("AVG_SYNC_EACH") != nullptr;        // development aid: name the kernel that faults
-    int kseq = 0;
+    int kseq = 0, nlaunch = 0;
     auto mark = [&](int kind) {
+        if (kind >= 0) nlaunch++;
         if (kt_on && nev < 128) { kinds[nev] = kind; cudaEventRecord(g_kt.ev[nev++], stream); }
         if (sync_each) {
             const cudaError_t e = cudaStreamSynchronize(stream);
@@ -3875,17 +3953,20 @@ cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t 
             for (int i = 0; i < 7; ++i) g_kt.ms[i] = 0;
         }
     }
+    if (launched) *launched = nlaunch;
     return cudaGetLastError();
 }
 
-cudaError_t avg_launch_settle(const AvgStepArgs& a_in, int n, cudaStream_t stream) {
+cudaError_t avg_launch_settle(const AvgStepArgs& a_in, int n, cudaStream_t stream, int* launched) {
     cudaError_t ec = configure_kernels();
     if (ec != cudaSuccess) return ec;
     AvgStepArgs a = a_in;
     a.post = 0;                                      // reset() calls p.stepSimulation only: no per-frame hooks (feeding.py:318-320)
     if (a.env_end - a.env_begin <= 0) return cudaSuccess;
     const int n_internal = a.n_internal > 0 ? a.n_internal : 1;
-    for (int i = 0; i < n * n_internal; ++i) launch_internal_step(a, stream, [](int) {});
+    int nlaunch = 0;
+    for (int i = 0; i < n * n_internal; ++i) launch_internal_step(a, stream, [&](int) { nlaunch++; });
+    if (launched) *launched = nlaunch;
     return cudaGetLastError();
 }
 

@@ -96,11 +96,11 @@ struct AvgStepArgs {
     unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)
 };
 
-int avg_kernels_per_step(int substeps, int n_internal, int particles);
-cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream);
+/* `launched` (optional) receives the number of kernels the call launched (22 for a ScratchItch step, 17 with the fused dynamics + solve kernel). */
+cudaError_t avg_launch_step(const AvgStepArgs& a, int substeps, cudaStream_t stream, int* launched = nullptr);
 /* `n` calls of p.stepSimulation without actions, hooks or epilogue for the environments of a.mask: the settle loop of
  * FeedingEnv.reset / DrinkingEnv.reset (feeding.py:318-320). */
-cudaError_t avg_launch_settle(const AvgStepArgs& a, int n, cudaStream_t stream);
+cudaError_t avg_launch_settle(const AvgStepArgs& a, int n, cudaStream_t stream, int* launched = nullptr);
 cudaError_t avg_launch_reset_obs(const AvgStepArgs& a, cudaStream_t stream);
 cudaError_t avg_launch_arm_limit(const unsigned char* blob, const float* q4, float* logits, int n, cudaStream_t stream);
 /* Publish the section pointers of a device ModelBlob in the constant-memory table read by the kernels (current device). */

@@ -317,3 +317,19 @@ def test_cuda_graph_rollout_with_device_auto_reset(torch_cuda):
     assert np.array_equal(envs[0].get_state().view(np.uint32), envs[1].get_state().view(np.uint32))
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("env_id,n", [("ScratchItchJaco-v0", 1500), ("BedBathingPR2-v0", 700), ("ScratchItchJacoHuman-v0", 300)])
+def test_fused_dynamics_solve_kernel_is_bit_identical(torch_cuda, env_id, n):
+    """Small launches run dynamics + solve of a sub-step as one kernel (avg_dynsolve_kernel, AVG_FUSE): the same two bodies, so the
+    environment records after a seeded roll are bit for bit those of the two-kernel pipeline.  The switch is read once per process,
+    hence the two sub-processes."""
+    import re, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sha = []
+    for fuse in ("0", "1"):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_state_hash.py"), env_id, str(n), "12"], capture_output=True, text=True,
+                             env=dict(os.environ, AVG_FUSE=fuse), timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        sha.append(re.search(r"state sha1 ([0-9a-f]{40})", out.stdout).group(1))
+    assert sha[0] == sha[1]
