@@ -18,7 +18,7 @@ agg = collections.defaultdict(lambda: collections.defaultdict(list))
 for (i, k), m in d.items():
     for mm, v in m.items(): agg[k][mm].append(v)
 # launches of each of our kernels in one env-step of one (half-)batch: a list cut at an arbitrary launch is normalised by these
-PER_STEP = {"avg_solve": 5, "avg_dynamics": 5, "avg_collide": 5, "avg_narrow": 5, "avg_epilogue": 1, "avg_prologue": 1}
+PER_STEP = {"avg_dynsolve": 5, "avg_solve": 5, "avg_dynamics": 5, "avg_collide": 5, "avg_narrow": 5, "avg_epilogue": 1, "avg_prologue": 1}
 def per_step(k):
     return next((c for n, c in PER_STEP.items() if n in k), 0)
 tot = sum(sum(v['gpu__time_duration.sum']) for v in agg.values())
