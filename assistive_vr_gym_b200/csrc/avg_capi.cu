@@ -122,7 +122,7 @@ int avg_create(int device, int n_env, AvgHandle** out) {
     /* avg_step splits the batch into two halves on two streams: the kernels of one half fill the tails (and the
        sparsely populated narrowphase kernel) of the other; at small batches (one partial wave per kernel) the two dependent
        chains of short kernels overlap (+7 % at 4096 environments).  AVG_STEP_CHUNKS=1 restores the single-stream sequence. */
-    h->step_chunks = n_env >= 2048 ? 2 : 1;
+    h->step_chunks = (n_env >= 2048 && n_env < 131072) ? 2 : 1;      /* staggered episodes, one B200: 32768 envs +6.6 %, 65536 +1.6 %, 131072 / 196608 +-0.5 %, 393216 -1.6 % */
     { const char* c = getenv("AVG_STEP_CHUNKS"); if (c && atoi(c) > 0) h->step_chunks = atoi(c) > 4 ? 4 : atoi(c); }
     for (int k = 0; k < 2; ++k) { cudaStreamCreateWithFlags(&h->xstream[k], cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_xjoin[k], cudaEventDisableTiming); }
     *out = h;
@@ -501,7 +501,8 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
     }
     /* The batch is stepped in chunks that alternate between two streams, so the device->host copy of one chunk's
        results (and the host->device copy of the next chunk's actions) overlaps the kernels of the other chunk. */
-    int n_chunks = h->n_env >= 16384 ? 2 : 1;           /* measured on B200 at 196608 envs: 1 -> 22.15, 2 -> 22.08, 4 -> 22.6, 8 -> 24.0 ms */
+    int n_chunks = (h->n_env >= 16384 && h->n_env < 262144) ? 2 : 1;    /* measured on B200 at 196608 envs: 1 -> 22.15, 2 -> 22.08, 4 -> 22.6, 8 -> 24.0 ms;
+                                                                           at 393216: 1 -> 47.19, 2 -> 47.76, 3 -> 48.43, 4 -> 48.62 ms (device-resident step: 46.93) */
     { const char* c = getenv("AVG_CHUNKS"); if (c && atoi(c) > 0) n_chunks = atoi(c); }
     const int per = ((h->n_env + n_chunks - 1) / n_chunks + 3) & ~3;
     for (int c = 0; c < n_chunks; ++c) {

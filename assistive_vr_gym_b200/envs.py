@@ -364,13 +364,17 @@ class BatchedAssistiveEnv:
             self._pinned = [capi.PinnedArray((self.num_envs, self.sim.n_obs), np.float32), capi.PinnedArray((self.num_envs,), np.float32),
                             capi.PinnedArray((self.num_envs,), np.uint8), capi.PinnedArray((self.num_envs, 2), np.float32)]
             self._h_obs, self._h_rew, self._h_done, self._h_info = (p.array for p in self._pinned)
+            self._h_success = np.empty(self.num_envs, dtype=np.int32); self._h_doneb = np.empty(self.num_envs, dtype=bool)
         self.sim.step_host(a, self._h_obs, self._h_rew, self._h_done, self._h_info)
         self.elapsed += 1
         timeout = self.elapsed >= MAX_EPISODE_STEPS
-        info = {"total_force_on_human": self._h_info[:, 0], "task_success": self._h_info[:, 1].astype(np.int32),
+        np.copyto(self._h_success, self._h_info[:, 1], casting="unsafe")      # preallocated: no 1.5 MB allocation per step at 393216 envs
+        if timeout: self._h_doneb.fill(True)
+        else: np.not_equal(self._h_done, 0, out=self._h_doneb)
+        info = {"total_force_on_human": self._h_info[:, 0], "task_success": self._h_success,
                 "action_robot_len": self.action_robot_len, "action_human_len": self.action_human_len,
                 "obs_robot_len": self.obs_robot_len, "obs_human_len": self.obs_human_len}
-        return self._h_obs, self._h_rew, self._h_done.astype(bool) | timeout, info
+        return self._h_obs, self._h_rew, self._h_doneb, info
 
     def pinned_actions(self) -> np.ndarray:
         """A page-locked [N, A] float32 array: actions written here reach the GPU without a staging copy."""

@@ -259,6 +259,9 @@ def main():
             env.reset_device(mask=(gid == (k // 20)))
         act_ep.uniform_(-1, 1, generator=gen)
         env.step(act_ep); env.elapsed = 0
+    # the state the timed window starts from (+ W warm-up steps): the end-to-end measurement below restarts from it, so both
+    # numbers cover the SAME steps of the same episodes (a batch that just rolls on gets slower: more environments in contact)
+    snap_state = env.get_state(); snap_variants = env.sim.get_variants().copy()
     for w in range(W):
         env.step(ring[w % len(ring)]); env.elapsed = 0
     barrier()
@@ -282,16 +285,18 @@ def main():
     reduce_episode_stats(stats)
     value = E * world * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end through the host-buffer API: the same steps of the episode as the device-resident measurement
-    #      (fresh reset with the same seed, W warm-up steps, then the timed steps), so the two numbers differ only by the
-    #      host<->device traffic (same staggered batch, a few steps later).  Actions sit in page-locked arrays (a caller writes its policy output there); results
+    # ---- end-to-end through the host-buffer API: the same steps of the same episodes as the device-resident measurement
+    #      (the staggered batch restored from its snapshot, the same W warm-up steps and actions, then the timed steps), so the
+    #      two numbers differ only by the host<->device traffic and the host-side call.  Actions sit in page-locked arrays (a caller writes its policy output there); results
     #      come back in the env's own pinned arrays.
     from assistive_vr_gym_b200 import capi
     e2e_steps = max(3, min(args.steps, 20))
     a_pin = [capi.PinnedArray((E, 7), np.float32) for _ in range(min(W + e2e_steps, 32))]
     for i, p in enumerate(a_pin):
         p.array[...] = ring[i % len(ring)].cpu().numpy()
-    for w in range(W):                               # continues on the staggered batch of the device-resident measurement
+    env.set_state(snap_state, snap_variants)         # the staggered batch as it was before the device-resident measurement
+    del snap_state
+    for w in range(W):
         env.step_host(a_pin[w % len(a_pin)].array); env.elapsed = 0
     barrier()
     t0 = time.perf_counter()
