@@ -563,7 +563,7 @@ def main():
                                       "note": "the same K steps taken right after a reset (few contacts yet): NOT the headline"},
                 "envs_with_contact_overflow": int(overflow_envs),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                             "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (22 kernels x 2 half-batches on 2 streams)" % (launches // max(1, args.steps)),
+                             "peak_source": peak_src, "bytes_per_env_step": bpe, "launch": "the %d kernel launches of one env-step (prologue, 5 x (collide, narrowphase, dynamics, solve), epilogue; batches of 2048 .. 131071 environments step as two halves on two streams)" % (launches // max(1, args.steps)),
                              "issue_slots": (lambda s: None if not s else dict(s, achieved_warp_inst_per_s=s["warp_inst_per_env_step"] * value / world,
                                                                                   frac=s["warp_inst_per_env_step"] * value / world / s["peak_warp_inst_per_s"]))(prof.get("issue_slots")),
                              "fp32": (lambda fp: None if not fp else {"flop_per_env_step": fp["flop_per_env_step_substep_kernels"],
