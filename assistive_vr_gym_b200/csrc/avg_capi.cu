@@ -504,7 +504,40 @@ int avg_step_host(AvgHandle* h, const float* actions, float* obs, float* reward,
     int n_chunks = (h->n_env >= 16384 && h->n_env < 262144) ? 2 : 1;    /* measured on B200 at 196608 envs: 1 -> 22.15, 2 -> 22.08, 4 -> 22.6, 8 -> 24.0 ms;
                                                                            at 393216: 1 -> 47.19, 2 -> 47.76, 3 -> 48.43, 4 -> 48.62 ms (device-resident step: 46.93) */
     { const char* c = getenv("AVG_CHUNKS"); if (c && atoi(c) > 0) n_chunks = atoi(c); }
-    const int per = ((h->n_env + n_chunks - 1) / n_chunks + 3) & ~3;
+    /* One chunk (large batches): the sub-steps of the whole batch as one sequence, then the epilogue range by range on the same
+       stream with each range's device->host copies on the second stream, so the copies overlap the epilogue of the next range
+       (52 MB of results at 393216 environments: ~1 ms on PCIe 5, the epilogue ~1.1 ms). */
+    int n_tail = (n_chunks == 1 && h->n_env >= 65536) ? 4 : 0;
+    { const char* c = getenv("AVG_TAIL_RANGES"); if (c && n_chunks == 1) n_tail = atoi(c) > 4 ? 4 : atoi(c); }
+    if (n_tail > 1) {
+        cudaStream_t st = h->stream, st2 = h->stream2;
+        AVG_CHECK(h, cudaMemcpyAsync(h->d_act, src_act, sizeof(float) * n * h->n_act, cudaMemcpyHostToDevice, st));
+        AvgStepArgs a; memset(&a, 0, sizeof(a));
+        int rc = fill_args(h, a, 0); if (rc) return rc;
+        a.actions = h->d_act; a.obs = h->d_obs; a.reward = h->d_rew; a.done = h->d_done; a.info = h->d_info;
+        a.phase = 1;
+        int nl = 0;
+        AVG_CHECK(h, avg_launch_step(a, h->substeps, st, &nl));
+        h->launches += nl;
+        const int per_t = ((h->n_env + n_tail - 1) / n_tail + 3) & ~3;
+        for (int c = 0; c < n_tail; ++c) {
+            const int b0 = c * per_t, b1 = (c + 1) * per_t < h->n_env ? (c + 1) * per_t : h->n_env;
+            if (b0 >= b1) break;
+            const size_t cnt = (size_t)(b1 - b0);
+            a.phase = 2; a.env_begin = b0; a.env_end = b1;
+            AVG_CHECK(h, avg_launch_step(a, h->substeps, st, &nl));
+            h->launches += nl;
+            cudaEvent_t ev = c == 0 ? h->ev_fork : (c == 1 ? h->ev_join : h->ev_xjoin[c - 2]);
+            AVG_CHECK(h, cudaEventRecord(ev, st));
+            AVG_CHECK(h, cudaStreamWaitEvent(st2, ev, 0));
+            AVG_CHECK(h, cudaMemcpyAsync(dst_obs + (size_t)b0 * h->n_obs, h->d_obs + (size_t)b0 * h->n_obs, sizeof(float) * cnt * h->n_obs, cudaMemcpyDeviceToHost, st2));
+            AVG_CHECK(h, cudaMemcpyAsync(dst_rew + b0, h->d_rew + b0, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st2));
+            AVG_CHECK(h, cudaMemcpyAsync(dst_info + 2 * (size_t)b0, h->d_info + 2 * (size_t)b0, sizeof(float) * cnt * 2, cudaMemcpyDeviceToHost, st2));
+            if (dst_done) AVG_CHECK(h, cudaMemcpyAsync(dst_done + b0, h->d_done + b0, cnt, cudaMemcpyDeviceToHost, st2));
+        }
+        n_chunks = 0;                                  /* done: skip the chunk loop below */
+    }
+    const int per = n_chunks > 0 ? ((h->n_env + n_chunks - 1) / n_chunks + 3) & ~3 : 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int b0 = c * per, b1 = (c + 1) * per < h->n_env ? (c + 1) * per : h->n_env;
         if (b0 >= b1) break;

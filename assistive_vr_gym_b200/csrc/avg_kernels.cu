@@ -3932,6 +3932,7 @@ cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t 
     if (n_range <= 0) return cudaSuccess;
     auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
     mark(-1);
+    if (a.phase != 2) {                              // phase 2: the epilogue alone (avg_step_host overlaps result copies with it, range by range)
     avg_prologue_kernel<<<grid(kWpbPro), 32 * kWpbPro, 0, stream>>>(a);
     mark(0);
     for (int f = 0; f < substeps; ++f)
@@ -3939,6 +3940,8 @@ cudaError_t avg_launch_step(const AvgStepArgs& a_in, int substeps, cudaStream_t 
             a.post = (i == n_internal - 1) ? 1 : 0;
             launch_internal_step(a, stream, mark);
         }
+    }
+    if (a.phase == 1) { if (launched) *launched = nlaunch; return cudaGetLastError(); }     // phase 1: everything but the epilogue
     if (a.task == AVG_TASK_BED_BATHING) avg_epilogue_bb_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sizeof(SmEpiBB) * kWpbEpi, stream>>>(a);
     else if (a.task == AVG_TASK_FEEDING || a.task == AVG_TASK_DRINKING) avg_epilogue_fd_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);
     else avg_epilogue_kernel<<<grid(kWpbEpi), 32 * kWpbEpi, sm_epi, stream>>>(a);

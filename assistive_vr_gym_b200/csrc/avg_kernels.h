@@ -91,6 +91,7 @@ struct AvgStepArgs {
     const uint8_t* mask;                               // reset / settle paths: environments to touch (null = all)
     float* part;                                       // [n_env][AVG_P_STRIDE] particle records (Feeding / Drinking), else null
     float* pscratch;                                   // [n_env][AVG_PS_STRIDE] particle scratch arena, else null
+    int phase;                                         // avg_launch_step: 0 the whole env-step, 1 without the epilogue, 2 the epilogue only (of [env_begin, env_end))
     int post;                                          // this internal step ends a p.stepSimulation call: run the per-frame hooks (env.py:343-349)
     int n_internal;                                    // internal steps per stepSimulation (numSubSteps, feeding.py:289)
     unsigned long long* dbg_counters;                  // AVG_DBG & 32: [8] narrowphase counters (items, plane-test rejects, GJK calls, GJK iterations, SAT calls)

@@ -91,6 +91,30 @@ def test_step_host_equals_device_step(torch_cuda, env_id, n):
     e1.close(); e2.close()
 
 
+def test_step_host_one_chunk_with_overlapped_result_copies(torch_cuda, monkeypatch):
+    """Large batches step as ONE sequence and run the epilogue range by range, each range's device->host copies on the second
+    stream (avg_step_host, from 262144 envs; forced here at a small batch through AVG_CHUNKS / AVG_TAIL_RANGES): bit for bit the
+    device-resident step, over pinned and over pageable caller buffers."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    n = 5003
+    monkeypatch.setenv("AVG_CHUNKS", "1"); monkeypatch.setenv("AVG_TAIL_RANGES", "4")
+    e1 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e1.reset()
+    e2 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e2.reset()
+    a = np.random.RandomState(0).uniform(-1, 1, (4, n, 7)).astype(np.float32)
+    pin = e2.pinned_actions()
+    for t in range(4):
+        o1, r1, d1, i1 = e1.step(torch.as_tensor(a[t], device="cuda"))
+        if t % 2 == 0:
+            o2, r2, d2, i2 = e2.step_host(a[t])                  # pageable actions: staged
+        else:
+            pin[...] = a[t]; o2, r2, d2, i2 = e2.step_host(pin)  # page-locked actions: in place
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(i1["total_force_on_human"].cpu().numpy(), i2["total_force_on_human"])
+        assert np.array_equal(i1["task_success"].cpu().numpy(), i2["task_success"])
+    e1.close(); e2.close()
+
+
 def test_reference_shaped_single_env(torch_cuda):
     """examples/random_actions.py shape: make -> reset -> step(action_space.sample()) with the reference's types."""
     from assistive_vr_gym_b200 import make
