@@ -357,3 +357,18 @@ def test_fused_dynamics_solve_kernel_is_bit_identical(torch_cuda, env_id, n):
         assert out.returncode == 0, out.stderr[-2000:]
         sha.append(re.search(r"state sha1 ([0-9a-f]{40})", out.stdout).group(1))
     assert sha[0] == sha[1]
+
+
+@pytest.mark.parametrize("n,expect", [(1000, 17), (3000, 34), (8192, 44), (140000, 22)])
+def test_launches_per_env_step(torch_cuda, n, expect):
+    """What one env-step launches (ScratchItchJaco-v0): 22 kernels as one sequence from 131072 environments; two stream halves of 22
+    below that; launches of <= 2048 environments fuse dynamics + solve (17 per sequence)."""
+    torch = torch_cuda
+    from assistive_vr_gym_b200 import make
+    env = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=2); env.reset()
+    a = torch.zeros((n, 7), device="cuda")
+    env.step(a)
+    c0 = env.sim.launch_count
+    env.step(a)
+    assert env.sim.launch_count - c0 == expect
+    env.close()
