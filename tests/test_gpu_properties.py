@@ -91,17 +91,17 @@ def test_step_host_equals_device_step(torch_cuda, env_id, n):
     e1.close(); e2.close()
 
 
-def test_step_host_one_chunk_with_overlapped_result_copies(torch_cuda, monkeypatch):
+@pytest.mark.parametrize("env_id,n", [("ScratchItchJaco-v0", 5003), ("BedBathingPR2-v0", 1026), ("FeedingJaco-v0", 70)])
+def test_step_host_one_chunk_with_overlapped_result_copies(torch_cuda, monkeypatch, env_id, n):
     """Large batches step as ONE sequence and run the epilogue range by range, each range's device->host copies on the second
     stream (avg_step_host, from 262144 envs; forced here at a small batch through AVG_CHUNKS / AVG_TAIL_RANGES): bit for bit the
     device-resident step, over pinned and over pageable caller buffers."""
     torch = torch_cuda
     from assistive_vr_gym_b200 import make
-    n = 5003
     monkeypatch.setenv("AVG_CHUNKS", "1"); monkeypatch.setenv("AVG_TAIL_RANGES", "4")
-    e1 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e1.reset()
-    e2 = make("ScratchItchJaco-v0", num_envs=n, device=0, seed=4); e2.reset()
-    a = np.random.RandomState(0).uniform(-1, 1, (4, n, 7)).astype(np.float32)
+    e1 = make(env_id, num_envs=n, device=0, seed=4); e1.reset()
+    e2 = make(env_id, num_envs=n, device=0, seed=4); e2.reset()
+    a = np.random.RandomState(0).uniform(-1, 1, (4, n, e1.sim.n_actions)).astype(np.float32)
     pin = e2.pinned_actions()
     for t in range(4):
         o1, r1, d1, i1 = e1.step(torch.as_tensor(a[t], device="cuda"))
