@@ -1128,10 +1128,28 @@ __device__ __forceinline__ void collide_body(const AvgStepArgs& a, SmCollide& s,
                                    np_capacity, a.dbg);
     if (lane == 0) { scr_i[AVG_S_NQ] = nc; scr_i[AVG_S_NSEP] = nsep_out; scr_i[AVG_S_NCAND] += ncand; if (overflow) scr_i[AVG_S_OVERFLOW] |= overflow; }
 }
+// OCC = blocks per SM the instance is compiled for: AVG_OCC_COLLIDE (5 blocks of 4 warps, 90 registers, nothing spilled) for handles
+// below AVG_COLLIDE_LARGE environments, where the step waits for this kernel's slowest warps; AVG_OCC_COLLIDE_LARGE (7 blocks, 72
+// registers, a few spills) above, where 28 instead of 20 resident warps per SM hide more of its load latency.  Measured on a B200,
+// 7 against 5 blocks: 393216 envs (staggered episodes) 43.35 -> 42.51 ms per step, policy rollout at 196608 envs +1.3 %,
+// ScratchItchPR2 at 131072 envs +1.6 %; 32768 envs -1.4 %, 4096 envs -3.7 % (6 blocks: +0.5 % / 8 blocks: +1.3 % at 393216).
+#ifndef AVG_OCC_COLLIDE_LARGE
+#define AVG_OCC_COLLIDE_LARGE (28 / AVG_WPB_COLLIDE)
+#endif
+#ifndef AVG_COLLIDE_LARGE
+#define AVG_COLLIDE_LARGE 131072     /* environments of the HANDLE (not of the launch): the batches avg_step runs as one sequence; choosing by the
+                                        handle keeps every partition of a batch (stream halves, host chunks, masked resets) on the same instance --
+                                        ptxas contracts mul + add differently at the two register budgets, so the instances differ by ulps */
+#endif
 __global__ void __launch_bounds__(32 * AVG_WPB_COLLIDE, AVG_OCC_COLLIDE)
 avg_collide_kernel(AvgStepArgs a) {
     AVG_KERNEL_PREAMBLE(SmCollide)
     collide_body<148 * AVG_OCC_COLLIDE * AVG_WPB_COLLIDE * AVG_PF_PCT / 100>(a, s, e, lane, m, grec, scr, a.np_queue, a.np_count, a.np_capacity);
+}
+__global__ void __launch_bounds__(32 * AVG_WPB_COLLIDE, AVG_OCC_COLLIDE_LARGE)
+avg_collide_large_kernel(AvgStepArgs a) {
+    AVG_KERNEL_PREAMBLE(SmCollide)
+    collide_body<148 * AVG_OCC_COLLIDE_LARGE * AVG_WPB_COLLIDE * AVG_PF_PCT / 100>(a, s, e, lane, m, grec, scr, a.np_queue, a.np_count, a.np_capacity);
 }
 
 // =================================================================================================================
@@ -3825,6 +3843,7 @@ cudaError_t configure_kernels() {
     const size_t sm_sol = sizeof(SmSolve) * kWpbSolve, sm_epi = sizeof(SmEpi) * kWpbEpi;
     const size_t sm_sol1 = sizeof(SmSolve) + sizeof(SmPartSmall), sm_sol2 = sizeof(SmSolve) + sizeof(SmPartLarge);
     if ((e1 = set_smem(avg_collide_kernel, sm_col)) != cudaSuccess) return e1;
+    if ((e1 = set_smem(avg_collide_large_kernel, sm_col)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_pcollide_kernel, sizeof(SmPCol) * kWpbPCol)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<8>, sm_dyn)) != cudaSuccess) return e1;
     if ((e1 = set_smem(avg_dynamics_kernel<10>, sm_dyn)) != cudaSuccess) return e1;
@@ -3863,7 +3882,8 @@ void launch_internal_step(const AvgStepArgs& a, cudaStream_t stream, MARK&& mark
     auto grid = [&](int wpb) { return (n_range + wpb - 1) / wpb; };
     const int np_grid = 148 * 16;                                       // grid-stride over the queue; a short queue is spread over all of these warps (ipw)
     const bool part = a.part != nullptr;
-    avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+    if (a.n_env >= AVG_COLLIDE_LARGE) avg_collide_large_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
+    else avg_collide_kernel<<<grid(kWpbCollide), 32 * kWpbCollide, sm_col, stream>>>(a);
     mark(1);
     if (part) { avg_pcollide_kernel<<<grid(kWpbPCol), 32 * kWpbPCol, sizeof(SmPCol) * kWpbPCol, stream>>>(a); mark(6); }
     if (n_range > 16384) avg_narrow_kernel<AVG_OCC_NARROW><<<np_grid, 128, 0, stream>>>(a);

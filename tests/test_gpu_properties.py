@@ -74,10 +74,11 @@ def test_state_invariants_at_scale(torch_cuda):
     assert np.percentile(np.linalg.norm(obs[:, 0:3], axis=1), 99) < 1.2
 
 
-@pytest.mark.parametrize("env_id,n", [("ScratchItchJaco-v0", 257), ("BedBathingPR2-v0", 130), ("ScratchItchPR2Human-v0", 66), ("ScratchItchJaco-v0", 40000)])
+@pytest.mark.parametrize("env_id,n", [("ScratchItchJaco-v0", 257), ("BedBathingPR2-v0", 130), ("ScratchItchPR2Human-v0", 66), ("ScratchItchJaco-v0", 40000), ("ScratchItchJaco-v0", 140000)])
 def test_step_host_equals_device_step(torch_cuda, env_id, n):
-    """The host-buffer entry point (pinned staging, two chunks on two streams from 16384 envs up) returns bit for bit what the
-    device-resident step returns (itself two half batches on two streams from 32768 envs up)."""
+    """The host-buffer entry point (pinned staging, two chunks on two streams for 16384 .. 262143 envs) returns bit for bit what the
+    device-resident step returns (itself two half batches on two streams for 2048 .. 131071 envs, one sequence above: at 140000 envs
+    the two partition the batch differently, and both use the handle's large-batch collide instance)."""
     torch = torch_cuda
     from assistive_vr_gym_b200 import make
     e1 = make(env_id, num_envs=n, device=0, seed=4); e1.reset()
